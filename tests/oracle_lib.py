@@ -1,0 +1,252 @@
+"""ctypes binding of the CPU oracle (oracle/mtf_oracle.h).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "libmtf_oracle.so")
+
+AM = {"ssd": 0, "ncc": 1, "mi": 2}
+SSM = {"homography": 0, "affine": 1}
+SM = {"esm": 0, "fclk": 1, "iclk": 2}
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("am", C.c_int), ("ssm", C.c_int), ("sm", C.c_int),
+                ("resx", C.c_int), ("resy", C.c_int), ("max_iters", C.c_int),
+                ("epsilon", C.c_double), ("hess_type", C.c_int), ("jac_type", C.c_int),
+                ("chained_warp", C.c_int), ("leven_marq", C.c_int),
+                ("lm_delta_init", C.c_double), ("lm_delta_update", C.c_double),
+                ("nt_semantics", C.c_int), ("grad_eps", C.c_double),
+                ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
+                ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
+                ("likelihood_alpha", C.c_double)]
+
+
+class OrcIterLog(C.Structure):
+    _fields_ = [("f", C.c_double), ("jacobian", C.c_double * 8), ("hessian", C.c_double * 64),
+                ("state_update", C.c_double * 8), ("corners", C.c_double * 8),
+                ("update_norm", C.c_double), ("rejected", C.c_int)]
+
+
+def build():
+    """(Re)build the oracle shared library if its sources are newer than the binary."""
+    src = [os.path.join(_ORACLE_DIR, f) for f in ("mtf_oracle.cpp", "mtf_oracle.h", "Makefile")]
+    if os.path.exists(_LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(_LIB_PATH) for s in src):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _ORACLE_DIR], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        build()
+    L = C.CDLL(_LIB_PATH)
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.orc_default_params.argtypes = [C.POINTER(OrcParams)]
+    L.orc_create.argtypes = [C.POINTER(OrcParams)]; L.orc_create.restype = C.c_void_p
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_image.argtypes = [C.c_void_p, fp, C.c_int, C.c_int]
+    L.orc_initialize.argtypes = [C.c_void_p, dp]; L.orc_initialize.restype = C.c_int
+    L.orc_update.argtypes = [C.c_void_p]; L.orc_update.restype = C.c_int
+    L.orc_set_region.argtypes = [C.c_void_p, dp]; L.orc_set_region.restype = C.c_int
+    L.orc_n_iters.argtypes = [C.c_void_p]; L.orc_n_iters.restype = C.c_int
+    L.orc_n_log.argtypes = [C.c_void_p]; L.orc_n_log.restype = C.c_int
+    L.orc_log.argtypes = [C.c_void_p, C.c_int]; L.orc_log.restype = C.POINTER(OrcIterLog)
+    L.orc_state_size.argtypes = [C.c_void_p]; L.orc_state_size.restype = C.c_int
+    L.orc_get_similarity.argtypes = [C.c_void_p]; L.orc_get_similarity.restype = C.c_double
+    for name in ("orc_get_corners", "orc_get_state", "orc_get_pts", "orc_get_init_pts", "orc_get_init_pix_vals",
+                 "orc_get_curr_pix_vals", "orc_get_curr_pix_grad", "orc_get_curr_pix_jacobian",
+                 "orc_get_init_pix_jacobian", "orc_get_init_warp", "orc_get_stage_times"):
+        getattr(L, name).argtypes = [C.c_void_p, dp]
+    L.orc_pf_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp]
+    L.orc_pix_val.argtypes = [fp, C.c_int, C.c_int, C.c_double, C.c_double]; L.orc_pix_val.restype = C.c_double
+    L.orc_get_pix_vals.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
+    L.orc_get_img_grad.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
+    L.orc_homography_dlt.argtypes = [dp, dp, dp]
+    L.orc_colpiv_qr_solve.argtypes = [dp, dp, C.c_int, dp]
+    L.orc_norm_unit_square_pts.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
+    L.orc_batch_track.argtypes = [C.POINTER(OrcParams), C.POINTER(fp), C.c_int, C.c_int, C.c_int, dp, C.c_int,
+                                  C.c_int, dp, ip, dp]
+    L.orc_batch_track.restype = C.c_long
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def make_params(am="ssd", ssm="homography", sm="fclk", **kw):
+    p = OrcParams()
+    lib().orc_default_params(C.byref(p))
+    p.am, p.ssm, p.sm = AM[am], SSM[ssm], SM[sm]
+    if sm == "esm" and "hess_type" not in kw:
+        p.hess_type = 2  # SumOfSelf (ESMParams.cc:7)
+    if sm == "iclk" and "hess_type" not in kw:
+        p.hess_type = 0  # InitialSelf (ICLKParams.cc:6)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+class OracleTracker:
+    """One reference-style tracker (SM + AM + SSM) evaluated by the CPU oracle."""
+
+    def __init__(self, params):
+        self.p = params
+        self.h = lib().orc_create(C.byref(params))
+        self.S = lib().orc_state_size(self.h)
+        self.N = params.resx * params.resy
+        self._img = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def set_image(self, img):
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        self._img = img  # the oracle keeps the pointer, like ImageBase::setCurrImg
+        lib().orc_set_image(self.h, _fp(img), img.shape[0], img.shape[1])
+
+    def initialize(self, corners):
+        c = np.ascontiguousarray(corners, dtype=np.float64).reshape(8)
+        return lib().orc_initialize(self.h, _dp(c))
+
+    def set_region(self, corners):
+        c = np.ascontiguousarray(corners, dtype=np.float64).reshape(8)
+        return lib().orc_set_region(self.h, _dp(c))
+
+    def update(self):
+        return lib().orc_update(self.h)
+
+    def _get(self, name, n):
+        out = np.empty(n, dtype=np.float64)
+        getattr(lib(), name)(self.h, _dp(out))
+        return out
+
+    @property
+    def n_iters(self):
+        return lib().orc_n_iters(self.h)
+
+    @property
+    def similarity(self):
+        return lib().orc_get_similarity(self.h)
+
+    def corners(self):
+        return self._get("orc_get_corners", 8).reshape(2, 4)
+
+    def state(self):
+        return self._get("orc_get_state", self.S)
+
+    def pts(self):
+        return self._get("orc_get_pts", 2 * self.N).reshape(self.N, 2)
+
+    def init_pts(self):
+        return self._get("orc_get_init_pts", 2 * self.N).reshape(self.N, 2)
+
+    def init_pix_vals(self):
+        return self._get("orc_get_init_pix_vals", self.N)
+
+    def curr_pix_vals(self):
+        return self._get("orc_get_curr_pix_vals", self.N)
+
+    def curr_pix_grad(self):
+        return self._get("orc_get_curr_pix_grad", 2 * self.N).reshape(2, self.N).T
+
+    def curr_pix_jacobian(self):
+        return self._get("orc_get_curr_pix_jacobian", self.N * self.S).reshape(self.S, self.N).T
+
+    def init_pix_jacobian(self):
+        return self._get("orc_get_init_pix_jacobian", self.N * self.S).reshape(self.S, self.N).T
+
+    def init_warp(self):
+        return self._get("orc_get_init_warp", 9).reshape(3, 3)
+
+    def stage_times(self):
+        return self._get("orc_get_stage_times", 9)
+
+    def log(self):
+        out = []
+        S = self.S
+        for i in range(lib().orc_n_log(self.h)):
+            e = lib().orc_log(self.h, i).contents
+            out.append(dict(f=e.f, jacobian=np.array(e.jacobian[:S]),
+                            hessian=np.array(e.hessian[:S * S]).reshape(S, S).T,
+                            state_update=np.array(e.state_update[:S]),
+                            corners=np.array(e.corners[:]).reshape(2, 4),
+                            update_norm=e.update_norm, rejected=bool(e.rejected)))
+        return out
+
+    def pf_evaluate(self, states):
+        states = np.ascontiguousarray(states, dtype=np.float64)
+        n = states.shape[0]
+        lik = np.empty(n); sim = np.empty(n)
+        lib().orc_pf_evaluate(self.h, _dp(states), n, _dp(lik), _dp(sim))
+        return lik, sim
+
+
+def pix_vals(img, pts, norm_mult=1.0, norm_add=0.0):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.empty(pts.shape[0])
+    lib().orc_get_pix_vals(_fp(img), img.shape[0], img.shape[1], _dp(pts), pts.shape[0], norm_mult, norm_add, _dp(out))
+    return out
+
+
+def img_grad(img, pts, grad_eps=1e-8, mult=1.0):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.empty(2 * pts.shape[0])
+    lib().orc_get_img_grad(_fp(img), img.shape[0], img.shape[1], _dp(pts), pts.shape[0], grad_eps, mult, _dp(out))
+    return out.reshape(2, -1).T
+
+
+def homography_dlt(in_corners, out_corners):
+    a = np.ascontiguousarray(in_corners, dtype=np.float64).reshape(8)
+    b = np.ascontiguousarray(out_corners, dtype=np.float64).reshape(8)
+    H = np.empty(9)
+    lib().orc_homography_dlt(_dp(a), _dp(b), _dp(H))
+    return H.reshape(3, 3)
+
+
+def colpiv_qr_solve(A, b):
+    A = np.asfortranarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty(A.shape[0])
+    lib().orc_colpiv_qr_solve(A.ctypes.data_as(C.POINTER(C.c_double)), _dp(b), A.shape[0], _dp(x))
+    return x
+
+
+def norm_unit_square_pts(resx, resy, min_x=-0.5, min_y=-0.5, max_x=0.5, max_y=0.5):
+    pts = np.empty(2 * resx * resy); c = np.empty(8)
+    lib().orc_norm_unit_square_pts(resx, resy, min_x, min_y, max_x, max_y, _dp(pts), _dp(c))
+    return pts.reshape(-1, 2), c.reshape(2, 4)
+
+
+def batch_track(params, frames, corners, n_threads=0):
+    """CPU baseline driver: P independent trackers, OpenMP over patches (GridTracker.cc:253-256)."""
+    frames = [np.ascontiguousarray(f, dtype=np.float32) for f in frames]
+    h, w = frames[0].shape
+    arr = (C.POINTER(C.c_float) * len(frames))(*[_fp(f) for f in frames])
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 8)
+    P = corners.shape[0]
+    final = np.empty((P, 8)); iters = np.zeros(P, dtype=np.int32); secs = C.c_double(0)
+    total = lib().orc_batch_track(C.byref(params), arr, len(frames), h, w, _dp(corners), P, n_threads,
+                                  _dp(final), iters.ctypes.data_as(C.POINTER(C.c_int)), C.byref(secs))
+    return total, secs.value, final.reshape(P, 2, 4), iters
