@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- LK iterations/sec of the B200 hot path (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- FCLK + SSD + Homography, 1024 independent 50x50 patches
+per GPU on 1024x1024 synthetic frames (mtf_b200/synth.py), fixed 30 Gauss-Newton iterations per patch per frame
+(epsilon = 0 disables the early exit so that every step does identical work).  One STEP = one frame: the whole
+batch tracked for 30 iterations = P * 30 LK iterations.
+
+  value      whole-job LK iterations/sec, frames already resident in HBM, CUDA-event timed per step on the
+             launching stream, L2 flushed between steps, max over ranks
+  e2e        the same through the reference-facing API with HOST buffers: pinned frame -> H2D -> update ->
+             D2H of the P x 8 corners inside the timed region
+  roofline   algorithmic HBM bytes ((8N + 432) per patch-iteration) / kernel time vs the measured
+             copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU restatement of the reference, kind "port") on the box's host cores, bounded sample
+
+--impl reference times the oracle's reference-faithful loop (oracle/, all host threads) on bounded samples of
+the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = 50
+N_PIX = RES * RES
+ITERS = 30
+P_PER_GPU = 1024
+IMG = 1024
+N_FRAMES = 8
+ALG_BYTES_PER_ITER = 8 * N_PIX + 432          # I_t footprint + I_0 (fp32 each) + W in + J,H,f out
+METRIC = "LK iters/sec (50x50 SSD+Homography)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = max(smax, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples above the idle clock
+        load = [x for x in sm if x > 0.5 * smax] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(seed_offset=0):
+    from mtf_b200 import synth
+    frames, _ = synth.make_sequence(N_FRAMES, IMG, IMG, seed=1234, walk_seed=5678, sigma=1.0)
+    corners = synth.make_patches(P_PER_GPU, 49.0, IMG, IMG, seed=42 + seed_offset)
+    # ping-pong order keeps consecutive frames one random-walk step apart for any number of steps
+    order = list(range(1, N_FRAMES)) + list(range(N_FRAMES - 2, -1, -1))
+    return frames, corners, order
+
+
+def oracle_params():
+    from oracle import oracle_lib as O
+    return O.make_params("ssd", "homography", "fclk", max_iters=ITERS, epsilon=0.0, grad_mode=0)
+
+
+def cpu_sample(frames, corners, n_patches, n_frames, threads):
+    """oracle batch driver (OpenMP over patches, GridTracker.cc:253-256) -> (iterations, seconds)"""
+    from oracle import oracle_lib as O
+    total, secs, _, _ = O.batch_track(oracle_params(), frames[:n_frames + 1], corners[:n_patches], n_threads=threads)
+    return total, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames, corners, _ = workload()
+    # bounded sample: 2 patches per core x 1 frame x 30 iterations per step
+    n_patches = min(P_PER_GPU, 2 * cores)
+    for _ in range(args.warmup):
+        cpu_sample(frames, corners, n_patches, 1, cores)
+    iters = secs = 0.0
+    for _ in range(args.steps):
+        a, b = cpu_sample(frames, corners, n_patches, 1, cores)
+        iters += a; secs += b
+    v = iters / secs
+    sample = "%d patches x 1 frame x %d iterations per step, %d steps" % (n_patches, ITERS, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "FCLK+SSD+Homography 50x50, %d iters/frame, CPU oracle (restatement of MTF, not MTF)" % ITERS,
+                   "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import torch
+    from mtf_b200 import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    frames, corners, order = workload(seed_offset=rank)
+    P = P_PER_GPU
+    prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=local_rank,
+                          threads_per_patch=args.threads)
+    tr = api.BatchTracker(prm)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    tr.set_stream(stream.cuda_stream)
+    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    gathered = torch.empty((world, P, 8), dtype=torch.float64, device=dev) if world > 1 else None
+    d_corners_ptr, _, _ = tr.device_results()
+
+    class _Raw:       # zero-copy torch view of the library's P x 8 result array
+        __cuda_array_interface__ = {"shape": (P, 8), "typestr": "<f8", "data": (d_corners_ptr, False), "version": 2}
+    d_corners = torch.as_tensor(_Raw(), device=dev)
+
+    tr.initialize(corners, d_frames[0])
+    tr.synchronize()
+
+    def step_device(i):
+        tr.setImage(d_frames[order[i % len(order)]])
+        tr.update()
+        if world > 1:
+            # north_star: one all-gather of the per-patch results over NVLink (per frame: LK iterations of
+            # different patches never interact)
+            dist.all_gather_into_tensor(gathered.view(-1), d_corners.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ device-resident timing
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = tr.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                                           # evict L2 between timed steps
+        ev[i][0].record(stream)
+        tr.setImage(d_frames[order[(args.warmup + i) % len(order)]])
+        kev[i][0].record(stream)
+        tr.update()
+        kev[i][1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), d_corners.view(-1))
+        ev[i][1].record(stream)
+    barrier()
+    launches = tr.launch_count - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    kms = sum(a.elapsed_time(b) for a, b in kev)
+    clocks = sampler.stop()
+    status = tr.patch_status()
+    finite = bool(np.isfinite(tr.getRegion()).all())
+
+    # ------------------------------------------------------------------ end to end (host buffers)
+    tr.initialize(corners, frames[0])
+    host_out = torch.empty((P, 8), dtype=torch.float64).pin_memory()
+    for i in range(args.warmup):
+        tr.set_image_pinned(pinned[order[i % len(order)]].data_ptr(), IMG, IMG, IMG)
+        tr.update()
+        host_out.copy_(d_corners, non_blocking=True)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.perf_counter()
+    t0.record(stream)
+    for i in range(args.steps):
+        tr.set_image_pinned(pinned[order[(args.warmup + i) % len(order)]].data_ptr(), IMG, IMG, IMG)   # H2D, 4 MB
+        tr.update()
+        host_out.copy_(d_corners, non_blocking=True)                                                   # D2H, 64 KB
+        stream.synchronize()                                                                          # the caller reads the corners
+    t1.record(stream)
+    barrier()
+    e2e_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0))
+
+    if world > 1:
+        t = torch.tensor([ms, kms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, kms, e2e_ms = [float(x) for x in t.tolist()]
+    total_iters = world * P * ITERS * args.steps
+    value = total_iters / (ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = ALG_BYTES_PER_ITER * P * ITERS * args.steps / (kms * 1e-3) / 1e9        # per GPU
+    out = {
+        "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
+                               % (P, ITERS, IMG, IMG),
+                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": tr.params.threads_per_patch or 128,
+                   "collective": "all_gather of P x 8 corners per frame" if world > 1 else "none"},
+        "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s",
+                "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "lk_update_kernel<SSD,Homography,FCLK>", "kernel_ms_per_launch": kms / args.steps,
+                     "alg_bytes_per_launch": ALG_BYTES_PER_ITER * P * ITERS, "peak_source": peak_src,
+                     "note": "fp64-issue bound, not HBM bound: see DESIGN.md"},
+        "clocks": clocks,
+        "valid": {"finite": finite, "patches_nan": int((status & 1 != 0).sum()), "patches_rank_deficient_H": int((status & 2 != 0).sum())},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_patches = min(P, 4 * cores)
+            it, secs = cpu_sample(frames, corners, n_patches, 1, cores)
+            if secs < 5.0:                      # aim for ~10 s of wall clock
+                reps = int(min(8, max(1, 10.0 / max(secs, 1e-3))))
+                it, secs = cpu_sample(frames, corners, n_patches, min(reps, N_FRAMES - 1), cores)
+            out["cpu_baseline"] = {"value": it / secs, "unit": "iters/s", "cores": cores, "kind": "port",
+                                   "sample": "%d patches, %d LK iterations, OpenMP over patches" % (n_patches, it)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--threads", type=int, default=0, help="threads per patch (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+/*
+ * mtf_b200.h -- C ABI of the B200-native Lucas-Kanade hot path (libmtf_b200.so).
+ *
+ * Drop-in boundary for abhineet123/MTF's per-iteration LK path.  The reference has no FFI for this
+ * path (its plug-in surface is three C++ abstract classes, include/mtf/TrackerBase.h:9-70,
+ * AM/include/mtf/AM/AppearanceModel.h:63-396, SSM/include/mtf/SSM/StateSpaceModel.h:49-408), so the
+ * entry points below are what a `TrackerBase` subclass added to mtf::getTracker
+ * (include/mtf/mtf.h:929) binds -- see include/mtf_b200_tracker.h for that subclass and
+ * INTEGRATION.md for the factory branch.  Each function names the reference member it replaces.
+ *
+ * Plain C, POD only: no Eigen / OpenCV / torch types.  Every function returns an mtfb_status;
+ * mtfb_last_error() gives the message for the calling thread.  A context is single-threaded and
+ * non-re-entrant like a reference tracker instance; distinct contexts may be used concurrently.
+ *
+ * One context = one BATCH of P independent patch trackers (the GridTracker.cc:247-264 /
+ * PF.cc:198-289 fan-out) sharing one image, one (SM, AM, SSM) combination and one parameter set.
+ *
+ * Layouts (all row-major C arrays, fp64 unless stated):
+ *   corners   P x 2 x 4   x_UL,x_UR,x_LR,x_LL,y_UL,y_UR,y_LR,y_LL per patch -- the 2x4 CV_64FC1
+ *                          cv::Mat of TrackerBase::initialize (SM/include/mtf/SM/SearchMethod.h:19)
+ *   state     P x S        S = 8 (Homography.cc:94-107 order) or 6 (Affine.cc:117-131 order)
+ *   pts       P x N x 2    x0,y0,x1,y1,... = Eigen column-major PtsT (2 x N)
+ *   pix_vals  P x N
+ *   pix_grad  P x 2 x N    all Ix then all Iy = column-major PixGradT (N x 2)
+ *   pix_jac   P x S x N    S contiguous N-columns = column-major MatrixXd (N x S)
+ *   hessian   S x S        column-major
+ */
+#ifndef MTF_B200_H
+#define MTF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mtfb_status {
+	MTFB_OK = 0,
+	MTFB_ERR_INVALID_ARG = 1,     /* mtf::utils::InvalidArgument      excpUtils.h:38-45 */
+	MTFB_ERR_NOT_SUPPORTED = 2,   /* mtf::utils::FunctonNotImplemented excpUtils.h:29-36 */
+	MTFB_ERR_LOGIC = 3,           /* mtf::utils::LogicError           excpUtils.h:47-54 (call order) */
+	MTFB_ERR_INVALID_STATE = 4,   /* mtf::utils::InvalidTrackerState  excpUtils.h:20-27 (NaN / singular H in >= 1 patch) */
+	MTFB_ERR_CUDA = 5,            /* CUDA runtime error, no device, wrong architecture */
+	MTFB_ERR_NO_MEMORY = 6
+} mtfb_status;
+
+/* AM/AM.cmake:5 names; SSM/SSM.cmake:1 names; SM/SM.cmake names */
+enum { MTFB_AM_SSD = 0, MTFB_AM_NCC = 1, MTFB_AM_MI = 2 };
+enum { MTFB_SSM_HOMOGRAPHY = 0, MTFB_SSM_AFFINE = 1 };
+enum { MTFB_SM_ESM = 0, MTFB_SM_FCLK = 1, MTFB_SM_ICLK = 2, MTFB_SM_PF = 3 };
+/* ESMParams::HessType / JacType (SM/include/mtf/SM/ESMParams.h:13-17) */
+enum { MTFB_ESM_HESS_INITIAL_SELF = 0, MTFB_ESM_HESS_CURRENT_SELF = 1, MTFB_ESM_HESS_SUM_OF_SELF = 2,
+       MTFB_ESM_HESS_ORIGINAL = 3, MTFB_ESM_HESS_SUM_OF_STD = 4, MTFB_ESM_HESS_STD = 5 };
+enum { MTFB_ESM_JAC_ORIGINAL = 0, MTFB_ESM_JAC_DIFF_OF_JACS = 1 };
+/* FCLKParams::HessType / ICLKParams::HessType (FCLKParams.h:8, ICLKParams.h:9) */
+enum { MTFB_LK_HESS_INITIAL_SELF = 0, MTFB_LK_HESS_CURRENT_SELF = 1, MTFB_LK_HESS_STD = 2 };
+/* per-patch status bits reported by mtfb_get_patch_status */
+enum { MTFB_PATCH_OK = 0, MTFB_PATCH_NAN = 1, MTFB_PATCH_SINGULAR = 2, MTFB_PATCH_OUT_OF_IMAGE = 4 };
+
+/*
+ * Parameters = the fields of {ESM,FCLK,ICLK,PF}Params + the AM/SSM parameters the path reads
+ * (SM/src/{ESM,FCLK,ICLK}Params.cc:4-17, AM/include/mtf/AM/MI.h MIParams, AM/include/mtf/AM/ImageBase.h:7-9,
+ * SSM/include/mtf/SSM/Homography.h HomographyParams).  mtfb_default_params() fills the shipped
+ * configuration (Config/mtf.cfg:14,24 + Config/modules.cfg).
+ */
+typedef struct mtfb_params {
+	int am, ssm, sm;
+	int resx, resy;              /* sampling resolution: N = resx * resy                          */
+	int n_patches;               /* P: independent trackers in the batch                          */
+	int max_iters;
+	double epsilon;              /* stop when || prev_corners - curr_corners ||^2 < epsilon       */
+	int hess_type, jac_type;
+	int chained_warp;            /* {esm,fc,ic}_chained_warp; only 1 is implemented               */
+	int leven_marq;
+	double lm_delta_init, lm_delta_update;
+	int nt_semantics;            /* 1: nt::SM control flow (SM/src/NT), 0: templated twins (SM/src) */
+	double grad_eps;             /* ImageBase.h:7-9; used for the out-of-image edge emulation only:
+	                                the product computes the eps -> 0 limit of the reference's finite
+	                                difference analytically (DESIGN.md "gradient semantics")      */
+	int hom_normalized_init;     /* only 0 (factory default, parameters.h:261) is implemented     */
+	int mi_n_bins;               /* MIParams n_bins (parameters.h:344)                            */
+	double mi_pre_seed;
+	int mi_pou;
+	double likelihood_alpha;     /* AMParams::likelihood_alpha, PF path                           */
+	int device;                  /* CUDA device ordinal                                           */
+	int threads_per_patch;       /* 0 = library default; otherwise 64, 128 or 256                 */
+} mtfb_params;
+
+/* one Gauss-Newton pass as the reference's record_event() trail would show it (NT/FCLK.cc:190-321);
+ * written by mtfb_update() when an iteration log is attached */
+typedef struct mtfb_iter_log {
+	double f;                    /* am->getSimilarity() after updateSimilarity                    */
+	double jacobian[8];          /* df_dp                                                         */
+	double hessian[64];          /* d2f_dp2, column-major S x S in the first S*S entries          */
+	double state_update[8];      /* ssm_update                                                    */
+	double corners[8];           /* ssm->getCorners() after the update                            */
+	double update_norm;          /* || prev_corners - curr_corners ||^2                           */
+	int rejected;                /* Levenberg-Marquardt rejected the previous step in this pass   */
+	int valid;                   /* 1 if this pass was executed                                   */
+} mtfb_iter_log;
+
+typedef struct mtfb_ctx mtfb_ctx;
+
+const char *mtfb_last_error(void);
+const char *mtfb_version(void);
+/* number of kernels this library has launched on the calling context so far (bench.py gpu_launches) */
+long mtfb_launch_count(const mtfb_ctx *ctx);
+
+void mtfb_default_params(mtfb_params *p);
+/* replaces: new nt::FCLK(AM(getAM(..)), SSM(getSSM(..)), params)  include/mtf/mtf.h:1282-1300 */
+mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out);
+mtfb_status mtfb_destroy(mtfb_ctx *ctx);
+/* run all work of this context on a caller-owned cudaStream_t, taken literally (NULL = CUDA's legacy default
+ * stream).  A new context runs on a private non-blocking stream of its own. */
+mtfb_status mtfb_set_stream(mtfb_ctx *ctx, void *cuda_stream);
+mtfb_status mtfb_synchronize(mtfb_ctx *ctx);
+
+/* replaces TrackerBase::setImage -> ImageBase::setCurrImg (AM/src/ImageBase.cc:38-60).  The reference keeps
+ * a pointer to a buffer the application overwrites in place every frame (TrackerBase.h:21-26), so this
+ * must be called before every initialize()/update(): it uploads the h x w float frame (row_stride in
+ * elements) to the device asynchronously on the context stream. */
+mtfb_status mtfb_set_image(mtfb_ctx *ctx, const float *host_img, int h, int w, int row_stride);
+/* same, frame already resident on the device (pitch in elements); the pointer is used, not copied */
+mtfb_status mtfb_set_image_device(mtfb_ctx *ctx, const float *dev_img, int h, int w, int pitch);
+
+/* replaces SearchMethod::initialize(corners) (SM/src/NT/FCLK.cc:102-169, NT/ESM.cc:110-146,
+ * NT/ICLK.cc:71-127): ssm.setCorners (4-point DLT, Utilities/src/warpUtils.cc:171-223) + am.initializePixVals
+ * + the SM-specific template gradients / Jacobians / Hessians, for all P patches, on the device. */
+mtfb_status mtfb_initialize(mtfb_ctx *ctx, const double *corners /* P x 8, host */);
+/* replaces SearchMethod::setRegion (NT/FCLK.cc:360-376, NT/ESM.cc:148-167) */
+mtfb_status mtfb_set_region(mtfb_ctx *ctx, const double *corners /* P x 8, host */);
+/* replaces SearchMethod::update() (NT/FCLK.cc:171-358, NT/ESM.cc:170-297, NT/ICLK.cc:160-299): the whole
+ * <= max_iters loop for every patch in ONE launch.  Asynchronous; results are read with the getters. */
+mtfb_status mtfb_update(mtfb_ctx *ctx);
+/* a single Gauss-Newton pass for every patch (max_iters = 1 for this call): stage parity and hosts that
+ * want to interleave their own logic between iterations.  Outputs may be NULL; host pointers. */
+mtfb_status mtfb_iterate_once(mtfb_ctx *ctx, double *jacobian /* P x S */, double *hessian /* P x S x S */,
+	double *similarity /* P */, double *state_update /* P x S */);
+/* attach (n_slots > 0) or detach (0) a device-side iteration log of n_slots passes per patch */
+mtfb_status mtfb_enable_iter_log(mtfb_ctx *ctx, int n_slots);
+mtfb_status mtfb_get_iter_log(mtfb_ctx *ctx, mtfb_iter_log *out /* P x n_slots, host */);
+
+/* replaces the PF particle loop NT/PF.cc:303-320: for object o (one initialised patch = one template) and
+ * each of its n_particles states: ssm.setState -> am.updatePixVals -> am.updateSimilarity(false) ->
+ * am.getLikelihood().  states: P x n_particles x S; outputs P x n_particles (NULL allowed). Host pointers. */
+mtfb_status mtfb_pf_evaluate(mtfb_ctx *ctx, const double *states, int n_particles,
+	double *likelihood, double *similarity);
+/* device-pointer variant (no copies): all three buffers live on ctx's device */
+mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *ctx, const double *d_states, int n_particles,
+	double *d_likelihood, double *d_similarity);
+
+/* getters = the accessors of SURVEY.md 8(a18): ssm->getCorners/getState/getPts, am->getSimilarity,
+ * am->getInitPixVals/getCurrPixVals/getCurrPixGrad ...; they synchronise the context stream.
+ * Host pointers. */
+mtfb_status mtfb_get_corners(mtfb_ctx *ctx, double *out /* P x 8 */);
+mtfb_status mtfb_get_state(mtfb_ctx *ctx, double *out /* P x S */);
+mtfb_status mtfb_get_n_iters(mtfb_ctx *ctx, int *out /* P: loop passes of the last update() */);
+mtfb_status mtfb_get_similarity(mtfb_ctx *ctx, double *out /* P */);
+mtfb_status mtfb_get_patch_status(mtfb_ctx *ctx, int *out /* P */);
+mtfb_status mtfb_get_init_warp(mtfb_ctx *ctx, double *out /* P x 9, DLT warp row-major */);
+mtfb_status mtfb_get_init_pts(mtfb_ctx *ctx, double *out /* P x N x 2 */);
+mtfb_status mtfb_get_init_pix_vals(mtfb_ctx *ctx, double *out /* P x N */);
+/* debug taps: evaluate pts / It / dIt_dx / dIt_dp at the CURRENT state with the path's own device
+ * functions (one extra launch); any output may be NULL */
+mtfb_status mtfb_get_curr_stage(mtfb_ctx *ctx, double *pts /* P x N x 2 */, double *pix_vals /* P x N */,
+	double *pix_grad /* P x 2 x N */, double *pix_jac /* P x S x N */);
+/* device pointers of the result arrays, valid until destroy (corners P x 8, state P x S, n_iters P int):
+ * what a multi-GPU host all-gathers without a host round trip */
+mtfb_status mtfb_device_results(mtfb_ctx *ctx, double **d_corners, double **d_state, int **d_n_iters);
+int mtfb_state_size(const mtfb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

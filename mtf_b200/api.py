@@ -1,0 +1,314 @@
+"""ctypes binding of libmtf_b200.so (include/mtf_b200.h) and a host-side mirror of the reference's
+tracker interface (include/mtf/TrackerBase.h:9-70): setImage / initialize / update / setRegion / getRegion.
+
+The C++ shim a reference maintainer would compile into MTF is include/mtf_b200_tracker.h; this module is
+the same thing for Python callers (tests, bench.py).  There is no CPU path: if the shared library is missing
+or no B200 is visible, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtf_b200.so")
+
+AM = {"ssd": 0, "ncc": 1, "mi": 2}
+SSM = {"homography": 0, "affine": 1, "8": 0, "6": 1}
+SM = {"esm": 0, "fclk": 1, "iclk": 2, "pf": 3}
+ESM_HESS = {"initial_self": 0, "current_self": 1, "sum_of_self": 2, "original": 3, "sum_of_std": 4, "std": 5}
+ESM_JAC = {"original": 0, "diff_of_jacs": 1}
+LK_HESS = {"initial_self": 0, "current_self": 1, "std": 2}
+
+STATUS_NAMES = {1: "InvalidArgument", 2: "FunctonNotImplemented", 3: "LogicError", 4: "InvalidTrackerState",
+                5: "CudaError", 6: "OutOfMemory"}
+
+
+class MTFError(RuntimeError):
+    """Counterpart of mtf::utils::Exception (Utilities/include/mtf/Utilities/excpUtils.h:8-55)."""
+
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+        self.status = status
+        self.type = STATUS_NAMES.get(status, str(status))
+
+
+class Params(C.Structure):
+    _fields_ = [("am", C.c_int), ("ssm", C.c_int), ("sm", C.c_int),
+                ("resx", C.c_int), ("resy", C.c_int), ("n_patches", C.c_int),
+                ("max_iters", C.c_int), ("epsilon", C.c_double),
+                ("hess_type", C.c_int), ("jac_type", C.c_int),
+                ("chained_warp", C.c_int), ("leven_marq", C.c_int),
+                ("lm_delta_init", C.c_double), ("lm_delta_update", C.c_double),
+                ("nt_semantics", C.c_int), ("grad_eps", C.c_double),
+                ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
+                ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
+                ("likelihood_alpha", C.c_double), ("device", C.c_int), ("threads_per_patch", C.c_int)]
+
+
+class IterLog(C.Structure):
+    _fields_ = [("f", C.c_double), ("jacobian", C.c_double * 8), ("hessian", C.c_double * 64),
+                ("state_update", C.c_double * 8), ("corners", C.c_double * 8),
+                ("update_norm", C.c_double), ("rejected", C.c_int), ("valid", C.c_int)]
+
+
+EXPORTS = [
+    "mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_create", "mtfb_destroy",
+    "mtfb_set_stream", "mtfb_synchronize", "mtfb_set_image", "mtfb_set_image_device", "mtfb_initialize",
+    "mtfb_set_region", "mtfb_update", "mtfb_iterate_once", "mtfb_enable_iter_log", "mtfb_get_iter_log",
+    "mtfb_pf_evaluate", "mtfb_pf_evaluate_device", "mtfb_get_corners", "mtfb_get_state", "mtfb_get_n_iters",
+    "mtfb_get_similarity", "mtfb_get_patch_status", "mtfb_get_init_warp", "mtfb_get_init_pts",
+    "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_device_results", "mtfb_state_size",
+]
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the C-ABI library and declare its prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise MTFError(5, "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C mtf_b200/csrc); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    L.mtfb_last_error.restype = C.c_char_p
+    L.mtfb_version.restype = C.c_char_p
+    L.mtfb_launch_count.argtypes = [vp]; L.mtfb_launch_count.restype = C.c_long
+    L.mtfb_default_params.argtypes = [C.POINTER(Params)]; L.mtfb_default_params.restype = None
+    L.mtfb_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.mtfb_destroy.argtypes = [vp]
+    L.mtfb_set_stream.argtypes = [vp, vp]
+    L.mtfb_synchronize.argtypes = [vp]
+    L.mtfb_set_image.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.mtfb_set_image_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.mtfb_initialize.argtypes = [vp, dp]
+    L.mtfb_set_region.argtypes = [vp, dp]
+    L.mtfb_update.argtypes = [vp]
+    L.mtfb_iterate_once.argtypes = [vp, dp, dp, dp, dp]
+    L.mtfb_enable_iter_log.argtypes = [vp, C.c_int]
+    L.mtfb_get_iter_log.argtypes = [vp, C.POINTER(IterLog)]
+    L.mtfb_pf_evaluate.argtypes = [vp, dp, C.c_int, dp, dp]
+    L.mtfb_pf_evaluate_device.argtypes = [vp, vp, C.c_int, vp, vp]
+    for name in ("mtfb_get_corners", "mtfb_get_state", "mtfb_get_similarity", "mtfb_get_init_warp",
+                 "mtfb_get_init_pts", "mtfb_get_init_pix_vals"):
+        getattr(L, name).argtypes = [vp, dp]
+    L.mtfb_get_n_iters.argtypes = [vp, ip]
+    L.mtfb_get_patch_status.argtypes = [vp, ip]
+    L.mtfb_get_curr_stage.argtypes = [vp, dp, dp, dp, dp]
+    L.mtfb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mtfb_state_size.argtypes = [vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def default_params(**kw):
+    p = Params()
+    load_library().mtfb_default_params(C.byref(p))
+    return set_params(p, **kw)
+
+
+def set_params(p, **kw):
+    for k, v in kw.items():
+        if k == "am":
+            v = AM[v] if isinstance(v, str) else v
+        elif k == "ssm":
+            v = SSM[v] if isinstance(v, str) else v
+        elif k == "sm":
+            v = SM[v] if isinstance(v, str) else v
+        elif k == "hess_type" and isinstance(v, str):
+            v = (ESM_HESS if p.sm == SM["esm"] else LK_HESS)[v]
+        elif k == "jac_type" and isinstance(v, str):
+            v = ESM_JAC[v]
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def make_params(am="ssd", ssm="homography", sm="fclk", **kw):
+    """Parameters of one (SM, AM, SSM) combination with the per-SM default Hessian of the reference
+    (ESMParams.cc:7 SumOfSelf, FCLKParams.cc:6 CurrentSelf, ICLKParams.cc:6 InitialSelf)."""
+    p = default_params(am=am, ssm=ssm, sm=sm)
+    if "hess_type" not in kw:
+        p.hess_type = {"esm": 2, "fclk": 1, "iclk": 0, "pf": 0}[sm if isinstance(sm, str) else
+                                                                  {v: k for k, v in SM.items()}[sm]]
+    return set_params(p, **kw)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class BatchTracker:
+    """P independent patch trackers sharing one image: the batched counterpart of the reference's
+    `vector<TrackerBase*>` fan-out (SM/src/GridTracker.cc:247-264).  Method names follow TrackerBase."""
+
+    def __init__(self, params):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        self.params = params
+        self._check(self._L.mtfb_create(C.byref(params), C.byref(self._h)))
+        self.S = self._L.mtfb_state_size(self._h)
+        self.N = params.resx * params.resy
+        self.P = params.n_patches
+        self._img = None
+
+    # ---------------------------------------------------------------- plumbing
+    def _check(self, status):
+        if status != 0:
+            raise MTFError(status, self._L.mtfb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.mtfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._check(self._L.mtfb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._L.mtfb_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return self._L.mtfb_launch_count(self._h)
+
+    # ---------------------------------------------------------------- TrackerBase
+    def setImage(self, img):
+        """img: float32 h x w NumPy array (CV_32FC1, inputType() of the reference trackers), or a CUDA
+        float32 torch tensor (kept by reference, like the cv::Mat header ImageBase::setCurrImg keeps)."""
+        if hasattr(img, "data_ptr"):      # torch tensor
+            if not img.is_cuda or img.dtype.itemsize != 4 or img.dim() != 2 or img.stride(1) != 1:
+                raise MTFError(1, "setImage: CUDA float32 2-D tensor with unit column stride required")
+            self._img = img
+            self._check(self._L.mtfb_set_image_device(self._h, C.c_void_p(img.data_ptr()), img.shape[0],
+                                                      img.shape[1], img.stride(0)))
+            return
+        if img.dtype != np.float32 or img.ndim != 2 or img.strides[1] != 4:
+            raise MTFError(1, "setImage: float32 2-D array with contiguous rows required")
+        self._img = img
+        self._check(self._L.mtfb_set_image(self._h, C.c_void_p(img.ctypes.data), img.shape[0], img.shape[1],
+                                           img.strides[0] // 4))
+
+    def set_image_pinned(self, ptr, h, w, row_stride):
+        """host pointer variant (pinned buffers owned by the caller)"""
+        self._check(self._L.mtfb_set_image(self._h, C.c_void_p(ptr), h, w, row_stride))
+
+    def initialize(self, corners, img=None):
+        if img is not None:
+            self.setImage(img)
+        c = np.ascontiguousarray(corners, dtype=np.float64).reshape(self.P, 8)
+        self._check(self._L.mtfb_initialize(self._h, _dp(c)))
+
+    def setRegion(self, corners, img=None):
+        if img is not None:
+            self.setImage(img)
+        c = np.ascontiguousarray(corners, dtype=np.float64).reshape(self.P, 8)
+        self._check(self._L.mtfb_set_region(self._h, _dp(c)))
+
+    def update(self, img=None):
+        if img is not None:
+            self.setImage(img)
+        self._check(self._L.mtfb_update(self._h))
+
+    def getRegion(self):
+        out = np.empty((self.P, 2, 4))
+        self._check(self._L.mtfb_get_corners(self._h, _dp(out)))
+        return out
+
+    # ---------------------------------------------------------------- accessors
+    def _get(self, name, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        ptr = out.ctypes.data_as(C.POINTER(C.c_double if dtype == np.float64 else C.c_int))
+        self._check(getattr(self._L, name)(self._h, ptr))
+        return out
+
+    def state(self):
+        return self._get("mtfb_get_state", (self.P, self.S))
+
+    def n_iters(self):
+        return self._get("mtfb_get_n_iters", (self.P,), np.int32)
+
+    def similarity(self):
+        return self._get("mtfb_get_similarity", (self.P,))
+
+    def patch_status(self):
+        return self._get("mtfb_get_patch_status", (self.P,), np.int32)
+
+    def init_warp(self):
+        return self._get("mtfb_get_init_warp", (self.P, 3, 3))
+
+    def init_pts(self):
+        return self._get("mtfb_get_init_pts", (self.P, self.N, 2))
+
+    def init_pix_vals(self):
+        return self._get("mtfb_get_init_pix_vals", (self.P, self.N))
+
+    def curr_stage(self, pts=True, pix_vals=True, pix_grad=True, pix_jac=True):
+        """(pts P x N x 2, It P x N, dIt_dx P x N x 2, dIt_dp P x N x S) at the current state."""
+        a = np.empty((self.P, self.N, 2)) if pts else None
+        b = np.empty((self.P, self.N)) if pix_vals else None
+        g = np.empty((self.P, 2, self.N)) if pix_grad else None
+        j = np.empty((self.P, self.S, self.N)) if pix_jac else None
+        null = C.POINTER(C.c_double)()
+        self._check(self._L.mtfb_get_curr_stage(self._h, _dp(a) if pts else null, _dp(b) if pix_vals else null,
+                                                _dp(g) if pix_grad else null, _dp(j) if pix_jac else null))
+        return (a, b, None if g is None else g.transpose(0, 2, 1), None if j is None else j.transpose(0, 2, 1))
+
+    def iterate_once(self):
+        """one Gauss-Newton pass: (J P x S, H P x S x S, f P, dp P x S)"""
+        J = np.empty((self.P, self.S)); H = np.empty((self.P, self.S, self.S)); f = np.empty(self.P)
+        dp = np.empty((self.P, self.S))
+        self._check(self._L.mtfb_iterate_once(self._h, _dp(J), _dp(H), _dp(f), _dp(dp)))
+        return J, H.transpose(0, 2, 1), f, dp      # column-major S x S -> [i][j]
+
+    def enable_iter_log(self, n_slots):
+        self._log_slots = n_slots
+        self._check(self._L.mtfb_enable_iter_log(self._h, n_slots))
+
+    def iter_log(self):
+        n = self._log_slots
+        arr = (IterLog * (self.P * n))()
+        self._check(self._L.mtfb_get_iter_log(self._h, arr))
+        S = self.S
+        out = []
+        for p in range(self.P):
+            rows = []
+            for i in range(n):
+                e = arr[p * n + i]
+                if not e.valid:
+                    break
+                rows.append(dict(f=e.f, jacobian=np.array(e.jacobian[:S]),
+                                 hessian=np.array(e.hessian[:S * S]).reshape(S, S).T,
+                                 state_update=np.array(e.state_update[:S]),
+                                 corners=np.array(e.corners[:]).reshape(2, 4),
+                                 update_norm=e.update_norm, rejected=bool(e.rejected)))
+            out.append(rows)
+        return out
+
+    def pf_evaluate(self, states):
+        states = np.ascontiguousarray(states, dtype=np.float64)
+        n = states.shape[1]
+        assert states.shape == (self.P, n, self.S)
+        lik = np.empty((self.P, n)); sim = np.empty((self.P, n))
+        self._check(self._L.mtfb_pf_evaluate(self._h, _dp(states), n, _dp(lik), _dp(sim)))
+        return lik, sim
+
+    def device_results(self):
+        """raw device pointers (corners P x 8 f64, state P x S f64, n_iters P i32)"""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.mtfb_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value

@@ -1,0 +1,434 @@
+// lk_kernels.cu -- the fused Lucas-Kanade kernels (sm_100a).
+//
+// One CTA tracks one patch for a whole frame: the <= max_iters Gauss-Newton loop of
+// nt::FCLK::update (SM/src/NT/FCLK.cc:171-358), nt::ESM::update (SM/src/NT/ESM.cc:170-297) and
+// nt::ICLK::update (SM/src/NT/ICLK.cc:160-299) runs inside a single launch.  Per pass every thread
+// walks its pixels once and does, in registers, what the reference does in eight sweeps over
+// materialised N-vectors / N x S matrices:
+//   ssm.getPts            warp the grid point                    (lk_math.cuh pixel_geometry)
+//   am.updatePixVals      bilinear sample                        (sample_pixel*)
+//   am.updatePixGrad      image gradient at the warped point     (sample_pixel_grad)
+//   ssm.cmptWarpedPixJacobian   dI/dp row                        (warped_pix_jacobian)
+//   am.updateSimilarity / updateCurrGrad / cmptCurrJacobian / cmptSelfHessian
+//                         f, J^T r and J^T J accumulated per thread in fp64
+// then the CTA reduces the 1 + S + S(S+1)/2 sums (warp butterfly + one shared-memory hop) and warp 0
+// runs the Levenberg-Marquardt bookkeeping, the S x S column-pivoted QR solve, the compositional
+// update and the corner-change stopping test.
+#include "lk_kernels.cuh"
+#include "lk_warp.cuh"
+
+namespace mtfb {
+
+enum { CTRL_NEXT = 0, CTRL_BREAK = 1, CTRL_REJECT = 2 };
+
+template<int S> struct AccLayout {
+	static constexpr int NH = S*(S + 1) / 2;
+	static constexpr int NA = 1 + S + NH;             // sum r^2 | J^T d | upper triangle of J^T J
+	__host__ __device__ static constexpr int tri(int i, int j){ return i*S - i*(i - 1) / 2 + (j - i); }  // i <= j
+};
+
+// CTA-wide sum of a per-thread accumulator vector; result in s_sum[0..CNT) after the call.
+template<int CNT, int T> __device__ __forceinline__ void block_reduce(double (&acc)[CNT], double *s_part /* [T/32][CNT] */,
+	double *s_sum){
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int idx[2];
+	warp_reduce_scatter<CNT>(acc, lane, idx);
+	if(idx[0] >= 0) s_part[warp*CNT + idx[0]] = acc[0];
+	if(idx[1] >= 0) s_part[warp*CNT + idx[1]] = acc[1];
+	__syncthreads();
+	for(int e = threadIdx.x; e < CNT; e += T){
+		double s = s_part[e];
+#pragma unroll
+		for(int w = 1; w < T / 32; ++w) s += s_part[w*CNT + e];
+		s_sum[e] = s;
+	}
+	__syncthreads();
+}
+
+struct PixIter {
+	int pix, row, col, dcol, drow, resx;
+	__device__ __forceinline__ PixIter(int tid, int step, int _resx) : pix(tid), row(tid / _resx), col(tid % _resx),
+		dcol(step % _resx), drow(step / _resx), resx(_resx){}
+	__device__ __forceinline__ void next(int step){
+		pix += step; col += dcol; row += drow;
+		if(col >= resx){ col -= resx; ++row; }
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// initialize(): ssm.setCorners + am.initializePixVals + initializePixGrad + cmptWarpedPixJacobian (at the
+// identity warp) + am.cmptSelfHessian  (NT/FCLK.cc:102-169, NT/ESM.cc:110-146, NT/ICLK.cc:71-127)
+// ------------------------------------------------------------------------------------------------
+template<int AM, int SSM, int T>
+__global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__restrict__ corners_in){
+	constexpr int S = StateSize<SSM>::value;
+	typedef AccLayout<S> L;
+	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	__shared__ double s_dlt[9];
+	__shared__ double s_part[(T / 32) * L::NA];
+	__shared__ double s_sum[L::NA];
+	const double *c_in = corners_in + (size_t)p * 8;
+	if(warp == 0){
+		Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
+		if(lane < 9){ s_dlt[lane] = dlt.m[lane]; b.dlt[(size_t)p * 9 + lane] = dlt.m[lane]; }
+		Mat3 I = mat3_identity();
+		if(lane < 9) b.warp[(size_t)p * 9 + lane] = I.m[lane];
+		if(lane < S) b.state[(size_t)p*S + lane] = 0;
+		if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }
+		if(lane == 0){ b.f[p] = 0; b.n_iters[p] = 0; b.status[p] = 0; }
+	}
+	__syncthreads();
+	Mat3 dlt, W = mat3_identity();
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	const double abcd[4] = { 1, 0, 0, 1 };
+	double acc[L::NA];
+#pragma unroll
+	for(int i = 0; i < L::NA; ++i) acc[i] = 0;
+	double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
+	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		double val, gx, gy;
+		sample_pixel_grad(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		val = b.pix_mult*val + b.pix_add;
+		double J[S];
+		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
+		I0[it.pix] = val;
+		// the chained template gradient is what cmptWarpedPixJacobian left in the Ix / Iy columns
+		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
+		G0[b.N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+#pragma unroll
+		for(int i = 0; i < S; ++i){
+#pragma unroll
+			for(int j = i; j < S; ++j) acc[1 + S + L::tri(i, j)] = fma(J[i], J[j], acc[1 + S + L::tri(i, j)]);
+		}
+	}
+	block_reduce<L::NA, T>(acc, s_part, s_sum);
+	if(tid < S*S){
+		int i = tid % S, j = tid / S;
+		int lo = i < j ? i : j, hi = i < j ? j : i;
+		b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];        // SSD self Hessian: -J^T J
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// update(): the whole per-frame loop
+// ------------------------------------------------------------------------------------------------
+template<int AM, int SSM, int SM, int T>
+__global__ void __launch_bounds__(T) lk_update_kernel(DevBatch b){
+	static_assert(AM == AM_SSD, "this kernel is the SSD instantiation");
+	constexpr int S = StateSize<SSM>::value;
+	typedef AccLayout<S> L;
+	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	__shared__ double s_part[(T / 32) * L::NA];
+	__shared__ double s_sum[L::NA];
+	__shared__ double s_W[9], s_corners[8], s_init_corners[8];
+	__shared__ int s_ctrl;
+	Mat3 dlt;
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = b.dlt[(size_t)p * 9 + i];
+	if(tid < 9) s_W[tid] = b.warp[(size_t)p * 9 + tid];
+	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
+	__syncthreads();
+	const double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
+	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
+	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
+	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
+	// Levenberg-Marquardt bookkeeping (uniform; only warp 0's copy is used)
+	double prev_similarity = 0, lm_delta = b.lm_delta_init, ssm_update = 0 /* lane l holds entry l */;
+	bool state_reset = false;
+	int iter_id = 0, n_passes = 0, patch_status = 0;
+	double f = 0;
+	while(iter_id < b.max_iters){
+		Mat3 W;
+#pragma unroll
+		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
+		double abcd[4] = { W.m[0], W.m[1], W.m[3], W.m[4] };      // Affine.cc:217-220: curr_state(2)+1, (3), (4), (5)+1
+		if(SSM == SSM_AFF){
+			// the reference reads them back from curr_state = getStateFromWarp(curr_warp): (w00 - 1) + 1 etc.
+			abcd[0] = (W.m[0] - 1) + 1; abcd[3] = (W.m[4] - 1) + 1;
+		}
+		double acc[L::NA];
+#pragma unroll
+		for(int i = 0; i < L::NA; ++i) acc[i] = 0;
+		for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			double It, gx = 0, gy = 0;
+			if(need_grad){ sample_pixel_grad(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, It, gx, gy); }
+			else{ It = sample_pixel(b.img, g.wx, g.wy); }
+			const double r = It - I0[it.pix];                         // I_diff (SSDBase.cc:78)
+			acc[0] = fma(r, r, acc[0]);
+			double Jt[S], Jj[S];                                      // Jj: what multiplies df/dI in the Jacobian
+			if(SM == SM_ICLK){
+				init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[b.N + it.pix], Jj);
+				// df_dI0 = I_diff (SSDBase.cc:34: I_diff aliases df_dI0)
+#pragma unroll
+				for(int s = 0; s < S; ++s) acc[1 + s] = fma(r, Jj[s], acc[1 + s]);
+				if(!need_grad) continue;
+				warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, Jt);
+			} else{
+				warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, Jt);
+				const double d = -r;                                  // df_dIt = -I_diff (SSDBase.cc:115-121)
+				if(SM == SM_ESM){
+					double J0[S];
+					init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[b.N + it.pix], J0);
+					if(esm_mean){
+						// mean_pix_jacobian = (init + curr) / 2 (NT/ESM.cc:246-248)
+#pragma unroll
+						for(int s = 0; s < S; ++s) J0[s] = (J0[s] + Jt[s]) / 2.0;
+					}
+					if(b.jac_type == MTFB_ESM_JAC_ORIGINAL){
+#pragma unroll
+						for(int s = 0; s < S; ++s) Jj[s] = J0[s];
+					} else{
+						// SSDBase::cmptDifferenceOfJacobians: df_dIt * (dI0_dp + dIt_dp) (SSDBase.cc:186)
+#pragma unroll
+						for(int s = 0; s < S; ++s) Jj[s] = esm_mean ? (2.0*J0[s]) : (J0[s] + Jt[s]);
+					}
+					if(b.hess_type == MTFB_ESM_HESS_ORIGINAL){
+#pragma unroll
+						for(int s = 0; s < S; ++s) Jt[s] = J0[s];
+					}
+				} else{
+#pragma unroll
+					for(int s = 0; s < S; ++s) Jj[s] = Jt[s];
+				}
+#pragma unroll
+				for(int s = 0; s < S; ++s) acc[1 + s] = fma(d, Jj[s], acc[1 + s]);
+			}
+#pragma unroll
+			for(int i = 0; i < S; ++i){
+#pragma unroll
+				for(int j = i; j < S; ++j) acc[1 + S + L::tri(i, j)] = fma(Jt[i], Jt[j], acc[1 + S + L::tri(i, j)]);
+			}
+		}
+		block_reduce<L::NA, T>(acc, s_part, s_sum);
+		++n_passes;
+		// ---------------------------------------------------------------- warp 0: decide, solve, update
+		if(warp == 0){
+			int ctrl = CTRL_NEXT;
+			bool rejected = false;
+			f = -s_sum[0] / 2;                                        // SSDBase.cc:94
+			Mat3 Wn = W;
+			double upd_norm = 0, x = 0;
+			double dp[S];
+			if(b.leven_marq && !state_reset){
+				if(iter_id > 0){
+					if(f < prev_similarity){
+						lm_delta *= b.lm_delta_update;
+#pragma unroll
+						for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, ssm_update, s);
+						if(SM == SM_ICLK){
+							// undo the inverse step by re-applying the forward update (NT/ICLK.cc:183)
+							Wn = compose_update<SSM>(W, dp);
+						} else{
+							double inv[S];
+							invert_state<SSM>(inv, dp);
+							Wn = compose_update<SSM>(W, inv);
+						}
+						state_reset = true; rejected = true; ctrl = CTRL_REJECT;
+					} else if(f > prev_similarity){
+						lm_delta /= b.lm_delta_update;
+					}
+				}
+				if(!rejected) prev_similarity = f;
+			}
+			double Jv = 0;
+			if(!rejected){
+				state_reset = false;
+				WarpColPivQR<S, S> qr;
+				// column `lane` of the Hessian
+				const int jc = lane < S ? lane : 0;
+				int hsel;                                           // 0: -J^T J, 1: init, 2: mean of both
+				if(SM == SM_ESM){
+					hsel = (b.hess_type == MTFB_ESM_HESS_INITIAL_SELF) ? 1 :
+						(b.hess_type == MTFB_ESM_HESS_SUM_OF_SELF || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD) ? 2 : 0;
+				} else if(SM == SM_FCLK){
+					hsel = (b.hess_type == MTFB_LK_HESS_INITIAL_SELF) ? 1 : 0;
+				} else{
+					hsel = (b.hess_type == MTFB_LK_HESS_CURRENT_SELF) ? 0 : 1;
+				}
+#pragma unroll
+				for(int i = 0; i < S; ++i){
+					const int lo = i < jc ? i : jc, hi = i < jc ? jc : i;
+					const double hc = -s_sum[1 + S + L::tri(lo, hi)];
+					const double hi0 = b.Hinit[(size_t)p * 64 + jc*S + i];
+					qr.a[i] = hsel == 0 ? hc : (hsel == 1 ? hi0 : (hc + hi0) * 0.5);
+				}
+				if(lane == S){
+#pragma unroll
+					for(int i = 0; i < S; ++i) qr.a[i] = jac_half ? s_sum[1 + i] * 0.5 : s_sum[1 + i];
+				}
+				if(lane < S) Jv = jac_half ? s_sum[1 + lane] * 0.5 : s_sum[1 + lane];
+				if(b.leven_marq){
+#pragma unroll
+					for(int i = 0; i < S; ++i) if(i == lane) qr.a[i] += lm_delta * qr.a[i];
+				}
+				if(b.log && n_passes <= b.log_slots && lane < S){
+					mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
+#pragma unroll
+					for(int i = 0; i < S; ++i) e->hessian[lane*S + i] = qr.a[i];
+				}
+				qr.factor(lane, true);
+				x = -qr.solve(lane);                                // state_update = -H^-1 J^T
+				if(qr.nonzero_pivots < S) patch_status |= MTFB_PATCH_SINGULAR;
+				ssm_update = x;
+#pragma unroll
+				for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, x, s);
+				if(SM == SM_ICLK){
+					double inv[S];
+					invert_state<SSM>(inv, dp);                     // NT/ICLK.cc:270-271
+					Wn = compose_update<SSM>(W, inv);
+				} else{
+					Wn = compose_update<SSM>(W, dp);
+				}
+			}
+			double nc[8];
+			warp_corners<SSM>(Wn, s_init_corners, nc);
+			if(!rejected){
+#pragma unroll
+				for(int i = 0; i < 8; ++i){ double d = s_corners[i] - nc[i]; upd_norm += d*d; }
+				if(upd_norm < b.epsilon) ctrl = CTRL_BREAK;
+				if(!(upd_norm == upd_norm) || !(f == f)) patch_status |= MTFB_PATCH_NAN;
+			}
+			__syncwarp();
+			if(lane < 9) s_W[lane] = Wn.m[lane];
+			if(lane < 8) s_corners[lane] = nc[lane];
+			if(lane == 0) s_ctrl = ctrl;
+			if(b.log && n_passes <= b.log_slots){
+				mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
+				if(lane < S){ e->jacobian[lane] = rejected ? 0.0 : Jv; e->state_update[lane] = rejected ? 0.0 : x; }
+				if(lane < 8) e->corners[lane] = nc[lane];
+				if(lane == 0){ e->f = f; e->update_norm = upd_norm; e->rejected = rejected; e->valid = 1; }
+			}
+		}
+		__syncthreads();
+		const int ctrl = s_ctrl;
+		if(ctrl == CTRL_BREAK) break;
+		// nt::FCLK re-enters its while loop without counting a rejected step (NT/FCLK.cc:187,210);
+		// every other loop is a for(...; ++iter_id) (FCLK.cc:117,135, ESM.cc:128, NT/ESM.cc:186, ICLK.cc:150, NT/ICLK.cc:167)
+		if(!(ctrl == CTRL_REJECT && SM == SM_FCLK && b.nt_semantics)) ++iter_id;
+	}
+	if(warp == 0){
+		Mat3 W;
+#pragma unroll
+		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
+		double st[S];
+		state_from_warp<SSM>(st, W);
+		if(lane < 9) b.warp[(size_t)p * 9 + lane] = W.m[lane];
+		if(lane < 8) b.corners[(size_t)p * 8 + lane] = s_corners[lane];
+#pragma unroll
+		for(int s = 0; s < S; ++s) if(lane == s) b.state[(size_t)p*S + s] = st[s];
+		if(lane == 0){ b.f[p] = f; b.n_iters[p] = n_passes; b.status[p] = patch_status; }
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// setRegion(): ssm.setCorners only -- new DLT, identity warp; the template is kept
+// (NT/FCLK.cc:360-376 with CurrentSelf Hessian, NT/ICLK.cc setRegion with update_ssm = 0)
+// ------------------------------------------------------------------------------------------------
+__global__ void lk_set_region_kernel(DevBatch b, const double *__restrict__ corners_in, int S){
+	const int p = blockIdx.x, lane = threadIdx.x;
+	const double *c_in = corners_in + (size_t)p * 8;
+	Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
+	Mat3 I = mat3_identity();
+	if(lane < 9){ b.dlt[(size_t)p * 9 + lane] = dlt.m[lane]; b.warp[(size_t)p * 9 + lane] = I.m[lane]; }
+	if(lane < S) b.state[(size_t)p*S + lane] = 0;
+	if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage taps: pts / It / dIt_dx / dIt_dp at the current state, through the same device functions
+// ------------------------------------------------------------------------------------------------
+template<int AM, int SSM, int T>
+__global__ void __launch_bounds__(T) lk_stage_kernel(DevBatch b, StageTaps t){
+	constexpr int S = StateSize<SSM>::value;
+	const int p = blockIdx.x, tid = threadIdx.x;
+	Mat3 dlt, W;
+#pragma unroll
+	for(int i = 0; i < 9; ++i){ dlt.m[i] = b.dlt[(size_t)p * 9 + i]; W.m[i] = b.warp[(size_t)p * 9 + i]; }
+	double abcd[4] = { W.m[0], W.m[1], W.m[3], W.m[4] };
+	if(SSM == SSM_AFF){ abcd[0] = (W.m[0] - 1) + 1; abcd[3] = (W.m[4] - 1) + 1; }
+	const size_t N = b.N;
+	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		double val, gx, gy;
+		sample_pixel_grad(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		val = b.pix_mult*val + b.pix_add;
+		double J[S];
+		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
+		if(t.pts){ t.pts[(p*N + it.pix) * 2] = g.wx; t.pts[(p*N + it.pix) * 2 + 1] = g.wy; }
+		if(t.pix_vals) t.pix_vals[p*N + it.pix] = val;
+		if(t.pix_grad){ t.pix_grad[p * 2 * N + it.pix] = gx; t.pix_grad[p * 2 * N + N + it.pix] = gy; }
+		if(t.pix_jac){
+#pragma unroll
+			for(int s = 0; s < S; ++s) t.pix_jac[(p*S + s)*N + it.pix] = J[s];
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+bool combo_supported(int am, int ssm, int sm){
+	return am == AM_SSD && (ssm == SSM_HOM || ssm == SSM_AFF) && (sm == SM_ESM || sm == SM_FCLK || sm == SM_ICLK);
+}
+
+template<int AM, int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	switch(threads){
+	case 64: lk_init_kernel<AM, SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners); break;
+	case 128: lk_init_kernel<AM, SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners); break;
+	case 256: lk_init_kernel<AM, SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_init(int am, int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	if(am != AM_SSD) return cudaErrorNotSupported;
+	if(ssm == SSM_HOM) return launch_init_t<AM_SSD, SSM_HOM>(threads, b, d_corners, st);
+	return launch_init_t<AM_SSD, SSM_AFF>(threads, b, d_corners, st);
+}
+
+cudaError_t launch_set_region(int am, int ssm, int sm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	(void)am; (void)sm; (void)threads;
+	lk_set_region_kernel<<<b.P, 32, 0, st>>>(b, d_corners, ssm == SSM_HOM ? 8 : 6);
+	return cudaGetLastError();
+}
+
+template<int AM, int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, cudaStream_t st){
+	switch(threads){
+	case 64: lk_update_kernel<AM, SSM, SM, 64><<<b.P, 64, 0, st>>>(b); break;
+	case 128: lk_update_kernel<AM, SSM, SM, 128><<<b.P, 128, 0, st>>>(b); break;
+	case 256: lk_update_kernel<AM, SSM, SM, 256><<<b.P, 256, 0, st>>>(b); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_update(int am, int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st){
+	if(!combo_supported(am, ssm, sm)) return cudaErrorNotSupported;
+	if(ssm == SSM_HOM){
+		if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_HOM, SM_ESM>(threads, b, st);
+		if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, b, st);
+		return launch_update_t<AM_SSD, SSM_HOM, SM_ICLK>(threads, b, st);
+	}
+	if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_AFF, SM_ESM>(threads, b, st);
+	if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_AFF, SM_FCLK>(threads, b, st);
+	return launch_update_t<AM_SSD, SSM_AFF, SM_ICLK>(threads, b, st);
+}
+
+template<int AM, int SSM> static cudaError_t launch_stage_t(int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
+	switch(threads){
+	case 64: lk_stage_kernel<AM, SSM, 64><<<b.P, 64, 0, st>>>(b, t); break;
+	case 128: lk_stage_kernel<AM, SSM, 128><<<b.P, 128, 0, st>>>(b, t); break;
+	case 256: lk_stage_kernel<AM, SSM, 256><<<b.P, 256, 0, st>>>(b, t); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_stage(int am, int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
+	(void)am;
+	if(ssm == SSM_HOM) return launch_stage_t<AM_SSD, SSM_HOM>(threads, b, t, st);
+	return launch_stage_t<AM_SSD, SSM_AFF>(threads, b, t, st);
+}
+
+} // namespace mtfb

@@ -1,0 +1,45 @@
+// lk_kernels.cuh -- declarations shared by the kernel translation unit and the C-ABI host code.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/mtf_b200.h"
+#include "lk_math.cuh"
+
+namespace mtfb {
+
+// Everything one launch needs, passed by value.  All pointers are device pointers; per-patch arrays are
+// indexed [patch][...] (SoA per patch so that consecutive threads touch consecutive addresses).
+struct DevBatch {
+	int P, N, resx, resy;
+	Image img;
+	const double *xv, *yv;       // normalised sampling grid (LinSpaced values), resx / resy entries
+	const double *norm_corners;  // 8: corners of the normalised grid (x0..x3, y0..y3)
+	double *dlt;                 // P x 9   DLT warp of setCorners, row-major
+	double *warp;                // P x 9   curr_warp, row-major
+	double *state;               // P x S   curr_state
+	double *corners;             // P x 8   curr_corners
+	double *init_corners;        // P x 8
+	double *I0;                  // P x N   template pixel values (am.I0)
+	double *G0;                  // P x 2 x N  template gradient, already chained with the init warp
+	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
+	double *f;                   // P       similarity
+	int *n_iters;                // P
+	int *status;                 // P
+	mtfb_iter_log *log;          // P x log_slots or null
+	int log_slots;
+	// parameters
+	int max_iters, hess_type, jac_type, leven_marq, nt_semantics;
+	double epsilon, lm_delta_init, lm_delta_update, grad_eps;
+	double pix_mult, pix_add;    // am pix_norm_mult / pix_norm_add (1, 0 except MI)
+	double grad_mult;            // pix_mult / (2 grad_eps)  (imgUtils.cc:238)
+};
+
+struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
+
+// launchers (lk_kernels.cu); threads = threads per patch (64 / 128 / 256)
+cudaError_t launch_init(int am, int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
+cudaError_t launch_set_region(int am, int ssm, int sm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
+cudaError_t launch_update(int am, int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
+cudaError_t launch_stage(int am, int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
+bool combo_supported(int am, int ssm, int sm);
+
+} // namespace mtfb

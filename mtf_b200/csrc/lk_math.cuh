@@ -1,0 +1,273 @@
+// lk_math.cuh -- per-pixel arithmetic of the Lucas-Kanade hot path (host+device inline functions).
+//
+// Everything in here is plain fp64 written in the reference's operation order and compiled with
+// -fmad=false (device) / -ffp-contract=off (host unit tests), so that warped coordinates, sampling
+// indices and interpolated pixel values come out bit-identical to the reference's Eigen path.
+// Fused multiply-adds are used only where they are spelled fma() explicitly (reductions).
+//
+// Reference functions restated (paths relative to the MTF tree):
+//   sample_pixel        Utilities/include/mtf/Utilities/imgUtils.h:51-113  getPixVal<Linear,Constant>
+//   sample_pixel_grad   Utilities/src/imgUtils.cc:233-254 getImgGrad -- the eps -> 0 limit of its central
+//                       finite difference, including what happens at integer coordinates and image borders
+//   Homography / Affine geometry  SSM/src/ProjectiveBase.cc:20-49, SSM/src/Homography.cc:50-132,231-294,
+//                       SSM/src/Affine.cc:64-150,213-242, Utilities/include/mtf/Utilities/warpUtils.h:9-21
+#pragma once
+
+#if defined(__CUDACC__)
+#define MTFB_HD __host__ __device__ __forceinline__
+#else
+#define MTFB_HD inline
+#endif
+
+namespace mtfb {
+
+enum { AM_SSD = 0, AM_NCC = 1, AM_MI = 2 };
+enum { SSM_HOM = 0, SSM_AFF = 1 };
+enum { SM_ESM = 0, SM_FCLK = 1, SM_ICLK = 2, SM_PF = 3 };
+
+struct Image {
+	const float *data;   // pitched, row-major
+	int h, w, pitch;     // pitch in elements
+};
+
+// imgUtils.h:51-53
+MTFB_HD bool check_overflow(double x, double y, int h, int w){
+	// written so that a NaN coordinate counts as outside: on x86 the reference's (int)NaN is INT_MIN, which
+	// its second checkOverflow(lx, ly) call rejects (imgUtils.h:105), with the same result
+	return !((x >= 0) && (x < w) && (y >= 0) && (y < h));
+}
+
+#if defined(__CUDA_ARCH__)
+#define MTFB_LDG(p) __ldg(p)
+#else
+#define MTFB_LDG(p) (*(p))
+#endif
+
+// getPixVal<Linear, Constant>: imgUtils.h:91-113.  overflow_val = 128 (imgUtils.h:57).
+MTFB_HD double sample_pixel(const Image &im, double x, double y){
+	if(check_overflow(x, y, im.h, im.w)){ return 128.0; }
+	int lx = static_cast<int>(x);
+	int ly = static_cast<int>(y);
+	double dx = x - lx;
+	double dy = y - ly;
+	int ux = dx == 0 ? lx : lx + 1;
+	int uy = dy == 0 ? ly : ly + 1;
+	if(ux >= im.w || uy >= im.h){ return 128.0; }
+	const float *r0 = im.data + (size_t)ly*im.pitch, *r1 = im.data + (size_t)uy*im.pitch;
+	double p00 = MTFB_LDG(r0 + lx), p01 = MTFB_LDG(r0 + ux), p10 = MTFB_LDG(r1 + lx), p11 = MTFB_LDG(r1 + ux);
+	return p00 * (1 - dx)*(1 - dy) + p01 * dx*(1 - dy) + p10 * (1 - dx)*dy + p11 * dx*dy;
+}
+
+// Pixel value (bit-exact getPixVal) and image gradient with the semantics of utils::getImgGrad
+// (imgUtils.cc:233-254): the central difference  (P(x+eps, y) - P(x-eps, y)) * (mult / (2 eps))  of the
+// piecewise-bilinear interpolant P (constant 128 outside the image), eps = grad_eps = 1e-8.
+//   * FAST PATH -- x-eps and x+eps lie in the same pixel cell as x (all but a 2e-8-wide band around each
+//     pixel column): P is linear in x there, so the quotient equals the cell's slope
+//     (1-dy)(p01-p00) + dy(p11-p10) up to the quotient's own rounding noise (~1e-5 relative); the slope is
+//     returned, computed from the four pixels already loaded for the value.
+//   * LITERAL PATH -- the two samples straddle a pixel column (always the case at integer coordinates, e.g. an
+//     axis-aligned patch at initialisation, where the quotient becomes the mean of the two one-sided slopes),
+//     or one of them leaves the image (the reference then divides (128 - I) by 2e-8): the reference's two
+//     getPixVal calls and its quotient are evaluated literally, so these cases match bit for bit.
+// grad_mult = mult / (2 eps) as imgUtils.cc:238 forms it; mult = pix_norm_mult (1 except MI).
+MTFB_HD void sample_pixel_grad(const Image &im, double x, double y, double grad_eps, double grad_mult, double mult,
+	double &val, double &gx, double &gy){
+	val = 128.0;
+	bool fast_x = false, fast_y = false;
+	double sx = 0, sy = 0;
+	if(!check_overflow(x, y, im.h, im.w)){
+		int lx = static_cast<int>(x);
+		int ly = static_cast<int>(y);
+		double dx = x - lx;
+		double dy = y - ly;
+		int ux = dx == 0 ? lx : lx + 1;
+		int uy = dy == 0 ? ly : ly + 1;
+		if(ux < im.w && uy < im.h){
+			const float *r0 = im.data + (size_t)ly*im.pitch, *r1 = im.data + (size_t)uy*im.pitch;
+			double p00 = MTFB_LDG(r0 + lx), p01 = MTFB_LDG(r0 + ux), p10 = MTFB_LDG(r1 + lx), p11 = MTFB_LDG(r1 + ux);
+			val = p00 * (1 - dx)*(1 - dy) + p01 * dx*(1 - dy) + p10 * (1 - dx)*dy + p11 * dx*dy;
+			fast_x = (x - grad_eps >= lx) && (x + grad_eps < lx + 1);
+			fast_y = (y - grad_eps >= ly) && (y + grad_eps < ly + 1);
+			sx = ((1 - dy)*(p01 - p00) + dy*(p11 - p10)) * mult;
+			sy = ((1 - dx)*(p10 - p00) + dx*(p11 - p01)) * mult;
+		}
+	}
+	if(fast_x){ gx = sx; }
+	else{
+		double inc = sample_pixel(im, x + grad_eps, y), dec = sample_pixel(im, x - grad_eps, y);
+		gx = (inc - dec)*grad_mult;
+	}
+	if(fast_y){ gy = sy; }
+	else{
+		double inc = sample_pixel(im, x, y + grad_eps), dec = sample_pixel(im, x, y - grad_eps);
+		gy = (inc - dec)*grad_mult;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 helpers, row-major m[3*r + c]; arithmetic order = Eigen's lazy coefficient-wise product
+// ------------------------------------------------------------------------------------------------
+struct Mat3 { double m[9]; };
+
+MTFB_HD Mat3 mat3_identity(){
+	Mat3 I;
+	for(int i = 0; i < 9; ++i) I.m[i] = 0;
+	I.m[0] = I.m[4] = I.m[8] = 1;
+	return I;
+}
+MTFB_HD Mat3 mat3_mul(const Mat3 &a, const Mat3 &b){
+	Mat3 c;
+	for(int i = 0; i < 3; ++i) for(int j = 0; j < 3; ++j){
+		double s = a.m[3 * i] * b.m[j];
+		s = s + a.m[3 * i + 1] * b.m[3 + j];
+		s = s + a.m[3 * i + 2] * b.m[6 + j];
+		c.m[3 * i + j] = s;
+	}
+	return c;
+}
+// Matrix3d::inverse(): cofactors times 1/det (Eigen compute_inverse_size3_helper)
+MTFB_HD double mat3_cofactor(const Mat3 &m, int i, int j){
+	int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+	return m.m[3 * i1 + j1] * m.m[3 * i2 + j2] - m.m[3 * i1 + j2] * m.m[3 * i2 + j1];
+}
+MTFB_HD Mat3 mat3_inverse(const Mat3 &m){
+	double c0 = mat3_cofactor(m, 0, 0), c1 = mat3_cofactor(m, 1, 0), c2 = mat3_cofactor(m, 2, 0);
+	double det = c0 * m.m[0];
+	det = det + c1 * m.m[3];
+	det = det + c2 * m.m[6];
+	double invdet = 1.0 / det;
+	Mat3 r;
+	r.m[0] = c0 * invdet; r.m[1] = c1 * invdet; r.m[2] = c2 * invdet;
+	r.m[3] = mat3_cofactor(m, 0, 1)*invdet; r.m[4] = mat3_cofactor(m, 1, 1)*invdet; r.m[5] = mat3_cofactor(m, 2, 1)*invdet;
+	r.m[6] = mat3_cofactor(m, 0, 2)*invdet; r.m[7] = mat3_cofactor(m, 1, 2)*invdet; r.m[8] = mat3_cofactor(m, 2, 2)*invdet;
+	return r;
+}
+
+// Homography::getWarpFromState Homography.cc:94-107 ; Affine::getWarpFromState Affine.cc:117-131
+template<int SSM> MTFB_HD Mat3 warp_from_state(const double *s){
+	Mat3 w;
+	if(SSM == SSM_HOM){
+		w.m[0] = 1 + s[0]; w.m[1] = s[1]; w.m[2] = s[2];
+		w.m[3] = s[3]; w.m[4] = 1 + s[4]; w.m[5] = s[5];
+		w.m[6] = s[6]; w.m[7] = s[7]; w.m[8] = 1;
+	} else{
+		w.m[0] = 1 + s[2]; w.m[1] = s[3]; w.m[2] = s[0];
+		w.m[3] = s[4]; w.m[4] = 1 + s[5]; w.m[5] = s[1];
+		w.m[6] = 0; w.m[7] = 0; w.m[8] = 1;
+	}
+	return w;
+}
+// Homography::getStateFromWarp Homography.cc:116-132 ; Affine::getStateFromWarp Affine.cc:133-143
+template<int SSM> MTFB_HD void state_from_warp(double *s, const Mat3 &w){
+	if(SSM == SSM_HOM){
+		s[0] = w.m[0] - 1; s[1] = w.m[1]; s[2] = w.m[2];
+		s[3] = w.m[3]; s[4] = w.m[4] - 1; s[5] = w.m[5];
+		s[6] = w.m[6]; s[7] = w.m[7];
+	} else{
+		s[0] = w.m[2]; s[1] = w.m[5]; s[2] = w.m[0] - 1;
+		s[3] = w.m[1]; s[4] = w.m[3]; s[5] = w.m[4] - 1;
+	}
+}
+// Homography::compositionalUpdate Homography.cc:73-92 ; Affine::compositionalUpdate Affine.cc:90-107
+// (the re-warp of the points is done by the pixel loop)
+template<int SSM> MTFB_HD Mat3 compose_update(const Mat3 &curr_warp, const double *state_update){
+	Mat3 upd = warp_from_state<SSM>(state_update);
+	Mat3 w = mat3_mul(curr_warp, upd);
+	if(SSM == SSM_HOM){
+		double d = w.m[8];
+		for(int i = 0; i < 9; ++i) w.m[i] = w.m[i] / d;
+	}
+	return w;
+}
+// Homography::invertState Homography.cc:109-114 ; Affine::invertState Affine.cc:145-150
+template<int SSM> MTFB_HD void invert_state(double *inv_state, const double *state){
+	Mat3 w = warp_from_state<SSM>(state);
+	Mat3 inv = mat3_inverse(w);
+	double d = inv.m[8];
+	for(int i = 0; i < 9; ++i) inv.m[i] = inv.m[i] / d;
+	state_from_warp<SSM>(inv_state, inv);
+}
+// corners of the current region: W . init_corners_hm, dehomogenised for the homography
+// (Homography.cc:85-91, Affine.cc:103-105).  init_corners: 8 doubles x0..x3,y0..y3 (hm z = 1)
+template<int SSM> MTFB_HD void warp_corners(const Mat3 &w, const double *init_corners, double *out){
+	for(int i = 0; i < 4; ++i){
+		double px = init_corners[i], py = init_corners[4 + i];
+		double hx = w.m[0] * px; hx = hx + w.m[1] * py; hx = hx + w.m[2] * 1.0;
+		double hy = w.m[3] * px; hy = hy + w.m[4] * py; hy = hy + w.m[5] * 1.0;
+		if(SSM == SSM_HOM){
+			double hz = w.m[6] * px; hz = hz + w.m[7] * py; hz = hz + w.m[8] * 1.0;
+			out[i] = hx / hz; out[4 + i] = hy / hz;
+		} else{
+			out[i] = hx; out[4 + i] = hy;
+		}
+	}
+}
+
+// Geometry of one grid point under the current warp.
+//   (u, v)         the normalised grid point (warpUtils.cc:15-33)
+//   dlt            4-point DLT warp of ssm.setCorners (ProjectiveBase.cc:20-25)
+//   ix, iy         init_pts      = dehomogenize(dlt . (u,v,1))
+//   Homography (normalized_init = 0): init_pts_hm keeps the DLT's third row (Homography.cc:68), so
+//                  curr_pts_hm = W . (dlt . (u,v,1)) and D = curr_pts_hm(2)
+//   Affine:        init_pts_hm is re-homogenised (Affine.cc:81-82), curr_pts = W.topRows(2) . (ix,iy,1)
+struct PixGeom { double ix, iy, wx, wy, D; };
+
+template<int SSM> MTFB_HD PixGeom pixel_geometry(const Mat3 &dlt, const Mat3 &W, double u, double v){
+	PixGeom g;
+	double hx = dlt.m[0] * u; hx = hx + dlt.m[1] * v; hx = hx + dlt.m[2] * 1.0;
+	double hy = dlt.m[3] * u; hy = hy + dlt.m[4] * v; hy = hy + dlt.m[5] * 1.0;
+	double hz = dlt.m[6] * u; hz = hz + dlt.m[7] * v; hz = hz + dlt.m[8] * 1.0;
+	g.ix = hx / hz; g.iy = hy / hz;
+	if(SSM == SSM_HOM){
+		double cx = W.m[0] * hx; cx = cx + W.m[1] * hy; cx = cx + W.m[2] * hz;
+		double cy = W.m[3] * hx; cy = cy + W.m[4] * hy; cy = cy + W.m[5] * hz;
+		double cz = W.m[6] * hx; cz = cz + W.m[7] * hy; cz = cz + W.m[8] * hz;
+		g.D = cz; g.wx = cx / cz; g.wy = cy / cz;
+	} else{
+		double cx = W.m[0] * g.ix; cx = cx + W.m[1] * g.iy; cx = cx + W.m[2] * 1.0;
+		double cy = W.m[3] * g.ix; cy = cy + W.m[4] * g.iy; cy = cy + W.m[5] * 1.0;
+		g.D = 1.0; g.wx = cx; g.wy = cy;
+	}
+	return g;
+}
+
+// ssm.cmptWarpedPixJacobian: Homography.cc:231-294, Affine.cc:213-242.  gx, gy = dI/dx at the warped point.
+// aff_abcd = (curr_state[2]+1, curr_state[3], curr_state[4], curr_state[5]+1) for the affine SSM.
+template<int SSM> MTFB_HD void warped_pix_jacobian(const Mat3 &W, const double *aff_abcd, const PixGeom &g,
+	double gx, double gy, double *J){
+	double x = g.ix, y = g.iy;
+	if(SSM == SSM_HOM){
+		double inv_det = 1.0 / g.D;
+		double dwx_dx = (W.m[0] - W.m[6] * g.wx), dwx_dy = (W.m[1] - W.m[7] * g.wx);
+		double dwy_dx = (W.m[3] - W.m[6] * g.wy), dwy_dy = (W.m[4] - W.m[7] * g.wy);
+		double Ix = (dwx_dx*gx + dwy_dx*gy)*inv_det;
+		double Iy = (dwx_dy*gx + dwy_dy*gy)*inv_det;
+		double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
+		J[6] = -x*Ixx - y*Iyx;
+		J[7] = -x*Ixy - y*Iyy;
+	} else{
+		double a = aff_abcd[0], b = aff_abcd[1], c = aff_abcd[2], d = aff_abcd[3];
+		double Ix = gx, Iy = gy;
+		double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+		J[0] = Ix*a + Iy*c; J[1] = Ix*b + Iy*d;
+		J[2] = Ixx*a + Iyx*c; J[3] = Ixy*a + Iyy*c;
+		J[4] = Ixx*b + Iyx*d; J[5] = Ixy*b + Iyy*d;
+	}
+}
+// pixel Jacobian of the TEMPLATE from its stored, pre-chained gradient (Ix, Iy): what
+// cmptWarpedPixJacobian produced at initialize() time, when curr_warp was the identity.
+template<int SSM> MTFB_HD void init_pix_jacobian(double x, double y, double Ix, double Iy, double *J){
+	double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+	if(SSM == SSM_HOM){
+		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
+		J[6] = -x*Ixx - y*Iyx;
+		J[7] = -x*Ixy - y*Iyy;
+	} else{
+		J[0] = Ix; J[1] = Iy; J[2] = Ixx; J[3] = Ixy; J[4] = Iyx; J[5] = Iyy;
+	}
+}
+
+template<int SSM> struct StateSize { static const int value = (SSM == SSM_HOM) ? 8 : 6; };
+
+} // namespace mtfb

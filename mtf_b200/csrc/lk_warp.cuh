@@ -1,0 +1,265 @@
+// lk_warp.cuh -- warp-level building blocks of the LK kernels (device only):
+//   * transposing butterfly reduction of a per-thread accumulator vector
+//   * column-pivoted Householder QR (the solver behind Eigen's colPivHouseholderQr().solve() that
+//     nt::FCLK / ESM / ICLK call every iteration: SM/src/NT/FCLK.cc:298, NT/ESM.cc:266, NT/ICLK.cc:228)
+//     with one matrix column per lane
+//   * the 4-point DLT of utils::computeHomographyDLT (Utilities/src/warpUtils.cc:171-223)
+#pragma once
+#include <cfloat>
+#include "lk_math.cuh"
+
+namespace mtfb {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// Butterfly "reduce-scatter" across the 32 lanes of a warp.
+// In: v[0..CNT) per lane.  Out: the warp-wide sum of entry e is left in exactly one lane; every lane ends
+// with at most 2 live entries in v[0], v[1] whose entry indices are idx0 / idx1 (-1 = none).
+// Costs about CNT 64-bit shuffles in total instead of 5*CNT for CNT independent all-reduces.
+// ------------------------------------------------------------------------------------------------
+template<int CNT, int MASK> struct Butterfly {
+	static constexpr int HALF = (CNT + 1) / 2;
+	template<int FULL> __device__ __forceinline__ static void run(double (&v)[FULL], int lane, int &base, bool &ok){
+		const bool up = (lane & MASK) != 0;
+#pragma unroll
+		for(int i = 0; i < HALF; ++i){
+			double lo = v[i];
+			double hi = (i + HALF < CNT) ? v[i + HALF] : 0.0;
+			double keep = up ? hi : lo;
+			double send = up ? lo : hi;
+			v[i] = keep + __shfl_xor_sync(FULL_MASK, send, MASK);
+		}
+		// slot i of this lane now stands for previous-level slot i + HALF*up
+		// (caller composes the index map; see warp_reduce_scatter)
+		(void)base; (void)ok;
+	}
+};
+
+template<int CNT> struct ReduceMap {
+	static constexpr int H1 = (CNT + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2, H4 = (H3 + 1) / 2, H5 = (H4 + 1) / 2;
+	static_assert(H5 <= 2, "accumulator vector too long for the 32-lane butterfly (max 64 entries)");
+};
+
+// returns through idx[0..1] the accumulator entry each of v[0], v[1] holds (or -1)
+template<int CNT> __device__ __forceinline__ void warp_reduce_scatter(double (&v)[CNT], int lane, int (&idx)[2]){
+	typedef ReduceMap<CNT> M;
+	int dummy = 0; bool ok = true;
+	Butterfly<CNT, 16>::run(v, lane, dummy, ok);
+	Butterfly<M::H1, 8>::run(v, lane, dummy, ok);
+	Butterfly<M::H2, 4>::run(v, lane, dummy, ok);
+	Butterfly<M::H3, 2>::run(v, lane, dummy, ok);
+	Butterfly<M::H4, 1>::run(v, lane, dummy, ok);
+	const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
+#pragma unroll
+	for(int j = 0; j < 2; ++j){
+		bool valid = j < M::H5;
+		int s4 = j + M::H5*b0;  valid = valid && (s4 < M::H4);     // slot at level 4
+		int s3 = s4 + M::H4*b1; valid = valid && (s3 < M::H3);
+		int s2 = s3 + M::H3*b2; valid = valid && (s2 < M::H2);
+		int s1 = s2 + M::H2*b3; valid = valid && (s1 < M::H1);
+		int s0 = s1 + M::H1*b4; valid = valid && (s0 < CNT);
+		idx[j] = valid ? s0 : -1;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column-pivoted Householder QR, Eigen 3.3 ColPivHouseholderQR::computeInPlace + _solve_impl semantics
+// (dgeqp3-style norm down-dating), ROWS x COLS, one column per lane (lanes 0..COLS-1); lane COLS may
+// carry a right-hand side that receives the reflectors on the fly.  Every loop is unrolled so the
+// per-lane column lives in registers.
+// ------------------------------------------------------------------------------------------------
+template<int ROWS, int COLS> struct WarpColPivQR {
+	static constexpr int SIZE = ROWS < COLS ? ROWS : COLS;
+	double a[ROWS];          // this lane's column (or the rhs on lane COLS)
+	double tau[SIZE];        // Householder coefficients (uniform)
+	int pos;                 // current position of this lane's column (-1: not a column)
+	int lane_at_pos[SIZE];   // uniform, valid after factor()
+	int nonzero_pivots;      // uniform
+
+	__device__ __forceinline__ void factor(int lane, bool with_rhs){
+		const bool is_col = lane < COLS;
+		const bool is_rhs = with_rhs && (lane == COLS);
+		pos = is_col ? lane : -1;
+		double cnd, cnu;
+		{
+			double s = 0;
+#pragma unroll
+			for(int r = 0; r < ROWS; ++r) s += a[r] * a[r];
+			cnd = sqrt(s); cnu = cnd;
+		}
+		double maxn = is_col ? cnu : 0.0;
+#pragma unroll
+		for(int off = 8; off >= 1; off >>= 1){
+			double o = __shfl_xor_sync(FULL_MASK, maxn, off);
+			maxn = (o > maxn) ? o : maxn;
+		}
+		maxn = __shfl_sync(FULL_MASK, maxn, 0);
+		const double th = maxn * DBL_EPSILON / double(ROWS);
+		const double threshold_helper = th * th;
+		const double norm_downdate_threshold = sqrt(DBL_EPSILON);
+		nonzero_pivots = SIZE;
+#pragma unroll
+		for(int k = 0; k < SIZE; ++k){
+			// pivot: first position >= k holding the largest updated column norm
+			const bool cand_ok = is_col && pos >= k;
+			double cand = cand_ok ? cnu : -1.0;
+			int cpos = cand_ok ? pos : (1 << 20);
+#pragma unroll
+			for(int off = 8; off >= 1; off >>= 1){
+				double ov = __shfl_xor_sync(FULL_MASK, cand, off);
+				int op = __shfl_xor_sync(FULL_MASK, cpos, off);
+				if(ov > cand || (ov == cand && op < cpos)){ cand = ov; cpos = op; }
+			}
+			double bmax = __shfl_sync(FULL_MASK, cand, 0);
+			int biggest = __shfl_sync(FULL_MASK, cpos, 0);
+			if(biggest >= (1 << 20)){ biggest = k; bmax = 0; }        // all-NaN norms: keep column k
+			if(nonzero_pivots == SIZE && bmax * bmax < threshold_helper * double(ROWS - k)) nonzero_pivots = k;
+			if(is_col){ if(pos == biggest) pos = k; else if(pos == k) pos = biggest; }
+			const int piv_lane = __ffs(__ballot_sync(FULL_MASK, is_col && pos == k)) - 1;
+			// makeHouseholderInPlace on this lane's column tail (only the pivot lane's result is used)
+			double tau_l = 0;
+			{
+				double c0 = a[k], tail_sq = 0;
+#pragma unroll
+				for(int r = k + 1; r < ROWS; ++r) tail_sq += a[r] * a[r];
+				if(lane == piv_lane){
+					double beta;
+					if(tail_sq <= DBL_MIN){
+						tau_l = 0; beta = c0;
+#pragma unroll
+						for(int r = k + 1; r < ROWS; ++r) a[r] = 0;
+					} else{
+						beta = sqrt(c0 * c0 + tail_sq);
+						if(c0 >= 0) beta = -beta;
+#pragma unroll
+						for(int r = k + 1; r < ROWS; ++r) a[r] = a[r] / (c0 - beta);
+						tau_l = (beta - c0) / beta;
+					}
+					a[k] = beta;
+				}
+			}
+			const double tk = __shfl_sync(FULL_MASK, tau_l, piv_lane);
+			tau[k] = tk;
+			double v[ROWS];
+#pragma unroll
+			for(int r = k + 1; r < ROWS; ++r) v[r] = __shfl_sync(FULL_MASK, a[r], piv_lane);
+			// applyHouseholderOnTheLeft to the remaining columns (and the rhs while k < nonzero_pivots)
+			const bool apply = (is_col && pos > k) || (is_rhs && k < nonzero_pivots);
+			if(apply){
+				if(ROWS - k == 1){
+					a[k] *= (1 - tk);
+				} else if(tk != 0){
+					double t = 0;
+#pragma unroll
+					for(int r = k + 1; r < ROWS; ++r) t += v[r] * a[r];
+					t += a[k];
+					a[k] -= tk * t;
+#pragma unroll
+					for(int r = k + 1; r < ROWS; ++r) a[r] -= tk * v[r] * t;
+				}
+			}
+			// column norm down-dating
+			if(is_col && pos > k && cnu != 0){
+				double t = fabs(a[k]) / cnu;
+				t = (1 + t)*(1 - t);
+				t = t < 0 ? 0 : t;
+				double rr = cnu / cnd;
+				double t2 = t * (rr * rr);
+				if(t2 <= norm_downdate_threshold){
+					double s = 0;
+#pragma unroll
+					for(int r = k + 1; r < ROWS; ++r) s += a[r] * a[r];
+					cnd = sqrt(s); cnu = cnd;
+				} else{
+					cnu *= sqrt(t);
+				}
+			}
+		}
+#pragma unroll
+		for(int i = 0; i < SIZE; ++i) lane_at_pos[i] = __ffs(__ballot_sync(FULL_MASK, is_col && pos == i)) - 1;
+	}
+
+	// back-substitution on the rhs lane, then x[perm[i]] = c[i]: returns x[lane] on lanes < COLS
+	__device__ __forceinline__ double solve(int lane){
+		static_assert(ROWS == COLS, "solve() is written for the square systems of the LK loop");
+		const int np = nonzero_pivots;
+#pragma unroll
+		for(int i = SIZE - 1; i >= 0; --i){
+			double s = a[i];
+#pragma unroll
+			for(int j = i + 1; j < SIZE; ++j){
+				double rij = __shfl_sync(FULL_MASK, a[i], lane_at_pos[j]);
+				if(j < np) s -= rij * a[j];
+			}
+			double rii = __shfl_sync(FULL_MASK, a[i], lane_at_pos[i]);
+			if(lane == COLS && i < np) a[i] = s / rii;
+		}
+		double x = 0;
+#pragma unroll
+		for(int i = 0; i < SIZE; ++i){
+			double ci = __shfl_sync(FULL_MASK, a[i], COLS);
+			if(pos == i) x = (i < np) ? ci : 0.0;
+		}
+		return x;
+	}
+};
+
+// utils::computeHomographyDLT(in_corners, out_corners), warpUtils.cc:171-223: the null vector of the 8x9
+// constraint matrix taken as JacobiSVD(ComputeFullV).matrixV().col(8).  For a wide matrix Eigen's QR
+// preconditioner makes that column the last column of Q of the column-pivoted Householder QR of the
+// adjoint (9x8), untouched by the Jacobi sweeps; that is what is computed here, by one warp.
+// corners: x0..x3, y0..y3.  Result (uniform across the warp) is normalised by its last entry.
+__device__ __forceinline__ Mat3 warp_homography_dlt(const double *in_c, const double *out_c, int lane){
+	WarpColPivQR<9, 8> qr;
+	{
+		const int i = (lane & 7) >> 1;
+		const double ix = in_c[i], iy = in_c[4 + i], ox = out_c[i], oy = out_c[4 + i];
+		if((lane & 1) == 0){
+			qr.a[0] = 0; qr.a[1] = 0; qr.a[2] = 0; qr.a[3] = -ix; qr.a[4] = -iy; qr.a[5] = -1;
+			qr.a[6] = oy*ix; qr.a[7] = oy*iy; qr.a[8] = oy;
+		} else{
+			qr.a[0] = ix; qr.a[1] = iy; qr.a[2] = 1; qr.a[3] = 0; qr.a[4] = 0; qr.a[5] = 0;
+			qr.a[6] = -ox*ix; qr.a[7] = -ox*iy; qr.a[8] = -ox;
+		}
+	}
+	// JacobiSVD::compute scales by the largest absolute coefficient first
+	double scale = 0;
+#pragma unroll
+	for(int r = 0; r < 9; ++r) scale = fmax(scale, fabs(qr.a[r]));
+	if(lane >= 8) scale = 0;
+#pragma unroll
+	for(int off = 4; off >= 1; off >>= 1) scale = fmax(scale, __shfl_xor_sync(FULL_MASK, scale, off));
+	scale = __shfl_sync(FULL_MASK, scale, 0);
+	if(scale == 0) scale = 1;
+#pragma unroll
+	for(int r = 0; r < 9; ++r) qr.a[r] = qr.a[r] / scale;
+	qr.factor(lane, false);
+	// Q e_9 = H_0 ... H_7 e_9
+	double h[9];
+#pragma unroll
+	for(int r = 0; r < 9; ++r) h[r] = 0;
+	h[8] = 1;
+#pragma unroll
+	for(int k = 7; k >= 0; --k){
+		double v[9];
+#pragma unroll
+		for(int r = k + 1; r < 9; ++r) v[r] = __shfl_sync(FULL_MASK, qr.a[r], qr.lane_at_pos[k]);
+		const double tk = qr.tau[k];
+		if(tk != 0){
+			double t = 0;
+#pragma unroll
+			for(int r = k + 1; r < 9; ++r) t += v[r] * h[r];
+			t += h[k];
+			h[k] -= tk * t;
+#pragma unroll
+			for(int r = k + 1; r < 9; ++r) h[r] -= tk * v[r] * t;
+		}
+	}
+	Mat3 H;
+#pragma unroll
+	for(int r = 0; r < 9; ++r) H.m[r] = h[r] / h[8];
+	return H;
+}
+
+} // namespace mtfb

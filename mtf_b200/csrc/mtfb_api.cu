@@ -1,0 +1,406 @@
+// mtfb_api.cu -- the extern "C" boundary (include/mtf_b200.h): context, device buffers, launches.
+// Host code only; no arithmetic of the path lives here except the LinSpaced grid of
+// utils::getNormUnitSquarePts (Utilities/src/warpUtils.cc:15-33), which is per-context, not per-pixel.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "lk_kernels.cuh"
+
+using namespace mtfb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+mtfb_status fail(mtfb_status st, const char *fmt, ...){
+	char buf[512];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+	g_last_error = buf;
+	return st;
+}
+#define CUDA_TRY(expr) do{ cudaError_t e_ = (expr); if(e_ != cudaSuccess) \
+	return fail(e_ == cudaErrorMemoryAllocation ? MTFB_ERR_NO_MEMORY : MTFB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); }while(0)
+
+// DenseBase::LinSpaced(size, low, high), Eigen 3.3 linspaced_op_impl<double, false>
+void lin_spaced(std::vector<double> &out, int size, double low, double high){
+	out.resize(size);
+	int size1 = size == 1 ? 1 : size - 1;
+	double step = size == 1 ? 0.0 : (high - low) / double(size - 1);
+	bool flip = std::fabs(high) < std::fabs(low);
+	for(int i = 0; i < size; ++i){
+		if(flip){ out[i] = (i == 0) ? low : (high - (size1 - i)*step); }
+		else{ out[i] = (i == size1) ? high : (low + i*step); }
+	}
+}
+
+} // namespace
+
+struct mtfb_ctx {
+	mtfb_params prm;
+	int S, N, P, threads;
+	cudaStream_t own_stream, stream;
+	DevBatch b;
+	// owned device memory
+	float *d_img_own; size_t img_capacity;      // elements
+	double *d_grid;                             // xv | yv | norm_corners
+	double *d_patch;                            // all per-patch fp64 arrays in one allocation
+	int *d_ints;                                // n_iters | status
+	double *d_corners_in;                       // staging for initialize()/set_region()
+	mtfb_iter_log *d_log;
+	double *d_scratch; size_t scratch_bytes;    // getters / pf
+	bool have_image, initialized;
+	long launches;
+};
+
+extern "C" {
+
+const char *mtfb_last_error(void){ return g_last_error.c_str(); }
+const char *mtfb_version(void){ return "mtf_b200 0.1 (sm_100a)"; }
+long mtfb_launch_count(const mtfb_ctx *ctx){ return ctx ? ctx->launches : 0; }
+int mtfb_state_size(const mtfb_ctx *ctx){ return ctx ? ctx->S : 0; }
+
+void mtfb_default_params(mtfb_params *p){
+	// shipped configuration: Config/mtf.cfg:14,24 (max_iters 30, epsilon 1e-4), Config/modules.cfg
+	// ({esm,fc,ic}_chained_warp 1, mi_n_bins / pre_seed as parameters.h:344-346), LM off (parameters.h:176)
+	std::memset(p, 0, sizeof(*p));
+	p->am = MTFB_AM_SSD; p->ssm = MTFB_SSM_HOMOGRAPHY; p->sm = MTFB_SM_FCLK;
+	p->resx = 50; p->resy = 50; p->n_patches = 1;
+	p->max_iters = 30; p->epsilon = 1e-4;
+	p->hess_type = MTFB_LK_HESS_CURRENT_SELF; p->jac_type = MTFB_ESM_JAC_DIFF_OF_JACS;
+	p->chained_warp = 1; p->leven_marq = 0; p->lm_delta_init = 0.01; p->lm_delta_update = 10;
+	p->nt_semantics = 1; p->grad_eps = 1e-8; p->hom_normalized_init = 0;
+	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1;
+	p->device = 0; p->threads_per_patch = 0;
+}
+
+mtfb_status mtfb_destroy(mtfb_ctx *c){
+	if(!c) return MTFB_OK;
+	cudaSetDevice(c->prm.device);
+	if(c->own_stream) cudaStreamSynchronize(c->own_stream);
+	cudaFree(c->d_img_own); cudaFree(c->d_grid); cudaFree(c->d_patch); cudaFree(c->d_ints);
+	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch);
+	if(c->own_stream) cudaStreamDestroy(c->own_stream);
+	delete c;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
+	if(!p || !out) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: null argument");
+	*out = nullptr;
+	if(p->resx < 2 || p->resy < 2 || p->n_patches < 1 || p->max_iters < 1)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: resx/resy >= 2, n_patches >= 1, max_iters >= 1 required");
+	if(p->sm != MTFB_SM_PF && !combo_supported(p->am, p->ssm, p->sm))
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: (am %d, ssm %d, sm %d) is not implemented", p->am, p->ssm, p->sm);
+	if(p->sm == MTFB_SM_PF && !(p->am == MTFB_AM_SSD && (p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE)))
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: PF evaluation is implemented for SSD only");
+	if(!p->chained_warp)
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: chained_warp = 0 (getWarpedImgGrad path) is not implemented");
+	if(p->hom_normalized_init)
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: hom_normalized_init = 1 is not implemented");
+	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
+	int threads = p->threads_per_patch ? p->threads_per_patch : 128;
+	if(threads != 64 && threads != 128 && threads != 256)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: threads_per_patch must be 0, 64, 128 or 256");
+	int n_dev = 0;
+	if(cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+		return fail(MTFB_ERR_CUDA, "mtfb_create: no CUDA device visible (this library has no CPU path)");
+	if(p->device < 0 || p->device >= n_dev) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: device %d of %d", p->device, n_dev);
+	CUDA_TRY(cudaSetDevice(p->device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, p->device));
+	if(prop.major != 10) return fail(MTFB_ERR_CUDA, "mtfb_create: built for sm_100a, device is sm_%d%d", prop.major, prop.minor);
+
+	mtfb_ctx *c = new (std::nothrow) mtfb_ctx();
+	if(!c) return fail(MTFB_ERR_NO_MEMORY, "mtfb_create: out of host memory");
+	std::memset(static_cast<void*>(c), 0, sizeof(*c));
+	c->prm = *p; c->threads = threads;
+	c->S = p->ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6;
+	c->N = p->resx * p->resy; c->P = p->n_patches;
+	const int S = c->S, N = c->N, P = c->P;
+	mtfb_status st = MTFB_OK;
+	do{
+		if(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+		c->stream = c->own_stream;
+		// grid: Homography uses the unit square (Homography.cc:32-48 -> ProjectiveBase.cc:9-18), Affine a
+		// pixel-scaled square [1 - res/2, res/2] (Affine.cc:53-56)
+		std::vector<double> xv, yv;
+		double min_x = -0.5, min_y = -0.5, max_x = 0.5, max_y = 0.5;
+		if(p->ssm == MTFB_SSM_AFFINE){ min_x = 1 - p->resx / 2.0; min_y = 1 - p->resy / 2.0; max_x = p->resx / 2.0; max_y = p->resy / 2.0; }
+		lin_spaced(xv, p->resx, min_x, max_x);
+		lin_spaced(yv, p->resy, min_y, max_y);
+		std::vector<double> grid(xv); grid.insert(grid.end(), yv.begin(), yv.end());
+		const double nc[8] = { min_x, max_x, max_x, min_x, min_y, min_y, max_y, max_y };
+		grid.insert(grid.end(), nc, nc + 8);
+		if(cudaMalloc(&c->d_grid, grid.size()*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+		if(cudaMemcpy(c->d_grid, grid.data(), grid.size()*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+		// per-patch arrays
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1;
+		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+		if(cudaMemset(c->d_ints, 0, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+		if(cudaMalloc(&c->d_corners_in, 8 * (size_t)P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+		DevBatch &b = c->b;
+		b.P = P; b.N = N; b.resx = p->resx; b.resy = p->resy;
+		b.xv = c->d_grid; b.yv = c->d_grid + p->resx; b.norm_corners = c->d_grid + p->resx + p->resy;
+		double *q = c->d_patch;
+		b.dlt = q; q += 9 * (size_t)P;
+		b.warp = q; q += 9 * (size_t)P;
+		b.state = q; q += (size_t)S*P;
+		b.corners = q; q += 8 * (size_t)P;
+		b.init_corners = q; q += 8 * (size_t)P;
+		b.Hinit = q; q += 64 * (size_t)P;
+		b.f = q; q += (size_t)P;
+		b.I0 = q; q += (size_t)N*P;
+		b.G0 = q; q += 2 * (size_t)N*P;
+		b.n_iters = c->d_ints; b.status = c->d_ints + P;
+		b.log = nullptr; b.log_slots = 0;
+		b.max_iters = p->max_iters; b.hess_type = p->hess_type; b.jac_type = p->jac_type;
+		b.leven_marq = p->leven_marq; b.nt_semantics = p->nt_semantics;
+		b.epsilon = p->epsilon; b.lm_delta_init = p->lm_delta_init; b.lm_delta_update = p->lm_delta_update;
+		b.grad_eps = p->grad_eps;
+		b.pix_mult = 1; b.pix_add = 0;
+		b.grad_mult = b.pix_mult / (2 * p->grad_eps);
+		b.img.data = nullptr; b.img.h = b.img.w = b.img.pitch = 0;
+	} while(0);
+	if(st != MTFB_OK){
+		cudaError_t e = cudaGetLastError();
+		fail(st, "mtfb_create: device allocation failed: %s", cudaGetErrorString(e));
+		std::string keep = g_last_error;
+		mtfb_destroy(c);
+		g_last_error = keep;
+		return st;
+	}
+	*out = c;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_set_stream(mtfb_ctx *c, void *cuda_stream){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_stream: null context");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->stream = static_cast<cudaStream_t>(cuda_stream);
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_synchronize(mtfb_ctx *c){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_synchronize: null context");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int row_stride){
+	if(!c || !host_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image: null argument");
+	if(h < 2 || w < 2 || row_stride < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image: bad geometry %d x %d stride %d", h, w, row_stride);
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const int pitch = (w + 31) & ~31;            // 128-byte rows
+	const size_t need = (size_t)pitch*h;
+	if(need > c->img_capacity){
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_img_own); c->d_img_own = nullptr; c->img_capacity = 0;
+		CUDA_TRY(cudaMalloc(&c->d_img_own, need*sizeof(float)));
+		c->img_capacity = need;
+	}
+	CUDA_TRY(cudaMemcpy2DAsync(c->d_img_own, (size_t)pitch*sizeof(float), host_img, (size_t)row_stride*sizeof(float),
+		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->stream));
+	c->b.img.data = c->d_img_own; c->b.img.h = h; c->b.img.w = w; c->b.img.pitch = pitch;
+	c->have_image = true;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_set_image_device(mtfb_ctx *c, const float *dev_img, int h, int w, int pitch){
+	if(!c || !dev_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: null argument");
+	if(h < 2 || w < 2 || pitch < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: bad geometry %d x %d pitch %d", h, w, pitch);
+	c->b.img.data = dev_img; c->b.img.h = h; c->b.img.w = w; c->b.img.pitch = pitch;
+	c->have_image = true;
+	return MTFB_OK;
+}
+
+static mtfb_status upload_corners(mtfb_ctx *c, const double *corners, const char *who){
+	if(!c || !corners) return fail(MTFB_ERR_INVALID_ARG, "%s: null argument", who);
+	if(!c->have_image) return fail(MTFB_ERR_LOGIC, "%s: setImage has not been called", who);
+	for(size_t i = 0; i < 8 * (size_t)c->P; ++i)
+		if(!std::isfinite(corners[i])) return fail(MTFB_ERR_INVALID_ARG, "%s: non-finite corner coordinate in patch %zu", who, i / 8);
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaMemcpyAsync(c->d_corners_in, corners, 8 * (size_t)c->P*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	// the host buffer may be pageable: wait, so that the caller can reuse it (the copy is 64 B per patch)
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
+	mtfb_status st = upload_corners(c, corners, "mtfb_initialize");
+	if(st != MTFB_OK) return st;
+	CUDA_TRY(launch_init(c->prm.am, c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
+	++c->launches;
+	c->initialized = true;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
+	if(c && !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_set_region: initialize has not been called");
+	if(c){
+		const bool ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) ||
+			(c->prm.sm == MTFB_SM_FCLK && c->prm.hess_type != MTFB_LK_HESS_INITIAL_SELF);
+		if(!ssm_only) return fail(MTFB_ERR_NOT_SUPPORTED,
+			"mtfb_set_region: only the SSM-only variants (FCLK with a current Hessian, ICLK, PF) are implemented");
+	}
+	mtfb_status st = upload_corners(c, corners, "mtfb_set_region");
+	if(st != MTFB_OK) return st;
+	CUDA_TRY(launch_set_region(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->b, c->d_corners_in, c->stream));
+	++c->launches;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_update(mtfb_ctx *c){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_update: null context");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_update: initialize has not been called");
+	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
+	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->b, c->stream));
+	++c->launches;
+	return MTFB_OK;
+}
+
+static mtfb_status ensure_scratch(mtfb_ctx *c, size_t bytes){
+	if(bytes <= c->scratch_bytes) return MTFB_OK;
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_bytes = 0;
+	CUDA_TRY(cudaMalloc(&c->d_scratch, bytes));
+	c->scratch_bytes = bytes;
+	return MTFB_OK;
+}
+
+static mtfb_status d2h(mtfb_ctx *c, void *dst, const void *src, size_t bytes){
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_enable_iter_log(mtfb_ctx *c, int n_slots){
+	if(!c || n_slots < 0) return fail(MTFB_ERR_INVALID_ARG, "mtfb_enable_iter_log: bad argument");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_log); c->d_log = nullptr; c->b.log = nullptr; c->b.log_slots = 0;
+	if(n_slots > 0){
+		CUDA_TRY(cudaMalloc(&c->d_log, sizeof(mtfb_iter_log)*(size_t)c->P*n_slots));
+		CUDA_TRY(cudaMemset(c->d_log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*n_slots));
+		c->b.log = c->d_log; c->b.log_slots = n_slots;
+	}
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_get_iter_log(mtfb_ctx *c, mtfb_iter_log *out){
+	if(!c || !out) return fail(MTFB_ERR_INVALID_ARG, "mtfb_get_iter_log: null argument");
+	if(!c->b.log) return fail(MTFB_ERR_LOGIC, "mtfb_get_iter_log: no iteration log attached");
+	return d2h(c, out, c->b.log, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots);
+}
+
+mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, double *similarity, double *state_update){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_iterate_once: null context");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_iterate_once: initialize has not been called");
+	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_iterate_once: not a Gauss-Newton context");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const int S = c->S, P = c->P;
+	mtfb_status st = ensure_scratch(c, sizeof(mtfb_iter_log)*(size_t)P);
+	if(st != MTFB_OK) return st;
+	DevBatch b = c->b;
+	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
+	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
+	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
+	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, b, c->stream));
+	++c->launches;
+	std::vector<mtfb_iter_log> host(P);
+	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);
+	if(st != MTFB_OK) return st;
+	for(int p = 0; p < P; ++p){
+		if(jacobian) std::memcpy(jacobian + (size_t)p*S, host[p].jacobian, S*sizeof(double));
+		if(hessian) std::memcpy(hessian + (size_t)p*S*S, host[p].hessian, S*S*sizeof(double));
+		if(similarity) similarity[p] = host[p].f;
+		if(state_update) std::memcpy(state_update + (size_t)p*S, host[p].state_update, S*sizeof(double));
+	}
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_pf_evaluate(mtfb_ctx *c, const double *, int, double *, double *){
+	(void)c;
+	return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate: not implemented yet");
+}
+mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *c, const double *, int, double *, double *){
+	(void)c;
+	return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate_device: not implemented yet");
+}
+
+#define GETTER_PRELUDE(name) \
+	if(!c || !out) return fail(MTFB_ERR_INVALID_ARG, name ": null argument"); \
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, name ": initialize has not been called");
+
+mtfb_status mtfb_get_corners(mtfb_ctx *c, double *out){ GETTER_PRELUDE("mtfb_get_corners") return d2h(c, out, c->b.corners, 8 * (size_t)c->P*sizeof(double)); }
+mtfb_status mtfb_get_state(mtfb_ctx *c, double *out){ GETTER_PRELUDE("mtfb_get_state") return d2h(c, out, c->b.state, (size_t)c->S*c->P*sizeof(double)); }
+mtfb_status mtfb_get_n_iters(mtfb_ctx *c, int *out){ GETTER_PRELUDE("mtfb_get_n_iters") return d2h(c, out, c->b.n_iters, (size_t)c->P*sizeof(int)); }
+mtfb_status mtfb_get_similarity(mtfb_ctx *c, double *out){ GETTER_PRELUDE("mtfb_get_similarity") return d2h(c, out, c->b.f, (size_t)c->P*sizeof(double)); }
+mtfb_status mtfb_get_patch_status(mtfb_ctx *c, int *out){ GETTER_PRELUDE("mtfb_get_patch_status") return d2h(c, out, c->b.status, (size_t)c->P*sizeof(int)); }
+mtfb_status mtfb_get_init_warp(mtfb_ctx *c, double *out){ GETTER_PRELUDE("mtfb_get_init_warp") return d2h(c, out, c->b.dlt, 9 * (size_t)c->P*sizeof(double)); }
+mtfb_status mtfb_get_init_pix_vals(mtfb_ctx *c, double *out){ GETTER_PRELUDE("mtfb_get_init_pix_vals") return d2h(c, out, c->b.I0, (size_t)c->N*c->P*sizeof(double)); }
+
+mtfb_status mtfb_get_curr_stage(mtfb_ctx *c, double *pts, double *pix_vals, double *pix_grad, double *pix_jac){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_get_curr_stage: null context");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_get_curr_stage: initialize has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t N = c->N, P = c->P, S = c->S;
+	const size_t n_pts = pts ? 2 * N*P : 0, n_val = pix_vals ? N*P : 0, n_grad = pix_grad ? 2 * N*P : 0, n_jac = pix_jac ? S*N*P : 0;
+	mtfb_status st = ensure_scratch(c, (n_pts + n_val + n_grad + n_jac + 1)*sizeof(double));
+	if(st != MTFB_OK) return st;
+	StageTaps t;
+	double *q = c->d_scratch;
+	t.pts = pts ? q : nullptr; q += n_pts;
+	t.pix_vals = pix_vals ? q : nullptr; q += n_val;
+	t.pix_grad = pix_grad ? q : nullptr; q += n_grad;
+	t.pix_jac = pix_jac ? q : nullptr;
+	CUDA_TRY(launch_stage(c->prm.am, c->prm.ssm, c->threads, c->b, t, c->stream));
+	++c->launches;
+	if(pts) CUDA_TRY(cudaMemcpyAsync(pts, t.pts, n_pts*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(pix_vals) CUDA_TRY(cudaMemcpyAsync(pix_vals, t.pix_vals, n_val*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(pix_grad) CUDA_TRY(cudaMemcpyAsync(pix_grad, t.pix_grad, n_grad*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(pix_jac) CUDA_TRY(cudaMemcpyAsync(pix_jac, t.pix_jac, n_jac*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_get_init_pts(mtfb_ctx *c, double *out){
+	GETTER_PRELUDE("mtfb_get_init_pts")
+	// init_pts are not stored: they are the points of the identity warp (recomputed from the DLT every pass)
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t N = c->N, P = c->P;
+	mtfb_status st = ensure_scratch(c, (2 * N*P + 9 * P)*sizeof(double));
+	if(st != MTFB_OK) return st;
+	// temporarily evaluate the stage kernel with curr_warp = identity
+	DevBatch b = c->b;
+	double *d_pts = c->d_scratch, *d_eye = c->d_scratch + 2 * N*P;
+	std::vector<double> eye(9 * P, 0.0);
+	for(size_t p = 0; p < P; ++p){ eye[9 * p] = eye[9 * p + 4] = eye[9 * p + 8] = 1; }
+	CUDA_TRY(cudaMemcpyAsync(d_eye, eye.data(), eye.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	b.warp = d_eye;
+	StageTaps t = { d_pts, nullptr, nullptr, nullptr };
+	CUDA_TRY(launch_stage(c->prm.am, c->prm.ssm, c->threads, b, t, c->stream));
+	++c->launches;
+	return d2h(c, out, d_pts, 2 * N*P*sizeof(double));
+}
+
+mtfb_status mtfb_device_results(mtfb_ctx *c, double **d_corners, double **d_state, int **d_n_iters){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_device_results: null context");
+	if(d_corners) *d_corners = c->b.corners;
+	if(d_state) *d_state = c->b.state;
+	if(d_n_iters) *d_n_iters = c->b.n_iters;
+	return MTFB_OK;
+}
+
+} // extern "C"

@@ -82,6 +82,47 @@ static void getImgGrad(double *img_grad, const float *img, const double *pts, do
 		img_grad[n_pix + pix_id] = (pix_val_inc - pix_val_dec)*grad_mult_factor;
 	}
 }
+// NOT a reference function (grad_mode = 1): getImgGrad above with the difference quotient replaced by the
+// cell's slope wherever x - eps and x + eps fall into the same pixel cell as x.  There the interpolant is
+// linear, so getImgGrad's quotient equals that slope up to its own rounding noise (~1e-5 relative); in every
+// other case (the samples straddle a pixel column or row -- always so at integer coordinates -- or one of
+// them leaves the image) the reference's quotient is evaluated literally.  The product computes its
+// gradients this way, so tests compare it (i) against this mode tightly and (ii) against the reference
+// mode within the quotient's noise.
+static void getImgGradAnalytic(double *img_grad, const float *img, const double *pts, double grad_eps,
+	unsigned int n_pix, unsigned int h, unsigned int w, double pix_mult_factor){
+	double grad_mult_factor = pix_mult_factor / (2 * grad_eps);
+	for(unsigned int pix_id = 0; pix_id < n_pix; ++pix_id){
+		double x = pts[2 * pix_id], y = pts[2 * pix_id + 1];
+		bool same_cell_x = false, same_cell_y = false;
+		double slope_x = 0, slope_y = 0;
+		if(!checkOverflow(x, y, h, w)){
+			int lx = static_cast<int>(x), ly = static_cast<int>(y);
+			double dx = x - lx, dy = y - ly;
+			int ux = dx == 0 ? lx : lx + 1, uy = dy == 0 ? ly : ly + 1;
+			if(ux < (int)w && uy < (int)h){
+				double p00 = img[(size_t)ly*w + lx], p01 = img[(size_t)ly*w + ux];
+				double p10 = img[(size_t)uy*w + lx], p11 = img[(size_t)uy*w + ux];
+				same_cell_x = (x - grad_eps >= lx) && (x + grad_eps < lx + 1);
+				same_cell_y = (y - grad_eps >= ly) && (y + grad_eps < ly + 1);
+				slope_x = ((1 - dy)*(p01 - p00) + dy*(p11 - p10)) * pix_mult_factor;
+				slope_y = ((1 - dx)*(p10 - p00) + dx*(p11 - p01)) * pix_mult_factor;
+			}
+		}
+		if(same_cell_x){ img_grad[pix_id] = slope_x; }
+		else{
+			double pix_val_inc = getPixVal(img, x + grad_eps, y, h, w);
+			double pix_val_dec = getPixVal(img, x - grad_eps, y, h, w);
+			img_grad[pix_id] = (pix_val_inc - pix_val_dec)*grad_mult_factor;
+		}
+		if(same_cell_y){ img_grad[n_pix + pix_id] = slope_y; }
+		else{
+			double pix_val_inc = getPixVal(img, x, y + grad_eps, h, w);
+			double pix_val_dec = getPixVal(img, x, y - grad_eps, h, w);
+			img_grad[n_pix + pix_id] = (pix_val_inc - pix_val_dec)*grad_mult_factor;
+		}
+	}
+}
 // utils::getWarpedImgGrad                                                      imgUtils.cc:177-202
 static void getWarpedImgGrad(double *warped_img_grad, const float *img, const double *wop /*8xN*/,
 	double grad_eps, unsigned int n_pix, unsigned int h, unsigned int w, double pix_mult_factor){
@@ -577,7 +618,7 @@ static inline double bSpl3Hess(double x){
 
 struct AM{
 	int type, resx, resy, n_pix, patch_size;
-	double grad_eps, pix_norm_mult, pix_norm_add, likelihood_alpha;
+	double grad_eps, pix_norm_mult, pix_norm_add, likelihood_alpha; int grad_mode;
 	const float *img; unsigned int img_height, img_width;
 	vec I0, It, dI0_dx, dIt_dx, df_dI0, df_dIt;
 	double f;
@@ -597,7 +638,7 @@ struct AM{
 
 	AM(const orc_params &p) : type(p.am), resx(p.resx), resy(p.resy), n_pix(p.resx*p.resy),
 		patch_size(p.resx*p.resy), grad_eps(p.grad_eps), pix_norm_mult(1), pix_norm_add(0),
-		likelihood_alpha(p.likelihood_alpha), img(nullptr), img_height(0), img_width(0), f(0),
+		likelihood_alpha(p.likelihood_alpha), grad_mode(p.grad_mode), img(nullptr), img_height(0), img_width(0), f(0),
 		init_pix_vals(false), init_pix_grad(false), init_sim(false), init_grad(false), init_hess(false),
 		n_bins(p.mi_n_bins), pre_seed(p.mi_pre_seed), pou(p.mi_pou != 0){
 		if(type == ORC_AM_MI){                                                 // MI::MI AM/src/MI.cc:55-123
@@ -626,7 +667,8 @@ struct AM{
 	// ImageBase::initializePixGrad(Matrix2Xd) ImageBase.cc:101-132
 	void initializePixGrad(const double *init_pts){
 		if(!init_pix_grad){ dI0_dx.resize(2 * (size_t)patch_size); dIt_dx.resize(2 * (size_t)patch_size); }
-		getImgGrad(dI0_dx.data(), img, init_pts, grad_eps, n_pix, img_height, img_width, pix_norm_mult);
+		if(grad_mode) getImgGradAnalytic(dI0_dx.data(), img, init_pts, grad_eps, n_pix, img_height, img_width, pix_norm_mult);
+		else getImgGrad(dI0_dx.data(), img, init_pts, grad_eps, n_pix, img_height, img_width, pix_norm_mult);
 		if(!init_pix_grad){ dIt_dx = dI0_dx; init_pix_grad = true; }
 	}
 	// ImageBase::initializePixGrad(Matrix8Xd) ImageBase.cc:134-166
@@ -641,7 +683,8 @@ struct AM{
 	}
 	// ImageBase::updatePixGrad(Matrix2Xd) ImageBase.cc:292-314
 	void updatePixGrad(const double *curr_pts){
-		getImgGrad(dIt_dx.data(), img, curr_pts, grad_eps, n_pix, img_height, img_width, pix_norm_mult);
+		if(grad_mode) getImgGradAnalytic(dIt_dx.data(), img, curr_pts, grad_eps, n_pix, img_height, img_width, pix_norm_mult);
+		else getImgGrad(dIt_dx.data(), img, curr_pts, grad_eps, n_pix, img_height, img_width, pix_norm_mult);
 	}
 	// ImageBase::updatePixGrad(Matrix8Xd) ImageBase.cc:340-362
 	void updatePixGradWarped(const double *warped_offset_pts){
@@ -1441,7 +1484,7 @@ void orc_default_params(orc_params *p){
 	p->hess_type = ORC_LK_HESS_CURRENT_SELF; p->jac_type = ORC_ESM_JAC_DIFF_OF_JACS;
 	p->chained_warp = 1; p->leven_marq = 0; p->lm_delta_init = 0.01; p->lm_delta_update = 10;
 	p->nt_semantics = 1; p->grad_eps = 1e-8; p->hom_normalized_init = 0;
-	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1;
+	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1; p->grad_mode = 0;
 }
 orc_tracker *orc_create(const orc_params *p){ return new orc_tracker(*p); }
 void orc_destroy(orc_tracker *t){ delete t; }
@@ -1483,6 +1526,9 @@ void orc_get_pix_vals(const float *img, int h, int w, const double *pts, int n, 
 }
 void orc_get_img_grad(const float *img, int h, int w, const double *pts, int n, double grad_eps, double pix_mult, double *o){
 	getImgGrad(o, img, pts, grad_eps, n, h, w, pix_mult);
+}
+void orc_get_img_grad_analytic(const float *img, int h, int w, const double *pts, int n, double grad_eps, double pix_mult, double *o){
+	getImgGradAnalytic(o, img, pts, grad_eps, n, h, w, pix_mult);
 }
 void orc_homography_dlt(const double *in_c, const double *out_c, double *H9){
 	Mat3 H = computeHomographyDLT(in_c, out_c); std::memcpy(H9, H.m, sizeof(H.m));

@@ -53,6 +53,8 @@ typedef struct orc_params {
 	double mi_pre_seed;
 	int mi_pou;
 	double likelihood_alpha;
+	int grad_mode;           /* 0: reference finite difference (imgUtils.cc:233-254); 1: its eps -> 0 limit,
+	                            evaluated analytically (not a reference mode; see mtf_oracle.cpp) */
 } orc_params;
 
 typedef struct orc_tracker orc_tracker;
@@ -105,6 +107,8 @@ double orc_pix_val(const float *img, int h, int w, double x, double y);
 void orc_get_pix_vals(const float *img, int h, int w, const double *pts, int n,
 	double norm_mult, double norm_add, double *out);
 void orc_get_img_grad(const float *img, int h, int w, const double *pts, int n,
+	double grad_eps, double pix_mult, double *outN2);
+void orc_get_img_grad_analytic(const float *img, int h, int w, const double *pts, int n,
 	double grad_eps, double pix_mult, double *outN2);
 void orc_homography_dlt(const double *in_corners, const double *out_corners, double *H9);
 void orc_colpiv_qr_solve(const double *A, const double *b, int n, double *x);

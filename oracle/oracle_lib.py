@@ -5,7 +5,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_ORACLE_DIR = _HERE
 _LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "libmtf_oracle.so")
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
@@ -22,7 +22,7 @@ class OrcParams(C.Structure):
                 ("nt_semantics", C.c_int), ("grad_eps", C.c_double),
                 ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
                 ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
-                ("likelihood_alpha", C.c_double)]
+                ("likelihood_alpha", C.c_double), ("grad_mode", C.c_int)]
 
 
 class OrcIterLog(C.Structure):
@@ -71,6 +71,7 @@ def lib():
     L.orc_pix_val.argtypes = [fp, C.c_int, C.c_int, C.c_double, C.c_double]; L.orc_pix_val.restype = C.c_double
     L.orc_get_pix_vals.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_get_img_grad.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
+    L.orc_get_img_grad_analytic.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_homography_dlt.argtypes = [dp, dp, dp]
     L.orc_colpiv_qr_solve.argtypes = [dp, dp, C.c_int, dp]
     L.orc_norm_unit_square_pts.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
@@ -214,6 +215,14 @@ def img_grad(img, pts, grad_eps=1e-8, mult=1.0):
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     out = np.empty(2 * pts.shape[0])
     lib().orc_get_img_grad(_fp(img), img.shape[0], img.shape[1], _dp(pts), pts.shape[0], grad_eps, mult, _dp(out))
+    return out.reshape(2, -1).T
+
+
+def img_grad_analytic(img, pts, grad_eps=1e-8, mult=1.0):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.empty(2 * pts.shape[0])
+    lib().orc_get_img_grad_analytic(_fp(img), img.shape[0], img.shape[1], _dp(pts), pts.shape[0], grad_eps, mult, _dp(out))
     return out.reshape(2, -1).T
 
 

@@ -1,0 +1,234 @@
+"""GPU: the CUDA path through the C-ABI against the CPU oracle on the same seeded inputs.
+
+Tolerances (stated once, used everywhere below):
+  * warped points, sampling indices, pixel values, DLT warps  -> bit-exact (np.array_equal)
+  * image gradient / pixel Jacobian vs the oracle's same-cell-slope mode (grad_mode = 1) -> bit-exact
+  * vs the reference's finite-difference mode (grad_mode = 0) -> the difference quotient's own noise
+    (FD_RTOL / FD_ATOL, see test_host_math.py)
+  * f, J^T r, J^T J (sums over N pixels in a different order), state updates, corners -> SUM_RTOL relative
+    to the largest entry of the quantity in analytic mode; FD mode LOOP_ATOL on corners in pixels
+"""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+FD_RTOL, FD_ATOL = 2e-5, 5e-5
+SUM_RTOL = 1e-9        # fp64 sums of 2500 terms in another order + an 8x8 solve of condition ~1e6..1e9
+FIRST_RTOL = 1e-12     # identical inputs, sums of N products in another order
+LATER_RTOL = 1e-7      # inputs differ by the previous solves' rounding (state differs ~1e-10 px)
+CORNER_ATOL_EXACT = 1e-6   # px, analytic-gradient oracle, after up to 30 Gauss-Newton passes
+CORNER_ATOL_FD = 5e-3      # px, reference finite-difference oracle (epsilon = 1e-4 stops at ~1e-2 px steps)
+
+SMS = ["fclk", "esm", "iclk"]
+SSMS = ["homography", "affine"]
+
+
+def _gpu(am, ssm, sm, P, **kw):
+    from mtf_b200 import api
+    p = api.make_params(am, ssm, sm, n_patches=P, **kw)
+    return api.BatchTracker(p)
+
+
+def _oracle(am, ssm, sm, **kw):
+    return O.OracleTracker(O.make_params(am, ssm, sm, **kw))
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+@pytest.mark.parametrize("kind", ["axis", "quad"])
+def test_initialize_bit_exact(seq384, ssm, kind):
+    frames, _ = seq384
+    cs = common.patches(9, 49.0, 384, 384) if kind == "axis" else common.quad_patches(9, 384, 384)
+    g = _gpu("ssd", ssm, "fclk", len(cs))
+    g.initialize(cs, frames[0])
+    dlt, ipts, I0 = g.init_warp(), g.init_pts(), g.init_pix_vals()
+    pts, It, grad, jac = g.curr_stage()
+    for i, c in enumerate(cs):
+        o = _oracle("ssd", ssm, "esm", grad_mode=1)
+        o.set_image(frames[0]); o.initialize(c)
+        assert np.array_equal(dlt[i], o.init_warp())
+        assert np.array_equal(ipts[i], o.init_pts())
+        assert np.array_equal(pts[i], o.pts())
+        assert np.array_equal(I0[i], o.init_pix_vals())
+        assert np.array_equal(It[i], o.init_pix_vals())
+        assert np.array_equal(jac[i], o.init_pix_jacobian())
+    assert np.array_equal(g.getRegion(), cs)
+    assert (g.patch_status() == 0).all()
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+def test_stage_taps_vs_reference_fd(seq384, ssm):
+    """pixel values bit-exact, gradient / pixel Jacobian within the reference quotient's noise"""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(4, 49.0, 384, 384), common.quad_patches(4, 384, 384)])
+    g = _gpu("ssd", ssm, "fclk", len(cs))
+    g.initialize(cs, frames[0])
+    g.setImage(frames[1])
+    pts, It, grad, jac = g.curr_stage()
+    for i, c in enumerate(cs):
+        o = _oracle("ssd", ssm, "fclk", max_iters=1, epsilon=-1.0, grad_mode=0)
+        o.set_image(frames[0]); o.initialize(c)
+        o.set_image(frames[1]); o.update()
+        assert np.array_equal(It[i], o.curr_pix_vals())
+        gr = o.curr_pix_grad()
+        assert (np.abs(grad[i] - gr) <= FD_ATOL + FD_RTOL * np.abs(gr)).all()
+        Jr = o.curr_pix_jacobian()
+        assert (np.abs(jac[i] - Jr) <= 1e-4 * np.abs(Jr).max(axis=0)).all()
+
+
+@pytest.mark.parametrize("sm", SMS)
+@pytest.mark.parametrize("ssm", SSMS)
+def test_iteration_log_parity(seq384, sm, ssm):
+    """every Gauss-Newton pass of update(): f, Jacobian, Hessian, state update, corners, stop test"""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=11)])
+    g = _gpu("ssd", ssm, sm, len(cs))
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("ssd", ssm, sm, grad_mode=1)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs = g.iter_log()
+        n_it = g.n_iters()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert n_it[i] == o.n_iters == len(ol) == len(logs[i])
+            for k, (a, b) in enumerate(zip(logs[i], ol)):
+                # pass 0 of frame 1 starts from bit-identical state: only the summation order differs.
+                # Later passes start from states that differ by the conditioning of the previous solve
+                # (~1e-10 px), which f and J^T r see multiplied by the image gradient.
+                first = fr is frames[1] and k == 0
+                tol = FIRST_RTOL if first else LATER_RTOL
+                assert abs(a["f"] - b["f"]) <= tol * max(abs(b["f"]), 1.0)
+                assert _rel(a["jacobian"], b["jacobian"]) <= tol * 10
+                assert _rel(a["hessian"], b["hessian"]) <= tol
+                assert np.abs(a["corners"] - b["corners"]).max() <= CORNER_ATOL_EXACT
+                assert a["rejected"] == b["rejected"]
+        assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= CORNER_ATOL_EXACT
+        assert np.abs(g.state() - np.array([o.state() for o in orcs])).max() <= 1e-8
+        assert np.allclose(g.similarity(), [o.similarity for o in orcs], rtol=LATER_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("sm", SMS)
+@pytest.mark.parametrize("ssm", SSMS)
+@pytest.mark.parametrize("lm", [0, 1])
+def test_tracking_vs_reference_fd(seq384, sm, ssm, lm):
+    """whole-loop parity with the oracle in the reference's finite-difference mode + ground truth recovery"""
+    from mtf_b200 import synth
+    frames, warps = seq384
+    cs = np.concatenate([common.patches(6, 49.0, 384, 384), common.patches(6, 52.3, 384, 384, seed=5),
+                         common.quad_patches(4, 384, 384, seed=3)])
+    g = _gpu("ssd", ssm, sm, len(cs), leven_marq=lm)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("ssd", ssm, sm, grad_mode=0, leven_marq=lm)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for t in (1, 2, 3):
+        g.update(frames[t])
+        for o in orcs:
+            o.set_image(frames[t]); o.update()
+        oc = np.array([o.corners() for o in orcs])
+        gc = g.getRegion()
+        assert np.abs(gc - oc).max() <= CORNER_ATOL_FD
+        oi = np.array([o.n_iters for o in orcs])
+        assert (np.abs(g.n_iters() - oi) <= 1).all() and (g.n_iters() == oi).mean() >= 0.9
+        if ssm == "homography":
+            gt = synth.warp_corners(warps[t], cs)
+            assert np.abs(gc - gt).max() < 0.25          # the tracker actually tracks
+    assert (g.patch_status() == 0).all()
+
+
+@pytest.mark.parametrize("sm,hess", [("fclk", "initial_self"), ("fclk", "std"), ("iclk", "current_self"), ("iclk", "std"),
+                                     ("esm", "initial_self"), ("esm", "current_self"), ("esm", "original"),
+                                     ("esm", "sum_of_std"), ("esm", "std")])
+def test_hessian_variants(seq384, sm, hess):
+    from mtf_b200 import api
+    frames, _ = seq384
+    cs = common.patches(4, 52.3, 384, 384, seed=9)
+    table = api.ESM_HESS if sm == "esm" else api.LK_HESS
+    for jac in ([0, 1] if sm == "esm" else [1]):
+        g = _gpu("ssd", "homography", sm, len(cs), hess_type=table[hess], jac_type=jac)
+        g.enable_iter_log(30)
+        g.initialize(cs, frames[0])
+        g.update(frames[1])
+        logs = g.iter_log()
+        for i, c in enumerate(cs):
+            o = _oracle("ssd", "homography", sm, grad_mode=1, hess_type=table[hess], jac_type=jac)
+            o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+            ol = o.log()
+            assert len(ol) == len(logs[i])
+            for a, b in zip(logs[i], ol):
+                assert _rel(a["jacobian"], b["jacobian"]) <= LATER_RTOL * 10
+                assert _rel(a["hessian"], b["hessian"]) <= LATER_RTOL
+                assert np.abs(a["corners"] - b["corners"]).max() <= CORNER_ATOL_EXACT
+
+
+def test_iterate_once_and_templated_semantics(seq384):
+    frames, _ = seq384
+    cs = common.patches(5, 52.3, 384, 384, seed=2)
+    g = _gpu("ssd", "homography", "fclk", len(cs), leven_marq=1, nt_semantics=0)
+    g.initialize(cs, frames[0]); g.setImage(frames[1])
+    J, H, f, dp = g.iterate_once()
+    for i, c in enumerate(cs):
+        o = _oracle("ssd", "homography", "fclk", grad_mode=1, leven_marq=1, nt_semantics=0, max_iters=1)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        e = o.log()[0]
+        assert _rel(J[i], e["jacobian"]) <= SUM_RTOL * 10 and _rel(H[i], e["hessian"]) <= SUM_RTOL
+        assert _rel(dp[i], e["state_update"]) <= 1e-7
+    # full loops with the templated iteration counting (a rejected step consumes an iteration)
+    g2 = _gpu("ssd", "homography", "fclk", len(cs), leven_marq=1, nt_semantics=0, max_iters=8)
+    g2.initialize(cs, frames[0]); g2.update(frames[2])
+    for i, c in enumerate(cs):
+        o = _oracle("ssd", "homography", "fclk", grad_mode=1, leven_marq=1, nt_semantics=0, max_iters=8)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[2]); o.update()
+        assert g2.n_iters()[i] == o.n_iters
+        assert np.abs(g2.getRegion()[i] - o.corners()).max() <= CORNER_ATOL_EXACT
+
+
+def test_out_of_image_patch_is_survivable(seq384):
+    """a patch hanging over the border samples the constant 128 like the reference and must not crash the batch"""
+    frames, _ = seq384
+    cs = common.patches(3, 49.0, 384, 384)
+    cs[1] += np.array([[-cs[1][0].min() - 10.0], [0.0]])        # 10 px outside on the left
+    g = _gpu("ssd", "homography", "fclk", len(cs), max_iters=3)
+    g.initialize(cs, frames[0])
+    I0 = g.init_pix_vals()
+    o = _oracle("ssd", "homography", "fclk", grad_mode=1, max_iters=3)
+    o.set_image(frames[0]); o.initialize(cs[1])
+    assert np.array_equal(I0[1], o.init_pix_vals()) and (I0[1] == 128.0).any()
+    g.update(frames[1])
+    assert np.isfinite(g.getRegion()[[0, 2]]).all()
+
+
+def test_error_contract(seq384):
+    from mtf_b200 import api
+    frames, _ = seq384
+    g = _gpu("ssd", "homography", "fclk", 2)
+    with pytest.raises(api.MTFError) as e:
+        g.update()
+    assert e.value.type == "LogicError"
+    with pytest.raises(api.MTFError) as e:
+        g.initialize(common.patches(2, 49.0, 384, 384))
+    assert e.value.type == "LogicError"                       # no image yet
+    with pytest.raises(api.MTFError) as e:
+        _gpu("ssd", "homography", "fclk", 2, chained_warp=0)
+    assert e.value.type == "FunctonNotImplemented"
+    bad = common.patches(2, 49.0, 384, 384); bad[0, 0, 0] = np.nan
+    g.setImage(frames[0])
+    with pytest.raises(api.MTFError) as e:
+        g.initialize(bad)
+    assert e.value.type == "InvalidArgument"
