@@ -93,7 +93,16 @@ class ClockSampler(threading.Thread):
 
 def workload(seed_offset=0):
     from mtf_b200 import synth
-    frames, _ = synth.make_sequence(N_FRAMES, IMG, IMG, seed=1234, walk_seed=5678, sigma=1.0)
+    cache = "/tmp/mtfb_bench_frames_%d_%d.npy" % (N_FRAMES, IMG)        # synthesis takes a few seconds per process
+    try:
+        frames = list(np.load(cache))
+    except Exception:
+        frames, _ = synth.make_sequence(N_FRAMES, IMG, IMG, seed=1234, walk_seed=5678, sigma=1.0)
+        try:
+            np.save(cache + ".%d.npy" % os.getpid(), np.stack(frames))
+            os.replace(cache + ".%d.npy" % os.getpid(), cache)
+        except Exception:
+            pass
     corners = synth.make_patches(P_PER_GPU, 49.0, IMG, IMG, seed=42 + seed_offset)
     # ping-pong order keeps consecutive frames one random-walk step apart for any number of steps
     order = list(range(1, N_FRAMES)) + list(range(N_FRAMES - 2, -1, -1))
@@ -157,7 +166,7 @@ def run_ours(args):
     frames, corners, order = workload(seed_offset=rank)
     P = P_PER_GPU
     prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=local_rank,
-                          threads_per_patch=args.threads)
+                          threads_per_patch=args.threads, occupancy=args.occ)
     tr = api.BatchTracker(prm)
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
@@ -250,7 +259,7 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
                                % (P, ITERS, IMG, IMG),
-                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": tr.params.threads_per_patch or 128,
+                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": tr.params.threads_per_patch or 128, "occupancy": args.occ,
                    "collective": "all_gather of P x 8 corners per frame" if world > 1 else "none"},
         "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
@@ -284,6 +293,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--threads", type=int, default=0, help="threads per patch (0 = library default)")
+    ap.add_argument("--occ", type=int, default=0, help="occupancy knob of the update kernel (0, 1, 2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -43,7 +43,8 @@ class Params(C.Structure):
                 ("nt_semantics", C.c_int), ("grad_eps", C.c_double),
                 ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
                 ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
-                ("likelihood_alpha", C.c_double), ("device", C.c_int), ("threads_per_patch", C.c_int)]
+                ("likelihood_alpha", C.c_double), ("device", C.c_int), ("threads_per_patch", C.c_int),
+                ("occupancy", C.c_int)]
 
 
 class IterLog(C.Structure):

@@ -27,12 +27,23 @@ template<int S> struct AccLayout {
 	__host__ __device__ static constexpr int tri(int i, int j){ return i*S - i*(i - 1) / 2 + (j - i); }  // i <= j
 };
 
+// a CTA of one warp (T == 32: one warp tracks one patch) needs no block barrier
+template<int T> __device__ __forceinline__ void cta_sync(){
+	if(T == 32) __syncwarp(); else __syncthreads();
+}
+
 // CTA-wide sum of a per-thread accumulator vector; result in s_sum[0..CNT) after the call.
 template<int CNT, int T> __device__ __forceinline__ void block_reduce(double (&acc)[CNT], double *s_part /* [T/32][CNT] */,
 	double *s_sum){
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int idx[2];
 	warp_reduce_scatter<CNT>(acc, lane, idx);
+	if(T == 32){
+		if(idx[0] >= 0) s_sum[idx[0]] = acc[0];
+		if(idx[1] >= 0) s_sum[idx[1]] = acc[1];
+		__syncwarp();
+		return;
+	}
 	if(idx[0] >= 0) s_part[warp*CNT + idx[0]] = acc[0];
 	if(idx[1] >= 0) s_part[warp*CNT + idx[1]] = acc[1];
 	__syncthreads();
@@ -43,6 +54,12 @@ template<int CNT, int T> __device__ __forceinline__ void block_reduce(double (&a
 		s_sum[e] = s;
 	}
 	__syncthreads();
+}
+
+// resident CTAs per SM requested from the compiler: OCC 0 / 1 / 2 = about 8 / 12 / 16 warps per SM
+// (<= 255 / 168 / 128 registers per thread)
+__host__ __device__ constexpr int min_blocks(int T, int OCC){
+	return (OCC == 0 ? 8 : OCC == 1 ? 12 : 16) * 32 / T > 0 ? (OCC == 0 ? 8 : OCC == 1 ? 12 : 16) * 32 / T : 1;
 }
 
 struct PixIter {
@@ -77,7 +94,7 @@ __global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__
 		if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }
 		if(lane == 0){ b.f[p] = 0; b.n_iters[p] = 0; b.status[p] = 0; }
 	}
-	__syncthreads();
+	cta_sync<T>();
 	Mat3 dlt, W = mat3_identity();
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
@@ -114,8 +131,8 @@ __global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__
 // ------------------------------------------------------------------------------------------------
 // update(): the whole per-frame loop
 // ------------------------------------------------------------------------------------------------
-template<int AM, int SSM, int SM, int T>
-__global__ void __launch_bounds__(T) lk_update_kernel(DevBatch b){
+template<int AM, int SSM, int SM, int T, int OCC>
+__global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBatch b){
 	static_assert(AM == AM_SSD, "this kernel is the SSD instantiation");
 	constexpr int S = StateSize<SSM>::value;
 	typedef AccLayout<S> L;
@@ -129,7 +146,7 @@ __global__ void __launch_bounds__(T) lk_update_kernel(DevBatch b){
 	for(int i = 0; i < 9; ++i) dlt.m[i] = b.dlt[(size_t)p * 9 + i];
 	if(tid < 9) s_W[tid] = b.warp[(size_t)p * 9 + tid];
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
-	__syncthreads();
+	cta_sync<T>();
 	const double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
 	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(T) lk_update_kernel(DevBatch b){
 				if(lane == 0){ e->f = f; e->update_norm = upd_norm; e->rejected = rejected; e->valid = 1; }
 			}
 		}
-		__syncthreads();
+		cta_sync<T>();
 		const int ctrl = s_ctrl;
 		if(ctrl == CTRL_BREAK) break;
 		// nt::FCLK re-enters its while loop without counting a rejected step (NT/FCLK.cc:187,210);
@@ -376,6 +393,7 @@ bool combo_supported(int am, int ssm, int sm){
 
 template<int AM, int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
 	switch(threads){
+	case 32: lk_init_kernel<AM, SSM, 32><<<b.P, 32, 0, st>>>(b, d_corners); break;
 	case 64: lk_init_kernel<AM, SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners); break;
 	case 128: lk_init_kernel<AM, SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners); break;
 	case 256: lk_init_kernel<AM, SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners); break;
@@ -395,29 +413,36 @@ cudaError_t launch_set_region(int am, int ssm, int sm, int threads, const DevBat
 	return cudaGetLastError();
 }
 
-template<int AM, int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, cudaStream_t st){
+template<int AM, int SSM, int SM, int OCC> static cudaError_t launch_update_o(int threads, const DevBatch &b, cudaStream_t st){
 	switch(threads){
-	case 64: lk_update_kernel<AM, SSM, SM, 64><<<b.P, 64, 0, st>>>(b); break;
-	case 128: lk_update_kernel<AM, SSM, SM, 128><<<b.P, 128, 0, st>>>(b); break;
-	case 256: lk_update_kernel<AM, SSM, SM, 256><<<b.P, 256, 0, st>>>(b); break;
+	case 32: lk_update_kernel<AM, SSM, SM, 32, OCC><<<b.P, 32, 0, st>>>(b); break;
+	case 64: lk_update_kernel<AM, SSM, SM, 64, OCC><<<b.P, 64, 0, st>>>(b); break;
+	case 128: lk_update_kernel<AM, SSM, SM, 128, OCC><<<b.P, 128, 0, st>>>(b); break;
+	case 256: lk_update_kernel<AM, SSM, SM, 256, OCC><<<b.P, 256, 0, st>>>(b); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
-cudaError_t launch_update(int am, int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st){
+template<int AM, int SSM, int SM> static cudaError_t launch_update_t(int threads, int occ, const DevBatch &b, cudaStream_t st){
+	if(occ == 0) return launch_update_o<AM, SSM, SM, 0>(threads, b, st);
+	if(occ == 1) return launch_update_o<AM, SSM, SM, 1>(threads, b, st);
+	return launch_update_o<AM, SSM, SM, 2>(threads, b, st);
+}
+cudaError_t launch_update(int am, int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st){
 	if(!combo_supported(am, ssm, sm)) return cudaErrorNotSupported;
 	if(ssm == SSM_HOM){
-		if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_HOM, SM_ESM>(threads, b, st);
-		if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, b, st);
-		return launch_update_t<AM_SSD, SSM_HOM, SM_ICLK>(threads, b, st);
+		if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_HOM, SM_ESM>(threads, occ, b, st);
+		if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, occ, b, st);
+		return launch_update_t<AM_SSD, SSM_HOM, SM_ICLK>(threads, occ, b, st);
 	}
-	if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_AFF, SM_ESM>(threads, b, st);
-	if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_AFF, SM_FCLK>(threads, b, st);
-	return launch_update_t<AM_SSD, SSM_AFF, SM_ICLK>(threads, b, st);
+	if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_AFF, SM_ESM>(threads, occ, b, st);
+	if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_AFF, SM_FCLK>(threads, occ, b, st);
+	return launch_update_t<AM_SSD, SSM_AFF, SM_ICLK>(threads, occ, b, st);
 }
 
 template<int AM, int SSM> static cudaError_t launch_stage_t(int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
 	switch(threads){
+	case 32: lk_stage_kernel<AM, SSM, 32><<<b.P, 32, 0, st>>>(b, t); break;
 	case 64: lk_stage_kernel<AM, SSM, 64><<<b.P, 64, 0, st>>>(b, t); break;
 	case 128: lk_stage_kernel<AM, SSM, 128><<<b.P, 128, 0, st>>>(b, t); break;
 	case 256: lk_stage_kernel<AM, SSM, 256><<<b.P, 256, 0, st>>>(b, t); break;

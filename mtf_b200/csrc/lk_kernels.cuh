@@ -38,7 +38,7 @@ struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
 // launchers (lk_kernels.cu); threads = threads per patch (64 / 128 / 256)
 cudaError_t launch_init(int am, int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_set_region(int am, int ssm, int sm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
-cudaError_t launch_update(int am, int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
+cudaError_t launch_update(int am, int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_stage(int am, int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
 bool combo_supported(int am, int ssm, int sm);
 

