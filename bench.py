@@ -259,7 +259,7 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
                                % (P, ITERS, IMG, IMG),
-                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": tr.params.threads_per_patch or 128, "occupancy": args.occ,
+                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto(32)", "occupancy": args.occ if args.threads else "auto(0)",
                    "collective": "all_gather of P x 8 corners per frame" if world > 1 else "none"},
         "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},

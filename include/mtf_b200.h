@@ -81,7 +81,7 @@ typedef struct mtfb_params {
 	int mi_pou;
 	double likelihood_alpha;     /* AMParams::likelihood_alpha, PF path                           */
 	int device;                  /* CUDA device ordinal                                           */
-	int threads_per_patch;       /* 0 = library default; otherwise 32, 64, 128 or 256             */
+	int threads_per_patch;       /* 0 = chosen from n_patches; otherwise 32, 64, 128 or 256        */
 	int occupancy;               /* register budget of the update kernel: 0 / 1 / 2 = about 8 / 12 /
 	                                16 resident warps per SM (tuning knob, results do not change)  */
 } mtfb_params;

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmtf_b200.so")
+LIB_PATH = os.environ.get("MTFB_LIB") or os.path.join(_HERE, "libmtf_b200.so")   # MTFB_LIB: experiment builds
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
 SSM = {"homography": 0, "affine": 1, "8": 0, "6": 1}

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__
 	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
 		double val, gx, gy;
-		sample_pixel_grad(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		sample_pixel_grad<AM != AM_MI>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
 		val = b.pix_mult*val + b.pix_add;
 		double J[S];
 		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
@@ -128,6 +128,70 @@ __global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__
 	}
 }
 
+// pixels per loop trip: 2 interleaves two pixels' dependency chains; measured SLOWER than 1 on B200 (register
+// pressure next to the 45 fp64 accumulators: profiles/README.md), kept as a build-time experiment knob
+#ifndef MTFB_PIXELS_PER_TRIP
+#define MTFB_PIXELS_PER_TRIP 1
+#endif
+
+// what one pixel contributes to the sums: r = I_t - I_0, Jj = the row that multiplies df/dI in the Jacobian,
+// Jt = the row whose outer product goes into the Hessian, wj = df/dI
+template<int S> struct PixTerms { double r, wj; double Jt[S], Jj[S]; };
+
+template<int SSM, int SM, class MW> __device__ __forceinline__ void pixel_terms(const DevBatch &b, const MW &W, const double *abcd,
+	const PixGeom &g, const Sample &smp, double i0, const double *__restrict__ G0, int pix, bool need_grad, bool esm_mean,
+	PixTerms<StateSize<SSM>::value> &t){
+	constexpr int S = StateSize<SSM>::value;
+	t.r = smp.val - i0;                                            // I_diff (SSDBase.cc:78)
+	if(SM == SM_ICLK){
+		// df_dI0 = I_diff (SSDBase.cc:34: I_diff aliases df_dI0); Jacobian of the template
+		t.wj = t.r;
+		init_pix_jacobian<SSM>(g.ix, g.iy, G0[pix], G0[b.N + pix], t.Jj);
+		if(need_grad) warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, t.Jt);
+		return;
+	}
+	t.wj = -t.r;                                                   // df_dIt = -I_diff (SSDBase.cc:115-121)
+	warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, t.Jt);
+	if(SM == SM_ESM){
+		double J0[S];
+		init_pix_jacobian<SSM>(g.ix, g.iy, G0[pix], G0[b.N + pix], J0);
+		if(esm_mean){
+			// mean_pix_jacobian = (init + curr) / 2 (NT/ESM.cc:246-248)
+#pragma unroll
+			for(int s = 0; s < S; ++s) J0[s] = (J0[s] + t.Jt[s]) / 2.0;
+		}
+		if(b.jac_type == MTFB_ESM_JAC_ORIGINAL){
+#pragma unroll
+			for(int s = 0; s < S; ++s) t.Jj[s] = J0[s];
+		} else{
+			// SSDBase::cmptDifferenceOfJacobians: df_dIt * (dI0_dp + dIt_dp) (SSDBase.cc:186)
+#pragma unroll
+			for(int s = 0; s < S; ++s) t.Jj[s] = esm_mean ? (2.0*J0[s]) : (J0[s] + t.Jt[s]);
+		}
+		if(b.hess_type == MTFB_ESM_HESS_ORIGINAL){
+#pragma unroll
+			for(int s = 0; s < S; ++s) t.Jt[s] = J0[s];
+		}
+	} else{
+#pragma unroll
+		for(int s = 0; s < S; ++s) t.Jj[s] = t.Jt[s];
+	}
+}
+
+template<int S> __device__ __forceinline__ void accumulate_terms(double (&acc)[AccLayout<S>::NA], const PixTerms<S> &t, bool with_hessian){
+	typedef AccLayout<S> L;
+	acc[0] = fma(t.r, t.r, acc[0]);
+#pragma unroll
+	for(int s = 0; s < S; ++s) acc[1 + s] = fma(t.wj, t.Jj[s], acc[1 + s]);
+	if(with_hessian){
+#pragma unroll
+		for(int i = 0; i < S; ++i){
+#pragma unroll
+			for(int j = i; j < S; ++j) acc[1 + S + L::tri(i, j)] = fma(t.Jt[i], t.Jt[j], acc[1 + S + L::tri(i, j)]);
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // update(): the whole per-frame loop
 // ------------------------------------------------------------------------------------------------
@@ -141,12 +205,22 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 	__shared__ double s_sum[L::NA];
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8];
 	__shared__ int s_ctrl;
-	Mat3 dlt;
-#pragma unroll
-	for(int i = 0; i < 9; ++i) dlt.m[i] = b.dlt[(size_t)p * 9 + i];
-	if(tid < 9) s_W[tid] = b.warp[(size_t)p * 9 + tid];
+	__shared__ double s_dlt[9];
+	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
 	cta_sync<T>();
+	// MTFB_SMEM_MATS: 0 = both warp-uniform 3x3 matrices in registers (36 registers next to the 45 fp64
+	// accumulators), 1 = the DLT warp, 2 = both read from shared memory where they are used (broadcast loads)
+#ifndef MTFB_SMEM_MATS
+#define MTFB_SMEM_MATS 0
+#endif
+#if MTFB_SMEM_MATS >= 1
+	const MemMat3 dlt = { s_dlt };
+#else
+	Mat3 dlt;
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+#endif
 	const double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
 	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
@@ -157,67 +231,55 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
 	while(iter_id < b.max_iters){
-		Mat3 W;
-#pragma unroll
-		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
-		double abcd[4] = { W.m[0], W.m[1], W.m[3], W.m[4] };      // Affine.cc:217-220: curr_state(2)+1, (3), (4), (5)+1
+		double abcd[4] = { 0, 0, 0, 0 };
 		if(SSM == SSM_AFF){
-			// the reference reads them back from curr_state = getStateFromWarp(curr_warp): (w00 - 1) + 1 etc.
-			abcd[0] = (W.m[0] - 1) + 1; abcd[3] = (W.m[4] - 1) + 1;
+			// Affine.cc:217-220 reads curr_state(2)+1, (3), (4), (5)+1 with curr_state = getStateFromWarp(curr_warp)
+			abcd[0] = (s_W[0] - 1) + 1; abcd[1] = s_W[1]; abcd[2] = s_W[3]; abcd[3] = (s_W[4] - 1) + 1;
 		}
 		double acc[L::NA];
 #pragma unroll
 		for(int i = 0; i < L::NA; ++i) acc[i] = 0;
-		for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
-			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
-			double It, gx = 0, gy = 0;
-			if(need_grad){ sample_pixel_grad(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, It, gx, gy); }
-			else{ It = sample_pixel(b.img, g.wx, g.wy); }
-			const double r = It - I0[it.pix];                         // I_diff (SSDBase.cc:78)
-			acc[0] = fma(r, r, acc[0]);
-			double Jt[S], Jj[S];                                      // Jj: what multiplies df/dI in the Jacobian
-			if(SM == SM_ICLK){
-				init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[b.N + it.pix], Jj);
-				// df_dI0 = I_diff (SSDBase.cc:34: I_diff aliases df_dI0)
+#if MTFB_SMEM_MATS >= 2
+		const MemMat3 Wm = { s_W };
+#else
+		Mat3 Wm;
 #pragma unroll
-				for(int s = 0; s < S; ++s) acc[1 + s] = fma(r, Jj[s], acc[1 + s]);
-				if(!need_grad) continue;
-				warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, Jt);
+		for(int i = 0; i < 9; ++i) Wm.m[i] = s_W[i];
+#endif
+		// two pixels per trip: their dependency chains (warp -> reciprocal -> indices -> loads -> interpolation ->
+		// chain rule) are independent, so the compiler interleaves them and each hides the other's latency
+		PixIter it(tid, T, b.resx);
+		while(it.pix < b.N){
+			const int pa = it.pix; const double ua = b.xv[it.col], va = b.yv[it.row];
+			it.next(T);
+			const bool vb = MTFB_PIXELS_PER_TRIP > 1 && it.pix < b.N;
+			const int pb = vb ? it.pix : pa; const double ub = vb ? b.xv[it.col] : ua, vbv = vb ? b.yv[it.row] : va;
+			if(MTFB_PIXELS_PER_TRIP > 1) it.next(T);
+			PixTerms<S> ta, tb;
+			PixGeom ga = pixel_geometry<SSM>(dlt, Wm, ua, va), gb;
+			Sample sa = need_grad ? sample_fast<true>(b.img, ga.wx, ga.wy, b.grad_eps, b.pix_mult) : Sample(), sb;
+			const double i0a = I0[pa];
+			double i0b = 0;
+			if(MTFB_PIXELS_PER_TRIP > 1){
+				gb = pixel_geometry<SSM>(dlt, Wm, ub, vbv);
+				sb = need_grad ? sample_fast<true>(b.img, gb.wx, gb.wy, b.grad_eps, b.pix_mult) : Sample();
+				i0b = I0[pb];
+			}
+			if(need_grad){
+				if(MTFB_PIXELS_PER_TRIP > 1){
+					if(sa.lit | sb.lit){
+						if(sa.lit) sample_literal(b.img, ga.wx, ga.wy, b.grad_eps, b.grad_mult, sa);
+						if(sb.lit) sample_literal(b.img, gb.wx, gb.wy, b.grad_eps, b.grad_mult, sb);
+					}
+				} else if(sa.lit) sample_literal(b.img, ga.wx, ga.wy, b.grad_eps, b.grad_mult, sa);
 			} else{
-				warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, Jt);
-				const double d = -r;                                  // df_dIt = -I_diff (SSDBase.cc:115-121)
-				if(SM == SM_ESM){
-					double J0[S];
-					init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[b.N + it.pix], J0);
-					if(esm_mean){
-						// mean_pix_jacobian = (init + curr) / 2 (NT/ESM.cc:246-248)
-#pragma unroll
-						for(int s = 0; s < S; ++s) J0[s] = (J0[s] + Jt[s]) / 2.0;
-					}
-					if(b.jac_type == MTFB_ESM_JAC_ORIGINAL){
-#pragma unroll
-						for(int s = 0; s < S; ++s) Jj[s] = J0[s];
-					} else{
-						// SSDBase::cmptDifferenceOfJacobians: df_dIt * (dI0_dp + dIt_dp) (SSDBase.cc:186)
-#pragma unroll
-						for(int s = 0; s < S; ++s) Jj[s] = esm_mean ? (2.0*J0[s]) : (J0[s] + Jt[s]);
-					}
-					if(b.hess_type == MTFB_ESM_HESS_ORIGINAL){
-#pragma unroll
-						for(int s = 0; s < S; ++s) Jt[s] = J0[s];
-					}
-				} else{
-#pragma unroll
-					for(int s = 0; s < S; ++s) Jj[s] = Jt[s];
-				}
-#pragma unroll
-				for(int s = 0; s < S; ++s) acc[1 + s] = fma(d, Jj[s], acc[1 + s]);
+				sa.val = sample_pixel(b.img, ga.wx, ga.wy); sa.gx = sa.gy = 0;
+				if(MTFB_PIXELS_PER_TRIP > 1){ sb.val = sample_pixel(b.img, gb.wx, gb.wy); sb.gx = sb.gy = 0; }
 			}
-#pragma unroll
-			for(int i = 0; i < S; ++i){
-#pragma unroll
-				for(int j = i; j < S; ++j) acc[1 + S + L::tri(i, j)] = fma(Jt[i], Jt[j], acc[1 + S + L::tri(i, j)]);
-			}
+			pixel_terms<SSM, SM>(b, Wm, abcd, ga, sa, i0a, G0, pa, need_grad, esm_mean, ta);
+			if(MTFB_PIXELS_PER_TRIP > 1) pixel_terms<SSM, SM>(b, Wm, abcd, gb, sb, i0b, G0, pb, need_grad, esm_mean, tb);
+			accumulate_terms<S>(acc, ta, need_grad);
+			if(MTFB_PIXELS_PER_TRIP > 1 && vb) accumulate_terms<S>(acc, tb, need_grad);
 		}
 		block_reduce<L::NA, T>(acc, s_part, s_sum);
 		++n_passes;
@@ -226,6 +288,9 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 			int ctrl = CTRL_NEXT;
 			bool rejected = false;
 			f = -s_sum[0] / 2;                                        // SSDBase.cc:94
+			Mat3 W;
+#pragma unroll
+			for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
 			Mat3 Wn = W;
 			double upd_norm = 0, x = 0;
 			double dp[S];
@@ -269,7 +334,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 				for(int i = 0; i < S; ++i){
 					const int lo = i < jc ? i : jc, hi = i < jc ? jc : i;
 					const double hc = -s_sum[1 + S + L::tri(lo, hi)];
-					const double hi0 = b.Hinit[(size_t)p * 64 + jc*S + i];
+					const double hi0 = hsel != 0 ? b.Hinit[(size_t)p * 64 + jc*S + i] : 0.0;
 					qr.a[i] = hsel == 0 ? hc : (hsel == 1 ? hi0 : (hc + hi0) * 0.5);
 				}
 				if(lane == S){
@@ -370,7 +435,7 @@ __global__ void __launch_bounds__(T) lk_stage_kernel(DevBatch b, StageTaps t){
 	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
 		double val, gx, gy;
-		sample_pixel_grad(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		sample_pixel_grad<AM != AM_MI>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
 		val = b.pix_mult*val + b.pix_add;
 		double J[S];
 		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
@@ -430,6 +495,10 @@ template<int AM, int SSM, int SM> static cudaError_t launch_update_t(int threads
 }
 cudaError_t launch_update(int am, int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st){
 	if(!combo_supported(am, ssm, sm)) return cudaErrorNotSupported;
+#ifdef MTFB_ONLY_FCLK_HOM      // experiment builds (profiles/): one combination, fast to compile
+	if(ssm == SSM_HOM && sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, occ, b, st);
+	return cudaErrorNotSupported;
+#else
 	if(ssm == SSM_HOM){
 		if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_HOM, SM_ESM>(threads, occ, b, st);
 		if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, occ, b, st);
@@ -438,6 +507,7 @@ cudaError_t launch_update(int am, int ssm, int sm, int threads, int occ, const D
 	if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_AFF, SM_ESM>(threads, occ, b, st);
 	if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_AFF, SM_FCLK>(threads, occ, b, st);
 	return launch_update_t<AM_SSD, SSM_AFF, SM_ICLK>(threads, occ, b, st);
+#endif
 }
 
 template<int AM, int SSM> static cudaError_t launch_stage_t(int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){

@@ -29,10 +29,14 @@ enum { SM_ESM = 0, SM_FCLK = 1, SM_ICLK = 2, SM_PF = 3 };
 struct Image {
 	const float *data;   // pitched, row-major
 	int h, w, pitch;     // pitch in elements
+	double hd, wd;       // (double)h, (double)w: the comparisons of imgUtils.h:51-53 promote the ints every call
 };
+MTFB_HD Image make_image(const float *data, int h, int w, int pitch){
+	Image im; im.data = data; im.h = h; im.w = w; im.pitch = pitch; im.hd = h; im.wd = w; return im;
+}
 
 // imgUtils.h:51-53
-MTFB_HD bool check_overflow(double x, double y, int h, int w){
+MTFB_HD bool check_overflow(double x, double y, double h, double w){
 	// written so that a NaN coordinate counts as outside: on x86 the reference's (int)NaN is INT_MIN, which
 	// its second checkOverflow(lx, ly) call rejects (imgUtils.h:105), with the same result
 	return !((x >= 0) && (x < w) && (y >= 0) && (y < h));
@@ -63,7 +67,7 @@ MTFB_HD double div_by(double a, double b, double rb){
 
 // getPixVal<Linear, Constant>: imgUtils.h:91-113.  overflow_val = 128 (imgUtils.h:57).
 MTFB_HD double sample_pixel(const Image &im, double x, double y){
-	if(check_overflow(x, y, im.h, im.w)){ return 128.0; }
+	if(check_overflow(x, y, im.hd, im.wd)){ return 128.0; }
 	int lx = static_cast<int>(x);
 	int ly = static_cast<int>(y);
 	double dx = x - lx;
@@ -88,44 +92,68 @@ MTFB_HD double sample_pixel(const Image &im, double x, double y){
 //     or one of them leaves the image (the reference then divides (128 - I) by 2e-8): the reference's two
 //     getPixVal calls and its quotient are evaluated literally, so these cases match bit for bit.
 // grad_mult = mult / (2 eps) as imgUtils.cc:238 forms it; mult = pix_norm_mult (1 except MI).
-MTFB_HD void sample_pixel_grad(const Image &im, double x, double y, double grad_eps, double grad_mult, double mult,
-	double &val, double &gx, double &gy){
-	val = 128.0;
-	bool fast_x = false, fast_y = false;
-	double sx = 0, sy = 0;
-	if(!check_overflow(x, y, im.h, im.w)){
-		int lx = static_cast<int>(x);
-		int ly = static_cast<int>(y);
-		double dx = x - lx;
-		double dy = y - ly;
-		int ux = dx == 0 ? lx : lx + 1;
-		int uy = dy == 0 ? ly : ly + 1;
-		if(ux < im.w && uy < im.h){
-			const float *r0 = im.data + (size_t)ly*im.pitch, *r1 = im.data + (size_t)uy*im.pitch;
-			double p00 = MTFB_LDG(r0 + lx), p01 = MTFB_LDG(r0 + ux), p10 = MTFB_LDG(r1 + lx), p11 = MTFB_LDG(r1 + ux);
-			val = p00 * (1 - dx)*(1 - dy) + p01 * dx*(1 - dy) + p10 * (1 - dx)*dy + p11 * dx*dy;
-			fast_x = (x - grad_eps >= lx) && (x + grad_eps < lx + 1);
-			fast_y = (y - grad_eps >= ly) && (y + grad_eps < ly + 1);
-			sx = ((1 - dy)*(p01 - p00) + dy*(p11 - p10)) * mult;
-			sy = ((1 - dx)*(p10 - p00) + dx*(p11 - p01)) * mult;
-		}
-	}
-	if(fast_x){ gx = sx; }
-	else{
+// The common path (sample_fast) is straight-line code -- validity is a predicate and the indices are clamped so
+// that the four loads are always legal -- so the compiler can overlap the load latency with arithmetic that
+// does not depend on the pixel values, and two pixels can be interleaved.  The literal path (sample_literal) is
+// a rarely taken branch the caller runs afterwards for the components flagged in Sample::lit.
+struct Sample { double val, gx, gy; int lit; };     // lit bit 0 / 1: gx / gy must be recomputed literally
+
+template<bool UNIT_MULT> MTFB_HD Sample sample_fast(const Image &im, double x, double y, double grad_eps, double mult){
+	Sample o;
+	const bool inb = !check_overflow(x, y, im.hd, im.wd);
+	const double xs = inb ? x : 0.0, ys = inb ? y : 0.0;
+	int lx = static_cast<int>(xs);
+	int ly = static_cast<int>(ys);
+	double dx = xs - lx;
+	double dy = ys - ly;
+	int ux = dx == 0 ? lx : lx + 1;
+	int uy = dy == 0 ? ly : ly + 1;
+	const bool ok = inb && ux < im.w && uy < im.h;
+	ux = ux < im.w ? ux : im.w - 1;
+	uy = uy < im.h ? uy : im.h - 1;
+	const float *r0 = im.data + (size_t)ly*im.pitch, *r1 = im.data + (size_t)uy*im.pitch;
+	double p00 = MTFB_LDG(r0 + lx), p01 = MTFB_LDG(r0 + ux), p10 = MTFB_LDG(r1 + lx), p11 = MTFB_LDG(r1 + ux);
+	const double v = p00 * (1 - dx)*(1 - dy) + p01 * dx*(1 - dy) + p10 * (1 - dx)*dy + p11 * dx*dy;
+	o.val = ok ? v : 128.0;
+	// both +-eps samples in the cell of (x, y)?  (dx = x - lx is exact)
+	const bool fast_x = ok && (dx >= grad_eps) && (dx <= 1 - grad_eps);
+	const bool fast_y = ok && (dy >= grad_eps) && (dy <= 1 - grad_eps);
+	o.gx = (1 - dy)*(p01 - p00) + dy*(p11 - p10);
+	o.gy = (1 - dx)*(p10 - p00) + dx*(p11 - p01);
+	if(!UNIT_MULT){ o.gx = o.gx * mult; o.gy = o.gy * mult; }
+	o.lit = (fast_x ? 0 : 1) | (fast_y ? 0 : 2);
+	return o;
+}
+MTFB_HD void sample_literal(const Image &im, double x, double y, double grad_eps, double grad_mult, Sample &o){
+	if(o.lit & 1){
 		double inc = sample_pixel(im, x + grad_eps, y), dec = sample_pixel(im, x - grad_eps, y);
-		gx = (inc - dec)*grad_mult;
+		o.gx = (inc - dec)*grad_mult;
 	}
-	if(fast_y){ gy = sy; }
-	else{
+	if(o.lit & 2){
 		double inc = sample_pixel(im, x, y + grad_eps), dec = sample_pixel(im, x, y - grad_eps);
-		gy = (inc - dec)*grad_mult;
+		o.gy = (inc - dec)*grad_mult;
 	}
+}
+template<bool UNIT_MULT> MTFB_HD void sample_pixel_grad(const Image &im, double x, double y, double grad_eps,
+	double grad_mult, double mult, double &val, double &gx, double &gy){
+	Sample o = sample_fast<UNIT_MULT>(im, x, y, grad_eps, mult);
+	if(o.lit) sample_literal(im, x, y, grad_eps, grad_mult, o);
+	val = o.val; gx = o.gx; gy = o.gy;
 }
 
 // ------------------------------------------------------------------------------------------------
 // 3x3 helpers, row-major m[3*r + c]; arithmetic order = Eigen's lazy coefficient-wise product
 // ------------------------------------------------------------------------------------------------
-struct Mat3 { double m[9]; };
+struct Mat3 {
+	double m[9];
+	MTFB_HD double operator[](int i) const{ return m[i]; }
+};
+// 3x3 matrix read from memory at every use (volatile: keeps a warp-uniform matrix OUT of the register file;
+// each read is one broadcast shared-memory load)
+struct MemMat3 {
+	const volatile double *p;
+	MTFB_HD double operator[](int i) const{ return p[i]; }
+};
 
 MTFB_HD Mat3 mat3_identity(){
 	Mat3 I;
@@ -236,21 +264,24 @@ template<int SSM> MTFB_HD void warp_corners(const Mat3 &w, const double *init_co
 //   Affine:        init_pts_hm is re-homogenised (Affine.cc:81-82), curr_pts = W.topRows(2) . (ix,iy,1)
 struct PixGeom { double ix, iy, wx, wy, D, rD; };     // rD = RN(1 / D) = the reference's inv_det (Homography.cc:250)
 
-template<int SSM> MTFB_HD PixGeom pixel_geometry(const Mat3 &dlt, const Mat3 &W, double u, double v){
+template<int SSM, class MD, class MW> MTFB_HD PixGeom pixel_geometry(const MD &dlt, const MW &W, double u, double v){
 	PixGeom g;
-	double hx = dlt.m[0] * u; hx = hx + dlt.m[1] * v; hx = hx + dlt.m[2] * 1.0;
-	double hy = dlt.m[3] * u; hy = hy + dlt.m[4] * v; hy = hy + dlt.m[5] * 1.0;
-	double hz = dlt.m[6] * u; hz = hz + dlt.m[7] * v; hz = hz + dlt.m[8] * 1.0;
-	const double rhz = ieee_rcp(hz);
-	g.ix = div_by(hx, hz, rhz); g.iy = div_by(hy, hz, rhz);
+	double hx = dlt[0] * u; hx = hx + dlt[1] * v; hx = hx + dlt[2] * 1.0;
+	double hy = dlt[3] * u; hy = hy + dlt[4] * v; hy = hy + dlt[5] * 1.0;
+	double hz = dlt[6] * u; hz = hz + dlt[7] * v; hz = hz + dlt[8] * 1.0;
 	if(SSM == SSM_HOM){
-		double cx = W.m[0] * hx; cx = cx + W.m[1] * hy; cx = cx + W.m[2] * hz;
-		double cy = W.m[3] * hx; cy = cy + W.m[4] * hy; cy = cy + W.m[5] * hz;
-		double cz = W.m[6] * hx; cz = cz + W.m[7] * hy; cz = cz + W.m[8] * hz;
+		// the warped point first: the image loads hang off it, the template point is needed only later
+		double cx = W[0] * hx; cx = cx + W[1] * hy; cx = cx + W[2] * hz;
+		double cy = W[3] * hx; cy = cy + W[4] * hy; cy = cy + W[5] * hz;
+		double cz = W[6] * hx; cz = cz + W[7] * hy; cz = cz + W[8] * hz;
 		g.D = cz; g.rD = ieee_rcp(cz); g.wx = div_by(cx, cz, g.rD); g.wy = div_by(cy, cz, g.rD);
+		const double rhz = ieee_rcp(hz);
+		g.ix = div_by(hx, hz, rhz); g.iy = div_by(hy, hz, rhz);
 	} else{
-		double cx = W.m[0] * g.ix; cx = cx + W.m[1] * g.iy; cx = cx + W.m[2] * 1.0;
-		double cy = W.m[3] * g.ix; cy = cy + W.m[4] * g.iy; cy = cy + W.m[5] * 1.0;
+		const double rhz = ieee_rcp(hz);
+		g.ix = div_by(hx, hz, rhz); g.iy = div_by(hy, hz, rhz);
+		double cx = W[0] * g.ix; cx = cx + W[1] * g.iy; cx = cx + W[2] * 1.0;
+		double cy = W[3] * g.ix; cy = cy + W[4] * g.iy; cy = cy + W[5] * 1.0;
 		g.D = 1.0; g.rD = 1.0; g.wx = cx; g.wy = cy;
 	}
 	return g;
@@ -258,13 +289,14 @@ template<int SSM> MTFB_HD PixGeom pixel_geometry(const Mat3 &dlt, const Mat3 &W,
 
 // ssm.cmptWarpedPixJacobian: Homography.cc:231-294, Affine.cc:213-242.  gx, gy = dI/dx at the warped point.
 // aff_abcd = (curr_state[2]+1, curr_state[3], curr_state[4], curr_state[5]+1) for the affine SSM.
-template<int SSM> MTFB_HD void warped_pix_jacobian(const Mat3 &W, const double *aff_abcd, const PixGeom &g,
+template<int SSM, class MW> MTFB_HD void warped_pix_jacobian(const MW &W, const double *aff_abcd, const PixGeom &g,
 	double gx, double gy, double *J){
 	double x = g.ix, y = g.iy;
 	if(SSM == SSM_HOM){
 		double inv_det = g.rD;
-		double dwx_dx = (W.m[0] - W.m[6] * g.wx), dwx_dy = (W.m[1] - W.m[7] * g.wx);
-		double dwy_dx = (W.m[3] - W.m[6] * g.wy), dwy_dy = (W.m[4] - W.m[7] * g.wy);
+		const double a00 = W[0], a01 = W[1], a10 = W[3], a11 = W[4], a20 = W[6], a21 = W[7];
+		double dwx_dx = (a00 - a20 * g.wx), dwx_dy = (a01 - a21 * g.wx);
+		double dwy_dx = (a10 - a20 * g.wy), dwy_dy = (a11 - a21 * g.wy);
 		double Ix = (dwx_dx*gx + dwy_dx*gy)*inv_det;
 		double Iy = (dwx_dy*gx + dwy_dy*gy)*inv_det;
 		double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;

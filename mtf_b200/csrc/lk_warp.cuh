@@ -88,32 +88,34 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 			for(int r = 0; r < ROWS; ++r) s += a[r] * a[r];
 			cnd = sqrt(s); cnu = cnd;
 		}
-		double maxn = is_col ? cnu : 0.0;
-#pragma unroll
-		for(int off = 8; off >= 1; off >>= 1){
-			double o = __shfl_xor_sync(FULL_MASK, maxn, off);
-			maxn = (o > maxn) ? o : maxn;
+		double maxn;
+		{
+			const bool ok = is_col && (cnu == cnu);
+			const unsigned hi = ok ? (unsigned)__double2hiint(cnu) : 0u;
+			const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+			const unsigned lo = (ok && hi == mhi) ? (unsigned)__double2loint(cnu) : 0u;
+			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+			maxn = __hiloint2double((int)mhi, (int)mlo);
 		}
-		maxn = __shfl_sync(FULL_MASK, maxn, 0);
 		const double th = maxn * DBL_EPSILON / double(ROWS);
 		const double threshold_helper = th * th;
 		const double norm_downdate_threshold = sqrt(DBL_EPSILON);
 		nonzero_pivots = SIZE;
 #pragma unroll
 		for(int k = 0; k < SIZE; ++k){
-			// pivot: first position >= k holding the largest updated column norm
-			const bool cand_ok = is_col && pos >= k;
-			double cand = cand_ok ? cnu : -1.0;
-			int cpos = cand_ok ? pos : (1 << 20);
-#pragma unroll
-			for(int off = 8; off >= 1; off >>= 1){
-				double ov = __shfl_xor_sync(FULL_MASK, cand, off);
-				int op = __shfl_xor_sync(FULL_MASK, cpos, off);
-				if(ov > cand || (ov == cand && op < cpos)){ cand = ov; cpos = op; }
-			}
-			double bmax = __shfl_sync(FULL_MASK, cand, 0);
-			int biggest = __shfl_sync(FULL_MASK, cpos, 0);
-			if(biggest >= (1 << 20)){ biggest = k; bmax = 0; }        // all-NaN norms: keep column k
+			// pivot: first position >= k holding the largest updated column norm.  Norms are >= 0, so their
+			// bit patterns order like unsigned integers: two 32-bit warp max-reductions find the largest value,
+			// a min-reduction over positions breaks ties the way Eigen's left-to-right scan does.
+			const bool cand_ok = is_col && pos >= k && (cnu == cnu);
+			const unsigned hi = cand_ok ? (unsigned)__double2hiint(cnu) : 0u;
+			const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+			const bool c1 = cand_ok && hi == mhi;
+			const unsigned lo = c1 ? (unsigned)__double2loint(cnu) : 0u;
+			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+			const bool c2 = c1 && lo == mlo;
+			int biggest = (int)__reduce_min_sync(FULL_MASK, c2 ? (unsigned)pos : 0xffffu);
+			double bmax = __hiloint2double((int)mhi, (int)mlo);
+			if(biggest == 0xffff){ biggest = k; bmax = 0; }           // all-NaN norms: keep column k
 			if(nonzero_pivots == SIZE && bmax * bmax < threshold_helper * double(ROWS - k)) nonzero_pivots = k;
 			if(is_col){ if(pos == biggest) pos = k; else if(pos == k) pos = biggest; }
 			const int piv_lane = __ffs(__ballot_sync(FULL_MASK, is_col && pos == k)) - 1;

@@ -102,10 +102,20 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(p->hom_normalized_init)
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: hom_normalized_init = 1 is not implemented");
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
-	int threads = p->threads_per_patch ? p->threads_per_patch : 128;
+	// default work split, measured on B200 (profiles/README.md): one warp per patch once the batch alone fills the
+	// ~8 warps per SM the fp64 accumulators leave room for; more warps per patch (and a tighter register budget,
+	// so that the whole batch is resident in one wave) for smaller batches
+	int threads = p->threads_per_patch;
+	int occ = p->occupancy;
+	if(!threads){
+		if(p->n_patches >= 900){ threads = 32; occ = 0; }
+		else if(p->n_patches >= 450){ threads = 64; occ = 2; }
+		else if(p->n_patches >= 200){ threads = 128; occ = 2; }
+		else{ threads = 256; occ = 2; }
+	}
 	if(threads != 32 && threads != 64 && threads != 128 && threads != 256)
 		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: threads_per_patch must be 0, 32, 64, 128 or 256");
-	if(p->occupancy < 0 || p->occupancy > 2) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: occupancy must be 0, 1 or 2");
+	if(occ < 0 || occ > 2) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: occupancy must be 0, 1 or 2");
 	int n_dev = 0;
 	if(cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
 		return fail(MTFB_ERR_CUDA, "mtfb_create: no CUDA device visible (this library has no CPU path)");
@@ -118,7 +128,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	mtfb_ctx *c = new (std::nothrow) mtfb_ctx();
 	if(!c) return fail(MTFB_ERR_NO_MEMORY, "mtfb_create: out of host memory");
 	std::memset(static_cast<void*>(c), 0, sizeof(*c));
-	c->prm = *p; c->threads = threads; c->occ = p->occupancy;
+	c->prm = *p; c->threads = threads; c->occ = occ;
 	c->S = p->ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6;
 	c->N = p->resx * p->resy; c->P = p->n_patches;
 	const int S = c->S, N = c->N, P = c->P;
@@ -166,7 +176,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.grad_eps = p->grad_eps;
 		b.pix_mult = 1; b.pix_add = 0;
 		b.grad_mult = b.pix_mult / (2 * p->grad_eps);
-		b.img.data = nullptr; b.img.h = b.img.w = b.img.pitch = 0;
+		b.img = make_image(nullptr, 0, 0, 0);
 	} while(0);
 	if(st != MTFB_OK){
 		cudaError_t e = cudaGetLastError();
@@ -209,7 +219,7 @@ mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int
 	}
 	CUDA_TRY(cudaMemcpy2DAsync(c->d_img_own, (size_t)pitch*sizeof(float), host_img, (size_t)row_stride*sizeof(float),
 		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->stream));
-	c->b.img.data = c->d_img_own; c->b.img.h = h; c->b.img.w = w; c->b.img.pitch = pitch;
+	c->b.img = make_image(c->d_img_own, h, w, pitch);
 	c->have_image = true;
 	return MTFB_OK;
 }
@@ -217,7 +227,7 @@ mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int
 mtfb_status mtfb_set_image_device(mtfb_ctx *c, const float *dev_img, int h, int w, int pitch){
 	if(!c || !dev_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: null argument");
 	if(h < 2 || w < 2 || pitch < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: bad geometry %d x %d pitch %d", h, w, pitch);
-	c->b.img.data = dev_img; c->b.img.h = h; c->b.img.w = w; c->b.img.pitch = pitch;
+	c->b.img = make_image(dev_img, h, w, pitch);
 	c->have_image = true;
 	return MTFB_OK;
 }

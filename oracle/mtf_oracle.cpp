@@ -103,10 +103,11 @@ static void getImgGradAnalytic(double *img_grad, const float *img, const double 
 			if(ux < (int)w && uy < (int)h){
 				double p00 = img[(size_t)ly*w + lx], p01 = img[(size_t)ly*w + ux];
 				double p10 = img[(size_t)uy*w + lx], p11 = img[(size_t)uy*w + ux];
-				same_cell_x = (x - grad_eps >= lx) && (x + grad_eps < lx + 1);
-				same_cell_y = (y - grad_eps >= ly) && (y + grad_eps < ly + 1);
-				slope_x = ((1 - dy)*(p01 - p00) + dy*(p11 - p10)) * pix_mult_factor;
-				slope_y = ((1 - dx)*(p10 - p00) + dx*(p11 - p01)) * pix_mult_factor;
+				same_cell_x = (dx >= grad_eps) && (dx <= 1 - grad_eps);       // dx = x - lx is exact
+				same_cell_y = (dy >= grad_eps) && (dy <= 1 - grad_eps);
+				slope_x = (1 - dy)*(p01 - p00) + dy*(p11 - p10);
+				slope_y = (1 - dx)*(p10 - p00) + dx*(p11 - p01);
+				if(pix_mult_factor != 1){ slope_x = slope_x * pix_mult_factor; slope_y = slope_y * pix_mult_factor; }
 			}
 		}
 		if(same_cell_x){ img_grad[pix_id] = slope_x; }
