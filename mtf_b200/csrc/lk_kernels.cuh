@@ -21,6 +21,7 @@ struct DevBatch {
 	double *I0;                  // P x N   template pixel values (am.I0)
 	double *G0;                  // P x 2 x N  template gradient, already chained with the init warp
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
+	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
 	double *f;                   // P       similarity
 	int *n_iters;                // P
 	int *status;                 // P
@@ -35,11 +36,17 @@ struct DevBatch {
 
 struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
 
-// launchers (lk_kernels.cu); threads = threads per patch (64 / 128 / 256)
-cudaError_t launch_init(int am, int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
-cudaError_t launch_set_region(int am, int ssm, int sm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
-cudaError_t launch_update(int am, int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
-cudaError_t launch_stage(int am, int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
-bool combo_supported(int am, int ssm, int sm);
+// launchers; threads = threads per patch (32 / 64 / 128 / 256), occ = register-budget knob of the SSD update kernel
+// lk_ssd.cu
+cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
+cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
+cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
+cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
+// lk_ncc.cu
+cudaError_t launch_init_ncc(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
+cudaError_t launch_update_ncc(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
+// pf_kernels.cu
+cudaError_t launch_pf_evaluate(int am, int ssm, const DevBatch &b, const double *d_states, int n_particles,
+	double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st);
 
 } // namespace mtfb

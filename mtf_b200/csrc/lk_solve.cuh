@@ -1,0 +1,157 @@
+// lk_solve.cuh -- the appearance-model-independent tail of one Gauss-Newton pass, run by warp 0 of the CTA:
+// Levenberg-Marquardt accept / reject, Hessian selection and damping, the S x S column-pivoted QR solve,
+// the (inverse) compositional update, the corner-change stopping test and the iteration log.
+// Control flow follows nt::FCLK::update (SM/src/NT/FCLK.cc:187-352), nt::ESM::update (NT/ESM.cc:186-296) and
+// nt::ICLK::update (NT/ICLK.cc:167-297); the templated twins differ only in how a rejected step is counted.
+#pragma once
+#include "lk_common.cuh"
+
+namespace mtfb {
+
+struct LMState {
+	double prev_similarity, lm_delta;
+	double ssm_update;          // lane l holds entry l of the last state update
+	bool state_reset;
+};
+
+// which Hessian the solve uses: 0 = the one the pixel pass just produced, 1 = the one stored at
+// initialize() (init_self_hessian), 2 = the mean of both (ESM SumOfSelf / SumOfStd, NT/ESM.cc:339-352)
+template<int SM> __device__ __forceinline__ int hessian_select(int hess_type){
+	if(SM == SM_ESM){
+		return (hess_type == MTFB_ESM_HESS_INITIAL_SELF) ? 1 :
+			(hess_type == MTFB_ESM_HESS_SUM_OF_SELF || hess_type == MTFB_ESM_HESS_SUM_OF_STD) ? 2 : 0;
+	}
+	if(SM == SM_FCLK) return (hess_type == MTFB_LK_HESS_INITIAL_SELF) ? 1 : 0;
+	return (hess_type == MTFB_LK_HESS_CURRENT_SELF) ? 0 : 1;
+}
+
+// f: similarity of this pass.  s_J[S]: df_dp as the search method uses it (ESM's 0.5 already applied).
+// s_Hc[S*S]: column-major Hessian of this pass (ignored when hsel == 1).
+// Writes s_W, s_corners, the log; returns CTRL_*.  All 32 lanes of warp 0 must call it.
+template<int SSM, int SM>
+__device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, int iter_id, int n_passes, double f,
+	const double *s_J, const double *s_Hc, double *s_W, double *s_corners, const double *s_init_corners,
+	LMState &lm, int &patch_status){
+	constexpr int S = StateSize<SSM>::value;
+	int ctrl = CTRL_NEXT;
+	bool rejected = false;
+	Mat3 W;
+#pragma unroll
+	for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
+	Mat3 Wn = W;
+	double upd_norm = 0, x = 0, Jv = 0;
+	double dp[S];
+	if(b.leven_marq && !lm.state_reset){
+		if(iter_id > 0){
+			if(f < lm.prev_similarity){
+				lm.lm_delta *= b.lm_delta_update;
+#pragma unroll
+				for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, lm.ssm_update, s);
+				if(SM == SM_ICLK){
+					// undo the inverse step by re-applying the forward update (NT/ICLK.cc:183)
+					Wn = compose_update<SSM>(W, dp);
+				} else{
+					double inv[S];
+					invert_state<SSM>(inv, dp);
+					Wn = compose_update<SSM>(W, inv);
+				}
+				lm.state_reset = true; rejected = true; ctrl = CTRL_REJECT;
+			} else if(f > lm.prev_similarity){
+				lm.lm_delta /= b.lm_delta_update;
+			}
+		}
+		if(!rejected) lm.prev_similarity = f;
+	}
+	if(!rejected){
+		lm.state_reset = false;
+		WarpColPivQR<S, S> qr;
+		const int hsel = hessian_select<SM>(b.hess_type);
+		const int jc = lane < S ? lane : 0;                      // column `lane` of the Hessian
+#pragma unroll
+		for(int i = 0; i < S; ++i){
+			const double hc = hsel != 1 ? s_Hc[jc*S + i] : 0.0;
+			const double hi0 = hsel != 0 ? b.Hinit[(size_t)p * 64 + jc*S + i] : 0.0;
+			qr.a[i] = hsel == 0 ? hc : (hsel == 1 ? hi0 : (hc + hi0) * 0.5);
+		}
+		if(lane == S){
+#pragma unroll
+			for(int i = 0; i < S; ++i) qr.a[i] = s_J[i];
+		}
+		if(lane < S) Jv = s_J[lane];
+		if(b.leven_marq){
+#pragma unroll
+			for(int i = 0; i < S; ++i) if(i == lane) qr.a[i] += lm.lm_delta * qr.a[i];      // NT/FCLK.cc:289-296
+		}
+		if(b.log && n_passes <= b.log_slots && lane < S){
+			mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
+#pragma unroll
+			for(int i = 0; i < S; ++i) e->hessian[lane*S + i] = qr.a[i];
+		}
+		qr.factor(lane, true);
+		x = -qr.solve(lane);                                     // state_update = -H^-1 J^T (NT/FCLK.cc:298)
+		if(qr.nonzero_pivots < S) patch_status |= MTFB_PATCH_SINGULAR;
+		lm.ssm_update = x;
+#pragma unroll
+		for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, x, s);
+		if(SM == SM_ICLK){
+			double inv[S];
+			invert_state<SSM>(inv, dp);                          // NT/ICLK.cc:270-271
+			Wn = compose_update<SSM>(W, inv);
+		} else{
+			Wn = compose_update<SSM>(W, dp);
+		}
+	}
+	double nc[8];
+	warp_corners<SSM>(Wn, s_init_corners, nc);
+	if(!rejected){
+#pragma unroll
+		for(int i = 0; i < 8; ++i){ double d = s_corners[i] - nc[i]; upd_norm += d*d; }
+		if(upd_norm < b.epsilon) ctrl = CTRL_BREAK;
+		if(!(upd_norm == upd_norm) || !(f == f)) patch_status |= MTFB_PATCH_NAN;
+	}
+	__syncwarp();
+	if(lane < 9) s_W[lane] = Wn.m[lane];
+	if(lane < 8) s_corners[lane] = nc[lane];
+	if(b.log && n_passes <= b.log_slots){
+		mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
+		if(lane < S){ e->jacobian[lane] = rejected ? 0.0 : Jv; e->state_update[lane] = rejected ? 0.0 : x; }
+		if(lane < 8) e->corners[lane] = nc[lane];
+		if(lane == 0){ e->f = f; e->update_norm = upd_norm; e->rejected = rejected; e->valid = 1; }
+	}
+	return ctrl;
+}
+
+// nt::FCLK re-enters its while loop without counting a rejected step (NT/FCLK.cc:187,210); every other loop
+// is a for(...; ++iter_id) (FCLK.cc:117,135, ESM.cc:128, NT/ESM.cc:186, ICLK.cc:150, NT/ICLK.cc:167)
+template<int SM> __device__ __forceinline__ bool counts_as_iteration(int ctrl, int nt_semantics){
+	return !(ctrl == CTRL_REJECT && SM == SM_FCLK && nt_semantics);
+}
+
+// final state of the patch -> global memory (warp 0)
+template<int SSM> __device__ __forceinline__ void store_patch_state(const DevBatch &b, int p, int lane, const double *s_W,
+	const double *s_corners, double f, int n_passes, int patch_status){
+	constexpr int S = StateSize<SSM>::value;
+	Mat3 W;
+#pragma unroll
+	for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
+	double st[S];
+	state_from_warp<SSM>(st, W);
+	if(lane < 9) b.warp[(size_t)p * 9 + lane] = W.m[lane];
+	if(lane < 8) b.corners[(size_t)p * 8 + lane] = s_corners[lane];
+#pragma unroll
+	for(int s = 0; s < S; ++s) if(lane == s) b.state[(size_t)p*S + s] = st[s];
+	if(lane == 0){ b.f[p] = f; b.n_iters[p] = n_passes; b.status[p] = patch_status; }
+}
+
+// ssm.setCorners for one patch (warp 0): 4-point DLT, identity warp, zero state
+template<int SSM> __device__ __forceinline__ Mat3 set_corners(const DevBatch &b, int p, int lane, const double *c_in){
+	constexpr int S = StateSize<SSM>::value;
+	Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
+	Mat3 I = mat3_identity();
+	if(lane < 9){ b.dlt[(size_t)p * 9 + lane] = dlt.m[lane]; b.warp[(size_t)p * 9 + lane] = I.m[lane]; }
+	if(lane < S) b.state[(size_t)p*S + lane] = 0;
+	if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }
+	return dlt;
+}
+
+} // namespace mtfb

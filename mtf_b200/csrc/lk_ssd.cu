@@ -1,4 +1,5 @@
-// lk_kernels.cu -- the fused Lucas-Kanade kernels (sm_100a).
+// lk_ssd.cu -- the fused Lucas-Kanade kernels for the SSD appearance model (sm_100a), plus the
+// AM-independent set-region and stage-tap kernels.
 //
 // One CTA tracks one patch for a whole frame: the <= max_iters Gauss-Newton loop of
 // nt::FCLK::update (SM/src/NT/FCLK.cc:171-358), nt::ESM::update (SM/src/NT/ESM.cc:170-297) and
@@ -14,70 +15,16 @@
 // then the CTA reduces the 1 + S + S(S+1)/2 sums (warp butterfly + one shared-memory hop) and warp 0
 // runs the Levenberg-Marquardt bookkeeping, the S x S column-pivoted QR solve, the compositional
 // update and the corner-change stopping test.
-#include "lk_kernels.cuh"
-#include "lk_warp.cuh"
+#include "lk_solve.cuh"
 
 namespace mtfb {
-
-enum { CTRL_NEXT = 0, CTRL_BREAK = 1, CTRL_REJECT = 2 };
-
-template<int S> struct AccLayout {
-	static constexpr int NH = S*(S + 1) / 2;
-	static constexpr int NA = 1 + S + NH;             // sum r^2 | J^T d | upper triangle of J^T J
-	__host__ __device__ static constexpr int tri(int i, int j){ return i*S - i*(i - 1) / 2 + (j - i); }  // i <= j
-};
-
-// a CTA of one warp (T == 32: one warp tracks one patch) needs no block barrier
-template<int T> __device__ __forceinline__ void cta_sync(){
-	if(T == 32) __syncwarp(); else __syncthreads();
-}
-
-// CTA-wide sum of a per-thread accumulator vector; result in s_sum[0..CNT) after the call.
-template<int CNT, int T> __device__ __forceinline__ void block_reduce(double (&acc)[CNT], double *s_part /* [T/32][CNT] */,
-	double *s_sum){
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int idx[2];
-	warp_reduce_scatter<CNT>(acc, lane, idx);
-	if(T == 32){
-		if(idx[0] >= 0) s_sum[idx[0]] = acc[0];
-		if(idx[1] >= 0) s_sum[idx[1]] = acc[1];
-		__syncwarp();
-		return;
-	}
-	if(idx[0] >= 0) s_part[warp*CNT + idx[0]] = acc[0];
-	if(idx[1] >= 0) s_part[warp*CNT + idx[1]] = acc[1];
-	__syncthreads();
-	for(int e = threadIdx.x; e < CNT; e += T){
-		double s = s_part[e];
-#pragma unroll
-		for(int w = 1; w < T / 32; ++w) s += s_part[w*CNT + e];
-		s_sum[e] = s;
-	}
-	__syncthreads();
-}
-
-// resident CTAs per SM requested from the compiler: OCC 0 / 1 / 2 = about 8 / 12 / 16 warps per SM
-// (<= 255 / 168 / 128 registers per thread)
-__host__ __device__ constexpr int min_blocks(int T, int OCC){
-	return (OCC == 0 ? 8 : OCC == 1 ? 12 : 16) * 32 / T > 0 ? (OCC == 0 ? 8 : OCC == 1 ? 12 : 16) * 32 / T : 1;
-}
-
-struct PixIter {
-	int pix, row, col, dcol, drow, resx;
-	__device__ __forceinline__ PixIter(int tid, int step, int _resx) : pix(tid), row(tid / _resx), col(tid % _resx),
-		dcol(step % _resx), drow(step / _resx), resx(_resx){}
-	__device__ __forceinline__ void next(int step){
-		pix += step; col += dcol; row += drow;
-		if(col >= resx){ col -= resx; ++row; }
-	}
-};
 
 // ------------------------------------------------------------------------------------------------
 // initialize(): ssm.setCorners + am.initializePixVals + initializePixGrad + cmptWarpedPixJacobian (at the
 // identity warp) + am.cmptSelfHessian  (NT/FCLK.cc:102-169, NT/ESM.cc:110-146, NT/ICLK.cc:71-127)
 // ------------------------------------------------------------------------------------------------
-template<int AM, int SSM, int T>
-__global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__restrict__ corners_in){
+template<int SSM, int T>
+__global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *__restrict__ corners_in){
 	constexpr int S = StateSize<SSM>::value;
 	typedef AccLayout<S> L;
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,12 +33,8 @@ __global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__
 	__shared__ double s_sum[L::NA];
 	const double *c_in = corners_in + (size_t)p * 8;
 	if(warp == 0){
-		Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
-		if(lane < 9){ s_dlt[lane] = dlt.m[lane]; b.dlt[(size_t)p * 9 + lane] = dlt.m[lane]; }
-		Mat3 I = mat3_identity();
-		if(lane < 9) b.warp[(size_t)p * 9 + lane] = I.m[lane];
-		if(lane < S) b.state[(size_t)p*S + lane] = 0;
-		if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }
+		Mat3 dlt = set_corners<SSM>(b, p, lane, c_in);
+		if(lane < 9) s_dlt[lane] = dlt.m[lane];
 		if(lane == 0){ b.f[p] = 0; b.n_iters[p] = 0; b.status[p] = 0; }
 	}
 	cta_sync<T>();
@@ -106,8 +49,7 @@ __global__ void __launch_bounds__(T) lk_init_kernel(DevBatch b, const double *__
 	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
 		double val, gx, gy;
-		sample_pixel_grad<AM != AM_MI>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
-		val = b.pix_mult*val + b.pix_add;
+		sample_pixel_grad<true>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
 		double J[S];
 		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
 		I0[it.pix] = val;
@@ -195,15 +137,15 @@ template<int S> __device__ __forceinline__ void accumulate_terms(double (&acc)[A
 // ------------------------------------------------------------------------------------------------
 // update(): the whole per-frame loop
 // ------------------------------------------------------------------------------------------------
-template<int AM, int SSM, int SM, int T, int OCC>
-__global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBatch b){
-	static_assert(AM == AM_SSD, "this kernel is the SSD instantiation");
+template<int SSM, int SM, int T, int OCC>
+__global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBatch b){
 	constexpr int S = StateSize<SSM>::value;
 	typedef AccLayout<S> L;
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	__shared__ double s_part[(T / 32) * L::NA];
 	__shared__ double s_sum[L::NA];
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8];
+	__shared__ double s_J[S], s_Hc[S*S];
 	__shared__ int s_ctrl;
 	__shared__ double s_dlt[9];
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
@@ -225,9 +167,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
 	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
-	// Levenberg-Marquardt bookkeeping (uniform; only warp 0's copy is used)
-	double prev_similarity = 0, lm_delta = b.lm_delta_init, ssm_update = 0 /* lane l holds entry l */;
-	bool state_reset = false;
+	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };          // uniform; only warp 0's copy is used
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
 	while(iter_id < b.max_iters){
@@ -283,126 +223,33 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 		}
 		block_reduce<L::NA, T>(acc, s_part, s_sum);
 		++n_passes;
-		// ---------------------------------------------------------------- warp 0: decide, solve, update
+		// SSD: f = -sum r^2 / 2 (SSDBase.cc:94), df_dp = sum df_dI * dI_dp, self Hessian = -J^T J (SSDBase.h:91-94)
+		if(tid < S*S){
+			const int i = tid % S, j = tid / S;
+			const int lo = i < j ? i : j, hi = i < j ? j : i;
+			s_Hc[j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];
+			if(tid < S) s_J[tid] = jac_half ? s_sum[1 + tid] * 0.5 : s_sum[1 + tid];
+		}
+		if(T == 32 && S*S > 32){
+			for(int e = tid + 32; e < S*S; e += 32){
+				const int i = e % S, j = e / S;
+				const int lo = i < j ? i : j, hi = i < j ? j : i;
+				s_Hc[j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];
+			}
+		}
+		cta_sync<T>();
 		if(warp == 0){
-			int ctrl = CTRL_NEXT;
-			bool rejected = false;
-			f = -s_sum[0] / 2;                                        // SSDBase.cc:94
-			Mat3 W;
-#pragma unroll
-			for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
-			Mat3 Wn = W;
-			double upd_norm = 0, x = 0;
-			double dp[S];
-			if(b.leven_marq && !state_reset){
-				if(iter_id > 0){
-					if(f < prev_similarity){
-						lm_delta *= b.lm_delta_update;
-#pragma unroll
-						for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, ssm_update, s);
-						if(SM == SM_ICLK){
-							// undo the inverse step by re-applying the forward update (NT/ICLK.cc:183)
-							Wn = compose_update<SSM>(W, dp);
-						} else{
-							double inv[S];
-							invert_state<SSM>(inv, dp);
-							Wn = compose_update<SSM>(W, inv);
-						}
-						state_reset = true; rejected = true; ctrl = CTRL_REJECT;
-					} else if(f > prev_similarity){
-						lm_delta /= b.lm_delta_update;
-					}
-				}
-				if(!rejected) prev_similarity = f;
-			}
-			double Jv = 0;
-			if(!rejected){
-				state_reset = false;
-				WarpColPivQR<S, S> qr;
-				// column `lane` of the Hessian
-				const int jc = lane < S ? lane : 0;
-				int hsel;                                           // 0: -J^T J, 1: init, 2: mean of both
-				if(SM == SM_ESM){
-					hsel = (b.hess_type == MTFB_ESM_HESS_INITIAL_SELF) ? 1 :
-						(b.hess_type == MTFB_ESM_HESS_SUM_OF_SELF || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD) ? 2 : 0;
-				} else if(SM == SM_FCLK){
-					hsel = (b.hess_type == MTFB_LK_HESS_INITIAL_SELF) ? 1 : 0;
-				} else{
-					hsel = (b.hess_type == MTFB_LK_HESS_CURRENT_SELF) ? 0 : 1;
-				}
-#pragma unroll
-				for(int i = 0; i < S; ++i){
-					const int lo = i < jc ? i : jc, hi = i < jc ? jc : i;
-					const double hc = -s_sum[1 + S + L::tri(lo, hi)];
-					const double hi0 = hsel != 0 ? b.Hinit[(size_t)p * 64 + jc*S + i] : 0.0;
-					qr.a[i] = hsel == 0 ? hc : (hsel == 1 ? hi0 : (hc + hi0) * 0.5);
-				}
-				if(lane == S){
-#pragma unroll
-					for(int i = 0; i < S; ++i) qr.a[i] = jac_half ? s_sum[1 + i] * 0.5 : s_sum[1 + i];
-				}
-				if(lane < S) Jv = jac_half ? s_sum[1 + lane] * 0.5 : s_sum[1 + lane];
-				if(b.leven_marq){
-#pragma unroll
-					for(int i = 0; i < S; ++i) if(i == lane) qr.a[i] += lm_delta * qr.a[i];
-				}
-				if(b.log && n_passes <= b.log_slots && lane < S){
-					mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
-#pragma unroll
-					for(int i = 0; i < S; ++i) e->hessian[lane*S + i] = qr.a[i];
-				}
-				qr.factor(lane, true);
-				x = -qr.solve(lane);                                // state_update = -H^-1 J^T
-				if(qr.nonzero_pivots < S) patch_status |= MTFB_PATCH_SINGULAR;
-				ssm_update = x;
-#pragma unroll
-				for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, x, s);
-				if(SM == SM_ICLK){
-					double inv[S];
-					invert_state<SSM>(inv, dp);                     // NT/ICLK.cc:270-271
-					Wn = compose_update<SSM>(W, inv);
-				} else{
-					Wn = compose_update<SSM>(W, dp);
-				}
-			}
-			double nc[8];
-			warp_corners<SSM>(Wn, s_init_corners, nc);
-			if(!rejected){
-#pragma unroll
-				for(int i = 0; i < 8; ++i){ double d = s_corners[i] - nc[i]; upd_norm += d*d; }
-				if(upd_norm < b.epsilon) ctrl = CTRL_BREAK;
-				if(!(upd_norm == upd_norm) || !(f == f)) patch_status |= MTFB_PATCH_NAN;
-			}
-			__syncwarp();
-			if(lane < 9) s_W[lane] = Wn.m[lane];
-			if(lane < 8) s_corners[lane] = nc[lane];
+			f = -s_sum[0] / 2;
+			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+				lm, patch_status);
 			if(lane == 0) s_ctrl = ctrl;
-			if(b.log && n_passes <= b.log_slots){
-				mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
-				if(lane < S){ e->jacobian[lane] = rejected ? 0.0 : Jv; e->state_update[lane] = rejected ? 0.0 : x; }
-				if(lane < 8) e->corners[lane] = nc[lane];
-				if(lane == 0){ e->f = f; e->update_norm = upd_norm; e->rejected = rejected; e->valid = 1; }
-			}
 		}
 		cta_sync<T>();
 		const int ctrl = s_ctrl;
 		if(ctrl == CTRL_BREAK) break;
-		// nt::FCLK re-enters its while loop without counting a rejected step (NT/FCLK.cc:187,210);
-		// every other loop is a for(...; ++iter_id) (FCLK.cc:117,135, ESM.cc:128, NT/ESM.cc:186, ICLK.cc:150, NT/ICLK.cc:167)
-		if(!(ctrl == CTRL_REJECT && SM == SM_FCLK && b.nt_semantics)) ++iter_id;
+		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
 	}
-	if(warp == 0){
-		Mat3 W;
-#pragma unroll
-		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
-		double st[S];
-		state_from_warp<SSM>(st, W);
-		if(lane < 9) b.warp[(size_t)p * 9 + lane] = W.m[lane];
-		if(lane < 8) b.corners[(size_t)p * 8 + lane] = s_corners[lane];
-#pragma unroll
-		for(int s = 0; s < S; ++s) if(lane == s) b.state[(size_t)p*S + s] = st[s];
-		if(lane == 0){ b.f[p] = f; b.n_iters[p] = n_passes; b.status[p] = patch_status; }
-	}
+	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,17 +259,13 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) lk_update_kernel(DevBat
 __global__ void lk_set_region_kernel(DevBatch b, const double *__restrict__ corners_in, int S){
 	const int p = blockIdx.x, lane = threadIdx.x;
 	const double *c_in = corners_in + (size_t)p * 8;
-	Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
-	Mat3 I = mat3_identity();
-	if(lane < 9){ b.dlt[(size_t)p * 9 + lane] = dlt.m[lane]; b.warp[(size_t)p * 9 + lane] = I.m[lane]; }
-	if(lane < S) b.state[(size_t)p*S + lane] = 0;
-	if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }
+	if(S == 8) set_corners<SSM_HOM>(b, p, lane, c_in); else set_corners<SSM_AFF>(b, p, lane, c_in);
 }
 
 // ------------------------------------------------------------------------------------------------
 // stage taps: pts / It / dIt_dx / dIt_dp at the current state, through the same device functions
 // ------------------------------------------------------------------------------------------------
-template<int AM, int SSM, int T>
+template<int SSM, int T>
 __global__ void __launch_bounds__(T) lk_stage_kernel(DevBatch b, StageTaps t){
 	constexpr int S = StateSize<SSM>::value;
 	const int p = blockIdx.x, tid = threadIdx.x;
@@ -435,7 +278,7 @@ __global__ void __launch_bounds__(T) lk_stage_kernel(DevBatch b, StageTaps t){
 	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
 		double val, gx, gy;
-		sample_pixel_grad<AM != AM_MI>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		sample_pixel_grad<false>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
 		val = b.pix_mult*val + b.pix_add;
 		double J[S];
 		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
@@ -452,78 +295,70 @@ __global__ void __launch_bounds__(T) lk_stage_kernel(DevBatch b, StageTaps t){
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-bool combo_supported(int am, int ssm, int sm){
-	return am == AM_SSD && (ssm == SSM_HOM || ssm == SSM_AFF) && (sm == SM_ESM || sm == SM_FCLK || sm == SM_ICLK);
-}
-
-template<int AM, int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+template<int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
 	switch(threads){
-	case 32: lk_init_kernel<AM, SSM, 32><<<b.P, 32, 0, st>>>(b, d_corners); break;
-	case 64: lk_init_kernel<AM, SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners); break;
-	case 128: lk_init_kernel<AM, SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners); break;
-	case 256: lk_init_kernel<AM, SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners); break;
+	case 32: ssd_init_kernel<SSM, 32><<<b.P, 32, 0, st>>>(b, d_corners); break;
+	case 64: ssd_init_kernel<SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners); break;
+	case 128: ssd_init_kernel<SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners); break;
+	case 256: ssd_init_kernel<SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
-cudaError_t launch_init(int am, int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
-	if(am != AM_SSD) return cudaErrorNotSupported;
-	if(ssm == SSM_HOM) return launch_init_t<AM_SSD, SSM_HOM>(threads, b, d_corners, st);
-	return launch_init_t<AM_SSD, SSM_AFF>(threads, b, d_corners, st);
+cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	if(ssm == SSM_HOM) return launch_init_t<SSM_HOM>(threads, b, d_corners, st);
+	return launch_init_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
-cudaError_t launch_set_region(int am, int ssm, int sm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
-	(void)am; (void)sm; (void)threads;
+cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st){
 	lk_set_region_kernel<<<b.P, 32, 0, st>>>(b, d_corners, ssm == SSM_HOM ? 8 : 6);
 	return cudaGetLastError();
 }
 
-template<int AM, int SSM, int SM, int OCC> static cudaError_t launch_update_o(int threads, const DevBatch &b, cudaStream_t st){
+template<int SSM, int SM, int OCC> static cudaError_t launch_update_o(int threads, const DevBatch &b, cudaStream_t st){
 	switch(threads){
-	case 32: lk_update_kernel<AM, SSM, SM, 32, OCC><<<b.P, 32, 0, st>>>(b); break;
-	case 64: lk_update_kernel<AM, SSM, SM, 64, OCC><<<b.P, 64, 0, st>>>(b); break;
-	case 128: lk_update_kernel<AM, SSM, SM, 128, OCC><<<b.P, 128, 0, st>>>(b); break;
-	case 256: lk_update_kernel<AM, SSM, SM, 256, OCC><<<b.P, 256, 0, st>>>(b); break;
+	case 32: ssd_update_kernel<SSM, SM, 32, OCC><<<b.P, 32, 0, st>>>(b); break;
+	case 64: ssd_update_kernel<SSM, SM, 64, OCC><<<b.P, 64, 0, st>>>(b); break;
+	case 128: ssd_update_kernel<SSM, SM, 128, OCC><<<b.P, 128, 0, st>>>(b); break;
+	case 256: ssd_update_kernel<SSM, SM, 256, OCC><<<b.P, 256, 0, st>>>(b); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
-template<int AM, int SSM, int SM> static cudaError_t launch_update_t(int threads, int occ, const DevBatch &b, cudaStream_t st){
-	if(occ == 0) return launch_update_o<AM, SSM, SM, 0>(threads, b, st);
-	if(occ == 1) return launch_update_o<AM, SSM, SM, 1>(threads, b, st);
-	return launch_update_o<AM, SSM, SM, 2>(threads, b, st);
+template<int SSM, int SM> static cudaError_t launch_update_t(int threads, int occ, const DevBatch &b, cudaStream_t st){
+	if(occ == 0) return launch_update_o<SSM, SM, 0>(threads, b, st);
+	if(occ == 1) return launch_update_o<SSM, SM, 1>(threads, b, st);
+	return launch_update_o<SSM, SM, 2>(threads, b, st);
 }
-cudaError_t launch_update(int am, int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st){
-	if(!combo_supported(am, ssm, sm)) return cudaErrorNotSupported;
+cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st){
 #ifdef MTFB_ONLY_FCLK_HOM      // experiment builds (profiles/): one combination, fast to compile
-	if(ssm == SSM_HOM && sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, occ, b, st);
+	if(ssm == SSM_HOM && sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, st);
 	return cudaErrorNotSupported;
 #else
 	if(ssm == SSM_HOM){
-		if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_HOM, SM_ESM>(threads, occ, b, st);
-		if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_HOM, SM_FCLK>(threads, occ, b, st);
-		return launch_update_t<AM_SSD, SSM_HOM, SM_ICLK>(threads, occ, b, st);
+		if(sm == SM_ESM) return launch_update_t<SSM_HOM, SM_ESM>(threads, occ, b, st);
+		if(sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, st);
+		return launch_update_t<SSM_HOM, SM_ICLK>(threads, occ, b, st);
 	}
-	if(sm == SM_ESM) return launch_update_t<AM_SSD, SSM_AFF, SM_ESM>(threads, occ, b, st);
-	if(sm == SM_FCLK) return launch_update_t<AM_SSD, SSM_AFF, SM_FCLK>(threads, occ, b, st);
-	return launch_update_t<AM_SSD, SSM_AFF, SM_ICLK>(threads, occ, b, st);
+	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, occ, b, st);
+	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, occ, b, st);
+	return launch_update_t<SSM_AFF, SM_ICLK>(threads, occ, b, st);
 #endif
 }
 
-template<int AM, int SSM> static cudaError_t launch_stage_t(int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
+template<int SSM> static cudaError_t launch_stage_t(int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
 	switch(threads){
-	case 32: lk_stage_kernel<AM, SSM, 32><<<b.P, 32, 0, st>>>(b, t); break;
-	case 64: lk_stage_kernel<AM, SSM, 64><<<b.P, 64, 0, st>>>(b, t); break;
-	case 128: lk_stage_kernel<AM, SSM, 128><<<b.P, 128, 0, st>>>(b, t); break;
-	case 256: lk_stage_kernel<AM, SSM, 256><<<b.P, 256, 0, st>>>(b, t); break;
+	case 32: lk_stage_kernel<SSM, 32><<<b.P, 32, 0, st>>>(b, t); break;
+	case 64: lk_stage_kernel<SSM, 64><<<b.P, 64, 0, st>>>(b, t); break;
+	case 128: lk_stage_kernel<SSM, 128><<<b.P, 128, 0, st>>>(b, t); break;
+	case 256: lk_stage_kernel<SSM, 256><<<b.P, 256, 0, st>>>(b, t); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
-cudaError_t launch_stage(int am, int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
-	(void)am;
-	if(ssm == SSM_HOM) return launch_stage_t<AM_SSD, SSM_HOM>(threads, b, t, st);
-	return launch_stage_t<AM_SSD, SSM_AFF>(threads, b, t, st);
+cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
+	if(ssm == SSM_HOM) return launch_stage_t<SSM_HOM>(threads, b, t, st);
+	return launch_stage_t<SSM_AFF>(threads, b, t, st);
 }
 
 } // namespace mtfb

@@ -15,7 +15,7 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 // ------------------------------------------------------------------------------------------------
 // Butterfly "reduce-scatter" across the 32 lanes of a warp.
 // In: v[0..CNT) per lane.  Out: the warp-wide sum of entry e is left in exactly one lane; every lane ends
-// with at most 2 live entries in v[0], v[1] whose entry indices are idx0 / idx1 (-1 = none).
+// with at most 3 live entries in v[0..2] whose entry indices are idx[0..2] (-1 = none).
 // Costs about CNT 64-bit shuffles in total instead of 5*CNT for CNT independent all-reduces.
 // ------------------------------------------------------------------------------------------------
 template<int CNT, int MASK> struct Butterfly {
@@ -38,11 +38,11 @@ template<int CNT, int MASK> struct Butterfly {
 
 template<int CNT> struct ReduceMap {
 	static constexpr int H1 = (CNT + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2, H4 = (H3 + 1) / 2, H5 = (H4 + 1) / 2;
-	static_assert(H5 <= 2, "accumulator vector too long for the 32-lane butterfly (max 64 entries)");
+	static_assert(H5 <= 3, "accumulator vector too long for the 32-lane butterfly (max 96 entries)");
 };
 
-// returns through idx[0..1] the accumulator entry each of v[0], v[1] holds (or -1)
-template<int CNT> __device__ __forceinline__ void warp_reduce_scatter(double (&v)[CNT], int lane, int (&idx)[2]){
+// returns through idx[0..2] the accumulator entry each of v[0..2] holds (or -1)
+template<int CNT> __device__ __forceinline__ void warp_reduce_scatter(double (&v)[CNT], int lane, int (&idx)[3]){
 	typedef ReduceMap<CNT> M;
 	int dummy = 0; bool ok = true;
 	Butterfly<CNT, 16>::run(v, lane, dummy, ok);
@@ -52,7 +52,7 @@ template<int CNT> __device__ __forceinline__ void warp_reduce_scatter(double (&v
 	Butterfly<M::H4, 1>::run(v, lane, dummy, ok);
 	const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
 #pragma unroll
-	for(int j = 0; j < 2; ++j){
+	for(int j = 0; j < 3; ++j){
 		bool valid = j < M::H5;
 		int s4 = j + M::H5*b0;  valid = valid && (s4 < M::H4);     // slot at level 4
 		int s3 = s4 + M::H4*b1; valid = valid && (s3 < M::H3);

@@ -37,6 +37,39 @@ void lin_spaced(std::vector<double> &out, int size, double low, double high){
 	}
 }
 
+bool combo_supported(const mtfb_params *p, const char **why){
+	*why = "";
+	const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
+	if(!(p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE)){ *why = "ssm must be homography or affine"; return false; }
+	if(p->sm == MTFB_SM_PF){
+		if(p->am != MTFB_AM_SSD){ *why = "PF particle evaluation is implemented for SSD only"; return false; }
+		return true;
+	}
+	if(!gn){ *why = "sm must be esm, fclk, iclk or pf"; return false; }
+	if(p->am == MTFB_AM_SSD) return true;
+	if(p->am == MTFB_AM_NCC){
+		// the self Hessians (NCC.cc:337-389) are implemented; the Std / Original / SumOfStd forms (NCC.cc:282-336) are not
+		bool ok;
+		if(p->sm == MTFB_SM_ESM) ok = p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS && (p->hess_type == MTFB_ESM_HESS_INITIAL_SELF ||
+			p->hess_type == MTFB_ESM_HESS_CURRENT_SELF || p->hess_type == MTFB_ESM_HESS_SUM_OF_SELF);
+		else if(p->sm == MTFB_SM_FCLK) ok = p->hess_type == MTFB_LK_HESS_INITIAL_SELF || p->hess_type == MTFB_LK_HESS_CURRENT_SELF;
+		else ok = p->hess_type == MTFB_LK_HESS_INITIAL_SELF;
+		if(!ok) *why = "NCC: only the self Hessians (and ESM's DiffOfJacs Jacobian) are implemented";
+		return ok;
+	}
+	*why = "am must be ssd or ncc";
+	return false;
+}
+
+cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	if(p.am == MTFB_AM_NCC) return launch_init_ncc(p.ssm, threads, b, d_corners, st);
+	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
+}
+cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, cudaStream_t st){
+	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
+	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, st);
+}
+
 } // namespace
 
 struct mtfb_ctx {
@@ -93,10 +126,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	*out = nullptr;
 	if(p->resx < 2 || p->resy < 2 || p->n_patches < 1 || p->max_iters < 1)
 		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: resx/resy >= 2, n_patches >= 1, max_iters >= 1 required");
-	if(p->sm != MTFB_SM_PF && !combo_supported(p->am, p->ssm, p->sm))
-		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: (am %d, ssm %d, sm %d) is not implemented", p->am, p->ssm, p->sm);
-	if(p->sm == MTFB_SM_PF && !(p->am == MTFB_AM_SSD && (p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE)))
-		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: PF evaluation is implemented for SSD only");
+	const char *why;
+	if(!combo_supported(p, &why))
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: (am %d, ssm %d, sm %d, hess %d, jac %d) is not implemented: %s",
+			p->am, p->ssm, p->sm, p->hess_type, p->jac_type, why);
 	if(!p->chained_warp)
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: chained_warp = 0 (getWarpedImgGrad path) is not implemented");
 	if(p->hom_normalized_init)
@@ -149,7 +182,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		if(cudaMalloc(&c->d_grid, grid.size()*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemcpy(c->d_grid, grid.data(), grid.size()*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		// per-patch arrays
-		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1;
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8;
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -166,6 +199,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.init_corners = q; q += 8 * (size_t)P;
 		b.Hinit = q; q += 64 * (size_t)P;
 		b.f = q; q += (size_t)P;
+		b.am_scal = q; q += 8 * (size_t)P;
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
@@ -247,7 +281,7 @@ static mtfb_status upload_corners(mtfb_ctx *c, const double *corners, const char
 mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 	mtfb_status st = upload_corners(c, corners, "mtfb_initialize");
 	if(st != MTFB_OK) return st;
-	CUDA_TRY(launch_init(c->prm.am, c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
+	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
 	c->initialized = true;
 	return MTFB_OK;
@@ -263,7 +297,7 @@ mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	}
 	mtfb_status st = upload_corners(c, corners, "mtfb_set_region");
 	if(st != MTFB_OK) return st;
-	CUDA_TRY(launch_set_region(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->b, c->d_corners_in, c->stream));
+	CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -274,7 +308,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->occ, c->b, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -326,7 +360,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm.am, c->prm.ssm, c->prm.sm, c->threads, c->occ, b, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->stream));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);
@@ -340,13 +374,32 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	return MTFB_OK;
 }
 
-mtfb_status mtfb_pf_evaluate(mtfb_ctx *c, const double *, int, double *, double *){
-	(void)c;
-	return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate: not implemented yet");
+mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *c, const double *d_states, int n_particles, double *d_likelihood, double *d_similarity){
+	if(!c || !d_states || n_particles < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_evaluate_device: bad argument");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_pf_evaluate_device: initialize has not been called");
+	if(c->prm.am != MTFB_AM_SSD) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate_device: implemented for SSD only");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(launch_pf_evaluate(c->prm.am, c->prm.ssm, c->b, d_states, n_particles, d_likelihood, d_similarity,
+		c->prm.likelihood_alpha, c->stream));
+	++c->launches;
+	return MTFB_OK;
 }
-mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *c, const double *, int, double *, double *){
-	(void)c;
-	return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate_device: not implemented yet");
+
+mtfb_status mtfb_pf_evaluate(mtfb_ctx *c, const double *states, int n_particles, double *likelihood, double *similarity){
+	if(!c || !states || n_particles < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_evaluate: bad argument");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_pf_evaluate: initialize has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t n = (size_t)c->P*n_particles;
+	mtfb_status st = ensure_scratch(c, (n*c->S + 2 * n)*sizeof(double));
+	if(st != MTFB_OK) return st;
+	double *d_states = c->d_scratch, *d_lik = d_states + n*c->S, *d_sim = d_lik + n;
+	CUDA_TRY(cudaMemcpyAsync(d_states, states, n*c->S*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	st = mtfb_pf_evaluate_device(c, d_states, n_particles, d_lik, d_sim);
+	if(st != MTFB_OK) return st;
+	if(likelihood) CUDA_TRY(cudaMemcpyAsync(likelihood, d_lik, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(similarity) CUDA_TRY(cudaMemcpyAsync(similarity, d_sim, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
 }
 
 #define GETTER_PRELUDE(name) \
@@ -375,7 +428,7 @@ mtfb_status mtfb_get_curr_stage(mtfb_ctx *c, double *pts, double *pix_vals, doub
 	t.pix_vals = pix_vals ? q : nullptr; q += n_val;
 	t.pix_grad = pix_grad ? q : nullptr; q += n_grad;
 	t.pix_jac = pix_jac ? q : nullptr;
-	CUDA_TRY(launch_stage(c->prm.am, c->prm.ssm, c->threads, c->b, t, c->stream));
+	CUDA_TRY(launch_stage(c->prm.ssm, c->threads, c->b, t, c->stream));
 	++c->launches;
 	if(pts) CUDA_TRY(cudaMemcpyAsync(pts, t.pts, n_pts*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if(pix_vals) CUDA_TRY(cudaMemcpyAsync(pix_vals, t.pix_vals, n_val*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -401,7 +454,7 @@ mtfb_status mtfb_get_init_pts(mtfb_ctx *c, double *out){
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	b.warp = d_eye;
 	StageTaps t = { d_pts, nullptr, nullptr, nullptr };
-	CUDA_TRY(launch_stage(c->prm.am, c->prm.ssm, c->threads, b, t, c->stream));
+	CUDA_TRY(launch_stage(c->prm.ssm, c->threads, b, t, c->stream));
 	++c->launches;
 	return d2h(c, out, d_pts, 2 * N*P*sizeof(double));
 }

@@ -232,3 +232,116 @@ def test_error_contract(seq384):
     with pytest.raises(api.MTFError) as e:
         g.initialize(bad)
     assert e.value.type == "InvalidArgument"
+
+
+# ------------------------------------------------------------------------------------------------ NCC
+NCC_FIRST_RTOL = 1e-9   # the centred products are formed from raw sums (sum D D^T - N m m^T): a few digits of cancellation
+NCC_LATER_RTOL = 1e-6
+
+
+@pytest.mark.parametrize("sm", SMS)
+@pytest.mark.parametrize("ssm", SSMS)
+def test_ncc_iteration_log_parity(seq384, sm, ssm):
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=11)])
+    g = _gpu("ncc", ssm, sm, len(cs))
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("ncc", ssm, sm, grad_mode=1)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs = g.iter_log()
+        n_it = g.n_iters()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert n_it[i] == o.n_iters == len(ol) == len(logs[i])
+            for k, (a, b) in enumerate(zip(logs[i], ol)):
+                first = fr is frames[1] and k == 0
+                tol = NCC_FIRST_RTOL if first else NCC_LATER_RTOL
+                assert abs(a["f"] - b["f"]) <= tol
+                assert _rel(a["jacobian"], b["jacobian"]) <= tol * 10
+                assert _rel(a["hessian"], b["hessian"]) <= tol
+                assert np.abs(a["corners"] - b["corners"]).max() <= 10 * CORNER_ATOL_EXACT
+        assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= 10 * CORNER_ATOL_EXACT
+
+
+@pytest.mark.parametrize("res", [10, 25])
+def test_ncc_affine_grid_cells(seq384, res):
+    """BASELINE config 3: ESM + NCC + Affine on a grid of small cells (GridTracker.cc:345-392 initialises every cell as
+    an axis-aligned patch_size x patch_size square around its centroid), vs the reference finite-difference oracle"""
+    from mtf_b200 import synth
+    frames, warps = seq384
+    rng = np.random.default_rng(5)
+    n = 36
+    cx = rng.uniform(60, 320, n); cy = rng.uniform(60, 320, n)
+    half = res / 2.0
+    cs = np.stack([np.stack([cx - half, cx + half, cx + half, cx - half], -1),
+                   np.stack([cy - half, cy - half, cy + half, cy + half], -1)], 1)
+    g = _gpu("ncc", "affine", "esm", n, resx=res, resy=res)
+    g.initialize(cs, frames[0])
+    g.update(frames[1])
+    gc, gi = g.getRegion(), g.n_iters()
+    ok = 0
+    for i in range(n):
+        o = _oracle("ncc", "affine", "esm", grad_mode=0, resx=res, resy=res)
+        o.set_image(frames[0]); o.initialize(cs[i]); o.set_image(frames[1]); o.update()
+        assert abs(int(gi[i]) - o.n_iters) <= 1
+        ok += int(gi[i]) == o.n_iters
+        # tiny, weakly textured cells: allow the reference quotient's gradient noise to move a slow-converging cell
+        assert np.abs(gc[i] - o.corners()).max() <= 2e-2
+    assert ok >= 0.85 * n
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+@pytest.mark.parametrize("lm", [0, 1])
+def test_ncc_tracking_vs_reference_fd(seq384, ssm, lm):
+    frames, warps = seq384
+    cs = np.concatenate([common.patches(5, 49.0, 384, 384), common.patches(5, 52.3, 384, 384, seed=5)])
+    for sm in SMS:
+        g = _gpu("ncc", ssm, sm, len(cs), leven_marq=lm)
+        g.initialize(cs, frames[0])
+        orcs = []
+        for c in cs:
+            o = _oracle("ncc", ssm, sm, grad_mode=0, leven_marq=lm)
+            o.set_image(frames[0]); o.initialize(c)
+            orcs.append(o)
+        for t in (1, 2):
+            g.update(frames[t])
+            for o in orcs:
+                o.set_image(frames[t]); o.update()
+            assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= CORNER_ATOL_FD
+            oi = np.array([o.n_iters for o in orcs])
+            assert (np.abs(g.n_iters() - oi) <= 1).all()
+
+
+# ------------------------------------------------------------------------------------------------ PF
+@pytest.mark.parametrize("ssm", SSMS)
+def test_pf_evaluate(seq384, ssm):
+    """per-particle parity (the reference's particle trajectories are seeded from random_device, so
+    parity is defined per particle given the state)"""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(2, 49.0, 384, 384), common.quad_patches(2, 384, 384, seed=4)])
+    S = 8 if ssm == "homography" else 6
+    n = 300
+    rng = np.random.default_rng(9)
+    scale = np.array([2e-2, 2e-2, 2.0, 2e-2, 2e-2, 2.0, 1e-5, 1e-5]) if S == 8 else np.array([2.0, 2.0, 2e-2, 2e-2, 2e-2, 2e-2])
+    states = rng.normal(size=(len(cs), n, S)) * scale
+    states[:, 0] = 0
+    states[0, 1, 2 if S == 8 else 0] = 400.0          # a particle thrown out of the image: samples the constant 128
+    g = _gpu("ssd", ssm, "pf", len(cs), likelihood_alpha=50.0)
+    g.initialize(cs, frames[0])
+    g.setImage(frames[1])
+    lik, sim = g.pf_evaluate(states)
+    for i, c in enumerate(cs):
+        o = _oracle("ssd", ssm, "fclk", likelihood_alpha=50.0)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1])
+        ol, os_ = o.pf_evaluate(states[i])
+        assert np.allclose(sim[i], os_, rtol=1e-12, atol=0)
+        assert np.allclose(lik[i], ol, rtol=1e-11, atol=1e-300)
+    with pytest.raises(Exception):
+        g.update()
