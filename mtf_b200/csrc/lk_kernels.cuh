@@ -45,6 +45,11 @@ cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTap
 // lk_ncc.cu
 cudaError_t launch_init_ncc(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_update_ncc(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
+// lk_mi.cu (mi_tab: P x 32 doubles of per-template histogram tables)
+cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double *d_corners, int n_bins, double pre_seed,
+	double *mi_tab, cudaStream_t st);
+cudaError_t launch_update_mi(int ssm, int sm, int threads, const DevBatch &b, int n_bins, double pre_seed, const double *mi_tab,
+	cudaStream_t st);
 // pf_kernels.cu
 cudaError_t launch_pf_evaluate(int am, int ssm, const DevBatch &b, const double *d_states, int n_particles,
 	double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st);

@@ -1,0 +1,390 @@
+// lk_mi.cu -- the fused Lucas-Kanade kernels for the MI appearance model (sm_100a).
+//
+// Reference (AM/src/MI.cc): mutual information with a cubic-B-spline Parzen joint histogram.
+//   updateSimilarity :346-382   curr_hist (B), joint_hist (B x B) from 4 x 4 B-spline weights per pixel, logs,
+//                               f = sum p_ij (log p_ij - log p_i - log q_j)
+//   updateCurrGrad  :426-443    df_dIt(pix) = sum_{4x4} curr_hist_grad . init_hist_mat . (1 + log p_ij - log p_i)
+//   updateInitGrad  :398-417    df_dI0(pix) likewise with the roles swapped
+//   cmptSelfHessian :515-594, cmptSelfHist :639-658   (evaluated once, at initialize(): init_self_hessian)
+//   B-splines: Utilities/include/mtf/Utilities/histUtils.h:206-224 (bSpl3WithGrad), :269-280 (bSpl3Hess)
+// The reference materialises B x N weight matrices and a B^2 x N joint-gradient matrix (zero-filled every
+// pass: 5 MB at N = 10^4); here the 4 weights of a pixel are recomputed from its value where they are used.
+// One pass = sweep 1 (warp + sample, values kept in shared memory, histograms built with shared-memory fp64
+// atomics), a 72-entry log table, sweep 2 (per-pixel gradient weight from a 4 x 4 table gather, pixel
+// Jacobian row, S or 2S sums).  Implemented Hessian: InitialSelf (the ICLK default, ICLKParams.cc:6).
+// Histogram atomics make the summation order, hence the last bits of f, vary from run to run.
+#include "lk_solve.cuh"
+
+namespace mtfb {
+
+constexpr int MI_BMAX = 16;
+
+// histUtils.h:206-224
+__device__ __forceinline__ void bspl3_with_grad(double &val, double &diff, double x){
+	val = 0; diff = 0;
+	if((x > -2) && (x <= -1)){
+		double temp = 2 + x; diff = (temp * temp) / 2; val = (diff * temp) / 3;
+	} else if((x > -1) && (x <= 0)){
+		double temp = x / 2; val = (2.0 / 3.0) - x*x*(1 + temp); diff = -x * (temp + x + 2);
+	} else if((x > 0) && (x <= 1)){
+		double temp = x / 2; val = (2.0 / 3.0) - x*x*(1 - temp); diff = x * (temp + x - 2);
+	} else if((x > 1) && (x < 2)){
+		double temp = 2 - x; diff = -(temp * temp) / 2; val = -(diff * temp) / 3;
+	}
+}
+// histUtils.h:269-280
+__device__ __forceinline__ double bspl3_hess(double x){
+	if((x > -2) && (x <= -1)) return 2 + x;
+	if((x > -1) && (x <= 0)) return -(3 * x + 2);
+	if((x > 0) && (x <= 1)) return 3 * x - 2;
+	if((x > 1) && (x < 2)) return 2 - x;
+	return 0;
+}
+
+// the (up to) 4 histogram bins a pixel value touches and its B-spline weights / derivatives (MI.cc:231-243)
+struct BinWeights { int lo, hi; double w[4], d[4]; };
+__device__ __forceinline__ BinWeights bin_weights(double v, int B){
+	BinWeights o;
+	const int bin = static_cast<int>(v);
+	o.lo = bin - 1 > 0 ? bin - 1 : 0;
+	o.hi = bin + 2 < B - 1 ? bin + 2 : B - 1;
+	double x = o.lo - v;
+#pragma unroll
+	for(int k = 0; k < 4; ++k){
+		bspl3_with_grad(o.w[k], o.d[k], x);
+		if(o.lo + k > o.hi){ o.w[k] = 0; o.d[k] = 0; }
+		x += 1;
+	}
+	return o;
+}
+
+struct MiParams { int B; double pre_seed, hist_pre_seed, hist_norm_mult; };
+
+// per-template table kept in global memory (P x MI_TAB doubles): [0..B) init_hist, [16..16+B) init_hist_log
+constexpr int MI_TAB = 32;
+
+template<int SSM, int T>
+__global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__restrict__ corners_in, MiParams mp, double *mi_tab){
+	constexpr int S = StateSize<SSM>::value;
+	constexpr int NH = S*(S + 1) / 2;
+	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int B = mp.B, N = b.N;
+	__shared__ double s_dlt[9];
+	__shared__ double s_hist[MI_BMAX], s_hist_log[MI_BMAX], s_joint[MI_BMAX*MI_BMAX], s_factor[MI_BMAX*MI_BMAX];
+	__shared__ double s_jhj[MI_BMAX*MI_BMAX*S];
+	__shared__ double s_part[(T / 32) * NH];
+	__shared__ double s_sum[NH];
+	const double *c_in = corners_in + (size_t)p * 8;
+	if(warp == 0){
+		Mat3 dlt = set_corners<SSM>(b, p, lane, c_in);
+		if(lane < 9) s_dlt[lane] = dlt.m[lane];
+		if(lane == 0){ b.n_iters[p] = 0; b.status[p] = 0; }
+	}
+	for(int i = tid; i < B; i += T) s_hist[i] = mp.hist_pre_seed;
+	for(int i = tid; i < B*B; i += T) s_joint[i] = mp.pre_seed;
+	for(int i = tid; i < B*B*S; i += T) s_jhj[i] = 0;
+	cta_sync<T>();
+	Mat3 dlt, W = mat3_identity();
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	const double abcd[4] = { 1, 0, 0, 1 };
+	double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
+	// phase 1: template values (scaled to bin units, MI.cc:91-94), chained gradient, init_hist and the self joint histogram
+	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		double val, gx, gy;
+		sample_pixel_grad<false>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		val = b.pix_mult*val + b.pix_add;
+		double J[S];
+		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
+		I0[it.pix] = val;
+		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
+		G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+		const BinWeights bw = bin_weights(val, B);
+#pragma unroll
+		for(int k = 0; k < 4; ++k){
+			if(bw.lo + k > bw.hi) continue;
+			atomicAdd(&s_hist[bw.lo + k], bw.w[k]);
+#pragma unroll
+			for(int l = 0; l < 4; ++l){
+				if(bw.lo + l > bw.hi) continue;
+				atomicAdd(&s_joint[(bw.lo + l)*B + (bw.lo + k)], bw.w[k] * bw.w[l]);        // JH(id1, id2): column-major
+			}
+		}
+	}
+	cta_sync<T>();
+	for(int i = tid; i < B; i += T){
+		const double h = s_hist[i] * mp.hist_norm_mult;
+		s_hist[i] = h; s_hist_log[i] = log(h);
+		mi_tab[(size_t)p*MI_TAB + i] = h; mi_tab[(size_t)p*MI_TAB + 16 + i] = s_hist_log[i];
+	}
+	cta_sync<T>();
+	for(int i = tid; i < B*B; i += T){
+		const double jh = s_joint[i] * mp.hist_norm_mult;
+		s_joint[i] = jh;
+		const int r = i % B;                                              // JH(r, c) = m[c*B + r]
+		s_factor[i] = 1 + log(jh) - s_hist_log[r];                        // self_grad_factor(curr = r, init = c) (MI.cc:655)
+	}
+	cta_sync<T>();
+	if(tid == 0){
+		// f = max_similarity = MI of the template with itself (MI.cc:270-283)
+		double f = 0;
+		for(int c = 0; c < B; ++c) for(int r = 0; r < B; ++r){
+			const double jh = s_joint[c*B + r];
+			f += jh * (log(jh) - s_hist_log[r] - s_hist_log[c]);
+		}
+		b.f[p] = f;
+	}
+	// phase 2: init_self_hessian = cmptSelfHessian(init_pix_jacobian) (MI.cc:515-594; at initialize() the current
+	// histograms are the initial ones)
+	double acc[NH];
+#pragma unroll
+	for(int i = 0; i < NH; ++i) acc[i] = 0;
+	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		double D[S];
+		init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D);
+		const double v = I0[it.pix];
+		const BinWeights bw = bin_weights(v, B);
+		double x = bw.lo - v, hist_hess_term = 0;
+#pragma unroll
+		for(int k = 0; k < 4; ++k){
+			const int curr_id = bw.lo + k;
+			const double hess_w = mp.hist_norm_mult * bspl3_hess(x);
+			x += 1;
+			if(curr_id > bw.hi) continue;
+			const double grad_k = bw.d[k] * (-mp.hist_norm_mult);           // curr_hist_grad (MI.cc:240)
+			double inner = 0;
+#pragma unroll
+			for(int l = 0; l < 4; ++l){
+				const int init_id = bw.lo + l;
+				if(init_id > bw.hi) continue;
+				const double gq = grad_k * bw.w[l];
+#pragma unroll
+				for(int s = 0; s < S; ++s) atomicAdd(&s_jhj[(curr_id*B + init_id)*S + s], gq * D[s]);
+				inner += bw.w[l] * s_factor[init_id*B + curr_id];
+			}
+			hist_hess_term += hess_w * inner;
+		}
+#pragma unroll
+		for(int i = 0; i < S; ++i){
+#pragma unroll
+			for(int j = i; j < S; ++j) acc[i*S - i*(i - 1) / 2 + (j - i)] = fma(hist_hess_term * D[i], D[j], acc[i*S - i*(i - 1) / 2 + (j - i)]);
+		}
+	}
+	block_reduce<NH, T>(acc, s_part, s_sum);             // also orders the atomics on s_jhj before the reads below
+	for(int e = tid; e < S*S; e += T){
+		const int i = e % S, j = e / S;
+		const int lo = i < j ? i : j, hi = i < j ? j : i;
+		double h = s_sum[lo*S - lo*(lo - 1) / 2 + (hi - lo)];
+		// + sum over joint bins of row^T row (1 / self_joint(curr, init) - 1 / curr_hist(curr)) (MI.cc:578-590)
+		for(int curr_id = 0; curr_id < B; ++curr_id) for(int init_id = 0; init_id < B; ++init_id){
+			const double hist_factor = (1.0 / s_joint[init_id*B + curr_id]) - (1.0 / s_hist[curr_id]);
+			const double *row = &s_jhj[(curr_id*B + init_id)*S];
+			h += row[i] * row[j] * hist_factor;
+		}
+		b.Hinit[(size_t)p * 64 + j*S + i] = h;
+	}
+}
+
+template<int SSM, int SM, int T>
+__global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch b, MiParams mp, const double *__restrict__ mi_tab){
+	constexpr int S = StateSize<SSM>::value;
+	constexpr bool CURR = (SM != SM_ICLK), INIT = (SM != SM_FCLK);
+	constexpr int NA = (CURR ? S : 0) + (INIT ? S : 0);
+	constexpr int oT = 0, o0 = CURR ? S : 0;
+	extern __shared__ __align__(16) double s_It[];                          // N current pixel values (bin units)
+	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int B = mp.B, N = b.N;
+	__shared__ double s_part[(T / 32) * NA];
+	__shared__ double s_sum[NA];
+	__shared__ double s_hist[MI_BMAX], s_hist_log[MI_BMAX], s_ihist_log[MI_BMAX], s_joint[MI_BMAX*MI_BMAX];
+	__shared__ double s_fac_t[MI_BMAX*MI_BMAX], s_fac_0[MI_BMAX*MI_BMAX];
+	__shared__ double s_W[9], s_dlt[9], s_corners[8], s_init_corners[8], s_J[S], s_f;
+	__shared__ int s_ctrl;
+	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
+	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
+	for(int i = tid; i < B; i += T) s_ihist_log[i] = mi_tab[(size_t)p*MI_TAB + 16 + i];
+	cta_sync<T>();
+	Mat3 dlt;
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	const double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
+	const bool jac_half = (SM == SM_ESM);
+	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
+	int iter_id = 0, n_passes = 0, patch_status = 0;
+	double f = 0;
+	while(iter_id < b.max_iters){
+		Mat3 W;
+#pragma unroll
+		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
+		double abcd[4] = { (W.m[0] - 1) + 1, W.m[1], W.m[3], (W.m[4] - 1) + 1 };
+		for(int i = tid; i < B; i += T) s_hist[i] = mp.hist_pre_seed;
+		for(int i = tid; i < B*B; i += T) s_joint[i] = mp.pre_seed;
+		cta_sync<T>();
+		// ---- sweep 1: updatePixVals (MI.cc:166-192) + the histograms of updateSimilarity (MI.cc:346-370)
+		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
+			s_It[it.pix] = It;
+			const BinWeights bc = bin_weights(It, B), bi = bin_weights(I0[it.pix], B);
+#pragma unroll
+			for(int k = 0; k < 4; ++k){
+				if(bc.lo + k > bc.hi) continue;
+				atomicAdd(&s_hist[bc.lo + k], bc.w[k]);
+#pragma unroll
+				for(int l = 0; l < 4; ++l){
+					if(bi.lo + l > bi.hi) continue;
+					atomicAdd(&s_joint[(bi.lo + l)*B + (bc.lo + k)], bc.w[k] * bi.w[l]);    // JH(curr_id, init_id)
+				}
+			}
+		}
+		cta_sync<T>();
+		for(int i = tid; i < B; i += T){
+			const double h = s_hist[i] * mp.hist_norm_mult;
+			s_hist[i] = h; s_hist_log[i] = log(h);
+		}
+		cta_sync<T>();
+		for(int i = tid; i < B*B; i += T){
+			const double jh = s_joint[i] * mp.hist_norm_mult, jl = log(jh);
+			const int curr_id = i % B, init_id = i / B;
+			s_joint[i] = jh * (jl - s_hist_log[curr_id] - s_ihist_log[init_id]);      // the term of f (MI.cc:376-380)
+			s_fac_t[i] = 1 + jl - s_hist_log[curr_id];                                // curr_grad_factor(curr, init) (MI.cc:430)
+			s_fac_0[i] = 1 + jl - s_ihist_log[init_id];                               // init_grad_factor(init, curr) (MI.cc:402)
+		}
+		cta_sync<T>();
+		if(tid == 0){
+			double fs = 0;
+			for(int curr_id = 0; curr_id < B; ++curr_id) for(int init_id = 0; init_id < B; ++init_id) fs += s_joint[init_id*B + curr_id];
+			s_f = fs;
+		}
+		// ---- sweep 2: df_dIt / df_dI0 per pixel (MI.cc:426-443, 398-417) and the Jacobian sums
+		double acc[NA];
+#pragma unroll
+		for(int i = 0; i < NA; ++i) acc[i] = 0;
+		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			const BinWeights bc = bin_weights(s_It[it.pix], B), bi = bin_weights(I0[it.pix], B);
+			double df_t = 0, df_0 = 0;
+			if(CURR){
+#pragma unroll
+				for(int k = 0; k < 4; ++k){
+					if(bc.lo + k > bc.hi) continue;
+					const double gk = bc.d[k] * (-mp.hist_norm_mult);                   // curr_hist_grad
+#pragma unroll
+					for(int l = 0; l < 4; ++l){
+						if(bi.lo + l > bi.hi) continue;
+						df_t += (gk * bi.w[l]) * s_fac_t[(bi.lo + l)*B + (bc.lo + k)];
+					}
+				}
+			}
+			if(INIT){
+#pragma unroll
+				for(int l = 0; l < 4; ++l){
+					if(bi.lo + l > bi.hi) continue;
+					const double gl = bi.d[l] * (-mp.hist_norm_mult);                   // init_hist_grad
+#pragma unroll
+					for(int k = 0; k < 4; ++k){
+						if(bc.lo + k > bc.hi) continue;
+						df_0 += (gl * bc.w[k]) * s_fac_0[(bi.lo + l)*B + (bc.lo + k)];
+					}
+				}
+			}
+			if(CURR){
+				Sample smp = sample_fast<false>(b.img, g.wx, g.wy, b.grad_eps, b.pix_mult);
+				if(smp.lit) sample_literal(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, smp);
+				double D[S];
+				warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, D);
+#pragma unroll
+				for(int i = 0; i < S; ++i) acc[oT + i] = fma(df_t, D[i], acc[oT + i]);
+			}
+			if(INIT){
+				double D0[S];
+				init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
+#pragma unroll
+				for(int i = 0; i < S; ++i) acc[o0 + i] = fma(df_0, D0[i], acc[o0 + i]);
+			}
+		}
+		block_reduce<NA, T>(acc, s_part, s_sum);
+		++n_passes;
+		if(tid < S){
+			double jv = CURR ? s_sum[oT + tid] : 0.0;
+			if(SM == SM_ESM) jv = jv - s_sum[o0 + tid];                             // AppearanceModel.h:162-166
+			if(SM == SM_ICLK) jv = s_sum[o0 + tid];
+			s_J[tid] = jac_half ? jv * 0.5 : jv;
+		}
+		cta_sync<T>();
+		if(warp == 0){
+			f = s_f;
+			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, nullptr, s_W, s_corners, s_init_corners,
+				lm, patch_status);
+			if(lane == 0) s_ctrl = ctrl;
+		}
+		cta_sync<T>();
+		const int ctrl = s_ctrl;
+		if(ctrl == CTRL_BREAK) break;
+		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
+	}
+	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
+}
+
+// ------------------------------------------------------------------------------------------------
+static MiParams make_mi_params(const DevBatch &b, int n_bins, double pre_seed){
+	MiParams mp;
+	mp.B = n_bins; mp.pre_seed = pre_seed;
+	mp.hist_pre_seed = n_bins * pre_seed;                                          // MI.cc:101
+	mp.hist_norm_mult = 1.0 / (static_cast<double>(b.N) + mp.hist_pre_seed * n_bins);   // MI.cc:104
+	return mp;
+}
+
+template<int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &b, const double *d_corners, const MiParams &mp,
+	double *mi_tab, cudaStream_t st){
+	switch(threads){
+	case 32: mi_init_kernel<SSM, 32><<<b.P, 32, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	case 64: mi_init_kernel<SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	case 128: mi_init_kernel<SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	case 256: mi_init_kernel<SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double *d_corners, int n_bins, double pre_seed,
+	double *mi_tab, cudaStream_t st){
+	if(n_bins < 4 || n_bins > MI_BMAX) return cudaErrorInvalidValue;
+	const MiParams mp = make_mi_params(b, n_bins, pre_seed);
+	if(ssm == SSM_HOM) return launch_init_t<SSM_HOM>(threads, b, d_corners, mp, mi_tab, st);
+	return launch_init_t<SSM_AFF>(threads, b, d_corners, mp, mi_tab, st);
+}
+
+template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
+	const size_t smem = (size_t)b.N * sizeof(double);
+	if(smem > 190 * 1024) return cudaErrorInvalidValue;
+	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if(e != cudaSuccess) return e;
+	mi_update_kernel<SSM, SM, T><<<b.P, T, smem, st>>>(b, mp, mi_tab);
+	return cudaGetLastError();
+}
+template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, const MiParams &mp, const double *mi_tab,
+	cudaStream_t st){
+	switch(threads){
+	case 32: return launch_one<SSM, SM, 32>(b, mp, mi_tab, st);
+	case 64: return launch_one<SSM, SM, 64>(b, mp, mi_tab, st);
+	case 128: return launch_one<SSM, SM, 128>(b, mp, mi_tab, st);
+	case 256: return launch_one<SSM, SM, 256>(b, mp, mi_tab, st);
+	default: return cudaErrorInvalidValue;
+	}
+}
+cudaError_t launch_update_mi(int ssm, int sm, int threads, const DevBatch &b, int n_bins, double pre_seed, const double *mi_tab,
+	cudaStream_t st){
+	const MiParams mp = make_mi_params(b, n_bins, pre_seed);
+	if(ssm == SSM_HOM){
+		if(sm == SM_ESM) return launch_update_t<SSM_HOM, SM_ESM>(threads, b, mp, mi_tab, st);
+		if(sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, b, mp, mi_tab, st);
+		return launch_update_t<SSM_HOM, SM_ICLK>(threads, b, mp, mi_tab, st);
+	}
+	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, b, mp, mi_tab, st);
+	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, b, mp, mi_tab, st);
+	return launch_update_t<SSM_AFF, SM_ICLK>(threads, b, mp, mi_tab, st);
+}
+
+} // namespace mtfb

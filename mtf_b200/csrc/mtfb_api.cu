@@ -57,15 +57,26 @@ bool combo_supported(const mtfb_params *p, const char **why){
 		if(!ok) *why = "NCC: only the self Hessians (and ESM's DiffOfJacs Jacobian) are implemented";
 		return ok;
 	}
-	*why = "am must be ssd or ncc";
+	if(p->am == MTFB_AM_MI){
+		// per-pass MI Hessians (MI.cc:461-637) are not implemented: the Hessian is init_self_hessian
+		const bool ok = (p->sm == MTFB_SM_ESM) ? (p->hess_type == MTFB_ESM_HESS_INITIAL_SELF && p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS)
+			: (p->hess_type == MTFB_LK_HESS_INITIAL_SELF);
+		if(!ok){ *why = "MI: only the InitialSelf Hessian (and ESM's DiffOfJacs Jacobian) is implemented"; return false; }
+		if(p->mi_n_bins < 4 || p->mi_n_bins > 16){ *why = "MI: 4 <= mi_n_bins <= 16"; return false; }
+		if(p->mi_pou && p->mi_n_bins < 6){ *why = "MI: partition of unity needs mi_n_bins >= 6"; return false; }
+		return true;
+	}
+	*why = "am must be ssd, ncc or mi";
 	return false;
 }
 
-cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, const double *d_corners, double *mi_tab, cudaStream_t st){
+	if(p.am == MTFB_AM_MI) return launch_init_mi(p.ssm, threads, b, d_corners, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_init_ncc(p.ssm, threads, b, d_corners, st);
 	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
 }
-cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, cudaStream_t st){
+cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st){
+	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
 	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, st);
 }
@@ -81,6 +92,7 @@ struct mtfb_ctx {
 	float *d_img_own; size_t img_capacity;      // elements
 	double *d_grid;                             // xv | yv | norm_corners
 	double *d_patch;                            // all per-patch fp64 arrays in one allocation
+	double *d_mi_tab;                           // MI: P x 32 histogram tables
 	int *d_ints;                                // n_iters | status
 	double *d_corners_in;                       // staging for initialize()/set_region()
 	mtfb_iter_log *d_log;
@@ -182,7 +194,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		if(cudaMalloc(&c->d_grid, grid.size()*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemcpy(c->d_grid, grid.data(), grid.size()*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		// per-patch arrays
-		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8;
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32;
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -200,6 +212,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.Hinit = q; q += 64 * (size_t)P;
 		b.f = q; q += (size_t)P;
 		b.am_scal = q; q += 8 * (size_t)P;
+		c->d_mi_tab = q; q += 32 * (size_t)P;
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
@@ -209,6 +222,13 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.epsilon = p->epsilon; b.lm_delta_init = p->lm_delta_init; b.lm_delta_update = p->lm_delta_update;
 		b.grad_eps = p->grad_eps;
 		b.pix_mult = 1; b.pix_add = 0;
+		if(p->am == MTFB_AM_MI){
+			// MI::MI (MI.cc:84-94): pixel values are rescaled to histogram-bin units
+			double norm_pix_min = 0, norm_pix_max = p->mi_n_bins - 1;
+			if(p->mi_pou){ norm_pix_min = 1; norm_pix_max = p->mi_n_bins - 2; }
+			b.pix_mult = (norm_pix_max - norm_pix_min) / (255.0 - 0.0 + 1);
+			b.pix_add = norm_pix_min;
+		}
 		b.grad_mult = b.pix_mult / (2 * p->grad_eps);
 		b.img = make_image(nullptr, 0, 0, 0);
 	} while(0);
@@ -281,7 +301,7 @@ static mtfb_status upload_corners(mtfb_ctx *c, const double *corners, const char
 mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 	mtfb_status st = upload_corners(c, corners, "mtfb_initialize");
 	if(st != MTFB_OK) return st;
-	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->stream));
+	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->d_mi_tab, c->stream));
 	++c->launches;
 	c->initialized = true;
 	return MTFB_OK;
@@ -308,7 +328,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -360,7 +380,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);

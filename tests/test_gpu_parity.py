@@ -345,3 +345,50 @@ def test_pf_evaluate(seq384, ssm):
         assert np.allclose(lik[i], ol, rtol=1e-11, atol=1e-300)
     with pytest.raises(Exception):
         g.update()
+
+
+# ------------------------------------------------------------------------------------------------ MI
+@pytest.mark.parametrize("sm", SMS)
+@pytest.mark.parametrize("ssm", SSMS)
+def test_mi_iteration_log_parity(seq384, sm, ssm):
+    """MI with the InitialSelf Hessian (ICLKParams.cc:6).  The shared-memory histogram atomics fix no summation
+    order, so even the first pass is compared with a tolerance instead of bit for bit."""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=11)])
+    g = _gpu("mi", ssm, sm, len(cs), hess_type=0, max_iters=10)
+    g.enable_iter_log(10)
+    g.initialize(cs, frames[0])
+    I0 = g.init_pix_vals()
+    for fr in frames[1:2]:
+        g.update(fr)
+        logs = g.iter_log()
+        n_it = g.n_iters()
+        for i, c in enumerate(cs):
+            o = _oracle("mi", ssm, sm, grad_mode=1, hess_type=0, max_iters=10)
+            o.set_image(frames[0]); o.initialize(c)
+            assert np.array_equal(I0[i], o.init_pix_vals())
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert n_it[i] == o.n_iters == len(ol) == len(logs[i])
+            for k, (a, b) in enumerate(zip(logs[i], ol)):
+                tol = 1e-10 if k == 0 else 1e-6
+                assert abs(a["f"] - b["f"]) <= tol
+                assert _rel(a["jacobian"], b["jacobian"]) <= tol * 10
+                assert _rel(a["hessian"], b["hessian"]) <= 1e-10        # init_self_hessian
+                # MI's init_self_hessian is poorly conditioned (cond ~1e10 in raw pixel coordinates): the solve turns the
+                # 1e-12 relative noise of the Jacobian into ~1e-8 px, and each further pass compounds it
+                assert np.abs(a["corners"] - b["corners"]).max() <= (1e-6 if k == 0 else 1e-4)
+
+
+def test_mi_iclk_100x100(seq384):
+    """BASELINE config 4 shape: ICLK + MI + Homography on 100 x 100 patches, vs the reference finite-difference oracle"""
+    frames, _ = seq384
+    cs = common.patches(4, 99.0, 384, 384, seed=8)
+    g = _gpu("mi", "homography", "iclk", len(cs), resx=100, resy=100, hess_type=0)
+    g.initialize(cs, frames[0])
+    g.update(frames[1])
+    for i, c in enumerate(cs):
+        o = _oracle("mi", "homography", "iclk", grad_mode=0, resx=100, resy=100, hess_type=0)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        assert abs(int(g.n_iters()[i]) - o.n_iters) <= 1
+        assert np.abs(g.getRegion()[i] - o.corners()).max() <= CORNER_ATOL_FD
