@@ -1,0 +1,72 @@
+"""Multi-GPU host logic: independent patches / grid cells / particles shard embarrassingly.
+
+One process per GPU.  Every rank owns a contiguous index range of the batch, tracks it with its own
+BatchTracker on its own copy of the frame, and the per-patch results (P_local x 8 corners, or particle
+weights) are all-gathered once per frame -- LK iterations of different patches never interact, so no
+collective is needed inside the iteration loop.  The reference has no counterpart: its fan-out is a
+shared-memory loop over `trackers[i]->update()` (SM/src/GridTracker.cc:247-264)."""
+import numpy as np
+
+
+def shard_range(n_items, world_size, rank):
+    """contiguous range [lo, hi) of rank: sizes differ by at most one, earlier ranks take the remainder"""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_items, world_size):
+    return [shard_range(n_items, world_size, r)[1] - shard_range(n_items, world_size, r)[0] for r in range(world_size)]
+
+
+def all_gather_rows(local, n_total, group=None):
+    """all-gather a (n_local, ...) tensor whose row counts follow shard_range into a (n_total, ...) tensor.
+
+    Uses all_gather_into_tensor when the shards are equal (one NCCL call on the caller's stream), padded
+    all_gather otherwise."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_total, world)
+    tail = tuple(local.shape[1:])
+    if len(set(sizes)) == 1:
+        out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+        return out
+    m = max(sizes)
+    padded = torch.zeros((m,) + tail, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+class ShardedBatchTracker:
+    """The batch of `corners.shape[0]` patches split over the ranks of a torch.distributed group.
+
+    make_local(n_local) must return an object with initialize / update / getRegion (a BatchTracker); it is a
+    parameter so that the sharding logic can be exercised without a GPU."""
+
+    def __init__(self, n_total, make_local, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_total = n_total
+        self.lo, self.hi = shard_range(n_total, self.world, self.rank)
+        self.local = make_local(self.hi - self.lo)
+
+    def initialize(self, corners, img):
+        c = np.asarray(corners, dtype=np.float64).reshape(self.n_total, 2, 4)
+        self.local.initialize(c[self.lo:self.hi], img)
+
+    def update(self, img):
+        self.local.update(img)
+
+    def getRegion(self, device=None):
+        """(n_total, 2, 4) corners of every patch, on every rank"""
+        import torch
+        loc = torch.as_tensor(np.ascontiguousarray(self.local.getRegion()).reshape(-1, 8))
+        if device is not None:
+            loc = loc.to(device)
+        return all_gather_rows(loc, self.n_total, self.group).reshape(self.n_total, 2, 4)
