@@ -1,0 +1,195 @@
+/*
+ * mtf_b200_tracker.h -- header-only C++ shim that plugs libmtf_b200.so into MTF.
+ *
+ * Compiled INSIDE the MTF tree (it includes MTF's own headers); it contains no arithmetic, only the mapping
+ * cv::Mat <-> raw pointers and mtfb_status -> mtf::utils::Exception.  Three classes:
+ *
+ *   mtf::b200::Tracker       : mtf::TrackerBase   one patch; what mtf::getTracker returns for sm "b200_fclk" ...
+ *   mtf::b200::Batch                              P patches tracked by ONE launch per frame
+ *   mtf::b200::BatchMember   : mtf::TrackerBase   patch i of a Batch, so that composites that hold a
+ *                                                 vector<TrackerBase*> (GridTracker, SM/src/GridTracker.cc:247-264)
+ *                                                 drive the whole batch through their existing loop
+ *
+ * Interface replaced: include/mtf/TrackerBase.h:9-70 (setImage / initialize / update / setRegion / getRegion /
+ * inputType), constructed where include/mtf/mtf.h:1282-1300 (getSM) constructs nt::FCLK / nt::ESM / nt::ICLK.
+ * Ownership, threading and error behaviour follow SURVEY.md 8(b): raw `new`, caller owns; an instance is
+ * single-threaded; errors are mtf::utils exceptions.
+ */
+#ifndef MTF_B200_TRACKER_H
+#define MTF_B200_TRACKER_H
+
+#include "mtf/TrackerBase.h"
+#include "mtf/Utilities/excpUtils.h"
+#include "opencv2/core/core.hpp"
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "mtf_b200.h"
+
+namespace mtf {
+namespace b200 {
+
+//! mtfb_status -> the exception the reference would have thrown (excpUtils.h:8-55)
+inline void check(mtfb_status st){
+	if(st == MTFB_OK){ return; }
+	const std::string msg = std::string("mtf_b200 :: ") + mtfb_last_error();
+	switch(st){
+	case MTFB_ERR_INVALID_ARG: throw mtf::utils::InvalidArgument(msg);
+	case MTFB_ERR_NOT_SUPPORTED: throw mtf::utils::FunctonNotImplemented(msg);
+	case MTFB_ERR_INVALID_STATE: throw mtf::utils::InvalidTrackerState(msg);
+	default: throw mtf::utils::LogicError(msg);
+	}
+}
+
+//! parameters from the names MTF's factory uses ("fclk", "ssd", "8" ...; include/mtf/mtf.h:1066-1300)
+inline mtfb_params makeParams(const char *sm, const char *am, const char *ssm, int n_patches, int resx, int resy){
+	mtfb_params p;
+	mtfb_default_params(&p);
+	if(!strcmp(sm, "esm")){ p.sm = MTFB_SM_ESM; p.hess_type = MTFB_ESM_HESS_SUM_OF_SELF; }
+	else if(!strcmp(sm, "fclk") || !strcmp(sm, "fc")){ p.sm = MTFB_SM_FCLK; p.hess_type = MTFB_LK_HESS_CURRENT_SELF; }
+	else if(!strcmp(sm, "iclk") || !strcmp(sm, "ic")){ p.sm = MTFB_SM_ICLK; p.hess_type = MTFB_LK_HESS_INITIAL_SELF; }
+	else if(!strcmp(sm, "pf")){ p.sm = MTFB_SM_PF; }
+	else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: unknown search method ") + sm); }
+	if(!strcmp(am, "ssd")){ p.am = MTFB_AM_SSD; }
+	else if(!strcmp(am, "ncc")){ p.am = MTFB_AM_NCC; }
+	else if(!strcmp(am, "mi")){ p.am = MTFB_AM_MI; }
+	else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: unknown appearance model ") + am); }
+	if(!strcmp(ssm, "8") || !strcmp(ssm, "hom") || !strcmp(ssm, "homography")){ p.ssm = MTFB_SSM_HOMOGRAPHY; }
+	else if(!strcmp(ssm, "6") || !strcmp(ssm, "aff") || !strcmp(ssm, "affine")){ p.ssm = MTFB_SSM_AFFINE; }
+	else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: unknown state space model ") + ssm); }
+	p.n_patches = n_patches; p.resx = resx; p.resy = resy;
+	return p;
+}
+
+//! P patches sharing one image: thin RAII wrapper of mtfb_ctx
+class Batch{
+public:
+	explicit Batch(const mtfb_params &params) : ctx(nullptr), prm(params), corners(8 * (size_t)params.n_patches, 0.0),
+		n_supplied(0), frame_id(0), updated_frame(-1){
+		check(mtfb_create(&prm, &ctx));
+	}
+	~Batch(){ mtfb_destroy(ctx); }
+	Batch(const Batch&) = delete;
+	Batch& operator=(const Batch&) = delete;
+
+	int size() const{ return prm.n_patches; }
+	//! TrackerBase::setImage: the reference keeps the cv::Mat header and re-reads the pixels on every call
+	//! (TrackerBase.h:21-26), so only the header is kept here and the upload happens in initialize()/update()
+	void setImage(const cv::Mat &img){
+		if(img.type() != CV_32FC1){ throw mtf::utils::InvalidArgument("mtf_b200 :: setImage :: CV_32FC1 image expected"); }
+		curr_img = img;
+	}
+	void upload(){
+		if(curr_img.empty()){ throw mtf::utils::LogicError("mtf_b200 :: setImage has not been called"); }
+		check(mtfb_set_image(ctx, curr_img.ptr<float>(), curr_img.rows, curr_img.cols,
+			static_cast<int>(curr_img.step / sizeof(float))));
+		++frame_id;
+	}
+	//! all P regions at once: corners = P x (2 x 4) doubles
+	void initialize(const double *all_corners){ upload(); check(mtfb_initialize(ctx, all_corners)); fetch(); }
+	void setRegion(const double *all_corners){ upload(); check(mtfb_set_region(ctx, all_corners)); fetch(); }
+	void update(){ upload(); check(mtfb_update(ctx)); fetch(); updated_frame = frame_id; }
+	const double* region(int i) const{ return &corners[8 * (size_t)i]; }
+	mtfb_ctx* handle(){ return ctx; }
+
+	// ---- used by BatchMember: members hand in their corners one by one; the batch is (re)initialised when the
+	// last one has arrived
+	void supplyCorners(int i, const cv::Mat &c, bool is_init){
+		for(int k = 0; k < 8; ++k){ pending_corners()[8 * (size_t)i + k] = c.at<double>(k / 4, k % 4); }
+		if(++n_supplied == size()){
+			n_supplied = 0;
+			if(is_init){ initialize(pending.data()); } else{ setRegion(pending.data()); }
+		}
+	}
+	const cv::Mat& image() const{ return curr_img; }
+
+private:
+	std::vector<double>& pending_corners(){ if(pending.empty()){ pending.assign(corners.size(), 0.0); } return pending; }
+	void fetch(){ check(mtfb_get_corners(ctx, corners.data())); }
+	mtfb_ctx *ctx;
+	mtfb_params prm;
+	cv::Mat curr_img;
+	std::vector<double> corners, pending;
+	int n_supplied, frame_id, updated_frame;
+};
+
+//! One patch tracked on the GPU; drop-in for nt::FCLK / nt::ESM / nt::ICLK (SM/src/NT/*.cc)
+class Tracker : public mtf::TrackerBase{
+public:
+	Tracker(const char *sm, const char *am, const char *ssm, int resx, int resy) :
+		batch(makeParams(sm, am, ssm, 1, resx, resy)){
+		name = std::string("b200_") + sm;
+		cv_corners_mat.create(2, 4, CV_64FC1);
+	}
+	explicit Tracker(const mtfb_params &params) : batch(params){
+		name = "b200";
+		cv_corners_mat.create(2, 4, CV_64FC1);
+	}
+	using TrackerBase::initialize;
+	using TrackerBase::update;
+	using TrackerBase::setRegion;
+	void setImage(const cv::Mat &img) override{ batch.setImage(img); }
+	void initialize(const cv::Mat &corners) override{ toArray(corners); batch.initialize(c8); publish(); }
+	void update() override{ batch.update(); publish(); }
+	void setRegion(const cv::Mat &corners) override{ toArray(corners); batch.setRegion(c8); publish(); }
+	int inputType() const override{ return CV_32FC1; }
+	Batch& getBatch(){ return batch; }
+private:
+	void toArray(const cv::Mat &corners){
+		if(corners.rows != 2 || corners.cols != 4 || corners.type() != CV_64FC1){
+			throw mtf::utils::InvalidArgument("mtf_b200 :: corners must be a 2 x 4 CV_64FC1 matrix");
+		}
+		for(int k = 0; k < 8; ++k){ c8[k] = corners.at<double>(k / 4, k % 4); }
+	}
+	void publish(){
+		const double *r = batch.region(0);
+		for(int k = 0; k < 8; ++k){ cv_corners_mat.at<double>(k / 4, k % 4) = r[k]; }
+	}
+	Batch batch;
+	double c8[8];
+};
+
+//! Patch i of a shared Batch.  A composite that loops `trackers[i]->update()` (GridTracker.cc:256-259, serial
+//! build) triggers one launch for the whole batch on member 0 and reads results for the others.
+class BatchMember : public mtf::TrackerBase{
+public:
+	BatchMember(std::shared_ptr<Batch> _batch, int _id) : batch(_batch), id(_id){
+		name = "b200_member";
+		cv_corners_mat.create(2, 4, CV_64FC1);
+	}
+	using TrackerBase::initialize;
+	using TrackerBase::update;
+	using TrackerBase::setRegion;
+	void setImage(const cv::Mat &img) override{ if(id == 0){ batch->setImage(img); } }
+	void initialize(const cv::Mat &corners) override{ batch->supplyCorners(id, corners, true); corners.copyTo(cv_corners_mat); }
+	void setRegion(const cv::Mat &corners) override{ batch->supplyCorners(id, corners, false); corners.copyTo(cv_corners_mat); }
+	//! member 0 launches the whole batch; the composite's loop visits the members in index order
+	//! (GridTracker.cc:256-259; the TBB / OpenMP variants of that loop, :248-255, must stay disabled)
+	void update() override{ if(id == 0){ batch->update(); } }
+	const cv::Mat& getRegion() override{
+		const double *r = batch->region(id);
+		for(int k = 0; k < 8; ++k){ cv_corners_mat.at<double>(k / 4, k % 4) = r[k]; }
+		return cv_corners_mat;
+	}
+	int inputType() const override{ return CV_32FC1; }
+private:
+	std::shared_ptr<Batch> batch;
+	int id;
+};
+
+//! grid_res^2 members over one batch: what replaces the loop at include/mtf/mtf.h:786-789
+inline std::vector<mtf::TrackerBase*> makeBatchMembers(const char *sm, const char *am, const char *ssm,
+	int n_trackers, int resx, int resy){
+	std::shared_ptr<Batch> batch(new Batch(makeParams(sm, am, ssm, n_trackers, resx, resy)));
+	std::vector<mtf::TrackerBase*> out;
+	for(int i = 0; i < n_trackers; ++i){ out.push_back(new BatchMember(batch, i)); }
+	return out;
+}
+
+} // namespace b200
+} // namespace mtf
+
+#endif

@@ -1,0 +1,53 @@
+// TEST DRIVER: compiles include/mtf_b200_tracker.h against the stand-in MTF / OpenCV headers and drives it the way runMTF
+// (Examples/cpp/runMTF.cc:154,692-704) and GridTracker (SM/src/GridTracker.cc:232-264) drive a TrackerBase.
+// usage: shim_driver <frames.bin: int32 n,h,w + n*h*w float32> <corners.bin: int32 P + P*8 float64> sm am ssm res -> prints corners
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "mtf_b200_tracker.h"
+
+int main(int argc, char **argv){
+	if(argc < 7){ fprintf(stderr, "usage\n"); return 2; }
+	FILE *f = fopen(argv[1], "rb"); int n, h, w;
+	if(!f || fread(&n, 4, 1, f) != 1 || fread(&h, 4, 1, f) != 1 || fread(&w, 4, 1, f) != 1) return 2;
+	std::vector<float> frames((size_t)n*h*w);
+	if(fread(frames.data(), 4, frames.size(), f) != frames.size()) return 2;
+	fclose(f);
+	f = fopen(argv[2], "rb"); int P;
+	if(!f || fread(&P, 4, 1, f) != 1) return 2;
+	std::vector<double> corners((size_t)P * 8);
+	if(fread(corners.data(), 8, corners.size(), f) != corners.size()) return 2;
+	fclose(f);
+	const int res = atoi(argv[6]);
+	try{
+		// the application keeps ONE image buffer and overwrites it in place every frame (TrackerBase.h:21-26)
+		cv::Mat img(h, w, CV_32FC1);
+		auto load = [&](int t){ for(int r = 0; r < h; ++r) memcpy(img.ptr<float>(r), &frames[((size_t)t*h + r)*w], w * 4); };
+		// (1) single trackers, one per patch, as runMTF would create them
+		std::vector<mtf::TrackerBase*> single;
+		for(int i = 0; i < P; ++i) single.push_back(new mtf::b200::Tracker(argv[3], argv[4], argv[5], res, res));
+		// (2) the same patches as members of one batch, as a GridTracker would hold them
+		std::vector<mtf::TrackerBase*> members = mtf::b200::makeBatchMembers(argv[3], argv[4], argv[5], P, res, res);
+		load(0);
+		for(int i = 0; i < P; ++i){
+			cv::Mat c(2, 4, CV_64FC1);
+			for(int k = 0; k < 8; ++k) c.at<double>(k / 4, k % 4) = corners[8 * (size_t)i + k];
+			single[i]->initialize(img, c);
+			members[i]->setImage(img); members[i]->initialize(c);
+		}
+		for(int t = 1; t < n; ++t){
+			load(t);
+			for(int i = 0; i < P; ++i){ single[i]->update(); members[i]->update(); }
+		}
+		for(int i = 0; i < P; ++i){
+			const cv::Mat &a = single[i]->getRegion(), &b = members[i]->getRegion();
+			for(int k = 0; k < 8; ++k) printf("%.17g %.17g\n", a.at<double>(k / 4, k % 4), b.at<double>(k / 4, k % 4));
+		}
+		// error contract: a bad corner matrix is an InvalidArgument exception, not a crash
+		try{ cv::Mat bad(3, 4, CV_64FC1); single[0]->initialize(bad); printf("NOEXC\n"); }
+		catch(const mtf::utils::Exception &e){ printf("EXC %s\n", e.type()); }
+	} catch(const mtf::utils::Exception &e){
+		fprintf(stderr, "%s: %s\n", e.type(), e.what()); return 1;
+	}
+	return 0;
+}

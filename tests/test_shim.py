@@ -1,0 +1,57 @@
+"""The C++ shim (include/mtf_b200_tracker.h) that subclasses mtf::TrackerBase.  MTF's own headers need Eigen / OpenCV /
+Boost, which this image lacks, so the shim is compiled against stand-ins with the same interface (tests/shim_standin).
+CPU: it compiles and links against the C-ABI library.  GPU: driven like runMTF / GridTracker drive a tracker, it returns
+the corners the Python binding returns for the same inputs (both sit on the same C ABI)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+
+ROOT = common.ROOT
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "shim_driver")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++11", "-Wall", "-Werror", "-O1", "-I", os.path.join(ROOT, "tests", "shim_standin"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "shim_standin", "shim_driver.cpp"),
+                           "-o", exe, "-L", os.path.join(ROOT, "mtf_b200"), "-lmtf_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "mtf_b200")])
+    return exe
+
+
+def test_shim_compiles_and_links(tmp_path):
+    assert os.path.exists(_build(tmp_path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sm,am,ssm,res", [("fclk", "ssd", "8", 50), ("esm", "ncc", "6", 25)])
+def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
+    from mtf_b200 import api
+    exe = _build(tmp_path)
+    frames = np.stack(seq384[0][:3]).astype(np.float32)
+    cs = common.patches(5, res - 1.0 if res == 50 else 24.6, 384, 384, seed=31)
+    fb, cb = str(tmp_path / "frames.bin"), str(tmp_path / "corners.bin")
+    with open(fb, "wb") as f:
+        f.write(struct.pack("iii", *frames.shape)); f.write(frames.tobytes())
+    with open(cb, "wb") as f:
+        f.write(struct.pack("i", len(cs))); f.write(np.ascontiguousarray(cs, dtype=np.float64).tobytes())
+    out = subprocess.check_output([exe, fb, cb, sm, am, ssm, str(res)], text=True).split("\n")
+    vals = np.array([[float(x) for x in l.split()] for l in out if l and l[0] in "-0123456789"])
+    single, member = vals[:, 0].reshape(len(cs), 2, 4), vals[:, 1].reshape(len(cs), 2, 4)
+    assert "EXC InvalidArgument" in out
+    hess = {"fclk": 1, "esm": 2}[sm]
+    tr = api.BatchTracker(api.make_params(am, {"8": "homography", "6": "affine"}[ssm], sm, n_patches=len(cs), resx=res, resy=res,
+                                          hess_type=hess))
+    tr.initialize(cs, frames[0])
+    for t in (1, 2):
+        tr.update(frames[t])
+    ref = tr.getRegion()
+    # batch members share one context with the Python run (same work split); single-patch trackers use another thread
+    # count per patch, i.e. another summation order
+    assert np.abs(member - ref).max() <= 1e-9
+    assert np.abs(single - ref).max() <= 1e-6
