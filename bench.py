@@ -40,6 +40,7 @@ IMG = 1024
 N_FRAMES = 8
 ALG_BYTES_PER_ITER = 8 * N_PIX + 432          # I_t footprint + I_0 (fp32 each) + W in + J,H,f out
 METRIC = "LK iters/sec (50x50 SSD+Homography)"
+NCU_DRAM_BYTES_PER_LAUNCH = 24471552 + 4352   # ncu --set full, this workload: the frame and I0 once, everything else on chip
 
 
 def peaks():
@@ -51,11 +52,12 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe), one sample every 20 ms with its arrival time;
+    summary() keeps the samples that fall inside the timed windows."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -63,32 +65,32 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                if self._stop_evt.is_set():
-                    break
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
-    def stop(self):
-        self._stop_evt.set()
+    def summary(self, windows):
         if self.proc is not None:
             self.proc.terminate()
-        sm, smax, reasons = [], 0.0, set()
-        for r in self.rows:
+        sm, smax, reasons, n_all = [], 0.0, set(), 0
+        for t, r in self.rows:
             try:
-                sm.append(float(r[0])); smax = max(smax, float(r[1]))
+                clk, mx = float(r[0]), float(r[1])
             except Exception:
                 continue
+            n_all += 1
+            smax = max(smax, mx)
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            sm.append(clk)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # under load = samples above the idle clock
-        load = [x for x in sm if x > 0.5 * smax] or sm
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_total": n_all}
 
 
 def workload(seed_offset=0):
@@ -111,7 +113,7 @@ def workload(seed_offset=0):
 
 def oracle_params():
     from oracle import oracle_lib as O
-    return O.make_params("ssd", "homography", "fclk", max_iters=ITERS, epsilon=0.0, grad_mode=0)
+    return O.make_params("ssd", "homography", "fclk", max_iters=ITERS, epsilon=0.0, grad_mode=0, fast_sums=1)
 
 
 def cpu_sample(frames, corners, n_patches, n_frames, threads):
@@ -158,6 +160,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank); sampler.start()        # nvidia-smi needs ~1 s to produce its first sample
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -201,11 +204,11 @@ def run_ours(args):
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
     launches0 = tr.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    win0 = time.time()
     for i in range(args.steps):
         flush.fill_(i & 0xff)                                           # evict L2 between timed steps
         ev[i][0].record(stream)
@@ -217,10 +220,10 @@ def run_ours(args):
             dist.all_gather_into_tensor(gathered.view(-1), d_corners.view(-1))
         ev[i][1].record(stream)
     barrier()
+    windows = [(win0, time.time())]
     launches = tr.launch_count - launches0
     ms = sum(a.elapsed_time(b) for a, b in ev)
     kms = sum(a.elapsed_time(b) for a, b in kev)
-    clocks = sampler.stop()
     status = tr.patch_status()
     finite = bool(np.isfinite(tr.getRegion()).all())
 
@@ -234,6 +237,7 @@ def run_ours(args):
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    win0 = time.time()
     wall0 = time.perf_counter()
     t0.record(stream)
     for i in range(args.steps):
@@ -244,6 +248,8 @@ def run_ours(args):
     t1.record(stream)
     barrier()
     e2e_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0))
+    windows.append((win0, time.time()))
+    clocks = sampler.summary(windows)
 
     if world > 1:
         t = torch.tensor([ms, kms, e2e_ms], dtype=torch.float64, device=dev)
@@ -265,7 +271,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "lk_update_kernel<SSD,Homography,FCLK>", "kernel_ms_per_launch": kms / args.steps,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_ncu_r1c_summary.txt (dram__bytes_read + write, one launch)",
+                     "kernel": "ssd_update_kernel<Homography,FCLK>", "kernel_ms_per_launch": kms / args.steps,
                      "alg_bytes_per_launch": ALG_BYTES_PER_ITER * P * ITERS, "peak_source": peak_src,
                      "note": "fp64-issue bound, not HBM bound: see DESIGN.md"},
         "clocks": clocks,
@@ -289,7 +296,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--threads", type=int, default=0, help="threads per patch (0 = library default)")

@@ -619,7 +619,7 @@ static inline double bSpl3Hess(double x){
 
 struct AM{
 	int type, resx, resy, n_pix, patch_size;
-	double grad_eps, pix_norm_mult, pix_norm_add, likelihood_alpha; int grad_mode;
+	double grad_eps, pix_norm_mult, pix_norm_add, likelihood_alpha; int grad_mode; bool fast_sums;
 	const float *img; unsigned int img_height, img_width;
 	vec I0, It, dI0_dx, dIt_dx, df_dI0, df_dIt;
 	double f;
@@ -639,7 +639,7 @@ struct AM{
 
 	AM(const orc_params &p) : type(p.am), resx(p.resx), resy(p.resy), n_pix(p.resx*p.resy),
 		patch_size(p.resx*p.resy), grad_eps(p.grad_eps), pix_norm_mult(1), pix_norm_add(0),
-		likelihood_alpha(p.likelihood_alpha), grad_mode(p.grad_mode), img(nullptr), img_height(0), img_width(0), f(0),
+		likelihood_alpha(p.likelihood_alpha), grad_mode(p.grad_mode), fast_sums(p.fast_sums != 0), img(nullptr), img_height(0), img_width(0), f(0),
 		init_pix_vals(false), init_pix_grad(false), init_sim(false), init_grad(false), init_hess(false),
 		n_bins(p.mi_n_bins), pre_seed(p.mi_pre_seed), pou(p.mi_pou != 0){
 		if(type == ORC_AM_MI){                                                 // MI::MI AM/src/MI.cc:55-123
@@ -790,12 +790,20 @@ struct AM{
 	}
 
 	// ------------------------------------------------------------------ Jacobians: (1xN).(NxS), sequential dot per column
-	static void gemv(double *out, const vec &v, const double *M, int N, int S){
-		for(int s = 0; s < S; ++s){
-			const double *col = M + (size_t)s*N; double acc = 0;
-			for(int i = 0; i < N; ++i) acc += v[i] * col[i];
-			out[s] = acc;
+	// fast_sums (timing only): lets the compiler vectorise the length-N dot products the way Eigen's product kernels
+	// do, instead of one sequential add chain; changes the summation order, so parity tests keep it off
+	static double dot(const double *a, const double *b, int N, bool fast){
+		double acc = 0;
+		if(fast){
+			#pragma omp simd reduction(+:acc)
+			for(int i = 0; i < N; ++i) acc += a[i] * b[i];
+		} else{
+			for(int i = 0; i < N; ++i) acc += a[i] * b[i];
 		}
+		return acc;
+	}
+	void gemv(double *out, const vec &v, const double *M, int N, int S) const{
+		for(int s = 0; s < S; ++s) out[s] = dot(v.data(), M + (size_t)s*N, N, fast_sums);
 	}
 	// SSDBase.cc:123-143 / NCC.cc:236-250 / AppearanceModel.h:146-149
 	void cmptInitJacobian(double *df_dp, const double *dI0_dp, int S) const{ gemv(df_dp, df_dI0, dI0_dp, patch_size, S); }
@@ -816,12 +824,9 @@ struct AM{
 		}
 	}
 	// ------------------------------------------------------------------ Hessians (column-major SxS out)
-	static void neg_JtJ(double *H, const double *J, int N, int S){
-		for(int i = 0; i < S; ++i) for(int j = 0; j < S; ++j){
-			const double *ci = J + (size_t)i*N, *cj = J + (size_t)j*N; double acc = 0;
-			for(int k = 0; k < N; ++k) acc += ci[k] * cj[k];
-			H[(size_t)j*S + i] = -acc;
-		}
+	void neg_JtJ(double *H, const double *J, int N, int S) const{
+		for(int i = 0; i < S; ++i) for(int j = 0; j < S; ++j)
+			H[(size_t)j*S + i] = -dot(J + (size_t)i*N, J + (size_t)j*N, N, fast_sums);
 	}
 	// NCC helper: (dI_dp.rowwise() - dI_dp.colwise().mean()).array() / b
 	void ncc_center(vec &out, const double *dI_dp, int S) const{
@@ -1485,7 +1490,7 @@ void orc_default_params(orc_params *p){
 	p->hess_type = ORC_LK_HESS_CURRENT_SELF; p->jac_type = ORC_ESM_JAC_DIFF_OF_JACS;
 	p->chained_warp = 1; p->leven_marq = 0; p->lm_delta_init = 0.01; p->lm_delta_update = 10;
 	p->nt_semantics = 1; p->grad_eps = 1e-8; p->hom_normalized_init = 0;
-	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1; p->grad_mode = 0;
+	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1; p->grad_mode = 0; p->fast_sums = 0;
 }
 orc_tracker *orc_create(const orc_params *p){ return new orc_tracker(*p); }
 void orc_destroy(orc_tracker *t){ delete t; }

@@ -55,6 +55,8 @@ typedef struct orc_params {
 	double likelihood_alpha;
 	int grad_mode;           /* 0: reference finite difference (imgUtils.cc:233-254); 1: its eps -> 0 limit,
 	                            evaluated analytically (not a reference mode; see mtf_oracle.cpp) */
+	int fast_sums;           /* 1: vectorised dot products in the Jacobian / Hessian products (CPU-baseline timing: Eigen's
+	                            product kernels are vectorised too); 0: sequential sums (parity tests) */
 } orc_params;
 
 typedef struct orc_tracker orc_tracker;

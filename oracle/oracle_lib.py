@@ -22,7 +22,7 @@ class OrcParams(C.Structure):
                 ("nt_semantics", C.c_int), ("grad_eps", C.c_double),
                 ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
                 ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
-                ("likelihood_alpha", C.c_double), ("grad_mode", C.c_int)]
+                ("likelihood_alpha", C.c_double), ("grad_mode", C.c_int), ("fast_sums", C.c_int)]
 
 
 class OrcIterLog(C.Structure):
