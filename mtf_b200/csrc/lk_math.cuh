@@ -264,27 +264,35 @@ template<int SSM> MTFB_HD void warp_corners(const Mat3 &w, const double *init_co
 //   Affine:        init_pts_hm is re-homogenised (Affine.cc:81-82), curr_pts = W.topRows(2) . (ix,iy,1)
 struct PixGeom { double ix, iy, wx, wy, D, rD; };     // rD = RN(1 / D) = the reference's inv_det (Homography.cc:250)
 
-template<int SSM, class MD, class MW> MTFB_HD PixGeom pixel_geometry(const MD &dlt, const MW &W, double u, double v){
+// the iteration-invariant half: init_pts_hm = dlt . (u, v, 1) and init_pts = its dehomogenisation
+template<class MD> MTFB_HD void template_point(const MD &dlt, double u, double v, double &hx, double &hy, double &hz,
+	double &ix, double &iy){
+	hx = dlt[0] * u; hx = hx + dlt[1] * v; hx = hx + dlt[2] * 1.0;
+	hy = dlt[3] * u; hy = hy + dlt[4] * v; hy = hy + dlt[5] * 1.0;
+	hz = dlt[6] * u; hz = hz + dlt[7] * v; hz = hz + dlt[8] * 1.0;
+	const double rhz = ieee_rcp(hz);
+	ix = div_by(hx, hz, rhz); iy = div_by(hy, hz, rhz);
+}
+// the per-pass half: the warped point (and its homogeneous denominator)
+template<int SSM, class MW> MTFB_HD PixGeom warp_template_point(const MW &W, double hx, double hy, double hz, double ix, double iy){
 	PixGeom g;
-	double hx = dlt[0] * u; hx = hx + dlt[1] * v; hx = hx + dlt[2] * 1.0;
-	double hy = dlt[3] * u; hy = hy + dlt[4] * v; hy = hy + dlt[5] * 1.0;
-	double hz = dlt[6] * u; hz = hz + dlt[7] * v; hz = hz + dlt[8] * 1.0;
+	g.ix = ix; g.iy = iy;
 	if(SSM == SSM_HOM){
-		// the warped point first: the image loads hang off it, the template point is needed only later
 		double cx = W[0] * hx; cx = cx + W[1] * hy; cx = cx + W[2] * hz;
 		double cy = W[3] * hx; cy = cy + W[4] * hy; cy = cy + W[5] * hz;
 		double cz = W[6] * hx; cz = cz + W[7] * hy; cz = cz + W[8] * hz;
 		g.D = cz; g.rD = ieee_rcp(cz); g.wx = div_by(cx, cz, g.rD); g.wy = div_by(cy, cz, g.rD);
-		const double rhz = ieee_rcp(hz);
-		g.ix = div_by(hx, hz, rhz); g.iy = div_by(hy, hz, rhz);
 	} else{
-		const double rhz = ieee_rcp(hz);
-		g.ix = div_by(hx, hz, rhz); g.iy = div_by(hy, hz, rhz);
-		double cx = W[0] * g.ix; cx = cx + W[1] * g.iy; cx = cx + W[2] * 1.0;
-		double cy = W[3] * g.ix; cy = cy + W[4] * g.iy; cy = cy + W[5] * 1.0;
+		double cx = W[0] * ix; cx = cx + W[1] * iy; cx = cx + W[2] * 1.0;
+		double cy = W[3] * ix; cy = cy + W[4] * iy; cy = cy + W[5] * 1.0;
 		g.D = 1.0; g.rD = 1.0; g.wx = cx; g.wy = cy;
 	}
 	return g;
+}
+template<int SSM, class MD, class MW> MTFB_HD PixGeom pixel_geometry(const MD &dlt, const MW &W, double u, double v){
+	double hx, hy, hz, ix, iy;
+	template_point(dlt, u, v, hx, hy, hz, ix, iy);
+	return warp_template_point<SSM>(W, hx, hy, hz, ix, iy);
 }
 
 // ssm.cmptWarpedPixJacobian: Homography.cc:231-294, Affine.cc:213-242.  gx, gy = dI/dx at the warped point.
