@@ -392,3 +392,17 @@ def test_mi_iclk_100x100(seq384):
         o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
         assert abs(int(g.n_iters()[i]) - o.n_iters) <= 1
         assert np.abs(g.getRegion()[i] - o.corners()).max() <= CORNER_ATOL_FD
+
+
+# ------------------------------------------------------------------------------------------------ kernel variants
+@pytest.mark.parametrize("threads,occ", [(32, 0), (64, 0), (64, 2), (128, 1), (256, 2)])
+def test_work_splits_agree(seq384, threads, occ):
+    """threads per patch and register budget are tuning knobs: results move only by summation order"""
+    frames, _ = seq384
+    cs = common.patches(6, 52.3, 384, 384, seed=17)
+    ref = _gpu("ssd", "homography", "fclk", len(cs), threads_per_patch=32, occupancy=0)
+    g = _gpu("ssd", "homography", "fclk", len(cs), threads_per_patch=threads, occupancy=occ)
+    ref.initialize(cs, frames[0]); g.initialize(cs, frames[0])
+    ref.update(frames[1]); g.update(frames[1])
+    assert np.array_equal(ref.n_iters(), g.n_iters())
+    assert np.abs(ref.getRegion() - g.getRegion()).max() <= 1e-8
