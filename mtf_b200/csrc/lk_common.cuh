@@ -75,6 +75,34 @@ template<int K, int T> __device__ __forceinline__ void block_allreduce(double (&
 	}
 }
 
+// ---- TMA / mbarrier plumbing (PTX; SASS: UBLKCP for the 1-D bulk copy, UTMALDG for the tensor copy)
+__device__ __forceinline__ unsigned smem_u32(const void *p){ return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count){
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes){
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase){
+	unsigned done;
+	do{
+		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+			: "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+	} while(!done);
+}
+// 1-D bulk async copy global -> shared
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar){
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 2-D tensor copy global -> shared: the box of the tensor map whose first element is (x, y); out-of-range elements are
+// zero-filled by the hardware
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar){
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		:: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
 struct PixIter {
 	int pix, row, col, dcol, drow, resx;
 	__device__ __forceinline__ PixIter(int tid, int step, int _resx) : pix(tid), row(tid / _resx), col(tid % _resx),

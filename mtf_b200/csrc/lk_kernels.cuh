@@ -1,5 +1,6 @@
 // lk_kernels.cuh -- declarations shared by the kernel translation unit and the C-ABI host code.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/mtf_b200.h"
 #include "lk_math.cuh"
@@ -25,6 +26,7 @@ struct DevBatch {
 	double *f;                   // P       similarity
 	int *n_iters;                // P
 	int *status;                 // P
+	long long *n_iters_prof;     // experiment builds (MTFB_PROF): phase cycle counters, else null
 	mtfb_iter_log *log;          // P x log_slots or null
 	int log_slots;
 	// parameters
@@ -34,12 +36,16 @@ struct DevBatch {
 	double grad_mult;            // pix_mult / (2 grad_eps)  (imgUtils.cc:238)
 };
 
+// frame window staged in shared memory by the SSD update kernel
+constexpr int TILE_W = 64, TILE_H = 64;
+
 struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
 
 // launchers; threads = threads per patch (32 / 64 / 128 / 256), occ = register-budget knob of the SSD update kernel
 // lk_ssd.cu
 cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
-cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
+// tmap: 2-D tensor map of the frame with a TILE_W x TILE_H box, or null (window staging off)
+cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, const CUtensorMap *tmap, cudaStream_t st);
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
 // lk_ncc.cu

@@ -98,7 +98,31 @@ MTFB_HD double sample_pixel(const Image &im, double x, double y){
 // a rarely taken branch the caller runs afterwards for the components flagged in Sample::lit.
 struct Sample { double val, gx, gy; int lit; };     // lit bit 0 / 1: gx / gy must be recomputed literally
 
-template<bool UNIT_MULT> MTFB_HD Sample sample_fast(const Image &im, double x, double y, double grad_eps, double mult){
+// where the four neighbours of a sample come from: global memory (read-only path) ...
+struct GlobalFetch {
+	MTFB_HD void operator()(const Image &im, int lx, int ux, int ly, int uy, double &p00, double &p01, double &p10, double &p11) const{
+		const float *r0 = im.data + (size_t)ly*im.pitch, *r1 = im.data + (size_t)uy*im.pitch;
+		p00 = MTFB_LDG(r0 + lx); p01 = MTFB_LDG(r0 + ux); p10 = MTFB_LDG(r1 + lx); p11 = MTFB_LDG(r1 + ux);
+	}
+};
+// ... or a TW x TH window of the frame staged in shared memory (by TMA), falling back to global memory for a
+// sample whose cell is not inside the window
+template<int TW, int TH> struct TileFetch {
+	const float *tile;      // TH rows of TW floats
+	int x0, y0;             // image coordinates of tile[0]; on == false: window not loaded
+	bool on;
+	MTFB_HD void operator()(const Image &im, int lx, int ux, int ly, int uy, double &p00, double &p01, double &p10, double &p11) const{
+		const int tx = lx - x0, ty = ly - y0, ux_ = ux - x0, uy_ = uy - y0;
+		if(on && tx >= 0 && ty >= 0 && ux_ < TW && uy_ < TH){
+			p00 = tile[ty*TW + tx]; p01 = tile[ty*TW + ux_]; p10 = tile[uy_*TW + tx]; p11 = tile[uy_*TW + ux_];
+		} else{
+			GlobalFetch()(im, lx, ux, ly, uy, p00, p01, p10, p11);
+		}
+	}
+};
+
+template<bool UNIT_MULT, class Fetch> MTFB_HD Sample sample_fast(const Image &im, const Fetch &fetch, double x, double y,
+	double grad_eps, double mult){
 	Sample o;
 	const bool inb = !check_overflow(x, y, im.hd, im.wd);
 	const double xs = inb ? x : 0.0, ys = inb ? y : 0.0;
@@ -111,8 +135,8 @@ template<bool UNIT_MULT> MTFB_HD Sample sample_fast(const Image &im, double x, d
 	const bool ok = inb && ux < im.w && uy < im.h;
 	ux = ux < im.w ? ux : im.w - 1;
 	uy = uy < im.h ? uy : im.h - 1;
-	const float *r0 = im.data + (size_t)ly*im.pitch, *r1 = im.data + (size_t)uy*im.pitch;
-	double p00 = MTFB_LDG(r0 + lx), p01 = MTFB_LDG(r0 + ux), p10 = MTFB_LDG(r1 + lx), p11 = MTFB_LDG(r1 + ux);
+	double p00, p01, p10, p11;
+	fetch(im, lx, ux, ly, uy, p00, p01, p10, p11);
 	const double v = p00 * (1 - dx)*(1 - dy) + p01 * dx*(1 - dy) + p10 * (1 - dx)*dy + p11 * dx*dy;
 	o.val = ok ? v : 128.0;
 	// both +-eps samples in the cell of (x, y)?  (dx = x - lx is exact)
@@ -123,6 +147,9 @@ template<bool UNIT_MULT> MTFB_HD Sample sample_fast(const Image &im, double x, d
 	if(!UNIT_MULT){ o.gx = o.gx * mult; o.gy = o.gy * mult; }
 	o.lit = (fast_x ? 0 : 1) | (fast_y ? 0 : 2);
 	return o;
+}
+template<bool UNIT_MULT> MTFB_HD Sample sample_fast(const Image &im, double x, double y, double grad_eps, double mult){
+	return sample_fast<UNIT_MULT>(im, GlobalFetch(), x, y, grad_eps, mult);
 }
 MTFB_HD void sample_literal(const Image &im, double x, double y, double grad_eps, double grad_mult, Sample &o){
 	if(o.lit & 1){

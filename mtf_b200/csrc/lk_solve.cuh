@@ -33,6 +33,9 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 	const double *s_J, const double *s_Hc, double *s_W, double *s_corners, const double *s_init_corners,
 	LMState &lm, int &patch_status){
 	constexpr int S = StateSize<SSM>::value;
+#if MTFB_PROF
+	const long long pt0 = clock64();
+#endif
 	int ctrl = CTRL_NEXT;
 	bool rejected = false;
 	Mat3 W;
@@ -87,9 +90,20 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 #pragma unroll
 			for(int i = 0; i < S; ++i) e->hessian[lane*S + i] = qr.a[i];
 		}
-		qr.factor(lane, true);
-		x = -qr.solve(lane);                                     // state_update = -H^-1 J^T (NT/FCLK.cc:298)
+#if MTFB_PROF
+		const long long pt1 = clock64();
+#endif
+		qr.factor_fast(lane, true);
+#if MTFB_PROF
+		const long long pt2 = clock64();
+#endif
+		x = -qr.solve_fast(lane);                                     // state_update = -H^-1 J^T (NT/FCLK.cc:298)
 		if(qr.nonzero_pivots < S) patch_status |= MTFB_PATCH_SINGULAR;
+#if MTFB_PROF
+		const long long pt3 = clock64();
+		if(lane == 0){ atomicAdd((unsigned long long*)b.n_iters_prof + 4, (unsigned long long)(pt1 - pt0)); atomicAdd((unsigned long long*)b.n_iters_prof + 5, (unsigned long long)(pt2 - pt1));
+			atomicAdd((unsigned long long*)b.n_iters_prof + 6, (unsigned long long)(pt3 - pt2)); }
+#endif
 		lm.ssm_update = x;
 #pragma unroll
 		for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, x, s);
@@ -118,6 +132,9 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 		if(lane < 8) e->corners[lane] = nc[lane];
 		if(lane == 0){ e->f = f; e->update_norm = upd_norm; e->rejected = rejected; e->valid = 1; }
 	}
+#if MTFB_PROF
+	if(lane == 0) atomicAdd((unsigned long long*)b.n_iters_prof + 7, (unsigned long long)(clock64() - pt0));
+#endif
 	return ctrl;
 }
 

@@ -74,8 +74,32 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 // ------------------------------------------------------------------------------------------------
 // update(): the whole per-frame loop
 // ------------------------------------------------------------------------------------------------
-template<int SSM, int SM, int T, int OCC>
-__global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBatch b){
+// MTFB_TMA_TENSOR = 1 stages the window with one cp.async.bulk.tensor.2d (UTMALDG).  On the gpurun B200 boxes that
+// instruction raises `illegal instruction` even in the CUDA programming guide's minimal form (standalone repro:
+// profiles/experiments/tma2d_test.cu), so the default build copies the window cooperatively; the 1-D bulk copy
+// (UBLKCP, pf_kernels.cu) works.
+#ifndef MTFB_TMA_TENSOR
+#define MTFB_TMA_TENSOR 0
+#endif
+// MTFB_WINDOW = 1 builds and uses the shared-memory window variant.  Measured SLOWER than sampling through L1
+// (1.93 vs 1.72 ms per launch, profiles/README.md): the gathers of one patch already hit L1, and the window costs an
+// index test per sample and 16 KB of shared memory per patch.  Off by default.
+#ifndef MTFB_WINDOW
+#define MTFB_WINDOW 0
+#endif
+
+// MTFB_PROF = 1: clock64() stamps around the phases of a pass, summed into b.am_scal[0..] of patch 0 (experiment builds)
+#if MTFB_PROF
+#define MTFB_PROF_T(k) const long long prof_t##k = clock64();
+#define MTFB_PROF_ADD() if(tid == 0){ atomicAdd((unsigned long long*)b.n_iters_prof + 0, (unsigned long long)(prof_t1 - prof_t0)); \
+	atomicAdd((unsigned long long*)b.n_iters_prof + 1, (unsigned long long)(prof_t2 - prof_t1)); atomicAdd((unsigned long long*)b.n_iters_prof + 2, (unsigned long long)(prof_t3 - prof_t2)); }
+#else
+#define MTFB_PROF_T(k)
+#define MTFB_PROF_ADD()
+#endif
+
+template<int SSM, int SM, int T, int OCC, bool TILE>
+__global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBatch b, const __grid_constant__ CUtensorMap tmap){
 	constexpr int S = StateSize<SSM>::value;
 	typedef AccLayout<S> L;
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -85,9 +109,48 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 	__shared__ double s_J[S], s_Hc[S*S];
 	__shared__ int s_ctrl;
 	__shared__ double s_dlt[9];
+	__shared__ __align__(128) float s_tile[TILE ? TILE_W*TILE_H : 1];
+	__shared__ __align__(8) unsigned long long s_bar;
+	__shared__ int s_tile_xy[3];
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
+	if(TILE && tid == 0) mbar_init(&s_bar, 1);
 	cta_sync<T>();
+	// Stage the window of the frame this patch will sample during the frame: one TMA tensor copy of a TILE_W x TILE_H box
+	// centred on the patch's current bounding box (the box of a convex quadrilateral's corners bounds all its points).
+	// A patch that is too large for the window, or that walks out of it during the passes, reads global memory instead.
+	TileFetch<TILE_W, TILE_H> fetch;
+	fetch.tile = s_tile; fetch.x0 = 0; fetch.y0 = 0; fetch.on = false;
+	if(TILE){
+		if(tid == 0){
+			double xmin = s_corners[0], xmax = s_corners[0], ymin = s_corners[4], ymax = s_corners[4];
+#pragma unroll
+			for(int i = 1; i < 4; ++i){
+				xmin = fmin(xmin, s_corners[i]); xmax = fmax(xmax, s_corners[i]);
+				ymin = fmin(ymin, s_corners[4 + i]); ymax = fmax(ymax, s_corners[4 + i]);
+			}
+			const bool fits = (xmax - xmin) <= TILE_W - 6 && (ymax - ymin) <= TILE_H - 6 &&
+				xmin > -1e6 && xmax < 1e6 && ymin > -1e6 && ymax < 1e6;          // also false for NaN corners
+			int x0 = 0, y0 = 0;
+			if(fits){ x0 = (int)floor(0.5*(xmin + xmax)) - TILE_W / 2; y0 = (int)floor(0.5*(ymin + ymax)) - TILE_H / 2; }
+			s_tile_xy[0] = x0; s_tile_xy[1] = y0; s_tile_xy[2] = fits;
+		}
+		cta_sync<T>();
+		fetch.x0 = s_tile_xy[0]; fetch.y0 = s_tile_xy[1]; fetch.on = s_tile_xy[2] != 0;
+		if(fetch.on){
+#if MTFB_TMA_TENSOR
+			if(tid == 0){ mbar_expect_tx(&s_bar, TILE_W*TILE_H * 4); tma_load_2d(s_tile, &tmap, fetch.x0, fetch.y0, &s_bar); }
+			mbar_wait(&s_bar, 0);
+#else
+			// cooperative copy of the window (rows are 256-byte runs: coalesced); outside the image the window is never read
+			for(int i = tid; i < TILE_W*TILE_H; i += T){
+				const int gx = fetch.x0 + (i % TILE_W), gy = fetch.y0 + (i / TILE_W);
+				s_tile[i] = (gx >= 0 && gx < b.img.w && gy >= 0 && gy < b.img.h) ? __ldg(b.img.data + (size_t)gy*b.img.pitch + gx) : 0.f;
+			}
+			cta_sync<T>();
+#endif
+		}
+	}
 	// MTFB_SMEM_MATS: 0 = both warp-uniform 3x3 matrices in registers (36 registers next to the 45 fp64
 	// accumulators), 1 = the DLT warp, 2 = both read from shared memory where they are used (broadcast loads)
 #ifndef MTFB_SMEM_MATS
@@ -108,6 +171,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
 	while(iter_id < b.max_iters){
+		MTFB_PROF_T(0)
 		double abcd[4] = { 0, 0, 0, 0 };
 		if(SSM == SSM_AFF){
 			// Affine.cc:217-220 reads curr_state(2)+1, (3), (4), (5)+1 with curr_state = getStateFromWarp(curr_warp)
@@ -134,12 +198,12 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 			if(MTFB_PIXELS_PER_TRIP > 1) it.next(T);
 			PixTerms<S> ta, tb;
 			PixGeom ga = pixel_geometry<SSM>(dlt, Wm, ua, va), gb;
-			Sample sa = need_grad ? sample_fast<true>(b.img, ga.wx, ga.wy, b.grad_eps, b.pix_mult) : Sample(), sb;
+			Sample sa = need_grad ? sample_fast<true>(b.img, fetch, ga.wx, ga.wy, b.grad_eps, b.pix_mult) : Sample(), sb;
 			const double i0a = I0[pa];
 			double i0b = 0;
 			if(MTFB_PIXELS_PER_TRIP > 1){
 				gb = pixel_geometry<SSM>(dlt, Wm, ub, vbv);
-				sb = need_grad ? sample_fast<true>(b.img, gb.wx, gb.wy, b.grad_eps, b.pix_mult) : Sample();
+				sb = need_grad ? sample_fast<true>(b.img, fetch, gb.wx, gb.wy, b.grad_eps, b.pix_mult) : Sample();
 				i0b = I0[pb];
 			}
 			if(need_grad){
@@ -158,7 +222,9 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 			accumulate_terms<S>(acc, ta, need_grad);
 			if(MTFB_PIXELS_PER_TRIP > 1 && vb) accumulate_terms<S>(acc, tb, need_grad);
 		}
+		MTFB_PROF_T(1)
 		block_reduce<L::NA, T>(acc, s_part, s_sum);
+		MTFB_PROF_T(2)
 		++n_passes;
 		// SSD: f = -sum r^2 / 2 (SSDBase.cc:94), df_dp = sum df_dI * dI_dp, self Hessian = -J^T J (SSDBase.h:91-94)
 		if(tid < S*S){
@@ -182,6 +248,8 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 			if(lane == 0) s_ctrl = ctrl;
 		}
 		cta_sync<T>();
+		MTFB_PROF_T(3)
+		MTFB_PROF_ADD()
 		const int ctrl = s_ctrl;
 		if(ctrl == CTRL_BREAK) break;
 		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
@@ -252,34 +320,41 @@ cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corner
 	return cudaGetLastError();
 }
 
-template<int SSM, int SM, int OCC> static cudaError_t launch_update_o(int threads, const DevBatch &b, cudaStream_t st){
+template<int SSM, int SM, int OCC, bool TILE> static cudaError_t launch_update_o(int threads, const DevBatch &b, const CUtensorMap &tmap,
+	cudaStream_t st){
 	switch(threads){
-	case 32: ssd_update_kernel<SSM, SM, 32, OCC><<<b.P, 32, 0, st>>>(b); break;
-	case 64: ssd_update_kernel<SSM, SM, 64, OCC><<<b.P, 64, 0, st>>>(b); break;
-	case 128: ssd_update_kernel<SSM, SM, 128, OCC><<<b.P, 128, 0, st>>>(b); break;
-	case 256: ssd_update_kernel<SSM, SM, 256, OCC><<<b.P, 256, 0, st>>>(b); break;
+	case 32: ssd_update_kernel<SSM, SM, 32, OCC, TILE><<<b.P, 32, 0, st>>>(b, tmap); break;
+	case 64: ssd_update_kernel<SSM, SM, 64, OCC, TILE><<<b.P, 64, 0, st>>>(b, tmap); break;
+	case 128: ssd_update_kernel<SSM, SM, 128, OCC, TILE><<<b.P, 128, 0, st>>>(b, tmap); break;
+	case 256: ssd_update_kernel<SSM, SM, 256, OCC, TILE><<<b.P, 256, 0, st>>>(b, tmap); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
-template<int SSM, int SM> static cudaError_t launch_update_t(int threads, int occ, const DevBatch &b, cudaStream_t st){
-	if(occ == 0) return launch_update_o<SSM, SM, 0>(threads, b, st);
-	if(occ == 1) return launch_update_o<SSM, SM, 1>(threads, b, st);
-	return launch_update_o<SSM, SM, 2>(threads, b, st);
+template<int SSM, int SM> static cudaError_t launch_update_t(int threads, int occ, const DevBatch &b, const CUtensorMap *tmap, cudaStream_t st){
+#if MTFB_WINDOW
+	if(tmap && occ == 0) return launch_update_o<SSM, SM, 0, true>(threads, b, *tmap, st);
+#else
+	(void)tmap;
+#endif
+	static const CUtensorMap none = {};
+	if(occ == 0) return launch_update_o<SSM, SM, 0, false>(threads, b, none, st);
+	if(occ == 1) return launch_update_o<SSM, SM, 1, false>(threads, b, none, st);
+	return launch_update_o<SSM, SM, 2, false>(threads, b, none, st);
 }
-cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st){
+cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, const CUtensorMap *tmap, cudaStream_t st){
 #ifdef MTFB_ONLY_FCLK_HOM      // experiment builds (profiles/): one combination, fast to compile
-	if(ssm == SSM_HOM && sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, st);
+	if(ssm == SSM_HOM && sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, tmap, st);
 	return cudaErrorNotSupported;
 #else
 	if(ssm == SSM_HOM){
-		if(sm == SM_ESM) return launch_update_t<SSM_HOM, SM_ESM>(threads, occ, b, st);
-		if(sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, st);
-		return launch_update_t<SSM_HOM, SM_ICLK>(threads, occ, b, st);
+		if(sm == SM_ESM) return launch_update_t<SSM_HOM, SM_ESM>(threads, occ, b, tmap, st);
+		if(sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, tmap, st);
+		return launch_update_t<SSM_HOM, SM_ICLK>(threads, occ, b, tmap, st);
 	}
-	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, occ, b, st);
-	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, occ, b, st);
-	return launch_update_t<SSM_AFF, SM_ICLK>(threads, occ, b, st);
+	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, occ, b, tmap, st);
+	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, occ, b, tmap, st);
+	return launch_update_t<SSM_AFF, SM_ICLK>(threads, occ, b, tmap, st);
 #endif
 }
 

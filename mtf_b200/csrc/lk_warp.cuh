@@ -185,6 +185,136 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 		for(int i = 0; i < SIZE; ++i) lane_at_pos[i] = __ffs(__ballot_sync(FULL_MASK, is_col && pos == i)) - 1;
 	}
 
+	// ---- the same factorisation tuned for the per-pass S x S solve, where it sits on every patch's critical path:
+	// pivoting and the rank test work on SQUARED column norms recomputed from the trailing rows (no square roots, no
+	// divisions, no down-dating bookkeeping; for 8 rows recomputing is cheaper and more accurate than down-dating),
+	// sums are pairwise trees instead of sequential chains, and every division by a pivot is a multiplication by a
+	// reciprocal taken once.  Same algorithm and rank rule as factor(); results differ from it by rounding only.
+	double rdiag;            // 1 / R(k, k) on the lane whose column became pivot k (factor_fast)
+
+	template<int FROM> __device__ __forceinline__ double tail_sumsq() const{
+		double p[ROWS];
+#pragma unroll
+		for(int r = FROM; r < ROWS; ++r) p[r] = a[r] * a[r];
+#pragma unroll
+		for(int w = 1; w < ROWS; w *= 2){
+#pragma unroll
+			for(int r = FROM; r + w < ROWS; r += 2 * w) p[r] += p[r + w];
+		}
+		return FROM < ROWS ? p[FROM < ROWS ? FROM : 0] : 0.0;
+	}
+	template<int FROM> __device__ __forceinline__ double tail_dot(const double (&v)[ROWS]) const{
+		double p[ROWS];
+#pragma unroll
+		for(int r = FROM; r < ROWS; ++r) p[r] = v[r] * a[r];
+#pragma unroll
+		for(int w = 1; w < ROWS; w *= 2){
+#pragma unroll
+			for(int r = FROM; r + w < ROWS; r += 2 * w) p[r] += p[r + w];
+		}
+		return FROM < ROWS ? p[FROM < ROWS ? FROM : 0] : 0.0;
+	}
+	template<int K> __device__ __forceinline__ void fast_step(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
+		const bool cand_ok = is_col && pos >= K && (csq == csq);
+		const unsigned hi = cand_ok ? (unsigned)__double2hiint(csq) : 0u;
+		const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+		const bool c1 = cand_ok && hi == mhi;
+		const unsigned lo = c1 ? (unsigned)__double2loint(csq) : 0u;
+		const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+		const bool c2 = c1 && lo == mlo;
+		int biggest = (int)__reduce_min_sync(FULL_MASK, c2 ? (unsigned)pos : 0xffffu);
+		double bsq = __hiloint2double((int)mhi, (int)mlo);
+		if(biggest == 0xffff){ biggest = K; bsq = 0; }
+		if(nonzero_pivots == SIZE && bsq < thsq * double(ROWS - K)) nonzero_pivots = K;
+		if(is_col){ if(pos == biggest) pos = K; else if(pos == K) pos = biggest; }
+		const int piv_lane = __ffs(__ballot_sync(FULL_MASK, is_col && pos == K)) - 1;
+		double tau_l = 0;
+		if(lane == piv_lane){
+			const double c0 = a[K], tail_sq = tail_sumsq<K + 1>();
+			double beta;
+			if(tail_sq <= DBL_MIN){
+				tau_l = 0; beta = c0;
+#pragma unroll
+				for(int r = K + 1; r < ROWS; ++r) a[r] = 0;
+			} else{
+				beta = sqrt(c0 * c0 + tail_sq);
+				if(c0 >= 0) beta = -beta;
+				const double rden = ieee_rcp(c0 - beta);
+#pragma unroll
+				for(int r = K + 1; r < ROWS; ++r) a[r] = a[r] * rden;
+			}
+			rdiag = ieee_rcp(beta);
+			if(tail_sq > DBL_MIN) tau_l = (beta - c0) * rdiag;
+			a[K] = beta;
+		}
+		const double tk = __shfl_sync(FULL_MASK, tau_l, piv_lane);
+		tau[K] = tk;
+		double v[ROWS];
+#pragma unroll
+		for(int r = K + 1; r < ROWS; ++r) v[r] = __shfl_sync(FULL_MASK, a[r], piv_lane);
+		const bool apply = (is_col && pos > K) || (is_rhs && K < nonzero_pivots);
+		if(apply){
+			if(ROWS - K == 1){
+				a[K] *= (1 - tk);
+			} else if(tk != 0){
+				const double t = tail_dot<K + 1>(v) + a[K];
+				const double tt = tk * t;
+				a[K] -= tt;
+#pragma unroll
+				for(int r = K + 1; r < ROWS; ++r) a[r] = fma(-tt, v[r], a[r]);
+			}
+		}
+		if(is_col && pos > K) csq = tail_sumsq<K + 1>();
+	}
+	template<int K> __device__ __forceinline__ void fast_steps(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
+		fast_step<K>(lane, is_col, is_rhs, csq, thsq);
+		if(K + 1 < SIZE) fast_steps<(K + 1 < SIZE ? K + 1 : K)>(lane, is_col, is_rhs, csq, thsq);
+	}
+	__device__ __forceinline__ void factor_fast(int lane, bool with_rhs){
+		const bool is_col = lane < COLS;
+		const bool is_rhs = with_rhs && (lane == COLS);
+		pos = is_col ? lane : -1;
+		rdiag = 0;
+		double csq = tail_sumsq<0>();
+		double maxsq;
+		{
+			const bool ok = is_col && (csq == csq);
+			const unsigned hi = ok ? (unsigned)__double2hiint(csq) : 0u;
+			const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+			const unsigned lo = (ok && hi == mhi) ? (unsigned)__double2loint(csq) : 0u;
+			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+			maxsq = __hiloint2double((int)mhi, (int)mlo);
+		}
+		const double e = DBL_EPSILON / double(ROWS);
+		const double thsq = maxsq * (e * e);                  // (max norm * eps / rows)^2, Eigen's threshold_helper
+		nonzero_pivots = SIZE;
+		fast_steps<0>(lane, is_col, is_rhs, csq, thsq);
+#pragma unroll
+		for(int i = 0; i < SIZE; ++i) lane_at_pos[i] = __ffs(__ballot_sync(FULL_MASK, is_col && pos == i)) - 1;
+	}
+	__device__ __forceinline__ double solve_fast(int lane){
+		static_assert(ROWS == COLS, "solve_fast() is written for the square systems of the LK loop");
+		const int np = nonzero_pivots;
+#pragma unroll
+		for(int i = SIZE - 1; i >= 0; --i){
+			double s = a[i];
+#pragma unroll
+			for(int j = i + 1; j < SIZE; ++j){
+				const double rij = __shfl_sync(FULL_MASK, a[i], lane_at_pos[j]);
+				if(j < np) s = fma(-rij, a[j], s);
+			}
+			const double rinv = __shfl_sync(FULL_MASK, rdiag, lane_at_pos[i]);
+			if(lane == COLS && i < np) a[i] = s * rinv;
+		}
+		double x = 0;
+#pragma unroll
+		for(int i = 0; i < SIZE; ++i){
+			const double ci = __shfl_sync(FULL_MASK, a[i], COLS);
+			if(pos == i) x = (i < np) ? ci : 0.0;
+		}
+		return x;
+	}
+
 	// back-substitution on the rhs lane, then x[perm[i]] = c[i]: returns x[lane] on lanes < COLS
 	__device__ __forceinline__ double solve(int lane){
 		static_assert(ROWS == COLS, "solve() is written for the square systems of the LK loop");

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <string>
@@ -75,10 +76,34 @@ cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, co
 	if(p.am == MTFB_AM_NCC) return launch_init_ncc(p.ssm, threads, b, d_corners, st);
 	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
 }
-cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st){
+cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, const CUtensorMap *tmap,
+	cudaStream_t st){
 	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
-	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, st);
+	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, tmap, st);
+}
+
+// 2-D tensor map of the frame for the TMA window copy (box TILE_W x TILE_H floats); false if the frame's layout does
+// not meet the TMA alignment rules (then the kernels sample global memory only)
+bool encode_frame_tensor_map(CUtensorMap *out, const float *data, int h, int w, int pitch){
+	typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+		const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static encode_fn fn = nullptr;
+	static bool looked = false;
+	if(!looked){
+		looked = true;
+		void *ptr = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			fn = reinterpret_cast<encode_fn>(ptr);
+	}
+	if(!fn || (reinterpret_cast<uintptr_t>(data) & 15) || ((size_t)pitch * 4) % 16 != 0 || w < 1 || h < 1) return false;
+	const cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
+	const cuuint64_t strides[1] = { (cuuint64_t)pitch * 4 };
+	const cuuint32_t box[2] = { (cuuint32_t)TILE_W, (cuuint32_t)TILE_H };
+	const cuuint32_t estr[2] = { 1, 1 };
+	return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 } // namespace
@@ -98,6 +123,8 @@ struct mtfb_ctx {
 	mtfb_iter_log *d_log;
 	double *d_scratch; size_t scratch_bytes;    // getters / pf
 	bool have_image, initialized;
+	alignas(64) CUtensorMap tmap; bool have_tmap;
+	const float *tmap_data; int tmap_h, tmap_w, tmap_pitch;
 	long launches;
 };
 
@@ -216,6 +243,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
+		b.n_iters_prof = nullptr;
+#if MTFB_PROF
+		if(cudaMalloc(&b.n_iters_prof, 64 * sizeof(long long)) != cudaSuccess || cudaMemset(b.n_iters_prof, 0, 64 * sizeof(long long)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+#endif
 		b.log = nullptr; b.log_slots = 0;
 		b.max_iters = p->max_iters; b.hess_type = p->hess_type; b.jac_type = p->jac_type;
 		b.leven_marq = p->leven_marq; b.nt_semantics = p->nt_semantics;
@@ -259,6 +290,13 @@ mtfb_status mtfb_synchronize(mtfb_ctx *c){
 	return MTFB_OK;
 }
 
+static void refresh_tensor_map(mtfb_ctx *c){
+	const Image &im = c->b.img;
+	if(c->have_tmap && c->tmap_data == im.data && c->tmap_h == im.h && c->tmap_w == im.w && c->tmap_pitch == im.pitch) return;
+	c->have_tmap = encode_frame_tensor_map(&c->tmap, im.data, im.h, im.w, im.pitch);
+	c->tmap_data = im.data; c->tmap_h = im.h; c->tmap_w = im.w; c->tmap_pitch = im.pitch;
+}
+
 mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int row_stride){
 	if(!c || !host_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image: null argument");
 	if(h < 2 || w < 2 || row_stride < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image: bad geometry %d x %d stride %d", h, w, row_stride);
@@ -275,6 +313,7 @@ mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int
 		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->stream));
 	c->b.img = make_image(c->d_img_own, h, w, pitch);
 	c->have_image = true;
+	refresh_tensor_map(c);
 	return MTFB_OK;
 }
 
@@ -283,6 +322,7 @@ mtfb_status mtfb_set_image_device(mtfb_ctx *c, const float *dev_img, int h, int 
 	if(h < 2 || w < 2 || pitch < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: bad geometry %d x %d pitch %d", h, w, pitch);
 	c->b.img = make_image(dev_img, h, w, pitch);
 	c->have_image = true;
+	refresh_tensor_map(c);
 	return MTFB_OK;
 }
 
@@ -328,7 +368,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->have_tmap ? &c->tmap : nullptr, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -380,7 +420,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->have_tmap ? &c->tmap : nullptr, c->stream));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);
@@ -478,6 +518,13 @@ mtfb_status mtfb_get_init_pts(mtfb_ctx *c, double *out){
 	++c->launches;
 	return d2h(c, out, d_pts, 2 * N*P*sizeof(double));
 }
+
+#if MTFB_PROF
+extern "C" int mtfb_prof_read(mtfb_ctx *c, long long *out, int n){
+	cudaStreamSynchronize(c->stream);
+	return (int)cudaMemcpy(out, c->b.n_iters_prof, n*sizeof(long long), cudaMemcpyDeviceToHost);
+}
+#endif
 
 mtfb_status mtfb_device_results(mtfb_ctx *c, double **d_corners, double **d_state, int **d_n_iters){
 	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_device_results: null context");

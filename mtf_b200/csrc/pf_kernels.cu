@@ -15,27 +15,6 @@
 
 namespace mtfb {
 
-__device__ __forceinline__ unsigned smem_u32(const void *p){ return (unsigned)__cvta_generic_to_shared(p); }
-
-// 1-D bulk async copy global -> shared (TMA, SASS UBLKCP), completion on an mbarrier
-__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar){
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		:: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count){
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes){
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase){
-	unsigned done;
-	do{
-		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-			: "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
-	} while(!done);
-}
-
 // dynamic shared memory: I0[N] | gA[N] | gB[N] | (gC[N] for the homography)
 //   homography: (gA, gB, gC) = init_pts_hm = dlt . (u, v, 1)   (Homography.cc:68 keeps the DLT's third row)
 //   affine:     (gA, gB)     = init_pts    = dehomogenize(dlt . (u, v, 1))
@@ -50,10 +29,7 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 	double *s_I0 = smem, *s_gA = smem + N, *s_gB = smem + 2 * N, *s_gC = smem + 3 * N;
 	// stage the template with one bulk copy (N * 8 bytes, 16-byte aligned: N is even or the tail is copied by hand)
 	const unsigned bulk_bytes = (unsigned)((N * 8) & ~15);
-	if(tid == 0){
-		mbar_init(&s_bar, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
+	if(tid == 0) mbar_init(&s_bar, 1);
 	__syncthreads();
 	if(tid == 0){
 		mbar_expect_tx(&s_bar, bulk_bytes);
