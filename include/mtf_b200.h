@@ -68,7 +68,8 @@ typedef struct mtfb_params {
 	int max_iters;
 	double epsilon;              /* stop when || prev_corners - curr_corners ||^2 < epsilon       */
 	int hess_type, jac_type;
-	int chained_warp;            /* {esm,fc,ic}_chained_warp; only 1 is implemented               */
+	int chained_warp;            /* {esm,fc,ic}_chained_warp (nt:: search methods only; 0 = the
+	                                getWarpedImgGrad path, evaluated literally)                    */
 	int leven_marq;
 	double lm_delta_init, lm_delta_update;
 	int nt_semantics;            /* 1: nt::SM control flow (SM/src/NT), 0: templated twins (SM/src) */

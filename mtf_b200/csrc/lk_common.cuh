@@ -96,11 +96,24 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 		:: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// 2-D tensor copy global -> shared: the box of the tensor map whose first element is (x, y); out-of-range elements are
-// zero-filled by the hardware
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar){
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-		:: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+// am.updatePixGrad + ssm.cmpt*PixJacobian in their two flavours (NT/FCLK.cc:222-236, NT/ESM.cc:387-404, NT/ICLK.cc:205-219):
+//   chained:      gradient of the image at the warped point (updatePixGrad(pts)), then cmptWarpedPixJacobian
+//   not chained:  gradient of the warped image (updateGradPts + getWarpedImgGrad), then cmptInitPixJacobian
+// fills smp.val / gx / gy (raw pixel units times pix_mult; the caller applies pix_add to val) and the Jacobian row
+template<int SSM, bool UNIT_MULT, class MW> __device__ __forceinline__ void pixel_value_and_gradient(const DevBatch &b, const MW &W,
+	const PixGeom &g, Sample &smp){
+	if(b.chained){
+		smp = sample_fast<UNIT_MULT>(b.img, g.wx, g.wy, b.grad_eps, b.pix_mult);
+		if(smp.lit) sample_literal(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, smp);
+	} else{
+		smp.val = sample_pixel(b.img, g.wx, g.wy); smp.lit = 0;
+		warped_image_gradient<SSM>(b.img, W, g, b.grad_eps, b.grad_mult, smp.gx, smp.gy);
+	}
+}
+template<int SSM, class MW> __device__ __forceinline__ void pixel_jacobian_row(const DevBatch &b, const MW &W, const double *abcd,
+	const PixGeom &g, double gx, double gy, double *J){
+	if(b.chained) warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
+	else init_pix_jacobian<SSM>(g.ix, g.iy, gx, gy, J);
 }
 
 struct PixIter {

@@ -1,6 +1,5 @@
 // lk_kernels.cuh -- declarations shared by the kernel translation unit and the C-ABI host code.
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/mtf_b200.h"
 #include "lk_math.cuh"
@@ -20,7 +19,8 @@ struct DevBatch {
 	double *corners;             // P x 8   curr_corners
 	double *init_corners;        // P x 8
 	double *I0;                  // P x N   template pixel values (am.I0)
-	double *G0;                  // P x 2 x N  template gradient, already chained with the init warp
+	double *G0;                  // P x 2 x N  template gradient: chained with the init warp, or (chained = 0) the
+	                             //            warped-image gradient of initialize() time
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
 	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
 	double *f;                   // P       similarity
@@ -31,21 +31,18 @@ struct DevBatch {
 	int log_slots;
 	// parameters
 	int max_iters, hess_type, jac_type, leven_marq, nt_semantics;
+	int chained;                 // {esm,fc,ic}_chained_warp
 	double epsilon, lm_delta_init, lm_delta_update, grad_eps;
 	double pix_mult, pix_add;    // am pix_norm_mult / pix_norm_add (1, 0 except MI)
 	double grad_mult;            // pix_mult / (2 grad_eps)  (imgUtils.cc:238)
 };
-
-// frame window staged in shared memory by the SSD update kernel
-constexpr int TILE_W = 64, TILE_H = 64;
 
 struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
 
 // launchers; threads = threads per patch (32 / 64 / 128 / 256), occ = register-budget knob of the SSD update kernel
 // lk_ssd.cu
 cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
-// tmap: 2-D tensor map of the frame with a TILE_W x TILE_H box, or null (window staging off)
-cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, const CUtensorMap *tmap, cudaStream_t st);
+cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
 // lk_ncc.cu

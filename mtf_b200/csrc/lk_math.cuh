@@ -105,22 +105,6 @@ struct GlobalFetch {
 		p00 = MTFB_LDG(r0 + lx); p01 = MTFB_LDG(r0 + ux); p10 = MTFB_LDG(r1 + lx); p11 = MTFB_LDG(r1 + ux);
 	}
 };
-// ... or a TW x TH window of the frame staged in shared memory (by TMA), falling back to global memory for a
-// sample whose cell is not inside the window
-template<int TW, int TH> struct TileFetch {
-	const float *tile;      // TH rows of TW floats
-	int x0, y0;             // image coordinates of tile[0]; on == false: window not loaded
-	bool on;
-	MTFB_HD void operator()(const Image &im, int lx, int ux, int ly, int uy, double &p00, double &p01, double &p10, double &p11) const{
-		const int tx = lx - x0, ty = ly - y0, ux_ = ux - x0, uy_ = uy - y0;
-		if(on && tx >= 0 && ty >= 0 && ux_ < TW && uy_ < TH){
-			p00 = tile[ty*TW + tx]; p01 = tile[ty*TW + ux_]; p10 = tile[uy_*TW + tx]; p11 = tile[uy_*TW + ux_];
-		} else{
-			GlobalFetch()(im, lx, ux, ly, uy, p00, p01, p10, p11);
-		}
-	}
-};
-
 template<bool UNIT_MULT, class Fetch> MTFB_HD Sample sample_fast(const Image &im, const Fetch &fetch, double x, double y,
 	double grad_eps, double mult){
 	Sample o;
@@ -289,7 +273,7 @@ template<int SSM> MTFB_HD void warp_corners(const Mat3 &w, const double *init_co
 //   Homography (normalized_init = 0): init_pts_hm keeps the DLT's third row (Homography.cc:68), so
 //                  curr_pts_hm = W . (dlt . (u,v,1)) and D = curr_pts_hm(2)
 //   Affine:        init_pts_hm is re-homogenised (Affine.cc:81-82), curr_pts = W.topRows(2) . (ix,iy,1)
-struct PixGeom { double ix, iy, wx, wy, D, rD; };     // rD = RN(1 / D) = the reference's inv_det (Homography.cc:250)
+struct PixGeom { double ix, iy, wx, wy, cx, cy, D, rD; };   // (cx, cy, D) = curr_pts_hm; rD = RN(1 / D) = the reference's inv_det (Homography.cc:250)
 
 // the iteration-invariant half: init_pts_hm = dlt . (u, v, 1) and init_pts = its dehomogenisation
 template<class MD> MTFB_HD void template_point(const MD &dlt, double u, double v, double &hx, double &hy, double &hz,
@@ -308,11 +292,12 @@ template<int SSM, class MW> MTFB_HD PixGeom warp_template_point(const MW &W, dou
 		double cx = W[0] * hx; cx = cx + W[1] * hy; cx = cx + W[2] * hz;
 		double cy = W[3] * hx; cy = cy + W[4] * hy; cy = cy + W[5] * hz;
 		double cz = W[6] * hx; cz = cz + W[7] * hy; cz = cz + W[8] * hz;
+		g.cx = cx; g.cy = cy;
 		g.D = cz; g.rD = ieee_rcp(cz); g.wx = div_by(cx, cz, g.rD); g.wy = div_by(cy, cz, g.rD);
 	} else{
 		double cx = W[0] * ix; cx = cx + W[1] * iy; cx = cx + W[2] * 1.0;
 		double cy = W[3] * ix; cy = cy + W[4] * iy; cy = cy + W[5] * 1.0;
-		g.D = 1.0; g.rD = 1.0; g.wx = cx; g.wy = cy;
+		g.cx = cx; g.cy = cy; g.D = 1.0; g.rD = 1.0; g.wx = cx; g.wy = cy;
 	}
 	return g;
 }
@@ -347,6 +332,33 @@ template<int SSM, class MW> MTFB_HD void warped_pix_jacobian(const MW &W, const 
 		J[4] = Ixx*b + Iyx*d; J[5] = Ixy*b + Iyy*d;
 	}
 }
+// The NON-chained gradient ({esm,fc,ic}_chained_warp = 0, the factory default of parameters.h:174,192): the gradient of
+// the WARPED image with respect to the template coordinates, i.e. central differences over the four points
+// ssm.updateGradPts builds (Homography.cc:803-827: curr_pts_hm +- eps * curr_warp.col(0|1), dehomogenised;
+// Affine.cc:293-312: curr_pts +- eps * the 2x2 block's columns) fed to utils::getWarpedImgGrad (imgUtils.cc:177-202).
+// Evaluated literally -- four more getPixVal's per pixel -- so it matches the reference bit for bit.
+template<int SSM, class MW> MTFB_HD void warped_image_gradient(const Image &im, const MW &W, const PixGeom &g, double grad_eps,
+	double grad_mult, double &gx, double &gy){
+	double px[4], py[4];
+	if(SSM == SSM_HOM){
+		const double dx0 = W[0] * grad_eps, dx1 = W[3] * grad_eps, dx2 = W[6] * grad_eps;
+		const double dy0 = W[1] * grad_eps, dy1 = W[4] * grad_eps, dy2 = W[7] * grad_eps;
+		const double ax[4] = { g.cx + dx0, g.cx - dx0, g.cx + dy0, g.cx - dy0 };
+		const double ay[4] = { g.cy + dx1, g.cy - dx1, g.cy + dy1, g.cy - dy1 };
+		const double az[4] = { g.D + dx2, g.D - dx2, g.D + dy2, g.D - dy2 };
+		for(int k = 0; k < 4; ++k){
+			const double r = ieee_rcp(az[k]);
+			px[k] = div_by(ax[k], az[k], r); py[k] = div_by(ay[k], az[k], r);
+		}
+	} else{
+		const double dx0 = W[0] * grad_eps, dx1 = W[3] * grad_eps, dy0 = W[1] * grad_eps, dy1 = W[4] * grad_eps;
+		px[0] = g.wx + dx0; py[0] = g.wy + dx1; px[1] = g.wx - dx0; py[1] = g.wy - dx1;
+		px[2] = g.wx + dy0; py[2] = g.wy + dy1; px[3] = g.wx - dy0; py[3] = g.wy - dy1;
+	}
+	gx = (sample_pixel(im, px[0], py[0]) - sample_pixel(im, px[1], py[1]))*grad_mult;
+	gy = (sample_pixel(im, px[2], py[2]) - sample_pixel(im, px[3], py[3]))*grad_mult;
+}
+
 // pixel Jacobian of the TEMPLATE from its stored, pre-chained gradient (Ix, Iy): what
 // cmptWarpedPixJacobian produced at initialize() time, when curr_warp was the identity.
 template<int SSM> MTFB_HD void init_pix_jacobian(double x, double y, double Ix, double Iy, double *J){

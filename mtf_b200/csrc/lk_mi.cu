@@ -9,15 +9,17 @@
 //   B-splines: Utilities/include/mtf/Utilities/histUtils.h:206-224 (bSpl3WithGrad), :269-280 (bSpl3Hess)
 // The reference materialises B x N weight matrices and a B^2 x N joint-gradient matrix (zero-filled every
 // pass: 5 MB at N = 10^4); here the 4 weights of a pixel are recomputed from its value where they are used.
-// One pass = sweep 1 (warp + sample, values kept in shared memory, histograms built with shared-memory fp64
-// atomics), a 72-entry log table, sweep 2 (per-pixel gradient weight from a 4 x 4 table gather, pixel
+// One pass = sweep 1 (warp + sample, values kept in shared memory, histograms built in per-lane private
+// shared-memory copies), a 72-entry log table, sweep 2 (per-pixel gradient weight from a 4 x 4 table gather, pixel
 // Jacobian row, S or 2S sums).  Implemented Hessian: InitialSelf (the ICLK default, ICLKParams.cc:6).
-// Histogram atomics make the summation order, hence the last bits of f, vary from run to run.
+// The per-pass histograms are accumulated in per-lane private copies and folded in a fixed order: deterministic.
+// (Only initialize() uses shared-memory atomics, for the B^2 x S joint-histogram Jacobian of the self Hessian.)
 #include "lk_solve.cuh"
 
 namespace mtfb {
 
 constexpr int MI_BMAX = 16;
+constexpr int MI_HBMAX = MI_BMAX + MI_BMAX*MI_BMAX;
 
 // histUtils.h:206-224
 __device__ __forceinline__ void bspl3_with_grad(double &val, double &diff, double x){
@@ -92,11 +94,11 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 	// phase 1: template values (scaled to bin units, MI.cc:91-94), chained gradient, init_hist and the self joint histogram
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
-		double val, gx, gy;
-		sample_pixel_grad<false>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
-		val = b.pix_mult*val + b.pix_add;
+		Sample smp;
+		pixel_value_and_gradient<SSM, false>(b, W, g, smp);
+		const double val = b.pix_mult*smp.val + b.pix_add;
 		double J[S];
-		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
+		pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, J);
 		I0[it.pix] = val;
 		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
 		G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
@@ -187,19 +189,29 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 	}
 }
 
-template<int SSM, int SM, int T>
+// KEEP_IT: keep the N current pixel values of sweep 1 in shared memory for sweep 2 (small patches); otherwise sweep 2
+// samples them again (same bits) and shared memory holds only the private histograms -- for 100 x 100 patches the
+// 80 KB value buffer would leave room for two warps per SM.
+template<int SSM, int SM, int T, bool KEEP_IT>
 __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch b, MiParams mp, const double *__restrict__ mi_tab){
 	constexpr int S = StateSize<SSM>::value;
 	constexpr bool CURR = (SM != SM_ICLK), INIT = (SM != SM_FCLK);
 	constexpr int NA = (CURR ? S : 0) + (INIT ? S : 0);
 	constexpr int oT = 0, o0 = CURR ? S : 0;
-	extern __shared__ __align__(16) double s_It[];                          // N current pixel values (bin units)
+	extern __shared__ __align__(16) double s_dyn[];
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int B = mp.B, N = b.N;
+	const int HB = B + B*B;                                                 // curr_hist | joint_hist entries
+	double *s_It = s_dyn;                                                   // N current pixel values (bin units), if KEEP_IT
+	const int it_slots = KEEP_IT ? ((N + 1) & ~1) : 0;
+	// one PRIVATE copy of both histograms per lane, [entry][lane]: a lane only ever touches its own column, so the
+	// 20 updates per pixel are plain read-modify-writes (bank = lane: conflict-free, no atomics, fixed summation order)
+	double *s_priv = s_dyn + it_slots + (size_t)warp*HB * 32;
 	__shared__ double s_part[(T / 32) * NA];
 	__shared__ double s_sum[NA];
 	__shared__ double s_hist[MI_BMAX], s_hist_log[MI_BMAX], s_ihist_log[MI_BMAX], s_joint[MI_BMAX*MI_BMAX];
 	__shared__ double s_fac_t[MI_BMAX*MI_BMAX], s_fac_0[MI_BMAX*MI_BMAX];
+	__shared__ double s_fold[(T / 32) * MI_HBMAX];
 	__shared__ double s_W[9], s_dlt[9], s_corners[8], s_init_corners[8], s_J[S], s_f;
 	__shared__ int s_ctrl;
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
@@ -219,25 +231,38 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 #pragma unroll
 		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
 		double abcd[4] = { (W.m[0] - 1) + 1, W.m[1], W.m[3], (W.m[4] - 1) + 1 };
-		for(int i = tid; i < B; i += T) s_hist[i] = mp.hist_pre_seed;
-		for(int i = tid; i < B*B; i += T) s_joint[i] = mp.pre_seed;
-		cta_sync<T>();
+		for(int e = 0; e < HB; ++e) s_priv[e * 32 + lane] = 0;
 		// ---- sweep 1: updatePixVals (MI.cc:166-192) + the histograms of updateSimilarity (MI.cc:346-370)
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
 			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
 			const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
-			s_It[it.pix] = It;
+			if(KEEP_IT) s_It[it.pix] = It;
 			const BinWeights bc = bin_weights(It, B), bi = bin_weights(I0[it.pix], B);
 #pragma unroll
 			for(int k = 0; k < 4; ++k){
 				if(bc.lo + k > bc.hi) continue;
-				atomicAdd(&s_hist[bc.lo + k], bc.w[k]);
+				s_priv[(bc.lo + k) * 32 + lane] += bc.w[k];
 #pragma unroll
 				for(int l = 0; l < 4; ++l){
 					if(bi.lo + l > bi.hi) continue;
-					atomicAdd(&s_joint[(bi.lo + l)*B + (bc.lo + k)], bc.w[k] * bi.w[l]);    // JH(curr_id, init_id)
+					s_priv[(B + (bi.lo + l)*B + (bc.lo + k)) * 32 + lane] += bc.w[k] * bi.w[l];    // JH(curr_id, init_id)
 				}
 			}
+		}
+		__syncwarp();
+		// fold the 32 private columns (shuffle tree), then the warps, in a fixed order
+		for(int e = 0; e < HB; ++e){
+			double v = s_priv[e * 32 + lane];
+#pragma unroll
+			for(int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL_MASK, v, off);
+			if(lane == 0) s_fold[warp*MI_HBMAX + e] = v;
+		}
+		cta_sync<T>();
+		for(int e = tid; e < HB; e += T){
+			double v = e < B ? mp.hist_pre_seed : mp.pre_seed;
+#pragma unroll
+			for(int w = 0; w < T / 32; ++w) v += s_fold[w*MI_HBMAX + e];
+			if(e < B) s_hist[e] = v; else s_joint[e - B] = v;
 		}
 		cta_sync<T>();
 		for(int i = tid; i < B; i += T){
@@ -264,7 +289,8 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		for(int i = 0; i < NA; ++i) acc[i] = 0;
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
 			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
-			const BinWeights bc = bin_weights(s_It[it.pix], B), bi = bin_weights(I0[it.pix], B);
+			const double It2 = KEEP_IT ? s_It[it.pix] : (b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add);
+			const BinWeights bc = bin_weights(It2, B), bi = bin_weights(I0[it.pix], B);
 			double df_t = 0, df_0 = 0;
 			if(CURR){
 #pragma unroll
@@ -291,10 +317,10 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 				}
 			}
 			if(CURR){
-				Sample smp = sample_fast<false>(b.img, g.wx, g.wy, b.grad_eps, b.pix_mult);
-				if(smp.lit) sample_literal(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, smp);
+				Sample smp;
+				pixel_value_and_gradient<SSM, false>(b, W, g, smp);
 				double D[S];
-				warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, D);
+				pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
 #pragma unroll
 				for(int i = 0; i < S; ++i) acc[oT + i] = fma(df_t, D[i], acc[oT + i]);
 			}
@@ -356,13 +382,17 @@ cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, mp, mi_tab, st);
 }
 
-template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
-	const size_t smem = (size_t)b.N * sizeof(double);
-	if(smem > 190 * 1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template<int SSM, int SM, int T, bool KEEP_IT> static cudaError_t launch_keep(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
+	const size_t smem = ((KEEP_IT ? (size_t)((b.N + 1) & ~1) : 0) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * 32) * sizeof(double);
+	if(smem > 200 * 1024) return cudaErrorInvalidValue;
+	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
-	mi_update_kernel<SSM, SM, T><<<b.P, T, smem, st>>>(b, mp, mi_tab);
+	mi_update_kernel<SSM, SM, T, KEEP_IT><<<b.P, T, smem, st>>>(b, mp, mi_tab);
 	return cudaGetLastError();
+}
+template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
+	if((size_t)b.N * sizeof(double) <= 24 * 1024) return launch_keep<SSM, SM, T, true>(b, mp, mi_tab, st);
+	return launch_keep<SSM, SM, T, false>(b, mp, mi_tab, st);
 }
 template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, const MiParams &mp, const double *mi_tab,
 	cudaStream_t st){

@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 	double s1[1] = { 0 };
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
-		double val, gx, gy;
-		sample_pixel_grad<true>(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, b.pix_mult, val, gx, gy);
+		Sample smp;
+		pixel_value_and_gradient<SSM, true>(b, W, g, smp);
+		const double val = smp.val;
 		double J[S];
-		warped_pix_jacobian<SSM>(W, abcd, g, gx, gy, J);
+		pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, J);
 		I0[it.pix] = val;
 		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
 		G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
@@ -164,10 +165,10 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 			const double Itcb = div_by(s_It[it.pix] - It_mean, bn, rb);                  // It_cntr_b (NCC.cc:213)
 			const double I0cc = div_by(I0[it.pix] - I0_mean, c, rc);                     // I0_cntr_c (NCC.cc:116)
 			if(L::CURR){
-				Sample smp = sample_fast<true>(b.img, g.wx, g.wy, b.grad_eps, b.pix_mult);
-				if(smp.lit) sample_literal(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, smp);
+				Sample smp;
+				pixel_value_and_gradient<SSM, true>(b, W, g, smp);
 				double D[S];
-				warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, D);
+				pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
 				const double wt = div_by(I0cc - f*Itcb, bn, rb) - mean_t;                // df_dIt (NCC.cc:214-222)
 #pragma unroll
 				for(int i = 0; i < S; ++i){

@@ -4,12 +4,6 @@
 
 namespace mtfb {
 
-// pixels per loop trip: 2 interleaves two pixels' dependency chains; measured SLOWER than 1 on B200 (register
-// pressure next to the 45 fp64 accumulators: profiles/README.md), kept as a build-time experiment knob
-#ifndef MTFB_PIXELS_PER_TRIP
-#define MTFB_PIXELS_PER_TRIP 1
-#endif
-
 // what one pixel contributes to the sums: r = I_t - I_0, Jj = the row that multiplies df/dI in the Jacobian,
 // Jt = the row whose outer product goes into the Hessian, wj = df/dI
 template<int S> struct PixTerms { double r, wj; double Jt[S], Jj[S]; };
@@ -22,15 +16,15 @@ template<int SSM, int SM, class MW> __device__ __forceinline__ void pixel_terms(
 	if(SM == SM_ICLK){
 		// df_dI0 = I_diff (SSDBase.cc:34: I_diff aliases df_dI0); Jacobian of the template
 		t.wj = t.r;
-		init_pix_jacobian<SSM>(g.ix, g.iy, G0[pix], G0[b.N + pix], t.Jj);
-		if(need_grad) warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, t.Jt);
+		init_pix_jacobian<SSM>(g.ix, g.iy, __ldcg(G0 + pix), __ldcg(G0 + b.N + pix), t.Jj);
+		if(need_grad) pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, t.Jt);
 		return;
 	}
 	t.wj = -t.r;                                                   // df_dIt = -I_diff (SSDBase.cc:115-121)
-	warped_pix_jacobian<SSM>(W, abcd, g, smp.gx, smp.gy, t.Jt);
+	pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, t.Jt);
 	if(SM == SM_ESM){
 		double J0[S];
-		init_pix_jacobian<SSM>(g.ix, g.iy, G0[pix], G0[b.N + pix], J0);
+		init_pix_jacobian<SSM>(g.ix, g.iy, __ldcg(G0 + pix), __ldcg(G0 + b.N + pix), J0);
 		if(esm_mean){
 			// mean_pix_jacobian = (init + curr) / 2 (NT/ESM.cc:246-248)
 #pragma unroll

@@ -76,34 +76,10 @@ cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, co
 	if(p.am == MTFB_AM_NCC) return launch_init_ncc(p.ssm, threads, b, d_corners, st);
 	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
 }
-cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, const CUtensorMap *tmap,
-	cudaStream_t st){
+cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st){
 	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
-	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, tmap, st);
-}
-
-// 2-D tensor map of the frame for the TMA window copy (box TILE_W x TILE_H floats); false if the frame's layout does
-// not meet the TMA alignment rules (then the kernels sample global memory only)
-bool encode_frame_tensor_map(CUtensorMap *out, const float *data, int h, int w, int pitch){
-	typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-		const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-	static encode_fn fn = nullptr;
-	static bool looked = false;
-	if(!looked){
-		looked = true;
-		void *ptr = nullptr;
-		cudaDriverEntryPointQueryResult q;
-		if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-			fn = reinterpret_cast<encode_fn>(ptr);
-	}
-	if(!fn || (reinterpret_cast<uintptr_t>(data) & 15) || ((size_t)pitch * 4) % 16 != 0 || w < 1 || h < 1) return false;
-	const cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
-	const cuuint64_t strides[1] = { (cuuint64_t)pitch * 4 };
-	const cuuint32_t box[2] = { (cuuint32_t)TILE_W, (cuuint32_t)TILE_H };
-	const cuuint32_t estr[2] = { 1, 1 };
-	return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-		CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, st);
 }
 
 } // namespace
@@ -123,8 +99,6 @@ struct mtfb_ctx {
 	mtfb_iter_log *d_log;
 	double *d_scratch; size_t scratch_bytes;    // getters / pf
 	bool have_image, initialized;
-	alignas(64) CUtensorMap tmap; bool have_tmap;
-	const float *tmap_data; int tmap_h, tmap_w, tmap_pitch;
 	long launches;
 };
 
@@ -169,8 +143,6 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(!combo_supported(p, &why))
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: (am %d, ssm %d, sm %d, hess %d, jac %d) is not implemented: %s",
 			p->am, p->ssm, p->sm, p->hess_type, p->jac_type, why);
-	if(!p->chained_warp)
-		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: chained_warp = 0 (getWarpedImgGrad path) is not implemented");
 	if(p->hom_normalized_init)
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: hom_normalized_init = 1 is not implemented");
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
@@ -179,6 +151,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	// so that the whole batch is resident in one wave) for smaller batches
 	int threads = p->threads_per_patch;
 	int occ = p->occupancy;
+	if(!threads && p->am == MTFB_AM_MI){
+		// MI keeps 18 KB of private histograms per warp (B = 8) next to the N current pixel values in shared memory
+		threads = p->n_patches >= 600 ? 32 : 64; occ = 0;
+	}
 	if(!threads){
 		if(p->n_patches >= 900){ threads = 32; occ = 0; }
 		else if(p->n_patches >= 450){ threads = 64; occ = 2; }
@@ -250,6 +226,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.log = nullptr; b.log_slots = 0;
 		b.max_iters = p->max_iters; b.hess_type = p->hess_type; b.jac_type = p->jac_type;
 		b.leven_marq = p->leven_marq; b.nt_semantics = p->nt_semantics;
+		// the templated search methods have no chained_warp switch: always chained (ESM.cc:94-95, FCLK.cc:82-86, ICLK.cc:80-90)
+		b.chained = (p->chained_warp || !p->nt_semantics) ? 1 : 0;
 		b.epsilon = p->epsilon; b.lm_delta_init = p->lm_delta_init; b.lm_delta_update = p->lm_delta_update;
 		b.grad_eps = p->grad_eps;
 		b.pix_mult = 1; b.pix_add = 0;
@@ -290,13 +268,6 @@ mtfb_status mtfb_synchronize(mtfb_ctx *c){
 	return MTFB_OK;
 }
 
-static void refresh_tensor_map(mtfb_ctx *c){
-	const Image &im = c->b.img;
-	if(c->have_tmap && c->tmap_data == im.data && c->tmap_h == im.h && c->tmap_w == im.w && c->tmap_pitch == im.pitch) return;
-	c->have_tmap = encode_frame_tensor_map(&c->tmap, im.data, im.h, im.w, im.pitch);
-	c->tmap_data = im.data; c->tmap_h = im.h; c->tmap_w = im.w; c->tmap_pitch = im.pitch;
-}
-
 mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int row_stride){
 	if(!c || !host_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image: null argument");
 	if(h < 2 || w < 2 || row_stride < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image: bad geometry %d x %d stride %d", h, w, row_stride);
@@ -313,7 +284,6 @@ mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int
 		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->stream));
 	c->b.img = make_image(c->d_img_own, h, w, pitch);
 	c->have_image = true;
-	refresh_tensor_map(c);
 	return MTFB_OK;
 }
 
@@ -322,7 +292,6 @@ mtfb_status mtfb_set_image_device(mtfb_ctx *c, const float *dev_img, int h, int 
 	if(h < 2 || w < 2 || pitch < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: bad geometry %d x %d pitch %d", h, w, pitch);
 	c->b.img = make_image(dev_img, h, w, pitch);
 	c->have_image = true;
-	refresh_tensor_map(c);
 	return MTFB_OK;
 }
 
@@ -368,7 +337,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->have_tmap ? &c->tmap : nullptr, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -420,7 +389,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->have_tmap ? &c->tmap : nullptr, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);

@@ -225,7 +225,7 @@ def test_error_contract(seq384):
         g.initialize(common.patches(2, 49.0, 384, 384))
     assert e.value.type == "LogicError"                       # no image yet
     with pytest.raises(api.MTFError) as e:
-        _gpu("ssd", "homography", "fclk", 2, chained_warp=0)
+        _gpu("ssd", "homography", "fclk", 2, hom_normalized_init=1)
     assert e.value.type == "FunctonNotImplemented"
     bad = common.patches(2, 49.0, 384, 384); bad[0, 0, 0] = np.nan
     g.setImage(frames[0])
@@ -406,3 +406,43 @@ def test_work_splits_agree(seq384, threads, occ):
     ref.update(frames[1]); g.update(frames[1])
     assert np.array_equal(ref.n_iters(), g.n_iters())
     assert np.abs(ref.getRegion() - g.getRegion()).max() <= 1e-8
+
+
+# ------------------------------------------------------------------------------------------------ non-chained warp
+@pytest.mark.parametrize("am,sm,ssm", [("ssd", "fclk", "homography"), ("ssd", "esm", "homography"), ("ssd", "iclk", "homography"),
+                                       ("ssd", "fclk", "affine"), ("ssd", "esm", "affine"), ("ssd", "iclk", "affine"),
+                                       ("ncc", "esm", "affine"), ("ncc", "fclk", "homography"), ("mi", "iclk", "homography")])
+def test_non_chained_warp_path(seq384, am, sm, ssm):
+    """{esm,fc,ic}_chained_warp = 0 (factory default of parameters.h:174,192): ssm.updateGradPts + utils::getWarpedImgGrad +
+    ssm.cmptInitPixJacobian.  The four extra samples per pixel are evaluated literally, so gradient and pixel Jacobian match
+    the reference's finite-difference computation bit for bit and the sums to summation order."""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=19)])
+    kw = {"hess_type": 0} if am == "mi" else {}
+    g = _gpu(am, ssm, sm, len(cs), chained_warp=0, **kw)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    g.setImage(frames[1])
+    pts, It, grad, jac = g.curr_stage()
+    g.update()
+    logs = g.iter_log()
+    for i, c in enumerate(cs):
+        o = _oracle(am, ssm, sm, grad_mode=0, chained_warp=0, **kw)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        ol = o.log()
+        assert len(ol) == len(logs[i])
+        if sm != "iclk":
+            o1 = _oracle(am, ssm, sm, grad_mode=0, chained_warp=0, max_iters=1, **kw)
+            o1.set_image(frames[0]); o1.initialize(c); o1.set_image(frames[1]); o1.update()
+            assert np.array_equal(It[i], o1.curr_pix_vals())
+            assert np.array_equal(grad[i], o1.curr_pix_grad())
+            assert np.array_equal(jac[i], o1.curr_pix_jacobian())
+        tol0 = {"ssd": FIRST_RTOL, "ncc": NCC_FIRST_RTOL, "mi": 1e-10}[am]
+        for k, (a, b) in enumerate(zip(logs[i], ol)):
+            # later passes start from states that differ by ~1e-10 px, which re-rolls the rounding noise of the finite
+            # differences themselves (~1e-5 of the gradient)
+            tol = tol0 if k == 0 else 1e-5
+            assert abs(a["f"] - b["f"]) <= tol * max(abs(b["f"]), 1.0)
+            assert _rel(a["jacobian"], b["jacobian"]) <= (tol * 10 if k == 0 else 1e-3)     # J -> 0 as the loop converges
+            assert _rel(a["hessian"], b["hessian"]) <= max(tol * 10, 1e-10)
+            assert np.abs(a["corners"] - b["corners"]).max() <= (1e-4 if am == "mi" else 1e-5)
