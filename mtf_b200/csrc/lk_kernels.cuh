@@ -32,6 +32,7 @@ struct DevBatch {
 	// parameters
 	int max_iters, hess_type, jac_type, leven_marq, nt_semantics;
 	int chained;                 // {esm,fc,ic}_chained_warp
+	int norm_init;               // hom_normalized_init
 	double epsilon, lm_delta_init, lm_delta_update, grad_eps;
 	double pix_mult, pix_add;    // am pix_norm_mult / pix_norm_add (1, 0 except MI)
 	double grad_mult;            // pix_mult / (2 grad_eps)  (imgUtils.cc:238)

@@ -301,9 +301,12 @@ template<int SSM, class MW> MTFB_HD PixGeom warp_template_point(const MW &W, dou
 	}
 	return g;
 }
-template<int SSM, class MD, class MW> MTFB_HD PixGeom pixel_geometry(const MD &dlt, const MW &W, double u, double v){
+// norm_init: hom_normalized_init = 1 (Homography.cc:57-62, shipped in Config/modules.cfg): the template points ARE the
+// normalised grid (init_pts_hm = (u, v, 1)) and the DLT warp is part of curr_warp instead
+template<int SSM, class MD, class MW> MTFB_HD PixGeom pixel_geometry(const MD &dlt, const MW &W, double u, double v, bool norm_init = false){
 	double hx, hy, hz, ix, iy;
-	template_point(dlt, u, v, hx, hy, hz, ix, iy);
+	if(norm_init){ hx = u; hy = v; hz = 1.0; ix = u; iy = v; }
+	else template_point(dlt, u, v, hx, hy, hz, ix, iy);
 	return warp_template_point<SSM>(W, hx, hy, hz, ix, iy);
 }
 

@@ -89,11 +89,12 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 	Mat3 dlt, W = mat3_identity();
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	if(b.norm_init) W = dlt;                                 // Homography.cc:57-62: curr_warp starts as the DLT warp
 	const double abcd[4] = { 1, 0, 0, 1 };
 	double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
 	// phase 1: template values (scaled to bin units, MI.cc:91-94), chained gradient, init_hist and the self joint histogram
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		Sample smp;
 		pixel_value_and_gradient<SSM, false>(b, W, g, smp);
 		const double val = b.pix_mult*smp.val + b.pix_add;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 #pragma unroll
 	for(int i = 0; i < NH; ++i) acc[i] = 0;
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		double D[S];
 		init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D);
 		const double v = I0[it.pix];
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		for(int e = 0; e < HB; ++e) s_priv[e * 32 + lane] = 0;
 		// ---- sweep 1: updatePixVals (MI.cc:166-192) + the histograms of updateSimilarity (MI.cc:346-370)
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
 			if(KEEP_IT) s_It[it.pix] = It;
 			const BinWeights bc = bin_weights(It, B), bi = bin_weights(I0[it.pix], B);
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 #pragma unroll
 		for(int i = 0; i < NA; ++i) acc[i] = 0;
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			const double It2 = KEEP_IT ? s_It[it.pix] : (b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add);
 			const BinWeights bc = bin_weights(It2, B), bi = bin_weights(I0[it.pix], B);
 			double df_t = 0, df_0 = 0;

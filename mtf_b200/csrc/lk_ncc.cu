@@ -53,13 +53,14 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 	Mat3 dlt, W = mat3_identity();
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	if(b.norm_init) W = dlt;                                 // Homography.cc:57-62: curr_warp starts as the DLT warp
 	const double abcd[4] = { 1, 0, 0, 1 };
 	double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
 	const int N = b.N;
 	// phase 1: template values and chained gradient, mean
 	double s1[1] = { 0 };
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		Sample smp;
 		pixel_value_and_gradient<SSM, true>(b, W, g, smp);
 		const double val = smp.val;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 #pragma unroll
 	for(int i = 0; i < L::NA; ++i) acc[i] = 0;
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		double D[S];
 		init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D);
 		const double I0cc = div_by(I0[it.pix] - I0_mean, c, rc);
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 		// ---- sweep 1: am.updatePixVals (ImageBase.cc:268-290) + the mean of NCC.cc:139
 		double s1[1] = { 0 };
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			const double It = sample_pixel(b.img, g.wx, g.wy);
 			s_It[it.pix] = It;
 			s1[0] += It;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 #pragma unroll
 		for(int i = 0; i < L::NA; ++i) acc[i] = 0;
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			const double Itcb = div_by(s_It[it.pix] - It_mean, bn, rb);                  // It_cntr_b (NCC.cc:213)
 			const double I0cc = div_by(I0[it.pix] - I0_mean, c, rc);                     // I0_cntr_c (NCC.cc:116)
 			if(L::CURR){

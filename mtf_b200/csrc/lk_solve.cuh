@@ -165,6 +165,18 @@ template<int SSM> __device__ __forceinline__ Mat3 set_corners(const DevBatch &b,
 	constexpr int S = StateSize<SSM>::value;
 	Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
 	Mat3 I = mat3_identity();
+	if(b.norm_init){
+		// Homography::setCorners with normalized_init (Homography.cc:57-62): the initial region is the normalised square,
+		// curr_warp = the DLT warp, curr_state = getStateFromWarp(curr_warp)
+		double st[S];
+		state_from_warp<SSM>(st, dlt);
+		if(lane < 9) b.warp[(size_t)p * 9 + lane] = dlt.m[lane];
+#pragma unroll
+		for(int s = 0; s < S; ++s) if(lane == s) b.state[(size_t)p*S + s] = st[s];
+		if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = b.norm_corners[lane]; }
+		if(lane < 9) b.dlt[(size_t)p * 9 + lane] = dlt.m[lane];
+		return dlt;
+	}
 	if(lane < 9){ b.dlt[(size_t)p * 9 + lane] = dlt.m[lane]; b.warp[(size_t)p * 9 + lane] = I.m[lane]; }
 	if(lane < S) b.state[(size_t)p*S + lane] = 0;
 	if(lane < 8){ b.corners[(size_t)p * 8 + lane] = c_in[lane]; b.init_corners[(size_t)p * 8 + lane] = c_in[lane]; }

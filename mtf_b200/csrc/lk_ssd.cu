@@ -42,13 +42,14 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 	Mat3 dlt, W = mat3_identity();
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	if(b.norm_init) W = dlt;                                 // Homography.cc:57-62: curr_warp starts as the DLT warp
 	const double abcd[4] = { 1, 0, 0, 1 };
 	double acc[L::NA];
 #pragma unroll
 	for(int i = 0; i < L::NA; ++i) acc[i] = 0;
 	double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
 	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		Sample smp;
 		pixel_value_and_gradient<SSM, true>(b, W, g, smp);
 		double J[S];
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 		for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
 			// streamed once per pass: cached in L2 only, L1 is left to the four image gathers per pixel
 			const double i0 = __ldcg(I0 + it.pix);
-			const PixGeom g = pixel_geometry<SSM>(dlt, Wm, b.xv[it.col], b.yv[it.row]);
+			const PixGeom g = pixel_geometry<SSM>(dlt, Wm, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			Sample smp;
 			if(need_grad){ pixel_value_and_gradient<SSM, true>(b, Wm, g, smp); }
 			else{ smp.val = sample_pixel(b.img, g.wx, g.wy); smp.gx = smp.gy = 0; smp.lit = 0; }
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(T) lk_stage_kernel(DevBatch b, StageTaps t){
 	if(SSM == SSM_AFF){ abcd[0] = (W.m[0] - 1) + 1; abcd[3] = (W.m[4] - 1) + 1; }
 	const size_t N = b.N;
 	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row]);
+		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		Sample smp;
 		pixel_value_and_gradient<SSM, false>(b, W, g, smp);
 		const double val = b.pix_mult*smp.val + b.pix_add, gx = smp.gx, gy = smp.gy;

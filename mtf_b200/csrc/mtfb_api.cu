@@ -143,8 +143,9 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(!combo_supported(p, &why))
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: (am %d, ssm %d, sm %d, hess %d, jac %d) is not implemented: %s",
 			p->am, p->ssm, p->sm, p->hess_type, p->jac_type, why);
-	if(p->hom_normalized_init)
-		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: hom_normalized_init = 1 is not implemented");
+	if(p->hom_normalized_init && p->ssm != MTFB_SSM_HOMOGRAPHY)
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: normalized_init is implemented for the homography only (the affine "
+			"variant goes through computeAffineNDLT, warpUtils.cc:345-390)");
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
 	// default work split, measured on B200 (profiles/README.md): one warp per patch once the batch alone fills the
 	// ~8 warps per SM the fp64 accumulators leave room for; more warps per patch (and a tighter register budget,
@@ -228,6 +229,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.leven_marq = p->leven_marq; b.nt_semantics = p->nt_semantics;
 		// the templated search methods have no chained_warp switch: always chained (ESM.cc:94-95, FCLK.cc:82-86, ICLK.cc:80-90)
 		b.chained = (p->chained_warp || !p->nt_semantics) ? 1 : 0;
+		b.norm_init = p->hom_normalized_init ? 1 : 0;
 		b.epsilon = p->epsilon; b.lm_delta_init = p->lm_delta_init; b.lm_delta_update = p->lm_delta_update;
 		b.grad_eps = p->grad_eps;
 		b.pix_mult = 1; b.pix_add = 0;

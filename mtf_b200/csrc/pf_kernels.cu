@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 			double hx = dlt.m[0] * u; hx = hx + dlt.m[1] * v; hx = hx + dlt.m[2] * 1.0;
 			double hy = dlt.m[3] * u; hy = hy + dlt.m[4] * v; hy = hy + dlt.m[5] * 1.0;
 			double hz = dlt.m[6] * u; hz = hz + dlt.m[7] * v; hz = hz + dlt.m[8] * 1.0;
+			if(b.norm_init){ hx = u; hy = v; hz = 1.0; }              // hom_normalized_init: init_pts_hm = (u, v, 1)
 			if(SSM == SSM_HOM){ s_gA[it.pix] = hx; s_gB[it.pix] = hy; s_gC[it.pix] = hz; }
 			else{ const double r = ieee_rcp(hz); s_gA[it.pix] = div_by(hx, hz, r); s_gB[it.pix] = div_by(hy, hz, r); }
 		}

@@ -44,6 +44,8 @@ def main():
                     "pixels_per_patch": res * res, "passes_per_frame": iters, "finite": bool(np.isfinite(tr.getRegion()).all())})
 
     lk("2: FCLK+SSD+Homography 1024 x 50x50", "ssd", "homography", "fclk", 1024, 50, 49.0, 30)
+    lk("2': same with hom_normalized_init=1 (Config/modules.cfg)", "ssd", "homography", "fclk", 1024, 50, 49.0, 30, hom_normalized_init=1)
+    lk("1': ESM+SSD+Homography 1024 x 50x50", "ssd", "homography", "esm", 1024, 50, 49.0, 30)
     lk("3: ESM+NCC+Affine 1024 cells 10x10", "ncc", "affine", "esm", 1024, 10, 10.0, 30)
     lk("3: ESM+NCC+Affine 1024 cells 25x25", "ncc", "affine", "esm", 1024, 25, 25.0, 30)
     lk("4: ICLK+MI+Homography 1024 x 100x100 (one GPU's share of 8192 on 8)", "mi", "homography", "iclk", 1024, 100, 99.0, 30,

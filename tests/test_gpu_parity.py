@@ -225,7 +225,7 @@ def test_error_contract(seq384):
         g.initialize(common.patches(2, 49.0, 384, 384))
     assert e.value.type == "LogicError"                       # no image yet
     with pytest.raises(api.MTFError) as e:
-        _gpu("ssd", "homography", "fclk", 2, hom_normalized_init=1)
+        _gpu("ssd", "affine", "fclk", 2, hom_normalized_init=1)
     assert e.value.type == "FunctonNotImplemented"
     bad = common.patches(2, 49.0, 384, 384); bad[0, 0, 0] = np.nan
     g.setImage(frames[0])
@@ -446,3 +446,37 @@ def test_non_chained_warp_path(seq384, am, sm, ssm):
             assert _rel(a["jacobian"], b["jacobian"]) <= (tol * 10 if k == 0 else 1e-3)     # J -> 0 as the loop converges
             assert _rel(a["hessian"], b["hessian"]) <= max(tol * 10, 1e-10)
             assert np.abs(a["corners"] - b["corners"]).max() <= (1e-4 if am == "mi" else 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ hom_normalized_init
+@pytest.mark.parametrize("am,sm", [("ssd", "fclk"), ("ssd", "esm"), ("ssd", "iclk"), ("ncc", "esm"), ("mi", "iclk")])
+def test_hom_normalized_init(seq384, am, sm):
+    """hom_normalized_init = 1 (shipped in Config/modules.cfg): the template points are the unit-square grid and the DLT
+    warp lives in curr_warp; the Hessian is then well conditioned and never rank-truncated"""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=23)])
+    kw = {"hess_type": 0} if am == "mi" else {}
+    g = _gpu(am, "homography", sm, len(cs), hom_normalized_init=1, **kw)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    ipts, I0, st0 = g.init_pts(), g.init_pix_vals(), g.state()
+    orcs = []
+    for i, c in enumerate(cs):
+        o = _oracle(am, "homography", sm, grad_mode=1, hom_normalized_init=1, **kw)
+        o.set_image(frames[0]); o.initialize(c)
+        assert np.array_equal(ipts[i], o.init_pts()) and np.array_equal(I0[i], o.init_pix_vals())
+        assert np.array_equal(st0[i], o.state())
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs = g.iter_log()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert len(ol) == len(logs[i])
+            for k, (a, b) in enumerate(zip(logs[i], ol)):
+                tol = 1e-6
+                assert abs(a["f"] - b["f"]) <= tol * max(abs(b["f"]), 1.0)
+                assert _rel(a["hessian"], b["hessian"]) <= tol
+                assert np.abs(a["corners"] - b["corners"]).max() <= (1e-4 if am == "mi" else 1e-6)
+    assert (g.patch_status() & 2 == 0).all() or am == "mi"
