@@ -169,7 +169,7 @@ def run_ours(args):
     frames, corners, order = workload(seed_offset=rank)
     P = P_PER_GPU
     prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=local_rank,
-                          threads_per_patch=args.threads, occupancy=args.occ)
+                          threads_per_patch=args.threads, occupancy=args.occ, precision=args.precision)
     tr = api.BatchTracker(prm)
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
@@ -262,17 +262,19 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64" if args.precision == "f64" else "f32 per pixel (exact sampling indices), f64 reduction + solve",
+        "data": "synthetic",
         "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
-                               % (P, ITERS, IMG, IMG),
-                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto(32)", "occupancy": args.occ if args.threads else "auto(0)",
+                               % (P, ITERS, IMG, IMG), "precision": args.precision,
+                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto", "occupancy": args.occ if args.threads else "auto",
                    "collective": "all_gather of P x 8 corners per frame" if world > 1 else "none"},
         "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_ncu_r1c_summary.txt (dram__bytes_read + write, one launch)",
-                     "kernel": "ssd_update_kernel<Homography,FCLK>", "kernel_ms_per_launch": kms / args.steps,
+                     "kernel": ("ssd_update_kernel" if args.precision == "f64" else "ssd_update_f32_kernel") + "<Homography,FCLK>",
+                     "kernel_ms_per_launch": kms / args.steps,
                      "alg_bytes_per_launch": ALG_BYTES_PER_ITER * P * ITERS, "peak_source": peak_src,
                      "note": "fp64-issue bound, not HBM bound: see DESIGN.md"},
         "clocks": clocks,
@@ -301,6 +303,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--threads", type=int, default=0, help="threads per patch (0 = library default)")
     ap.add_argument("--occ", type=int, default=0, help="occupancy knob of the update kernel (0, 1, 2)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="per-pixel arithmetic of the update kernel (include/mtf_b200.h MTFB_PRECISION_*)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -52,6 +52,14 @@ enum { MTFB_ESM_HESS_INITIAL_SELF = 0, MTFB_ESM_HESS_CURRENT_SELF = 1, MTFB_ESM_
 enum { MTFB_ESM_JAC_ORIGINAL = 0, MTFB_ESM_JAC_DIFF_OF_JACS = 1 };
 /* FCLKParams::HessType / ICLKParams::HessType (FCLKParams.h:8, ICLKParams.h:9) */
 enum { MTFB_LK_HESS_INITIAL_SELF = 0, MTFB_LK_HESS_CURRENT_SELF = 1, MTFB_LK_HESS_STD = 2 };
+/* arithmetic of the per-pixel part of the update kernel (mtfb_params::precision).
+ *   F64: every operation in fp64, in the reference's order: warped points, sampling indices, pixel values bit-identical
+ *        to the reference's Eigen path; Jacobian / Hessian to summation order.
+ *   F32: fp32 per-pixel arithmetic in patch-local coordinates with BIT-EXACT SAMPLING INDICES (pixels whose fp32
+ *        coordinate is within the fp32 error bound of a cell boundary are re-evaluated in fp64), fp64 reduction and
+ *        solve; Jacobian / Hessian / corners agree with F64 to fp32 tolerance.  SSD, chained
+ *        warp only. */
+enum { MTFB_PRECISION_F64 = 0, MTFB_PRECISION_F32 = 1 };
 /* per-patch status bits reported by mtfb_get_patch_status */
 enum { MTFB_PATCH_OK = 0, MTFB_PATCH_NAN = 1, MTFB_PATCH_SINGULAR = 2, MTFB_PATCH_OUT_OF_IMAGE = 4 };
 
@@ -86,6 +94,7 @@ typedef struct mtfb_params {
 	int threads_per_patch;       /* 0 = chosen from n_patches; otherwise 32, 64, 128 or 256        */
 	int occupancy;               /* register budget of the update kernel: 0 / 1 / 2 = about 8 / 12 /
 	                                16 resident warps per SM (tuning knob, results do not change)  */
+	int precision;               /* MTFB_PRECISION_F64 (default) or MTFB_PRECISION_F32                */
 } mtfb_params;
 
 /* one Gauss-Newton pass as the reference's record_event() trail would show it (NT/FCLK.cc:190-321);
@@ -166,6 +175,11 @@ mtfb_status mtfb_get_init_pix_vals(mtfb_ctx *ctx, double *out /* P x N */);
  * functions (one extra launch); any output may be NULL */
 mtfb_status mtfb_get_curr_stage(mtfb_ctx *ctx, double *pts /* P x N x 2 */, double *pix_vals /* P x N */,
 	double *pix_grad /* P x 2 x N */, double *pix_jac /* P x S x N */);
+/* precision = MTFB_PRECISION_F32 only: the same taps from the fp32 front end.  idx: the sampling indices (lx, ly)
+ * = ((int)x, (int)y) of imgUtils.h:99-100, -1 where the point is outside the image; fast_err: |fp32 - fp64| warped
+ * coordinate (px) for pixels that took the fp32 path, -1 for those re-evaluated in fp64.  Any output may be NULL. */
+mtfb_status mtfb_get_curr_stage_f32(mtfb_ctx *ctx, int *idx /* P x N x 2 */, float *pix_vals /* P x N */,
+	float *pix_grad /* P x 2 x N */, double *pix_jac /* P x S x N */, float *fast_err /* P x N */);
 /* device pointers of the result arrays, valid until destroy (corners P x 8, state P x S, n_iters P int):
  * what a multi-GPU host all-gathers without a host round trip */
 mtfb_status mtfb_device_results(mtfb_ctx *ctx, double **d_corners, double **d_state, int **d_n_iters);

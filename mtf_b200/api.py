@@ -19,6 +19,7 @@ SM = {"esm": 0, "fclk": 1, "iclk": 2, "pf": 3}
 ESM_HESS = {"initial_self": 0, "current_self": 1, "sum_of_self": 2, "original": 3, "sum_of_std": 4, "std": 5}
 ESM_JAC = {"original": 0, "diff_of_jacs": 1}
 LK_HESS = {"initial_self": 0, "current_self": 1, "std": 2}
+PRECISION = {"f64": 0, "f32": 1}
 
 STATUS_NAMES = {1: "InvalidArgument", 2: "FunctonNotImplemented", 3: "LogicError", 4: "InvalidTrackerState",
                 5: "CudaError", 6: "OutOfMemory"}
@@ -44,7 +45,7 @@ class Params(C.Structure):
                 ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
                 ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
                 ("likelihood_alpha", C.c_double), ("device", C.c_int), ("threads_per_patch", C.c_int),
-                ("occupancy", C.c_int)]
+                ("occupancy", C.c_int), ("precision", C.c_int)]
 
 
 class IterLog(C.Structure):
@@ -59,7 +60,8 @@ EXPORTS = [
     "mtfb_set_region", "mtfb_update", "mtfb_iterate_once", "mtfb_enable_iter_log", "mtfb_get_iter_log",
     "mtfb_pf_evaluate", "mtfb_pf_evaluate_device", "mtfb_get_corners", "mtfb_get_state", "mtfb_get_n_iters",
     "mtfb_get_similarity", "mtfb_get_patch_status", "mtfb_get_init_warp", "mtfb_get_init_pts",
-    "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_device_results", "mtfb_state_size",
+    "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_get_curr_stage_f32", "mtfb_device_results",
+    "mtfb_state_size",
 ]
 
 _lib = None
@@ -99,6 +101,7 @@ def load_library(path=LIB_PATH):
     L.mtfb_get_n_iters.argtypes = [vp, ip]
     L.mtfb_get_patch_status.argtypes = [vp, ip]
     L.mtfb_get_curr_stage.argtypes = [vp, dp, dp, dp, dp]
+    L.mtfb_get_curr_stage_f32.argtypes = [vp, vp, vp, vp, vp, vp]
     L.mtfb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mtfb_state_size.argtypes = [vp]
     for name in EXPORTS:
@@ -127,6 +130,8 @@ def set_params(p, **kw):
             v = (ESM_HESS if p.sm == SM["esm"] else LK_HESS)[v]
         elif k == "jac_type" and isinstance(v, str):
             v = ESM_JAC[v]
+        elif k == "precision" and isinstance(v, str):
+            v = PRECISION[v]
         if not hasattr(p, k):
             raise KeyError(k)
         setattr(p, k, v)
@@ -268,6 +273,18 @@ class BatchTracker:
         self._check(self._L.mtfb_get_curr_stage(self._h, _dp(a) if pts else null, _dp(b) if pix_vals else null,
                                                 _dp(g) if pix_grad else null, _dp(j) if pix_jac else null))
         return (a, b, None if g is None else g.transpose(0, 2, 1), None if j is None else j.transpose(0, 2, 1))
+
+    def curr_stage_f32(self):
+        """precision='f32' contexts: (idx P x N x 2 int32 = (lx, ly) or -1, It P x N f32, dIt_dx P x N x 2 f32,
+        dIt_dp P x N x S f64 in the reference's basis, fast_err P x N f32) at the current state."""
+        idx = np.empty((self.P, self.N, 2), dtype=np.int32)
+        val = np.empty((self.P, self.N), dtype=np.float32)
+        g = np.empty((self.P, 2, self.N), dtype=np.float32)
+        j = np.empty((self.P, self.S, self.N))
+        err = np.empty((self.P, self.N), dtype=np.float32)
+        self._check(self._L.mtfb_get_curr_stage_f32(self._h, idx.ctypes.data, val.ctypes.data, g.ctypes.data,
+                                                    j.ctypes.data, err.ctypes.data))
+        return idx, val, g.transpose(0, 2, 1), j.transpose(0, 2, 1), err
 
     def iterate_once(self):
         """one Gauss-Newton pass: (J P x S, H P x S x S, f P, dp P x S)"""

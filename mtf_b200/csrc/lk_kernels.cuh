@@ -12,6 +12,7 @@ struct DevBatch {
 	int P, N, resx, resy;
 	Image img;
 	const double *xv, *yv;       // normalised sampling grid (LinSpaced values), resx / resy entries
+	const float *xvf, *yvf;      // the same values rounded to fp32 (precision = MTFB_PRECISION_F32)
 	const double *norm_corners;  // 8: corners of the normalised grid (x0..x3, y0..y3)
 	double *dlt;                 // P x 9   DLT warp of setCorners, row-major
 	double *warp;                // P x 9   curr_warp, row-major
@@ -21,6 +22,7 @@ struct DevBatch {
 	double *I0;                  // P x N   template pixel values (am.I0)
 	double *G0;                  // P x 2 x N  template gradient: chained with the init warp, or (chained = 0) the
 	                             //            warped-image gradient of initialize() time
+	float *I0f, *G0f;            // fp32 copies of I0 / G0 (precision = MTFB_PRECISION_F32), else null
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
 	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
 	double *f;                   // P       similarity
@@ -39,6 +41,9 @@ struct DevBatch {
 };
 
 struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
+// taps of the fp32 front end (lk_ssd_f32.cu): idx P x N x 2 (lx, ly), fast_err P x N (|fp32 - fp64| warped coordinate
+// of the pixels that took the fp32 path, -1 for those that took the fp64 path)
+struct StageTapsF32 { int *idx; float *pix_vals, *pix_grad, *fast_err; double *pix_jac; };
 
 // launchers; threads = threads per patch (32 / 64 / 128 / 256), occ = register-budget knob of the SSD update kernel
 // lk_ssd.cu
@@ -46,6 +51,9 @@ cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const doubl
 cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
+// lk_ssd_f32.cu
+cudaError_t launch_update_ssd_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
+cudaError_t launch_stage_f32(int ssm, const DevBatch &b, const StageTapsF32 &t, cudaStream_t st);
 // lk_ncc.cu
 cudaError_t launch_init_ncc(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_update_ncc(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);

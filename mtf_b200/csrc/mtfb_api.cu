@@ -77,6 +77,7 @@ cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, co
 	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
 }
 cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st){
+	if(p.precision == MTFB_PRECISION_F32) return launch_update_ssd_f32(p.ssm, p.sm, threads, b, st);
 	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
 	return launch_update_ssd(p.ssm, p.sm, threads, occ, b, st);
@@ -94,6 +95,7 @@ struct mtfb_ctx {
 	double *d_grid;                             // xv | yv | norm_corners
 	double *d_patch;                            // all per-patch fp64 arrays in one allocation
 	double *d_mi_tab;                           // MI: P x 32 histogram tables
+	float *d_f32;                               // precision F32: xvf | yvf | I0f | G0f
 	int *d_ints;                                // n_iters | status
 	double *d_corners_in;                       // staging for initialize()/set_region()
 	mtfb_iter_log *d_log;
@@ -120,7 +122,7 @@ void mtfb_default_params(mtfb_params *p){
 	p->chained_warp = 1; p->leven_marq = 0; p->lm_delta_init = 0.01; p->lm_delta_update = 10;
 	p->nt_semantics = 1; p->grad_eps = 1e-8; p->hom_normalized_init = 0;
 	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1;
-	p->device = 0; p->threads_per_patch = 0; p->occupancy = 0;
+	p->device = 0; p->threads_per_patch = 0; p->occupancy = 0; p->precision = MTFB_PRECISION_F64;
 }
 
 mtfb_status mtfb_destroy(mtfb_ctx *c){
@@ -128,7 +130,7 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaSetDevice(c->prm.device);
 	if(c->own_stream) cudaStreamSynchronize(c->own_stream);
 	cudaFree(c->d_img_own); cudaFree(c->d_grid); cudaFree(c->d_patch); cudaFree(c->d_ints);
-	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch);
+	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32);
 	if(c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return MTFB_OK;
@@ -147,6 +149,16 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: normalized_init is implemented for the homography only (the affine "
 			"variant goes through computeAffineNDLT, warpUtils.cc:345-390)");
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
+	if(p->precision != MTFB_PRECISION_F64 && p->precision != MTFB_PRECISION_F32)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: precision must be MTFB_PRECISION_F64 or MTFB_PRECISION_F32");
+	if(p->precision == MTFB_PRECISION_F32){
+		const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
+		if(p->am != MTFB_AM_SSD || !gn || !(p->chained_warp || !p->nt_semantics))
+			return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 is implemented for SSD with ESM / FCLK / ICLK and the "
+				"chained warp; use MTFB_PRECISION_F64");
+		if(!(p->grad_eps < 1e-6)) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 needs grad_eps < 1e-6 (the fp32 "
+			"path returns the cell slope, the eps -> 0 limit of the reference's finite difference)");
+	}
 	// default work split, measured on B200 (profiles/README.md): one warp per patch once the batch alone fills the
 	// ~8 warps per SM the fp64 accumulators leave room for; more warps per patch (and a tighter register budget,
 	// so that the whole batch is resident in one wave) for smaller batches
@@ -155,6 +167,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(!threads && p->am == MTFB_AM_MI){
 		// MI keeps 18 KB of private histograms per warp (B = 8) next to the N current pixel values in shared memory
 		threads = p->n_patches >= 600 ? 32 : 64; occ = 0;
+	}
+	if(!threads && p->precision == MTFB_PRECISION_F32){
+		// ~7 CTAs per SM resident at <= 146 registers: two warps per patch fill the SM from 450 patches up
+		threads = p->n_patches >= 450 ? 64 : p->n_patches >= 200 ? 128 : 256;
 	}
 	if(!threads){
 		if(p->n_patches >= 900){ threads = 32; occ = 0; }
@@ -220,6 +236,18 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
+		b.xvf = b.yvf = nullptr; b.I0f = b.G0f = nullptr;
+		if(p->precision == MTFB_PRECISION_F32){
+			const size_t n_grid = (size_t)p->resx + p->resy, n_f32 = n_grid + 3 * (size_t)N*P;
+			if(cudaMalloc(&c->d_f32, n_f32*sizeof(float)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+			if(cudaMemset(c->d_f32, 0, n_f32*sizeof(float)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+			std::vector<float> gf(n_grid);
+			for(int i = 0; i < p->resx; ++i) gf[i] = (float)xv[i];
+			for(int i = 0; i < p->resy; ++i) gf[p->resx + i] = (float)yv[i];
+			if(cudaMemcpy(c->d_f32, gf.data(), n_grid*sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+			b.xvf = c->d_f32; b.yvf = c->d_f32 + p->resx;
+			b.I0f = c->d_f32 + n_grid; b.G0f = b.I0f + (size_t)N*P;
+		}
 		b.n_iters_prof = nullptr;
 #if MTFB_PROF
 		if(cudaMalloc(&b.n_iters_prof, 64 * sizeof(long long)) != cudaSuccess || cudaMemset(b.n_iters_prof, 0, 64 * sizeof(long long)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -464,6 +492,35 @@ mtfb_status mtfb_get_curr_stage(mtfb_ctx *c, double *pts, double *pix_vals, doub
 	if(pts) CUDA_TRY(cudaMemcpyAsync(pts, t.pts, n_pts*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if(pix_vals) CUDA_TRY(cudaMemcpyAsync(pix_vals, t.pix_vals, n_val*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if(pix_grad) CUDA_TRY(cudaMemcpyAsync(pix_grad, t.pix_grad, n_grad*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(pix_jac) CUDA_TRY(cudaMemcpyAsync(pix_jac, t.pix_jac, n_jac*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_get_curr_stage_f32(mtfb_ctx *c, int *idx, float *pix_vals, float *pix_grad, double *pix_jac, float *fast_err){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_get_curr_stage_f32: null context");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_get_curr_stage_f32: initialize has not been called");
+	if(c->prm.precision != MTFB_PRECISION_F32) return fail(MTFB_ERR_LOGIC, "mtfb_get_curr_stage_f32: context is not MTFB_PRECISION_F32");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t N = c->N, P = c->P, S = c->S;
+	// 8-byte slots for everything: simple and aligned
+	const size_t n_idx = idx ? N*P : 0, n_val = pix_vals ? (N*P + 1) / 2 : 0, n_grad = pix_grad ? N*P : 0, n_jac = pix_jac ? S*N*P : 0,
+		n_err = fast_err ? (N*P + 1) / 2 : 0;
+	mtfb_status st = ensure_scratch(c, (n_idx + n_val + n_grad + n_jac + n_err + 1)*sizeof(double));
+	if(st != MTFB_OK) return st;
+	StageTapsF32 t;
+	double *q = c->d_scratch;
+	t.idx = idx ? reinterpret_cast<int*>(q) : nullptr; q += n_idx;
+	t.pix_vals = pix_vals ? reinterpret_cast<float*>(q) : nullptr; q += n_val;
+	t.pix_grad = pix_grad ? reinterpret_cast<float*>(q) : nullptr; q += n_grad;
+	t.fast_err = fast_err ? reinterpret_cast<float*>(q) : nullptr; q += n_err;
+	t.pix_jac = pix_jac ? q : nullptr;
+	CUDA_TRY(launch_stage_f32(c->prm.ssm, c->b, t, c->stream));
+	++c->launches;
+	if(idx) CUDA_TRY(cudaMemcpyAsync(idx, t.idx, 2 * N*P*sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	if(pix_vals) CUDA_TRY(cudaMemcpyAsync(pix_vals, t.pix_vals, N*P*sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	if(pix_grad) CUDA_TRY(cudaMemcpyAsync(pix_grad, t.pix_grad, 2 * N*P*sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	if(fast_err) CUDA_TRY(cudaMemcpyAsync(fast_err, t.fast_err, N*P*sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	if(pix_jac) CUDA_TRY(cudaMemcpyAsync(pix_jac, t.pix_jac, n_jac*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return MTFB_OK;

@@ -1504,6 +1504,8 @@ const orc_iter_log *orc_log(const orc_tracker *t, int i){ return &t->log[i]; }
 void orc_get_corners(const orc_tracker *t, double *out8){ std::memcpy(out8, t->ssm.curr_corners, 8 * sizeof(double)); }
 void orc_get_state(const orc_tracker *t, double *outS){ for(int i = 0; i < t->S; ++i) outS[i] = t->ssm.curr_state[i]; }
 int orc_state_size(const orc_tracker *t){ return t->S; }
+// ssm.setState (ProjectiveBase.cc:41-49, Affine.cc:109-115): curr_warp = getWarpFromState, curr_pts = warp . init_pts_hm
+void orc_set_state(orc_tracker *t, const double *state){ t->ssm.setState(state); }
 void orc_get_pts(const orc_tracker *t, double *o){ std::memcpy(o, t->ssm.curr_pts.data(), 2 * (size_t)t->N*sizeof(double)); }
 void orc_get_init_pts(const orc_tracker *t, double *o){ std::memcpy(o, t->ssm.init_pts.data(), 2 * (size_t)t->N*sizeof(double)); }
 void orc_get_init_pix_vals(const orc_tracker *t, double *o){ std::memcpy(o, t->am.I0.data(), (size_t)t->N*sizeof(double)); }

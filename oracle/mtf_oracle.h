@@ -87,6 +87,8 @@ const orc_iter_log *orc_log(const orc_tracker *t, int i);
 void orc_get_corners(const orc_tracker *t, double *out8);
 void orc_get_state(const orc_tracker *t, double *outS);
 int orc_state_size(const orc_tracker *t);
+/* ssm.setState: warp the template points with the given state (stage tests at an arbitrary state) */
+void orc_set_state(orc_tracker *t, const double *state);
 void orc_get_pts(const orc_tracker *t, double *out2N);
 void orc_get_init_pts(const orc_tracker *t, double *out2N);
 void orc_get_init_pix_vals(const orc_tracker *t, double *outN);

@@ -68,6 +68,7 @@ def lib():
                  "orc_get_init_pix_jacobian", "orc_get_init_warp", "orc_get_stage_times"):
         getattr(L, name).argtypes = [C.c_void_p, dp]
     L.orc_pf_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp]
+    L.orc_set_state.argtypes = [C.c_void_p, dp]
     L.orc_pix_val.argtypes = [fp, C.c_int, C.c_int, C.c_double, C.c_double]; L.orc_pix_val.restype = C.c_double
     L.orc_get_pix_vals.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_get_img_grad.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
@@ -154,6 +155,12 @@ class OracleTracker:
 
     def state(self):
         return self._get("orc_get_state", self.S)
+
+    def set_state(self, state):
+        """ssm.setState: warp the template points with `state` (no appearance update)"""
+        s = np.ascontiguousarray(state, dtype=np.float64)
+        assert s.size == self.S
+        lib().orc_set_state(self.h, _dp(s))
 
     def pts(self):
         return self._get("orc_get_pts", 2 * self.N).reshape(self.N, 2)

@@ -1,0 +1,213 @@
+"""GPU: the fp32-arithmetic precision of the SSD kernels (mtfb_params.precision = MTFB_PRECISION_F32,
+mtf_b200/csrc/lk_ssd_f32.cu) against the CPU oracle, through the C-ABI.
+
+BASELINE.json north_star: "bit-exact warped sampling indices, Jacobian/Hessian and final corner coordinates within a
+stated fp32 tolerance".  The tolerances, stated once:
+  * sampling indices (lx, ly) = ((int)x, (int)y) of imgUtils.h:99-100 at the same state  -> bit-exact, every pixel
+  * pixel values  -> PIX_ATOL gray levels (fp32 bilinear weights: 2^-24 relative on a 0..255 value times the
+    local slope's amplification of the ~1e-5 px coordinate error)
+  * f, J^T r, J^T J of the first pass (identical state on both sides) -> F32_RTOL relative to the largest entry
+  * corners after a converged loop -> CORNER_ATOL_F32 px;  with the reference's epsilon = 1e-4 stopping rule the
+    last accepted step is itself ~1e-2 px, so there the bound is CORNER_ATOL_STOP and iteration counts may differ by one
+"""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+PIX_ATOL = 2e-3
+GRAD_ATOL = 2e-3           # gray levels per pixel
+F32_RTOL = 2e-5
+CORNER_ATOL_F32 = 2e-3     # px, fixed point of the loop (30 passes, epsilon = 0)
+CORNER_ATOL_STOP = 3e-2    # px, epsilon = 1e-4 stopping rule
+
+SMS = ["fclk", "esm", "iclk"]
+SSMS = ["homography", "affine"]
+
+
+def _gpu(ssm, sm, P, **kw):
+    from mtf_b200 import api
+    p = api.make_params("ssd", ssm, sm, n_patches=P, precision="f32", **kw)
+    return api.BatchTracker(p)
+
+
+def _oracle(ssm, sm, **kw):
+    return O.OracleTracker(O.make_params("ssd", ssm, sm, **kw))
+
+
+def _ref_indices(pts, h, w):
+    """(lx, ly) of getPixVal (imgUtils.h:91-113): (int)x, (int)y for points inside [0, w) x [0, h); -1 outside"""
+    inb = (pts[:, 0] >= 0) & (pts[:, 0] < w) & (pts[:, 1] >= 0) & (pts[:, 1] < h)
+    idx = np.where(inb[:, None], np.floor(pts), -1).astype(np.int32)
+    return idx
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _mixed_patches(h, w):
+    # integer-aligned (49.0: every template point on a pixel corner -> the straddling finite difference), generic
+    # sub-pixel, general quadrilaterals, and two boxes hanging over the image border
+    cs = [common.patches(4, 49.0, h, w), common.patches(4, 52.3, h, w, seed=3), common.quad_patches(4, h, w)]
+    edge = np.array([[[-12.3, 37.7, 37.7, -12.3], [100.2, 100.2, 150.2, 150.2]],
+                     [[w - 30.5, w + 19.5, w + 19.5, w - 30.5], [h - 28.0, h - 28.0, h + 22.0, h + 22.0]]])
+    return np.concatenate(cs + [edge])
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+def test_f32_sampling_indices_bit_exact(seq384, ssm):
+    frames, _ = seq384
+    h, w = frames[0].shape
+    cs = _mixed_patches(h, w)
+    g = _gpu(ssm, "fclk", len(cs), max_iters=4)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle(ssm, "fclk", grad_mode=1)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    worst_err, n_slow, n_all = 0.0, 0, 0
+    for step in range(4):
+        if step:
+            g.update(frames[step])
+        idx, val, grad, jac, ferr = g.curr_stage_f32()
+        st = g.state()
+        for i, o in enumerate(orcs):
+            o.set_image(frames[step])
+            o.set_state(st[i])
+            ref = _ref_indices(o.pts(), h, w)
+            assert np.array_equal(idx[i], ref), (ssm, step, i, np.argwhere(idx[i] != ref)[:4])
+            # values at the same points
+            rv = O.pix_vals(frames[step], o.pts())
+            assert np.abs(val[i] - rv).max() <= PIX_ATOL
+        fast = ferr >= 0
+        worst_err = max(worst_err, float(ferr[fast].max()) if fast.any() else 0.0)
+        if step:
+            n_slow += int((~fast[:12]).sum()); n_all += fast[:12].size
+    # the fp32 coordinates of the pixels that stayed on the fp32 path: far inside the guard band
+    assert worst_err < 2e-5, worst_err
+    # generic states: < 2 % of the pixels of the interior patches are re-evaluated in fp64
+    assert n_slow < 0.02 * n_all, (n_slow, n_all)
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+def test_f32_integer_aligned_start_takes_fp64_path(seq384, ssm):
+    """axis-aligned 49 px box at initialize(): every template point sits on a pixel corner, where the reference's
+    central difference averages the two one-sided slopes; the fp32 kernel must hand all of them to the fp64 path"""
+    frames, _ = seq384
+    cs = common.patches(3, 49.0, 384, 384)
+    g = _gpu(ssm, "fclk", len(cs))
+    g.initialize(cs, frames[0])
+    idx, val, grad, jac, ferr = g.curr_stage_f32()
+    assert (ferr < 0).all()
+    for i, c in enumerate(cs):
+        o = _oracle(ssm, "esm", grad_mode=1)        # ESM keeps init_pix_jacobian
+        o.set_image(frames[0]); o.initialize(c)
+        assert np.array_equal(val[i], o.init_pix_vals().astype(np.float32))
+        J = o.init_pix_jacobian()
+        assert (np.abs(jac[i] - J) <= 1e-5 * np.abs(J).max(axis=0)).all()
+
+
+@pytest.mark.parametrize("sm", SMS)
+@pytest.mark.parametrize("ssm", SSMS)
+@pytest.mark.parametrize("norm_init", [0, 1])
+def test_f32_first_pass_sums(seq384, sm, ssm, norm_init):
+    """f, J^T r, J^T J, state update of the first pass (identical state on both sides)"""
+    if norm_init and ssm != "homography":
+        pytest.skip("normalized_init is a Homography parameter")
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(4, 52.3, 384, 384, seed=5), common.quad_patches(4, 384, 384, seed=11)])
+    g = _gpu(ssm, sm, len(cs), hom_normalized_init=norm_init)
+    g.enable_iter_log(2)
+    g.initialize(cs, frames[0])
+    g.update(frames[1])
+    logs = g.iter_log()
+    for i, c in enumerate(cs):
+        o = _oracle(ssm, sm, grad_mode=1, hom_normalized_init=norm_init)
+        o.set_image(frames[0]); o.initialize(c)
+        o.set_image(frames[1]); o.update()
+        a, b = logs[i][0], o.log()[0]
+        assert abs(a["f"] - b["f"]) <= F32_RTOL * abs(b["f"])
+        assert _rel(a["hessian"], b["hessian"]) <= F32_RTOL
+        assert _rel(a["jacobian"], b["jacobian"]) <= 10 * F32_RTOL
+        if norm_init:
+            # well-conditioned basis: the solve amplifies the 1e-6 input differences by cond(H) ~ 1e3
+            assert _rel(a["state_update"], b["state_update"]) <= 1e-2
+        assert np.abs(a["corners"] - b["corners"]).max() <= 5e-3
+
+
+@pytest.mark.parametrize("sm", SMS)
+@pytest.mark.parametrize("ssm", SSMS)
+def test_f32_converged_corners(seq384, sm, ssm):
+    """30 passes per frame on both sides (epsilon = 0): the fixed points agree to CORNER_ATOL_F32"""
+    frames, warps = seq384
+    cs = np.concatenate([common.patches(6, 52.3, 384, 384, seed=5), common.quad_patches(6, 384, 384, seed=11)])
+    norm = 1 if ssm == "homography" else 0
+    g = _gpu(ssm, sm, len(cs), epsilon=0.0, hom_normalized_init=norm)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle(ssm, sm, grad_mode=1, epsilon=0.0, hom_normalized_init=norm)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:4]:
+        g.update(fr)
+        got = g.getRegion()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            assert np.abs(got[i] - o.corners()).max() <= CORNER_ATOL_F32, (sm, ssm, i, np.abs(got[i] - o.corners()).max())
+    assert (g.patch_status() & 1 == 0).all()
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+def test_f32_reference_stopping_rule(seq384, ssm):
+    """shipped configuration (epsilon = 1e-4, hom_normalized_init = 0) against the reference's finite-difference mode"""
+    frames, _ = seq384
+    cs = common.patches(12, 52.3, 384, 384, seed=9)
+    g = _gpu(ssm, "fclk", len(cs))
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle(ssm, "fclk", grad_mode=0)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:4]:
+        g.update(fr)
+        got, n_it = g.getRegion(), g.n_iters()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            assert np.abs(got[i] - o.corners()).max() <= CORNER_ATOL_STOP
+            assert abs(int(n_it[i]) - o.n_iters) <= 2
+
+
+def test_f32_matches_f64_kernel_large_batch(seq384):
+    """1024-patch batch, the bench configuration in small: fp32 and fp64 kernels side by side, and the work split
+    (threads per patch) does not change the fp32 result beyond summation order"""
+    from mtf_b200 import api, synth
+    frames, _ = seq384
+    cs = synth.make_patches(256, 30.7, 384, 384)
+    ref = api.BatchTracker(api.make_params("ssd", "homography", "fclk", n_patches=len(cs), epsilon=0.0, resx=30, resy=30,
+                                           hom_normalized_init=1))
+    ref.initialize(cs, frames[0]); ref.update(frames[1])
+    want = ref.getRegion()
+    outs = []
+    for threads in (32, 64, 128):
+        g = _gpu("homography", "fclk", len(cs), epsilon=0.0, resx=30, resy=30, threads_per_patch=threads,
+                 hom_normalized_init=1)
+        g.initialize(cs, frames[0]); g.update(frames[1])
+        outs.append(g.getRegion())
+        assert np.abs(outs[-1] - want).max() <= CORNER_ATOL_F32
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-4 and np.abs(outs[1] - outs[2]).max() <= 1e-4
+
+
+def test_f32_unsupported_combinations():
+    from mtf_b200 import api
+    for kw in (dict(am="ncc"), dict(am="mi", sm="iclk"), dict(chained_warp=0), dict(sm="pf")):
+        am = kw.pop("am", "ssd"); sm = kw.pop("sm", "fclk")
+        with pytest.raises(api.MTFError) as e:
+            api.BatchTracker(api.make_params(am, "homography", sm, n_patches=2, precision="f32", **kw))
+        assert e.value.type == "FunctonNotImplemented"
