@@ -174,7 +174,15 @@ def run_ours(args):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     tr.set_stream(stream.cuda_stream)
-    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+    if args.pitch_pad:
+        # experiment: device frames with a row pitch of IMG + pad floats (L1 set-conflict study, profiles/README.md)
+        d_frames = []
+        for f in frames:
+            buf = torch.empty((IMG, IMG + args.pitch_pad), dtype=torch.float32, device=dev)
+            buf[:, :IMG].copy_(torch.from_numpy(f))
+            d_frames.append(buf[:, :IMG])
+    else:
+        d_frames = [torch.from_numpy(f).to(dev) for f in frames]
     pinned = [torch.from_numpy(f).pin_memory() for f in frames]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     gathered = torch.empty((world, P, 8), dtype=torch.float64, device=dev) if world > 1 else None
@@ -305,6 +313,7 @@ def main():
     ap.add_argument("--occ", type=int, default=0, help="occupancy knob of the update kernel (0, 1, 2)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
                     help="per-pixel arithmetic of the update kernel (include/mtf_b200.h MTFB_PRECISION_*)")
+    ap.add_argument("--pitch-pad", type=int, default=0, help="experiment: extra floats per device frame row")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

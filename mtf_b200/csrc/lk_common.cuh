@@ -45,6 +45,28 @@ template<int CNT, int T> __device__ __forceinline__ void block_reduce(double (&a
 	__syncthreads();
 }
 
+// the same for fp32 per-thread sums: the butterfly runs in fp32 (half the shuffles, fp32 adds), the <= 3 entries a lane
+// is left with are widened to fp64 for the sum across warps
+template<int CNT, int T> __device__ __forceinline__ void block_reduce_f32(float (&acc)[CNT], double *s_part /* [T/32][CNT] */,
+	double *s_sum){
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int idx[3];
+	warp_reduce_scatter<CNT>(acc, lane, idx);
+	double *dst = (T == 32) ? s_sum : s_part + warp*CNT;
+	if(idx[0] >= 0) dst[idx[0]] = (double)acc[0];
+	if(CNT > 1 && idx[1] >= 0) dst[idx[1]] = (double)acc[CNT > 1 ? 1 : 0];
+	if(CNT > 64 && idx[2] >= 0) dst[idx[2]] = (double)acc[CNT > 2 ? 2 : 0];
+	if(T == 32){ __syncwarp(); return; }
+	__syncthreads();
+	for(int e = threadIdx.x; e < CNT; e += T){
+		double s = s_part[e];
+#pragma unroll
+		for(int w = 1; w < T / 32; ++w) s += s_part[w*CNT + e];
+		s_sum[e] = s;
+	}
+	__syncthreads();
+}
+
 // resident CTAs per SM requested from the compiler: OCC 0 / 1 / 2 = about 8 / 12 / 16 warps per SM
 // (<= 255 / 168 / 128 registers per thread)
 __host__ __device__ constexpr int min_blocks(int T, int OCC){
@@ -118,6 +140,7 @@ template<int SSM, class MW> __device__ __forceinline__ void pixel_jacobian_row(c
 
 struct PixIter {
 	int pix, row, col, dcol, drow, resx;
+	__device__ __forceinline__ PixIter(){}
 	__device__ __forceinline__ PixIter(int tid, int step, int _resx) : pix(tid), row(tid / _resx), col(tid % _resx),
 		dcol(step % _resx), drow(step / _resx), resx(_resx){}
 	__device__ __forceinline__ void next(int step){

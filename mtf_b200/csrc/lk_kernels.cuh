@@ -12,7 +12,7 @@ struct DevBatch {
 	int P, N, resx, resy;
 	Image img;
 	const double *xv, *yv;       // normalised sampling grid (LinSpaced values), resx / resy entries
-	const float *xvf, *yvf;      // the same values rounded to fp32 (precision = MTFB_PRECISION_F32)
+	float gx_lo, gx_step, gy_lo, gy_step;   // the same grid in fp32 as low + i * step (precision = MTFB_PRECISION_F32)
 	const double *norm_corners;  // 8: corners of the normalised grid (x0..x3, y0..y3)
 	double *dlt;                 // P x 9   DLT warp of setCorners, row-major
 	double *warp;                // P x 9   curr_warp, row-major
@@ -23,6 +23,7 @@ struct DevBatch {
 	double *G0;                  // P x 2 x N  template gradient: chained with the init warp, or (chained = 0) the
 	                             //            warped-image gradient of initialize() time
 	float *I0f, *G0f;            // fp32 copies of I0 / G0 (precision = MTFB_PRECISION_F32), else null
+	int I0f_stride;              // elements per patch in I0f (N rounded up to 4: 16-byte aligned rows for the bulk copy)
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
 	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
 	double *f;                   // P       similarity

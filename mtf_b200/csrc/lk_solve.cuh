@@ -28,10 +28,12 @@ template<int SM> __device__ __forceinline__ int hessian_select(int hess_type){
 // f: similarity of this pass.  s_J[S]: df_dp as the search method uses it (ESM's 0.5 already applied).
 // s_Hc[S*S]: column-major Hessian of this pass (ignored when hsel == 1).
 // Writes s_W, s_corners, the log; returns CTRL_*.  All 32 lanes of warp 0 must call it.
-template<int SSM, int SM>
+// PRESOLVED: the caller has solved for the state update already (s_dp[S]; lk_ssd_f32.cu solves in its own basis);
+// only valid without Levenberg-Marquardt.  s_J / s_Hc are then used for the log alone (may be null without a log).
+template<int SSM, int SM, bool PRESOLVED = false>
 __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, int iter_id, int n_passes, double f,
 	const double *s_J, const double *s_Hc, double *s_W, double *s_corners, const double *s_init_corners,
-	LMState &lm, int &patch_status){
+	LMState &lm, int &patch_status, const double *s_dp = nullptr){
 	constexpr int S = StateSize<SSM>::value;
 #if MTFB_PROF
 	const long long pt0 = clock64();
@@ -65,7 +67,18 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 		}
 		if(!rejected) lm.prev_similarity = f;
 	}
-	if(!rejected){
+	if(PRESOLVED){
+		x = lane < S ? s_dp[lane] : 0.0;
+#pragma unroll
+		for(int s = 0; s < S; ++s) dp[s] = s_dp[s];
+		if(SM == SM_ICLK){
+			double inv[S];
+			invert_state<SSM>(inv, dp);                          // NT/ICLK.cc:270-271
+			Wn = compose_update<SSM>(W, inv);
+		} else{
+			Wn = compose_update<SSM>(W, dp);
+		}
+	} else if(!rejected){
 		lm.state_reset = false;
 		WarpColPivQR<S, S> qr;
 		const int hsel = hessian_select<SM>(b.hess_type);

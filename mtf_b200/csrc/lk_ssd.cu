@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 		G0[b.N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
 		if(b.I0f){
 			// fp32 copies for the fp32-arithmetic update kernel (lk_ssd_f32.cu)
-			b.I0f[(size_t)p*b.N + it.pix] = (float)smp.val;
+			b.I0f[(size_t)p*b.I0f_stride + it.pix] = (float)smp.val;
 			b.G0f[(size_t)p * 2 * b.N + it.pix] = (float)G0[it.pix];
 			b.G0f[(size_t)p * 2 * b.N + b.N + it.pix] = (float)G0[b.N + it.pix];
 		}

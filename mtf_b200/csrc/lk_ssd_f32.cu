@@ -52,6 +52,14 @@ __device__ __forceinline__ float rcp_approx(float x){
 	return r;
 }
 
+// 1 / d in fp64 from the fp32 reciprocal and two Newton steps (d > 0, normal range)
+__device__ __forceinline__ double rcp_newton(double d){
+	double r = (double)rcp_approx((float)d);
+	r = fma(fma(-d, r, 1.0), r, r);
+	r = fma(fma(-d, r, 1.0), r, r);
+	return r;
+}
+
 // Centre and scale of the template points, from the corners of the initial region: x0, y0 = mean corner, s = the
 // largest |corner - centre| coordinate.  Any choice works (the basis map is exact algebra); this one puts the
 // template points into [-1, 1]^2.  hom_normalized_init: the template points are the unit grid itself.
@@ -96,84 +104,145 @@ template<int SSM> __device__ __forceinline__ void make_basis_map(double x0, doub
 #undef TT
 }
 
-// Per-pass constants, by one thread, in fp64 (about 80 operations per pass and patch).
+// Per-pass constants, by the 32 lanes of warp 0, in fp64 (lane i < 9 owns entry i of the 3 x 3 product).
 //
 // Error bound behind delta (Homography; u, v in [-1/2, 1/2]).  wxl = num / den with num = c0 u + c1 v + c2 evaluated as
-// two fp32 fmaf's on coefficients and grid values rounded to fp32: every term carries <= 2 roundings of 2^-24 and each
-// fmaf one more on its partial sum, so |err(num)| <= 4 . 2^-24 . A with A = |c0|/2 + |c1|/2 + |c2|, and likewise
-// |err(den)| <= 4 . 2^-24 . B; MUFU.RCP (1 ulp) and the final product add 2 . 2^-24 relative.  With Dmin <= |den|,
-// E = A / Dmin >= |wxl| and rho = B / Dmin >= 1:   |err(wxl)| <= 2^-24 . E . (6 + 4 rho)   (= 6e-7 E at rho = 1).
-// delta = 2.5 x that bound + 2e-6 px (tests/test_gpu_parity.py measures the actual error through the tap).
-// Affine: wxl = c0 xl + c1 yl + c2 with |xl|, |yl| <= 1 known to 10 . 2^-24 (their own quotient): E = |c0| + |c1| + |c2|,
-// |err| <= (10 + 4) . 2^-24 . E: the same formula with rho = 2.
-template<int SSM> __device__ __forceinline__ void pass_constants(const DevBatch &b, const double *W, const double *dlt, double x0, double y0,
-	double s, float *cf, int *ci){
+// two fp32 fmaf's on coefficients rounded to fp32 (2^-24 relative) and grid values u = fmaf(i, step, low) that differ
+// from the fp64 LinSpaced values by <= 1.5 . 2^-24 absolute (= 3 . 2^-24 relative to |u|max = 1/2): every term carries
+// <= 4 roundings of 2^-24 and each fmaf one more on its partial sum, so |err(num)| <= 6 . 2^-24 . A with
+// A = |c0|/2 + |c1|/2 + |c2|, and likewise |err(den)| <= 6 . 2^-24 . B; MUFU.RCP (1 ulp) and the final product add
+// 2 . 2^-24 relative, the (wxl - 1/2) of the floor another 2^-24.  With Dmin <= |den|, E = A / Dmin >= |wxl| and
+// rho = B / Dmin >= 1:      |err(wxl)| <= 2^-24 . E . (9 + 6 rho)          (= 9e-7 E at rho = 1).
+// delta = 2.5 x that bound + 2e-6 px (tests/test_gpu_f32.py measures the actual error through the tap).
+// Affine: wxl = c0 xl + c1 yl + c2 with |xl|, |yl| <= 1 known to 14 . 2^-24 (their own sums and quotient):
+// E = |c0| + |c1| + |c2|, |err| <= (14 + 4) . 2^-24 . E: covered by the same formula with rho = 2.
+template<int SSM> __device__ __forceinline__ void pass_constants(const DevBatch &b, int lane, const double *W, const double *dlt,
+	double x0, double y0, double s, float *cf, int *ci){
 	double E, rho = 2;
 	int X0 = 0, Y0 = 0;
 	bool sane = true;
+	double m[9];                                                 // the centred rows, uniform across the warp
 	if(SSM == SSM_HOM){
-		double M[9];
-		if(b.norm_init){
-#pragma unroll
-			for(int i = 0; i < 9; ++i) M[i] = W[i];
-		} else{
-#pragma unroll
-			for(int r = 0; r < 3; ++r)
-#pragma unroll
-			for(int c = 0; c < 3; ++c) M[3 * r + c] = W[3 * r] * dlt[c] + W[3 * r + 1] * dlt[3 + c] + W[3 * r + 2] * dlt[6 + c];
+		double Mi = 0;
+		{
+			const int i = lane < 9 ? lane : 0, r = i / 3, c = i % 3;
+			Mi = b.norm_init ? W[i] : (W[3 * r] * dlt[c] + W[3 * r + 1] * dlt[3 + c] + W[3 * r + 2] * dlt[6 + c]);
 		}
-		const double cx = M[2] / M[8], cy = M[5] / M[8];
-		sane = (fabs(cx) < 1e8) && (fabs(cy) < 1e8);
+		const double m2 = __shfl_sync(FULL_MASK, Mi, 2), m5 = __shfl_sync(FULL_MASK, Mi, 5), m8 = __shfl_sync(FULL_MASK, Mi, 8);
+		const bool m8_ok = (m8 > 1e-30) && (m8 < 1e30);
+		const double r8 = rcp_newton(m8_ok ? m8 : 1.0);             // relative error ~1e-16: only picks the integer origin
+		const double cx = m2 * r8, cy = m5 * r8;
+		sane = m8_ok && (fabs(cx) < 2e6) && (fabs(cy) < 2e6);      // the magic-number floor needs |coordinates| < 2^22
 		if(sane){ X0 = (int)floor(cx); Y0 = (int)floor(cy); }
+		const double mz = __shfl_sync(FULL_MASK, Mi, 6 + lane % 3);
+		if(lane < 3) Mi -= X0*mz; else if(lane < 6) Mi -= Y0*mz;
 #pragma unroll
-		for(int c = 0; c < 3; ++c){ M[c] -= X0*M[6 + c]; M[3 + c] -= Y0*M[6 + c]; }
-#pragma unroll
-		for(int i = 0; i < 9; ++i) cf[C_M + i] = (float)M[i];
-		cf[C_A + 0] = (float)(W[0] - W[6] * X0); cf[C_A + 1] = (float)(W[1] - W[7] * X0);
-		cf[C_A + 2] = (float)(W[3] - W[6] * Y0); cf[C_A + 3] = (float)(W[4] - W[7] * Y0);
-		cf[C_A + 4] = (float)W[6]; cf[C_A + 5] = (float)W[7];
-		const double Ax = 0.5*fabs(M[0]) + 0.5*fabs(M[1]) + fabs(M[2]), Ay = 0.5*fabs(M[3]) + 0.5*fabs(M[4]) + fabs(M[5]);
-		const double Dmin = fabs(M[8]) - 0.5*fabs(M[6]) - 0.5*fabs(M[7]);
-		E = fmax(Ax, Ay) / Dmin;
-		rho = (fabs(M[8]) + 0.5*fabs(M[6]) + 0.5*fabs(M[7])) / Dmin;
-		sane = sane && (Dmin > 0);
+		for(int i = 0; i < 9; ++i) m[i] = __shfl_sync(FULL_MASK, Mi, i);
+		if(lane < 9) cf[C_M + lane] = (float)Mi;
+		if(lane == 9) cf[C_A + 0] = (float)(W[0] - W[6] * X0);
+		if(lane == 10) cf[C_A + 1] = (float)(W[1] - W[7] * X0);
+		if(lane == 11) cf[C_A + 2] = (float)(W[3] - W[6] * Y0);
+		if(lane == 12) cf[C_A + 3] = (float)(W[4] - W[7] * Y0);
+		if(lane == 13) cf[C_A + 4] = (float)W[6];
+		if(lane == 14) cf[C_A + 5] = (float)W[7];
+		const double Ax = 0.5*fabs(m[0]) + 0.5*fabs(m[1]) + fabs(m[2]), Ay = 0.5*fabs(m[3]) + 0.5*fabs(m[4]) + fabs(m[5]);
+		const double Dmin = fabs(m[8]) - 0.5*fabs(m[6]) - 0.5*fabs(m[7]);
+		const bool dmin_ok = (Dmin > 1e-30) && (Dmin < 1e30);
+		const double rD = rcp_newton(dmin_ok ? Dmin : 1.0);
+		E = fmax(Ax, Ay) * rD;
+		rho = (fabs(m[8]) + 0.5*fabs(m[6]) + 0.5*fabs(m[7])) * rD;
+		sane = sane && dmin_ok;
 	} else{
 		const double cx = W[0] * x0 + W[1] * y0 + W[2], cy = W[3] * x0 + W[4] * y0 + W[5];
-		sane = (fabs(cx) < 1e8) && (fabs(cy) < 1e8);
+		sane = (fabs(cx) < 2e6) && (fabs(cy) < 2e6);
 		if(sane){ X0 = (int)floor(cx); Y0 = (int)floor(cy); }
 		const double c[6] = { W[0] * s, W[1] * s, cx - X0, W[3] * s, W[4] * s, cy - Y0 };
+		if(lane == 0){
 #pragma unroll
-		for(int i = 0; i < 6; ++i) cf[C_M + i] = (float)c[i];
-		cf[C_M + 6] = 0; cf[C_M + 7] = 0; cf[C_M + 8] = 1;
-		// Affine.cc:217-220 reads curr_state(2)+1, (3), (4), (5)+1 with curr_state = getStateFromWarp(curr_warp)
-		cf[C_A + 0] = (float)((W[0] - 1) + 1); cf[C_A + 1] = (float)W[1]; cf[C_A + 2] = (float)W[3]; cf[C_A + 3] = (float)((W[4] - 1) + 1);
-		cf[C_A + 4] = 0; cf[C_A + 5] = 0;
+			for(int i = 0; i < 6; ++i) cf[C_M + i] = (float)c[i];
+			cf[C_M + 6] = 0; cf[C_M + 7] = 0; cf[C_M + 8] = 1;
+			// Affine.cc:217-220 reads curr_state(2)+1, (3), (4), (5)+1 with curr_state = getStateFromWarp(curr_warp)
+			cf[C_A + 0] = (float)((W[0] - 1) + 1); cf[C_A + 1] = (float)W[1]; cf[C_A + 2] = (float)W[3]; cf[C_A + 3] = (float)((W[4] - 1) + 1);
+			cf[C_A + 4] = 0; cf[C_A + 5] = 0;
+		}
 		E = fmax(fabs(c[0]) + fabs(c[1]) + fabs(c[2]), fabs(c[3]) + fabs(c[4]) + fabs(c[5]));
 	}
-	double delta = 2.5 * 5.9604644775390625e-8 * (6 + 4 * rho) * E + 2e-6;
+	double delta = 2.5 * 5.9604644775390625e-8 * (9 + 6 * rho) * E + 2e-6;
 	if(!sane || !(delta < 0.25)) delta = 2.0;                    // every pixel takes the fp64 path
-	cf[C_DELTA] = (float)delta;
-	// fast path only if all four neighbours are inside the image: 0 <= lx, lx + 1 <= w - 1 (same for y)
-	cf[C_LOX] = (float)(-(double)X0); cf[C_HIX] = (float)((double)b.img.w - 2 - X0);
-	cf[C_LOY] = (float)(-(double)Y0); cf[C_HIY] = (float)((double)b.img.h - 2 - Y0);
-	ci[0] = X0; ci[1] = Y0;
+	if(lane == 0){
+		cf[C_DELTA] = (float)delta;
+		// fast path only if all four neighbours are inside the image: 0 <= lx, lx + 1 <= w - 1 (same for y)
+		cf[C_LOX] = (float)(-(double)X0); cf[C_HIX] = (float)((double)b.img.w - 2 - X0);
+		cf[C_LOY] = (float)(-(double)Y0); cf[C_HIY] = (float)((double)b.img.h - 2 - Y0);
+		ci[0] = X0; ci[1] = Y0;
+	}
 }
 
-// what the fp32 front end hands to the chain rule
-struct PixF { float xl, yl, wxl, wyl, invD, val, gx, gy; int lx, ly; float ferr; };
+// per-patch setup by warp 0: template frame, basis maps, centred DLT rows, first pass constants
+template<int SSM> __device__ __forceinline__ void patch_setup(const DevBatch &b, int lane, const double *s_W, const double *s_dlt,
+	const double *s_init_corners, double *s_loc, double *s_T, double *s_Tinv, float *s_dl, float *s_cf, int *s_ci){
+	double x0, y0, s;
+	template_frame<SSM>(b, s_init_corners, x0, y0, s);
+	const double rs = 1.0 / s;
+	if(lane == 0){
+		s_loc[0] = x0; s_loc[1] = y0; s_loc[2] = s;
+		make_basis_map<SSM>(x0, y0, s, s_T);
+	}
+	if(lane == 1) make_basis_map<SSM>(-x0*rs, -y0*rs, rs, s_Tinv);        // xl = -x0/s + x/s: the inverse map
+	if(lane == 2){
+		// centred / scaled DLT rows.  Third row constant (rectangles, parallelograms: an affine DLT up to rounding):
+		// the division is folded into the coefficients and the pixel loop skips it (s_dl[6] = s_dl[7] = 0 exactly)
+		// hom_normalized_init: the template points are the grid itself, (xl, yl) = (u, v) / s with s = 1/2
+		const bool unit = (SSM == SSM_HOM) && b.norm_init;
+		// (xl, yl) only parametrise the Jacobian basis, in fp32: a relative 1e-9 is invisible there
+		const bool aff = unit || (fabs(s_dlt[6]) <= 1e-9*fabs(s_dlt[8]) && fabs(s_dlt[7]) <= 1e-9*fabs(s_dlt[8]));
+		const double q = aff ? rs / s_dlt[8] : rs;
+#pragma unroll
+		for(int c = 0; c < 3; ++c){
+			s_dl[c] = unit ? (c == 0 ? 2.0f : 0.0f) : (float)((s_dlt[c] - x0*s_dlt[6 + c])*q);
+			s_dl[3 + c] = unit ? (c == 1 ? 2.0f : 0.0f) : (float)((s_dlt[3 + c] - y0*s_dlt[6 + c])*q);
+			s_dl[6 + c] = aff ? (c == 2 ? 1.0f : 0.0f) : (float)s_dlt[6 + c];
+		}
+	}
+	pass_constants<SSM>(b, lane, s_W, s_dlt, x0, y0, s, s_cf, s_ci);
+}
 
-// One pixel: template-local coordinates, warped point, sample + image gradient.
-//   dl[9]: rows of the centred / scaled DLT ((dlt0 - x0 dlt2) / s, (dlt1 - y0 dlt2) / s, dlt2) -- unused with normalized_init
-// WANT_TAP: also report the sampling indices of the fast path and its coordinate error (debug tap).
-template<int SSM, bool WANT_TAP> __device__ __forceinline__ void pixel_front(const DevBatch &b, const PassConst &k, const float (&dl)[9],
-	const double *s_dlt, const double *s_W, int row, int col, PixF &o){
-	const float u = __ldg(b.xvf + col), v = __ldg(b.yvf + row);
-	if(SSM == SSM_HOM && b.norm_init){ o.xl = u + u; o.yl = v + v; }             // s = 1/2
-	else{
-		const float hz = fmaf(dl[6], u, fmaf(dl[7], v, dl[8]));
-		const float rz = rcp_approx(hz);
-		o.xl = fmaf(dl[0], u, fmaf(dl[1], v, dl[2])) * rz;
-		o.yl = fmaf(dl[3], u, fmaf(dl[4], v, dl[5])) * rz;
+// pixel iterator with the grid position kept in fp32 (small integers: exact) -- no int -> float conversions
+struct PixIterF {
+	int pix; float rowf, colf, dcolf, drowf, resxf;
+	__device__ __forceinline__ PixIterF(){}
+	__device__ __forceinline__ PixIterF(int tid, int step, int resx) : pix(tid), rowf((float)(tid / resx)), colf((float)(tid % resx)),
+		dcolf((float)(step % resx)), drowf((float)(step / resx)), resxf((float)resx){}
+	__device__ __forceinline__ void next(int step){
+		pix += step; colf += dcolf; rowf += drowf;
+		if(colf >= resxf){ colf -= resxf; rowf += 1.0f; }
+	}
+};
+
+// what the fp32 front end hands to the chain rule
+struct PixF { float xl, yl, wxl, wyl, invD, val, gx, gy; int lx, ly; bool fast; };
+
+// floor(x) for |x| < 2^22 without the conversion pipe: RN(x - 1/2) through the 1.5 * 2^23 trick.  Ties and
+// near-ties (x within an ulp of an integer) may come out one off; the caller's guard band sends those to fp64.
+__device__ __forceinline__ void fast_floor(float x, float &fl, int &il){
+	const float magic = 12582912.0f;
+	const float t = (x - 0.5f) + magic;
+	fl = t - magic;
+	il = __float_as_int(t) - 0x4B400000;
+}
+
+// One pixel, straight-line fp32: template-local coordinates, warped point, and -- where the point is safely inside a
+// pixel cell (o.fast) -- the bilinear sample and its gradient.  Loads are issued for every lane (at a safe address
+// when !fast) so that two pixels can be interleaved without a branch in between.
+//   dl[9]: rows of the centred / scaled DLT (patch_setup) -- unused with normalized_init
+template<int SSM> __device__ __forceinline__ void front_fast(const DevBatch &b, const PassConst &k, const float (&dl)[9], bool dlt_affine,
+	float rowf, float colf, PixF &o){
+	const float u = fmaf(colf, b.gx_step, b.gx_lo), v = fmaf(rowf, b.gy_step, b.gy_lo);
+	o.xl = fmaf(dl[0], u, fmaf(dl[1], v, dl[2]));
+	o.yl = fmaf(dl[3], u, fmaf(dl[4], v, dl[5]));
+	if(!dlt_affine){
+		const float rz = rcp_approx(fmaf(dl[6], u, fmaf(dl[7], v, dl[8])));
+		o.xl *= rz; o.yl *= rz;
 	}
 	if(SSM == SSM_HOM){
 		const float D = fmaf(k.m[6], u, fmaf(k.m[7], v, k.m[8]));
@@ -185,40 +254,49 @@ template<int SSM, bool WANT_TAP> __device__ __forceinline__ void pixel_front(con
 		o.wxl = fmaf(k.m[0], o.xl, fmaf(k.m[1], o.yl, k.m[2]));
 		o.wyl = fmaf(k.m[3], o.xl, fmaf(k.m[4], o.yl, k.m[5]));
 	}
-	const float fx = floorf(o.wxl), fy = floorf(o.wyl);
-	const float dx = o.wxl - fx, dy = o.wyl - fy;                          // exact (Sterbenz)
+	float fx, fy; int ix, iy;
+	fast_floor(o.wxl, fx, ix);
+	fast_floor(o.wyl, fy, iy);
+	const float dx = o.wxl - fx, dy = o.wyl - fy;
 	const float hi = 1.0f - k.delta;
 	// written so that NaN fails
-	const bool fast = (dx >= k.delta) && (dx <= hi) && (dy >= k.delta) && (dy <= hi) &&
+	o.fast = (dx >= k.delta) && (dx <= hi) && (dy >= k.delta) && (dy <= hi) &&
 		(fx >= k.lox) && (fx <= k.hix) && (fy >= k.loy) && (fy <= k.hiy);
-	if(fast){
-		const int lx = k.X0 + (int)fx, ly = k.Y0 + (int)fy;
-		const float *r0 = b.img.data + (size_t)ly*b.img.pitch + lx;
-		const float p00 = __ldg(r0), p01 = __ldg(r0 + 1), p10 = __ldg(r0 + b.img.pitch), p11 = __ldg(r0 + b.img.pitch + 1);
-		const float t0 = p01 - p00, t1 = p11 - p10;
-		const float top = fmaf(dx, t0, p00), bot = fmaf(dx, t1, p10);
-		o.gy = bot - top;                                                    // (1 - dx)(p10 - p00) + dx (p11 - p01)
-		o.val = fmaf(dy, o.gy, top);
-		o.gx = fmaf(dy, t1 - t0, t0);                                        // (1 - dy)(p01 - p00) + dy (p11 - p10)
-		if(WANT_TAP){ o.lx = lx; o.ly = ly; }
-	}
-	if(!fast || WANT_TAP){
-		// reference-exact fp64: warped point, indices, value, gradient (incl. the literal finite difference where the
-		// two samples straddle a cell or leave the image)
-		const PixGeom g = pixel_geometry<SSM>(MemMat3{ s_dlt }, MemMat3{ s_W }, __ldg(b.xv + col), __ldg(b.yv + row), b.norm_init != 0);
-		if(WANT_TAP) o.ferr = fast ? (float)fmax(fabs((double)o.wxl - (g.wx - k.X0)), fabs((double)o.wyl - (g.wy - k.Y0))) : -1.0f;
-		if(!fast){
-			Sample smp = sample_fast<true>(b.img, g.wx, g.wy, b.grad_eps, 1.0);
-			if(smp.lit) sample_literal(b.img, g.wx, g.wy, b.grad_eps, b.grad_mult, smp);
-			o.val = (float)smp.val; o.gx = (float)smp.gx; o.gy = (float)smp.gy;
-			o.wxl = (float)(g.wx - k.X0); o.wyl = (float)(g.wy - k.Y0);
-			if(SSM == SSM_HOM) o.invD = (float)g.rD;
-			if(WANT_TAP){
-				const bool inb = !check_overflow(g.wx, g.wy, b.img.hd, b.img.wd);
-				o.lx = inb ? (int)g.wx : -1; o.ly = inb ? (int)g.wy : -1;
-			}
-		}
-	}
+	o.lx = k.X0 + ix; o.ly = k.Y0 + iy;
+	const int off = o.fast ? o.ly*b.img.pitch + o.lx : 0;
+	const float *r0 = b.img.data + off, *r1 = r0 + b.img.pitch;
+	const float p00 = __ldg(r0), p01 = __ldg(r0 + 1), p10 = __ldg(r1), p11 = __ldg(r1 + 1);
+	const float t0 = p01 - p00, t1 = p11 - p10;
+	const float top = fmaf(dx, t0, p00), bot = fmaf(dx, t1, p10);
+	o.gy = bot - top;                                                    // (1 - dx)(p10 - p00) + dx (p11 - p01)
+	o.val = fmaf(dy, o.gy, top);
+	o.gx = fmaf(dy, t1 - t0, t0);                                        // (1 - dy)(p01 - p00) + dy (p11 - p10)
+}
+// The same pixel through the reference-exact fp64 functions of lk_math.cuh: warped point, indices, value, gradient
+// (incl. the literal finite difference where the two samples straddle a cell or leave the image).
+// Inlined into the rarely taken branch: an out-of-line call was measured 12 % slower (the live accumulators are saved and
+// restored around it: profiles/README.md).
+struct ExactOut { float val, gx, gy, wxl, wyl, invD; int lx, ly; };
+struct ExactArgs { Image img; const double *xv, *yv; const double *s_dlt, *s_W; double grad_eps, grad_mult; int norm_init, X0, Y0; };
+template<int SSM> __device__ __forceinline__ ExactOut exact_pixel(ExactArgs a, int row, int col){
+	const PixGeom g = pixel_geometry<SSM>(MemMat3{ a.s_dlt }, MemMat3{ a.s_W }, __ldg(a.xv + col), __ldg(a.yv + row), a.norm_init != 0);
+	Sample smp = sample_fast<true>(a.img, g.wx, g.wy, a.grad_eps, 1.0);
+	if(smp.lit) sample_literal(a.img, g.wx, g.wy, a.grad_eps, a.grad_mult, smp);
+	ExactOut o;
+	o.val = (float)smp.val; o.gx = (float)smp.gx; o.gy = (float)smp.gy;
+	o.wxl = (float)(g.wx - a.X0); o.wyl = (float)(g.wy - a.Y0);
+	o.invD = (SSM == SSM_HOM) ? (float)g.rD : 1.0f;
+	const bool inb = !check_overflow(g.wx, g.wy, a.img.hd, a.img.wd);
+	o.lx = inb ? (int)g.wx : -1; o.ly = inb ? (int)g.wy : -1;
+	return o;
+}
+template<int SSM> __device__ __forceinline__ void front_exact(const DevBatch &b, const PassConst &k, const double *s_dlt, const double *s_W,
+	float rowf, float colf, PixF &o){
+	ExactArgs a;
+	a.img = b.img; a.xv = b.xv; a.yv = b.yv; a.s_dlt = s_dlt; a.s_W = s_W; a.grad_eps = b.grad_eps; a.grad_mult = b.grad_mult;
+	a.norm_init = b.norm_init; a.X0 = k.X0; a.Y0 = k.Y0;
+	const ExactOut e = exact_pixel<SSM>(a, (int)rowf, (int)colf);
+	o.val = e.val; o.gx = e.gx; o.gy = e.gy; o.wxl = e.wxl; o.wyl = e.wyl; o.invD = e.invD; o.lx = e.lx; o.ly = e.ly;
 }
 
 // chained gradient (Gx, Gy): the image gradient times d(warped point)/d(template point)
@@ -246,6 +324,154 @@ template<int SSM> __device__ __forceinline__ void local_row(float xl, float yl, 
 	}
 }
 
+// Per-thread sums in packed fp32x2 registers, updated with fma.rn.f32x2 (SASS FFMA2: two fused multiply-adds per
+// issue slot; ptxas folds the {a, a} operand into the instruction's scalar-broadcast form).  Pairing: with
+// P_i = (J_i, J_i+1) for even i,   P_i * J_i -> (H_ii, H_i,i+1),   P_i * J_j -> (H_ij, H_i+1,j) for j >= i + 2,
+// H_i+1,i+1 alone; (g_i, g_i+1) += w * P_i.  S = 8: 20 FFMA2 + 5 FFMA instead of 45 FFMA per pixel.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi){
+	unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi){
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b){
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+template<int S> struct PackedAcc {
+	typedef AccLayout<S> L;
+	static constexpr int NP = S*S / 4;                 // pairs of the Hessian: S/2 row pairs x (1 + (S - 2 - i) ...) summed = S^2/4
+	unsigned long long h2[NP], g2[S / 2];
+	float hd[S / 2], f;
+	__device__ __forceinline__ void clear(){
+#pragma unroll
+		for(int i = 0; i < NP; ++i) h2[i] = 0ull;
+#pragma unroll
+		for(int i = 0; i < S / 2; ++i){ g2[i] = 0ull; hd[i] = 0; }
+		f = 0;
+	}
+	__device__ __forceinline__ void add(float r, float wj, const float (&Jj)[S], const float (&Jt)[S], bool with_hessian){
+		f = fmaf(r, r, f);
+		const unsigned long long w2 = pack2(wj, wj);
+#pragma unroll
+		for(int i = 0; i < S; i += 2) ffma2(g2[i / 2], w2, pack2(Jj[i], Jj[i + 1]));
+		if(with_hessian){
+			int q = 0;
+#pragma unroll
+			for(int i = 0; i < S; i += 2){
+				const unsigned long long P = pack2(Jt[i], Jt[i + 1]);
+				ffma2(h2[q++], pack2(Jt[i], Jt[i]), P);
+				hd[i / 2] = fmaf(Jt[i + 1], Jt[i + 1], hd[i / 2]);
+#pragma unroll
+				for(int j = i + 2; j < S; ++j) ffma2(h2[q++], pack2(Jt[j], Jt[j]), P);
+			}
+		}
+	}
+	// -> AccLayout order: sum r^2 | J^T d | upper triangle of J^T J
+	__device__ __forceinline__ void unpack(float (&acc)[L::NA]) const{
+		acc[0] = f;
+#pragma unroll
+		for(int i = 0; i < S; i += 2) unpack2(g2[i / 2], acc[1 + i], acc[2 + i]);
+		int q = 0;
+#pragma unroll
+		for(int i = 0; i < S; i += 2){
+			unpack2(h2[q++], acc[1 + S + L::tri(i, i)], acc[1 + S + L::tri(i, i + 1)]);
+			acc[1 + S + L::tri(i + 1, i + 1)] = hd[i / 2];
+#pragma unroll
+			for(int j = i + 2; j < S; ++j) unpack2(h2[q++], acc[1 + S + L::tri(i, j)], acc[1 + S + L::tri(i + 1, j)]);
+		}
+	}
+};
+
+// what one pixel adds to the sums (same cases as lk_ssd_terms.cuh pixel_terms / accumulate_terms)
+template<int SSM, int SM> __device__ __forceinline__ void accumulate_pixel(const DevBatch &b, const PassConst &k, const PixF &px, float i0,
+	const float *__restrict__ G0, int pix, bool valid, bool need_grad, bool esm_mean, PackedAcc<StateSize<SSM>::value> &acc){
+	constexpr int S = StateSize<SSM>::value;
+	const float r = valid ? px.val - i0 : 0.0f;                     // I_diff (SSDBase.cc:78)
+	float Jt[S], Jj[S], wj;
+#pragma unroll
+	for(int s = 0; s < S; ++s) Jt[s] = 0;
+	if(need_grad){
+		float Gx, Gy;
+		chain_gradient<SSM>(k, px, Gx, Gy);
+		if(!valid){ Gx = 0; Gy = 0; }
+		local_row<SSM>(px.xl, px.yl, Gx, Gy, Jt);
+	}
+	if(SM == SM_ICLK){
+		wj = r;                                                     // df_dI0 = I_diff (SSDBase.cc:34)
+		local_row<SSM>(px.xl, px.yl, __ldcg(G0 + pix), __ldcg(G0 + b.N + pix), Jj);
+	} else if(SM == SM_ESM){
+		wj = -r;                                                    // df_dIt = -I_diff (SSDBase.cc:115-121)
+		float J0[S];
+		float g0x = __ldcg(G0 + pix), g0y = __ldcg(G0 + b.N + pix);
+		if(!valid){ g0x = 0; g0y = 0; }
+		local_row<SSM>(px.xl, px.yl, g0x, g0y, J0);
+		if(esm_mean){
+#pragma unroll
+			for(int s = 0; s < S; ++s) J0[s] = (J0[s] + Jt[s]) * 0.5f;     // NT/ESM.cc:246-248
+		}
+		if(b.jac_type == MTFB_ESM_JAC_ORIGINAL){
+#pragma unroll
+			for(int s = 0; s < S; ++s) Jj[s] = J0[s];
+		} else{
+#pragma unroll
+			for(int s = 0; s < S; ++s) Jj[s] = esm_mean ? (2.0f*J0[s]) : (J0[s] + Jt[s]);   // SSDBase.cc:186
+		}
+		if(b.hess_type == MTFB_ESM_HESS_ORIGINAL){
+#pragma unroll
+			for(int s = 0; s < S; ++s) Jt[s] = J0[s];
+		}
+	} else{
+		wj = -r;
+#pragma unroll
+		for(int s = 0; s < S; ++s) Jj[s] = Jt[s];
+	}
+	acc.add(r, wj, Jj, Jt, need_grad);
+}
+
+// Solve (J_loc^T J_loc) x = g for the state update in the LOCAL basis by Gauss-Jordan elimination without pivoting
+// (the matrix is symmetric positive definite and, in this basis, well conditioned), one column per lane, rhs on lane S;
+// then map to the reference's parameters: dp = T^-1 x.  Returns false (uniformly) if a pivot is not safely positive --
+// the caller then takes the reference's rank-revealing QR in the reference basis.
+// In exact arithmetic dp equals the reference's -H^-1 J^T (NT/FCLK.cc:298): H = -T^T A T, J^T = T^T g.
+template<int S> __device__ __forceinline__ bool solve_local(int lane, const double *s_sum, const double *s_Tinv, double g_scale, double *s_x,
+	double *s_dp){
+	typedef AccLayout<S> L;
+	double a[S];
+	const int j = lane < S ? lane : 0;
+#pragma unroll
+	for(int i = 0; i < S; ++i) a[i] = (lane == S) ? s_sum[1 + i] * g_scale : s_sum[1 + S + L::tri(i < j ? i : j, i < j ? j : i)];
+	double dmax = 0;
+#pragma unroll
+	for(int i = 0; i < S; ++i) dmax = fmax(dmax, s_sum[1 + S + L::tri(i, i)]);
+	bool ok = dmax > 0 && dmax < 1e300;
+#pragma unroll
+	for(int kk = 0; kk < S; ++kk){
+		const double piv = __shfl_sync(FULL_MASK, a[kk], kk);
+		ok = ok && (piv > 1e-11 * dmax);
+		double v[S];
+#pragma unroll
+		for(int i = 0; i < S; ++i) if(i != kk) v[i] = __shfl_sync(FULL_MASK, a[i], kk);
+		const double t = a[kk] * rcp_newton(ok ? piv : 1.0);
+		a[kk] = t;
+#pragma unroll
+		for(int i = 0; i < S; ++i) if(i != kk) a[i] = fma(-v[i], t, a[i]);
+	}
+	if(!ok) return false;
+	if(lane == S){
+#pragma unroll
+		for(int i = 0; i < S; ++i) s_x[i] = a[i];
+	}
+	__syncwarp();
+	if(lane < S){
+		double d = 0;
+#pragma unroll
+		for(int m = 0; m < S; ++m) d = fma(s_Tinv[lane*S + m], s_x[m], d);
+		s_dp[lane] = d;
+	}
+	__syncwarp();
+	return true;
+}
+
 } // namespace f32
 
 using namespace f32;
@@ -264,43 +490,45 @@ using namespace f32;
 #define F32_PROF_ADD()
 #endif
 
-template<int SSM, int SM, int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b){
+template<int SSM, int SM, int T, int MINB, int U>
+__global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, unsigned smem_bytes){
 	constexpr int S = StateSize<SSM>::value;
 	typedef AccLayout<S> L;
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	__shared__ double s_part[(T / 32) * L::NA];
 	__shared__ double s_sum[L::NA];
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8], s_dlt[9];
-	__shared__ double s_J[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_loc[3];
+	__shared__ double s_J[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_Tinv[S*S], s_loc[3], s_x[S], s_dp[S];
 	__shared__ float s_cf[C_COUNT], s_dl[9];
 	__shared__ int s_ci[2];
 	__shared__ int s_ctrl;
+	extern __shared__ __align__(16) float s_tmpl[];
+	__shared__ __align__(8) unsigned long long s_bar;
+	const bool use_smem = b.I0f_stride * (int)sizeof(float) <= (int)smem_bytes;
+	if(use_smem && tid == 0) mbar_init(&s_bar, 1);
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
 	cta_sync<T>();
-	if(tid == 0){
-		double x0, y0, s;
-		template_frame<SSM>(b, s_init_corners, x0, y0, s);
-		s_loc[0] = x0; s_loc[1] = y0; s_loc[2] = s;
-		make_basis_map<SSM>(x0, y0, s, s_T);
-		const double rs = 1.0 / s;
-#pragma unroll
-		for(int c = 0; c < 3; ++c){
-			s_dl[c] = (float)((s_dlt[c] - x0*s_dlt[6 + c])*rs);
-			s_dl[3 + c] = (float)((s_dlt[3 + c] - y0*s_dlt[6 + c])*rs);
-			s_dl[6 + c] = (float)s_dlt[6 + c];
-		}
-		pass_constants<SSM>(b, s_W, s_dlt, x0, y0, s, s_cf, s_ci);
+	if(use_smem && tid == 0){
+		const unsigned bytes = (unsigned)b.I0f_stride * (unsigned)sizeof(float);          // stride is a multiple of 4 floats
+		mbar_expect_tx(&s_bar, bytes);
+		bulk_copy_g2s(s_tmpl, b.I0f + (size_t)p*b.I0f_stride, bytes, &s_bar);
 	}
+	if(warp == 0) patch_setup<SSM>(b, lane, s_W, s_dlt, s_init_corners, s_loc, s_T, s_Tinv, s_dl, s_cf, s_ci);
 	cta_sync<T>();
 	float dl[9];
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dl[i] = s_dl[i];
-	const float *I0 = b.I0f + (size_t)p*b.N, *G0 = b.G0f + (size_t)p * 2 * b.N;
+	const bool dlt_affine = (dl[6] == 0.0f) && (dl[7] == 0.0f);
+	const float *I0 = b.I0f + (size_t)p*b.I0f_stride, *G0 = b.G0f + (size_t)p * 2 * b.N;
+	// the template, staged once per frame by one bulk async copy (TMA, SASS UBLKCP) issued before the per-patch setup;
+	// templates too large for the launch's dynamic shared memory are read through L2 instead
+	if(use_smem) mbar_wait(&s_bar, 0);
 	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
 	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
+	// the Hessian of this pass alone, no damping, nobody watching the reference-basis matrices: solve in the local basis
+	const bool local_solve = (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
@@ -313,105 +541,89 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b){
 		for(int i = 0; i < 6; ++i) k.a[i] = s_cf[C_A + i];
 		k.delta = s_cf[C_DELTA]; k.lox = s_cf[C_LOX]; k.hix = s_cf[C_HIX]; k.loy = s_cf[C_LOY]; k.hiy = s_cf[C_HIY];
 		k.X0 = s_ci[0]; k.Y0 = s_ci[1];
-		float acc[L::NA];
+		PackedAcc<S> acc;
+		acc.clear();
+		// U pixels per trip (pix, pix + T, ...): their dependent chains (coordinates -> loads -> chain rule) interleave
+		PixIterF it[U];
 #pragma unroll
-		for(int i = 0; i < L::NA; ++i) acc[i] = 0;
-		for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
-			const float i0 = __ldcg(I0 + it.pix);
-			PixF px;
-			pixel_front<SSM, false>(b, k, dl, s_dlt, s_W, it.row, it.col, px);
-			const float r = px.val - i0;                                   // I_diff (SSDBase.cc:78)
-			float Jt[S], Jj[S], wj;
-			if(need_grad){
-				float Gx, Gy;
-				chain_gradient<SSM>(k, px, Gx, Gy);
-				local_row<SSM>(px.xl, px.yl, Gx, Gy, Jt);
+		for(int u = 0; u < U; ++u) it[u] = PixIterF(tid + u*T, U*T, b.resx);
+		for(; it[0].pix < b.N; ){
+			bool vu[U]; int pixu[U]; float rowu[U], colu[U], i0[U];
+			PixF px[U];
+#pragma unroll
+			for(int u = 0; u < U; ++u){
+				vu[u] = (u == 0) || (it[u].pix < b.N);
+				pixu[u] = vu[u] ? it[u].pix : it[0].pix; rowu[u] = vu[u] ? it[u].rowf : it[0].rowf; colu[u] = vu[u] ? it[u].colf : it[0].colf;
+				i0[u] = use_smem ? s_tmpl[pixu[u]] : __ldcg(I0 + pixu[u]);
 			}
-			if(SM == SM_ICLK){
-				wj = r;                                                     // df_dI0 = I_diff (SSDBase.cc:34)
-				local_row<SSM>(px.xl, px.yl, __ldcg(G0 + it.pix), __ldcg(G0 + b.N + it.pix), Jj);
-			} else if(SM == SM_ESM){
-				wj = -r;                                                    // df_dIt = -I_diff (SSDBase.cc:115-121)
-				float J0[S];
-				local_row<SSM>(px.xl, px.yl, __ldcg(G0 + it.pix), __ldcg(G0 + b.N + it.pix), J0);
-				if(esm_mean){
 #pragma unroll
-					for(int s = 0; s < S; ++s) J0[s] = (J0[s] + Jt[s]) * 0.5f;     // NT/ESM.cc:246-248
-				}
-				if(b.jac_type == MTFB_ESM_JAC_ORIGINAL){
+			for(int u = 0; u < U; ++u) front_fast<SSM>(b, k, dl, dlt_affine, rowu[u], colu[u], px[u]);
 #pragma unroll
-					for(int s = 0; s < S; ++s) Jj[s] = J0[s];
-				} else{
+			for(int u = 0; u < U; ++u) if(!px[u].fast) front_exact<SSM>(b, k, s_dlt, s_W, rowu[u], colu[u], px[u]);
 #pragma unroll
-					for(int s = 0; s < S; ++s) Jj[s] = esm_mean ? (2.0f*J0[s]) : (J0[s] + Jt[s]);   // SSDBase.cc:186
-				}
-				if(b.hess_type == MTFB_ESM_HESS_ORIGINAL){
+			for(int u = 0; u < U; ++u) accumulate_pixel<SSM, SM>(b, k, px[u], i0[u], G0, pixu[u], vu[u], need_grad, esm_mean, acc);
 #pragma unroll
-					for(int s = 0; s < S; ++s) Jt[s] = J0[s];
-				}
-			} else{
-				wj = -r;
-#pragma unroll
-				for(int s = 0; s < S; ++s) Jj[s] = Jt[s];
-			}
-			acc[0] = fmaf(r, r, acc[0]);
-#pragma unroll
-			for(int s = 0; s < S; ++s) acc[1 + s] = fmaf(wj, Jj[s], acc[1 + s]);
-			if(need_grad){
-#pragma unroll
-				for(int i = 0; i < S; ++i){
-#pragma unroll
-					for(int j = i; j < S; ++j) acc[1 + S + L::tri(i, j)] = fmaf(Jt[i], Jt[j], acc[1 + S + L::tri(i, j)]);
-				}
-			}
+			for(int u = 0; u < U; ++u) it[u].next(U*T);
 		}
+		float accf[L::NA];
+		acc.unpack(accf);
 		F32_PROF_T(1)
-		double accd[L::NA];
-#pragma unroll
-		for(int i = 0; i < L::NA; ++i) accd[i] = (double)acc[i];
-		block_reduce<L::NA, T>(accd, s_part, s_sum);
+		block_reduce_f32<L::NA, T>(accf, s_part, s_sum);
 		++n_passes;
 		F32_PROF_T(2)
-		// local basis -> the reference's: H = T^T H_loc T, g = T^T g_loc (fp64)
-		for(int e = tid; e < S*S; e += T){
-			const int i = e / S, m = e % S;
-			s_Hl[e] = s_sum[1 + S + L::tri(i < m ? i : m, i < m ? m : i)];
+		bool solved = false;
+		if(local_solve){
+			if(warp == 0) solved = solve_local<S>(lane, s_sum, s_Tinv, jac_half ? 0.5 : 1.0, s_x, s_dp);
+			if(T > 32){
+				if(tid == 0) s_ctrl = solved ? 1 : 0;
+				__syncthreads();
+				solved = s_ctrl != 0;
+				__syncthreads();
+			}
 		}
-		cta_sync<T>();
-		for(int e = tid; e < S*S; e += T){
-			const int i = e / S, kk = e % S;
-			double a = 0;
+		if(!solved){
+			// local basis -> the reference's: H = T^T H_loc T, g = T^T g_loc (fp64), then the reference's QR
+			for(int e = tid; e < S*S; e += T){
+				const int i = e / S, m = e % S;
+				s_Hl[e] = s_sum[1 + S + L::tri(i < m ? i : m, i < m ? m : i)];
+			}
+			cta_sync<T>();
+			for(int e = tid; e < S*S; e += T){
+				const int i = e / S, kk = e % S;
+				double a = 0;
 #pragma unroll
-			for(int m = 0; m < S; ++m) a = fma(s_Hl[i*S + m], s_T[m*S + kk], a);
-			s_A[e] = a;                                                     // (H_loc T)[i][kk]
-		}
-		cta_sync<T>();
-		for(int e = tid; e < S*S; e += T){
-			const int i = e % S, j = e / S;                                 // s_Hc is column-major: entry (i, j) at j*S + i
-			const int lo = i < j ? i : j, hi = i < j ? j : i;
-			double a = 0;
+				for(int m = 0; m < S; ++m) a = fma(s_Hl[i*S + m], s_T[m*S + kk], a);
+				s_A[e] = a;                                                     // (H_loc T)[i][kk]
+			}
+			cta_sync<T>();
+			for(int e = tid; e < S*S; e += T){
+				const int i = e % S, j = e / S;                                 // s_Hc is column-major: entry (i, j) at j*S + i
+				const int lo = i < j ? i : j, hi = i < j ? j : i;
+				double a = 0;
 #pragma unroll
-			for(int m = 0; m < S; ++m) a = fma(s_T[m*S + lo], s_A[m*S + hi], a);
-			s_Hc[e] = -a;                                                   // SSD self Hessian: -J^T J (SSDBase.h:91-94)
-		}
-		if(tid < S){
-			double a = 0;
+				for(int m = 0; m < S; ++m) a = fma(s_T[m*S + lo], s_A[m*S + hi], a);
+				s_Hc[e] = -a;                                                   // SSD self Hessian: -J^T J (SSDBase.h:91-94)
+			}
+			if(tid < S){
+				double a = 0;
 #pragma unroll
-			for(int m = 0; m < S; ++m) a = fma(s_T[m*S + tid], s_sum[1 + m], a);
-			s_J[tid] = jac_half ? a * 0.5 : a;
+				for(int m = 0; m < S; ++m) a = fma(s_T[m*S + tid], s_sum[1 + m], a);
+				s_J[tid] = jac_half ? a * 0.5 : a;
+			}
+			cta_sync<T>();
 		}
-		cta_sync<T>();
 		F32_PROF_T(3)
 		if(warp == 0){
 			f = -s_sum[0] / 2;
-			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+			int ctrl;
+			if(solved) ctrl = serial_step<SSM, SM, true>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+				lm, patch_status, s_dp);
+			else ctrl = serial_step<SSM, SM, false>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
 				lm, patch_status);
-			if(lane == 0){
-				s_ctrl = ctrl;
-			}
+			if(lane == 0) s_ctrl = ctrl;
 			__syncwarp();
 			F32_PROF_T(4)
-			if(lane == 0 && ctrl != CTRL_BREAK) pass_constants<SSM>(b, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
+			if(ctrl != CTRL_BREAK) pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
 			F32_PROF_T(5)
 			F32_PROF_ADD()
 		}
@@ -429,25 +641,13 @@ template<int SSM, int T>
 __global__ void __launch_bounds__(T) ssd_stage_f32_kernel(DevBatch b, StageTapsF32 t){
 	constexpr int S = StateSize<SSM>::value;
 	const int p = blockIdx.x, tid = threadIdx.x;
-	__shared__ double s_W[9], s_dlt[9], s_ic[8], s_T[S*S], s_loc[3];
+	__shared__ double s_W[9], s_dlt[9], s_ic[8], s_T[S*S], s_Tinv[S*S], s_loc[3];
 	__shared__ float s_cf[C_COUNT], s_dl[9];
 	__shared__ int s_ci[2];
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8) s_ic[tid] = b.init_corners[(size_t)p * 8 + tid];
 	__syncthreads();
-	if(tid == 0){
-		double x0, y0, s;
-		template_frame<SSM>(b, s_ic, x0, y0, s);
-		s_loc[0] = x0; s_loc[1] = y0; s_loc[2] = s;
-		make_basis_map<SSM>(x0, y0, s, s_T);
-		const double rs = 1.0 / s;
-		for(int c = 0; c < 3; ++c){
-			s_dl[c] = (float)((s_dlt[c] - x0*s_dlt[6 + c])*rs);
-			s_dl[3 + c] = (float)((s_dlt[3 + c] - y0*s_dlt[6 + c])*rs);
-			s_dl[6 + c] = (float)s_dlt[6 + c];
-		}
-		pass_constants<SSM>(b, s_W, s_dlt, x0, y0, s, s_cf, s_ci);
-	}
+	if(tid < 32) patch_setup<SSM>(b, tid, s_W, s_dlt, s_ic, s_loc, s_T, s_Tinv, s_dl, s_cf, s_ci);
 	__syncthreads();
 	PassConst k;
 	float dl[9];
@@ -455,10 +655,16 @@ __global__ void __launch_bounds__(T) ssd_stage_f32_kernel(DevBatch b, StageTapsF
 	for(int i = 0; i < 6; ++i) k.a[i] = s_cf[C_A + i];
 	k.delta = s_cf[C_DELTA]; k.lox = s_cf[C_LOX]; k.hix = s_cf[C_HIX]; k.loy = s_cf[C_LOY]; k.hiy = s_cf[C_HIY];
 	k.X0 = s_ci[0]; k.Y0 = s_ci[1];
+	const bool dlt_affine = (dl[6] == 0.0f) && (dl[7] == 0.0f);
 	const size_t N = b.N;
-	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
-		PixF px;
-		pixel_front<SSM, true>(b, k, dl, s_dlt, s_W, it.row, it.col, px);
+	for(PixIterF it(tid, T, b.resx); it.pix < b.N; it.next(T)){
+		PixF px, ex;
+		front_fast<SSM>(b, k, dl, dlt_affine, it.rowf, it.colf, px);
+		ex = px;
+		front_exact<SSM>(b, k, s_dlt, s_W, it.rowf, it.colf, ex);
+		// (the fp64 point rounded to fp32: the comparison resolves 2^-24 of the local coordinate, a tenth of the bound)
+		const float ferr = px.fast ? fmaxf(fabsf(px.wxl - ex.wxl), fabsf(px.wyl - ex.wyl)) : -1.0f;
+		if(!px.fast) px = ex;
 		float Gx, Gy, Jl[S];
 		chain_gradient<SSM>(k, px, Gx, Gy);
 		local_row<SSM>(px.xl, px.yl, Gx, Gy, Jl);
@@ -466,7 +672,7 @@ __global__ void __launch_bounds__(T) ssd_stage_f32_kernel(DevBatch b, StageTapsF
 		if(t.idx){ t.idx[2 * q] = px.lx; t.idx[2 * q + 1] = px.ly; }
 		if(t.pix_vals) t.pix_vals[q] = px.val;
 		if(t.pix_grad){ t.pix_grad[p * 2 * N + it.pix] = px.gx; t.pix_grad[p * 2 * N + N + it.pix] = px.gy; }
-		if(t.fast_err) t.fast_err[q] = px.ferr;
+		if(t.fast_err) t.fast_err[q] = ferr;
 		if(t.pix_jac){
 			for(int c = 0; c < S; ++c){
 				double a = 0;
@@ -480,15 +686,40 @@ __global__ void __launch_bounds__(T) ssd_stage_f32_kernel(DevBatch b, StageTapsF
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+#ifndef MTFB_F32_U32
+#define MTFB_F32_U32 4      // pixels per trip at one warp per patch (<= 255 registers)
+#endif
+#ifndef MTFB_F32_U64
+#define MTFB_F32_U64 1      // ... at two or more warps per patch (<= 128 registers)
+#endif
+#ifndef MTFB_F32_MINB128
+#define MTFB_F32_MINB128 4
+#endif
+#ifndef MTFB_F32_MINB256
+#define MTFB_F32_MINB256 2
+#endif
+template<int SSM, int SM, int T, int MINB, int U> static cudaError_t launch_one(const DevBatch &b, cudaStream_t st){
+	// dynamic shared memory = the template (I0f row), if MINB CTAs of it still leave the SM most of its L1 for the image
+	// gathers; else the kernel reads the template through L2
+	size_t smem = (size_t)b.I0f_stride*sizeof(float);
+	if(smem*MINB > 96 * 1024) smem = 0;
+	static bool configured = false;                  // per instantiation; attributes are per function and sticky
+	if(!configured){
+		cudaError_t e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 / MINB);
+		if(e != cudaSuccess) return e;
+		configured = true;
+	}
+	ssd_update_f32_kernel<SSM, SM, T, MINB, U><<<b.P, T, smem, st>>>(b, (unsigned)smem);
+	return cudaGetLastError();
+}
 template<int SSM, int SM> static cudaError_t launch_update_f32_t(int threads, const DevBatch &b, cudaStream_t st){
 	switch(threads){
-	case 32: ssd_update_f32_kernel<SSM, SM, 32, 14><<<b.P, 32, 0, st>>>(b); break;
-	case 64: ssd_update_f32_kernel<SSM, SM, 64, 7><<<b.P, 64, 0, st>>>(b); break;
-	case 128: ssd_update_f32_kernel<SSM, SM, 128, 4><<<b.P, 128, 0, st>>>(b); break;
-	case 256: ssd_update_f32_kernel<SSM, SM, 256, 2><<<b.P, 256, 0, st>>>(b); break;
+	case 32: return launch_one<SSM, SM, 32, 8, MTFB_F32_U32>(b, st);
+	case 64: return launch_one<SSM, SM, 64, 7, MTFB_F32_U64>(b, st);
+	case 128: return launch_one<SSM, SM, 128, MTFB_F32_MINB128, MTFB_F32_U64>(b, st);
+	case 256: return launch_one<SSM, SM, 256, MTFB_F32_MINB256, MTFB_F32_U64>(b, st);
 	default: return cudaErrorInvalidValue;
 	}
-	return cudaGetLastError();
 }
 cudaError_t launch_update_ssd_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st){
 #ifdef MTFB_ONLY_FCLK_HOM

@@ -20,14 +20,14 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 // ------------------------------------------------------------------------------------------------
 template<int CNT, int MASK> struct Butterfly {
 	static constexpr int HALF = (CNT + 1) / 2;
-	template<int FULL> __device__ __forceinline__ static void run(double (&v)[FULL], int lane, int &base, bool &ok){
+	template<class V, int FULL> __device__ __forceinline__ static void run(V (&v)[FULL], int lane, int &base, bool &ok){
 		const bool up = (lane & MASK) != 0;
 #pragma unroll
 		for(int i = 0; i < HALF; ++i){
-			double lo = v[i];
-			double hi = (i + HALF < CNT) ? v[i + HALF] : 0.0;
-			double keep = up ? hi : lo;
-			double send = up ? lo : hi;
+			V lo = v[i];
+			V hi = (i + HALF < CNT) ? v[i + HALF] : V(0);
+			V keep = up ? hi : lo;
+			V send = up ? lo : hi;
 			v[i] = keep + __shfl_xor_sync(FULL_MASK, send, MASK);
 		}
 		// slot i of this lane now stands for previous-level slot i + HALF*up
@@ -42,7 +42,7 @@ template<int CNT> struct ReduceMap {
 };
 
 // returns through idx[0..2] the accumulator entry each of v[0..2] holds (or -1)
-template<int CNT> __device__ __forceinline__ void warp_reduce_scatter(double (&v)[CNT], int lane, int (&idx)[3]){
+template<int CNT, class V> __device__ __forceinline__ void warp_reduce_scatter(V (&v)[CNT], int lane, int (&idx)[3]){
 	typedef ReduceMap<CNT> M;
 	int dummy = 0; bool ok = true;
 	Butterfly<CNT, 16>::run(v, lane, dummy, ok);

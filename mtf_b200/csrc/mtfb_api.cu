@@ -169,8 +169,9 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		threads = p->n_patches >= 600 ? 32 : 64; occ = 0;
 	}
 	if(!threads && p->precision == MTFB_PRECISION_F32){
-		// ~7 CTAs per SM resident at <= 146 registers: two warps per patch fill the SM from 450 patches up
-		threads = p->n_patches >= 450 ? 64 : p->n_patches >= 200 ? 128 : 256;
+		// measured on B200 (profiles/README.md): two warps per patch once the batch gives every SM ~7 CTAs at 128
+		// registers, four CTAs of four warps below that, eight warps per patch for small batches
+		threads = p->n_patches >= 700 ? 64 : p->n_patches >= 150 ? 128 : 256;
 	}
 	if(!threads){
 		if(p->n_patches >= 900){ threads = 32; occ = 0; }
@@ -236,17 +237,17 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
-		b.xvf = b.yvf = nullptr; b.I0f = b.G0f = nullptr;
+		b.I0f = b.G0f = nullptr; b.I0f_stride = 0;
+		b.gx_lo = b.gx_step = b.gy_lo = b.gy_step = 0;
 		if(p->precision == MTFB_PRECISION_F32){
-			const size_t n_grid = (size_t)p->resx + p->resy, n_f32 = n_grid + 3 * (size_t)N*P;
+			const size_t stride = ((size_t)N + 3) & ~(size_t)3, n_f32 = (stride + 2 * (size_t)N)*P;
 			if(cudaMalloc(&c->d_f32, n_f32*sizeof(float)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 			if(cudaMemset(c->d_f32, 0, n_f32*sizeof(float)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
-			std::vector<float> gf(n_grid);
-			for(int i = 0; i < p->resx; ++i) gf[i] = (float)xv[i];
-			for(int i = 0; i < p->resy; ++i) gf[p->resx + i] = (float)yv[i];
-			if(cudaMemcpy(c->d_f32, gf.data(), n_grid*sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
-			b.xvf = c->d_f32; b.yvf = c->d_f32 + p->resx;
-			b.I0f = c->d_f32 + n_grid; b.G0f = b.I0f + (size_t)N*P;
+			b.I0f = c->d_f32; b.I0f_stride = (int)stride; b.G0f = c->d_f32 + stride*P;
+			// the LinSpaced grid as low + i * step: the kernel's coordinate error bound accounts for the <= 1.5 ulp this
+			// differs from the fp64 grid values by (lk_ssd_f32.cu pass_constants)
+			b.gx_lo = (float)xv[0]; b.gx_step = (float)((xv[p->resx - 1] - xv[0]) / (p->resx - 1));
+			b.gy_lo = (float)yv[0]; b.gy_step = (float)((yv[p->resy - 1] - yv[0]) / (p->resy - 1));
 		}
 		b.n_iters_prof = nullptr;
 #if MTFB_PROF

@@ -1,7 +1,7 @@
 """phase cycle counters of the fp32 SSD update kernel (experiment build -DMTFB_PROF=1, see profiles/build_variant.sh)"""
 import ctypes as C, os, sys
 sys.path.insert(0, '.')
-os.environ["MTFB_LIB"] = os.path.abspath("mtf_b200/csrc/_variants/libprof.so")
+os.environ.setdefault("MTFB_LIB", os.path.abspath("mtf_b200/csrc/_variants/libprof.so"))
 import numpy as np
 from mtf_b200 import api, synth
 sys.argv = ["bench"]
@@ -17,5 +17,5 @@ for T in (32, 64, 128):
     out = (C.c_longlong * 16)()
     api.load_library().mtfb_prof_read(tr._h, out, 16)
     v = np.array(out[:16], dtype=np.float64) / (1024 * 30 * 4)
-    print("f32 T=%d cycles per patch-pass: pixel loop %.0f, reduce %.0f, basis map %.0f, serial step %.0f (setup %.0f, QR %.0f, "
+    print(os.path.basename(os.environ["MTFB_LIB"]), "f32 T=%d cycles per patch-pass: pixel loop %.0f, reduce %.0f, basis map %.0f, serial step %.0f (setup %.0f, QR %.0f, "
           "back-subst %.0f), pass constants %.0f" % (T, v[8], v[9], v[10], v[11], v[4], v[5], v[6], v[12]))
