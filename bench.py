@@ -40,7 +40,9 @@ IMG = 1024
 N_FRAMES = 8
 ALG_BYTES_PER_ITER = 8 * N_PIX + 432          # I_t footprint + I_0 (fp32 each) + W in + J,H,f out
 METRIC = "LK iters/sec (50x50 SSD+Homography)"
-NCU_DRAM_BYTES_PER_LAUNCH = 24471552 + 4352   # ncu --set full, this workload: the frame and I0 once, everything else on chip
+# ncu --set full, this workload: the frame and the template once, everything else stays on chip
+NCU_DRAM_BYTES_PER_LAUNCH = {"f64": 24471552 + 4352, "f32": 14355200 + 768}
+NCU_TRAFFIC_SOURCE = {"f64": "profiles/r01_ncu_r1c_summary.txt", "f32": "profiles/r01_ncu_f32_summary.txt"}
 
 
 def peaks():
@@ -95,20 +97,34 @@ class ClockSampler(threading.Thread):
 
 def workload(seed_offset=0):
     from mtf_b200 import synth
-    cache = "/tmp/mtfb_bench_frames_%d_%d.npy" % (N_FRAMES, IMG)        # synthesis takes a few seconds per process
+    cache = "/tmp/mtfb_bench_seq_%d_%d.npz" % (N_FRAMES, IMG)        # synthesis takes a few seconds per process
+    global TRUE_WARPS
     try:
-        frames = list(np.load(cache))
+        z = np.load(cache)
+        frames, TRUE_WARPS = list(z["frames"]), list(z["warps"])
     except Exception:
-        frames, _ = synth.make_sequence(N_FRAMES, IMG, IMG, seed=1234, walk_seed=5678, sigma=1.0)
+        frames, TRUE_WARPS = synth.make_sequence(N_FRAMES, IMG, IMG, seed=1234, walk_seed=5678, sigma=1.0)
         try:
-            np.save(cache + ".%d.npy" % os.getpid(), np.stack(frames))
-            os.replace(cache + ".%d.npy" % os.getpid(), cache)
+            tmp = cache + ".%d.npz" % os.getpid()
+            np.savez(tmp, frames=np.stack(frames), warps=np.stack(TRUE_WARPS))
+            os.replace(tmp, cache)
         except Exception:
             pass
     corners = synth.make_patches(P_PER_GPU, 49.0, IMG, IMG, seed=42 + seed_offset)
     # ping-pong order keeps consecutive frames one random-walk step apart for any number of steps
     order = list(range(1, N_FRAMES)) + list(range(N_FRAMES - 2, -1, -1))
     return frames, corners, order
+
+
+TRUE_WARPS = None
+
+
+def truth_error(final, corners, frame_index):
+    """|tracked corner - ground-truth corner| (px) per patch: the synthetic frames are frame 0 under known homographies"""
+    from mtf_b200 import synth
+    gt = synth.warp_corners(TRUE_WARPS[frame_index], corners)
+    d = np.abs(final - gt).max(axis=(1, 2))
+    return {"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())}
 
 
 def oracle_params():
@@ -150,41 +166,17 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-def run_ours(args):
+def measure(args, precision, dev, world, rank, local_rank, dist, frames, corners, order, d_frames, pinned, flush):
+    """one arm (precision 'f32' | 'f64'): device-resident timing, then end to end from pinned host frames.
+    -> dict(ms, kms, e2e_ms, launches, status, finite, windows)"""
     import torch
     from mtf_b200 import api
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
-    torch.cuda.set_device(local_rank)
-    sampler = ClockSampler(local_rank); sampler.start()        # nvidia-smi needs ~1 s to produce its first sample
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    frames, corners, order = workload(seed_offset=rank)
     P = P_PER_GPU
     prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=local_rank,
-                          threads_per_patch=args.threads, occupancy=args.occ, precision=args.precision)
+                          threads_per_patch=args.threads, occupancy=args.occ, precision=precision)
     tr = api.BatchTracker(prm)
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
+    stream = torch.cuda.current_stream(dev)
     tr.set_stream(stream.cuda_stream)
-    if args.pitch_pad:
-        # experiment: device frames with a row pitch of IMG + pad floats (L1 set-conflict study, profiles/README.md)
-        d_frames = []
-        for f in frames:
-            buf = torch.empty((IMG, IMG + args.pitch_pad), dtype=torch.float32, device=dev)
-            buf[:, :IMG].copy_(torch.from_numpy(f))
-            d_frames.append(buf[:, :IMG])
-    else:
-        d_frames = [torch.from_numpy(f).to(dev) for f in frames]
-    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     gathered = torch.empty((world, P, 8), dtype=torch.float64, device=dev) if world > 1 else None
     d_corners_ptr, _, _ = tr.device_results()
 
@@ -233,7 +225,8 @@ def run_ours(args):
     ms = sum(a.elapsed_time(b) for a, b in ev)
     kms = sum(a.elapsed_time(b) for a, b in kev)
     status = tr.patch_status()
-    finite = bool(np.isfinite(tr.getRegion()).all())
+    final = tr.getRegion()
+    last_frame = order[(args.warmup + args.steps - 1) % len(order)]
 
     # ------------------------------------------------------------------ end to end (host buffers)
     tr.initialize(corners, frames[0])
@@ -257,37 +250,100 @@ def run_ours(args):
     barrier()
     e2e_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0))
     windows.append((win0, time.time()))
-    clocks = sampler.summary(windows)
-
     if world > 1:
         t = torch.tensor([ms, kms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, kms, e2e_ms = [float(x) for x in t.tolist()]
+    tr.close()
+    return dict(ms=ms, kms=kms, e2e_ms=e2e_ms, launches=int(launches), status=status, final=final, windows=windows,
+                truth=truth_error(final, corners, last_frame))
+
+
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank); sampler.start()        # nvidia-smi needs ~1 s to produce its first sample
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    frames, corners, order = workload(seed_offset=rank)
+    P = P_PER_GPU
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    if args.pitch_pad:
+        # experiment: device frames with a row pitch of IMG + pad floats (L1 set-conflict study, profiles/README.md)
+        d_frames = []
+        for f in frames:
+            buf = torch.empty((IMG, IMG + args.pitch_pad), dtype=torch.float32, device=dev)
+            buf[:, :IMG].copy_(torch.from_numpy(f))
+            d_frames.append(buf[:, :IMG])
+    else:
+        d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    common = (dev, world, rank, local_rank, dist, frames, corners, order, d_frames, pinned, flush)
+
+    # headline arm: the precision asked for (default f32 = north_star's "bit-exact sampling indices, fp32 tolerance");
+    # the other arm (fp64 in the reference's operation order) is timed in the same process and reported beside it
+    main = measure(args, args.precision, *common)
+    other_prec = "f64" if args.precision == "f32" else "f32"
+    other = measure(args, other_prec, *common) if not args.one_arm else None
+    clocks = sampler.summary(main["windows"] + (other["windows"] if other else []))
+
     total_iters = world * P * ITERS * args.steps
-    value = total_iters / (ms * 1e-3)
     peak, peak_src = peaks()
-    achieved = ALG_BYTES_PER_ITER * P * ITERS * args.steps / (kms * 1e-3) / 1e9        # per GPU
+
+    def roofline(m, precision):
+        achieved = ALG_BYTES_PER_ITER * P * ITERS * args.steps / (m["kms"] * 1e-3) / 1e9        # per GPU
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH[precision],
+                "traffic_source": NCU_TRAFFIC_SOURCE[precision] + " (dram__bytes_read + write, one launch)",
+                "kernel": ("ssd_update_kernel" if precision == "f64" else "ssd_update_f32_kernel") + "<Homography,FCLK>",
+                "kernel_ms_per_launch": m["kms"] / args.steps,
+                "alg_bytes_per_launch": ALG_BYTES_PER_ITER * P * ITERS, "peak_source": peak_src,
+                "note": ("fp64-issue bound" if precision == "f64" else "latency / issue bound") + ", not HBM bound: see DESIGN.md"}
+
+    def dtype(precision):
+        return "f64" if precision == "f64" else "f32 per pixel (bit-exact sampling indices), f64 reduction + solve"
+
+    status, final = main["status"], main["final"]
     out = {
-        "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if args.precision == "f64" else "f32 per pixel (exact sampling indices), f64 reduction + solve",
-        "data": "synthetic",
+        "metric": METRIC, "value": total_iters / (main["ms"] * 1e-3), "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype(args.precision), "data": "synthetic",
         "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
                                % (P, ITERS, IMG, IMG), "precision": args.precision,
-                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto", "occupancy": args.occ if args.threads else "auto",
+                   "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto",
+                   "occupancy": args.occ if args.threads else "auto",
                    "collective": "all_gather of P x 8 corners per frame" if world > 1 else "none"},
-        "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s",
+        "e2e": {"value": total_iters / (main["e2e_ms"] * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_ncu_r1c_summary.txt (dram__bytes_read + write, one launch)",
-                     "kernel": ("ssd_update_kernel" if args.precision == "f64" else "ssd_update_f32_kernel") + "<Homography,FCLK>",
-                     "kernel_ms_per_launch": kms / args.steps,
-                     "alg_bytes_per_launch": ALG_BYTES_PER_ITER * P * ITERS, "peak_source": peak_src,
-                     "note": "fp64-issue bound, not HBM bound: see DESIGN.md"},
+        "gpu_launches": main["launches"],
+        "roofline": roofline(main, args.precision),
         "clocks": clocks,
-        "valid": {"finite": finite, "patches_nan": int((status & 1 != 0).sum()), "patches_rank_deficient_H": int((status & 2 != 0).sum())},
+        "valid": {"finite": bool(np.isfinite(final).all()), "patches_nan": int((status & 1 != 0).sum()),
+                  "patches_rank_deficient_H": int((status & 2 != 0).sum()),
+                  # after warmup + steps frames of tracking, against the synthetic sequence's ground truth
+                  "corner_err_vs_truth_px": main["truth"]},
     }
+    if other is not None:
+        d = np.abs(other["final"] - final).max(axis=(1, 2))
+        out["other_precision"] = {
+            "precision": other_prec, "dtype": dtype(other_prec), "value": total_iters / (other["ms"] * 1e-3),
+            "ms_per_step": other["ms"] / args.steps, "e2e": total_iters / (other["e2e_ms"] * 1e-3),
+            "roofline_frac": roofline(other, other_prec)["frac"], "gpu_launches": other["launches"],
+            "corner_err_vs_truth_px": other["truth"],
+            "patches_rank_deficient_H": int((other["status"] & 2 != 0).sum()),
+            # the two arms track the same patches through the same frames: how far apart they end up (px)
+            "corner_diff_px": {"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())}}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -311,8 +367,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--threads", type=int, default=0, help="threads per patch (0 = library default)")
     ap.add_argument("--occ", type=int, default=0, help="occupancy knob of the update kernel (0, 1, 2)")
-    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
-                    help="per-pixel arithmetic of the update kernel (include/mtf_b200.h MTFB_PRECISION_*)")
+    ap.add_argument("--precision", default="f32", choices=["f64", "f32"],
+                    help="per-pixel arithmetic of the headline arm (include/mtf_b200.h MTFB_PRECISION_*); the other one is "
+                         "timed too and reported under other_precision")
+    ap.add_argument("--one-arm", action="store_true", help="time only the --precision arm")
     ap.add_argument("--pitch-pad", type=int, default=0, help="experiment: extra floats per device frame row")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -137,8 +137,11 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 		if(!(upd_norm == upd_norm) || !(f == f)) patch_status |= MTFB_PATCH_NAN;
 	}
 	__syncwarp();
-	if(lane < 9) s_W[lane] = Wn.m[lane];
-	if(lane < 8) s_corners[lane] = nc[lane];
+	// (unrolled: a lane-indexed read of a register array would go through local memory)
+#pragma unroll
+	for(int i = 0; i < 9; ++i) if(lane == i) s_W[i] = Wn.m[i];
+#pragma unroll
+	for(int i = 0; i < 8; ++i) if(lane == i) s_corners[i] = nc[i];
 	if(b.log && n_passes <= b.log_slots){
 		mtfb_iter_log *e = b.log + (size_t)p*b.log_slots + (n_passes - 1);
 		if(lane < S){ e->jacobian[lane] = rejected ? 0.0 : Jv; e->state_update[lane] = rejected ? 0.0 : x; }

@@ -44,7 +44,12 @@ struct PassConst {
 	float m[9], a[6];
 	float delta, lox, hix, loy, hiy;
 	int X0, Y0;
+	// where the four neighbours are read from: the frame in global memory, or the patch's window of it in shared memory
+	// (generic pointer), with the integer origin relative to that array
+	const float *base; int pitch, Xr, Yr;
 };
+// side of the square frame window a CTA keeps in shared memory (pitch F32_WIN + 1: rotated patches walk columns)
+constexpr int F32_WIN = 56, F32_WINP = F32_WIN + 1;
 
 __device__ __forceinline__ float rcp_approx(float x){
 	float r;
@@ -104,7 +109,7 @@ template<int SSM> __device__ __forceinline__ void make_basis_map(double x0, doub
 #undef TT
 }
 
-// Per-pass constants, by the 32 lanes of warp 0, in fp64 (lane i < 9 owns entry i of the 3 x 3 product).
+// Per-pass constants, by the 32 lanes of warp 0 (lane i < 9 owns entry i of the 3 x 3 product).
 //
 // Error bound behind delta (Homography; u, v in [-1/2, 1/2]).  wxl = num / den with num = c0 u + c1 v + c2 evaluated as
 // two fp32 fmaf's on coefficients rounded to fp32 (2^-24 relative) and grid values u = fmaf(i, step, low) that differ
@@ -118,39 +123,44 @@ template<int SSM> __device__ __forceinline__ void make_basis_map(double x0, doub
 // E = |c0| + |c1| + |c2|, |err| <= (14 + 4) . 2^-24 . E: covered by the same formula with rho = 2.
 template<int SSM> __device__ __forceinline__ void pass_constants(const DevBatch &b, int lane, const double *W, const double *dlt,
 	double x0, double y0, double s, float *cf, int *ci){
-	double E, rho = 2;
+	// The integer origin only has to be NEAR the patch centre (any integer is a valid origin), and delta only has to be an
+	// upper bound with its 2.5x margin: both are computed in fp32.  What must be exact -- the centred rows
+	// M0 - X0 M2, M1 - Y0 M2 -- is one fp64 fma per entry before the rounding to fp32.
+	float E, rho = 2.0f;
 	int X0 = 0, Y0 = 0;
 	bool sane = true;
-	double m[9];                                                 // the centred rows, uniform across the warp
 	if(SSM == SSM_HOM){
-		double Mi = 0;
+		double Mi;
 		{
-			const int i = lane < 9 ? lane : 0, r = i / 3, c = i % 3;
-			Mi = b.norm_init ? W[i] : (W[3 * r] * dlt[c] + W[3 * r + 1] * dlt[3 + c] + W[3 * r + 2] * dlt[6 + c]);
+			const int i = lane < 9 ? lane : 0, r = i / 3, c = i - 3 * r;
+			Mi = b.norm_init ? W[i] : fma(W[3 * r + 2], dlt[6 + c], fma(W[3 * r + 1], dlt[3 + c], W[3 * r] * dlt[c]));
 		}
-		const double m2 = __shfl_sync(FULL_MASK, Mi, 2), m5 = __shfl_sync(FULL_MASK, Mi, 5), m8 = __shfl_sync(FULL_MASK, Mi, 8);
-		const bool m8_ok = (m8 > 1e-30) && (m8 < 1e30);
-		const double r8 = rcp_newton(m8_ok ? m8 : 1.0);             // relative error ~1e-16: only picks the integer origin
-		const double cx = m2 * r8, cy = m5 * r8;
-		sane = m8_ok && (fabs(cx) < 2e6) && (fabs(cy) < 2e6);      // the magic-number floor needs |coordinates| < 2^22
-		if(sane){ X0 = (int)floor(cx); Y0 = (int)floor(cy); }
+		const float Mf = (float)Mi;
+		const float m2 = __shfl_sync(FULL_MASK, Mf, 2), m5 = __shfl_sync(FULL_MASK, Mf, 5), m8 = __shfl_sync(FULL_MASK, Mf, 8);
+		const float r8 = rcp_approx(m8);
+		const float cx = m2 * r8, cy = m5 * r8;
+		sane = (m8 > 1e-30f) && (fabsf(cx) < 2e6f) && (fabsf(cy) < 2e6f);          // the magic-number floor needs |coordinates| < 2^22
+		if(sane){ X0 = (int)floorf(cx); Y0 = (int)floorf(cy); }
 		const double mz = __shfl_sync(FULL_MASK, Mi, 6 + lane % 3);
-		if(lane < 3) Mi -= X0*mz; else if(lane < 6) Mi -= Y0*mz;
-#pragma unroll
-		for(int i = 0; i < 9; ++i) m[i] = __shfl_sync(FULL_MASK, Mi, i);
+		if(lane < 6) Mi = fma(-(double)(lane < 3 ? X0 : Y0), mz, Mi);
+		const float Mc = fabsf((float)Mi);
 		if(lane < 9) cf[C_M + lane] = (float)Mi;
-		if(lane == 9) cf[C_A + 0] = (float)(W[0] - W[6] * X0);
-		if(lane == 10) cf[C_A + 1] = (float)(W[1] - W[7] * X0);
-		if(lane == 11) cf[C_A + 2] = (float)(W[3] - W[6] * Y0);
-		if(lane == 12) cf[C_A + 3] = (float)(W[4] - W[7] * Y0);
-		if(lane == 13) cf[C_A + 4] = (float)W[6];
-		if(lane == 14) cf[C_A + 5] = (float)W[7];
-		const double Ax = 0.5*fabs(m[0]) + 0.5*fabs(m[1]) + fabs(m[2]), Ay = 0.5*fabs(m[3]) + 0.5*fabs(m[4]) + fabs(m[5]);
-		const double Dmin = fabs(m[8]) - 0.5*fabs(m[6]) - 0.5*fabs(m[7]);
-		const bool dmin_ok = (Dmin > 1e-30) && (Dmin < 1e30);
-		const double rD = rcp_newton(dmin_ok ? Dmin : 1.0);
-		E = fmax(Ax, Ay) * rD;
-		rho = (fabs(m[8]) + 0.5*fabs(m[6]) + 0.5*fabs(m[7])) * rD;
+		if(lane >= 9 && lane < 15){
+			// a00 - a20 X0, a01 - a21 X0, a10 - a20 Y0, a11 - a21 Y0, a20, a21
+			const int q = lane - 9;
+			const int ia = q < 2 ? q : (q < 4 ? q + 1 : q + 2), ib = 6 + (q & 1);
+			const double sc = q < 2 ? (double)X0 : (q < 4 ? (double)Y0 : 0.0);
+			cf[C_A + q] = (float)fma(-W[ib], sc, W[ia]);
+		}
+		float m[9];
+#pragma unroll
+		for(int i = 0; i < 9; ++i) m[i] = __shfl_sync(FULL_MASK, Mc, i);
+		const float Ax = 0.5f*m[0] + 0.5f*m[1] + m[2], Ay = 0.5f*m[3] + 0.5f*m[4] + m[5];
+		const float Dmin = m[8] - 0.5f*m[6] - 0.5f*m[7];
+		const bool dmin_ok = (Dmin > 1e-30f) && (Dmin < 1e30f);
+		const float rD = rcp_approx(dmin_ok ? Dmin : 1.0f);
+		E = fmaxf(Ax, Ay) * rD;
+		rho = (m[8] + 0.5f*m[6] + 0.5f*m[7]) * rD;
 		sane = sane && dmin_ok;
 	} else{
 		const double cx = W[0] * x0 + W[1] * y0 + W[2], cy = W[3] * x0 + W[4] * y0 + W[5];
@@ -165,17 +175,42 @@ template<int SSM> __device__ __forceinline__ void pass_constants(const DevBatch 
 			cf[C_A + 0] = (float)((W[0] - 1) + 1); cf[C_A + 1] = (float)W[1]; cf[C_A + 2] = (float)W[3]; cf[C_A + 3] = (float)((W[4] - 1) + 1);
 			cf[C_A + 4] = 0; cf[C_A + 5] = 0;
 		}
-		E = fmax(fabs(c[0]) + fabs(c[1]) + fabs(c[2]), fabs(c[3]) + fabs(c[4]) + fabs(c[5]));
+		E = (float)fmax(fabs(c[0]) + fabs(c[1]) + fabs(c[2]), fabs(c[3]) + fabs(c[4]) + fabs(c[5]));
 	}
-	double delta = 2.5 * 5.9604644775390625e-8 * (9 + 6 * rho) * E + 2e-6;
-	if(!sane || !(delta < 0.25)) delta = 2.0;                    // every pixel takes the fp64 path
+	// (1 + 1e-5): the bound itself is evaluated in fp32
+	float delta = 2.5f * 5.9604644775390625e-8f * (9.0f + 6.0f * rho) * E * 1.00001f + 2e-6f;
+	if(!sane || !(delta < 0.25f)) delta = 2.0f;                  // every pixel takes the fp64 path
 	if(lane == 0){
-		cf[C_DELTA] = (float)delta;
+		cf[C_DELTA] = delta;
 		// fast path only if all four neighbours are inside the image: 0 <= lx, lx + 1 <= w - 1 (same for y)
-		cf[C_LOX] = (float)(-(double)X0); cf[C_HIX] = (float)((double)b.img.w - 2 - X0);
-		cf[C_LOY] = (float)(-(double)Y0); cf[C_HIY] = (float)((double)b.img.h - 2 - Y0);
+		cf[C_LOX] = (float)(-X0); cf[C_HIX] = (float)(b.img.w - 2 - X0);
+		cf[C_LOY] = (float)(-Y0); cf[C_HIY] = (float)(b.img.h - 2 - Y0);
 		ci[0] = X0; ci[1] = Y0;
 	}
+}
+
+// Frame window in shared memory (one thread, once per pass): does the F32_WIN x F32_WIN window staged at origin
+// (wi[0], wi[1]) still hold every neighbour the patch's samples can touch -- the integer hull of its four corners plus
+// one?  If not, pick a new origin centred on the patch (clipped to the frame) and ask for a restage; a patch that does
+// not fit the window (or a frame smaller than it) samples the frame in global memory for this pass.
+// wi: 0 ox, 1 oy, 2 use the window this pass, 3 restage before the pass, 4 window contents valid
+__device__ __forceinline__ void window_decide(const DevBatch &b, const double *corners, bool have_window, int *wi){
+	wi[2] = 0; wi[3] = 0;
+	if(!have_window || b.img.w < F32_WIN || b.img.h < F32_WIN) return;
+	double x0 = corners[0], x1 = corners[0], y0 = corners[4], y1 = corners[4];
+#pragma unroll
+	for(int i = 1; i < 4; ++i){ x0 = fmin(x0, corners[i]); x1 = fmax(x1, corners[i]); y0 = fmin(y0, corners[4 + i]); y1 = fmax(y1, corners[4 + i]); }
+	if(!(x0 > -1e6 && x1 < 1e6 && y0 > -1e6 && y1 < 1e6)) return;
+	const int ix0 = (int)floor(x0), ix1 = (int)floor(x1) + 1, iy0 = (int)floor(y0), iy1 = (int)floor(y1) + 1;
+	if(ix1 - ix0 + 1 > F32_WIN || iy1 - iy0 + 1 > F32_WIN) return;
+	const bool covered = wi[4] && ix0 >= wi[0] && ix1 <= wi[0] + F32_WIN - 1 && iy0 >= wi[1] && iy1 <= wi[1] + F32_WIN - 1;
+	if(!covered){
+		int ox = (ix0 + ix1 + 1) / 2 - F32_WIN / 2, oy = (iy0 + iy1 + 1) / 2 - F32_WIN / 2;
+		ox = ox < 0 ? 0 : (ox > b.img.w - F32_WIN ? b.img.w - F32_WIN : ox);
+		oy = oy < 0 ? 0 : (oy > b.img.h - F32_WIN ? b.img.h - F32_WIN : oy);
+		wi[0] = ox; wi[1] = oy; wi[3] = 1; wi[4] = 1;
+	}
+	wi[2] = 1;
 }
 
 // per-patch setup by warp 0: template frame, basis maps, centred DLT rows, first pass constants
@@ -263,9 +298,9 @@ template<int SSM> __device__ __forceinline__ void front_fast(const DevBatch &b, 
 	o.fast = (dx >= k.delta) && (dx <= hi) && (dy >= k.delta) && (dy <= hi) &&
 		(fx >= k.lox) && (fx <= k.hix) && (fy >= k.loy) && (fy <= k.hiy);
 	o.lx = k.X0 + ix; o.ly = k.Y0 + iy;
-	const int off = o.fast ? o.ly*b.img.pitch + o.lx : 0;
-	const float *r0 = b.img.data + off, *r1 = r0 + b.img.pitch;
-	const float p00 = __ldg(r0), p01 = __ldg(r0 + 1), p10 = __ldg(r1), p11 = __ldg(r1 + 1);
+	const int off = o.fast ? (k.Yr + iy)*k.pitch + (k.Xr + ix) : 0;
+	const float *r0 = k.base + off, *r1 = r0 + k.pitch;
+	const float p00 = r0[0], p01 = r0[1], p10 = r1[0], p11 = r1[1];
 	const float t0 = p01 - p00, t1 = p11 - p10;
 	const float top = fmaf(dx, t0, p00), bot = fmaf(dx, t1, p10);
 	o.gy = bot - top;                                                    // (1 - dx)(p10 - p00) + dx (p11 - p01)
@@ -491,7 +526,7 @@ using namespace f32;
 #endif
 
 template<int SSM, int SM, int T, int MINB, int U>
-__global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, unsigned smem_bytes){
+__global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, unsigned smem_bytes, unsigned win_elems){
 	constexpr int S = StateSize<SSM>::value;
 	typedef AccLayout<S> L;
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -500,11 +535,11 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8], s_dlt[9];
 	__shared__ double s_J[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_Tinv[S*S], s_loc[3], s_x[S], s_dp[S];
 	__shared__ float s_cf[C_COUNT], s_dl[9];
-	__shared__ int s_ci[2];
+	__shared__ int s_ci[2], s_wi[5];
 	__shared__ int s_ctrl;
 	extern __shared__ __align__(16) float s_tmpl[];
 	__shared__ __align__(8) unsigned long long s_bar;
-	const bool use_smem = b.I0f_stride * (int)sizeof(float) <= (int)smem_bytes;
+	const bool use_smem = smem_bytes != 0;             // the launcher sized the dynamic shared memory for the template or not
 	if(use_smem && tid == 0) mbar_init(&s_bar, 1);
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
@@ -514,7 +549,10 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 		mbar_expect_tx(&s_bar, bytes);
 		bulk_copy_g2s(s_tmpl, b.I0f + (size_t)p*b.I0f_stride, bytes, &s_bar);
 	}
-	if(warp == 0) patch_setup<SSM>(b, lane, s_W, s_dlt, s_init_corners, s_loc, s_T, s_Tinv, s_dl, s_cf, s_ci);
+	if(warp == 0){
+		patch_setup<SSM>(b, lane, s_W, s_dlt, s_init_corners, s_loc, s_T, s_Tinv, s_dl, s_cf, s_ci);
+		if(lane == 0){ s_wi[4] = 0; window_decide(b, s_corners, win_elems != 0, s_wi); }
+	}
 	cta_sync<T>();
 	float dl[9];
 #pragma unroll
@@ -524,6 +562,11 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	// the template, staged once per frame by one bulk async copy (TMA, SASS UBLKCP) issued before the per-patch setup;
 	// templates too large for the launch's dynamic shared memory are read through L2 instead
 	if(use_smem) mbar_wait(&s_bar, 0);
+	const float *tmpl = use_smem ? (const float*)s_tmpl : I0;     // generic pointer: one load instruction either way
+	// per-thread bit columns of the pixels deferred to the fp64 path, behind the template in dynamic shared memory
+	const int slow_words = ((b.N + T - 1) / T + 31) / 32;
+	unsigned *s_slow = reinterpret_cast<unsigned*>(s_tmpl) + (use_smem ? b.I0f_stride : 0);
+	float *s_win = reinterpret_cast<float*>(s_slow + slow_words*T);
 	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
 	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
@@ -532,6 +575,11 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
+	// first grid position of each of this thread's U pixel streams (two integer divisions and five conversions: once per
+	// frame, not once per pass)
+	PixIterF it_first[U];
+#pragma unroll
+	for(int u = 0; u < U; ++u) it_first[u] = PixIterF(tid + u*T, U*T, b.resx);
 	while(iter_id < b.max_iters){
 		F32_PROF_T(0)
 		PassConst k;
@@ -541,29 +589,73 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 		for(int i = 0; i < 6; ++i) k.a[i] = s_cf[C_A + i];
 		k.delta = s_cf[C_DELTA]; k.lox = s_cf[C_LOX]; k.hix = s_cf[C_HIX]; k.loy = s_cf[C_LOY]; k.hiy = s_cf[C_HIY];
 		k.X0 = s_ci[0]; k.Y0 = s_ci[1];
+		k.base = b.img.data; k.pitch = b.img.pitch; k.Xr = k.X0; k.Yr = k.Y0;
+		if(s_wi[2]){
+			// this pass samples the shared-memory window of the frame (s_wi: window_decide)
+			const int ox = s_wi[0], oy = s_wi[1];
+			if(s_wi[3]){
+				for(int i = tid; i < F32_WIN*F32_WIN; i += T){
+					const int r = i / F32_WIN, c = i - r*F32_WIN;
+					s_win[r*F32_WINP + c] = __ldg(b.img.data + (size_t)(oy + r)*b.img.pitch + ox + c);
+				}
+				cta_sync<T>();
+			}
+			k.base = s_win; k.pitch = F32_WINP; k.Xr = k.X0 - ox; k.Yr = k.Y0 - oy;
+			// all four neighbours inside the window (which lies inside the frame)
+			k.lox = (float)(ox - k.X0); k.hix = (float)(ox + F32_WIN - 2 - k.X0);
+			k.loy = (float)(oy - k.Y0); k.hiy = (float)(oy + F32_WIN - 2 - k.Y0);
+		}
 		PackedAcc<S> acc;
 		acc.clear();
-		// U pixels per trip (pix, pix + T, ...): their dependent chains (coordinates -> loads -> chain rule) interleave
+		// U pixels per trip (pix, pix + T, ...): their dependent chains (coordinates -> loads -> chain rule) interleave.
+		// The loop is branch-free: a pixel that must take the fp64 path contributes nothing here (weight zero) and sets a
+		// bit in this thread's column of s_slow; the bits are worked off after the loop.  (Nearly) every pixel is slow only
+		// when the warp sits on the pixel lattice -- the first pass after initialize() with an integer-aligned box.
+		for(int w = 0; w < slow_words; ++w) s_slow[w*T + tid] = 0u;
 		PixIterF it[U];
 #pragma unroll
-		for(int u = 0; u < U; ++u) it[u] = PixIterF(tid + u*T, U*T, b.resx);
-		for(; it[0].pix < b.N; ){
+		for(int u = 0; u < U; ++u) it[u] = it_first[u];
+		for(int g = 0; it[0].pix < b.N; g += U){
 			bool vu[U]; int pixu[U]; float rowu[U], colu[U], i0[U];
 			PixF px[U];
 #pragma unroll
 			for(int u = 0; u < U; ++u){
 				vu[u] = (u == 0) || (it[u].pix < b.N);
 				pixu[u] = vu[u] ? it[u].pix : it[0].pix; rowu[u] = vu[u] ? it[u].rowf : it[0].rowf; colu[u] = vu[u] ? it[u].colf : it[0].colf;
-				i0[u] = use_smem ? s_tmpl[pixu[u]] : __ldcg(I0 + pixu[u]);
+				i0[u] = tmpl[pixu[u]];
 			}
 #pragma unroll
 			for(int u = 0; u < U; ++u) front_fast<SSM>(b, k, dl, dlt_affine, rowu[u], colu[u], px[u]);
 #pragma unroll
-			for(int u = 0; u < U; ++u) if(!px[u].fast) front_exact<SSM>(b, k, s_dlt, s_W, rowu[u], colu[u], px[u]);
-#pragma unroll
-			for(int u = 0; u < U; ++u) accumulate_pixel<SSM, SM>(b, k, px[u], i0[u], G0, pixu[u], vu[u], need_grad, esm_mean, acc);
+			for(int u = 0; u < U; ++u){
+				if(vu[u] && !px[u].fast) s_slow[((g + u) >> 5)*T + tid] |= 1u << ((g + u) & 31);      // pixel tid + (g + u) T
+				accumulate_pixel<SSM, SM>(b, k, px[u], i0[u], G0, pixu[u], vu[u] && px[u].fast, need_grad, esm_mean, acc);
+			}
 #pragma unroll
 			for(int u = 0; u < U; ++u) it[u].next(U*T);
+		}
+		for(int w = 0; w < slow_words; ++w){
+			unsigned bits = s_slow[w*T + tid];
+			while(bits){
+				const int g = 32 * w + __ffs(bits) - 1;
+				bits &= bits - 1;
+				const int pix = tid + g*T;
+				PixF px;
+				px.fast = false;
+				const float rowf = (float)(pix / b.resx), colf = (float)(pix % b.resx);
+				// template-local coordinates as the fast path computes them
+				{
+					const float u = fmaf(colf, b.gx_step, b.gx_lo), v = fmaf(rowf, b.gy_step, b.gy_lo);
+					px.xl = fmaf(dl[0], u, fmaf(dl[1], v, dl[2]));
+					px.yl = fmaf(dl[3], u, fmaf(dl[4], v, dl[5]));
+					if(!dlt_affine){
+						const float rz = rcp_approx(fmaf(dl[6], u, fmaf(dl[7], v, dl[8])));
+						px.xl *= rz; px.yl *= rz;
+					}
+				}
+				front_exact<SSM>(b, k, s_dlt, s_W, rowf, colf, px);
+				accumulate_pixel<SSM, SM>(b, k, px, tmpl[pix], G0, pix, true, need_grad, esm_mean, acc);
+			}
 		}
 		float accf[L::NA];
 		acc.unpack(accf);
@@ -623,7 +715,10 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 			if(lane == 0) s_ctrl = ctrl;
 			__syncwarp();
 			F32_PROF_T(4)
-			if(ctrl != CTRL_BREAK) pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
+			if(ctrl != CTRL_BREAK){
+				pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
+				if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+			}
 			F32_PROF_T(5)
 			F32_PROF_ADD()
 		}
@@ -655,6 +750,7 @@ __global__ void __launch_bounds__(T) ssd_stage_f32_kernel(DevBatch b, StageTapsF
 	for(int i = 0; i < 6; ++i) k.a[i] = s_cf[C_A + i];
 	k.delta = s_cf[C_DELTA]; k.lox = s_cf[C_LOX]; k.hix = s_cf[C_HIX]; k.loy = s_cf[C_LOY]; k.hiy = s_cf[C_HIY];
 	k.X0 = s_ci[0]; k.Y0 = s_ci[1];
+	k.base = b.img.data; k.pitch = b.img.pitch; k.Xr = k.X0; k.Yr = k.Y0;
 	const bool dlt_affine = (dl[6] == 0.0f) && (dl[7] == 0.0f);
 	const size_t N = b.N;
 	for(PixIterF it(tid, T, b.resx); it.pix < b.N; it.next(T)){
@@ -703,13 +799,33 @@ template<int SSM, int SM, int T, int MINB, int U> static cudaError_t launch_one(
 	// gathers; else the kernel reads the template through L2
 	size_t smem = (size_t)b.I0f_stride*sizeof(float);
 	if(smem*MINB > 96 * 1024) smem = 0;
+#ifdef MTFB_F32_NO_STAGE     // experiment: template through L2 instead of shared memory
+	smem = 0;
+#endif
+	const size_t slow_bytes = (size_t)((((b.N + T - 1) / T + 31) / 32)*T) * sizeof(unsigned);
+	// the frame window, if MINB CTAs with it still fit the SM's shared memory
+	size_t win_bytes = (size_t)F32_WIN*F32_WINP*sizeof(float);
+	if((smem + slow_bytes + win_bytes + 6 * 1024)*MINB > 216 * 1024) win_bytes = 0;
+#ifdef MTFB_F32_NO_WINDOW    // experiment: gather from the frame in global memory
+	win_bytes = 0;
+#endif
 	static bool configured = false;                  // per instantiation; attributes are per function and sticky
 	if(!configured){
-		cudaError_t e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 / MINB);
+		cudaError_t e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 / MINB + 32 * 1024);
+		if(e != cudaSuccess) return e;
+		// shared memory carve-out: what MINB resident CTAs need (static + dynamic + 1 KB the system reserves per CTA);
+		// the rest of the SM's 228 KB stays L1 for the image gathers.  Too small a carve-out would cost resident CTAs.
+		cudaFuncAttributes fa;
+		e = cudaFuncGetAttributes(&fa, ssd_update_f32_kernel<SSM, SM, T, MINB, U>);
+		if(e != cudaSuccess) return e;
+		const size_t per_cta = fa.sharedSizeBytes + (size_t)b.I0f_stride*sizeof(float) + slow_bytes + (size_t)F32_WIN*F32_WINP*sizeof(float) + 1024;
+		const int carve = (int)((per_cta*MINB * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+		e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
 		if(e != cudaSuccess) return e;
 		configured = true;
 	}
-	ssd_update_f32_kernel<SSM, SM, T, MINB, U><<<b.P, T, smem, st>>>(b, (unsigned)smem);
+	if(slow_bytes > 16 * 1024) return cudaErrorInvalidValue;      // > 4 M pixels per patch
+	ssd_update_f32_kernel<SSM, SM, T, MINB, U><<<b.P, T, smem + slow_bytes + win_bytes, st>>>(b, (unsigned)smem, (unsigned)(win_bytes / sizeof(float)));
 	return cudaGetLastError();
 }
 template<int SSM, int SM> static cudaError_t launch_update_f32_t(int threads, const DevBatch &b, cudaStream_t st){
