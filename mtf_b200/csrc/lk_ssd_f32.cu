@@ -372,6 +372,31 @@ __device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &
 __device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b){
 	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
+#ifdef MTFB_F32_NO_PACK     // experiment: one FFMA per sum (45 per pixel) instead of the packed form
+template<int S> struct PackedAcc {
+	typedef AccLayout<S> L;
+	float a[L::NA];
+	__device__ __forceinline__ void clear(){
+#pragma unroll
+		for(int i = 0; i < L::NA; ++i) a[i] = 0;
+	}
+	__device__ __forceinline__ void add(float r, float wj, const float (&Jj)[S], const float (&Jt)[S], bool with_hessian){
+		a[0] = fmaf(r, r, a[0]);
+#pragma unroll
+		for(int s = 0; s < S; ++s) a[1 + s] = fmaf(wj, Jj[s], a[1 + s]);
+		if(with_hessian){
+#pragma unroll
+			for(int i = 0; i < S; ++i)
+#pragma unroll
+			for(int j = i; j < S; ++j) a[1 + S + L::tri(i, j)] = fmaf(Jt[i], Jt[j], a[1 + S + L::tri(i, j)]);
+		}
+	}
+	__device__ __forceinline__ void unpack(float (&acc)[L::NA]) const{
+#pragma unroll
+		for(int i = 0; i < L::NA; ++i) acc[i] = a[i];
+	}
+};
+#else
 template<int S> struct PackedAcc {
 	typedef AccLayout<S> L;
 	static constexpr int NP = S*S / 4;                 // pairs of the Hessian: S/2 row pairs x (1 + (S - 2 - i) ...) summed = S^2/4
@@ -416,6 +441,8 @@ template<int S> struct PackedAcc {
 		}
 	}
 };
+
+#endif
 
 // what one pixel adds to the sums (same cases as lk_ssd_terms.cuh pixel_terms / accumulate_terms)
 template<int SSM, int SM> __device__ __forceinline__ void accumulate_pixel(const DevBatch &b, const PassConst &k, const PixF &px, float i0,

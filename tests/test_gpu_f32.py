@@ -211,3 +211,96 @@ def test_f32_unsupported_combinations():
         with pytest.raises(api.MTFError) as e:
             api.BatchTracker(api.make_params(am, "homography", sm, n_patches=2, precision="f32", **kw))
         assert e.value.type == "FunctonNotImplemented"
+
+
+@pytest.mark.parametrize("res,side", [((10, 10), 9.0), ((25, 25), 26.3), ((64, 40), 51.7), ((100, 100), 99.0)])
+def test_f32_resolutions(seq384, res, side):
+    """sampling grids other than 50 x 50: cells of GridTracker size, a non-square grid, one larger than the 56-pixel
+    frame window (which then samples the frame in global memory)"""
+    frames, _ = seq384
+    cs = common.patches(5, side, 384, 384, seed=21)
+    if res == (64, 40):
+        cs[:, 1, :] = cs[:, 1, :1] + (cs[:, 1, :] - cs[:, 1, :1]) * (40.0 / 64.0)       # 64 : 40 boxes
+    g = _gpu("homography", "fclk", len(cs), resx=res[0], resy=res[1], epsilon=0.0, hom_normalized_init=1)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("homography", "fclk", grad_mode=1, epsilon=0.0, hom_normalized_init=1, resx=res[0], resy=res[1])
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        got = g.getRegion()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            # a 10 x 10 cell has 100 pixels behind 8 parameters: its fixed point is 10x more sensitive to the gradients
+            tol = CORNER_ATOL_F32 * (10 if res[0] * res[1] <= 100 else 1)
+            assert np.abs(got[i] - o.corners()).max() <= tol, (res, i, np.abs(got[i] - o.corners()).max())
+
+
+def test_f32_fast_motion_restages_window():
+    """3 px of corner jitter per frame: the patch leaves the margin of its shared-memory frame window (56 px for a 50 px
+    box) and the window is restaged mid-frame; results must not depend on it"""
+    from mtf_b200 import synth
+    frames, _ = synth.make_sequence(5, 320, 320, seed=77, walk_seed=99, sigma=3.0)
+    cs = common.patches(6, 49.0, 320, 320, seed=5)
+    g = _gpu("homography", "fclk", len(cs), epsilon=0.0, hom_normalized_init=1)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("homography", "fclk", grad_mode=1, epsilon=0.0, hom_normalized_init=1)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:]:
+        g.update(fr)
+        got = g.getRegion()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            assert np.abs(got[i] - o.corners()).max() <= CORNER_ATOL_F32
+
+
+def test_f32_frame_smaller_than_window():
+    from mtf_b200 import synth
+    frames, _ = synth.make_sequence(3, 48, 52, seed=3, walk_seed=4, sigma=0.3)
+    cs = np.array([[[12.3, 32.3, 32.3, 12.3], [14.6, 14.6, 34.6, 34.6]]])
+    g = _gpu("affine", "esm", 1, resx=20, resy=20, epsilon=0.0)
+    g.initialize(cs, frames[0])
+    o = _oracle("affine", "esm", grad_mode=1, epsilon=0.0, resx=20, resy=20)
+    o.set_image(frames[0]); o.initialize(cs[0])
+    for fr in frames[1:]:
+        g.update(fr)
+        o.set_image(fr); o.update()
+        assert np.abs(g.getRegion()[0] - o.corners()).max() <= CORNER_ATOL_F32
+
+
+def test_f32_default_work_split_large_batch(seq384):
+    """720 patches: the library picks two warps per patch; fp32 and fp64 kernels side by side on every patch"""
+    from mtf_b200 import api, synth
+    frames, _ = seq384
+    cs = synth.make_patches(720, 20.7, 384, 384)
+    kw = dict(n_patches=len(cs), epsilon=0.0, resx=20, resy=20, hom_normalized_init=1)
+    ref = api.BatchTracker(api.make_params("ssd", "homography", "fclk", **kw))
+    g = api.BatchTracker(api.make_params("ssd", "homography", "fclk", precision="f32", **kw))
+    for t in (ref, g):
+        t.initialize(cs, frames[0])
+    for fr in frames[1:3]:
+        ref.update(fr); g.update(fr)
+        d = np.abs(g.getRegion() - ref.getRegion()).max(axis=(1, 2))
+        # 400 pixels per patch: a few weakly textured patches sit on flat minima; the bulk must agree tightly
+        assert np.median(d) <= 2e-4 and np.percentile(d, 99) <= CORNER_ATOL_F32 * 5, (np.median(d), d.max())
+    assert (g.patch_status() & 1 == 0).all()
+
+
+def test_f32_set_region_and_iterate_once(seq384):
+    frames, _ = seq384
+    cs = common.patches(4, 52.3, 384, 384, seed=8)
+    g = _gpu("homography", "fclk", len(cs), hom_normalized_init=1)
+    g.initialize(cs, frames[0])
+    g.update(frames[1])
+    moved = g.getRegion() + 0.37
+    g.setRegion(moved)
+    assert np.array_equal(g.getRegion(), moved)
+    J, H, f, dp = g.iterate_once()
+    assert np.isfinite(J).all() and np.isfinite(H).all() and np.isfinite(dp).all()
+    for i in range(len(cs)):
+        assert np.allclose(H[i], H[i].T, rtol=1e-12, atol=0) and (np.linalg.eigvalsh(-H[i]) > 0).all()
