@@ -134,6 +134,16 @@ mtfb_status mtfb_set_image(mtfb_ctx *ctx, const float *host_img, int h, int w, i
 /* same, frame already resident on the device (pitch in elements); the pointer is used, not copied */
 mtfb_status mtfb_set_image_device(mtfb_ctx *ctx, const float *dev_img, int h, int w, int pitch);
 
+/* replaces the pre-processing in front of setImage: utils::GaussianSmoothing (PreProcBase::processFrame for CV_32FC1,
+ * Utilities/src/preprocUtils.cc:108-127; pre_proc_type "gauss", gauss_kernel_size 5, gauss_sigma_x 3 of
+ * Config/parameters.h:229-235) applied to the RAW frame on the device: uint8, channels = 1 (gray) or 3 (BGR, converted with
+ * cv::cvtColor's float weights), row_stride in BYTES.  Uploads h x w x channels bytes instead of 4 h w, then behaves like
+ * mtfb_set_image with the smoothed float frame.  kernel_size must be 5; sigma > 0 (sigma_y = sigma_x as MTF passes it). */
+mtfb_status mtfb_set_image_u8(mtfb_ctx *ctx, const unsigned char *host_img, int h, int w, int row_stride, int channels,
+	int kernel_size, double sigma);
+/* the frame the trackers currently sample (after mtfb_set_image / mtfb_set_image_u8), h x w floats, contiguous; host pointer */
+mtfb_status mtfb_get_image(mtfb_ctx *ctx, float *out);
+
 /* replaces SearchMethod::initialize(corners) (SM/src/NT/FCLK.cc:102-169, NT/ESM.cc:110-146,
  * NT/ICLK.cc:71-127): ssm.setCorners (4-point DLT, Utilities/src/warpUtils.cc:171-223) + am.initializePixVals
  * + the SM-specific template gradients / Jacobians / Hessians, for all P patches, on the device. */

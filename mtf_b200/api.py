@@ -56,7 +56,8 @@ class IterLog(C.Structure):
 
 EXPORTS = [
     "mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_create", "mtfb_destroy",
-    "mtfb_set_stream", "mtfb_synchronize", "mtfb_set_image", "mtfb_set_image_device", "mtfb_initialize",
+    "mtfb_set_stream", "mtfb_synchronize", "mtfb_set_image", "mtfb_set_image_device", "mtfb_set_image_u8",
+    "mtfb_get_image", "mtfb_initialize",
     "mtfb_set_region", "mtfb_update", "mtfb_iterate_once", "mtfb_enable_iter_log", "mtfb_get_iter_log",
     "mtfb_pf_evaluate", "mtfb_pf_evaluate_device", "mtfb_get_corners", "mtfb_get_state", "mtfb_get_n_iters",
     "mtfb_get_similarity", "mtfb_get_patch_status", "mtfb_get_init_warp", "mtfb_get_init_pts",
@@ -87,6 +88,8 @@ def load_library(path=LIB_PATH):
     L.mtfb_synchronize.argtypes = [vp]
     L.mtfb_set_image.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.mtfb_set_image_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.mtfb_set_image_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.mtfb_get_image.argtypes = [vp, vp]
     L.mtfb_initialize.argtypes = [vp, dp]
     L.mtfb_set_region.argtypes = [vp, dp]
     L.mtfb_update.argtypes = [vp]
@@ -208,6 +211,25 @@ class BatchTracker:
         self._img = img
         self._check(self._L.mtfb_set_image(self._h, C.c_void_p(img.ctypes.data), img.shape[0], img.shape[1],
                                            img.strides[0] // 4))
+
+    def setRawImage(self, img, kernel_size=5, sigma=3.0):
+        """raw uint8 frame, h x w (gray) or h x w x 3 (BGR): the pre-processing MTF runs in front of setImage
+        (utils::GaussianSmoothing, preprocUtils.cc:108-127) is done on the device behind the upload"""
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and (img.shape[2] != 3 or img.strides[2] != 1)) \
+                or img.strides[1] != (1 if img.ndim == 2 else 3):
+            raise MTFError(1, "setRawImage: uint8 h x w or h x w x 3 array with contiguous rows required")
+        self._img = img
+        self._check(self._L.mtfb_set_image_u8(self._h, C.c_void_p(img.ctypes.data), img.shape[0], img.shape[1],
+                                              img.strides[0], 1 if img.ndim == 2 else 3, kernel_size, float(sigma)))
+
+    def set_raw_image_pinned(self, ptr, h, w, row_stride, channels, kernel_size=5, sigma=3.0):
+        self._check(self._L.mtfb_set_image_u8(self._h, C.c_void_p(ptr), h, w, row_stride, channels, kernel_size, float(sigma)))
+
+    def image(self, h, w):
+        """the float frame the trackers currently sample"""
+        out = np.empty((h, w), dtype=np.float32)
+        self._check(self._L.mtfb_get_image(self._h, C.c_void_p(out.ctypes.data)))
+        return out
 
     def set_image_pinned(self, ptr, h, w, row_stride):
         """host pointer variant (pinned buffers owned by the caller)"""

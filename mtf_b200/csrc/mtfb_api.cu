@@ -92,6 +92,7 @@ struct mtfb_ctx {
 	DevBatch b;
 	// owned device memory
 	float *d_img_own; size_t img_capacity;      // elements
+	unsigned char *d_raw; size_t raw_capacity;  // bytes: the raw uint8 frame of mtfb_set_image_u8
 	double *d_grid;                             // xv | yv | norm_corners
 	double *d_patch;                            // all per-patch fp64 arrays in one allocation
 	double *d_mi_tab;                           // MI: P x 32 histogram tables
@@ -130,7 +131,7 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaSetDevice(c->prm.device);
 	if(c->own_stream) cudaStreamSynchronize(c->own_stream);
 	cudaFree(c->d_img_own); cudaFree(c->d_grid); cudaFree(c->d_patch); cudaFree(c->d_ints);
-	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32);
+	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32); cudaFree(c->d_raw);
 	if(c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return MTFB_OK;
@@ -315,6 +316,56 @@ mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int
 		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->stream));
 	c->b.img = make_image(c->d_img_own, h, w, pitch);
 	c->have_image = true;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_set_image_u8(mtfb_ctx *c, const unsigned char *host_img, int h, int w, int row_stride, int channels, int kernel_size,
+	double sigma){
+	if(!c || !host_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8: null argument");
+	if(channels != 1 && channels != 3) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8: channels must be 1 (gray) or 3 (BGR)");
+	if(h < 3 || w < 3 || row_stride < w*channels) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8: bad geometry %d x %d x %d stride %d", h, w, channels, row_stride);
+	if(kernel_size != 5) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_set_image_u8: gauss_kernel_size %d (only the default 5 is implemented)", kernel_size);
+	if(!(sigma > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8: sigma must be > 0");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const int pitch = (w + 31) & ~31;
+	const size_t need = (size_t)pitch*h, raw_pitch = ((size_t)w*channels + 127) & ~(size_t)127, raw_need = raw_pitch*h;
+	if(need > c->img_capacity || raw_need > c->raw_capacity){
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(need > c->img_capacity){
+			cudaFree(c->d_img_own); c->d_img_own = nullptr; c->img_capacity = 0;
+			CUDA_TRY(cudaMalloc(&c->d_img_own, need*sizeof(float)));
+			c->img_capacity = need;
+		}
+		if(raw_need > c->raw_capacity){
+			cudaFree(c->d_raw); c->d_raw = nullptr; c->raw_capacity = 0;
+			CUDA_TRY(cudaMalloc(&c->d_raw, raw_need));
+			c->raw_capacity = raw_need;
+		}
+	}
+	CUDA_TRY(cudaMemcpy2DAsync(c->d_raw, raw_pitch, host_img, (size_t)row_stride, (size_t)w*channels, h, cudaMemcpyHostToDevice, c->stream));
+	// cv::getGaussianKernel(5, sigma, CV_32F) as OpenCV 2.4 / 3.x computes it
+	float k5[5];
+	{
+		const double scale2X = -0.5 / (sigma*sigma);
+		double sum = 0;
+		for(int i = 0; i < 5; ++i){ const double x = i - 2.0; k5[i] = (float)std::exp(scale2X*x*x); sum += k5[i]; }
+		sum = 1. / sum;
+		for(int i = 0; i < 5; ++i) k5[i] = (float)(k5[i] * sum);
+	}
+	CUDA_TRY(launch_preproc_gauss5(c->d_raw, (int)raw_pitch, channels, c->d_img_own, pitch, h, w, k5, c->stream));
+	++c->launches;
+	c->b.img = make_image(c->d_img_own, h, w, pitch);
+	c->have_image = true;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_get_image(mtfb_ctx *c, float *out){
+	if(!c || !out) return fail(MTFB_ERR_INVALID_ARG, "mtfb_get_image: null argument");
+	if(!c->have_image) return fail(MTFB_ERR_LOGIC, "mtfb_get_image: setImage has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)c->b.img.w*sizeof(float), c->b.img.data, (size_t)c->b.img.pitch*sizeof(float),
+		(size_t)c->b.img.w*sizeof(float), c->b.img.h, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return MTFB_OK;
 }
 

@@ -1549,6 +1549,69 @@ void orc_norm_unit_square_pts(int resx, int resy, double min_x, double min_y, do
 	getNormUnitSquarePts(pts2N, corners8, resx, resy, min_x, min_y, max_x, max_y);
 }
 
+// ---- pre-processing of the raw frame: what PreProcBase::processFrame does for output_type CV_32FC1
+// with the default GaussianSmoothing (Utilities/src/preprocUtils.cc:108-127, Utilities/include/mtf/Utilities/preprocUtils.h:67-78,
+// Config/include/mtf/Config/parameters.h:229-235: pre_proc_type "gauss", kernel 5, sigma 3):
+//   frame_raw.convertTo(CV_32F) -> cv::cvtColor(BGR2GRAY) (3-channel input) -> cv::GaussianBlur(ksize 5, sigma, sigma)
+// The arithmetic lives in OpenCV (not vendored by MTF; ReadMe.md:116 asks for 2.4 / 3.x), restated from its published
+// algorithm: gray = B*0.114f + G*0.587f + R*0.299f in float (imgproc color conversion, RGB2Gray<float>); the kernel of
+// cv::getGaussianKernel(5, sigma, CV_32F): exp(-x^2 / (2 sigma^2)) rounded to float, normalised by the double sum of the
+// floats; separable filtering, row pass then column pass through a float buffer, symmetric 5-tap form
+//   s = x0*k0 + (x-1 + x+1)*k1 + (x-2 + x+2)*k2       (SymmRowSmallVec_32f / SymmColumnSmallVec_32f32f)
+// borders BORDER_REFLECT_101 (cv::borderInterpolate).  OpenCV's SIMD builds fuse some of these multiply-adds, so cv2
+// itself reproduces this only to 1-2 ulp (tests/golden/make_preproc_golden.py, tests/test_preproc.py).
+void orc_gaussian_kernel5(double sigma, float *k5){
+	const double scale2X = -0.5 / (sigma*sigma);
+	double sum = 0;
+	for(int i = 0; i < 5; ++i){
+		const double x = i - 2.0;
+		k5[i] = (float)std::exp(scale2X*x*x);
+		sum += k5[i];
+	}
+	sum = 1. / sum;
+	for(int i = 0; i < 5; ++i) k5[i] = (float)(k5[i] * sum);
+}
+static inline int reflect101(int i, int n){
+	if(n == 1) return 0;
+	while(i < 0 || i >= n){ if(i < 0) i = -i; else i = 2 * n - 2 - i; }
+	return i;
+}
+void orc_preproc_gauss5(const unsigned char *img, int h, int w, int stride, int channels, double sigma, float *out){
+	float k[5];
+	orc_gaussian_kernel5(sigma, k);
+	const float k0 = k[2], k1 = k[1], k2 = k[0];
+	std::vector<float> gray((size_t)h*w), tmp((size_t)h*w);
+	for(int y = 0; y < h; ++y){
+		const unsigned char *r = img + (size_t)y*stride;
+		for(int x = 0; x < w; ++x){
+			if(channels == 3){
+				const float b = r[3 * x], g = r[3 * x + 1], rr = r[3 * x + 2];
+				float v = b*0.114f; v = v + g*0.587f; v = v + rr*0.299f;
+				gray[(size_t)y*w + x] = v;
+			} else gray[(size_t)y*w + x] = r[x];
+		}
+	}
+	for(int y = 0; y < h; ++y){
+		const float *a = &gray[(size_t)y*w];
+		for(int x = 0; x < w; ++x){
+			float s = a[x] * k0;
+			s = s + (a[reflect101(x - 1, w)] + a[reflect101(x + 1, w)])*k1;
+			s = s + (a[reflect101(x - 2, w)] + a[reflect101(x + 2, w)])*k2;
+			tmp[(size_t)y*w + x] = s;
+		}
+	}
+	for(int y = 0; y < h; ++y){
+		const float *c0 = &tmp[(size_t)y*w], *m1 = &tmp[(size_t)reflect101(y - 1, h)*w], *p1 = &tmp[(size_t)reflect101(y + 1, h)*w],
+			*m2 = &tmp[(size_t)reflect101(y - 2, h)*w], *p2 = &tmp[(size_t)reflect101(y + 2, h)*w];
+		for(int x = 0; x < w; ++x){
+			float s = c0[x] * k0;
+			s = s + (m1[x] + p1[x])*k1;
+			s = s + (m2[x] + p2[x])*k2;
+			out[(size_t)y*w + x] = s;
+		}
+	}
+}
+
 // GridTracker.cc:247-264 fan-out: independent trackers, one per patch, OpenMP over patches
 long orc_batch_track(const orc_params *p, const float *const *frames, int n_frames, int h, int w,
 	const double *corners, int n_patches, int n_threads, double *final_corners, int *iters_per_patch, double *seconds){

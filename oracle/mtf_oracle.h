@@ -119,6 +119,11 @@ void orc_colpiv_qr_solve(const double *A, const double *b, int n, double *x);
 void orc_norm_unit_square_pts(int resx, int resy, double min_x, double min_y,
 	double max_x, double max_y, double *pts2N, double *corners8);
 
+/* pre-processing (PreProcBase::processFrame with GaussianSmoothing, CV_32FC1 output): uint8 gray (channels 1) or BGR
+ * (channels 3) frame, stride in bytes -> h x w float.  orc_gaussian_kernel5 = cv::getGaussianKernel(5, sigma, CV_32F) */
+void orc_gaussian_kernel5(double sigma, float *k5);
+void orc_preproc_gauss5(const unsigned char *img, int h, int w, int stride, int channels, double sigma, float *out);
+
 /* batch drivers used as the CPU baseline: P independent trackers over the same image,
  * OpenMP over patches as GridTracker.cc:253-256 does.  Returns total LK iterations. */
 long orc_batch_track(const orc_params *p, const float *const *frames, int n_frames, int h, int w,

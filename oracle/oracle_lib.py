@@ -69,6 +69,8 @@ def lib():
         getattr(L, name).argtypes = [C.c_void_p, dp]
     L.orc_pf_evaluate.argtypes = [C.c_void_p, dp, C.c_int, dp, dp]
     L.orc_set_state.argtypes = [C.c_void_p, dp]
+    L.orc_gaussian_kernel5.argtypes = [C.c_double, fp]
+    L.orc_preproc_gauss5.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, fp]
     L.orc_pix_val.argtypes = [fp, C.c_int, C.c_int, C.c_double, C.c_double]; L.orc_pix_val.restype = C.c_double
     L.orc_get_pix_vals.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_get_img_grad.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
@@ -231,6 +233,22 @@ def img_grad_analytic(img, pts, grad_eps=1e-8, mult=1.0):
     out = np.empty(2 * pts.shape[0])
     lib().orc_get_img_grad_analytic(_fp(img), img.shape[0], img.shape[1], _dp(pts), pts.shape[0], grad_eps, mult, _dp(out))
     return out.reshape(2, -1).T
+
+
+def gaussian_kernel5(sigma=3.0):
+    k = np.empty(5, dtype=np.float32)
+    lib().orc_gaussian_kernel5(float(sigma), _fp(k))
+    return k
+
+
+def preproc_gauss5(img_u8, sigma=3.0):
+    """uint8 h x w (gray) or h x w x 3 (BGR) -> float32 h x w: convertTo + BGR2GRAY + GaussianBlur(5, sigma)"""
+    a = np.ascontiguousarray(img_u8, dtype=np.uint8)
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    h, w = a.shape[:2]
+    out = np.empty((h, w), dtype=np.float32)
+    lib().orc_preproc_gauss5(a.ctypes.data, h, w, a.strides[0], ch, float(sigma), _fp(out))
+    return out
 
 
 def homography_dlt(in_corners, out_corners):
