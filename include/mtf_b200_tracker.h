@@ -68,9 +68,17 @@ inline mtfb_params makeParams(const char *sm, const char *am, const char *ssm, i
 class Batch{
 public:
 	explicit Batch(const mtfb_params &params) : ctx(nullptr), prm(params), corners(8 * (size_t)params.n_patches, 0.0),
-		n_supplied(0), frame_id(0), updated_frame(-1){
+		n_supplied(0), frame_id(0), updated_frame(-1), raw_channels(0), gauss_kernel_size(5), gauss_sigma(3.0){
 		check(mtfb_create(&prm, &ctx));
 	}
+	//! Take RAW uint8 frames (channels = 1 gray / 3 BGR) and run MTF's default pre-processing -- utils::GaussianSmoothing,
+	//! Utilities/src/preprocUtils.cc:108-127, parameters.h:229-235 -- on the device behind the upload.  The application then
+	//! creates this tracker's pre-processor with pre_proc_type "none" (inputType() reports CV_8UC1 / CV_8UC3).
+	void useRawInput(int channels, int kernel_size = 5, double sigma = 3.0){
+		if(channels != 1 && channels != 3){ throw mtf::utils::InvalidArgument("mtf_b200 :: useRawInput :: channels must be 1 or 3"); }
+		raw_channels = channels; gauss_kernel_size = kernel_size; gauss_sigma = sigma;
+	}
+	int inputType() const{ return raw_channels == 3 ? CV_8UC3 : raw_channels == 1 ? CV_8UC1 : CV_32FC1; }
 	~Batch(){ mtfb_destroy(ctx); }
 	Batch(const Batch&) = delete;
 	Batch& operator=(const Batch&) = delete;
@@ -79,13 +87,18 @@ public:
 	//! TrackerBase::setImage: the reference keeps the cv::Mat header and re-reads the pixels on every call
 	//! (TrackerBase.h:21-26), so only the header is kept here and the upload happens in initialize()/update()
 	void setImage(const cv::Mat &img){
-		if(img.type() != CV_32FC1){ throw mtf::utils::InvalidArgument("mtf_b200 :: setImage :: CV_32FC1 image expected"); }
+		if(img.type() != inputType()){ throw mtf::utils::InvalidArgument("mtf_b200 :: setImage :: image type differs from inputType()"); }
 		curr_img = img;
 	}
 	void upload(){
 		if(curr_img.empty()){ throw mtf::utils::LogicError("mtf_b200 :: setImage has not been called"); }
-		check(mtfb_set_image(ctx, curr_img.ptr<float>(), curr_img.rows, curr_img.cols,
-			static_cast<int>(curr_img.step / sizeof(float))));
+		if(raw_channels){
+			check(mtfb_set_image_u8(ctx, curr_img.ptr<unsigned char>(), curr_img.rows, curr_img.cols,
+				static_cast<int>(curr_img.step), raw_channels, gauss_kernel_size, gauss_sigma));
+		} else{
+			check(mtfb_set_image(ctx, curr_img.ptr<float>(), curr_img.rows, curr_img.cols,
+				static_cast<int>(curr_img.step / sizeof(float))));
+		}
 		++frame_id;
 	}
 	//! all P regions at once: corners = P x (2 x 4) doubles
@@ -114,6 +127,8 @@ private:
 	cv::Mat curr_img;
 	std::vector<double> corners, pending;
 	int n_supplied, frame_id, updated_frame;
+	int raw_channels, gauss_kernel_size;
+	double gauss_sigma;
 };
 
 //! One patch tracked on the GPU; drop-in for nt::FCLK / nt::ESM / nt::ICLK (SM/src/NT/*.cc)
@@ -135,7 +150,7 @@ public:
 	void initialize(const cv::Mat &corners) override{ toArray(corners); batch.initialize(c8); publish(); }
 	void update() override{ batch.update(); publish(); }
 	void setRegion(const cv::Mat &corners) override{ toArray(corners); batch.setRegion(c8); publish(); }
-	int inputType() const override{ return CV_32FC1; }
+	int inputType() const override{ return batch.inputType(); }
 	Batch& getBatch(){ return batch; }
 private:
 	void toArray(const cv::Mat &corners){
@@ -174,7 +189,7 @@ public:
 		for(int k = 0; k < 8; ++k){ cv_corners_mat.at<double>(k / 4, k % 4) = r[k]; }
 		return cv_corners_mat;
 	}
-	int inputType() const override{ return CV_32FC1; }
+	int inputType() const override{ return batch->inputType(); }
 private:
 	std::shared_ptr<Batch> batch;
 	int id;

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <memory>
 #include <vector>
+#define CV_8UC1 0
+#define CV_8UC3 16
 #define CV_32FC1 5
 #define CV_64FC1 6
 namespace cv {
@@ -29,7 +31,7 @@ public:
 	template<class T> const T* ptr(int r = 0) const{ return reinterpret_cast<const T*>(data + r*step); }
 	void copyTo(Mat &o) const{ o.create(rows, cols, type_); for(int r = 0; r < rows; ++r) std::memcpy(o.data + r*o.step, data + r*step, cols*esz(type_)); }
 private:
-	static size_t esz(int t){ return t == CV_64FC1 ? 8 : 4; }
+	static size_t esz(int t){ return t == CV_64FC1 ? 8 : t == CV_8UC1 ? 1 : t == CV_8UC3 ? 3 : 4; }
 	int type_ = 0;
 	std::shared_ptr<std::vector<unsigned char>> store;
 };

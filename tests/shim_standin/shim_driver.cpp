@@ -43,6 +43,23 @@ int main(int argc, char **argv){
 			const cv::Mat &a = single[i]->getRegion(), &b = members[i]->getRegion();
 			for(int k = 0; k < 8; ++k) printf("%.17g %.17g\n", a.at<double>(k / 4, k % 4), b.at<double>(k / 4, k % 4));
 		}
+		// (3) raw uint8 frames with the pre-processing on the device (Batch::useRawInput), as an application would feed a
+		// tracker whose inputType() is CV_8UC1 through a "none" pre-processor
+		if(argc > 7 && !strcmp(argv[7], "raw")){
+			mtf::b200::Tracker raw(argv[3], argv[4], argv[5], res, res);
+			raw.getBatch().useRawInput(1);
+			if(raw.inputType() != CV_8UC1){ printf("BADTYPE\n"); }
+			cv::Mat img8(h, w, CV_8UC1);
+			auto load8 = [&](int t){ for(int r = 0; r < h; ++r) for(int c = 0; c < w; ++c){
+				float v = frames[((size_t)t*h + r)*w + c]; v = v < 0 ? 0 : (v > 255 ? 255 : v); img8.ptr<unsigned char>(r)[c] = (unsigned char)(v + 0.5f); } };
+			load8(0);
+			cv::Mat c(2, 4, CV_64FC1);
+			for(int k = 0; k < 8; ++k) c.at<double>(k / 4, k % 4) = corners[k];
+			raw.initialize(img8, c);
+			for(int t = 1; t < n; ++t){ load8(t); raw.update(); }
+			const cv::Mat &a = raw.getRegion();
+			for(int k = 0; k < 8; ++k) printf("RAW %.17g\n", a.at<double>(k / 4, k % 4));
+		}
 		// error contract: a bad corner matrix is an InvalidArgument exception, not a crash
 		try{ cv::Mat bad(3, 4, CV_64FC1); single[0]->initialize(bad); printf("NOEXC\n"); }
 		catch(const mtf::utils::Exception &e){ printf("EXC %s\n", e.type()); }

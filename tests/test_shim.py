@@ -40,7 +40,7 @@ def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
         f.write(struct.pack("iii", *frames.shape)); f.write(frames.tobytes())
     with open(cb, "wb") as f:
         f.write(struct.pack("i", len(cs))); f.write(np.ascontiguousarray(cs, dtype=np.float64).tobytes())
-    out = subprocess.check_output([exe, fb, cb, sm, am, ssm, str(res)], text=True).split("\n")
+    out = subprocess.check_output([exe, fb, cb, sm, am, ssm, str(res), "raw"], text=True).split("\n")
     vals = np.array([[float(x) for x in l.split()] for l in out if l and l[0] in "-0123456789"])
     single, member = vals[:, 0].reshape(len(cs), 2, 4), vals[:, 1].reshape(len(cs), 2, 4)
     assert "EXC InvalidArgument" in out
@@ -55,3 +55,13 @@ def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
     # count per patch, i.e. another summation order
     assert np.abs(member - ref).max() <= 1e-9
     assert np.abs(single - ref).max() <= 1e-6
+    # raw uint8 frames through Batch::useRawInput == the Python binding's setRawImage on the same bytes
+    raw = np.array([float(l.split()[1]) for l in out if l.startswith("RAW ")]).reshape(2, 4)
+    assert "BADTYPE" not in out
+    u8 = [np.floor(np.clip(f, 0, 255) + 0.5).astype(np.uint8) for f in frames]
+    t8 = api.BatchTracker(api.make_params(am, {"8": "homography", "6": "affine"}[ssm], sm, n_patches=1, resx=res, resy=res,
+                                          hess_type=hess))
+    t8.setRawImage(u8[0]); t8.initialize(cs[:1])
+    for t in (1, 2):
+        t8.setRawImage(u8[t]); t8.update()
+    assert np.abs(raw - t8.getRegion()[0]).max() <= 1e-9
