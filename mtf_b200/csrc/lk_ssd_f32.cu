@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(T) ssd_stage_f32_kernel(DevBatch b, StageTapsF
 #define MTFB_F32_U32 4      // pixels per trip at one warp per patch (<= 255 registers)
 #endif
 #ifndef MTFB_F32_U64
-#define MTFB_F32_U64 1      // ... at two or more warps per patch (<= 128 registers)
+#define MTFB_F32_U64 2      // ... at two or more warps per patch (<= 128 registers; 0.681 vs 0.702 ms with one pixel per trip)
 #endif
 #ifndef MTFB_F32_MINB128
 #define MTFB_F32_MINB128 4
@@ -836,7 +836,10 @@ template<int SSM, int SM, int T, int MINB, int U> static cudaError_t launch_one(
 #ifdef MTFB_F32_NO_WINDOW    // experiment: gather from the frame in global memory
 	win_bytes = 0;
 #endif
-	static bool configured = false;                  // per instantiation; attributes are per function and sticky
+	static bool configured_dev[64] = {};             // per instantiation and device; attributes are per function and sticky
+	int dev = 0;
+	cudaGetDevice(&dev);
+	bool &configured = configured_dev[dev & 63];
 	if(!configured){
 		cudaError_t e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 / MINB + 32 * 1024);
 		if(e != cudaSuccess) return e;

@@ -46,6 +46,16 @@ def main():
     lk("2: FCLK+SSD+Homography 1024 x 50x50", "ssd", "homography", "fclk", 1024, 50, 49.0, 30)
     lk("2': same with hom_normalized_init=1 (Config/modules.cfg)", "ssd", "homography", "fclk", 1024, 50, 49.0, 30, hom_normalized_init=1)
     lk("1': ESM+SSD+Homography 1024 x 50x50", "ssd", "homography", "esm", 1024, 50, 49.0, 30)
+    # the fp32-arithmetic precision (SSD): same configurations
+    lk("2 (F32): FCLK+SSD+Homography 1024 x 50x50", "ssd", "homography", "fclk", 1024, 50, 49.0, 30, precision="f32")
+    lk("2' (F32): same with hom_normalized_init=1", "ssd", "homography", "fclk", 1024, 50, 49.0, 30, hom_normalized_init=1, precision="f32")
+    lk("1' (F32): ESM+SSD+Homography 1024 x 50x50 (SumOfSelf: reference-basis QR)", "ssd", "homography", "esm", 1024, 50, 49.0, 30, precision="f32")
+    lk("(F32): ESM+SSD+Homography, CurrentSelf Hessian (local-basis solve)", "ssd", "homography", "esm", 1024, 50, 49.0, 30, precision="f32", hess_type=1)
+    lk("(F32): ICLK+SSD+Homography 1024 x 50x50", "ssd", "homography", "iclk", 1024, 50, 49.0, 30, precision="f32")
+    lk("(F32): FCLK+SSD+Affine 1024 x 50x50", "ssd", "affine", "fclk", 1024, 50, 49.0, 30, precision="f32")
+    lk("(F64): FCLK+SSD+Affine 1024 x 50x50", "ssd", "affine", "fclk", 1024, 50, 49.0, 30)
+    lk("(F64): ICLK+SSD+Homography 1024 x 50x50", "ssd", "homography", "iclk", 1024, 50, 49.0, 30)
+    lk("(F32): FCLK+SSD+Homography 1024 cells 25x25", "ssd", "homography", "fclk", 1024, 25, 25.0, 30, precision="f32")
     lk("3: ESM+NCC+Affine 1024 cells 10x10", "ncc", "affine", "esm", 1024, 10, 10.0, 30)
     lk("3: ESM+NCC+Affine 1024 cells 25x25", "ncc", "affine", "esm", 1024, 25, 25.0, 30)
     lk("4: ICLK+MI+Homography 1024 x 100x100 (one GPU's share of 8192 on 8)", "mi", "homography", "iclk", 1024, 100, 99.0, 30,
