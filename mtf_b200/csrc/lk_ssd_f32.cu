@@ -65,6 +65,12 @@ __device__ __forceinline__ double rcp_newton(double d){
 	return r;
 }
 
+// one Newton step: relative error ~4e-15, plenty for the pivots of a solve whose inputs carry fp32 rounding
+__device__ __forceinline__ double rcp_newton1(double d){
+	const double r = (double)rcp_approx((float)d);
+	return fma(fma(-d, r, 1.0), r, r);
+}
+
 // Centre and scale of the template points, from the corners of the initial region: x0, y0 = mean corner, s = the
 // largest |corner - centre| coordinate.  Any choice works (the basis map is exact algebra); this one puts the
 // template points into [-1, 1]^2.  hom_normalized_init: the template points are the unit grid itself.
@@ -197,13 +203,17 @@ template<int SSM> __device__ __forceinline__ void pass_constants(const DevBatch 
 __device__ __forceinline__ void window_decide(const DevBatch &b, const double *corners, bool have_window, int *wi){
 	wi[2] = 0; wi[3] = 0;
 	if(!have_window || b.img.w < F32_WIN || b.img.h < F32_WIN) return;
-	double x0 = corners[0], x1 = corners[0], y0 = corners[4], y1 = corners[4];
+	// fp32 is enough: the hull is widened by a pixel, and a sample the window misses takes the fp64 path anyway
+	float x0 = (float)corners[0], x1 = x0, y0 = (float)corners[4], y1 = y0;
 #pragma unroll
-	for(int i = 1; i < 4; ++i){ x0 = fmin(x0, corners[i]); x1 = fmax(x1, corners[i]); y0 = fmin(y0, corners[4 + i]); y1 = fmax(y1, corners[4 + i]); }
-	if(!(x0 > -1e6 && x1 < 1e6 && y0 > -1e6 && y1 < 1e6)) return;
-	const int ix0 = (int)floor(x0), ix1 = (int)floor(x1) + 1, iy0 = (int)floor(y0), iy1 = (int)floor(y1) + 1;
-	if(ix1 - ix0 + 1 > F32_WIN || iy1 - iy0 + 1 > F32_WIN) return;
-	const bool covered = wi[4] && ix0 >= wi[0] && ix1 <= wi[0] + F32_WIN - 1 && iy0 >= wi[1] && iy1 <= wi[1] + F32_WIN - 1;
+	for(int i = 1; i < 4; ++i){
+		const float cx = (float)corners[i], cy = (float)corners[4 + i];
+		x0 = fminf(x0, cx); x1 = fmaxf(x1, cx); y0 = fminf(y0, cy); y1 = fmaxf(y1, cy);
+	}
+	if(!(x0 > -1e6f && x1 < 1e6f && y0 > -1e6f && y1 < 1e6f)) return;
+	const int ix0 = (int)floorf(x0) - 1, ix1 = (int)floorf(x1) + 2, iy0 = (int)floorf(y0) - 1, iy1 = (int)floorf(y1) + 2;
+	if(ix1 - ix0 + 1 > F32_WIN + 2 || iy1 - iy0 + 1 > F32_WIN + 2) return;
+	const bool covered = wi[4] && ix0 + 1 >= wi[0] && ix1 - 1 <= wi[0] + F32_WIN - 1 && iy0 + 1 >= wi[1] && iy1 - 1 <= wi[1] + F32_WIN - 1;
 	if(!covered){
 		int ox = (ix0 + ix1 + 1) / 2 - F32_WIN / 2, oy = (iy0 + iy1 + 1) / 2 - F32_WIN / 2;
 		ox = ox < 0 ? 0 : (ox > b.img.w - F32_WIN ? b.img.w - F32_WIN : ox);
@@ -513,7 +523,7 @@ template<int S> __device__ __forceinline__ bool solve_local(int lane, const doub
 		double v[S];
 #pragma unroll
 		for(int i = 0; i < S; ++i) if(i != kk) v[i] = __shfl_sync(FULL_MASK, a[i], kk);
-		const double t = a[kk] * rcp_newton(ok ? piv : 1.0);
+		const double t = a[kk] * rcp_newton1(ok ? piv : 1.0);
 		a[kk] = t;
 #pragma unroll
 		for(int i = 0; i < S; ++i) if(i != kk) a[i] = fma(-v[i], t, a[i]);
@@ -532,6 +542,57 @@ template<int S> __device__ __forceinline__ bool solve_local(int lane, const doub
 	}
 	__syncwarp();
 	return true;
+}
+
+// entry (k, c) of the update's warp matrix getWarpFromState(dp) (Homography.cc:94-107, Affine.cc:117-131)
+template<int SSM> __device__ __forceinline__ double update_entry(const double *dp, int k, int c){
+	double u = (k == c) ? 1.0 : 0.0;
+	if(SSM == SSM_HOM){
+		const int idx = 3 * k + c;
+		if(idx < 8) u += dp[idx];
+	} else{
+		// [[1 + s2, s3, s0], [s4, 1 + s5, s1], [0, 0, 1]]
+		const int idx = (k == 0) ? (c == 0 ? 2 : c == 1 ? 3 : 0) : (c == 0 ? 4 : c == 1 ? 5 : 1);
+		if(k < 2) u += dp[idx];
+	}
+	return u;
+}
+// The tail of a pass once the state update is known, for the forward-compositional searches without
+// Levenberg-Marquardt and without an iteration log (what serial_step<.., PRESOLVED> does, spread over the lanes of the
+// warp instead of replicated on each): ssm.compositionalUpdate (Homography.cc:73-92, Affine.cc:90-107) with lane i < 9
+// on entry i of curr_warp . update, the four corners on lanes 0..3, the corner-change test (NT/FCLK.cc:331-343).
+template<int SSM> __device__ __forceinline__ int apply_update_lean(const DevBatch &b, int lane, double f, const double *s_dp,
+	double *s_W, double *s_corners, const double *s_init_corners, int &patch_status){
+	const int i = lane < 9 ? lane : 0, r = i / 3, c = i - 3 * r;
+	double Wn = s_W[3 * r] * update_entry<SSM>(s_dp, 0, c);
+	Wn = fma(s_W[3 * r + 1], update_entry<SSM>(s_dp, 1, c), Wn);
+	Wn = fma(s_W[3 * r + 2], update_entry<SSM>(s_dp, 2, c), Wn);
+	if(SSM == SSM_HOM){
+		const double d = __shfl_sync(FULL_MASK, Wn, 8);
+		Wn = (lane == 8) ? 1.0 : Wn * rcp_newton(d);
+	}
+	__syncwarp();
+	if(lane < 9) s_W[lane] = Wn;
+	__syncwarp();
+	double v = 0, nx = 0, ny = 0;
+	if(lane < 4){
+		const double px = s_init_corners[lane], py = s_init_corners[4 + lane];
+		double hx = fma(s_W[1], py, s_W[0] * px) + s_W[2], hy = fma(s_W[4], py, s_W[3] * px) + s_W[5];
+		if(SSM == SSM_HOM){
+			const double rz = rcp_newton(fma(s_W[7], py, s_W[6] * px) + s_W[8]);
+			hx *= rz; hy *= rz;
+		}
+		nx = hx; ny = hy;
+		const double dx = s_corners[lane] - nx, dy = s_corners[4 + lane] - ny;
+		v = fma(dx, dx, dy*dy);
+	}
+	v += __shfl_xor_sync(FULL_MASK, v, 1);
+	v += __shfl_xor_sync(FULL_MASK, v, 2);
+	const double upd_norm = __shfl_sync(FULL_MASK, v, 0);
+	if(lane < 4){ s_corners[lane] = nx; s_corners[4 + lane] = ny; }
+	if(!(upd_norm == upd_norm) || !(f == f)) patch_status |= MTFB_PATCH_NAN;
+	__syncwarp();
+	return upd_norm < b.epsilon ? CTRL_BREAK : CTRL_NEXT;
 }
 
 } // namespace f32
@@ -735,7 +796,8 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 		if(warp == 0){
 			f = -s_sum[0] / 2;
 			int ctrl;
-			if(solved) ctrl = serial_step<SSM, SM, true>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+			if(solved && SM != SM_ICLK) ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
+			else if(solved) ctrl = serial_step<SSM, SM, true>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
 				lm, patch_status, s_dp);
 			else ctrl = serial_step<SSM, SM, false>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
 				lm, patch_status);

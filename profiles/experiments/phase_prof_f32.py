@@ -7,7 +7,7 @@ from mtf_b200 import api, synth
 sys.argv = ["bench"]
 import bench
 frames, corners, order = bench.workload()
-for T in (32, 64, 128):
+for T in (64, 128):
     tr = api.BatchTracker(api.make_params("ssd", "homography", "fclk", n_patches=1024, max_iters=30, epsilon=0.0,
                                           threads_per_patch=T, precision="f32"))
     tr.initialize(corners, frames[0])

@@ -163,6 +163,32 @@ def test_f32_converged_corners(seq384, sm, ssm):
     assert (g.patch_status() & 1 == 0).all()
 
 
+@pytest.mark.parametrize("sm,hess", [("esm", "current_self"), ("esm", "initial_self"), ("iclk", "current_self"),
+                                     ("fclk", "initial_self")])
+@pytest.mark.parametrize("ssm", SSMS)
+def test_f32_other_hessians_converged(seq384, sm, hess, ssm):
+    """the Hessian choices next to each search method's default: pass-local ones take the local-basis solve (ESM / ICLK
+    CurrentSelf), stored ones the reference-basis QR (InitialSelf)"""
+    from mtf_b200 import api
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(4, 52.3, 384, 384, seed=15), common.quad_patches(4, 384, 384, seed=16)])
+    norm = 1 if ssm == "homography" else 0
+    h_gpu = (api.ESM_HESS if sm == "esm" else api.LK_HESS)[hess]
+    g = _gpu(ssm, sm, len(cs), epsilon=0.0, hom_normalized_init=norm, hess_type=h_gpu)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle(ssm, sm, grad_mode=1, epsilon=0.0, hom_normalized_init=norm, hess_type=h_gpu)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        got = g.getRegion()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            assert np.abs(got[i] - o.corners()).max() <= CORNER_ATOL_F32, (sm, hess, ssm, i, np.abs(got[i] - o.corners()).max())
+
+
 @pytest.mark.parametrize("ssm", SSMS)
 def test_f32_reference_stopping_rule(seq384, ssm):
     """shipped configuration (epsilon = 1e-4, hom_normalized_init = 0) against the reference's finite-difference mode"""
