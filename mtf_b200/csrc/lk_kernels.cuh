@@ -26,6 +26,7 @@ struct DevBatch {
 	int I0f_stride;              // elements per patch in I0f (N rounded up to 4: 16-byte aligned rows for the bulk copy)
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
 	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
+	double *ncc_tab;             // P x 64  NCC: template sums behind cmptInitHessian (sum D0 | sum D0 D0^T | sum I0cc D0)
 	double *f;                   // P       similarity
 	int *n_iters;                // P
 	int *status;                 // P

@@ -15,14 +15,30 @@
 
 namespace mtfb {
 
-template<int S, int SM> struct NccLayout {
+// STD: the pass also needs the sums behind NCC::cmptCurrHessian / cmptInitHessian (NCC.cc:282-336):
+// sum I0cc D (oC) for the current image, sum Itcb D0 (oB0) for the template
+template<int S, int SM, bool STD = false> struct NccLayout {
 	static constexpr int NH = S*(S + 1) / 2;
 	static constexpr bool CURR = (SM != SM_ICLK);          // needs the current-image Jacobian terms
 	static constexpr bool INIT = (SM != SM_FCLK);          // needs the template Jacobian term
 	static constexpr int oD = 0, oDD = oD + (CURR ? S : 0), oW = oDD + (CURR ? NH : 0), oB = oW + (CURR ? S : 0),
-		o0 = oB + (CURR ? S : 0), NA = o0 + (INIT ? S : 0);
+		o0 = oB + (CURR ? S : 0), oC = o0 + (INIT ? S : 0), oB0 = oC + ((STD && CURR) ? S : 0), NA = oB0 + ((STD && INIT) ? S : 0);
 	__host__ __device__ static constexpr int tri(int i, int j){ return i*S - i*(i - 1) / 2 + (j - i); }
 };
+
+// NCC::cmptCurrHessian (which = 0: ... + 3 u u^T) / cmptInitHessian (which = 1: ... + 3 w w^T) from sums, NCC.cc:282-336:
+//   Jc = (D - column mean) / b (b = |Itc| in BOTH, the reference's quirk),  u = Jc^T Itcb,  w = Jc^T I0cc,
+//   H = -f Jc^T Jc - u w^T - w u^T + 3 (u u^T | w w^T)
+// sD = sum D, sDD = sum D D^T (upper), sB = sum Itcb D, sC = sum I0cc D; thread e = (i, j) of S*S
+template<int S> __device__ __forceinline__ double ncc_std_hessian(int i, int j, const double *sD, const double *sDD, const double *sB,
+	const double *sC, double sum_itcb, double sum_i0cc, double f, double bnorm, int N, int which){
+	const int lo = i < j ? i : j, hi = i < j ? j : i;
+	const double mi = sD[i] / N, mj = sD[j] / N;
+	const double jcjc = ((sDD[lo*S - lo*(lo - 1) / 2 + (hi - lo)] - N*mi*mj) / bnorm) / bnorm;
+	const double ui = (sB[i] - mi*sum_itcb) / bnorm, uj = (sB[j] - mj*sum_itcb) / bnorm;
+	const double wi = (sC[i] - mi*sum_i0cc) / bnorm, wj = (sC[j] - mj*sum_i0cc) / bnorm;
+	return -f*jcjc - ui*wj - wi*uj + 3 * (which == 0 ? ui*uj : wi*wj);
+}
 
 // self Hessian from the accumulated sums (NCC.cc:337-389): thread e = (i, j) of S*S
 template<int S> __device__ __forceinline__ double ncc_self_hessian(int i, int j, const double *sD, const double *sDD,
@@ -104,12 +120,15 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 		b.Hinit[(size_t)p * 64 + j*S + i] = ncc_self_hessian<S>(i, j, s_sum + L::oD, s_sum + L::oDD, s_sum + L::oB, s2[1] / c, c, N);
 	}
 	if(tid == 0){ b.am_scal[(size_t)p * 8] = I0_mean; b.am_scal[(size_t)p * 8 + 1] = c; }
+	// the template sums NCC::cmptInitHessian is built from on every pass (ICLK Std, ESM SumOfStd)
+	for(int e = tid; e < S; e += T){ b.ncc_tab[(size_t)p * 64 + e] = s_sum[L::oD + e]; b.ncc_tab[(size_t)p * 64 + S + L::NH + e] = s_sum[L::oB + e]; }
+	for(int e = tid; e < L::NH; e += T) b.ncc_tab[(size_t)p * 64 + S + e] = s_sum[L::oDD + e];
 }
 
-template<int SSM, int SM, int T>
+template<int SSM, int SM, int T, bool STD>
 __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatch b){
 	constexpr int S = StateSize<SSM>::value;
-	typedef NccLayout<S, SM> L;
+	typedef NccLayout<S, SM, STD> L;
 	extern __shared__ __align__(16) double s_It[];                          // N current pixel values
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = b.N;
@@ -176,6 +195,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 					acc[L::oD + i] += D[i];
 					acc[L::oW + i] = fma(wt, D[i], acc[L::oW + i]);
 					acc[L::oB + i] = fma(Itcb, D[i], acc[L::oB + i]);
+					if(STD) acc[L::oC + i] = fma(I0cc, D[i], acc[L::oC + i]);
 #pragma unroll
 					for(int j = i; j < S; ++j) acc[L::oDD + L::tri(i, j)] = fma(D[i], D[j], acc[L::oDD + L::tri(i, j)]);
 				}
@@ -185,14 +205,24 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 				init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
 				const double w0 = div_by(Itcb - f*I0cc, c, rc) - mean_0;                 // df_dI0 (NCC.cc:174-182)
 #pragma unroll
-				for(int i = 0; i < S; ++i) acc[L::o0 + i] = fma(w0, D0[i], acc[L::o0 + i]);
+				for(int i = 0; i < S; ++i){
+					acc[L::o0 + i] = fma(w0, D0[i], acc[L::o0 + i]);
+					if(STD) acc[L::oB0 + i] = fma(Itcb, D0[i], acc[L::oB0 + i]);
+				}
 			}
 		}
 		block_reduce<L::NA, T>(acc, s_part, s_sum);
 		++n_passes;
 		for(int e = tid; e < S*S; e += T){
 			const int i = e % S, j = e / S;
-			if(L::CURR) s_Hc[j*S + i] = ncc_self_hessian<S>(i, j, s_sum + L::oD, s_sum + L::oDD, s_sum + L::oB, sum_itcb, bn, N);
+			if(STD){
+				// FCLK / ESM Std: cmptCurrHessian; ICLK Std: cmptInitHessian; ESM SumOfStd: half their sum (NT/ESM.cc:339-352)
+				const double *tab = b.ncc_tab + (size_t)p * 64;
+				double hc = 0, hi = 0;
+				if(L::CURR) hc = ncc_std_hessian<S>(i, j, s_sum + L::oD, s_sum + L::oDD, s_sum + L::oB, s_sum + L::oC, sum_itcb, sum_i0cc, f, bn, N, 0);
+				if(L::INIT) hi = ncc_std_hessian<S>(i, j, tab, tab + S, s_sum + L::oB0, tab + S + L::NH, sum_itcb, sum_i0cc, f, bn, N, 1);
+				s_Hc[j*S + i] = (SM == SM_ICLK) ? hi : (SM == SM_ESM && b.hess_type == MTFB_ESM_HESS_SUM_OF_STD) ? (hc + hi) * 0.5 : hc;
+			} else if(L::CURR) s_Hc[j*S + i] = ncc_self_hessian<S>(i, j, s_sum + L::oD, s_sum + L::oDD, s_sum + L::oB, sum_itcb, bn, N);
 			if(e < S){
 				// FCLK: df_dIt . dIt_dp (NCC.cc:252-266); ESM: (df_dIt . dIt_dp - df_dI0 . dI0_dp) / 2 (NCC.cc:268-280,
 				// NT/ESM.cc:308-309); ICLK: df_dI0 . dI0_dp (NCC.cc:236-250)
@@ -204,7 +234,9 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 		}
 		cta_sync<T>();
 		if(warp == 0){
-			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+			// STD: s_Hc is the complete Hessian of the pass
+			const int ctrl = STD ? serial_step<SSM, SM, false, 0>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+				lm, patch_status) : serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
 				lm, patch_status);
 			if(lane == 0) s_ctrl = ctrl;
 		}
@@ -232,13 +264,18 @@ cudaError_t launch_init_ncc(int ssm, int threads, const DevBatch &b, const doubl
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
-template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, cudaStream_t st){
+template<int SSM, int SM, int T, bool STD> static cudaError_t launch_one_s(const DevBatch &b, cudaStream_t st){
 	const size_t smem = (size_t)b.N * sizeof(double);
 	if(smem > 200 * 1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(ncc_update_kernel<SSM, SM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(ncc_update_kernel<SSM, SM, T, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
-	ncc_update_kernel<SSM, SM, T><<<b.P, T, smem, st>>>(b);
+	ncc_update_kernel<SSM, SM, T, STD><<<b.P, T, smem, st>>>(b);
 	return cudaGetLastError();
+}
+template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, cudaStream_t st){
+	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD)
+		: (b.hess_type == MTFB_LK_HESS_STD);
+	return std_hess ? launch_one_s<SSM, SM, T, true>(b, st) : launch_one_s<SSM, SM, T, false>(b, st);
 }
 template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, cudaStream_t st){
 	switch(threads){

@@ -30,7 +30,8 @@ template<int SM> __device__ __forceinline__ int hessian_select(int hess_type){
 // Writes s_W, s_corners, the log; returns CTRL_*.  All 32 lanes of warp 0 must call it.
 // PRESOLVED: the caller has solved for the state update already (s_dp[S]; lk_ssd_f32.cu solves in its own basis);
 // only valid without Levenberg-Marquardt.  s_J / s_Hc are then used for the log alone (may be null without a log).
-template<int SSM, int SM, bool PRESOLVED = false>
+// HSEL >= 0 overrides hessian_select (kernels that assemble the complete Hessian of the pass themselves).
+template<int SSM, int SM, bool PRESOLVED = false, int HSEL = -1>
 __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, int iter_id, int n_passes, double f,
 	const double *s_J, const double *s_Hc, double *s_W, double *s_corners, const double *s_init_corners,
 	LMState &lm, int &patch_status, const double *s_dp = nullptr){
@@ -81,7 +82,7 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 	} else if(!rejected){
 		lm.state_reset = false;
 		WarpColPivQR<S, S> qr;
-		const int hsel = hessian_select<SM>(b.hess_type);
+		const int hsel = HSEL >= 0 ? HSEL : hessian_select<SM>(b.hess_type);
 		const int jc = lane < S ? lane : 0;                      // column `lane` of the Hessian
 #pragma unroll
 		for(int i = 0; i < S; ++i){

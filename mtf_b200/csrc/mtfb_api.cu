@@ -49,13 +49,14 @@ bool combo_supported(const mtfb_params *p, const char **why){
 	if(!gn){ *why = "sm must be esm, fclk, iclk or pf"; return false; }
 	if(p->am == MTFB_AM_SSD) return true;
 	if(p->am == MTFB_AM_NCC){
-		// the self Hessians (NCC.cc:337-389) are implemented; the Std / Original / SumOfStd forms (NCC.cc:282-336) are not
+		// the self Hessians (NCC.cc:337-389) and the Std forms cmptCurrHessian / cmptInitHessian (NCC.cc:282-336) are
+		// implemented; ESM's Original Hessian / Jacobian (mean pixel Jacobian) and ICLK's CurrentSelf are not
 		bool ok;
-		if(p->sm == MTFB_SM_ESM) ok = p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS && (p->hess_type == MTFB_ESM_HESS_INITIAL_SELF ||
-			p->hess_type == MTFB_ESM_HESS_CURRENT_SELF || p->hess_type == MTFB_ESM_HESS_SUM_OF_SELF);
-		else if(p->sm == MTFB_SM_FCLK) ok = p->hess_type == MTFB_LK_HESS_INITIAL_SELF || p->hess_type == MTFB_LK_HESS_CURRENT_SELF;
-		else ok = p->hess_type == MTFB_LK_HESS_INITIAL_SELF;
-		if(!ok) *why = "NCC: only the self Hessians (and ESM's DiffOfJacs Jacobian) are implemented";
+		if(p->sm == MTFB_SM_ESM) ok = p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS && p->hess_type != MTFB_ESM_HESS_ORIGINAL &&
+			p->hess_type >= MTFB_ESM_HESS_INITIAL_SELF && p->hess_type <= MTFB_ESM_HESS_STD;
+		else if(p->sm == MTFB_SM_FCLK) ok = p->hess_type >= MTFB_LK_HESS_INITIAL_SELF && p->hess_type <= MTFB_LK_HESS_STD;
+		else ok = p->hess_type == MTFB_LK_HESS_INITIAL_SELF || p->hess_type == MTFB_LK_HESS_STD;
+		if(!ok) *why = "NCC: ESM's Original Hessian / Jacobian and ICLK's CurrentSelf Hessian are not implemented";
 		return ok;
 	}
 	if(p->am == MTFB_AM_MI){
@@ -216,7 +217,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		if(cudaMalloc(&c->d_grid, grid.size()*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemcpy(c->d_grid, grid.data(), grid.size()*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		// per-patch arrays
-		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32;
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64;
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -235,6 +236,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.f = q; q += (size_t)P;
 		b.am_scal = q; q += 8 * (size_t)P;
 		c->d_mi_tab = q; q += 32 * (size_t)P;
+		b.ncc_tab = q; q += 64 * (size_t)P;
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;

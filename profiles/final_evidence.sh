@@ -9,4 +9,4 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:ssd_update_f32 -s 3 -c 1 -f -o gpurun_out/prof_f32 python bench.py --one-arm --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:ssd_update_kernel -s 3 -c 1 -f -o gpurun_out/prof_f64 python bench.py --one-arm --precision f64 --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1
 ls -la gpurun_out | tail -n 12
-test -f scratch/pscale.py && python scratch/pscale.py > gpurun_out/pscale.txt 2>&1
+python profiles/experiments/pscale.py > gpurun_out/pscale.txt 2>&1
