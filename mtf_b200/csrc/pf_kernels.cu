@@ -18,7 +18,10 @@ namespace mtfb {
 // dynamic shared memory: I0[N] | gA[N] | gB[N] | (gC[N] for the homography)
 //   homography: (gA, gB, gC) = init_pts_hm = dlt . (u, v, 1)   (Homography.cc:68 keeps the DLT's third row)
 //   affine:     (gA, gB)     = init_pts    = dehomogenize(dlt . (u, v, 1))
-template<int SSM, int T>
+// AM = AM_NCC: am->updateSimilarity(false) is NCC.cc:124-161 (f = <I0c, Itc> / (|Itc| c)) and the likelihood NCC.cc:50-53
+// (exp(-alpha (1/f - 1)^2)); the template is staged centred (I0 - mean) and the three sums sum It, sum It^2,
+// sum I0c It of one sweep give a = sum I0c It - mean_t sum I0c and b^2 = sum It^2 - N mean_t^2.
+template<int SSM, int AM, int T>
 __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double *__restrict__ states, int n_particles,
 	double *__restrict__ likelihood, double *__restrict__ similarity, double alpha){
 	constexpr int S = StateSize<SSM>::value;
@@ -52,6 +55,19 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 	}
 	mbar_wait(&s_bar, 0);
 	__syncthreads();
+	__shared__ double s_i0c_part[T / 32];
+	double sum_i0c = 0, ncc_c = 1;
+	if(AM == AM_NCC){
+		const double I0_mean = b.am_scal[(size_t)obj * 8];
+		ncc_c = b.am_scal[(size_t)obj * 8 + 1];
+		double part = 0;
+		for(int i = tid; i < N; i += T){ const double v = s_I0[i] - I0_mean; s_I0[i] = v; part += v; }     // I0_cntr (NCC.cc:63-64)
+#pragma unroll
+		for(int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(FULL_MASK, part, off);
+		if(lane == 0) s_i0c_part[warp] = part;
+		__syncthreads();
+		for(int w = 0; w < T / 32; ++w) sum_i0c += s_i0c_part[w];
+	}
 	const int warps = T / 32;
 	for(int pi = blockIdx.x*warps + warp; pi < n_particles; pi += gridDim.x*warps){
 		const double *st = states + ((size_t)obj*n_particles + pi)*S;
@@ -59,7 +75,7 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 #pragma unroll
 		for(int s = 0; s < S; ++s) sv[s] = st[s];
 		const Mat3 W = warp_from_state<SSM>(sv);
-		double acc = 0;
+		double acc = 0, acc_t = 0, acc_tt = 0;
 		for(int pix = lane; pix < N; pix += 32){
 			double wx, wy;
 			if(SSM == SSM_HOM){
@@ -74,22 +90,42 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 				wx = W.m[0] * ix; wx = wx + W.m[1] * iy; wx = wx + W.m[2] * 1.0;
 				wy = W.m[3] * ix; wy = wy + W.m[4] * iy; wy = wy + W.m[5] * 1.0;
 			}
-			const double d = sample_pixel(b.img, wx, wy) - s_I0[pix];
-			acc = fma(d, d, acc);
+			const double It = sample_pixel(b.img, wx, wy);
+			if(AM == AM_NCC){
+				acc = fma(s_I0[pix], It, acc); acc_t += It; acc_tt = fma(It, It, acc_tt);
+			} else{
+				const double d = It - s_I0[pix];
+				acc = fma(d, d, acc);
+			}
 		}
 #pragma unroll
-		for(int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, off);
+		for(int off = 16; off >= 1; off >>= 1){
+			acc += __shfl_xor_sync(FULL_MASK, acc, off);
+			if(AM == AM_NCC){ acc_t += __shfl_xor_sync(FULL_MASK, acc_t, off); acc_tt += __shfl_xor_sync(FULL_MASK, acc_tt, off); }
+		}
 		if(lane == 0){
-			const double f = -acc / 2;
+			double f, lik;
+			if(AM == AM_NCC){
+				const double mean_t = acc_t / N;
+				const double a = acc - mean_t*sum_i0c, bb = acc_tt - N*mean_t*mean_t;
+				// a particle that samples a constant (e.g. thrown out of the image: 128 everywhere) has Itc = 0: the reference's
+				// 0 / 0.  The one-sweep variance only knows that to rounding, so "constant" is bb <= 1e-12 sum It^2
+				f = (bb > 1e-12*acc_tt) ? a / (sqrt(bb) * ncc_c) : nan("");
+				const double d = (1.0 / f) - 1;
+				lik = exp(-alpha * d*d);
+			} else{
+				f = -acc / 2;
+				lik = exp(-alpha * sqrt(-f / double(N)));
+			}
 			if(similarity) similarity[(size_t)obj*n_particles + pi] = f;
-			if(likelihood) likelihood[(size_t)obj*n_particles + pi] = exp(-alpha * sqrt(-f / double(N)));
+			if(likelihood) likelihood[(size_t)obj*n_particles + pi] = lik;
 		}
 	}
 }
 
 cudaError_t launch_pf_evaluate(int am, int ssm, const DevBatch &b, const double *d_states, int n_particles,
 	double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st){
-	if(am != AM_SSD) return cudaErrorNotSupported;
+	if(am != AM_SSD && am != AM_NCC) return cudaErrorNotSupported;
 	constexpr int T = 256;
 	const size_t smem = (size_t)b.N * 8 * (ssm == SSM_HOM ? 4 : 3);
 	if(smem > 220 * 1024) return cudaErrorInvalidValue;
@@ -103,16 +139,14 @@ cudaError_t launch_pf_evaluate(int am, int ssm, const DevBatch &b, const double 
 	if(per_obj > max_useful) per_obj = max_useful;
 	if(per_obj < 1) per_obj = 1;
 	dim3 grid(per_obj, b.P);
-	cudaError_t e;
-	if(ssm == SSM_HOM){
-		e = cudaFuncSetAttribute(pf_evaluate_kernel<SSM_HOM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if(e != cudaSuccess) return e;
-		pf_evaluate_kernel<SSM_HOM, T><<<grid, T, smem, st>>>(b, d_states, n_particles, d_likelihood, d_similarity, alpha);
-	} else{
-		e = cudaFuncSetAttribute(pf_evaluate_kernel<SSM_AFF, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if(e != cudaSuccess) return e;
-		pf_evaluate_kernel<SSM_AFF, T><<<grid, T, smem, st>>>(b, d_states, n_particles, d_likelihood, d_similarity, alpha);
-	}
+	cudaError_t e = cudaSuccess;
+#define MTFB_PF_LAUNCH(SSM_, AM_) do{ \
+		e = cudaFuncSetAttribute(pf_evaluate_kernel<SSM_, AM_, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+		if(e != cudaSuccess) return e; \
+		pf_evaluate_kernel<SSM_, AM_, T><<<grid, T, smem, st>>>(b, d_states, n_particles, d_likelihood, d_similarity, alpha); }while(0)
+	if(ssm == SSM_HOM){ if(am == AM_NCC) MTFB_PF_LAUNCH(SSM_HOM, AM_NCC); else MTFB_PF_LAUNCH(SSM_HOM, AM_SSD); }
+	else{ if(am == AM_NCC) MTFB_PF_LAUNCH(SSM_AFF, AM_NCC); else MTFB_PF_LAUNCH(SSM_AFF, AM_SSD); }
+#undef MTFB_PF_LAUNCH
 	return cudaGetLastError();
 }
 
