@@ -500,11 +500,16 @@ template<int SSM, int SM> __device__ __forceinline__ void accumulate_pixel(const
 	acc.add(r, wj, Jj, Jt, need_grad);
 }
 
-// Solve (J_loc^T J_loc) x = g for the state update in the LOCAL basis by Gauss-Jordan elimination without pivoting
-// (the matrix is symmetric positive definite and, in this basis, well conditioned), one column per lane, rhs on lane S;
-// then map to the reference's parameters: dp = T^-1 x.  Returns false (uniformly) if a pivot is not safely positive --
-// the caller then takes the reference's rank-revealing QR in the reference basis.
+// Solve (J_loc^T J_loc) x = g for the state update in the LOCAL basis, one column per lane, rhs on lane S; then map to
+// the reference's parameters: dp = T^-1 x.  Returns false (uniformly) if a pivot is not safely positive -- the caller then
+// takes the reference's rank-revealing QR in the reference basis.
 // In exact arithmetic dp equals the reference's -H^-1 J^T (NT/FCLK.cc:298): H = -T^T A T, J^T = T^T g.
+//
+// The matrix is symmetric positive definite and, in this basis, well conditioned: Gauss-Jordan without pivoting, each
+// pivot row normalised by a reciprocal (fp32 seed + one Newton step).
+// MTFB_F32_BAREISS (experiment builds) selects the fraction-free form a_ij <- (a_kk a_ij - a_ik a_kj) / a_(k-1)(k-1), whose
+// only division is by the PREVIOUS pivot, i.e. off the dependent chain -- measured slower (0.657 vs 0.640 ms per frame):
+// three fp64 operations per entry instead of one load the shared fp64 pipe more than the shorter chain saves.
 template<int S> __device__ __forceinline__ bool solve_local(int lane, const double *s_sum, const double *s_Tinv, double g_scale, double *s_x,
 	double *s_dp){
 	typedef AccLayout<S> L;
@@ -512,6 +517,7 @@ template<int S> __device__ __forceinline__ bool solve_local(int lane, const doub
 	const int j = lane < S ? lane : 0;
 #pragma unroll
 	for(int i = 0; i < S; ++i) a[i] = (lane == S) ? s_sum[1 + i] * g_scale : s_sum[1 + S + L::tri(i < j ? i : j, i < j ? j : i)];
+#ifndef MTFB_F32_BAREISS
 	double dmax = 0;
 #pragma unroll
 	for(int i = 0; i < S; ++i) dmax = fmax(dmax, s_sum[1 + S + L::tri(i, i)]);
@@ -529,16 +535,59 @@ template<int S> __device__ __forceinline__ bool solve_local(int lane, const doub
 		for(int i = 0; i < S; ++i) if(i != kk) a[i] = fma(-v[i], t, a[i]);
 	}
 	if(!ok) return false;
+#else
+	// Jacobi scaling: s_i ~ 1 / sqrt(A_ii) (any positive scaling is exact algebra; fp32 rsqrt is plenty)
+	float sc[S];
+	{
+		float mine = 0.0f;
+#pragma unroll
+		for(int i = 0; i < S; ++i) if(lane == i) mine = (float)a[i];
+		mine = rsqrtf(mine);
+#pragma unroll
+		for(int i = 0; i < S; ++i) sc[i] = __shfl_sync(FULL_MASK, mine, i);
+	}
+	bool ok = true;
+#pragma unroll
+	for(int i = 0; i < S; ++i) ok = ok && (sc[i] > 0.0f) && (sc[i] < 1e18f);          // diagonal finite and positive
+	{
+		double my_s = 1.0;
+#pragma unroll
+		for(int i = 0; i < S; ++i) if(lane == i) my_s = (double)sc[i];
+#pragma unroll
+		for(int i = 0; i < S; ++i) a[i] = a[i] * ((double)sc[i] * my_s);              // rhs lane: my_s = 1
+	}
+	double rprev = 1.0;
+#pragma unroll
+	for(int kk = 0; kk < S; ++kk){
+		const double piv = __shfl_sync(FULL_MASK, a[kk], kk);
+		ok = ok && (piv * rprev > 1e-11);                                             // the ordinary pivot of the unit-diagonal matrix
+		double v[S];
+#pragma unroll
+		for(int i = 0; i < S; ++i) if(i != kk) v[i] = __shfl_sync(FULL_MASK, a[i], kk);
+		const double akk = a[kk];
+#pragma unroll
+		for(int i = 0; i < S; ++i) if(i != kk) a[i] = fma(piv, a[i], -(v[i] * akk)) * rprev;
+		rprev = rcp_newton1(ok ? piv : 1.0);                                          // needed one step later
+	}
+	if(!ok) return false;
+	// every diagonal entry is now det (= the last pivot): x~ = rhs / det, x = diag(s) x~
+	{
+		const double det = __shfl_sync(FULL_MASK, a[S - 1], S - 1);
+		const double rdet = rcp_newton(det);
+#pragma unroll
+		for(int i = 0; i < S; ++i) a[i] = a[i] * rdet * (double)sc[i];
+	}
+#endif
 	if(lane == S){
 #pragma unroll
 		for(int i = 0; i < S; ++i) s_x[i] = a[i];
 	}
 	__syncwarp();
 	if(lane < S){
-		double d = 0;
+		double d0 = 0, d1 = 0;
 #pragma unroll
-		for(int m = 0; m < S; ++m) d = fma(s_Tinv[lane*S + m], s_x[m], d);
-		s_dp[lane] = d;
+		for(int m = 0; m < S; m += 2){ d0 = fma(s_Tinv[lane*S + m], s_x[m], d0); d1 = fma(s_Tinv[lane*S + m + 1], s_x[m + 1], d1); }
+		s_dp[lane] = d0 + d1;
 	}
 	__syncwarp();
 	return true;
