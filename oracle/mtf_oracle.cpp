@@ -42,7 +42,11 @@ static inline double now_s(){
 // Utilities/include/mtf/Utilities/imgUtils.h:51-113
 // ---------------------------------------------------------------------------------------------
 static inline bool checkOverflow(double x, double y, unsigned int h, unsigned int w){
-	return ((x < 0) || (x >= w) || (y < 0) || (y >= h));                       // imgUtils.h:51-53
+	// imgUtils.h:51-53 is ((x < 0) || (x >= w) || (y < 0) || (y >= h)).  Written here so that a NaN coordinate counts as
+	// outside: the reference then goes on to static_cast<int>(NaN), undefined behaviour that on x86 yields INT_MIN and is
+	// caught by its second checkOverflow(lx, ly) -- unless the optimiser, entitled to assume lx >= 0 after the first check,
+	// removes that test (gcc 13 -O3 does: out-of-bounds read).  Same result for every non-NaN input.
+	return !((x >= 0) && (x < w) && (y >= 0) && (y < h));
 }
 // getPixVal<InterpType::Linear, BorderType::Constant>                          imgUtils.h:91-113
 static inline double getPixVal(const float *img, double x, double y,

@@ -330,3 +330,51 @@ def test_f32_set_region_and_iterate_once(seq384):
     assert np.isfinite(J).all() and np.isfinite(H).all() and np.isfinite(dp).all()
     for i in range(len(cs)):
         assert np.allclose(H[i], H[i].T, rtol=1e-12, atol=0) and (np.linalg.eigvalsh(-H[i]) > 0).all()
+
+
+@pytest.mark.parametrize("sm", ["fclk", "esm"])
+def test_f32_levenberg_marquardt(seq384, sm):
+    """LM damping is not basis invariant: with leven_marq the fp32 kernel maps its sums to the reference basis and runs the
+    reference's damped QR solve and accept / reject logic (NT/FCLK.cc:187-296)"""
+    frames, _ = seq384
+    cs = common.patches(6, 52.3, 384, 384, seed=17)
+    g = _gpu("homography", sm, len(cs), leven_marq=1, hom_normalized_init=1, epsilon=0.0)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("homography", sm, grad_mode=1, leven_marq=1, hom_normalized_init=1, epsilon=0.0)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs, got = g.iter_log(), g.getRegion()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            assert np.abs(got[i] - o.corners()).max() <= CORNER_ATOL_F32
+            # accept / reject compares f with the previous pass's f: the same decisions while f still moves by more than
+            # fp32 noise (the first passes); near convergence the comparison is a tie that fp32 rounding may break either way
+            assert [e["rejected"] for e in logs[i][:3]] == [e["rejected"] for e in o.log()[:3]]
+
+
+def test_f32_textureless_patch_is_survivable(seq384):
+    """a patch on a constant region has J = 0 and H = 0: the local solve declines (no positive pivot) and the reference's QR
+    divides 0 by 0 exactly as Eigen's does (its rank threshold is relative to the largest column norm, 0 here) -- the patch
+    goes NaN, is flagged, costs bounded time, and its neighbours in the batch are unaffected"""
+    frames, _ = seq384
+    flat = [f.copy() for f in frames[:2]]
+    for f in flat:
+        f[100:190, 100:190] = 77.0
+    cs = common.patches(3, 52.3, 384, 384, seed=19)
+    cs[1] = np.array([[110.2, 162.5, 162.5, 110.2], [112.4, 112.4, 164.7, 164.7]])
+    g = _gpu("homography", "fclk", len(cs), max_iters=5)
+    g.initialize(cs, flat[0])
+    g.update(flat[1])
+    got, st = g.getRegion(), g.patch_status()
+    assert (st[1] & 1) and not np.isfinite(got[1]).any()                  # MTFB_PATCH_NAN
+    o = _oracle("homography", "fclk", grad_mode=1, max_iters=5)
+    o.set_image(flat[0]); o.initialize(cs[1]); o.set_image(flat[1]); o.update()
+    assert not np.isfinite(o.corners()).any()                             # so does the reference
+    ref = _gpu("homography", "fclk", 2, max_iters=5)
+    ref.initialize(cs[[0, 2]], flat[0]); ref.update(flat[1])
+    assert np.abs(got[[0, 2]] - ref.getRegion()).max() <= 1e-9
