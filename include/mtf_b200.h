@@ -57,8 +57,8 @@ enum { MTFB_LK_HESS_INITIAL_SELF = 0, MTFB_LK_HESS_CURRENT_SELF = 1, MTFB_LK_HES
  *        to the reference's Eigen path; Jacobian / Hessian to summation order.
  *   F32: fp32 per-pixel arithmetic in patch-local coordinates with BIT-EXACT SAMPLING INDICES (pixels whose fp32
  *        coordinate is within the fp32 error bound of a cell boundary are re-evaluated in fp64), fp64 reduction and
- *        solve; Jacobian / Hessian / corners agree with F64 to fp32 tolerance.  SSD, chained
- *        warp only. */
+ *        solve; Jacobian / Hessian / corners agree with F64 to fp32 tolerance.  SSD only: ESM / FCLK /
+ *        ICLK with the chained warp, and PF particle evaluation. */
 enum { MTFB_PRECISION_F64 = 0, MTFB_PRECISION_F32 = 1 };
 /* per-patch status bits reported by mtfb_get_patch_status */
 enum { MTFB_PATCH_OK = 0, MTFB_PATCH_NAN = 1, MTFB_PATCH_SINGULAR = 2, MTFB_PATCH_OUT_OF_IMAGE = 4 };

@@ -868,6 +868,109 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Particle evaluation in the F32 precision (the body of the particle loop of nt::PF::update, SM/src/NT/PF.cc:303-320:
+// ssm->setState -> am->updatePixVals -> am->updateSimilarity(false) -> am->getLikelihood(), SSD.h:41-43): the same
+// patch-local fp32 geometry, guard band and bit-exact sampling indices as the Gauss-Newton kernel above; a particle's
+// warp takes the place of a pass's warp (pass_constants once per particle, by the warp that evaluates it).
+// One CTA = one object's template (fp32 row staged by one bulk async copy) and a slice of its particles; one warp per
+// particle, lanes stride over the pixels; the sum of squares is fp32 per lane (<= N / 32 terms), fp64 across lanes.
+// ------------------------------------------------------------------------------------------------
+template<int SSM, int T>
+__global__ void __launch_bounds__(T) pf_evaluate_f32_kernel(DevBatch b, const double *__restrict__ states, int n_particles,
+	double *__restrict__ likelihood, double *__restrict__ similarity, double alpha){
+	constexpr int S = StateSize<SSM>::value;
+	constexpr int NW = T / 32;
+	const int obj = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int N = b.N;
+	extern __shared__ __align__(16) float s_tmpl[];
+	__shared__ __align__(8) unsigned long long s_bar;
+	__shared__ double s_dlt[9], s_ic[8], s_T[S*S], s_Tinv[S*S], s_loc[3], s_Wid[9];
+	__shared__ double s_W[NW][9];
+	__shared__ float s_cf0[C_COUNT], s_dl[9], s_cf[NW][C_COUNT];
+	__shared__ int s_ci0[2], s_ci[NW][2];
+	if(tid == 0) mbar_init(&s_bar, 1);
+	if(tid < 9){ s_dlt[tid] = b.dlt[(size_t)obj * 9 + tid]; s_Wid[tid] = (tid % 4 == 0) ? 1.0 : 0.0; }
+	if(tid < 8) s_ic[tid] = b.init_corners[(size_t)obj * 8 + tid];
+	__syncthreads();
+	if(tid == 0){
+		const unsigned bytes = (unsigned)b.I0f_stride * (unsigned)sizeof(float);
+		mbar_expect_tx(&s_bar, bytes);
+		bulk_copy_g2s(s_tmpl, b.I0f + (size_t)obj*b.I0f_stride, bytes, &s_bar);
+	}
+	// the object's template frame and centred DLT rows (the per-particle constants come later)
+	if(warp == 0) patch_setup<SSM>(b, lane, s_Wid, s_dlt, s_ic, s_loc, s_T, s_Tinv, s_dl, s_cf0, s_ci0);
+	__syncthreads();
+	float dl[9];
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dl[i] = s_dl[i];
+	const bool dlt_affine = (dl[6] == 0.0f) && (dl[7] == 0.0f);
+	mbar_wait(&s_bar, 0);
+	for(int pi = blockIdx.x*NW + warp; pi < n_particles; pi += gridDim.x*NW){
+		const double *st = states + ((size_t)obj*n_particles + pi)*S;
+		// ssm->setState: curr_warp = getWarpFromState(state) (ProjectiveBase.cc:41-49, Affine.cc:109-115)
+		if(lane < 9){
+			const int r = lane / 3, c = lane - 3 * r;
+			s_W[warp][lane] = update_entry<SSM>(st, r, c);
+		}
+		__syncwarp();
+		pass_constants<SSM>(b, lane, s_W[warp], s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf[warp], s_ci[warp]);
+		__syncwarp();
+		PassConst k;
+#pragma unroll
+		for(int i = 0; i < 9; ++i) k.m[i] = s_cf[warp][C_M + i];
+#pragma unroll
+		for(int i = 0; i < 6; ++i) k.a[i] = s_cf[warp][C_A + i];
+		k.delta = s_cf[warp][C_DELTA]; k.lox = s_cf[warp][C_LOX]; k.hix = s_cf[warp][C_HIX]; k.loy = s_cf[warp][C_LOY]; k.hiy = s_cf[warp][C_HIY];
+		k.X0 = s_ci[warp][0]; k.Y0 = s_ci[warp][1];
+		k.base = b.img.data; k.pitch = b.img.pitch; k.Xr = k.X0; k.Yr = k.Y0;
+		float acc = 0.0f;
+		for(PixIterF it(lane, 32, b.resx); it.pix < N; it.next(32)){
+			PixF px;
+			front_fast<SSM>(b, k, dl, dlt_affine, it.rowf, it.colf, px);
+			if(!px.fast) front_exact<SSM>(b, k, s_dlt, s_W[warp], it.rowf, it.colf, px);
+			const float d = px.val - s_tmpl[it.pix];
+			acc = fmaf(d, d, acc);
+		}
+		double accd = (double)acc;
+#pragma unroll
+		for(int off = 16; off >= 1; off >>= 1) accd += __shfl_xor_sync(FULL_MASK, accd, off);
+		if(lane == 0){
+			const double f = -accd / 2;                                      // SSDBase.cc:94
+			if(similarity) similarity[(size_t)obj*n_particles + pi] = f;
+			if(likelihood) likelihood[(size_t)obj*n_particles + pi] = exp(-alpha * sqrt(-f / double(N)));
+		}
+		__syncwarp();
+	}
+}
+
+cudaError_t launch_pf_evaluate_f32(int ssm, const DevBatch &b, const double *d_states, int n_particles, double *d_likelihood,
+	double *d_similarity, double alpha, cudaStream_t st){
+	constexpr int T = 256;
+	const size_t smem = (size_t)b.I0f_stride*sizeof(float);
+	if(smem > 160 * 1024) return cudaErrorInvalidValue;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	// enough CTAs per object to fill the machine (4 CTAs of 8 warps per SM), never more than one particle per warp
+	int per_obj = (sms * 4 + b.P - 1) / b.P;
+	const int max_useful = (n_particles + T / 32 - 1) / (T / 32);
+	if(per_obj > max_useful) per_obj = max_useful;
+	if(per_obj < 1) per_obj = 1;
+	const dim3 grid(per_obj, b.P);
+	cudaError_t e;
+	if(ssm == SSM_HOM){
+		e = cudaFuncSetAttribute(pf_evaluate_f32_kernel<SSM_HOM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return e;
+		pf_evaluate_f32_kernel<SSM_HOM, T><<<grid, T, smem, st>>>(b, d_states, n_particles, d_likelihood, d_similarity, alpha);
+	} else{
+		e = cudaFuncSetAttribute(pf_evaluate_f32_kernel<SSM_AFF, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return e;
+		pf_evaluate_f32_kernel<SSM_AFF, T><<<grid, T, smem, st>>>(b, d_states, n_particles, d_likelihood, d_similarity, alpha);
+	}
+	return cudaGetLastError();
+}
+
 // debug tap of the fp32 front end at the current state: sampling indices (lx, ly; -1 = outside the image), pixel
 // value, image gradient, reference-basis Jacobian row (through the basis map) and the fast path's coordinate error
 template<int SSM, int T>

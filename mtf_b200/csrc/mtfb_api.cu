@@ -155,9 +155,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: precision must be MTFB_PRECISION_F64 or MTFB_PRECISION_F32");
 	if(p->precision == MTFB_PRECISION_F32){
 		const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
-		if(p->am != MTFB_AM_SSD || !gn || !(p->chained_warp || !p->nt_semantics))
-			return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 is implemented for SSD with ESM / FCLK / ICLK and the "
-				"chained warp; use MTFB_PRECISION_F64");
+		const bool pf = p->sm == MTFB_SM_PF;
+		if(p->am != MTFB_AM_SSD || !(gn || pf) || (gn && !(p->chained_warp || !p->nt_semantics)))
+			return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 is implemented for SSD with ESM / FCLK / ICLK (chained "
+				"warp) and PF; use MTFB_PRECISION_F64");
 		if(!(p->grad_eps < 1e-6)) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 needs grad_eps < 1e-6 (the fp32 "
 			"path returns the cell slope, the eps -> 0 limit of the reference's finite difference)");
 	}
@@ -492,8 +493,11 @@ mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *c, const double *d_states, int n_p
 	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_pf_evaluate_device: initialize has not been called");
 	if(c->prm.am != MTFB_AM_SSD && c->prm.am != MTFB_AM_NCC) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate_device: implemented for SSD and NCC");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
-	CUDA_TRY(launch_pf_evaluate(c->prm.am, c->prm.ssm, c->b, d_states, n_particles, d_likelihood, d_similarity,
-		c->prm.likelihood_alpha, c->stream));
+	if(c->prm.precision == MTFB_PRECISION_F32)
+		CUDA_TRY(launch_pf_evaluate_f32(c->prm.ssm, c->b, d_states, n_particles, d_likelihood, d_similarity, c->prm.likelihood_alpha, c->stream));
+	else
+		CUDA_TRY(launch_pf_evaluate(c->prm.am, c->prm.ssm, c->b, d_states, n_particles, d_likelihood, d_similarity,
+			c->prm.likelihood_alpha, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }

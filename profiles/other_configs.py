@@ -64,6 +64,8 @@ def main():
     P, n = 8, 10000
     cs = synth.make_patches(P, 49.0, 1024, 1024)
     tr = api.BatchTracker(api.make_params("ssd", "homography", "pf", n_patches=P))
+    tr32 = api.BatchTracker(api.make_params("ssd", "homography", "pf", n_patches=P, precision="f32"))      # F32 particle evaluation
+    tr32.set_stream(stream.cuda_stream)
     tr.set_stream(stream.cuda_stream)
     tr.initialize(cs, d_frames[0]); tr.setImage(d_frames[1])
     rng = np.random.default_rng(0)
@@ -75,6 +77,12 @@ def main():
         tr._check(L.mtfb_pf_evaluate_device(tr._h, states.data_ptr(), n, lik.data_ptr(), sim.data_ptr()))
     ms = timed(pf, stream, 5)
     out.append({"config": "5: PF+SSD+Homography 8 objects x 10000 particles x 50x50 (one GPU's share of 64 objects on 8)",
+                "ms_per_frame": ms, "particles_per_s": P * n / (ms * 1e-3), "finite": bool(torch.isfinite(lik).all())})
+    def pf32():
+        tr32._check(L.mtfb_pf_evaluate_device(tr32._h, states.data_ptr(), n, lik.data_ptr(), sim.data_ptr()))
+    tr32.initialize(cs, d_frames[0]); tr32.setImage(d_frames[1])
+    ms = timed(pf32, stream, 5)
+    out.append({"config": "5 (F32): PF+SSD+Homography 8 objects x 10000 particles x 50x50",
                 "ms_per_frame": ms, "particles_per_s": P * n / (ms * 1e-3), "finite": bool(torch.isfinite(lik).all())})
     for o in out:
         print(json.dumps(o))

@@ -232,7 +232,7 @@ def test_f32_matches_f64_kernel_large_batch(seq384):
 
 def test_f32_unsupported_combinations():
     from mtf_b200 import api
-    for kw in (dict(am="ncc"), dict(am="mi", sm="iclk"), dict(chained_warp=0), dict(sm="pf")):
+    for kw in (dict(am="ncc"), dict(am="mi", sm="iclk"), dict(chained_warp=0), dict(am="ncc", sm="pf")):
         am = kw.pop("am", "ssd"); sm = kw.pop("sm", "fclk")
         with pytest.raises(api.MTFError) as e:
             api.BatchTracker(api.make_params(am, "homography", sm, n_patches=2, precision="f32", **kw))
@@ -378,3 +378,29 @@ def test_f32_textureless_patch_is_survivable(seq384):
     ref = _gpu("homography", "fclk", 2, max_iters=5)
     ref.initialize(cs[[0, 2]], flat[0]); ref.update(flat[1])
     assert np.abs(got[[0, 2]] - ref.getRegion()).max() <= 1e-9
+
+
+@pytest.mark.parametrize("ssm", SSMS)
+def test_f32_pf_evaluate(seq384, ssm):
+    """particle evaluation in the fp32 precision: per-particle similarity against the oracle (same states), including a
+    particle thrown out of the image (every sample is the constant 128) and the identity on an integer-aligned box
+    (every sample on the pixel lattice)"""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(2, 49.0, 384, 384), common.quad_patches(2, 384, 384, seed=4)])
+    S = 8 if ssm == "homography" else 6
+    n = 300
+    rng = np.random.default_rng(9)
+    scale = np.array([2e-2, 2e-2, 2.0, 2e-2, 2e-2, 2.0, 1e-5, 1e-5]) if S == 8 else np.array([2.0, 2.0, 2e-2, 2e-2, 2e-2, 2e-2])
+    states = rng.normal(size=(len(cs), n, S)) * scale
+    states[:, 0] = 0
+    states[0, 1, 2 if S == 8 else 0] = 400.0
+    g = _gpu(ssm, "pf", len(cs), likelihood_alpha=0.5)
+    g.initialize(cs, frames[0])
+    g.setImage(frames[1])
+    lik, sim = g.pf_evaluate(states)
+    for i, c in enumerate(cs):
+        o = _oracle(ssm, "fclk", likelihood_alpha=0.5)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1])
+        ol, os_ = o.pf_evaluate(states[i])
+        assert np.allclose(sim[i], os_, rtol=F32_RTOL, atol=0)
+        assert np.allclose(lik[i], ol, rtol=1e-3, atol=1e-300)
