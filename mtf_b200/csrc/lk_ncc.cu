@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
 	const double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
 	const double I0_mean = b.am_scal[(size_t)p * 8], c = b.am_scal[(size_t)p * 8 + 1], rc = ieee_rcp(c);
-	const bool jac_half = (SM == SM_ESM);                                    // NT/ESM.cc:308-309 (DiffOfJacs)
+	// ESM's Original variants work on mean_pix_jacobian = (init + curr) / 2 (NT/ESM.cc:246-248): the Jacobian is
+	// df_dIt . mean (NT/ESM.cc:301-303, no halving), the Hessian cmptCurrHessian(mean) (NT/ESM.cc:325-327)
+	const bool jac_orig = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL);
+	const bool hess_orig = (SM == SM_ESM) && (b.hess_type == MTFB_ESM_HESS_ORIGINAL);
+	const bool jac_half = (SM == SM_ESM) && !jac_orig;                       // NT/ESM.cc:308-309 (DiffOfJacs)
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
@@ -184,25 +188,38 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			const double Itcb = div_by(s_It[it.pix] - It_mean, bn, rb);                  // It_cntr_b (NCC.cc:213)
 			const double I0cc = div_by(I0[it.pix] - I0_mean, c, rc);                     // I0_cntr_c (NCC.cc:116)
+			double D[S], D0[S];
 			if(L::CURR){
 				Sample smp;
 				pixel_value_and_gradient<SSM, true>(b, W, g, smp);
-				double D[S];
 				pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
+			}
+			if(L::INIT) init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
+			if(L::CURR){
 				const double wt = div_by(I0cc - f*Itcb, bn, rb) - mean_t;                // df_dIt (NCC.cc:214-222)
 #pragma unroll
 				for(int i = 0; i < S; ++i){
-					acc[L::oD + i] += D[i];
-					acc[L::oW + i] = fma(wt, D[i], acc[L::oW + i]);
-					acc[L::oB + i] = fma(Itcb, D[i], acc[L::oB + i]);
-					if(STD) acc[L::oC + i] = fma(I0cc, D[i], acc[L::oC + i]);
+					// the row behind the Hessian sums (Dh) and the one behind the Jacobian (Dj): the current pixel Jacobian, or
+					// ESM's mean pixel Jacobian
+					double Dh = D[i], Dj = D[i];
+					if(SM == SM_ESM && (jac_orig || hess_orig)){
+						const double Dm = (D0[i] + D[i]) / 2.0;
+						if(hess_orig) Dh = Dm;
+						if(jac_orig) Dj = Dm;
+					}
+					D[i] = Dh;
+					acc[L::oD + i] += Dh;
+					acc[L::oW + i] = fma(wt, Dj, acc[L::oW + i]);
+					acc[L::oB + i] = fma(Itcb, Dh, acc[L::oB + i]);
+					if(STD) acc[L::oC + i] = fma(I0cc, Dh, acc[L::oC + i]);
+				}
+#pragma unroll
+				for(int i = 0; i < S; ++i){
 #pragma unroll
 					for(int j = i; j < S; ++j) acc[L::oDD + L::tri(i, j)] = fma(D[i], D[j], acc[L::oDD + L::tri(i, j)]);
 				}
 			}
 			if(L::INIT){
-				double D0[S];
-				init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
 				const double w0 = div_by(Itcb - f*I0cc, c, rc) - mean_0;                 // df_dI0 (NCC.cc:174-182)
 #pragma unroll
 				for(int i = 0; i < S; ++i){
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 				// FCLK: df_dIt . dIt_dp (NCC.cc:252-266); ESM: (df_dIt . dIt_dp - df_dI0 . dI0_dp) / 2 (NCC.cc:268-280,
 				// NT/ESM.cc:308-309); ICLK: df_dI0 . dI0_dp (NCC.cc:236-250)
 				double jv = L::CURR ? s_sum[L::oW + e] : 0.0;
-				if(SM == SM_ESM) jv = jv - s_sum[L::o0 + e];
+				if(SM == SM_ESM && !jac_orig) jv = jv - s_sum[L::o0 + e];
 				if(SM == SM_ICLK) jv = s_sum[L::o0 + e];
 				s_J[e] = jac_half ? jv * 0.5 : jv;
 			}
@@ -273,7 +290,8 @@ template<int SSM, int SM, int T, bool STD> static cudaError_t launch_one_s(const
 	return cudaGetLastError();
 }
 template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, cudaStream_t st){
-	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD)
+	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD ||
+		b.hess_type == MTFB_ESM_HESS_ORIGINAL)
 		: (b.hess_type == MTFB_LK_HESS_STD);
 	return std_hess ? launch_one_s<SSM, SM, T, true>(b, st) : launch_one_s<SSM, SM, T, false>(b, st);
 }

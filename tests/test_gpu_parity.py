@@ -270,28 +270,29 @@ def test_ncc_iteration_log_parity(seq384, sm, ssm):
         assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= 10 * CORNER_ATOL_EXACT
 
 
-@pytest.mark.parametrize("sm,hess", [("fclk", "std"), ("iclk", "std"), ("esm", "std"), ("esm", "sum_of_std")])
+@pytest.mark.parametrize("sm,hess,jac", [("fclk", "std", 1), ("iclk", "std", 1), ("esm", "std", 1), ("esm", "sum_of_std", 1),
+                                         ("esm", "original", 1), ("esm", "original", 0), ("esm", "sum_of_self", 0)])
 @pytest.mark.parametrize("ssm", SSMS)
-def test_ncc_std_hessians(seq384, sm, hess, ssm):
+def test_ncc_std_hessians(seq384, sm, hess, jac, ssm):
     """NCC::cmptCurrHessian / cmptInitHessian (NCC.cc:282-336) behind FCLK / ICLK / ESM Std and ESM SumOfStd: every pass"""
     from mtf_b200 import api
     frames, _ = seq384
     cs = np.concatenate([common.patches(3, 52.3, 384, 384, seed=4), common.quad_patches(3, 384, 384, seed=12)])
     h = (api.ESM_HESS if sm == "esm" else api.LK_HESS)[hess]
-    g = _gpu("ncc", ssm, sm, len(cs), hess_type=h, max_iters=12)
+    g = _gpu("ncc", ssm, sm, len(cs), hess_type=h, jac_type=jac, max_iters=12)
     g.enable_iter_log(12)
     g.initialize(cs, frames[0])
     g.update(frames[1])
     logs = g.iter_log()
     n_it = g.n_iters()
     for i, c in enumerate(cs):
-        o = _oracle("ncc", ssm, sm, grad_mode=1, hess_type=h, max_iters=12)
+        o = _oracle("ncc", ssm, sm, grad_mode=1, hess_type=h, jac_type=jac, max_iters=12)
         o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
         ol = o.log()
         assert n_it[i] == o.n_iters == len(ol) == len(logs[i])
         for k, (a, b) in enumerate(zip(logs[i], ol)):
             tol = NCC_FIRST_RTOL if k == 0 else NCC_LATER_RTOL
-            assert _rel(a["hessian"], b["hessian"]) <= tol * 10, (sm, hess, ssm, i, k, _rel(a["hessian"], b["hessian"]))
+            assert _rel(a["hessian"], b["hessian"]) <= tol * 10, (sm, hess, jac, ssm, i, k, _rel(a["hessian"], b["hessian"]))
             assert _rel(a["jacobian"], b["jacobian"]) <= tol * 10
             assert np.abs(a["corners"] - b["corners"]).max() <= 10 * CORNER_ATOL_EXACT
     assert np.isfinite(g.getRegion()).all()
