@@ -148,7 +148,8 @@ mtfb_status mtfb_get_image(mtfb_ctx *ctx, float *out);
  * NT/ICLK.cc:71-127): ssm.setCorners (4-point DLT, Utilities/src/warpUtils.cc:171-223) + am.initializePixVals
  * + the SM-specific template gradients / Jacobians / Hessians, for all P patches, on the device. */
 mtfb_status mtfb_initialize(mtfb_ctx *ctx, const double *corners /* P x 8, host */);
-/* replaces SearchMethod::setRegion (NT/FCLK.cc:360-376, NT/ESM.cc:148-167) */
+/* replaces SearchMethod::setRegion (NT/FCLK.cc:360-376, NT/ESM.cc:148-167, NT/ICLK.cc:132-160 with update_ssm = 0): new
+ * corners, identity warp; ESM and FCLK-InitialSelf also rebuild init_pix_jacobian / init_self_hessian (SSD only) */
 mtfb_status mtfb_set_region(mtfb_ctx *ctx, const double *corners /* P x 8, host */);
 /* replaces SearchMethod::update() (NT/FCLK.cc:171-358, NT/ESM.cc:170-297, NT/ICLK.cc:160-299): the whole
  * <= max_iters loop for every patch in ONE launch.  Asynchronous; results are read with the getters. */

@@ -22,6 +22,8 @@ struct DevBatch {
 	double *I0;                  // P x N   template pixel values (am.I0)
 	double *G0;                  // P x 2 x N  template gradient: chained with the init warp, or (chained = 0) the
 	                             //            warped-image gradient of initialize() time
+	double *G0raw;               // P x 2 x N  am.getInitPixGrad(): the template gradient before any chaining (kept for
+	                             //            setRegion of ESM / FCLK-InitialSelf, SSD), else null
 	float *I0f, *G0f;            // fp32 copies of I0 / G0 (precision = MTFB_PRECISION_F32), else null
 	int I0f_stride;              // elements per patch in I0f (N rounded up to 4: 16-byte aligned rows for the bulk copy)
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
@@ -52,6 +54,8 @@ struct StageTapsF32 { int *idx; float *pix_vals, *pix_grad, *fast_err; double *p
 cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
+// setRegion of the search methods that keep template Jacobians (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): SSD
+cudaError_t launch_reinit_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
 // lk_ssd_f32.cu
 cudaError_t launch_update_ssd_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);

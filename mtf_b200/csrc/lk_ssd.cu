@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 		// Ix / Iy columns
 		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
 		G0[b.N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+		if(b.G0raw){ b.G0raw[(size_t)p * 2 * b.N + it.pix] = smp.gx; b.G0raw[(size_t)p * 2 * b.N + b.N + it.pix] = smp.gy; }
 		if(b.I0f){
 			// fp32 copies for the fp32-arithmetic update kernel (lk_ssd_f32.cu)
 			b.I0f[(size_t)p*b.I0f_stride + it.pix] = (float)smp.val;
@@ -76,6 +77,63 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 		int i = tid % S, j = tid / S;
 		int lo = i < j ? i : j, hi = i < j ? j : i;
 		b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];        // SSD self Hessian: -J^T J
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// setRegion() of the search methods that keep template Jacobians -- nt::ESM::setRegion (NT/ESM.cc:150-168) and
+// nt::FCLK::setRegion with the InitialSelf Hessian (NT/FCLK.cc:360-376): ssm.setCorners, then
+// init_pix_jacobian = ssm.cmptInitPixJacobian(am.getInitPixGrad()) at the NEW template points (always the un-chained
+// form, whatever chained_warp says: the reference's choice) and init_self_hessian = am.cmptSelfHessian(init_pix_jacobian).
+// The template values are kept.
+// ------------------------------------------------------------------------------------------------
+template<int SSM, int T>
+__global__ void __launch_bounds__(T) ssd_reinit_kernel(DevBatch b, const double *__restrict__ corners_in){
+	constexpr int S = StateSize<SSM>::value;
+	typedef AccLayout<S> L;
+	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	__shared__ double s_dlt[9];
+	__shared__ double s_part[(T / 32) * L::NA];
+	__shared__ double s_sum[L::NA];
+	if(warp == 0){
+		Mat3 dlt = set_corners<SSM>(b, p, lane, corners_in + (size_t)p * 8);
+		if(lane < 9) s_dlt[lane] = dlt.m[lane];
+	}
+	cta_sync<T>();
+	Mat3 dlt, W = mat3_identity();
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	if(b.norm_init) W = dlt;
+	double acc[L::NA];
+#pragma unroll
+	for(int i = 0; i < L::NA; ++i) acc[i] = 0;
+	double *G0 = b.G0 + (size_t)p * 2 * b.N;
+	const double *Gr = b.G0raw + (size_t)p * 2 * b.N;
+	for(PixIter it(tid, T, b.resx); it.pix < b.N; it.next(T)){
+		const PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+		const double gx = Gr[it.pix], gy = Gr[b.N + it.pix];
+		double J[S];
+		init_pix_jacobian<SSM>(g.ix, g.iy, gx, gy, J);
+		G0[it.pix] = gx; G0[b.N + it.pix] = gy;                              // the Ix / Iy columns of cmptInitPixJacobian
+		if(b.G0f){ b.G0f[(size_t)p * 2 * b.N + it.pix] = (float)gx; b.G0f[(size_t)p * 2 * b.N + b.N + it.pix] = (float)gy; }
+#pragma unroll
+		for(int i = 0; i < S; ++i){
+#pragma unroll
+			for(int j = i; j < S; ++j) acc[1 + S + L::tri(i, j)] = fma(J[i], J[j], acc[1 + S + L::tri(i, j)]);
+		}
+	}
+	block_reduce<L::NA, T>(acc, s_part, s_sum);
+	if(tid < S*S){
+		int i = tid % S, j = tid / S;
+		int lo = i < j ? i : j, hi = i < j ? j : i;
+		b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];
+	}
+	if(T == 32 && S*S > 32){
+		for(int e = tid + 32; e < S*S; e += 32){
+			const int i = e % S, j = e / S;
+			const int lo = i < j ? i : j, hi = i < j ? j : i;
+			b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];
+		}
 	}
 }
 
@@ -231,6 +289,22 @@ template<int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &
 cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
 	if(ssm == SSM_HOM) return launch_init_t<SSM_HOM>(threads, b, d_corners, st);
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, st);
+}
+
+template<int SSM> static cudaError_t launch_reinit_t(int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	switch(threads){
+	case 32: ssd_reinit_kernel<SSM, 32><<<b.P, 32, 0, st>>>(b, d_corners); break;
+	case 64: ssd_reinit_kernel<SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners); break;
+	case 128: ssd_reinit_kernel<SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners); break;
+	case 256: ssd_reinit_kernel<SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_reinit_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	if(!b.G0raw) return cudaErrorInvalidValue;
+	if(ssm == SSM_HOM) return launch_reinit_t<SSM_HOM>(threads, b, d_corners, st);
+	return launch_reinit_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st){

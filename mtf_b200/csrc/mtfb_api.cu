@@ -218,7 +218,9 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		if(cudaMalloc(&c->d_grid, grid.size()*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemcpy(c->d_grid, grid.data(), grid.size()*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		// per-patch arrays
-		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64;
+		// SSD with ESM / FCLK keeps the un-chained template gradient for setRegion (NT/ESM.cc:150-168, NT/FCLK.cc:360-376)
+		const bool keep_raw_grad = p->am == MTFB_AM_SSD && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK);
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + (keep_raw_grad ? 2 * (size_t)N : 0);
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -240,6 +242,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.ncc_tab = q; q += 64 * (size_t)P;
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
+		b.G0raw = nullptr;
+		if(keep_raw_grad){ b.G0raw = q; q += 2 * (size_t)N*P; }
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
 		b.I0f = b.G0f = nullptr; b.I0f_stride = 0;
 		b.gx_lo = b.gx_step = b.gy_lo = b.gy_step = 0;
@@ -403,15 +407,18 @@ mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 
 mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	if(c && !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_set_region: initialize has not been called");
+	bool ssm_only = true;
 	if(c){
-		const bool ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) ||
+		ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) ||
 			(c->prm.sm == MTFB_SM_FCLK && c->prm.hess_type != MTFB_LK_HESS_INITIAL_SELF);
-		if(!ssm_only) return fail(MTFB_ERR_NOT_SUPPORTED,
-			"mtfb_set_region: only the SSM-only variants (FCLK with a current Hessian, ICLK, PF) are implemented");
+		// ESM and FCLK-InitialSelf also rebuild the template Jacobian and init_self_hessian at the new points: SSD
+		if(!ssm_only && !c->b.G0raw) return fail(MTFB_ERR_NOT_SUPPORTED,
+			"mtfb_set_region: for ESM and for FCLK with the InitialSelf Hessian only the SSD appearance model is implemented");
 	}
 	mtfb_status st = upload_corners(c, corners, "mtfb_set_region");
 	if(st != MTFB_OK) return st;
-	CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
+	if(ssm_only) CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
+	else CUDA_TRY(launch_reinit_ssd(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
 	return MTFB_OK;
 }

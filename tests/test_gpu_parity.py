@@ -512,3 +512,36 @@ def test_hom_normalized_init(seq384, am, sm):
                 assert _rel(a["hessian"], b["hessian"]) <= tol
                 assert np.abs(a["corners"] - b["corners"]).max() <= (1e-4 if am == "mi" else 1e-6)
     assert (g.patch_status() & 2 == 0).all() or am == "mi"
+
+
+@pytest.mark.parametrize("sm,hess", [("esm", "sum_of_self"), ("esm", "initial_self"), ("esm", "current_self"), ("fclk", "initial_self")])
+@pytest.mark.parametrize("ssm", SSMS)
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_set_region_rebuilds_template_jacobian(seq384, sm, hess, ssm, precision):
+    """nt::ESM::setRegion / nt::FCLK::setRegion with InitialSelf (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): new corners,
+    init_pix_jacobian from the kept template gradient at the new points, init_self_hessian rebuilt; template values kept"""
+    from mtf_b200 import api
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 52.3, 384, 384, seed=23), common.quad_patches(3, 384, 384, seed=24)])
+    h = (api.ESM_HESS if sm == "esm" else api.LK_HESS)[hess]
+    g = _gpu("ssd", ssm, sm, len(cs), hess_type=h, precision=precision)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    g.update(frames[1])
+    moved = g.getRegion() + np.array([[0.8], [-0.6]])
+    g.setRegion(moved)
+    assert np.array_equal(g.getRegion(), moved)
+    g.update(frames[2])
+    got, logs = g.getRegion(), g.iter_log()
+    for i, c in enumerate(cs):
+        o = _oracle("ssd", ssm, sm, grad_mode=1, hess_type=h)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        o.set_region(o.corners() + np.array([[0.8], [-0.6]]))
+        o.set_image(frames[2]); o.update()
+        if precision == "f64":
+            assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= LATER_RTOL
+            assert _rel(logs[i][0]["jacobian"], o.log()[0]["jacobian"]) <= LATER_RTOL * 10
+            assert np.abs(got[i] - o.corners()).max() <= 10 * CORNER_ATOL_EXACT
+        else:
+            assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= 1e-4
+            assert np.abs(got[i] - o.corners()).max() <= 3e-2          # epsilon = 1e-4 stopping rule, fp32 arithmetic
