@@ -172,9 +172,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		threads = p->n_patches >= 600 ? 32 : 64; occ = 0;
 	}
 	if(!threads && p->precision == MTFB_PRECISION_F32){
-		// measured on B200 (profiles/README.md): two warps per patch once the batch gives every SM ~7 CTAs at 128
-		// registers, four CTAs of four warps below that, eight warps per patch for small batches
-		threads = p->n_patches >= 700 ? 64 : p->n_patches >= 150 ? 128 : 256;
+		// measured on B200 (profiles/r01_pscale.txt): four warps per patch while the batch fits one wave of four 128-thread
+		// CTAs per SM (148 x 4 = 592 patches: 0.355 ms against 0.412 ms at two warps), two warps per patch above that
+		// (888 patches: 0.512 against 0.600 ms), eight warps per patch for small batches
+		threads = p->n_patches > 592 ? 64 : p->n_patches >= 150 ? 128 : 256;
 	}
 	if(!threads){
 		if(p->n_patches >= 900){ threads = 32; occ = 0; }
