@@ -193,9 +193,13 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 // KEEP_IT: keep the N current pixel values of sweep 1 in shared memory for sweep 2 (small patches); otherwise sweep 2
 // samples them again (same bits) and shared memory holds only the private histograms -- for 100 x 100 patches the
 // 80 KB value buffer would leave room for two warps per SM.
-template<int SSM, int SM, int T, bool KEEP_IT>
+// SELF: the pass also builds am.cmptSelfHessian(curr_pix_jacobian) (MI.cc:515-594) -- the CurrentSelf / SumOfSelf Hessians of
+// FCLK / ESM / ICLK: cmptSelfHist (the joint histogram of the current patch with itself, MI.cc:639-658), its logs, and one
+// more sweep over the pixels with the same code as the template's init_self_hessian in mi_init_kernel.
+template<int SSM, int SM, int T, bool KEEP_IT, bool SELF>
 __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch b, MiParams mp, const double *__restrict__ mi_tab){
 	constexpr int S = StateSize<SSM>::value;
+	constexpr int NH = S*(S + 1) / 2;
 	constexpr bool CURR = (SM != SM_ICLK), INIT = (SM != SM_FCLK);
 	constexpr int NA = (CURR ? S : 0) + (INIT ? S : 0);
 	constexpr int oT = 0, o0 = CURR ? S : 0;
@@ -215,6 +219,9 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 	__shared__ double s_fold[(T / 32) * MI_HBMAX];
 	__shared__ double s_W[9], s_dlt[9], s_corners[8], s_init_corners[8], s_J[S], s_f;
 	__shared__ int s_ctrl;
+	// SELF only (size 1 otherwise): self joint histogram, its gradient factor, joint_hist_jacobian, the Hessian sums
+	__shared__ double s_sj[SELF ? MI_BMAX*MI_BMAX : 1], s_sfac[SELF ? MI_BMAX*MI_BMAX : 1], s_jhj[SELF ? MI_BMAX*MI_BMAX*S : 1];
+	__shared__ double s_part2[SELF ? (T / 32) * NH : 1], s_sum2[SELF ? NH : 1], s_Hc[SELF ? S*S : 1];
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
 	for(int i = tid; i < B; i += T) s_ihist_log[i] = mi_tab[(size_t)p*MI_TAB + 16 + i];
@@ -334,6 +341,87 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		}
 		block_reduce<NA, T>(acc, s_part, s_sum);
 		++n_passes;
+		if(SELF){
+			// ---- cmptSelfHist (MI.cc:639-658): joint histogram of the current patch with itself, logs, self_grad_factor
+			for(int i = tid; i < B*B; i += T) s_sj[i] = mp.pre_seed;
+			for(int i = tid; i < B*B*S; i += T) s_jhj[i] = 0;
+			cta_sync<T>();
+			for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+				double v;
+				if(KEEP_IT) v = s_It[it.pix];
+				else{
+					PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+					v = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
+				}
+				const BinWeights bw = bin_weights(v, B);
+#pragma unroll
+				for(int k = 0; k < 4; ++k){
+					if(bw.lo + k > bw.hi) continue;
+#pragma unroll
+					for(int l = 0; l < 4; ++l){
+						if(bw.lo + l > bw.hi) continue;
+						atomicAdd(&s_sj[(bw.lo + l)*B + (bw.lo + k)], bw.w[k] * bw.w[l]);
+					}
+				}
+			}
+			cta_sync<T>();
+			for(int i = tid; i < B*B; i += T){
+				const double jh = s_sj[i] * mp.hist_norm_mult;
+				s_sj[i] = jh;
+				s_sfac[i] = 1 + log(jh) - s_hist_log[i % B];                          // self_grad_factor(curr, init) (MI.cc:655)
+			}
+			cta_sync<T>();
+			// ---- cmptSelfHessian(curr_pix_jacobian) (MI.cc:558-592): the same sweep as the template's in mi_init_kernel
+			double acc2[NH];
+#pragma unroll
+			for(int i = 0; i < NH; ++i) acc2[i] = 0;
+			for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+				PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+				Sample smp;
+				pixel_value_and_gradient<SSM, false>(b, W, g, smp);
+				double D[S];
+				pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
+				const double v = KEEP_IT ? s_It[it.pix] : (b.pix_mult*smp.val + b.pix_add);
+				const BinWeights bw = bin_weights(v, B);
+				double x = bw.lo - v, hist_hess_term = 0;
+#pragma unroll
+				for(int k = 0; k < 4; ++k){
+					const int curr_id = bw.lo + k;
+					const double hess_w = mp.hist_norm_mult * bspl3_hess(x);
+					x += 1;
+					if(curr_id > bw.hi) continue;
+					const double grad_k = bw.d[k] * (-mp.hist_norm_mult);               // curr_hist_grad (MI.cc:240)
+					double inner = 0;
+#pragma unroll
+					for(int l = 0; l < 4; ++l){
+						const int init_id = bw.lo + l;
+						if(init_id > bw.hi) continue;
+						const double gq = grad_k * bw.w[l];
+#pragma unroll
+						for(int q = 0; q < S; ++q) atomicAdd(&s_jhj[(curr_id*B + init_id)*S + q], gq * D[q]);
+						inner += bw.w[l] * s_sfac[init_id*B + curr_id];
+					}
+					hist_hess_term += hess_w * inner;
+				}
+#pragma unroll
+				for(int i = 0; i < S; ++i){
+#pragma unroll
+					for(int j = i; j < S; ++j) acc2[i*S - i*(i - 1) / 2 + (j - i)] = fma(hist_hess_term * D[i], D[j], acc2[i*S - i*(i - 1) / 2 + (j - i)]);
+				}
+			}
+			block_reduce<NH, T>(acc2, s_part2, s_sum2);             // also orders the atomics on s_jhj before the reads below
+			for(int e = tid; e < S*S; e += T){
+				const int i = e % S, j = e / S;
+				const int lo = i < j ? i : j, hi = i < j ? j : i;
+				double h = s_sum2[lo*S - lo*(lo - 1) / 2 + (hi - lo)];
+				for(int curr_id = 0; curr_id < B; ++curr_id) for(int init_id = 0; init_id < B; ++init_id){
+					const double hist_factor = (1.0 / s_sj[init_id*B + curr_id]) - (1.0 / s_hist[curr_id]);
+					const double *row = &s_jhj[(curr_id*B + init_id)*S];
+					h += row[i] * row[j] * hist_factor;
+				}
+				s_Hc[j*S + i] = h;
+			}
+		}
 		if(tid < S){
 			double jv = CURR ? s_sum[oT + tid] : 0.0;
 			if(SM == SM_ESM) jv = jv - s_sum[o0 + tid];                             // AppearanceModel.h:162-166
@@ -343,7 +431,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		cta_sync<T>();
 		if(warp == 0){
 			f = s_f;
-			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, nullptr, s_W, s_corners, s_init_corners,
+			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, SELF ? s_Hc : nullptr, s_W, s_corners, s_init_corners,
 				lm, patch_status);
 			if(lane == 0) s_ctrl = ctrl;
 		}
@@ -383,13 +471,19 @@ cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, mp, mi_tab, st);
 }
 
-template<int SSM, int SM, int T, bool KEEP_IT> static cudaError_t launch_keep(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
+template<int SSM, int SM, int T, bool KEEP_IT, bool SELF> static cudaError_t launch_self(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	const size_t smem = ((KEEP_IT ? (size_t)((b.N + 1) & ~1) : 0) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * 32) * sizeof(double);
-	if(smem > 200 * 1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if(smem > 180 * 1024) return cudaErrorInvalidValue;
+	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT, SELF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
-	mi_update_kernel<SSM, SM, T, KEEP_IT><<<b.P, T, smem, st>>>(b, mp, mi_tab);
+	mi_update_kernel<SSM, SM, T, KEEP_IT, SELF><<<b.P, T, smem, st>>>(b, mp, mi_tab);
 	return cudaGetLastError();
+}
+template<int SSM, int SM, int T, bool KEEP_IT> static cudaError_t launch_keep(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
+	// the pass's own self Hessian is needed by CurrentSelf (all three searches) and ESM's SumOfSelf
+	const bool self = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_CURRENT_SELF || b.hess_type == MTFB_ESM_HESS_SUM_OF_SELF)
+		: (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
+	return self ? launch_self<SSM, SM, T, KEEP_IT, true>(b, mp, mi_tab, st) : launch_self<SSM, SM, T, KEEP_IT, false>(b, mp, mi_tab, st);
 }
 template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	if((size_t)b.N * sizeof(double) <= 24 * 1024) return launch_keep<SSM, SM, T, true>(b, mp, mi_tab, st);

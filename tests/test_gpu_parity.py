@@ -298,6 +298,36 @@ def test_ncc_std_hessians(seq384, sm, hess, jac, ssm):
     assert np.isfinite(g.getRegion()).all()
 
 
+@pytest.mark.parametrize("sm,hess", [("fclk", "current_self"), ("esm", "sum_of_self"), ("esm", "current_self"), ("iclk", "current_self")])
+@pytest.mark.parametrize("ssm", SSMS)
+def test_mi_per_pass_self_hessian(seq384, sm, hess, ssm):
+    """MI::cmptSelfHessian(curr_pix_jacobian) every pass (MI.cc:515-594: cmptSelfHist, self_grad_factor, joint_hist_jacobian):
+    the CurrentSelf Hessians of FCLK / ESM / ICLK and ESM's SumOfSelf (FCLKParams.cc:6 / ESMParams.cc:7 defaults)"""
+    from mtf_b200 import api
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(2, 52.3, 384, 384, seed=31), common.quad_patches(2, 384, 384, seed=32)])
+    h = (api.ESM_HESS if sm == "esm" else api.LK_HESS)[hess]
+    g = _gpu("mi", ssm, sm, len(cs), hess_type=h, max_iters=6)
+    g.enable_iter_log(6)
+    g.initialize(cs, frames[0])
+    g.update(frames[1])
+    logs, n_it = g.iter_log(), g.n_iters()
+    for i, c in enumerate(cs):
+        o = _oracle("mi", ssm, sm, grad_mode=1, hess_type=h, max_iters=6)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        ol = o.log()
+        assert n_it[i] == o.n_iters == len(ol) == len(logs[i])
+        for k, (a, b) in enumerate(zip(logs[i], ol)):
+            # first pass: identical state, sums in another order (shared-memory atomics); later passes inherit the
+            # previous solves' conditioning like the InitialSelf case above
+            tol = 1e-9 if k == 0 else 1e-5
+            assert abs(a["f"] - b["f"]) <= tol
+            assert _rel(a["hessian"], b["hessian"]) <= tol, (sm, hess, ssm, i, k, _rel(a["hessian"], b["hessian"]))
+            assert _rel(a["jacobian"], b["jacobian"]) <= tol * 10
+            assert np.abs(a["corners"] - b["corners"]).max() <= (1e-6 if k == 0 else 1e-3)
+    assert np.isfinite(g.getRegion()).all()
+
+
 @pytest.mark.parametrize("res", [10, 25])
 def test_ncc_affine_grid_cells(seq384, res):
     """BASELINE config 3: ESM + NCC + Affine on a grid of small cells (GridTracker.cc:345-392 initialises every cell as
