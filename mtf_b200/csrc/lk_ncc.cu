@@ -17,9 +17,10 @@ namespace mtfb {
 
 // STD: the pass also needs the sums behind NCC::cmptCurrHessian / cmptInitHessian (NCC.cc:282-336):
 // sum I0cc D (oC) for the current image, sum Itcb D0 (oB0) for the template
-template<int S, int SM, bool STD = false> struct NccLayout {
+// ICLK_CURR: ICLK with the CurrentSelf Hessian also needs the current-image terms (NT/ICLK.cc:205-226)
+template<int S, int SM, bool STD = false, bool ICLK_CURR = false> struct NccLayout {
 	static constexpr int NH = S*(S + 1) / 2;
-	static constexpr bool CURR = (SM != SM_ICLK);          // needs the current-image Jacobian terms
+	static constexpr bool CURR = (SM != SM_ICLK) || ICLK_CURR;   // needs the current-image Jacobian terms
 	static constexpr bool INIT = (SM != SM_FCLK);          // needs the template Jacobian term
 	static constexpr int oD = 0, oDD = oD + (CURR ? S : 0), oW = oDD + (CURR ? NH : 0), oB = oW + (CURR ? S : 0),
 		o0 = oB + (CURR ? S : 0), oC = o0 + (INIT ? S : 0), oB0 = oC + ((STD && CURR) ? S : 0), NA = oB0 + ((STD && INIT) ? S : 0);
@@ -125,10 +126,12 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 	for(int e = tid; e < L::NH; e += T) b.ncc_tab[(size_t)p * 64 + S + e] = s_sum[L::oDD + e];
 }
 
-template<int SSM, int SM, int T, bool STD>
+// MODE 0: self Hessians; 1 (STD): the Std forms; 2: ICLK with the CurrentSelf Hessian
+template<int SSM, int SM, int T, int MODE>
 __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatch b){
 	constexpr int S = StateSize<SSM>::value;
-	typedef NccLayout<S, SM, STD> L;
+	constexpr bool STD = (MODE == 1);
+	typedef NccLayout<S, SM, STD, MODE == 2> L;
 	extern __shared__ __align__(16) double s_It[];                          // N current pixel values
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = b.N;
@@ -281,19 +284,20 @@ cudaError_t launch_init_ncc(int ssm, int threads, const DevBatch &b, const doubl
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
-template<int SSM, int SM, int T, bool STD> static cudaError_t launch_one_s(const DevBatch &b, cudaStream_t st){
+template<int SSM, int SM, int T, int MODE> static cudaError_t launch_one_s(const DevBatch &b, cudaStream_t st){
 	const size_t smem = (size_t)b.N * sizeof(double);
 	if(smem > 200 * 1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(ncc_update_kernel<SSM, SM, T, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(ncc_update_kernel<SSM, SM, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
-	ncc_update_kernel<SSM, SM, T, STD><<<b.P, T, smem, st>>>(b);
+	ncc_update_kernel<SSM, SM, T, MODE><<<b.P, T, smem, st>>>(b);
 	return cudaGetLastError();
 }
 template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, cudaStream_t st){
 	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD ||
 		b.hess_type == MTFB_ESM_HESS_ORIGINAL)
 		: (b.hess_type == MTFB_LK_HESS_STD);
-	return std_hess ? launch_one_s<SSM, SM, T, true>(b, st) : launch_one_s<SSM, SM, T, false>(b, st);
+	if(SM == SM_ICLK && b.hess_type == MTFB_LK_HESS_CURRENT_SELF) return launch_one_s<SSM, SM, T, (SM == SM_ICLK ? 2 : 0)>(b, st);
+	return std_hess ? launch_one_s<SSM, SM, T, 1>(b, st) : launch_one_s<SSM, SM, T, 0>(b, st);
 }
 template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, cudaStream_t st){
 	switch(threads){

@@ -50,13 +50,13 @@ bool combo_supported(const mtfb_params *p, const char **why){
 	if(p->am == MTFB_AM_SSD) return true;
 	if(p->am == MTFB_AM_NCC){
 		// the self Hessians (NCC.cc:337-389) and the Std forms cmptCurrHessian / cmptInitHessian (NCC.cc:282-336) are
-		// implemented, for ESM also on the mean pixel Jacobian (Original Jacobian / Hessian); ICLK's CurrentSelf is not
+		// implemented, for ESM also on the mean pixel Jacobian (Original Jacobian / Hessian)
 		bool ok;
 		if(p->sm == MTFB_SM_ESM) ok = (p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS || p->jac_type == MTFB_ESM_JAC_ORIGINAL) &&
 			p->hess_type >= MTFB_ESM_HESS_INITIAL_SELF && p->hess_type <= MTFB_ESM_HESS_STD;
 		else if(p->sm == MTFB_SM_FCLK) ok = p->hess_type >= MTFB_LK_HESS_INITIAL_SELF && p->hess_type <= MTFB_LK_HESS_STD;
-		else ok = p->hess_type == MTFB_LK_HESS_INITIAL_SELF || p->hess_type == MTFB_LK_HESS_STD;
-		if(!ok) *why = "NCC: ICLK's CurrentSelf Hessian is not implemented";
+		else ok = p->hess_type >= MTFB_LK_HESS_INITIAL_SELF && p->hess_type <= MTFB_LK_HESS_STD;
+		if(!ok) *why = "NCC: unknown Hessian / Jacobian type";
 		return ok;
 	}
 	if(p->am == MTFB_AM_MI){

@@ -271,7 +271,8 @@ def test_ncc_iteration_log_parity(seq384, sm, ssm):
 
 
 @pytest.mark.parametrize("sm,hess,jac", [("fclk", "std", 1), ("iclk", "std", 1), ("esm", "std", 1), ("esm", "sum_of_std", 1),
-                                         ("esm", "original", 1), ("esm", "original", 0), ("esm", "sum_of_self", 0)])
+                                         ("esm", "original", 1), ("esm", "original", 0), ("esm", "sum_of_self", 0),
+                                         ("iclk", "current_self", 1)])
 @pytest.mark.parametrize("ssm", SSMS)
 def test_ncc_std_hessians(seq384, sm, hess, jac, ssm):
     """NCC::cmptCurrHessian / cmptInitHessian (NCC.cc:282-336) behind FCLK / ICLK / ESM Std and ESM SumOfStd: every pass"""
