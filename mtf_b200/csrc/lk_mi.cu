@@ -196,8 +196,11 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 // SELF: the pass also builds am.cmptSelfHessian(curr_pix_jacobian) (MI.cc:515-594) -- the CurrentSelf / SumOfSelf Hessians of
 // FCLK / ESM / ICLK: cmptSelfHist (the joint histogram of the current patch with itself, MI.cc:639-658), its logs, and one
 // more sweep over the pixels with the same code as the template's init_self_hessian in mi_init_kernel.
-template<int SSM, int SM, int T, bool KEEP_IT, bool SELF>
+// HMODE 2: the Std forms instead -- cmptCurrHessian (MI.cc:603-637: FCLK / ESM Std), cmptInitHessian (MI.cc:461-514: ICLK Std),
+// half their sum (ESM SumOfStd, NT/ESM.cc:339-343) -- through the same sweep with the template's bins as the partner.
+template<int SSM, int SM, int T, bool KEEP_IT, int HMODE>
 __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch b, MiParams mp, const double *__restrict__ mi_tab){
+	constexpr bool SELF = (HMODE != 0);                 // a per-pass Hessian is assembled in s_Hc
 	constexpr int S = StateSize<SSM>::value;
 	constexpr int NH = S*(S + 1) / 2;
 	constexpr bool CURR = (SM != SM_ICLK), INIT = (SM != SM_FCLK);
@@ -222,6 +225,8 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 	// SELF only (size 1 otherwise): self joint histogram, its gradient factor, joint_hist_jacobian, the Hessian sums
 	__shared__ double s_sj[SELF ? MI_BMAX*MI_BMAX : 1], s_sfac[SELF ? MI_BMAX*MI_BMAX : 1], s_jhj[SELF ? MI_BMAX*MI_BMAX*S : 1];
 	__shared__ double s_part2[SELF ? (T / 32) * NH : 1], s_sum2[SELF ? NH : 1], s_Hc[SELF ? S*S : 1];
+	__shared__ double s_jh[HMODE == 2 ? MI_BMAX*MI_BMAX : 1], s_ihist[HMODE == 2 ? MI_BMAX : 1];      // joint_hist, init_hist
+	if(HMODE == 2){ for(int i = tid; i < B; i += T) s_ihist[i] = mi_tab[(size_t)p*MI_TAB + i]; }
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
 	for(int i = tid; i < B; i += T) s_ihist_log[i] = mi_tab[(size_t)p*MI_TAB + 16 + i];
@@ -280,6 +285,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		cta_sync<T>();
 		for(int i = tid; i < B*B; i += T){
 			const double jh = s_joint[i] * mp.hist_norm_mult, jl = log(jh);
+			if(HMODE == 2) s_jh[i] = jh;
 			const int curr_id = i % B, init_id = i / B;
 			s_joint[i] = jh * (jl - s_hist_log[curr_id] - s_ihist_log[init_id]);      // the term of f (MI.cc:376-380)
 			s_fac_t[i] = 1 + jl - s_hist_log[curr_id];                                // curr_grad_factor(curr, init) (MI.cc:430)
@@ -342,84 +348,110 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		block_reduce<NA, T>(acc, s_part, s_sum);
 		++n_passes;
 		if(SELF){
-			// ---- cmptSelfHist (MI.cc:639-658): joint histogram of the current patch with itself, logs, self_grad_factor
-			for(int i = tid; i < B*B; i += T) s_sj[i] = mp.pre_seed;
-			for(int i = tid; i < B*B*S; i += T) s_jhj[i] = 0;
-			cta_sync<T>();
-			for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-				double v;
-				if(KEEP_IT) v = s_It[it.pix];
-				else{
+			// which Hessians this pass assembles: 0 = cmptSelfHessian(curr), 1 = cmptCurrHessian(curr), 2 = cmptInitHessian(init)
+			int modes[2] = { 0, 0 }, n_modes = 1;
+			double coef = 1.0;
+			if(HMODE == 2){
+				if(SM == SM_ICLK) modes[0] = 2;
+				else if(SM == SM_ESM && b.hess_type == MTFB_ESM_HESS_SUM_OF_STD){ modes[0] = 1; modes[1] = 2; n_modes = 2; coef = 0.5; }
+				else modes[0] = 1;
+			}
+			for(int mi = 0; mi < n_modes; ++mi){
+				const int mode = modes[mi];
+				for(int i = tid; i < B*B*S; i += T) s_jhj[i] = 0;
+				if(mode == 0){
+					// ---- cmptSelfHist (MI.cc:639-658): joint histogram of the current patch with itself, logs, self_grad_factor
+					for(int i = tid; i < B*B; i += T) s_sj[i] = mp.pre_seed;
+					cta_sync<T>();
+					for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+						double v;
+						if(KEEP_IT) v = s_It[it.pix];
+						else{
+							PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+							v = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
+						}
+						const BinWeights bw = bin_weights(v, B);
+#pragma unroll
+						for(int k = 0; k < 4; ++k){
+							if(bw.lo + k > bw.hi) continue;
+#pragma unroll
+							for(int l = 0; l < 4; ++l){
+								if(bw.lo + l > bw.hi) continue;
+								atomicAdd(&s_sj[(bw.lo + l)*B + (bw.lo + k)], bw.w[k] * bw.w[l]);
+							}
+						}
+					}
+					cta_sync<T>();
+					for(int i = tid; i < B*B; i += T){
+						const double jh = s_sj[i] * mp.hist_norm_mult;
+						s_sj[i] = jh;
+						s_sfac[i] = 1 + log(jh) - s_hist_log[i % B];                      // self_grad_factor(curr, init) (MI.cc:655)
+					}
+				}
+				cta_sync<T>();
+				// ---- the Hessian sweep (MI.cc:558-592 / 614-636 / 472-512).  p = the bins of the patch whose pixel Jacobian is
+				// used (current patch, or the template for cmptInitHessian), q = the partner's bins
+				double acc2[NH];
+#pragma unroll
+				for(int i = 0; i < NH; ++i) acc2[i] = 0;
+				for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
 					PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
-					v = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
-				}
-				const BinWeights bw = bin_weights(v, B);
+					double D[S], vc;
+					if(mode == 2){
+						init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D);
+						vc = KEEP_IT ? s_It[it.pix] : (b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add);
+					} else{
+						Sample smp;
+						pixel_value_and_gradient<SSM, false>(b, W, g, smp);
+						pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
+						vc = KEEP_IT ? s_It[it.pix] : (b.pix_mult*smp.val + b.pix_add);
+					}
+					const double vp = (mode == 2) ? I0[it.pix] : vc;
+					const BinWeights bp = bin_weights(vp, B);
+					const BinWeights bq = (mode == 0) ? bp : bin_weights(mode == 1 ? I0[it.pix] : vc, B);
+					double x = bp.lo - vp, hist_hess_term = 0;
 #pragma unroll
-				for(int k = 0; k < 4; ++k){
-					if(bw.lo + k > bw.hi) continue;
+					for(int k = 0; k < 4; ++k){
+						const int p_id = bp.lo + k;
+						const double hess_w = mp.hist_norm_mult * bspl3_hess(x);
+						x += 1;
+						if(p_id > bp.hi) continue;
+						const double grad_k = bp.d[k] * (-mp.hist_norm_mult);               // curr_hist_grad / init_hist_grad (MI.cc:240)
+						double inner = 0;
 #pragma unroll
-					for(int l = 0; l < 4; ++l){
-						if(bw.lo + l > bw.hi) continue;
-						atomicAdd(&s_sj[(bw.lo + l)*B + (bw.lo + k)], bw.w[k] * bw.w[l]);
+						for(int l = 0; l < 4; ++l){
+							const int q_id = bq.lo + l;
+							if(q_id > bq.hi) continue;
+							const double gq = grad_k * bq.w[l];
+							// joint_hist_jacobian row (curr_id, init_id); the factor tables are indexed [init * B + curr]
+							const int curr_id = (mode == 2) ? q_id : p_id, init_id = (mode == 2) ? p_id : q_id;
+#pragma unroll
+							for(int r = 0; r < S; ++r) atomicAdd(&s_jhj[(curr_id*B + init_id)*S + r], gq * D[r]);
+							inner += bq.w[l] * (mode == 0 ? s_sfac[init_id*B + curr_id] : mode == 1 ? s_fac_t[init_id*B + curr_id] : s_fac_0[init_id*B + curr_id]);
+						}
+						hist_hess_term += hess_w * inner;
+					}
+#pragma unroll
+					for(int i = 0; i < S; ++i){
+#pragma unroll
+						for(int j = i; j < S; ++j) acc2[i*S - i*(i - 1) / 2 + (j - i)] = fma(hist_hess_term * D[i], D[j], acc2[i*S - i*(i - 1) / 2 + (j - i)]);
 					}
 				}
-			}
-			cta_sync<T>();
-			for(int i = tid; i < B*B; i += T){
-				const double jh = s_sj[i] * mp.hist_norm_mult;
-				s_sj[i] = jh;
-				s_sfac[i] = 1 + log(jh) - s_hist_log[i % B];                          // self_grad_factor(curr, init) (MI.cc:655)
-			}
-			cta_sync<T>();
-			// ---- cmptSelfHessian(curr_pix_jacobian) (MI.cc:558-592): the same sweep as the template's in mi_init_kernel
-			double acc2[NH];
-#pragma unroll
-			for(int i = 0; i < NH; ++i) acc2[i] = 0;
-			for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-				PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
-				Sample smp;
-				pixel_value_and_gradient<SSM, false>(b, W, g, smp);
-				double D[S];
-				pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
-				const double v = KEEP_IT ? s_It[it.pix] : (b.pix_mult*smp.val + b.pix_add);
-				const BinWeights bw = bin_weights(v, B);
-				double x = bw.lo - v, hist_hess_term = 0;
-#pragma unroll
-				for(int k = 0; k < 4; ++k){
-					const int curr_id = bw.lo + k;
-					const double hess_w = mp.hist_norm_mult * bspl3_hess(x);
-					x += 1;
-					if(curr_id > bw.hi) continue;
-					const double grad_k = bw.d[k] * (-mp.hist_norm_mult);               // curr_hist_grad (MI.cc:240)
-					double inner = 0;
-#pragma unroll
-					for(int l = 0; l < 4; ++l){
-						const int init_id = bw.lo + l;
-						if(init_id > bw.hi) continue;
-						const double gq = grad_k * bw.w[l];
-#pragma unroll
-						for(int q = 0; q < S; ++q) atomicAdd(&s_jhj[(curr_id*B + init_id)*S + q], gq * D[q]);
-						inner += bw.w[l] * s_sfac[init_id*B + curr_id];
+				block_reduce<NH, T>(acc2, s_part2, s_sum2);             // also orders the atomics on s_jhj before the reads below
+				for(int e = tid; e < S*S; e += T){
+					const int i = e % S, j = e / S;
+					const int lo = i < j ? i : j, hi = i < j ? j : i;
+					double h = s_sum2[lo*S - lo*(lo - 1) / 2 + (hi - lo)];
+					for(int curr_id = 0; curr_id < B; ++curr_id) for(int init_id = 0; init_id < B; ++init_id){
+						const double joint = (mode == 0) ? s_sj[init_id*B + curr_id] : s_jh[(HMODE == 2) ? init_id*B + curr_id : 0];
+						const double marg = (mode == 2) ? s_ihist[(HMODE == 2) ? init_id : 0] : s_hist[curr_id];
+						const double hist_factor = (1.0 / joint) - (1.0 / marg);
+						const double *row = &s_jhj[(curr_id*B + init_id)*S];
+						h += row[i] * row[j] * hist_factor;
 					}
-					hist_hess_term += hess_w * inner;
+					s_Hc[j*S + i] = (mi == 0 ? 0.0 : s_Hc[j*S + i]) + coef*h;
 				}
-#pragma unroll
-				for(int i = 0; i < S; ++i){
-#pragma unroll
-					for(int j = i; j < S; ++j) acc2[i*S - i*(i - 1) / 2 + (j - i)] = fma(hist_hess_term * D[i], D[j], acc2[i*S - i*(i - 1) / 2 + (j - i)]);
-				}
-			}
-			block_reduce<NH, T>(acc2, s_part2, s_sum2);             // also orders the atomics on s_jhj before the reads below
-			for(int e = tid; e < S*S; e += T){
-				const int i = e % S, j = e / S;
-				const int lo = i < j ? i : j, hi = i < j ? j : i;
-				double h = s_sum2[lo*S - lo*(lo - 1) / 2 + (hi - lo)];
-				for(int curr_id = 0; curr_id < B; ++curr_id) for(int init_id = 0; init_id < B; ++init_id){
-					const double hist_factor = (1.0 / s_sj[init_id*B + curr_id]) - (1.0 / s_hist[curr_id]);
-					const double *row = &s_jhj[(curr_id*B + init_id)*S];
-					h += row[i] * row[j] * hist_factor;
-				}
-				s_Hc[j*S + i] = h;
+				cta_sync<T>();
 			}
 		}
 		if(tid < S){
@@ -431,8 +463,10 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		cta_sync<T>();
 		if(warp == 0){
 			f = s_f;
-			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, SELF ? s_Hc : nullptr, s_W, s_corners, s_init_corners,
-				lm, patch_status);
+			// HMODE 2: s_Hc is the complete Hessian of the pass
+			const int ctrl = (HMODE == 2) ? serial_step<SSM, SM, false, 0>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners,
+				s_init_corners, lm, patch_status) : serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, SELF ? s_Hc : nullptr, s_W,
+				s_corners, s_init_corners, lm, patch_status);
 			if(lane == 0) s_ctrl = ctrl;
 		}
 		cta_sync<T>();
@@ -471,19 +505,22 @@ cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, mp, mi_tab, st);
 }
 
-template<int SSM, int SM, int T, bool KEEP_IT, bool SELF> static cudaError_t launch_self(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
+template<int SSM, int SM, int T, bool KEEP_IT, int HMODE> static cudaError_t launch_self(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	const size_t smem = ((KEEP_IT ? (size_t)((b.N + 1) & ~1) : 0) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * 32) * sizeof(double);
 	if(smem > 180 * 1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT, SELF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT, HMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
-	mi_update_kernel<SSM, SM, T, KEEP_IT, SELF><<<b.P, T, smem, st>>>(b, mp, mi_tab);
+	mi_update_kernel<SSM, SM, T, KEEP_IT, HMODE><<<b.P, T, smem, st>>>(b, mp, mi_tab);
 	return cudaGetLastError();
 }
 template<int SSM, int SM, int T, bool KEEP_IT> static cudaError_t launch_keep(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	// the pass's own self Hessian is needed by CurrentSelf (all three searches) and ESM's SumOfSelf
 	const bool self = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_CURRENT_SELF || b.hess_type == MTFB_ESM_HESS_SUM_OF_SELF)
 		: (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
-	return self ? launch_self<SSM, SM, T, KEEP_IT, true>(b, mp, mi_tab, st) : launch_self<SSM, SM, T, KEEP_IT, false>(b, mp, mi_tab, st);
+	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD)
+		: (b.hess_type == MTFB_LK_HESS_STD);
+	if(std_hess) return launch_self<SSM, SM, T, KEEP_IT, 2>(b, mp, mi_tab, st);
+	return self ? launch_self<SSM, SM, T, KEEP_IT, 1>(b, mp, mi_tab, st) : launch_self<SSM, SM, T, KEEP_IT, 0>(b, mp, mi_tab, st);
 }
 template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	if((size_t)b.N * sizeof(double) <= 24 * 1024) return launch_keep<SSM, SM, T, true>(b, mp, mi_tab, st);

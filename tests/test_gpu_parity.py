@@ -299,7 +299,8 @@ def test_ncc_std_hessians(seq384, sm, hess, jac, ssm):
     assert np.isfinite(g.getRegion()).all()
 
 
-@pytest.mark.parametrize("sm,hess", [("fclk", "current_self"), ("esm", "sum_of_self"), ("esm", "current_self"), ("iclk", "current_self")])
+@pytest.mark.parametrize("sm,hess", [("fclk", "current_self"), ("esm", "sum_of_self"), ("esm", "current_self"), ("iclk", "current_self"),
+                                     ("fclk", "std"), ("iclk", "std"), ("esm", "std"), ("esm", "sum_of_std")])
 @pytest.mark.parametrize("ssm", SSMS)
 def test_mi_per_pass_self_hessian(seq384, sm, hess, ssm):
     """MI::cmptSelfHessian(curr_pix_jacobian) every pass (MI.cc:515-594: cmptSelfHist, self_grad_factor, joint_hist_jacobian):
