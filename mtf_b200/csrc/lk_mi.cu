@@ -528,11 +528,11 @@ template<int SSM, int SM, int T> static cudaError_t launch_one(const DevBatch &b
 }
 template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const DevBatch &b, const MiParams &mp, const double *mi_tab,
 	cudaStream_t st){
+	// one or two warps per patch: the private histogram copies (18 KB per warp at 8 bins) leave no room for more, and the
+	// library never picks more for MI (mtfb_create); wider requests run at two
 	switch(threads){
 	case 32: return launch_one<SSM, SM, 32>(b, mp, mi_tab, st);
-	case 64: return launch_one<SSM, SM, 64>(b, mp, mi_tab, st);
-	case 128: return launch_one<SSM, SM, 128>(b, mp, mi_tab, st);
-	case 256: return launch_one<SSM, SM, 256>(b, mp, mi_tab, st);
+	case 64: case 128: case 256: return launch_one<SSM, SM, 64>(b, mp, mi_tab, st);
 	default: return cudaErrorInvalidValue;
 	}
 }
