@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
 	const double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
-	const bool jac_half = (SM == SM_ESM);
+	const bool jac_orig = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL);
+	const bool hess_orig = (SM == SM_ESM) && (b.hess_type == MTFB_ESM_HESS_ORIGINAL);        // cmptCurrHessian(mean_pix_jacobian)
+	const bool jac_half = (SM == SM_ESM) && !jac_orig;
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
@@ -330,17 +332,21 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 					}
 				}
 			}
+			double D[S], D0[S];
+			if(INIT) init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
 			if(CURR){
 				Sample smp;
 				pixel_value_and_gradient<SSM, false>(b, W, g, smp);
-				double D[S];
 				pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
+				// ESM's Original Jacobian: df_dIt . mean_pix_jacobian (NT/ESM.cc:246-248, 301-303)
+				if(SM == SM_ESM && jac_orig){
+#pragma unroll
+					for(int i = 0; i < S; ++i) D[i] = (D0[i] + D[i]) / 2.0;
+				}
 #pragma unroll
 				for(int i = 0; i < S; ++i) acc[oT + i] = fma(df_t, D[i], acc[oT + i]);
 			}
 			if(INIT){
-				double D0[S];
-				init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
 #pragma unroll
 				for(int i = 0; i < S; ++i) acc[o0 + i] = fma(df_0, D0[i], acc[o0 + i]);
 			}
@@ -405,6 +411,12 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 						pixel_value_and_gradient<SSM, false>(b, W, g, smp);
 						pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, D);
 						vc = KEEP_IT ? s_It[it.pix] : (b.pix_mult*smp.val + b.pix_add);
+						if(SM == SM_ESM && hess_orig){
+							double D0[S];
+							init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
+#pragma unroll
+							for(int i = 0; i < S; ++i) D[i] = (D0[i] + D[i]) / 2.0;
+						}
 					}
 					const double vp = (mode == 2) ? I0[it.pix] : vc;
 					const BinWeights bp = bin_weights(vp, B);
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		}
 		if(tid < S){
 			double jv = CURR ? s_sum[oT + tid] : 0.0;
-			if(SM == SM_ESM) jv = jv - s_sum[o0 + tid];                             // AppearanceModel.h:162-166
+			if(SM == SM_ESM && !jac_orig) jv = jv - s_sum[o0 + tid];                // AppearanceModel.h:162-166
 			if(SM == SM_ICLK) jv = s_sum[o0 + tid];
 			s_J[tid] = jac_half ? jv * 0.5 : jv;
 		}
@@ -517,8 +529,8 @@ template<int SSM, int SM, int T, bool KEEP_IT> static cudaError_t launch_keep(co
 	// the pass's own self Hessian is needed by CurrentSelf (all three searches) and ESM's SumOfSelf
 	const bool self = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_CURRENT_SELF || b.hess_type == MTFB_ESM_HESS_SUM_OF_SELF)
 		: (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
-	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD)
-		: (b.hess_type == MTFB_LK_HESS_STD);
+	const bool std_hess = (SM == SM_ESM) ? (b.hess_type == MTFB_ESM_HESS_STD || b.hess_type == MTFB_ESM_HESS_SUM_OF_STD ||
+		b.hess_type == MTFB_ESM_HESS_ORIGINAL) : (b.hess_type == MTFB_LK_HESS_STD);
 	if(std_hess) return launch_self<SSM, SM, T, KEEP_IT, 2>(b, mp, mi_tab, st);
 	return self ? launch_self<SSM, SM, T, KEEP_IT, 1>(b, mp, mi_tab, st) : launch_self<SSM, SM, T, KEEP_IT, 0>(b, mp, mi_tab, st);
 }

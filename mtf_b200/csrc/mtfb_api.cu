@@ -61,12 +61,11 @@ bool combo_supported(const mtfb_params *p, const char **why){
 	}
 	if(p->am == MTFB_AM_MI){
 		// the self Hessians (init_self_hessian and the per-pass cmptSelfHessian, MI.cc:515-594) and the Std forms
-		// cmptInitHessian / cmptCurrHessian (MI.cc:461-514, 603-637) are implemented; ESM's Original variants (mean pixel
-		// Jacobian) are not
-		const bool ok = (p->sm == MTFB_SM_ESM) ? (p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS && p->hess_type != MTFB_ESM_HESS_ORIGINAL &&
+		// cmptInitHessian / cmptCurrHessian (MI.cc:461-514, 603-637) are implemented, for ESM also on the mean pixel Jacobian
+		const bool ok = (p->sm == MTFB_SM_ESM) ? ((p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS || p->jac_type == MTFB_ESM_JAC_ORIGINAL) &&
 				p->hess_type >= MTFB_ESM_HESS_INITIAL_SELF && p->hess_type <= MTFB_ESM_HESS_STD)
 			: (p->hess_type >= MTFB_LK_HESS_INITIAL_SELF && p->hess_type <= MTFB_LK_HESS_STD);
-		if(!ok){ *why = "MI: ESM's Original Hessian / Jacobian (mean pixel Jacobian) are not implemented"; return false; }
+		if(!ok){ *why = "MI: unknown Hessian / Jacobian type"; return false; }
 		if(p->mi_n_bins < 4 || p->mi_n_bins > 16){ *why = "MI: 4 <= mi_n_bins <= 16"; return false; }
 		if(p->mi_pou && p->mi_n_bins < 6){ *why = "MI: partition of unity needs mi_n_bins >= 6"; return false; }
 		return true;

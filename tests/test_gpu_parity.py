@@ -300,7 +300,8 @@ def test_ncc_std_hessians(seq384, sm, hess, jac, ssm):
 
 
 @pytest.mark.parametrize("sm,hess", [("fclk", "current_self"), ("esm", "sum_of_self"), ("esm", "current_self"), ("iclk", "current_self"),
-                                     ("fclk", "std"), ("iclk", "std"), ("esm", "std"), ("esm", "sum_of_std")])
+                                     ("fclk", "std"), ("iclk", "std"), ("esm", "std"), ("esm", "sum_of_std"),
+                                     ("esm", "original"), ("esm", "original_jac")])
 @pytest.mark.parametrize("ssm", SSMS)
 def test_mi_per_pass_self_hessian(seq384, sm, hess, ssm):
     """MI::cmptSelfHessian(curr_pix_jacobian) every pass (MI.cc:515-594: cmptSelfHist, self_grad_factor, joint_hist_jacobian):
@@ -308,14 +309,17 @@ def test_mi_per_pass_self_hessian(seq384, sm, hess, ssm):
     from mtf_b200 import api
     frames, _ = seq384
     cs = np.concatenate([common.patches(2, 52.3, 384, 384, seed=31), common.quad_patches(2, 384, 384, seed=32)])
+    jac = 1
+    if hess == "original_jac":          # ESM's Original Jacobian (mean pixel Jacobian) with its default Hessian
+        hess, jac = "sum_of_self", 0
     h = (api.ESM_HESS if sm == "esm" else api.LK_HESS)[hess]
-    g = _gpu("mi", ssm, sm, len(cs), hess_type=h, max_iters=6)
+    g = _gpu("mi", ssm, sm, len(cs), hess_type=h, jac_type=jac, max_iters=6)
     g.enable_iter_log(6)
     g.initialize(cs, frames[0])
     g.update(frames[1])
     logs, n_it = g.iter_log(), g.n_iters()
     for i, c in enumerate(cs):
-        o = _oracle("mi", ssm, sm, grad_mode=1, hess_type=h, max_iters=6)
+        o = _oracle("mi", ssm, sm, grad_mode=1, hess_type=h, jac_type=jac, max_iters=6)
         o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
         ol = o.log()
         assert n_it[i] == o.n_iters == len(ol) == len(logs[i])
