@@ -498,6 +498,7 @@ static MiParams make_mi_params(const DevBatch &b, int n_bins, double pre_seed){
 	return mp;
 }
 
+#ifndef MTFB_MI_AFFINE_TU
 template<int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &b, const double *d_corners, const MiParams &mp,
 	double *mi_tab, cudaStream_t st){
 	switch(threads){
@@ -516,6 +517,8 @@ cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double
 	if(ssm == SSM_HOM) return launch_init_t<SSM_HOM>(threads, b, d_corners, mp, mi_tab, st);
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, mp, mi_tab, st);
 }
+
+#endif
 
 template<int SSM, int SM, int T, bool KEEP_IT, int HMODE> static cudaError_t launch_self(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	const size_t smem = ((KEEP_IT ? (size_t)((b.N + 1) & ~1) : 0) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * 32) * sizeof(double);
@@ -548,6 +551,10 @@ template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const 
 	default: return cudaErrorInvalidValue;
 	}
 }
+// the update kernels are instantiated in two translation units (this file for the homography, lk_mi_aff.cu -- which
+// includes this file with MTFB_MI_AFFINE_TU -- for the affine SSM): they compile in parallel
+cudaError_t launch_update_mi_aff(int sm, int threads, const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st);
+#ifndef MTFB_MI_AFFINE_TU
 cudaError_t launch_update_mi(int ssm, int sm, int threads, const DevBatch &b, int n_bins, double pre_seed, const double *mi_tab,
 	cudaStream_t st){
 	const MiParams mp = make_mi_params(b, n_bins, pre_seed);
@@ -556,9 +563,14 @@ cudaError_t launch_update_mi(int ssm, int sm, int threads, const DevBatch &b, in
 		if(sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, b, mp, mi_tab, st);
 		return launch_update_t<SSM_HOM, SM_ICLK>(threads, b, mp, mi_tab, st);
 	}
+	return launch_update_mi_aff(sm, threads, b, mp, mi_tab, st);
+}
+#else
+cudaError_t launch_update_mi_aff(int sm, int threads, const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
 	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, b, mp, mi_tab, st);
 	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, b, mp, mi_tab, st);
 	return launch_update_t<SSM_AFF, SM_ICLK>(threads, b, mp, mi_tab, st);
 }
+#endif
 
 } // namespace mtfb
