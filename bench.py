@@ -16,6 +16,8 @@ sampling indices, the arithmetic north_star specifies) fills the contract's keys
              launching stream, L2 flushed between steps, max over ranks
   e2e        the same through the reference-facing API with HOST buffers: pinned frame -> H2D -> update ->
              D2H of the P x 8 corners inside the timed region
+  e2e_raw_u8 the same from the RAW uint8 frame MTF's pre-processor would receive: 1 MB upload, gray + 5 x 5 Gaussian on the
+             device (mtfb_set_image_u8), update, D2H
   roofline   algorithmic HBM bytes ((8N + 432) per patch-iteration) / kernel time vs the measured
              copy bandwidth of MEASURED_PEAKS.json
   cpu_baseline  the oracle (CPU restatement of the reference, kind "port") on the box's host cores, bounded sample
