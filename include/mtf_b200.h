@@ -164,7 +164,7 @@ mtfb_status mtfb_get_iter_log(mtfb_ctx *ctx, mtfb_iter_log *out /* P x n_slots, 
 
 /* replaces the PF particle loop NT/PF.cc:303-320: for object o (one initialised patch = one template) and
  * each of its n_particles states: ssm.setState -> am.updatePixVals -> am.updateSimilarity(false) ->
- * am.getLikelihood() (SSD.h:41-43, NCC.cc:50-53; SSD and NCC).  states: P x n_particles x S; outputs P x n_particles
+ * am.getLikelihood() (SSD.h:41-43, NCC.cc:50-53, MI.cc:384-387).  states: P x n_particles x S; outputs P x n_particles
  * (NULL allowed). Host pointers. */
 mtfb_status mtfb_pf_evaluate(mtfb_ctx *ctx, const double *states, int n_particles,
 	double *likelihood, double *similarity);

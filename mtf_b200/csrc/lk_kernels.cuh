@@ -73,6 +73,9 @@ cudaError_t launch_update_mi(int ssm, int sm, int threads, const DevBatch &b, in
 // preproc.cu: uint8 gray / BGR frame (pitch in bytes) -> float frame (pitch in elements); k5 = the 5 kernel taps
 cudaError_t launch_preproc_gauss5(const unsigned char *d_src, int src_pitch, int channels, float *d_dst, int dst_pitch, int h, int w,
 	const float *k5, cudaStream_t st);
+// MI particle evaluation (lk_mi.cu)
+cudaError_t launch_pf_evaluate_mi(int ssm, const DevBatch &b, int n_bins, double pre_seed, const double *mi_tab, const double *d_states,
+	int n_particles, double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st);
 // pf_kernels.cu
 cudaError_t launch_pf_evaluate(int am, int ssm, const DevBatch &b, const double *d_states, int n_particles,
 	double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st);

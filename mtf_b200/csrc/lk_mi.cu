@@ -551,6 +551,109 @@ template<int SSM, int SM> static cudaError_t launch_update_t(int threads, const 
 	default: return cudaErrorInvalidValue;
 	}
 }
+#ifndef MTFB_MI_AFFINE_TU
+// ------------------------------------------------------------------------------------------------
+// Particle evaluation for MI (the particle loop of nt::PF::update, SM/src/NT/PF.cc:303-320, with am = MI):
+// ssm->setState -> am->updatePixVals (MI.cc:166-192) -> am->updateSimilarity(false) (MI.cc:346-382: curr_hist and
+// joint_hist through the 4 x 4 B-spline weights, logs, f = sum joint (log joint - log curr - log init)) ->
+// am->getLikelihood() (MI.cc:384-387).  One warp per particle with a private copy of both histograms per lane, as
+// in the update kernel (conflict-free read-modify-writes, fixed summation order); the template's values stay in shared memory.
+// ------------------------------------------------------------------------------------------------
+template<int SSM, int T>
+__global__ void __launch_bounds__(T) pf_evaluate_mi_kernel(DevBatch b, MiParams mp, const double *__restrict__ mi_tab,
+	const double *__restrict__ states, int n_particles, double *__restrict__ likelihood, double *__restrict__ similarity, double alpha){
+	constexpr int S = StateSize<SSM>::value;
+	constexpr int NW = T / 32;
+	extern __shared__ __align__(16) double s_dyn[];
+	const int obj = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int B = mp.B, N = b.N, HB = B + B*B;
+	double *s_I0 = s_dyn;                                                   // N template values (bin units)
+	double *s_priv = s_dyn + ((N + 1) & ~1) + (size_t)warp*HB * 32;          // [entry][lane] private histograms of this warp
+	__shared__ double s_ihist_log[MI_BMAX], s_h[NW][MI_HBMAX], s_hlog[NW][MI_BMAX];
+	for(int i = tid; i < N; i += T) s_I0[i] = b.I0[(size_t)obj*N + i];
+	for(int i = tid; i < B; i += T) s_ihist_log[i] = mi_tab[(size_t)obj*MI_TAB + 16 + i];
+	Mat3 dlt;
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = b.dlt[(size_t)obj * 9 + i];
+	__syncthreads();
+	for(int pi = blockIdx.x*NW + warp; pi < n_particles; pi += gridDim.x*NW){
+		const double *st = states + ((size_t)obj*n_particles + pi)*S;
+		double sv[S];
+#pragma unroll
+		for(int q = 0; q < S; ++q) sv[q] = st[q];
+		const Mat3 W = warp_from_state<SSM>(sv);
+		for(int e = 0; e < HB; ++e) s_priv[e * 32 + lane] = 0;
+		for(PixIter it(lane, 32, b.resx); it.pix < N; it.next(32)){
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+			const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
+			const BinWeights bc = bin_weights(It, B), bi = bin_weights(s_I0[it.pix], B);
+#pragma unroll
+			for(int k = 0; k < 4; ++k){
+				if(bc.lo + k > bc.hi) continue;
+				s_priv[(bc.lo + k) * 32 + lane] += bc.w[k];
+#pragma unroll
+				for(int l = 0; l < 4; ++l){
+					if(bi.lo + l > bi.hi) continue;
+					s_priv[(B + (bi.lo + l)*B + (bc.lo + k)) * 32 + lane] += bc.w[k] * bi.w[l];    // JH(curr_id, init_id)
+				}
+			}
+		}
+		__syncwarp();
+		for(int e = 0; e < HB; ++e){
+			double v = s_priv[e * 32 + lane];
+#pragma unroll
+			for(int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL_MASK, v, off);
+			if(lane == 0) s_h[warp][e] = ((e < B ? mp.hist_pre_seed : mp.pre_seed) + v) * mp.hist_norm_mult;
+		}
+		__syncwarp();
+		for(int i = lane; i < B; i += 32) s_hlog[warp][i] = log(s_h[warp][i]);
+		__syncwarp();
+		double fs = 0;
+		for(int i = lane; i < B*B; i += 32){
+			const double jh = s_h[warp][B + i];
+			fs += jh * (log(jh) - s_hlog[warp][i % B] - s_ihist_log[i / B]);            // MI.cc:376-380
+		}
+#pragma unroll
+		for(int off = 16; off >= 1; off >>= 1) fs += __shfl_xor_sync(FULL_MASK, fs, off);
+		if(lane == 0){
+			if(similarity) similarity[(size_t)obj*n_particles + pi] = fs;
+			const double d = (1.0 / fs) - 1;                                            // MI.cc:384-387
+			if(likelihood) likelihood[(size_t)obj*n_particles + pi] = exp(-alpha * d*d);
+		}
+		__syncwarp();
+	}
+}
+
+cudaError_t launch_pf_evaluate_mi(int ssm, const DevBatch &b, int n_bins, double pre_seed, const double *mi_tab, const double *d_states,
+	int n_particles, double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st){
+	if(n_bins < 4 || n_bins > MI_BMAX) return cudaErrorInvalidValue;
+	const MiParams mp = make_mi_params(b, n_bins, pre_seed);
+	constexpr int T = 128;
+	const size_t smem = ((size_t)((b.N + 1) & ~1) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * 32) * sizeof(double);
+	if(smem > 200 * 1024) return cudaErrorInvalidValue;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int ctas_per_sm = (int)((200 * 1024) / (smem + 2048)) < 1 ? 1 : (int)((200 * 1024) / (smem + 2048));
+	int per_obj = (sms*ctas_per_sm + b.P - 1) / b.P;
+	const int max_useful = (n_particles + T / 32 - 1) / (T / 32);
+	if(per_obj > max_useful) per_obj = max_useful;
+	if(per_obj < 1) per_obj = 1;
+	const dim3 grid(per_obj, b.P);
+	cudaError_t e;
+	if(ssm == SSM_HOM){
+		e = cudaFuncSetAttribute(pf_evaluate_mi_kernel<SSM_HOM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return e;
+		pf_evaluate_mi_kernel<SSM_HOM, T><<<grid, T, smem, st>>>(b, mp, mi_tab, d_states, n_particles, d_likelihood, d_similarity, alpha);
+	} else{
+		e = cudaFuncSetAttribute(pf_evaluate_mi_kernel<SSM_AFF, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return e;
+		pf_evaluate_mi_kernel<SSM_AFF, T><<<grid, T, smem, st>>>(b, mp, mi_tab, d_states, n_particles, d_likelihood, d_similarity, alpha);
+	}
+	return cudaGetLastError();
+}
+#endif
+
 // the update kernels are instantiated in two translation units (this file for the homography, lk_mi_aff.cu -- which
 // includes this file with MTFB_MI_AFFINE_TU -- for the affine SSM): they compile in parallel
 cudaError_t launch_update_mi_aff(int sm, int threads, const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st);

@@ -43,8 +43,9 @@ bool combo_supported(const mtfb_params *p, const char **why){
 	const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
 	if(!(p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE)){ *why = "ssm must be homography or affine"; return false; }
 	if(p->sm == MTFB_SM_PF){
-		if(p->am != MTFB_AM_SSD && p->am != MTFB_AM_NCC){ *why = "PF particle evaluation is implemented for SSD and NCC"; return false; }
-		return true;
+		if(p->am == MTFB_AM_MI && (p->mi_n_bins < 4 || p->mi_n_bins > 16)){ *why = "MI: 4 <= mi_n_bins <= 16"; return false; }
+		if(p->am == MTFB_AM_MI && p->mi_pou && p->mi_n_bins < 6){ *why = "MI: partition of unity needs mi_n_bins >= 6"; return false; }
+		return p->am == MTFB_AM_SSD || p->am == MTFB_AM_NCC || p->am == MTFB_AM_MI;
 	}
 	if(!gn){ *why = "sm must be esm, fclk, iclk or pf"; return false; }
 	if(p->am == MTFB_AM_SSD) return true;
@@ -501,9 +502,12 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *c, const double *d_states, int n_particles, double *d_likelihood, double *d_similarity){
 	if(!c || !d_states || n_particles < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_evaluate_device: bad argument");
 	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_pf_evaluate_device: initialize has not been called");
-	if(c->prm.am != MTFB_AM_SSD && c->prm.am != MTFB_AM_NCC) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_evaluate_device: implemented for SSD and NCC");
+
 	CUDA_TRY(cudaSetDevice(c->prm.device));
-	if(c->prm.precision == MTFB_PRECISION_F32)
+	if(c->prm.am == MTFB_AM_MI)
+		CUDA_TRY(launch_pf_evaluate_mi(c->prm.ssm, c->b, c->prm.mi_n_bins, c->prm.mi_pre_seed, c->d_mi_tab, d_states, n_particles,
+			d_likelihood, d_similarity, c->prm.likelihood_alpha, c->stream));
+	else if(c->prm.precision == MTFB_PRECISION_F32)
 		CUDA_TRY(launch_pf_evaluate_f32(c->prm.ssm, c->b, d_states, n_particles, d_likelihood, d_similarity, c->prm.likelihood_alpha, c->stream));
 	else
 		CUDA_TRY(launch_pf_evaluate(c->prm.am, c->prm.ssm, c->b, d_states, n_particles, d_likelihood, d_similarity,

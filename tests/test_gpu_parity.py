@@ -385,7 +385,7 @@ def test_ncc_tracking_vs_reference_fd(seq384, ssm, lm):
 
 # ------------------------------------------------------------------------------------------------ PF
 @pytest.mark.parametrize("ssm", SSMS)
-@pytest.mark.parametrize("am", ["ssd", "ncc"])
+@pytest.mark.parametrize("am", ["ssd", "ncc", "mi"])
 def test_pf_evaluate(seq384, ssm, am):
     """per-particle parity (the reference's particle trajectories are seeded from random_device, so
     parity is defined per particle given the state)"""
