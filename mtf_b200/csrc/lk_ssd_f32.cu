@@ -27,6 +27,7 @@
 //
 // This file is compiled with -fmad=false like the rest (the fp64 slow path must not contract); fp32 fused
 // multiply-adds are spelled fmaf().
+#include <type_traits>
 #include "lk_solve.cuh"
 
 namespace mtfb {
@@ -199,9 +200,10 @@ template<int SSM> __device__ __forceinline__ void pass_constants(const DevBatch 
 // (wi[0], wi[1]) still hold every neighbour the patch's samples can touch -- the integer hull of its four corners plus
 // one?  If not, pick a new origin centred on the patch (clipped to the frame) and ask for a restage; a patch that does
 // not fit the window (or a frame smaller than it) samples the frame in global memory for this pass.
-// wi: 0 ox, 1 oy, 2 use the window this pass, 3 restage before the pass, 4 window contents valid
+// wi: 0 ox, 1 oy, 2 use the window this pass, 3 restage before the pass, 4 window contents valid, 5 the window holds the
+// whole hull (+ 1 pixel) of the patch: no per-sample range test needed
 __device__ __forceinline__ void window_decide(const DevBatch &b, const double *corners, bool have_window, int *wi){
-	wi[2] = 0; wi[3] = 0;
+	wi[2] = 0; wi[3] = 0; wi[5] = 0;
 	if(!have_window || b.img.w < F32_WIN || b.img.h < F32_WIN) return;
 	// fp32 is enough: the hull is widened by a pixel, and a sample the window misses takes the fp64 path anyway
 	float x0 = (float)corners[0], x1 = x0, y0 = (float)corners[4], y1 = y0;
@@ -221,6 +223,8 @@ __device__ __forceinline__ void window_decide(const DevBatch &b, const double *c
 		wi[0] = ox; wi[1] = oy; wi[3] = 1; wi[4] = 1;
 	}
 	wi[2] = 1;
+	// (false only when the clipping at the frame border moved the window off the patch)
+	wi[5] = (ix0 >= wi[0] && ix1 <= wi[0] + F32_WIN - 1 && iy0 >= wi[1] && iy1 <= wi[1] + F32_WIN - 1) ? 1 : 0;
 }
 
 // per-patch setup by warp 0: template frame, basis maps, centred DLT rows, first pass constants
@@ -280,7 +284,9 @@ __device__ __forceinline__ void fast_floor(float x, float &fl, int &il){
 // pixel cell (o.fast) -- the bilinear sample and its gradient.  Loads are issued for every lane (at a safe address
 // when !fast) so that two pixels can be interleaved without a branch in between.
 //   dl[9]: rows of the centred / scaled DLT (patch_setup) -- unused with normalized_init
-template<int SSM> __device__ __forceinline__ void front_fast(const DevBatch &b, const PassConst &k, const float (&dl)[9], bool dlt_affine,
+// CHK = false: the caller knows that every sample's four neighbours lie inside the array it reads (the frame window covers the
+// hull of the patch's corners plus a pixel: window_decide), so the four range comparisons are dropped.
+template<int SSM, bool CHK = true> __device__ __forceinline__ void front_fast(const DevBatch &b, const PassConst &k, const float (&dl)[9], bool dlt_affine,
 	float rowf, float colf, PixF &o){
 	const float u = fmaf(colf, b.gx_step, b.gx_lo), v = fmaf(rowf, b.gy_step, b.gy_lo);
 	o.xl = fmaf(dl[0], u, fmaf(dl[1], v, dl[2]));
@@ -305,8 +311,8 @@ template<int SSM> __device__ __forceinline__ void front_fast(const DevBatch &b, 
 	const float dx = o.wxl - fx, dy = o.wyl - fy;
 	const float hi = 1.0f - k.delta;
 	// written so that NaN fails
-	o.fast = (dx >= k.delta) && (dx <= hi) && (dy >= k.delta) && (dy <= hi) &&
-		(fx >= k.lox) && (fx <= k.hix) && (fy >= k.loy) && (fy <= k.hiy);
+	o.fast = (dx >= k.delta) && (dx <= hi) && (dy >= k.delta) && (dy <= hi);
+	if(CHK) o.fast = o.fast && (fx >= k.lox) && (fx <= k.hix) && (fy >= k.loy) && (fy <= k.hiy);
 	o.lx = k.X0 + ix; o.ly = k.Y0 + iy;
 	const int off = o.fast ? (k.Yr + iy)*k.pitch + (k.Xr + ix) : 0;
 	const float *r0 = k.base + off, *r1 = r0 + k.pitch;
@@ -672,7 +678,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8], s_dlt[9];
 	__shared__ double s_J[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_Tinv[S*S], s_loc[3], s_x[S], s_dp[S];
 	__shared__ float s_cf[C_COUNT], s_dl[9];
-	__shared__ int s_ci[2], s_wi[5];
+	__shared__ int s_ci[2], s_wi[6];
 	__shared__ int s_ctrl;
 	extern __shared__ __align__(16) float s_tmpl[];
 	__shared__ __align__(8) unsigned long long s_bar;
@@ -749,28 +755,33 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 		// bit in this thread's column of s_slow; the bits are worked off after the loop.  (Nearly) every pixel is slow only
 		// when the warp sits on the pixel lattice -- the first pass after initialize() with an integer-aligned box.
 		for(int w = 0; w < slow_words; ++w) s_slow[w*T + tid] = 0u;
-		PixIterF it[U];
+		auto pixel_loop = [&](auto chk){
+			constexpr bool CHK = decltype(chk)::value;
+			PixIterF it[U];
 #pragma unroll
-		for(int u = 0; u < U; ++u) it[u] = it_first[u];
-		for(int g = 0; it[0].pix < b.N; g += U){
-			bool vu[U]; int pixu[U]; float rowu[U], colu[U], i0[U];
-			PixF px[U];
+			for(int u = 0; u < U; ++u) it[u] = it_first[u];
+			for(int g = 0; it[0].pix < b.N; g += U){
+				bool vu[U]; int pixu[U]; float rowu[U], colu[U], i0[U];
+				PixF px[U];
 #pragma unroll
-			for(int u = 0; u < U; ++u){
-				vu[u] = (u == 0) || (it[u].pix < b.N);
-				pixu[u] = vu[u] ? it[u].pix : it[0].pix; rowu[u] = vu[u] ? it[u].rowf : it[0].rowf; colu[u] = vu[u] ? it[u].colf : it[0].colf;
-				i0[u] = tmpl[pixu[u]];
+				for(int u = 0; u < U; ++u){
+					vu[u] = (u == 0) || (it[u].pix < b.N);
+					pixu[u] = vu[u] ? it[u].pix : it[0].pix; rowu[u] = vu[u] ? it[u].rowf : it[0].rowf; colu[u] = vu[u] ? it[u].colf : it[0].colf;
+					i0[u] = tmpl[pixu[u]];
+				}
+#pragma unroll
+				for(int u = 0; u < U; ++u) front_fast<SSM, CHK>(b, k, dl, dlt_affine, rowu[u], colu[u], px[u]);
+#pragma unroll
+				for(int u = 0; u < U; ++u){
+					if(vu[u] && !px[u].fast) s_slow[((g + u) >> 5)*T + tid] |= 1u << ((g + u) & 31);      // pixel tid + (g + u) T
+					accumulate_pixel<SSM, SM>(b, k, px[u], i0[u], G0, pixu[u], vu[u] && px[u].fast, need_grad, esm_mean, acc);
+				}
+#pragma unroll
+				for(int u = 0; u < U; ++u) it[u].next(U*T);
 			}
-#pragma unroll
-			for(int u = 0; u < U; ++u) front_fast<SSM>(b, k, dl, dlt_affine, rowu[u], colu[u], px[u]);
-#pragma unroll
-			for(int u = 0; u < U; ++u){
-				if(vu[u] && !px[u].fast) s_slow[((g + u) >> 5)*T + tid] |= 1u << ((g + u) & 31);      // pixel tid + (g + u) T
-				accumulate_pixel<SSM, SM>(b, k, px[u], i0[u], G0, pixu[u], vu[u] && px[u].fast, need_grad, esm_mean, acc);
-			}
-#pragma unroll
-			for(int u = 0; u < U; ++u) it[u].next(U*T);
-		}
+		};
+		// the window holds the patch's whole hull: no per-sample range test (uniform choice, once per pass)
+		if(s_wi[2] && s_wi[5]) pixel_loop(std::false_type{}); else pixel_loop(std::true_type{});
 		for(int w = 0; w < slow_words; ++w){
 			unsigned bits = s_slow[w*T + tid];
 			while(bits){
