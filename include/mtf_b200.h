@@ -60,6 +60,16 @@ enum { MTFB_LK_HESS_INITIAL_SELF = 0, MTFB_LK_HESS_CURRENT_SELF = 1, MTFB_LK_HES
  *        solve; Jacobian / Hessian / corners agree with F64 to fp32 tolerance.  SSD only: ESM / FCLK /
  *        ICLK with the chained warp, and PF particle evaluation. */
 enum { MTFB_PRECISION_F64 = 0, MTFB_PRECISION_F32 = 1 };
+/* how the F32 precision solves H dp = -J^T when the Hessian is the pass's own (FCLK / ESM CurrentSelf, no LM)
+ * (mtfb_params::f32_solve; F64 contexts always run the reference's solve):
+ *   REFERENCE: H and J^T are mapped from the kernel's centred accumulation basis to the reference's parameters in fp64 and
+ *        solved by the same column-pivoted Householder QR with Eigen's rank rule (`colPivHouseholderQr().solve`,
+ *        SM/src/NT/FCLK.cc:298, NT/ESM.cc:266) -- including the truncated steps that rule takes when raw pixel coordinates
+ *        (hom_normalized_init = 0) make H numerically rank deficient.
+ *   LOCAL: an 8 x 8 Gauss-Jordan solve in the centred basis (condition ~1e3 instead of ~1e16), mapped back: the full
+ *        Gauss-Newton step -H^-1 J^T in exact arithmetic, without the rank decisions.  Faster; converges to the same fixed
+ *        point; per-pass updates differ from the reference's wherever its rank rule fires. */
+enum { MTFB_F32_SOLVE_REFERENCE = 0, MTFB_F32_SOLVE_LOCAL = 1 };
 /* per-patch status bits reported by mtfb_get_patch_status */
 enum { MTFB_PATCH_OK = 0, MTFB_PATCH_NAN = 1, MTFB_PATCH_SINGULAR = 2, MTFB_PATCH_OUT_OF_IMAGE = 4 };
 
@@ -95,6 +105,7 @@ typedef struct mtfb_params {
 	int occupancy;               /* register budget of the update kernel: 0 / 1 / 2 = about 8 / 12 /
 	                                16 resident warps per SM (tuning knob, results do not change)  */
 	int precision;               /* MTFB_PRECISION_F64 (default) or MTFB_PRECISION_F32                */
+	int f32_solve;               /* MTFB_F32_SOLVE_REFERENCE (default) or MTFB_F32_SOLVE_LOCAL; F32 only */
 } mtfb_params;
 
 /* one Gauss-Newton pass as the reference's record_event() trail would show it (NT/FCLK.cc:190-321);
@@ -196,6 +207,14 @@ mtfb_status mtfb_get_curr_stage_f32(mtfb_ctx *ctx, int *idx /* P x N x 2 */, flo
  * what a multi-GPU host all-gathers without a host round trip */
 mtfb_status mtfb_device_results(mtfb_ctx *ctx, double **d_corners, double **d_state, int **d_n_iters);
 int mtfb_state_size(const mtfb_ctx *ctx);
+
+/* test entry point (no reference counterpart as a function: the solve inside nt::FCLK / ESM / ICLK::update,
+ * `H.colPivHouseholderQr().solve(J^T)`, SM/src/NT/FCLK.cc:298, NT/ESM.cc:266, NT/ICLK.cc:228): runs the device's warp-level
+ * column-pivoted Householder QR on n_sys caller-supplied n x n systems (n = 6 or 8; A column-major, host pointers).
+ * fast = 0: the literal restatement of Eigen 3.3's computeInPlace (norm down-dating); 1: the tuned per-pass variant.
+ * Outputs: x (n_sys x n), nonzero_pivots (n_sys, may be NULL), perm (n_sys x n: original column at position i, may be NULL). */
+mtfb_status mtfb_debug_colpiv_qr_solve(int device, int n, int fast, int n_sys, const double *A, const double *b, double *x,
+	int *nonzero_pivots, int *perm);
 
 #ifdef __cplusplus
 }

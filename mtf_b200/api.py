@@ -20,6 +20,7 @@ ESM_HESS = {"initial_self": 0, "current_self": 1, "sum_of_self": 2, "original": 
 ESM_JAC = {"original": 0, "diff_of_jacs": 1}
 LK_HESS = {"initial_self": 0, "current_self": 1, "std": 2}
 PRECISION = {"f64": 0, "f32": 1}
+F32_SOLVE = {"reference": 0, "local": 1}
 
 STATUS_NAMES = {1: "InvalidArgument", 2: "FunctonNotImplemented", 3: "LogicError", 4: "InvalidTrackerState",
                 5: "CudaError", 6: "OutOfMemory"}
@@ -45,7 +46,7 @@ class Params(C.Structure):
                 ("hom_normalized_init", C.c_int), ("mi_n_bins", C.c_int),
                 ("mi_pre_seed", C.c_double), ("mi_pou", C.c_int),
                 ("likelihood_alpha", C.c_double), ("device", C.c_int), ("threads_per_patch", C.c_int),
-                ("occupancy", C.c_int), ("precision", C.c_int)]
+                ("occupancy", C.c_int), ("precision", C.c_int), ("f32_solve", C.c_int)]
 
 
 class IterLog(C.Structure):
@@ -62,7 +63,7 @@ EXPORTS = [
     "mtfb_pf_evaluate", "mtfb_pf_evaluate_device", "mtfb_get_corners", "mtfb_get_state", "mtfb_get_n_iters",
     "mtfb_get_similarity", "mtfb_get_patch_status", "mtfb_get_init_warp", "mtfb_get_init_pts",
     "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_get_curr_stage_f32", "mtfb_device_results",
-    "mtfb_state_size",
+    "mtfb_state_size", "mtfb_debug_colpiv_qr_solve",
 ]
 
 _lib = None
@@ -107,6 +108,7 @@ def load_library(path=LIB_PATH):
     L.mtfb_get_curr_stage_f32.argtypes = [vp, vp, vp, vp, vp, vp]
     L.mtfb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mtfb_state_size.argtypes = [vp]
+    L.mtfb_debug_colpiv_qr_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, ip]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params"):
@@ -135,6 +137,8 @@ def set_params(p, **kw):
             v = ESM_JAC[v]
         elif k == "precision" and isinstance(v, str):
             v = PRECISION[v]
+        elif k == "f32_solve" and isinstance(v, str):
+            v = F32_SOLVE[v]
         if not hasattr(p, k):
             raise KeyError(k)
         setattr(p, k, v)
@@ -153,6 +157,22 @@ def make_params(am="ssd", ssm="homography", sm="fclk", **kw):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def debug_colpiv_qr_solve(A, b, fast=False, device=0):
+    """the device's warp-level column-pivoted QR on host-supplied systems: A (n_sys, n, n), b (n_sys, n)
+    -> x (n_sys, n), nonzero_pivots (n_sys,), perm (n_sys, n)"""
+    L = load_library()
+    A = np.asarray(A, dtype=np.float64)
+    n_sys, n = A.shape[0], A.shape[-1]
+    Ac = np.ascontiguousarray(A.transpose(0, 2, 1))          # column-major per system
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty((n_sys, n)); nz = np.empty(n_sys, dtype=np.int32); perm = np.empty((n_sys, n), dtype=np.int32)
+    st = L.mtfb_debug_colpiv_qr_solve(device, n, 1 if fast else 0, n_sys, _dp(Ac), _dp(b), _dp(x),
+                                      nz.ctypes.data_as(C.POINTER(C.c_int)), perm.ctypes.data_as(C.POINTER(C.c_int)))
+    if st != 0:
+        raise MTFError(st, L.mtfb_last_error().decode())
+    return x, nz, perm
 
 
 class BatchTracker:

@@ -39,6 +39,7 @@ struct DevBatch {
 	int max_iters, hess_type, jac_type, leven_marq, nt_semantics;
 	int chained;                 // {esm,fc,ic}_chained_warp
 	int norm_init;               // hom_normalized_init
+	int f32_local_solve;         // mtfb_params::f32_solve == MTFB_F32_SOLVE_LOCAL
 	double epsilon, lm_delta_init, lm_delta_update, grad_eps;
 	double pix_mult, pix_add;    // am pix_norm_mult / pix_norm_add (1, 0 except MI)
 	double grad_mult;            // pix_mult / (2 grad_eps)  (imgUtils.cc:238)
@@ -76,6 +77,9 @@ cudaError_t launch_preproc_gauss5(const unsigned char *d_src, int src_pitch, int
 // MI particle evaluation (lk_mi.cu)
 cudaError_t launch_pf_evaluate_mi(int ssm, const DevBatch &b, int n_bins, double pre_seed, const double *mi_tab, const double *d_states,
 	int n_particles, double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st);
+// debug_kernels.cu
+cudaError_t launch_debug_qr_solve(int n, int fast, int n_sys, const double *d_A, const double *d_b, double *d_x, int *d_nz, int *d_perm,
+	cudaStream_t st);
 // pf_kernels.cu
 cudaError_t launch_pf_evaluate(int am, int ssm, const DevBatch &b, const double *d_states, int n_particles,
 	double *d_likelihood, double *d_similarity, double alpha, cudaStream_t st);

@@ -73,9 +73,10 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 		}
 	}
 	block_reduce<L::NA, T>(acc, s_part, s_sum);
-	if(tid < S*S){
-		int i = tid % S, j = tid / S;
-		int lo = i < j ? i : j, hi = i < j ? j : i;
+	// (strided: T = 32 threads write the 64 entries of the homography's Hessian in two trips)
+	for(int e = tid; e < S*S; e += T){
+		const int i = e % S, j = e / S;
+		const int lo = i < j ? i : j, hi = i < j ? j : i;
 		b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];        // SSD self Hessian: -J^T J
 	}
 }
@@ -123,17 +124,10 @@ __global__ void __launch_bounds__(T) ssd_reinit_kernel(DevBatch b, const double 
 		}
 	}
 	block_reduce<L::NA, T>(acc, s_part, s_sum);
-	if(tid < S*S){
-		int i = tid % S, j = tid / S;
-		int lo = i < j ? i : j, hi = i < j ? j : i;
+	for(int e = tid; e < S*S; e += T){
+		const int i = e % S, j = e / S;
+		const int lo = i < j ? i : j, hi = i < j ? j : i;
 		b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];
-	}
-	if(T == 32 && S*S > 32){
-		for(int e = tid + 32; e < S*S; e += 32){
-			const int i = e % S, j = e / S;
-			const int lo = i < j ? i : j, hi = i < j ? j : i;
-			b.Hinit[(size_t)p * 64 + j*S + i] = -s_sum[1 + S + L::tri(lo, hi)];
-		}
 	}
 }
 

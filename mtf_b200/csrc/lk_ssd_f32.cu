@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
 	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
 	// the Hessian of this pass alone, no damping, nobody watching the reference-basis matrices: solve in the local basis
-	const bool local_solve = (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
+	const bool local_solve = b.f32_local_solve && (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;

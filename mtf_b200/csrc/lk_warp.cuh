@@ -97,8 +97,9 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
 			maxn = __hiloint2double((int)mhi, (int)mlo);
 		}
-		const double th = maxn * DBL_EPSILON / double(ROWS);
-		const double threshold_helper = th * th;
+		// Eigen 3.3 computeInPlace(): threshold_helper = abs2(colNormsUpdated.maxCoeff() * epsilon) / rows
+		const double me = maxn * DBL_EPSILON;
+		const double threshold_helper = me * me / double(ROWS);
 		const double norm_downdate_threshold = sqrt(DBL_EPSILON);
 		nonzero_pivots = SIZE;
 #pragma unroll
@@ -285,8 +286,8 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
 			maxsq = __hiloint2double((int)mhi, (int)mlo);
 		}
-		const double e = DBL_EPSILON / double(ROWS);
-		const double thsq = maxsq * (e * e);                  // (max norm * eps / rows)^2, Eigen's threshold_helper
+		// Eigen's threshold_helper = (max norm * eps)^2 / rows, on the squared norms this factorisation keeps
+		const double thsq = maxsq * (DBL_EPSILON * DBL_EPSILON) / double(ROWS);
 		nonzero_pivots = SIZE;
 		fast_steps<0>(lane, is_col, is_rhs, csq, thsq);
 #pragma unroll

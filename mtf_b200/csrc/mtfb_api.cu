@@ -128,6 +128,7 @@ void mtfb_default_params(mtfb_params *p){
 	p->nt_semantics = 1; p->grad_eps = 1e-8; p->hom_normalized_init = 0;
 	p->mi_n_bins = 8; p->mi_pre_seed = 10; p->mi_pou = 0; p->likelihood_alpha = 1;
 	p->device = 0; p->threads_per_patch = 0; p->occupancy = 0; p->precision = MTFB_PRECISION_F64;
+	p->f32_solve = MTFB_F32_SOLVE_REFERENCE;
 }
 
 mtfb_status mtfb_destroy(mtfb_ctx *c){
@@ -156,6 +157,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
 	if(p->precision != MTFB_PRECISION_F64 && p->precision != MTFB_PRECISION_F32)
 		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: precision must be MTFB_PRECISION_F64 or MTFB_PRECISION_F32");
+	if(p->f32_solve != MTFB_F32_SOLVE_REFERENCE && p->f32_solve != MTFB_F32_SOLVE_LOCAL)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: f32_solve must be MTFB_F32_SOLVE_REFERENCE or MTFB_F32_SOLVE_LOCAL");
 	if(p->precision == MTFB_PRECISION_F32){
 		const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
 		const bool pf = p->sm == MTFB_SM_PF;
@@ -271,6 +274,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		// the templated search methods have no chained_warp switch: always chained (ESM.cc:94-95, FCLK.cc:82-86, ICLK.cc:80-90)
 		b.chained = (p->chained_warp || !p->nt_semantics) ? 1 : 0;
 		b.norm_init = p->hom_normalized_init ? 1 : 0;
+		b.f32_local_solve = (p->f32_solve == MTFB_F32_SOLVE_LOCAL) ? 1 : 0;
 		b.epsilon = p->epsilon; b.lm_delta_init = p->lm_delta_init; b.lm_delta_update = p->lm_delta_update;
 		b.grad_eps = p->grad_eps;
 		b.pix_mult = 1; b.pix_add = 0;
@@ -625,6 +629,26 @@ extern "C" int mtfb_prof_read(mtfb_ctx *c, long long *out, int n){
 	return (int)cudaMemcpy(out, c->b.n_iters_prof, n*sizeof(long long), cudaMemcpyDeviceToHost);
 }
 #endif
+
+mtfb_status mtfb_debug_colpiv_qr_solve(int device, int n, int fast, int n_sys, const double *A, const double *b, double *x,
+	int *nonzero_pivots, int *perm){
+	if(!A || !b || !x || n_sys < 1 || (n != 6 && n != 8)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_debug_colpiv_qr_solve: bad argument");
+	CUDA_TRY(cudaSetDevice(device));
+	double *d = nullptr; int *di = nullptr;
+	const size_t nA = (size_t)n_sys*n*n, nv = (size_t)n_sys*n;
+	CUDA_TRY(cudaMalloc(&d, (nA + 2 * nv)*sizeof(double)));
+	if(cudaMalloc(&di, (nv + n_sys)*sizeof(int)) != cudaSuccess){ cudaFree(d); return fail(MTFB_ERR_NO_MEMORY, "mtfb_debug_colpiv_qr_solve: out of device memory"); }
+	cudaError_t e = cudaMemcpy(d, A, nA*sizeof(double), cudaMemcpyHostToDevice);
+	if(e == cudaSuccess) e = cudaMemcpy(d + nA, b, nv*sizeof(double), cudaMemcpyHostToDevice);
+	if(e == cudaSuccess) e = launch_debug_qr_solve(n, fast, n_sys, d, d + nA, d + nA + nv, di, di + n_sys, 0);
+	if(e == cudaSuccess) e = cudaDeviceSynchronize();
+	if(e == cudaSuccess) e = cudaMemcpy(x, d + nA + nv, nv*sizeof(double), cudaMemcpyDeviceToHost);
+	if(e == cudaSuccess && nonzero_pivots) e = cudaMemcpy(nonzero_pivots, di, n_sys*sizeof(int), cudaMemcpyDeviceToHost);
+	if(e == cudaSuccess && perm) e = cudaMemcpy(perm, di + n_sys, nv*sizeof(int), cudaMemcpyDeviceToHost);
+	cudaFree(d); cudaFree(di);
+	if(e != cudaSuccess) return fail(MTFB_ERR_CUDA, "mtfb_debug_colpiv_qr_solve: %s", cudaGetErrorString(e));
+	return MTFB_OK;
+}
 
 mtfb_status mtfb_device_results(mtfb_ctx *c, double **d_corners, double **d_state, int **d_n_iters){
 	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_device_results: null context");

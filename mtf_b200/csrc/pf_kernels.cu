@@ -30,15 +30,19 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 	const int obj = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = b.N;
 	double *s_I0 = smem, *s_gA = smem + N, *s_gB = smem + 2 * N, *s_gC = smem + 3 * N;
-	// stage the template with one bulk copy (N * 8 bytes, 16-byte aligned: N is even or the tail is copied by hand)
-	const unsigned bulk_bytes = (unsigned)((N * 8) & ~15);
+	// stage the template with one bulk copy: cp.async.bulk needs a 16-byte aligned source and a multiple of 16 bytes.  The
+	// object's row starts at I0 + obj * N doubles, which is only 8-byte aligned when obj * N (or the offset of I0 inside the
+	// per-patch allocation: odd P) is odd -- such rows, and the odd tail element of any row, are copied by the threads instead
+	const double *src = b.I0 + (size_t)obj*N;
+	const bool src_aligned = (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
+	const unsigned bulk_bytes = src_aligned ? (unsigned)((N * 8) & ~15) : 0u;
 	if(tid == 0) mbar_init(&s_bar, 1);
 	__syncthreads();
-	if(tid == 0){
+	if(tid == 0 && bulk_bytes){
 		mbar_expect_tx(&s_bar, bulk_bytes);
-		bulk_copy_g2s(s_I0, b.I0 + (size_t)obj*N, bulk_bytes, &s_bar);
+		bulk_copy_g2s(s_I0, src, bulk_bytes, &s_bar);
 	}
-	for(int i = (int)(bulk_bytes / 8) + tid; i < N; i += T) s_I0[i] = b.I0[(size_t)obj*N + i];
+	for(int i = (int)(bulk_bytes / 8) + tid; i < N; i += T) s_I0[i] = src[i];
 	{
 		Mat3 dlt;
 #pragma unroll
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(T) pf_evaluate_kernel(DevBatch b, const double
 			else{ const double r = ieee_rcp(hz); s_gA[it.pix] = div_by(hx, hz, r); s_gB[it.pix] = div_by(hy, hz, r); }
 		}
 	}
-	mbar_wait(&s_bar, 0);
+	if(bulk_bytes) mbar_wait(&s_bar, 0);
 	__syncthreads();
 	__shared__ double s_i0c_part[T / 32];
 	double sum_i0c = 0, ncc_c = 1;

@@ -207,8 +207,12 @@ struct ColPivQR{
 		}
 		const double eps = DBL_EPSILON;
 		double maxn = *std::max_element(colNormsUpdated.begin(), colNormsUpdated.end());
-		double th = maxn*eps / double(rows);
-		double threshold_helper = th*th;
+		// Eigen 3.3 ColPivHouseholderQR.h computeInPlace():
+		//   RealScalar threshold_helper = numext::abs2<RealScalar>(m_colNormsUpdated.maxCoeff() * NumTraits<RealScalar>::epsilon()) / RealScalar(rows);
+		// i.e. (max norm * eps)^2 / rows -- the division by rows is OUTSIDE the square (Eigen 3.2 has the same value:
+		// m_colSqNorms.maxCoeff() * abs2(epsilon) / rows)
+		double me = maxn*eps;
+		double threshold_helper = me*me / double(rows);
 		double norm_downdate_threshold = std::sqrt(eps);
 		nonzero_pivots = size;
 		vec temp(cols);
@@ -1547,6 +1551,15 @@ void orc_homography_dlt(const double *in_c, const double *out_c, double *H9){
 }
 void orc_colpiv_qr_solve(const double *A, const double *b, int n, double *x){
 	ColPivQR qr; qr.compute(A, n, n); qr.solve(b, x);
+}
+// the factorisation itself, for cross-checks against LAPACK dgeqp3: qr_out = the rows x cols matrix Eigen's matrixQR() holds
+// (R in the upper triangle, Householder vectors below), perm_out[i] = original column at position i, returns nonzeroPivots()
+int orc_colpiv_qr(const double *A, int rows, int cols, double *qr_out, int *perm_out, double *hcoeffs_out){
+	ColPivQR qr; qr.compute(A, rows, cols);
+	for(size_t i = 0; i < (size_t)rows*cols; ++i) qr_out[i] = qr.qr[i];
+	for(int i = 0; i < cols; ++i) perm_out[i] = qr.perm[i];
+	for(int i = 0; i < qr.size; ++i) hcoeffs_out[i] = qr.hCoeffs[i];
+	return qr.nonzero_pivots;
 }
 void orc_norm_unit_square_pts(int resx, int resy, double min_x, double min_y, double max_x, double max_y,
 	double *pts2N, double *corners8){

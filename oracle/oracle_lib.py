@@ -77,6 +77,7 @@ def lib():
     L.orc_get_img_grad_analytic.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_homography_dlt.argtypes = [dp, dp, dp]
     L.orc_colpiv_qr_solve.argtypes = [dp, dp, C.c_int, dp]
+    L.orc_colpiv_qr.argtypes = [dp, C.c_int, C.c_int, dp, ip, dp]; L.orc_colpiv_qr.restype = C.c_int
     L.orc_norm_unit_square_pts.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
     L.orc_batch_track.argtypes = [C.POINTER(OrcParams), C.POINTER(fp), C.c_int, C.c_int, C.c_int, dp, C.c_int,
                                   C.c_int, dp, ip, dp]
@@ -265,6 +266,16 @@ def colpiv_qr_solve(A, b):
     x = np.empty(A.shape[0])
     lib().orc_colpiv_qr_solve(A.ctypes.data_as(C.POINTER(C.c_double)), _dp(b), A.shape[0], _dp(x))
     return x
+
+
+def colpiv_qr(A):
+    """(R upper-triangular rows x cols, perm, householder coefficients, nonzero_pivots) of Eigen's ColPivHouseholderQR"""
+    A = np.asfortranarray(A, dtype=np.float64)
+    rows, cols = A.shape
+    qr = np.empty((rows, cols), order="F"); perm = np.empty(cols, dtype=np.int32); tau = np.empty(min(rows, cols))
+    nz = lib().orc_colpiv_qr(A.ctypes.data_as(C.POINTER(C.c_double)), rows, cols, qr.ctypes.data_as(C.POINTER(C.c_double)),
+                             perm.ctypes.data_as(C.POINTER(C.c_int)), _dp(tau))
+    return np.triu(qr), perm, tau, nz
 
 
 def norm_unit_square_pts(resx, resy, min_x=-0.5, min_y=-0.5, max_x=0.5, max_y=0.5):

@@ -142,12 +142,14 @@ def test_f32_first_pass_sums(seq384, sm, ssm, norm_init):
 
 @pytest.mark.parametrize("sm", SMS)
 @pytest.mark.parametrize("ssm", SSMS)
-def test_f32_converged_corners(seq384, sm, ssm):
-    """30 passes per frame on both sides (epsilon = 0): the fixed points agree to CORNER_ATOL_F32"""
+@pytest.mark.parametrize("solve", ["reference", "local"])
+def test_f32_converged_corners(seq384, sm, ssm, solve):
+    """30 passes per frame on both sides (epsilon = 0): the fixed points agree to CORNER_ATOL_F32, with the reference's
+    QR in the reference's basis and with the local-basis solve (mtfb_params.f32_solve)"""
     frames, warps = seq384
     cs = np.concatenate([common.patches(6, 52.3, 384, 384, seed=5), common.quad_patches(6, 384, 384, seed=11)])
     norm = 1 if ssm == "homography" else 0
-    g = _gpu(ssm, sm, len(cs), epsilon=0.0, hom_normalized_init=norm)
+    g = _gpu(ssm, sm, len(cs), epsilon=0.0, hom_normalized_init=norm, f32_solve=solve)
     g.initialize(cs, frames[0])
     orcs = []
     for c in cs:

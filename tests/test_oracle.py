@@ -127,3 +127,54 @@ def test_tracking_recovers_ground_truth(seq384, am, sm):
             o.set_image(frames[t]); o.update()
             assert np.abs(o.corners() - synth.warp_corners(warps[t], c)).max() < 0.25
             assert o.n_iters < 30
+
+
+def test_colpiv_qr_pivots_and_R_match_lapack_dgeqp3():
+    """Eigen's ColPivHouseholderQR and LAPACK's dgeqp3 are the same algorithm (largest remaining column norm, norm
+    down-dating): same pivot order, R equal up to the sign convention of each row"""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(31)
+    for n in (6, 8):
+        for _ in range(40):
+            J = rng.normal(size=(60, n)) * rng.uniform(0.1, 30, size=n)
+            A = -(J.T @ J)
+            R, perm, _, nz = O.colpiv_qr(A)
+            _, R2, P2 = sl.qr(A, pivoting=True)
+            assert nz == n and np.array_equal(perm, P2)
+            assert np.allclose(np.abs(R), np.abs(R2), rtol=1e-10, atol=1e-10 * np.abs(R2).max())
+    # the 9 x 8 adjoint of the DLT constraint matrix (warpUtils.cc:171-223 through JacobiSVD's QR preconditioner)
+    A = rng.normal(size=(9, 8))
+    R, perm, _, nz = O.colpiv_qr(A)
+    _, R2, P2 = sl.qr(A, pivoting=True)
+    assert nz == 8 and np.array_equal(perm, P2) and np.allclose(np.abs(R[:8]), np.abs(R2[:8]), rtol=1e-10)
+
+
+def test_colpiv_qr_rank_threshold_is_eigens():
+    """Eigen 3.3 ColPivHouseholderQR::computeInPlace: threshold_helper = abs2(maxColNorm * epsilon) / rows, and pivot k counts
+    as zero when its squared norm < threshold_helper * (rows - k).  A diagonal matrix whose last entry t sits between
+    eps / rows (a misreading with the division inside the square) and eps / sqrt(rows) tells the two apart."""
+    eps = np.finfo(float).eps
+    for n in (6, 8):
+        b = np.arange(1.0, n + 1)
+        for t, rank in ((eps / np.sqrt(n) * 1.05, n), (eps / np.sqrt(n) * 0.95, n - 1), (eps / n * 1.5, n - 1), (eps / n * 0.5, n - 1)):
+            A = np.diag(np.r_[np.ones(n - 1), t])
+            R, perm, _, nz = O.colpiv_qr(A)
+            assert nz == rank, (n, t, nz)
+            x = O.colpiv_qr_solve(A, b)
+            assert np.allclose(x[:n - 1], b[:n - 1])
+            assert (x[n - 1] == 0.0) if rank < n else np.isclose(x[n - 1], b[n - 1] / t)
+
+
+def test_dlt_matches_opencv():
+    """the 4-point DLT against cv2.getPerspectiveTransform (an independent 8 x 8 linear solve)"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(32)
+    unit = np.array([[-0.5, 0.5, 0.5, -0.5], [-0.5, -0.5, 0.5, 0.5]])
+    for _ in range(50):
+        c = np.array([[300, 360, 365, 295], [480, 475, 540, 550.0]]) + rng.uniform(-10, 10, (2, 4))
+        H = O.homography_dlt(unit, c)
+        H2 = cv2.getPerspectiveTransform(unit.T.astype(np.float32), c.T.astype(np.float32))
+        # float32 corners on OpenCV's side: compare through the corners they map to
+        m = H2 @ np.vstack([unit, np.ones(4)])
+        assert np.allclose(m[:2] / m[2], c, atol=2e-4)
+        assert np.allclose(H / H[2, 2], H2 / H2[2, 2], rtol=2e-5, atol=2e-5 * np.abs(H).max())
