@@ -182,7 +182,7 @@ def measure(args, precision, dev, world, rank, local_rank, dist, frames, corners
     from mtf_b200 import api
     P = P_PER_GPU
     prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=local_rank,
-                          threads_per_patch=args.threads, occupancy=args.occ, precision=precision)
+                          threads_per_patch=args.threads, occupancy=args.occ, precision=precision, f32_solve=args.f32_solve)
     tr = api.BatchTracker(prm)
     stream = torch.cuda.current_stream(dev)
     tr.set_stream(stream.cuda_stream)
@@ -354,6 +354,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": dtype(args.precision), "data": "synthetic",
         "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
                                % (P, ITERS, IMG, IMG), "precision": args.precision,
+                   "f32_solve": args.f32_solve if args.precision == "f32" else None,
                    "frames": "ping-pong over frames 1..%d of the synthetic sequence; frame 0 initialises" % (N_FRAMES - 1),
                    "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto",
                    "occupancy": args.occ if args.threads else "auto",
@@ -407,6 +408,9 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f64", "f32"],
                     help="per-pixel arithmetic of the headline arm (include/mtf_b200.h MTFB_PRECISION_*); the other one is "
                          "timed too and reported under other_precision")
+    ap.add_argument("--f32-solve", default="reference", choices=["reference", "local"],
+                    help="F32 arm: the reference's column-pivoted QR in the reference's basis (default, what parity is claimed "
+                         "for) or the Gauss-Jordan solve in the patch-local basis (include/mtf_b200.h MTFB_F32_SOLVE_*)")
     ap.add_argument("--one-arm", action="store_true", help="time only the --precision arm")
     ap.add_argument("--pitch-pad", type=int, default=0, help="experiment: extra floats per device frame row")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

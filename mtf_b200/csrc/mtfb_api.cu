@@ -1,11 +1,13 @@
 // mtfb_api.cu -- the extern "C" boundary (include/mtf_b200.h): context, device buffers, launches.
 // Host code only; no arithmetic of the path lives here except the LinSpaced grid of
 // utils::getNormUnitSquarePts (Utilities/src/warpUtils.cc:15-33), which is per-context, not per-pixel.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -75,12 +77,47 @@ bool combo_supported(const mtfb_params *p, const char **why){
 	return false;
 }
 
+// Which pixels each thread of the moment kernel (lk_ssd_mom.cu) owns: a thread stays in one column, so a column's rows
+// are split among n or n + 1 threads (n = T / resx).  Items are ordered longest first, class by class and column by
+// column inside a class, so that the 32 threads of a warp have (nearly) the same number of rows and walk adjacent columns
+// of the same row.  Returns false if the resolution does not fit (a thread may own at most 64 rows).
+bool build_mom_work(int resx, int resy, int T, std::vector<int> &tab /* T x 4 */){
+	tab.assign((size_t)T * 4, 0);
+	if(resx > T) return false;
+	int n_lo = T / resx;
+	if(n_lo > resy) n_lo = resy;
+	int n_more = (n_lo < resy) ? T - n_lo*resx : 0;          // columns that get n_lo + 1 threads
+	if(n_more > resx) n_more = resx;
+	struct Item { int col, row0, nrows, cls; };
+	std::vector<Item> items;
+	for(int c = 0; c < resx; ++c){
+		// the columns with more threads are the first n_more: their (shorter) items go last
+		const int n = n_lo + (c < n_more ? 1 : 0);
+		for(int k = 0; k < n; ++k){
+			const int r0 = (int)((long long)resy*k / n), r1 = (int)((long long)resy*(k + 1) / n);
+			items.push_back({ c, r0, r1 - r0, k });
+		}
+	}
+	std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b){
+		if(a.nrows != b.nrows) return a.nrows > b.nrows;
+		if(a.cls != b.cls) return a.cls < b.cls;
+		return a.col < b.col;
+	});
+	if((int)items.size() > T || items.empty() || items[0].nrows > 64) return false;
+	for(size_t i = 0; i < items.size(); ++i){
+		tab[4 * i] = items[i].col; tab[4 * i + 1] = items[i].row0; tab[4 * i + 2] = items[i].nrows;
+	}
+	return true;
+}
+
 cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, const double *d_corners, double *mi_tab, cudaStream_t st){
 	if(p.am == MTFB_AM_MI) return launch_init_mi(p.ssm, threads, b, d_corners, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_init_ncc(p.ssm, threads, b, d_corners, st);
 	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
 }
-cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st){
+cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st,
+	const int4 *mom_work = nullptr, int mom_threads = 0){
+	if(p.precision == MTFB_PRECISION_F32 && mom_work) return launch_update_ssd_mom(p.ssm, mom_threads, b, mom_work, st);
 	if(p.precision == MTFB_PRECISION_F32) return launch_update_ssd_f32(p.ssm, p.sm, threads, b, st);
 	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
@@ -107,7 +144,15 @@ struct mtfb_ctx {
 	double *d_scratch; size_t scratch_bytes;    // getters / pf
 	bool have_image, initialized;
 	long launches;
+	// F32 + FCLK: the moment kernel (lk_ssd_mom.cu) and its thread -> pixels table; the Affine SSM takes it only while
+	// every initial region is a parallelogram (the kernel's grid frame needs an affine DLT there)
+	int4 *d_mom_work; int mom_threads; bool all_parallelograms;
 };
+static const int4 *mom_work_for(const mtfb_ctx *c){
+	if(!c->d_mom_work) return nullptr;
+	if(c->prm.ssm == MTFB_SSM_AFFINE && !c->all_parallelograms) return nullptr;
+	return c->d_mom_work;
+}
 
 extern "C" {
 
@@ -137,6 +182,7 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	if(c->own_stream) cudaStreamSynchronize(c->own_stream);
 	cudaFree(c->d_img_own); cudaFree(c->d_grid); cudaFree(c->d_patch); cudaFree(c->d_ints);
 	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32); cudaFree(c->d_raw);
+	cudaFree(c->d_mom_work);
 	if(c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return MTFB_OK;
@@ -263,6 +309,24 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 			// differs from the fp64 grid values by (lk_ssd_f32.cu pass_constants)
 			b.gx_lo = (float)xv[0]; b.gx_step = (float)((xv[p->resx - 1] - xv[0]) / (p->resx - 1));
 			b.gy_lo = (float)yv[0]; b.gy_step = (float)((yv[p->resy - 1] - yv[0]) / (p->resy - 1));
+		}
+		if(p->precision == MTFB_PRECISION_F32 && p->am == MTFB_AM_SSD && p->sm == MTFB_SM_FCLK){
+			// the moment kernel: four warps per patch (one per SM sub-partition) from ~1000 pixels per patch on; fewer threads
+			// for small cells so that a thread still owns several rows.  MTFB_F32_KERNEL=classic selects the first-generation
+			// kernel (experiments, A/B timing)
+			const char *sel = std::getenv("MTFB_F32_KERNEL");
+			int mt = p->threads_per_patch;
+			if(!mt) mt = N >= 1024 ? 128 : (N >= 400 ? 64 : 32);
+			std::vector<int> tab;
+			bool ok = !(sel && std::strcmp(sel, "classic") == 0) && build_mom_work(p->resx, p->resy, mt, tab);
+			if(!ok && !p->threads_per_patch && !(sel && std::strcmp(sel, "classic") == 0)){
+				mt = 256; ok = build_mom_work(p->resx, p->resy, mt, tab);
+			}
+			if(ok){
+				if(cudaMalloc(&c->d_mom_work, tab.size()*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
+				if(cudaMemcpy(c->d_mom_work, tab.data(), tab.size()*sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
+				c->mom_threads = mt;
+			}
 		}
 		b.n_iters_prof = nullptr;
 #if MTFB_PROF
@@ -397,6 +461,14 @@ static mtfb_status upload_corners(mtfb_ctx *c, const double *corners, const char
 	if(!c->have_image) return fail(MTFB_ERR_LOGIC, "%s: setImage has not been called", who);
 	for(size_t i = 0; i < 8 * (size_t)c->P; ++i)
 		if(!std::isfinite(corners[i])) return fail(MTFB_ERR_INVALID_ARG, "%s: non-finite corner coordinate in patch %zu", who, i / 8);
+	c->all_parallelograms = true;
+	for(size_t q = 0; q < (size_t)c->P && c->all_parallelograms; ++q){
+		const double *k = corners + 8 * q;
+		double scale = 0;
+		for(int i = 0; i < 8; ++i) scale = std::max(scale, std::fabs(k[i]));
+		// UL - UR + LR - LL = 0 in both coordinates
+		if(std::fabs(k[0] - k[1] + k[2] - k[3]) > 1e-9*scale || std::fabs(k[4] - k[5] + k[6] - k[7]) > 1e-9*scale) c->all_parallelograms = false;
+	}
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	CUDA_TRY(cudaMemcpyAsync(c->d_corners_in, corners, 8 * (size_t)c->P*sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	// the host buffer may be pageable: wait, so that the caller can reuse it (the copy is 64 B per patch)
@@ -437,7 +509,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads));
 	++c->launches;
 	return MTFB_OK;
 }
@@ -489,7 +561,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);
