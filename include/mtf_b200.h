@@ -211,7 +211,8 @@ int mtfb_state_size(const mtfb_ctx *ctx);
 /* test entry point (no reference counterpart as a function: the solve inside nt::FCLK / ESM / ICLK::update,
  * `H.colPivHouseholderQr().solve(J^T)`, SM/src/NT/FCLK.cc:298, NT/ESM.cc:266, NT/ICLK.cc:228): runs the device's warp-level
  * column-pivoted Householder QR on n_sys caller-supplied n x n systems (n = 6 or 8; A column-major, host pointers).
- * fast = 0: the literal restatement of Eigen 3.3's computeInPlace (norm down-dating); 1: the tuned per-pass variant.
+ * fast = 0: the literal restatement of Eigen 3.3's computeInPlace (norm down-dating); 1: the tuned per-pass variant;
+ * 2: the variant of the F32 precision (square root / reciprocals from Newton-refined fp32 seeds, column-wise back-substitution).
  * Outputs: x (n_sys x n), nonzero_pivots (n_sys, may be NULL), perm (n_sys x n: original column at position i, may be NULL). */
 mtfb_status mtfb_debug_colpiv_qr_solve(int device, int n, int fast, int n_sys, const double *A, const double *b, double *x,
 	int *nonzero_pivots, int *perm);

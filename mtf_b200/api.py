@@ -168,7 +168,7 @@ def debug_colpiv_qr_solve(A, b, fast=False, device=0):
     Ac = np.ascontiguousarray(A.transpose(0, 2, 1))          # column-major per system
     b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.empty((n_sys, n)); nz = np.empty(n_sys, dtype=np.int32); perm = np.empty((n_sys, n), dtype=np.int32)
-    st = L.mtfb_debug_colpiv_qr_solve(device, n, 1 if fast else 0, n_sys, _dp(Ac), _dp(b), _dp(x),
+    st = L.mtfb_debug_colpiv_qr_solve(device, n, int(fast), n_sys, _dp(Ac), _dp(b), _dp(x),
                                       nz.ctypes.data_as(C.POINTER(C.c_int)), perm.ctypes.data_as(C.POINTER(C.c_int)))
     if st != 0:
         raise MTFError(st, L.mtfb_last_error().decode())

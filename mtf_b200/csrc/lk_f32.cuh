@@ -574,6 +574,63 @@ template<int S> __device__ __forceinline__ bool solve_local(int lane, const doub
 	return true;
 }
 
+// The reference's solve for the pass-local Hessian, by one warp and without a trip through shared memory: lane j < S builds
+// column j of H = -T^T (J_loc^T J_loc) T (the SSD self Hessian in the reference's parameters, SSDBase.h:91-94, fp64), lane S
+// the right-hand side J^T = g_scale T^T g_loc, and the warp runs the column-pivoted Householder QR with Eigen's rank rule
+// (`-H.colPivHouseholderQr().solve(J^T)`, SM/src/NT/FCLK.cc:298, NT/ESM.cc:266) in its F32-precision variant (lk_warp.cuh
+// factor_lean).  s_T row-major: J_ref[k] = sum_m J_loc[m] T[m][k].  Writes s_dp[S]; sets MTFB_PATCH_SINGULAR like
+// serial_step does.
+template<int S> __device__ __forceinline__ void solve_reference_warp(int lane, const double *s_sum, const double *s_T, double g_scale,
+	double *s_dp, int &patch_status, long long *prof = nullptr){
+	typedef AccLayout<S> L;
+#if MTFB_PROF
+	const long long pt0 = clock64();
+#endif
+	const int j = lane < S ? lane : 0;
+	double tj[S], A[S];
+#pragma unroll
+	for(int n = 0; n < S; ++n) tj[n] = s_T[n*S + j];
+#pragma unroll
+	for(int m = 0; m < S; ++m){
+		double a0 = 0, a1 = 0;
+#pragma unroll
+		for(int n = 0; n < S; n += 2){
+			a0 = fma(s_sum[1 + S + L::tri(m < n ? m : n, m < n ? n : m)], tj[n], a0);
+			a1 = fma(s_sum[1 + S + L::tri(m < n + 1 ? m : n + 1, m < n + 1 ? n + 1 : m)], tj[n + 1], a1);
+		}
+		A[m] = a0 + a1;                                                  // (H_loc T)[m][j]
+	}
+	if(lane == S){
+#pragma unroll
+		for(int m = 0; m < S; ++m) A[m] = -g_scale * s_sum[1 + m];       // the sign is undone below
+	}
+	WarpColPivQR<S, S> qr;
+#pragma unroll
+	for(int i = 0; i < S; ++i){
+		double a0 = 0, a1 = 0;
+#pragma unroll
+		for(int m = 0; m < S; m += 2){ a0 = fma(s_T[m*S + i], A[m], a0); a1 = fma(s_T[(m + 1)*S + i], A[m + 1], a1); }
+		qr.a[i] = -(a0 + a1);
+	}
+#if MTFB_PROF
+	const long long pt1 = clock64();
+#endif
+	qr.factor_lean(lane, true);
+#if MTFB_PROF
+	const long long pt2 = clock64();
+#endif
+	const double x = -qr.solve_fast_cols(lane);                          // state_update = -H^-1 J^T
+#if MTFB_PROF
+	if(prof && lane == 0){
+		atomicAdd((unsigned long long*)prof + 4, (unsigned long long)(pt1 - pt0)); atomicAdd((unsigned long long*)prof + 5, (unsigned long long)(pt2 - pt1));
+		atomicAdd((unsigned long long*)prof + 6, (unsigned long long)(clock64() - pt2));
+	}
+#endif
+	if(qr.nonzero_pivots < S) patch_status |= MTFB_PATCH_SINGULAR;
+	if(lane < S) s_dp[lane] = x;
+	__syncwarp();
+}
+
 // entry (k, c) of the update's warp matrix getWarpFromState(dp) (Homography.cc:94-107, Affine.cc:117-131)
 template<int SSM> __device__ __forceinline__ double update_entry(const double *dp, int k, int c){
 	double u = (k == c) ? 1.0 : 0.0;

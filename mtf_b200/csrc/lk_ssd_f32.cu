@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
 	// the Hessian of this pass alone, no damping, nobody watching the reference-basis matrices: solve in the local basis
 	const bool local_solve = b.f32_local_solve && (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
+	const bool lean_tail = (SM != SM_ICLK) && (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
@@ -190,65 +191,87 @@ __global__ void __launch_bounds__(T, MINB) ssd_update_f32_kernel(DevBatch b, uns
 		block_reduce_f32<L::NA, T>(accf, s_part, s_sum);
 		++n_passes;
 		F32_PROF_T(2)
-		bool solved = false;
-		if(local_solve){
-			if(warp == 0) solved = solve_local<S>(lane, s_sum, s_Tinv, jac_half ? 0.5 : 1.0, s_x, s_dp);
-			if(T > 32){
-				if(tid == 0) s_ctrl = solved ? 1 : 0;
-				__syncthreads();
-				solved = s_ctrl != 0;
-				__syncthreads();
+		// pass-local Hessian, forward update, no Levenberg-Marquardt, no iteration log: warp 0 solves (local basis if asked for
+		// and safe, else the reference's QR in the reference's parameters) and applies the update spread over its lanes
+		if(lean_tail){
+			if(warp == 0){
+				bool solved = false;
+				if(local_solve) solved = solve_local<S>(lane, s_sum, s_Tinv, jac_half ? 0.5 : 1.0, s_x, s_dp);
+				if(!solved) solve_reference_warp<S>(lane, s_sum, s_T, jac_half ? 0.5 : 1.0, s_dp, patch_status);
+				F32_PROF_T(3)
+				f = -s_sum[0] / 2;
+				const int ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
+				if(lane == 0) s_ctrl = ctrl;
+				__syncwarp();
+				F32_PROF_T(4)
+				if(ctrl != CTRL_BREAK){
+					pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
+					if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+				}
+				F32_PROF_T(5)
+				F32_PROF_ADD()
 			}
-		}
-		if(!solved){
-			// local basis -> the reference's: H = T^T H_loc T, g = T^T g_loc (fp64), then the reference's QR
-			for(int e = tid; e < S*S; e += T){
-				const int i = e / S, m = e % S;
-				s_Hl[e] = s_sum[1 + S + L::tri(i < m ? i : m, i < m ? m : i)];
+		} else{
+			bool solved = false;
+			if(local_solve){
+				if(warp == 0) solved = solve_local<S>(lane, s_sum, s_Tinv, jac_half ? 0.5 : 1.0, s_x, s_dp);
+				if(T > 32){
+					if(tid == 0) s_ctrl = solved ? 1 : 0;
+					__syncthreads();
+					solved = s_ctrl != 0;
+					__syncthreads();
+				}
 			}
-			cta_sync<T>();
-			for(int e = tid; e < S*S; e += T){
-				const int i = e / S, kk = e % S;
-				double a = 0;
+			if(!solved){
+				// local basis -> the reference's: H = T^T H_loc T, g = T^T g_loc (fp64), then the reference's QR
+				for(int e = tid; e < S*S; e += T){
+					const int i = e / S, m = e % S;
+					s_Hl[e] = s_sum[1 + S + L::tri(i < m ? i : m, i < m ? m : i)];
+				}
+				cta_sync<T>();
+				for(int e = tid; e < S*S; e += T){
+					const int i = e / S, kk = e % S;
+					double a = 0;
 #pragma unroll
-				for(int m = 0; m < S; ++m) a = fma(s_Hl[i*S + m], s_T[m*S + kk], a);
-				s_A[e] = a;                                                     // (H_loc T)[i][kk]
-			}
-			cta_sync<T>();
-			for(int e = tid; e < S*S; e += T){
-				const int i = e % S, j = e / S;                                 // s_Hc is column-major: entry (i, j) at j*S + i
-				const int lo = i < j ? i : j, hi = i < j ? j : i;
-				double a = 0;
+					for(int m = 0; m < S; ++m) a = fma(s_Hl[i*S + m], s_T[m*S + kk], a);
+					s_A[e] = a;                                                     // (H_loc T)[i][kk]
+				}
+				cta_sync<T>();
+				for(int e = tid; e < S*S; e += T){
+					const int i = e % S, j = e / S;                                 // s_Hc is column-major: entry (i, j) at j*S + i
+					const int lo = i < j ? i : j, hi = i < j ? j : i;
+					double a = 0;
 #pragma unroll
-				for(int m = 0; m < S; ++m) a = fma(s_T[m*S + lo], s_A[m*S + hi], a);
-				s_Hc[e] = -a;                                                   // SSD self Hessian: -J^T J (SSDBase.h:91-94)
-			}
-			if(tid < S){
-				double a = 0;
+					for(int m = 0; m < S; ++m) a = fma(s_T[m*S + lo], s_A[m*S + hi], a);
+					s_Hc[e] = -a;                                                   // SSD self Hessian: -J^T J (SSDBase.h:91-94)
+				}
+				if(tid < S){
+					double a = 0;
 #pragma unroll
-				for(int m = 0; m < S; ++m) a = fma(s_T[m*S + tid], s_sum[1 + m], a);
-				s_J[tid] = jac_half ? a * 0.5 : a;
+					for(int m = 0; m < S; ++m) a = fma(s_T[m*S + tid], s_sum[1 + m], a);
+					s_J[tid] = jac_half ? a * 0.5 : a;
+				}
+				cta_sync<T>();
 			}
-			cta_sync<T>();
-		}
-		F32_PROF_T(3)
-		if(warp == 0){
-			f = -s_sum[0] / 2;
-			int ctrl;
-			if(solved && SM != SM_ICLK) ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
-			else if(solved) ctrl = serial_step<SSM, SM, true>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
-				lm, patch_status, s_dp);
-			else ctrl = serial_step<SSM, SM, false>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
-				lm, patch_status);
-			if(lane == 0) s_ctrl = ctrl;
-			__syncwarp();
-			F32_PROF_T(4)
-			if(ctrl != CTRL_BREAK){
-				pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
-				if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+			F32_PROF_T(3)
+			if(warp == 0){
+				f = -s_sum[0] / 2;
+				int ctrl;
+				if(solved && SM != SM_ICLK) ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
+				else if(solved) ctrl = serial_step<SSM, SM, true>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+					lm, patch_status, s_dp);
+				else ctrl = serial_step<SSM, SM, false>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+					lm, patch_status);
+				if(lane == 0) s_ctrl = ctrl;
+				__syncwarp();
+				F32_PROF_T(4)
+				if(ctrl != CTRL_BREAK){
+					pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
+					if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+				}
+				F32_PROF_T(5)
+				F32_PROF_ADD()
 			}
-			F32_PROF_T(5)
-			F32_PROF_ADD()
 		}
 		cta_sync<T>();
 		const int ctrl = s_ctrl;

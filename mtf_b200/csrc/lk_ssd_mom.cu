@@ -111,7 +111,7 @@ template<int SSM> __device__ __forceinline__ void adjoint_maps(const DevBatch &b
 // Per-pass constants by warp 0 (same error analysis as f32::pass_constants, lk_f32.cuh, with |u|, |v| <= 1 and the grid
 // values correctly rounded: the bound there is an upper bound here).
 template<int SSM> __device__ __forceinline__ void pass_constants_mom(const DevBatch &b, int lane, const double *W, const double *Dt,
-	float *cf, int *ci){
+	float *cf, int *ci, double *M64){
 	float E, rho = 2.0f;
 	int X0 = 0, Y0 = 0;
 	bool sane = true;
@@ -121,6 +121,7 @@ template<int SSM> __device__ __forceinline__ void pass_constants_mom(const DevBa
 		Mi = fma(W[3 * r + 2], Dt[6 + c], fma(W[3 * r + 1], Dt[3 + c], W[3 * r] * Dt[c]));
 		if(SSM == SSM_AFF && r == 2) Mi = (c == 2) ? 1.0 : 0.0;
 	}
+	if(lane < 9) M64[lane] = Mi;                                 // the fp64 map, for the pixels the fp32 guard band defers
 	const float Mf = (float)Mi;
 	const float m2 = __shfl_sync(FULL_MASK, Mf, 2), m5 = __shfl_sync(FULL_MASK, Mf, 5), m8 = __shfl_sync(FULL_MASK, Mf, 8);
 	const float r8 = rcp_approx(m8);
@@ -210,9 +211,28 @@ struct PassRegs {
 	int X0, Y0;
 };
 
-// One pixel of the thread's column, fp32: warped point, guard-band decision, bilinear sample + gradient, chain rule, sums.
+// chain rule and sums of one pixel once its sample is known (shared by the three evaluation tiers): gradient with respect to
+// (u, v), scaled as the reference's dI/dp is (Homography.cc:250-262 in the grid frame); valid = false adds nothing
+template<int SSM> __device__ __forceinline__ void mom_pixel_back(const PassRegs &k, const float4 &vt, bool proj, float wxl, float wyl,
+	float invD, float gx, float gy, float val, float i0, bool valid, MomAcc<SSM> &acc){
+	float gs = valid ? invD : 0.0f;
+	if(SSM == SSM_HOM && proj) gs *= rcp_approx(fmaf(k.d7, vt.x, k.cZ));
+	const float gxd = gx * gs, gyd = gy * gs;
+	float Gu, Gv;
+	if(SSM == SSM_HOM){
+		Gu = fmaf(fmaf(-k.m6, wxl, k.m0), gxd, fmaf(-k.m6, wyl, k.m3) * gyd);
+		Gv = fmaf(fmaf(-k.m7, wxl, k.m1), gxd, fmaf(-k.m7, wyl, k.m4) * gyd);
+	} else{
+		Gu = fmaf(k.m0, gxd, k.m3 * gyd);
+		Gv = fmaf(k.m1, gxd, k.m4 * gyd);
+	}
+	const float r = valid ? val - i0 : 0.0f;                                      // I_diff (SSDBase.cc:78)
+	acc.add(Gu, Gv, -r, r, vt);                                                   // df_dIt = -I_diff (SSDBase.cc:115-121)
+}
+
+// TIER 1.  One pixel of the thread's column, fp32: warped point, guard-band decision, bilinear sample + gradient.
 // WIN: the neighbours come from the shared-memory window that covers the patch's whole hull (no range test, compile-time
-// pitch); else from whatever k.base points to, range-tested.  Returns false if the pixel must take the fp64 path (it then
+// pitch); else from whatever k.base points to, range-tested.  Returns false if the pixel must be re-evaluated (it then
 // has contributed nothing).
 template<int SSM, bool WIN> __device__ __forceinline__ bool mom_pixel(const PassRegs &k, const float *base, const float4 &vt, bool proj,
 	float i0, MomAcc<SSM> &acc){
@@ -242,43 +262,51 @@ template<int SSM, bool WIN> __device__ __forceinline__ bool mom_pixel(const Pass
 	const float gy = bot - top;                                                   // (1 - dx)(p10 - p00) + dx (p11 - p01)
 	const float val = fmaf(dy, gy, top);
 	const float gx = fmaf(dy, t1 - t0, t0);                                       // (1 - dy)(p01 - p00) + dy (p11 - p10)
-	// gradient with respect to (u, v), scaled as the reference's dI/dp is (Homography.cc:250-262 in the grid frame)
-	float gs = fast ? invD : 0.0f;
-	if(SSM == SSM_HOM && proj) gs *= rcp_approx(fmaf(k.d7, v, k.cZ));
-	const float gxd = gx * gs, gyd = gy * gs;
-	float Gu, Gv;
-	if(SSM == SSM_HOM){
-		Gu = fmaf(fmaf(-k.m6, wxl, k.m0), gxd, fmaf(-k.m6, wyl, k.m3) * gyd);
-		Gv = fmaf(fmaf(-k.m7, wxl, k.m1), gxd, fmaf(-k.m7, wyl, k.m4) * gyd);
-	} else{
-		Gu = fmaf(k.m0, gxd, k.m3 * gyd);
-		Gv = fmaf(k.m1, gxd, k.m4 * gyd);
-	}
-	const float r = fast ? val - i0 : 0.0f;                                       // I_diff (SSDBase.cc:78)
-	acc.add(Gu, Gv, -r, r, vt);                                                   // df_dIt = -I_diff (SSDBase.cc:115-121)
+	mom_pixel_back<SSM>(k, vt, proj, wxl, wyl, invD, gx, gy, val, i0, fast, acc);
 	return fast;
 }
 
-// The same pixel through the reference-exact fp64 functions (lk_f32.cuh front_exact), then the fp32 chain rule and sums.
+// TIER 2.  A pixel whose fp32 coordinate fell inside the guard band of a cell boundary: the same map in fp64,
+// x = (M (u, v, 1))_x / (M (u, v, 1))_z with M = curr_warp . D as pass_constants_mom formed it.  This differs from the
+// reference's own fp64 evaluation order by a few ulp of the coordinate (< 1e-12 px), so (int)x and the choice between the
+// cell's slope and the reference's straddling finite difference (imgUtils.cc:233-254, |frac| < grad_eps) are the reference's
+// whenever frac(x), frac(y) are farther than d2 = 2 grad_eps + 1e-9 from 0 and 1; then the sample is the cell's bilinear
+// patch like tier 1, from the frame in global memory.  Returns false for the rest (on or next to the pixel lattice, outside
+// the frame): tier 3.
+struct MidArgs { Image img; const double *xv, *yv, *M; double uc, uh, vc, vh, d2; int X0, Y0; };
+template<int SSM> __device__ __forceinline__ bool mom_pixel_mid(const PassRegs &k, const MidArgs &a, const float4 &vt, bool proj,
+	int row, int col, float i0, MomAcc<SSM> &acc){
+	const double u = (__ldg(a.xv + col) - a.uc) / a.uh, v = (__ldg(a.yv + row) - a.vc) / a.vh;
+	const double nx = fma(a.M[0], u, fma(a.M[1], v, a.M[2])), ny = fma(a.M[3], u, fma(a.M[4], v, a.M[5]));
+	double rd = 1.0, x = nx, y = ny;
+	if(SSM == SSM_HOM){
+		rd = 1.0 / fma(a.M[6], u, fma(a.M[7], v, a.M[8]));
+		x = nx * rd; y = ny * rd;
+	}
+	const double fx = floor(x), fy = floor(y), dx = x - fx, dy = y - fy;
+	const bool ok = (dx >= a.d2) && (dx <= 1.0 - a.d2) && (dy >= a.d2) && (dy <= 1.0 - a.d2) &&
+		(fx >= 0.0) && (fx <= (double)(a.img.w - 2)) && (fy >= 0.0) && (fy <= (double)(a.img.h - 2));
+	if(!ok) return false;
+	const float *r0 = a.img.data + (size_t)(int)fy*a.img.pitch + (int)fx, *r1 = r0 + a.img.pitch;
+	const float p00 = __ldg(r0), p01 = __ldg(r0 + 1), p10 = __ldg(r1), p11 = __ldg(r1 + 1);
+	const float dxf = (float)dx, dyf = (float)dy;
+	const float t0 = p01 - p00, t1 = p11 - p10;
+	const float top = fmaf(dxf, t0, p00), bot = fmaf(dxf, t1, p10);
+	const float gy = bot - top;
+	const float val = fmaf(dyf, gy, top);
+	const float gx = fmaf(dyf, t1 - t0, t0);
+	mom_pixel_back<SSM>(k, vt, proj, (float)(x - a.X0), (float)(y - a.Y0), (float)rd, gx, gy, val, i0, true, acc);
+	return true;
+}
+
+// TIER 3.  The same pixel through the reference-exact fp64 functions (lk_f32.cuh exact_pixel), then the fp32 chain rule and sums.
 template<int SSM> __device__ __forceinline__ void mom_pixel_exact(const DevBatch &b, const PassRegs &k, const float4 &vt, bool proj,
 	const double *s_dlt, const double *s_W, int row, int col, float i0, MomAcc<SSM> &acc){
 	ExactArgs a;
 	a.img = b.img; a.xv = b.xv; a.yv = b.yv; a.s_dlt = s_dlt; a.s_W = s_W; a.grad_eps = b.grad_eps; a.grad_mult = b.grad_mult;
 	a.norm_init = b.norm_init; a.X0 = k.X0; a.Y0 = k.Y0;
 	const ExactOut e = exact_pixel<SSM>(a, row, col);
-	float gs = e.invD;
-	if(SSM == SSM_HOM && proj) gs *= rcp_approx(fmaf(k.d7, vt.x, k.cZ));
-	const float gxd = e.gx * gs, gyd = e.gy * gs;
-	float Gu, Gv;
-	if(SSM == SSM_HOM){
-		Gu = fmaf(fmaf(-k.m6, e.wxl, k.m0), gxd, fmaf(-k.m6, e.wyl, k.m3) * gyd);
-		Gv = fmaf(fmaf(-k.m7, e.wxl, k.m1), gxd, fmaf(-k.m7, e.wyl, k.m4) * gyd);
-	} else{
-		Gu = fmaf(k.m0, gxd, k.m3 * gyd);
-		Gv = fmaf(k.m1, gxd, k.m4 * gyd);
-	}
-	const float r = e.val - i0;
-	acc.add(Gu, Gv, -r, r, vt);
+	mom_pixel_back<SSM>(k, vt, proj, e.wxl, e.wyl, e.invD, e.gx, e.gy, e.val, i0, true, acc);
 }
 
 } // namespace mom
@@ -293,9 +321,17 @@ using namespace mom;
 	atomicAdd((unsigned long long*)b.n_iters_prof + 10, (unsigned long long)(prof_t3 - prof_t2)); \
 	atomicAdd((unsigned long long*)b.n_iters_prof + 11, (unsigned long long)(prof_t4 - prof_t3)); \
 	atomicAdd((unsigned long long*)b.n_iters_prof + 12, (unsigned long long)(prof_t5 - prof_t4)); }
+#define MOM_PROF_KERNEL_T(k) const long long prof_k##k = clock64();
+#define MOM_PROF_KERNEL_ADD() if(tid == 0){ \
+	atomicAdd((unsigned long long*)b.n_iters_prof + 13, (unsigned long long)(prof_k1 - prof_k0)); \
+	atomicAdd((unsigned long long*)b.n_iters_prof + 14, (unsigned long long)(prof_k2 - prof_k1)); \
+	atomicAdd((unsigned long long*)b.n_iters_prof + 15, (unsigned long long)(clock64() - prof_k2)); \
+	atomicMax((unsigned long long*)b.n_iters_prof + 3, (unsigned long long)(clock64() - prof_k0)); }
 #else
 #define MOM_PROF_T(k)
 #define MOM_PROF_ADD()
+#define MOM_PROF_KERNEL_T(k)
+#define MOM_PROF_KERNEL_ADD()
 #endif
 
 // work: per thread (column, first row, rows, -) -- which pixels of the patch the thread owns (mtfb_api.cu builds the table
@@ -309,10 +345,12 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 	typedef MomentTab<SSM> MT;
 	constexpr int NM = MT::NM, NR = NM + 1;                // moments + sum r^2
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	MOM_PROF_KERNEL_T(0)
 	__shared__ double s_part[(T / 32) * NR];
 	__shared__ double s_sum[L::NA];
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8], s_dlt[9], s_Dt[9];
 	__shared__ double s_J[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_Tinv[S*S], s_x[S], s_dp[S];
+	__shared__ double s_M64[9], s_gc[4];
 	__shared__ float s_cf[K_COUNT];
 	__shared__ int s_ci[2], s_wi[6];
 	__shared__ int s_ctrl;
@@ -339,23 +377,29 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 	if(warp == 0){
 		adjoint_maps<SSM>(b, lane, s_dlt, s_Dt, s_T, s_Tinv);
 		__syncwarp();
-		pass_constants_mom<SSM>(b, lane, s_W, s_Dt, s_cf, s_ci);
+		pass_constants_mom<SSM>(b, lane, s_W, s_Dt, s_cf, s_ci, s_M64);
 		if(lane == 0){ s_wi[4] = 0; window_decide(b, s_corners, win_elems != 0, s_wi); }
 	}
 	// this thread's pixels: rows row0 .. row0 + nrows - 1 of column col
 	const int4 wk = __ldg(work + tid);
 	const int col = wk.x, row0 = wk.y, nrows = wk.z;
 	const float u = (float)((__ldg(b.xv + col) - 0.5*(x_lo + x_hi)) / (0.5*(x_hi - x_lo)));
+	if(tid == 0){ s_gc[0] = 0.5*(x_lo + x_hi); s_gc[1] = 0.5*(x_hi - x_lo); s_gc[2] = 0.5*(y_lo + y_hi); s_gc[3] = 0.5*(y_hi - y_lo); }
 	cta_sync<T>();
 	// general quadrilateral: the DLT's third row varies over the patch (relative 1e-9: invisible in fp32 otherwise)
 	const bool proj = (SSM == SSM_HOM) && !(fabs(s_Dt[6]) <= 1e-9*fabs(s_Dt[8]) && fabs(s_Dt[7]) <= 1e-9*fabs(s_Dt[8]));
 	const float *I0 = b.I0f + (size_t)p*b.I0f_stride;
 	if(use_smem) mbar_wait(&s_bar, 0);
 	const float *tmpl = (use_smem ? (const float*)s_dyn : I0) + row0*b.resx + col;
-	const bool local_solve = b.f32_local_solve && (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
+	const bool lean_tail = (hessian_select<SM>(b.hess_type) == 0) && !b.leven_marq && !b.log;
+	const bool local_solve = b.f32_local_solve && lean_tail;
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
+	MOM_PROF_KERNEL_T(1)
+#if MTFB_PROF == 2
+	int prof_slow = 0;
+#endif
 	while(iter_id < b.max_iters){
 		MOM_PROF_T(0)
 		PassRegs k;
@@ -410,10 +454,17 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 					slow |= (fast ? 0u : 1u) << i;
 				}
 			}
+#if MTFB_PROF == 2
+			prof_slow += __popc(slow);
+#endif
 			while(slow){
 				const int i = c0 + __ffs((int)slow) - 1;
 				slow &= slow - 1;
-				mom_pixel_exact<SSM>(b, k, s_vtab[row0 + i], proj, s_dlt, s_W, row0 + i, col, tmpl[i*resx], acc);
+				MidArgs ma;
+				ma.img = b.img; ma.xv = b.xv; ma.yv = b.yv; ma.M = s_M64; ma.uc = s_gc[0]; ma.uh = s_gc[1]; ma.vc = s_gc[2]; ma.vh = s_gc[3];
+				ma.d2 = 2.0*b.grad_eps + 1e-9; ma.X0 = k.X0; ma.Y0 = k.Y0;
+				if(!mom_pixel_mid<SSM>(k, ma, s_vtab[row0 + i], proj, row0 + i, col, tmpl[i*resx], acc))
+					mom_pixel_exact<SSM>(b, k, s_vtab[row0 + i], proj, s_dlt, s_W, row0 + i, col, tmpl[i*resx], acc);
 			}
 		}
 		// moments: u^a S_b
@@ -471,17 +522,27 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 		}
 		++n_passes;
 		MOM_PROF_T(2)
-		bool solved = false;
-		if(local_solve){
-			if(warp == 0) solved = solve_local<S>(lane, s_sum, s_Tinv, 1.0, s_x, s_dp);
-			if(T > 32){
-				if(tid == 0) s_ctrl = solved ? 1 : 0;
-				__syncthreads();
-				solved = s_ctrl != 0;
-				__syncthreads();
+		// pass-local Hessian, no Levenberg-Marquardt, no iteration log: warp 0 solves (local basis if asked for and safe, else
+		// the reference's QR in the reference's parameters) and applies the update with the work spread over its lanes
+		if(lean_tail){
+			if(warp == 0){
+				bool solved = false;
+				if(local_solve) solved = solve_local<S>(lane, s_sum, s_Tinv, 1.0, s_x, s_dp);
+				if(!solved) solve_reference_warp<S>(lane, s_sum, s_T, 1.0, s_dp, patch_status, b.n_iters_prof);
+				MOM_PROF_T(3)
+				f = -s_sum[0] / 2;
+				const int ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
+				if(lane == 0) s_ctrl = ctrl;
+				__syncwarp();
+				MOM_PROF_T(4)
+				if(ctrl != CTRL_BREAK){
+					pass_constants_mom<SSM>(b, lane, s_W, s_Dt, s_cf, s_ci, s_M64);
+					if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+				}
+				MOM_PROF_T(5)
+				MOM_PROF_ADD()
 			}
-		}
-		if(!solved){
+		} else{
 			// local basis -> the reference's: H = T^T H_loc T, g = T^T g_loc (fp64), then the reference's QR
 			for(int e = tid; e < S*S; e += T){
 				const int i = e / S, m = e % S;
@@ -511,30 +572,46 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 				s_J[tid] = a;
 			}
 			cta_sync<T>();
-		}
-		MOM_PROF_T(3)
-		if(warp == 0){
-			f = -s_sum[0] / 2;
-			int ctrl;
-			if(solved) ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
-			else ctrl = serial_step<SSM, SM, false>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
-				lm, patch_status);
-			if(lane == 0) s_ctrl = ctrl;
-			__syncwarp();
-			MOM_PROF_T(4)
-			if(ctrl != CTRL_BREAK){
-				pass_constants_mom<SSM>(b, lane, s_W, s_Dt, s_cf, s_ci);
-				if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+			if(warp == 0){
+				MOM_PROF_T(3)
+				f = -s_sum[0] / 2;
+				const int ctrl = serial_step<SSM, SM, false>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
+					lm, patch_status);
+				if(lane == 0) s_ctrl = ctrl;
+				__syncwarp();
+				MOM_PROF_T(4)
+				if(ctrl != CTRL_BREAK){
+					pass_constants_mom<SSM>(b, lane, s_W, s_Dt, s_cf, s_ci, s_M64);
+					if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+				}
+				MOM_PROF_T(5)
+				MOM_PROF_ADD()
 			}
-			MOM_PROF_T(5)
-			MOM_PROF_ADD()
 		}
 		cta_sync<T>();
 		const int ctrl = s_ctrl;
 		if(ctrl == CTRL_BREAK) break;
 		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
 	}
+	MOM_PROF_KERNEL_T(2)
 	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
+	MOM_PROF_KERNEL_ADD()
+#if MTFB_PROF == 2
+	// per-patch diagnostics through the similarity getter: cycles of this CTA + (pixel evaluations deferred to fp64) / 2^20
+	prof_slow = __reduce_add_sync(0xffffffffu, prof_slow);
+	__shared__ int s_prof_slow;
+	if(tid == 0) s_prof_slow = 0;
+	__syncthreads();
+	if(lane == 0) atomicAdd(&s_prof_slow, prof_slow);
+	__syncthreads();
+	if(tid == 0){
+		b.f[p] = (double)(clock64() - prof_k0) + (double)s_prof_slow / 1048576.0;
+		unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+		b.n_iters[p] = (int)smid;
+		b.am_scal[(size_t)p * 8] = (double)gt;                       // end time, ns
+	}
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

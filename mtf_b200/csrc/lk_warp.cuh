@@ -63,6 +63,37 @@ template<int CNT, class V> __device__ __forceinline__ void warp_reduce_scatter(V
 	}
 }
 
+// 1 / sqrt(s) and 1 / d for the solve of the F32 precision (factor_fast<true>): fp32 MUFU seed on the exponent-reduced
+// argument, two Newton steps in fp64 (relative error ~2e-16, not correctly rounded).  The inputs of that solve carry fp32
+// rounding from the pixel sums, so the last bit is noise there; the F64 kernels keep sqrt() / __drcp_rn().
+__device__ __forceinline__ double rsqrt_newton(double s){
+	const int hi = __double2hiint(s);
+	if(!((unsigned)(hi - 0x00100000) < 0x7fe00000u)) return 1.0 / sqrt(s);            // zero, subnormal, negative, inf, nan
+	const int e2 = ((hi >> 20) - 1023) & ~1;                                           // even exponent
+	const double m = __hiloint2double(hi - (e2 << 20), __double2loint(s));             // in [1, 4)
+	float r0;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)m));
+	double r = (double)r0;
+	double mr = m * r;
+	r = fma(0.5 * r, fma(-mr, r, 1.0), r);
+	mr = m * r;
+	r = fma(0.5 * r, fma(-mr, r, 1.0), r);
+	return __hiloint2double(__double2hiint(r) - ((e2 >> 1) << 20), __double2loint(r));
+}
+__device__ __forceinline__ double rcp_newton_scaled(double d){
+	const int hi = __double2hiint(d);
+	const int ef = (hi >> 20) & 0x7ff;
+	if(!(ef > 64 && ef < 1983)) return __drcp_rn(d);                                   // keeps the result's exponent normal too
+	const int ex = ef - 1023;
+	const double m = __hiloint2double(hi - (ex << 20), __double2loint(d));             // |m| in [1, 2), sign kept
+	float r0;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)m));
+	double r = (double)r0;
+	r = fma(fma(-m, r, 1.0), r, r);
+	r = fma(fma(-m, r, 1.0), r, r);
+	return __hiloint2double(__double2hiint(r) - (ex << 20), __double2loint(r));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Column-pivoted Householder QR, Eigen 3.3 ColPivHouseholderQR::computeInPlace + _solve_impl semantics
 // (dgeqp3-style norm down-dating), ROWS x COLS, one column per lane (lanes 0..COLS-1); lane COLS may
@@ -215,7 +246,7 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 		}
 		return FROM < ROWS ? p[FROM < ROWS ? FROM : 0] : 0.0;
 	}
-	template<int K> __device__ __forceinline__ void fast_step(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
+	template<int K, bool APPROX> __device__ __forceinline__ void fast_step(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
 		const bool cand_ok = is_col && pos >= K && (csq == csq);
 		const unsigned hi = cand_ok ? (unsigned)__double2hiint(csq) : 0u;
 		const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
@@ -237,6 +268,17 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 				tau_l = 0; beta = c0;
 #pragma unroll
 				for(int r = K + 1; r < ROWS; ++r) a[r] = 0;
+			} else if(APPROX){
+				// the same quantities from one reciprocal square root and one reciprocal, both Newton-refined fp32 seeds
+				const double nrm2 = fma(c0, c0, tail_sq);
+				const double rs = rsqrt_newton(nrm2);
+				double nrm = nrm2 * rs;
+				nrm = fma(0.5 * rs, fma(-nrm, nrm, nrm2), nrm);
+				beta = c0 >= 0 ? -nrm : nrm;
+				const double rden = rcp_newton_scaled(c0 - beta);
+#pragma unroll
+				for(int r = K + 1; r < ROWS; ++r) a[r] = a[r] * rden;
+				rdiag = c0 >= 0 ? -rs : rs;
 			} else{
 				beta = sqrt(c0 * c0 + tail_sq);
 				if(c0 >= 0) beta = -beta;
@@ -244,7 +286,7 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 #pragma unroll
 				for(int r = K + 1; r < ROWS; ++r) a[r] = a[r] * rden;
 			}
-			rdiag = ieee_rcp(beta);
+			if(!APPROX || tail_sq <= DBL_MIN) rdiag = ieee_rcp(beta);
 			if(tail_sq > DBL_MIN) tau_l = (beta - c0) * rdiag;
 			a[K] = beta;
 		}
@@ -267,11 +309,11 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 		}
 		if(is_col && pos > K) csq = tail_sumsq<K + 1>();
 	}
-	template<int K> __device__ __forceinline__ void fast_steps(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
-		fast_step<K>(lane, is_col, is_rhs, csq, thsq);
-		if(K + 1 < SIZE) fast_steps<(K + 1 < SIZE ? K + 1 : K)>(lane, is_col, is_rhs, csq, thsq);
+	template<int K, bool APPROX> __device__ __forceinline__ void fast_steps(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
+		fast_step<K, APPROX>(lane, is_col, is_rhs, csq, thsq);
+		if(K + 1 < SIZE) fast_steps<(K + 1 < SIZE ? K + 1 : K), APPROX>(lane, is_col, is_rhs, csq, thsq);
 	}
-	__device__ __forceinline__ void factor_fast(int lane, bool with_rhs){
+	template<bool APPROX = false> __device__ __forceinline__ void factor_fast(int lane, bool with_rhs){
 		const bool is_col = lane < COLS;
 		const bool is_rhs = with_rhs && (lane == COLS);
 		pos = is_col ? lane : -1;
@@ -289,7 +331,118 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 		// Eigen's threshold_helper = (max norm * eps)^2 / rows, on the squared norms this factorisation keeps
 		const double thsq = maxsq * (DBL_EPSILON * DBL_EPSILON) / double(ROWS);
 		nonzero_pivots = SIZE;
-		fast_steps<0>(lane, is_col, is_rhs, csq, thsq);
+		fast_steps<0, APPROX>(lane, is_col, is_rhs, csq, thsq);
+#pragma unroll
+		for(int i = 0; i < SIZE; ++i) lane_at_pos[i] = __ffs(__ballot_sync(FULL_MASK, is_col && pos == i)) - 1;
+	}
+	// ---- the factorisation for the solve of the F32 precision (lk_f32.cuh solve_reference_warp): the same column-pivoted
+	// Householder QR and rank rule, with the reflector of step k applied in its un-normalised form
+	//     H_k = I - g w w^T,   w = (c0 - beta, a[k+1..]),   g = 1 / (beta (beta - c0)) = 1 / (|a_k|^2 + |c0| |a_k|)
+	// (identical to Eigen's I - tau v v^T with v = w / w_k, tau = g w_k^2): one reciprocal instead of a square root, a
+	// reciprocal and a division; the tail of the pivot column is broadcast as it is (before the scalar chain finishes), and
+	// the dot products w[k+1..] . a_j[k+1..] do not wait for beta either.  Reciprocal square root and reciprocal come from
+	// Newton-refined fp32 seeds (rsqrt_newton / rcp_newton_scaled).  Results differ from factor_fast<false>() by rounding
+	// only (a few ulp of each R entry); rdiag = 1 / R(k, k) is kept for solve_fast_cols().
+	template<int K> __device__ __forceinline__ void lean_step(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
+		// pivot: the largest squared tail norm among the columns at positions >= K; ties -> the lowest position, like
+		// Eigen's left-to-right scan
+		const bool cand_ok = is_col && pos >= K && (csq == csq);
+		const unsigned hi = cand_ok ? (unsigned)__double2hiint(csq) : 0u;
+		const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+		const bool c1 = cand_ok && hi == mhi;
+		const unsigned m1 = __ballot_sync(FULL_MASK, c1);
+		int piv_lane;
+		double bsq;
+		if(__popc(m1) == 1){
+			piv_lane = __ffs(m1) - 1;
+			bsq = __shfl_sync(FULL_MASK, csq, piv_lane);
+		} else if(m1 == 0u){
+			piv_lane = __ffs(__ballot_sync(FULL_MASK, is_col && pos == K)) - 1;            // all-NaN norms: keep column K
+			bsq = 0;
+		} else{
+			const unsigned lo = c1 ? (unsigned)__double2loint(csq) : 0u;
+			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+			const bool c2 = c1 && lo == mlo;
+			const int biggest = (int)__reduce_min_sync(FULL_MASK, c2 ? (unsigned)pos : 0xffffu);
+			piv_lane = __ffs(__ballot_sync(FULL_MASK, c2 && pos == biggest)) - 1;
+			bsq = __hiloint2double((int)mhi, (int)mlo);
+		}
+		if(nonzero_pivots == SIZE && bsq < thsq * double(ROWS - K)) nonzero_pivots = K;
+		{
+			// the pivot column moves to position K, the column that was there takes its place
+			const int piv_pos = __shfl_sync(FULL_MASK, pos, piv_lane);
+			if(is_col){ if(lane == piv_lane) pos = K; else if(pos == K) pos = piv_pos; }
+		}
+		// the pivot column's entries from row K down, as they are
+		double w[ROWS];
+#pragma unroll
+		for(int r = K; r < ROWS; ++r) w[r] = __shfl_sync(FULL_MASK, a[r], piv_lane);
+		const double c0 = w[K];
+		// (uniform: every lane evaluates the scalars of the reflector from the broadcast column -- no second round trip)
+		double tail_sq;
+		{
+			double p[ROWS];
+#pragma unroll
+			for(int r = K + 1; r < ROWS; ++r) p[r] = w[r] * w[r];
+#pragma unroll
+			for(int wd = 1; wd < ROWS; wd *= 2){
+#pragma unroll
+				for(int r = K + 1; r + wd < ROWS; r += 2 * wd) p[r] += p[r + wd];
+			}
+			tail_sq = (K + 1 < ROWS) ? p[K + 1 < ROWS ? K + 1 : 0] : 0.0;
+		}
+		// partial dot product with this lane's column (or the rhs): independent of the scalar chain below
+		const bool apply = (is_col && pos > K) || (is_rhs && K < nonzero_pivots);
+		double dot = 0;
+		if(K + 1 < ROWS) dot = tail_dot<K + 1>(w);
+		double beta, g, wk;
+		if(tail_sq <= DBL_MIN){
+			beta = c0; g = 0; wk = 0;                                                        // tau = 0: the identity
+		} else{
+			const double nrm2 = fma(c0, c0, tail_sq);
+			const double rs = rsqrt_newton(nrm2);
+			double nrm = nrm2 * rs;
+			nrm = fma(0.5 * rs, fma(-nrm, nrm, nrm2), nrm);
+			beta = c0 >= 0 ? -nrm : nrm;
+			wk = c0 - beta;
+			g = rcp_newton_scaled(fma(fabs(c0), nrm, nrm2));
+			if(lane == piv_lane) rdiag = c0 >= 0 ? -rs : rs;
+		}
+		if(lane == piv_lane){
+			a[K] = beta;
+			if(tail_sq <= DBL_MIN) rdiag = ieee_rcp(beta);
+		}
+		if(apply && g != 0){
+			const double t = fma(wk, a[K], dot);
+			const double tt = g * t;
+			a[K] = fma(-tt, wk, a[K]);
+#pragma unroll
+			for(int r = K + 1; r < ROWS; ++r) a[r] = fma(-tt, w[r], a[r]);
+		}
+		if(is_col && pos > K) csq = tail_sumsq<K + 1>();
+	}
+	template<int K> __device__ __forceinline__ void lean_steps(int lane, bool is_col, bool is_rhs, double &csq, double thsq){
+		lean_step<K>(lane, is_col, is_rhs, csq, thsq);
+		if(K + 1 < SIZE) lean_steps<(K + 1 < SIZE ? K + 1 : K)>(lane, is_col, is_rhs, csq, thsq);
+	}
+	__device__ __forceinline__ void factor_lean(int lane, bool with_rhs){
+		const bool is_col = lane < COLS;
+		const bool is_rhs = with_rhs && (lane == COLS);
+		pos = is_col ? lane : -1;
+		rdiag = 0;
+		double csq = tail_sumsq<0>();
+		double maxsq;
+		{
+			const bool ok = is_col && (csq == csq);
+			const unsigned hi = ok ? (unsigned)__double2hiint(csq) : 0u;
+			const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+			const unsigned lo = (ok && hi == mhi) ? (unsigned)__double2loint(csq) : 0u;
+			const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+			maxsq = __hiloint2double((int)mhi, (int)mlo);
+		}
+		const double thsq = maxsq * (DBL_EPSILON * DBL_EPSILON) / double(ROWS);
+		nonzero_pivots = SIZE;
+		lean_steps<0>(lane, is_col, is_rhs, csq, thsq);
 #pragma unroll
 		for(int i = 0; i < SIZE; ++i) lane_at_pos[i] = __ffs(__ballot_sync(FULL_MASK, is_col && pos == i)) - 1;
 	}
@@ -312,6 +465,34 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 		for(int i = 0; i < SIZE; ++i){
 			const double ci = __shfl_sync(FULL_MASK, a[i], COLS);
 			if(pos == i) x = (i < np) ? ci : 0.0;
+		}
+		return x;
+	}
+
+	// The same back-substitution column by column: x_i = c_i / R_ii, then c_j -= R_ji x_i for j < i.  Column i of R sits in
+	// one lane, so its entries come from shuffles that do not depend on x (they overlap the previous step), and the
+	// dependent chain is one multiply and one fused multiply-add per step instead of a row's worth.
+	__device__ __forceinline__ double solve_fast_cols(int lane){
+		static_assert(ROWS == COLS, "solve_fast_cols() is written for the square systems of the LK loop");
+		const int np = nonzero_pivots;
+#pragma unroll
+		for(int i = SIZE - 1; i >= 0; --i){
+			const double rinv = __shfl_sync(FULL_MASK, rdiag, lane_at_pos[i]);
+			double rc[SIZE];
+#pragma unroll
+			for(int j = 0; j < i; ++j) rc[j] = __shfl_sync(FULL_MASK, a[j], lane_at_pos[i]);
+			const double xi = (i < np) ? a[i] * rinv : 0.0;          // meaningful on the rhs lane only
+			if(lane == COLS){
+				a[i] = xi;
+#pragma unroll
+				for(int j = 0; j < i; ++j) a[j] = fma(-rc[j], xi, a[j]);
+			}
+		}
+		double x = 0;
+#pragma unroll
+		for(int i = 0; i < SIZE; ++i){
+			const double ci = __shfl_sync(FULL_MASK, a[i], COLS);
+			if(pos == i) x = ci;
 		}
 		return x;
 	}

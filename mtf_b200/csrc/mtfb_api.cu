@@ -700,6 +700,10 @@ extern "C" int mtfb_prof_read(mtfb_ctx *c, long long *out, int n){
 	cudaStreamSynchronize(c->stream);
 	return (int)cudaMemcpy(out, c->b.n_iters_prof, n*sizeof(long long), cudaMemcpyDeviceToHost);
 }
+extern "C" int mtfb_prof_reset(mtfb_ctx *c){
+	cudaStreamSynchronize(c->stream);
+	return (int)cudaMemset(c->b.n_iters_prof, 0, 64 * sizeof(long long));
+}
 #endif
 
 mtfb_status mtfb_debug_colpiv_qr_solve(int device, int n, int fast, int n_sys, const double *A, const double *b, double *x,
