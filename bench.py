@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- LK iterations/sec of the B200 hot path (BASELINE.json metric), one JSON line on stdout.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--scaling weak|strong]
+
+Without --config the line is the headline (config 2, weak scaling) and carries the other BASELINE configurations, run with
+fewer steps, under "other_configs" (benchlib.py: config 3 GridTracker cells, config 4 the 8192-patch MI batch sharded over
+the ranks, config 5 the particle filter); --config N prints that configuration's line alone.
 
 Workload (config.workload): BASELINE.json configs[1] -- FCLK + SSD + Homography, 1024 independent 50x50 patches
 per GPU on 1024x1024 synthetic frames (mtf_b200/synth.py), fixed 30 Gauss-Newton iterations per patch per frame
 (epsilon = 0 disables the early exit so that every step does identical work).  One STEP = one frame: the whole
 batch tracked for 30 iterations = P * 30 LK iterations.
 
-Two arms are timed in one process: the headline arm (--precision, default f32 = fp32 per-pixel arithmetic with bit-exact
-sampling indices, the arithmetic north_star specifies) fills the contract's keys; the other precision is reported under
-"other_precision" (value, e2e, roofline fraction, distance between the two arms' corners and from the ground truth).
+Three arms are timed in one process: the headline arm (--precision f32 --f32-solve reference: fp32 per-pixel arithmetic with
+bit-exact sampling indices, the arithmetic north_star specifies, and the REFERENCE's column-pivoted QR solve in the reference's
+parameters -- the arm parity is claimed for) fills the contract's keys; the F32 arm with the opt-in patch-local solve and the
+F64 arm are reported under "other_arms" (value, e2e, roofline fraction, distance of their corners from the headline arm's and
+from the ground truth).
 
   value      whole-job LK iterations/sec, frames already resident in HBM, CUDA-event timed per step on the
              launching stream, L2 flushed between steps, max over ranks
@@ -175,23 +181,27 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
-def measure(args, precision, dev, world, rank, local_rank, dist, frames, corners, order, d_frames, pinned, raw_pinned, flush):
-    """one arm (precision 'f32' | 'f64'): device-resident timing, then end to end from pinned host frames.
+def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_frames, pinned, raw_pinned):
+    """one arm (precision 'f32' | 'f64', F32 solve 'reference' | 'local'): device-resident timing, then end to end from pinned
+    host frames.  corners: this rank's patches; n_total: patches of the whole job (the all-gather's row count).
     -> dict(ms, kms, e2e_ms, launches, status, finite, windows)"""
     import torch
-    from mtf_b200 import api
-    P = P_PER_GPU
-    prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=local_rank,
-                          threads_per_patch=args.threads, occupancy=args.occ, precision=precision, f32_solve=args.f32_solve)
+    from mtf_b200 import api, sharding
+    dev, world, dist, flush = env.dev, env.world, env.dist, env.flush
+    P = corners.shape[0]
+    prm = api.make_params("ssd", "homography", "fclk", n_patches=P, max_iters=ITERS, epsilon=0.0, device=env.local_rank,
+                          threads_per_patch=args.threads, occupancy=args.occ, precision=precision, f32_solve=f32_solve)
     tr = api.BatchTracker(prm)
     stream = torch.cuda.current_stream(dev)
     tr.set_stream(stream.cuda_stream)
-    gathered = torch.empty((world, P, 8), dtype=torch.float64, device=dev) if world > 1 else None
-    d_corners_ptr, _, _ = tr.device_results()
+    # zero-copy torch view of the library's P x 8 result array: what the all-gather reads (no host hop)
+    d_corners = sharding.device_view(tr.device_results()[0], (P, 8), dev)
 
-    class _Raw:       # zero-copy torch view of the library's P x 8 result array
-        __cuda_array_interface__ = {"shape": (P, 8), "typestr": "<f8", "data": (d_corners_ptr, False), "version": 2}
-    d_corners = torch.as_tensor(_Raw(), device=dev)
+    def gather():
+        # north_star: one all-gather of the per-patch results over NVLink (per frame: LK iterations of different patches
+        # never interact, SURVEY.md 8e)
+        if world > 1:
+            sharding.all_gather_rows(d_corners, n_total)
 
     tr.initialize(corners, d_frames[0])
     tr.synchronize()
@@ -199,10 +209,7 @@ def measure(args, precision, dev, world, rank, local_rank, dist, frames, corners
     def step_device(i):
         tr.setImage(d_frames[order[i % len(order)]])
         tr.update()
-        if world > 1:
-            # north_star: one all-gather of the per-patch results over NVLink (per frame: LK iterations of
-            # different patches never interact)
-            dist.all_gather_into_tensor(gathered.view(-1), d_corners.view(-1))
+        gather()
 
     def barrier():
         if world > 1:
@@ -225,8 +232,7 @@ def measure(args, precision, dev, world, rank, local_rank, dist, frames, corners
         kev[i][0].record(stream)
         tr.update()
         kev[i][1].record(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), d_corners.view(-1))
+        gather()
         ev[i][1].record(stream)
     barrier()
     windows = [(win0, time.time())]
@@ -289,25 +295,19 @@ def measure(args, precision, dev, world, rank, local_rank, dist, frames, corners
                 truth=truth_error(final, corners, last_frame))
 
 
-def run_ours(args):
+def config2_line(args, env, sampler, strong):
+    """the headline: FCLK + SSD + Homography, 1024 patches per GPU (weak) or 1024 in total (strong)"""
     import torch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
-    torch.cuda.set_device(local_rank)
-    sampler = ClockSampler(local_rank); sampler.start()        # nvidia-smi needs ~1 s to produce its first sample
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    frames, corners, order = workload(seed_offset=rank)
-    P = P_PER_GPU
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
+    from mtf_b200 import sharding
+    world, rank, dev = env.world, env.rank, env.dev
+    if strong:
+        frames, corners_all, order = workload(seed_offset=0)
+        lo, hi = sharding.shard_range(P_PER_GPU, world, rank)
+        corners, n_total = corners_all[lo:hi], P_PER_GPU
+    else:
+        frames, corners, order = workload(seed_offset=rank)
+        n_total = P_PER_GPU * world
+    P = corners.shape[0]
     if args.pitch_pad:
         # experiment: device frames with a row pitch of IMG + pad floats (L1 set-conflict study, profiles/README.md)
         d_frames = []
@@ -321,26 +321,31 @@ def run_ours(args):
     # the raw uint8 frames a camera / video decoder would deliver (the synthetic frames are already smooth; the extra blur
     # only changes what is tracked, not the work)
     raw_pinned = [torch.from_numpy(np.clip(np.rint(f), 0, 255).astype(np.uint8)).pin_memory() for f in frames]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    common = (dev, world, rank, local_rank, dist, frames, corners, order, d_frames, pinned, raw_pinned, flush)
+    common = (env, n_total, frames, corners, order, d_frames, pinned, raw_pinned)
 
-    # headline arm: the precision asked for (default f32 = north_star's "bit-exact sampling indices, fp32 tolerance");
-    # the other arm (fp64 in the reference's operation order) is timed in the same process and reported beside it
-    main = measure(args, args.precision, *common)
-    other_prec = "f64" if args.precision == "f32" else "f32"
-    other = measure(args, other_prec, *common) if not args.one_arm else None
-    clocks = sampler.summary(main["windows"] + (other["windows"] if other else []))
-
-    total_iters = world * P * ITERS * args.steps
+    # headline arm: fp32 per-pixel arithmetic + the reference's solve (what parity is claimed for); the other arms are timed
+    # in the same process and reported beside it
+    arms = [(args.precision, args.f32_solve)]
+    if not args.one_arm:
+        arms += [a for a in (("f32", "reference"), ("f32", "local"), ("f64", "reference")) if a != arms[0] and not (a[0] == "f64" and arms[0][0] == "f64")]
+    res = [measure(args, prec, solve, *common) for prec, solve in arms]
+    main = res[0]
+    windows = [w for m in res for w in m["windows"]]
+    clocks = sampler.summary(windows)
+    total_iters = n_total * ITERS * args.steps
     peak, peak_src = peaks()
+
+    def kernel_name(precision):
+        if precision == "f64":
+            return "ssd_update_kernel<Homography,FCLK>"
+        return ("ssd_update_f32_kernel" if os.environ.get("MTFB_F32_KERNEL") == "classic" else "ssd_fclk_mom_kernel") + "<Homography>"
 
     def roofline(m, precision):
         achieved = ALG_BYTES_PER_ITER * P * ITERS * args.steps / (m["kms"] * 1e-3) / 1e9        # per GPU
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH[precision],
                 "traffic_source": NCU_TRAFFIC_SOURCE[precision] + " (dram__bytes_read + write, one launch)",
-                "kernel": ("ssd_update_kernel" if precision == "f64" else "ssd_update_f32_kernel") + "<Homography,FCLK>",
-                "kernel_ms_per_launch": m["kms"] / args.steps,
+                "kernel": kernel_name(precision), "kernel_ms_per_launch": m["kms"] / args.steps,
                 "alg_bytes_per_launch": ALG_BYTES_PER_ITER * P * ITERS, "peak_source": peak_src,
                 "note": ("fp64-issue bound" if precision == "f64" else "latency / issue bound") + ", not HBM bound: see DESIGN.md"}
 
@@ -350,51 +355,83 @@ def run_ours(args):
     status, final = main["status"], main["final"]
     out = {
         "metric": METRIC, "value": total_iters / (main["ms"] * 1e-3), "unit": "iters/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": dtype(args.precision), "data": "synthetic",
-        "config": {"workload": "FCLK+SSD+Homography, %d patches/GPU 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
-                               % (P, ITERS, IMG, IMG), "precision": args.precision,
-                   "f32_solve": args.f32_solve if args.precision == "f32" else None,
+        "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": dtype(arms[0][0]), "data": "synthetic",
+        "config": {"workload": "FCLK+SSD+Homography, %d patches%s 50x50, %d iters/frame (epsilon=0), %dx%d f32 frames"
+                               % (P_PER_GPU, " in total" if strong else "/GPU", ITERS, IMG, IMG), "precision": arms[0][0],
+                   "f32_solve": arms[0][1] if arms[0][0] == "f32" else None,
                    "frames": "ping-pong over frames 1..%d of the synthetic sequence; frame 0 initialises" % (N_FRAMES - 1),
                    "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto",
                    "occupancy": args.occ if args.threads else "auto",
-                   "collective": "all_gather of P x 8 corners per frame" if world > 1 else "none"},
+                   "collective": "all_gather of P x 8 corners per frame from the kernel's output buffer" if world > 1 else "none"},
         "e2e": {"value": total_iters / (main["e2e_ms"] * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
         # the same with RAW uint8 frames: upload 1 B / pixel, gray + 5 x 5 Gaussian on the device (mtfb_set_image_u8), update, D2H
         "e2e_raw_u8": {"value": total_iters / (main["raw_ms"] * 1e-3), "unit": "iters/s",
                        "h2d_bytes_per_step": IMG * IMG, "d2h_bytes_per_step": P * 8 * 8, "gpu_launches_per_step": 2},
         "gpu_launches": main["launches"],
-        "roofline": roofline(main, args.precision),
+        "roofline": roofline(main, arms[0][0]),
         "clocks": clocks,
         "valid": {"finite": bool(np.isfinite(final).all()), "patches_nan": int((status & 1 != 0).sum()),
                   "patches_rank_deficient_H": int((status & 2 != 0).sum()),
                   # after warmup + steps frames of tracking, against the synthetic sequence's ground truth
                   "corner_err_vs_truth_px": main["truth"]},
     }
-    if other is not None:
-        d = np.abs(other["final"] - final).max(axis=(1, 2))
-        out["other_precision"] = {
-            "precision": other_prec, "dtype": dtype(other_prec), "value": total_iters / (other["ms"] * 1e-3),
-            "ms_per_step": other["ms"] / args.steps, "e2e": total_iters / (other["e2e_ms"] * 1e-3),
-            "roofline_frac": roofline(other, other_prec)["frac"], "gpu_launches": other["launches"],
-            "corner_err_vs_truth_px": other["truth"],
-            "patches_rank_deficient_H": int((other["status"] & 2 != 0).sum()),
-            # the two arms track the same patches through the same frames: how far apart they end up (px)
-            "corner_diff_px": {"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())}}
-    if rank == 0:
-        if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            n_patches = min(P, 4 * cores)
-            it, secs = cpu_sample(frames, corners, n_patches, 1, cores)
-            if secs < 5.0:                      # aim for ~10 s of wall clock
-                reps = int(min(8, max(1, 10.0 / max(secs, 1e-3))))
-                it, secs = cpu_sample(frames, corners, n_patches, min(reps, N_FRAMES - 1), cores)
-            out["cpu_baseline"] = {"value": it / secs, "unit": "iters/s", "cores": cores, "kind": "port",
-                                   "sample": "%d patches, %d LK iterations, OpenMP over patches" % (n_patches, it)}
+    if len(res) > 1:
+        out["other_arms"] = {}
+        for (prec, solve), m in zip(arms[1:], res[1:]):
+            d = np.abs(m["final"] - final).max(axis=(1, 2))
+            out["other_arms"]["%s_%s_solve" % (prec, solve) if prec == "f32" else prec] = {
+                "precision": prec, "f32_solve": solve if prec == "f32" else None, "dtype": dtype(prec),
+                "value": total_iters / (m["ms"] * 1e-3), "ms_per_step": m["ms"] / args.steps, "e2e": total_iters / (m["e2e_ms"] * 1e-3),
+                "roofline_frac": roofline(m, prec)["frac"], "kernel_ms_per_launch": m["kms"] / args.steps, "gpu_launches": m["launches"],
+                "corner_err_vs_truth_px": m["truth"], "patches_rank_deficient_H": int((m["status"] & 2 != 0).sum()),
+                # the arms track the same patches through the same frames: how far from the headline arm they end up (px)
+                "corner_diff_vs_headline_px": {"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())}}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_patches = min(P, 4 * cores)
+        it, secs = cpu_sample(frames, corners, n_patches, 1, cores)
+        if secs < 5.0:                      # aim for ~10 s of wall clock
+            reps = int(min(8, max(1, 10.0 / max(secs, 1e-3))))
+            it, secs = cpu_sample(frames, corners, n_patches, min(reps, N_FRAMES - 1), cores)
+        out["cpu_baseline"] = {"value": it / secs, "unit": "iters/s", "cores": cores, "kind": "port",
+                               "sample": "%d patches, %d LK iterations, OpenMP over patches" % (n_patches, it)}
+    return out
+
+
+def run_ours(args):
+    import benchlib
+    env = benchlib.Env(args)
+    sampler = ClockSampler(env.local_rank); sampler.start()        # nvidia-smi needs ~1 s to produce its first sample
+    strong = args.scaling == "strong"
+    cpu = not args.no_cpu
+    few = max(3, min(args.steps, 10))
+    if args.config == 2:
+        out = config2_line(args, env, sampler, strong)
+        if not args.no_others and not args.one_arm:
+            # the other BASELINE configurations, fewer steps each; a failure of one must not take the headline down
+            others = {}
+            for name, fn in (("config3_res25", lambda: benchlib.run_config3(env, ROOT, 25, few, 3, strong, cpu)),
+                             ("config3_res10", lambda: benchlib.run_config3(env, ROOT, 10, few, 3, strong, cpu)),
+                             ("config4", lambda: benchlib.run_config4(env, ROOT, few, 3, cpu=cpu)),
+                             ("config5", lambda: benchlib.run_config5(env, ROOT, few, 3, cpu=cpu))):
+                try:
+                    others[name] = fn()
+                except Exception as e:          # reported, not hidden
+                    others[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            out["other_configs"] = others
+    elif args.config == 3:
+        out = benchlib.run_config3(env, ROOT, args.res or 25, args.steps, args.warmup, strong, cpu)
+    elif args.config == 4:
+        out = benchlib.run_config4(env, ROOT, args.steps, args.warmup, cpu=cpu)
+    else:
+        out = benchlib.run_config5(env, ROOT, args.steps, args.warmup, precision=args.precision, cpu=cpu)
+    if args.config != 2:
+        out["clocks"] = sampler.summary([(0, time.time() + 1)])
+    if env.rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
 
 
 def main():
@@ -411,7 +448,13 @@ def main():
     ap.add_argument("--f32-solve", default="reference", choices=["reference", "local"],
                     help="F32 arm: the reference's column-pivoted QR in the reference's basis (default, what parity is claimed "
                          "for) or the Gauss-Jordan solve in the patch-local basis (include/mtf_b200.h MTFB_F32_SOLVE_*)")
-    ap.add_argument("--one-arm", action="store_true", help="time only the --precision arm")
+    ap.add_argument("--one-arm", action="store_true", help="time only the --precision / --f32-solve arm (and no other configuration)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (benchlib.py)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="configs 2 / 3 at N > 1: patches per GPU fixed (weak) or 1024 patches in total split over the ranks "
+                         "(strong); configs 4 and 5 are fixed-size batches, always strong")
+    ap.add_argument("--res", type=int, default=0, help="config 3: cell resolution (25 = modules.cfg, 10 = parameters.h default)")
+    ap.add_argument("--no-others", action="store_true", help="config 2: do not append the other configurations' lines")
     ap.add_argument("--pitch-pad", type=int, default=0, help="experiment: extra floats per device frame row")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -183,6 +183,53 @@ mtfb_status mtfb_pf_evaluate(mtfb_ctx *ctx, const double *states, int n_particle
 mtfb_status mtfb_pf_evaluate_device(mtfb_ctx *ctx, const double *d_states, int n_particles,
 	double *d_likelihood, double *d_similarity);
 
+/* ---- the particle filter search method around mtfb_pf_evaluate: nt::PF (SM/src/NT/PF.cc:15-600, SM/include/mtf/SM/PFParams.h) ----
+ * A context created with sm = MTFB_SM_PF becomes a PF tracker once mtfb_pf_configure() has been called (before
+ * mtfb_initialize): mtfb_initialize() then also runs PF::initializeParticles (NT/PF.cc:185-198), mtfb_set_region() is
+ * PF::setRegion (NT/PF.cc:596-600) and mtfb_update() is PF::update (NT/PF.cc:207-446) for every object of the batch: dynamic
+ * model -> particle evaluation -> weights -> resampling -> mean state, all on the device (pf_tracker.cu).
+ * Implemented: Homography (generatePerturbation with and without hom_corner_based_sampling, Homography.cc:899-915); ONE sampler
+ * distribution (n_distr = 1); RandomWalk / AutoRegression1 x Additive / Compositional; likelihood AM / Gaussian / Reciprocal
+ * (the last two for SSD and NCC); resampling None / BinaryMultinomial / LinearMultinomial, adaptive or not; mean None / SSM /
+ * Corners; reset_to_mean.  Not implemented (MTFB_ERR_NOT_SUPPORTED): Residual resampling, several distributions with
+ * update_distr_wts, pix_sigma, jacobian_as_sigma, enable_learning, the Affine samplers (Affine.cc:464-560). */
+enum { MTFB_PF_RANDOM_WALK = 0, MTFB_PF_AUTO_REGRESSION1 = 1 };                                  /* PFParams::DynamicModel */
+enum { MTFB_PF_UPDATE_ADDITIVE = 0, MTFB_PF_UPDATE_COMPOSITIONAL = 1 };                          /* PFParams::UpdateType */
+enum { MTFB_PF_LIKELIHOOD_AM = 0, MTFB_PF_LIKELIHOOD_GAUSSIAN = 1, MTFB_PF_LIKELIHOOD_RECIPROCAL = 2 };  /* LikelihoodFunc */
+enum { MTFB_PF_RESAMPLE_NONE = 0, MTFB_PF_RESAMPLE_BINARY_MULTINOMIAL = 1, MTFB_PF_RESAMPLE_LINEAR_MULTINOMIAL = 2,
+       MTFB_PF_RESAMPLE_RESIDUAL = 3 };                                                          /* ResamplingType */
+enum { MTFB_PF_MEAN_NONE = 0, MTFB_PF_MEAN_SSM = 1, MTFB_PF_MEAN_CORNERS = 2 };                  /* MeanType */
+typedef struct mtfb_pf_params {
+	int n_particles;
+	int max_iters;               /* PF iterations per frame (pf_max_iters) */
+	double epsilon;              /* stop iterating when || prev_corners - curr_corners ||^2 < epsilon */
+	int dynamic_model, update_type, likelihood_func, resampling_type, mean_type;
+	int reset_to_mean;
+	double adaptive_resampling_thresh;   /* in (0, 1]: resample only when n_eff <= thresh * n_particles; else always */
+	double measurement_sigma;
+	double ar_coeff;             /* `a` of the AutoRegression1 models (ProjectiveBase.h:72-75 default 0.5) */
+	double ssm_sigma[8], ssm_mean[8];    /* the sampler's normal distributions, one per state entry; with corner based sampling
+	                                        entry 0 is the common translation's and entry 1 the corner offsets' (Homography.cc:901-906) */
+	int corner_based_sampling;   /* HomographyParams::corner_based_sampling (parameters.h:262 default 1) */
+	unsigned long long seed;     /* device generator (Philox4x32-10 + Box-Muller); the reference seeds from random_device */
+	int object_offset;           /* index of this context's first object in a job sharded over several contexts / GPUs */
+	int record_randoms;          /* keep the deviates of the last update for mtfb_pf_get_random_stream */
+} mtfb_pf_params;
+/* Config/modules.cfg:152-177 (500 particles, AutoRegression1, Compositional, AM likelihood, BinaryMultinomial with adaptive
+ * threshold 0.2, mean None, one iteration); sigma / mean zero: the caller sets the sampler */
+void mtfb_pf_default_params(mtfb_pf_params *p);
+/* replaces: new nt::PF(am, ssm, params) + ssm->initializeSampler (NT/PF.cc:15-134, 152) */
+mtfb_status mtfb_pf_configure(mtfb_ctx *ctx, const mtfb_pf_params *p);
+/* random stream for the NEXT mtfb_update() from the host instead of the device generator (parity tests; replaying a recorded
+ * run): normals max_iters x P x n_particles x R standard normal deviates (R = 8, or 10 with corner based sampling: tx, ty, then
+ * (dx, dy) of the four corners), uniforms max_iters x P x n_particles in (0, 1).  Either may be NULL. */
+mtfb_status mtfb_pf_set_random_stream(mtfb_ctx *ctx, const double *normals, const double *uniforms);
+/* the deviates the last mtfb_update() used (record_randoms = 1), same layouts; uniforms of objects that did not resample are 0 */
+mtfb_status mtfb_pf_get_random_stream(mtfb_ctx *ctx, double *normals, double *uniforms);
+/* particle_states[curr_set_id], particle_wts, particle_cum_wts, max_wt_id after the last update; any output may be NULL */
+mtfb_status mtfb_pf_get_particles(mtfb_ctx *ctx, double *states /* P x n x S */, double *weights /* P x n */,
+	double *cum_weights /* P x n */, int *max_wt_id /* P */);
+
 /* getters = the accessors of SURVEY.md 8(a18): ssm->getCorners/getState/getPts, am->getSimilarity,
  * am->getInitPixVals/getCurrPixVals/getCurrPixGrad ...; they synchronise the context stream.
  * Host pointers. */

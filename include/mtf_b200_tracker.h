@@ -5,6 +5,7 @@
  * cv::Mat <-> raw pointers and mtfb_status -> mtf::utils::Exception.  Three classes:
  *
  *   mtf::b200::Tracker       : mtf::TrackerBase   one patch; what mtf::getTracker returns for sm "b200_fclk" ...
+ *   mtf::b200::PFTracker     : mtf::TrackerBase   one object tracked by the particle filter (nt::PF, SM/src/NT/PF.cc)
  *   mtf::b200::Batch                              P patches tracked by ONE launch per frame
  *   mtf::b200::BatchMember   : mtf::TrackerBase   patch i of a Batch, so that composites that hold a
  *                                                 vector<TrackerBase*> (GridTracker, SM/src/GridTracker.cc:247-264)
@@ -68,9 +69,11 @@ inline mtfb_params makeParams(const char *sm, const char *am, const char *ssm, i
 class Batch{
 public:
 	explicit Batch(const mtfb_params &params) : ctx(nullptr), prm(params), corners(8 * (size_t)params.n_patches, 0.0),
-		n_supplied(0), frame_id(0), updated_frame(-1), raw_channels(0), gauss_kernel_size(5), gauss_sigma(3.0){
+		n_supplied(0), frame_id(0), updated_frame(-1), gen(0), raw_channels(0), gauss_kernel_size(5), gauss_sigma(3.0){
 		check(mtfb_create(&prm, &ctx));
 	}
+	//! make a batch created with sm "pf" a particle filter tracker (mtfb_pf_configure: nt::PF's constructor + initializeSampler)
+	void configurePF(const mtfb_pf_params &pf){ check(mtfb_pf_configure(ctx, &pf)); }
 	//! Take RAW uint8 frames (channels = 1 gray / 3 BGR) and run MTF's default pre-processing -- utils::GaussianSmoothing,
 	//! Utilities/src/preprocUtils.cc:108-127, parameters.h:229-235 -- on the device behind the upload.  The application then
 	//! creates this tracker's pre-processor with pre_proc_type "none" (inputType() reports CV_8UC1 / CV_8UC3).
@@ -104,7 +107,14 @@ public:
 	//! all P regions at once: corners = P x (2 x 4) doubles
 	void initialize(const double *all_corners){ upload(); check(mtfb_initialize(ctx, all_corners)); fetch(); }
 	void setRegion(const double *all_corners){ upload(); check(mtfb_set_region(ctx, all_corners)); fetch(); }
-	void update(){ upload(); check(mtfb_update(ctx)); fetch(); updated_frame = frame_id; }
+	void update(){
+		if(n_supplied != 0){
+			throw mtf::utils::LogicError("mtf_b200 :: update() while only some members of the batch have supplied their corners");
+		}
+		upload(); check(mtfb_update(ctx)); fetch(); updated_frame = frame_id;
+	}
+	//! bumped whenever the regions are refreshed from the device (initialize / setRegion / update)
+	long generation() const{ return gen; }
 	const double* region(int i) const{ return &corners[8 * (size_t)i]; }
 	mtfb_ctx* handle(){ return ctx; }
 
@@ -121,12 +131,13 @@ public:
 
 private:
 	std::vector<double>& pending_corners(){ if(pending.empty()){ pending.assign(corners.size(), 0.0); } return pending; }
-	void fetch(){ check(mtfb_get_corners(ctx, corners.data())); }
+	void fetch(){ check(mtfb_get_corners(ctx, corners.data())); ++gen; }
 	mtfb_ctx *ctx;
 	mtfb_params prm;
 	cv::Mat curr_img;
 	std::vector<double> corners, pending;
 	int n_supplied, frame_id, updated_frame;
+	long gen;
 	int raw_channels, gauss_kernel_size;
 	double gauss_sigma;
 };
@@ -135,12 +146,55 @@ private:
 class Tracker : public mtf::TrackerBase{
 public:
 	Tracker(const char *sm, const char *am, const char *ssm, int resx, int resy) :
-		batch(makeParams(sm, am, ssm, 1, resx, resy)){
+		batch(makeParams(notPF(sm), am, ssm, 1, resx, resy)){
 		name = std::string("b200_") + sm;
 		cv_corners_mat.create(2, 4, CV_64FC1);
 	}
 	explicit Tracker(const mtfb_params &params) : batch(params){
 		name = "b200";
+		cv_corners_mat.create(2, 4, CV_64FC1);
+	}
+	using TrackerBase::initialize;
+	using TrackerBase::update;
+	using TrackerBase::setRegion;
+	void setImage(const cv::Mat &img) override{ batch.setImage(img); }
+	void initialize(const cv::Mat &corners) override{ toArray(corners); batch.initialize(c8); publish(); }
+	void update() override{ batch.update(); publish(); }
+	void setRegion(const cv::Mat &corners) override{ toArray(corners); batch.setRegion(c8); publish(); }
+	int inputType() const override{ return batch.inputType(); }
+	Batch& getBatch(){ return batch; }
+protected:
+	//! the particle filter needs its sampler (PFParams): PFTracker below
+	static const char* notPF(const char *sm){
+		if(!strcmp(sm, "pf")){ throw mtf::utils::InvalidArgument("mtf_b200 :: sm \"pf\" is constructed as mtf::b200::PFTracker (it needs PFParams)"); }
+		return sm;
+	}
+private:
+	void toArray(const cv::Mat &corners){
+		if(corners.rows != 2 || corners.cols != 4 || corners.type() != CV_64FC1){
+			throw mtf::utils::InvalidArgument("mtf_b200 :: corners must be a 2 x 4 CV_64FC1 matrix");
+		}
+		for(int k = 0; k < 8; ++k){ c8[k] = corners.at<double>(k / 4, k % 4); }
+	}
+	void publish(){
+		const double *r = batch.region(0);
+		for(int k = 0; k < 8; ++k){ cv_corners_mat.at<double>(k / 4, k % 4) = r[k]; }
+	}
+	Batch batch;
+	double c8[8];
+};
+
+//! One object tracked by the particle filter on the GPU; drop-in for nt::PF (SM/src/NT/PF.cc), constructed where
+//! include/mtf/mtf.h:345-346 constructs PF<AM, SSM>(getPFParams().get(), ...): the caller fills mtfb_pf_params from PFParams
+//! (n_particles, dynamic_model, update_type, likelihood_func, resampling_type, mean_type, reset_to_mean,
+//! adaptive_resampling_thresh, measurement_sigma, the first distribution's ssm_sigma / ssm_mean) and
+//! HomographyParams::corner_based_sampling.
+class PFTracker : public mtf::TrackerBase{
+public:
+	PFTracker(const char *am, const char *ssm, int resx, int resy, const mtfb_pf_params &pf) :
+		batch(makeParams("pf", am, ssm, 1, resx, resy)){
+		batch.configurePF(pf);
+		name = "b200_pf";
 		cv_corners_mat.create(2, 4, CV_64FC1);
 	}
 	using TrackerBase::initialize;
@@ -171,7 +225,7 @@ private:
 //! build) triggers one launch for the whole batch on member 0 and reads results for the others.
 class BatchMember : public mtf::TrackerBase{
 public:
-	BatchMember(std::shared_ptr<Batch> _batch, int _id) : batch(_batch), id(_id){
+	BatchMember(std::shared_ptr<Batch> _batch, int _id) : batch(_batch), id(_id), pending(false), supplied_gen(-1){
 		name = "b200_member";
 		cv_corners_mat.create(2, 4, CV_64FC1);
 	}
@@ -179,20 +233,35 @@ public:
 	using TrackerBase::update;
 	using TrackerBase::setRegion;
 	void setImage(const cv::Mat &img) override{ if(id == 0){ batch->setImage(img); } }
-	void initialize(const cv::Mat &corners) override{ batch->supplyCorners(id, corners, true); corners.copyTo(cv_corners_mat); }
-	void setRegion(const cv::Mat &corners) override{ batch->supplyCorners(id, corners, false); corners.copyTo(cv_corners_mat); }
+	//! The batch is (re)initialised when its LAST member has supplied corners; until then this member's region is the one it
+	//! supplied -- GridTracker::resetTrackers reads trackers[i]->getRegion() right after trackers[i]->initialize(corners)
+	//! (SM/src/GridTracker.cc:381-387), and after setCorners the region equals the supplied corners exactly
+	void initialize(const cv::Mat &corners) override{ supply(corners, true); }
+	void setRegion(const cv::Mat &corners) override{ supply(corners, false); }
 	//! member 0 launches the whole batch; the composite's loop visits the members in index order
 	//! (GridTracker.cc:256-259; the TBB / OpenMP variants of that loop, :248-255, must stay disabled)
 	void update() override{ if(id == 0){ batch->update(); } }
 	const cv::Mat& getRegion() override{
+		if(pending && batch->generation() == supplied_gen){ return cv_corners_mat; }      // not flushed to the device yet
+		pending = false;
 		const double *r = batch->region(id);
 		for(int k = 0; k < 8; ++k){ cv_corners_mat.at<double>(k / 4, k % 4) = r[k]; }
 		return cv_corners_mat;
 	}
 	int inputType() const override{ return batch->inputType(); }
 private:
+	void supply(const cv::Mat &corners, bool is_init){
+		if(corners.rows != 2 || corners.cols != 4 || corners.type() != CV_64FC1){
+			throw mtf::utils::InvalidArgument("mtf_b200 :: corners must be a 2 x 4 CV_64FC1 matrix");
+		}
+		corners.copyTo(cv_corners_mat);
+		pending = true; supplied_gen = batch->generation();
+		batch->supplyCorners(id, corners, is_init);
+	}
 	std::shared_ptr<Batch> batch;
 	int id;
+	bool pending;
+	long supplied_gen;
 };
 
 //! grid_res^2 members over one batch: what replaces the loop at include/mtf/mtf.h:786-789

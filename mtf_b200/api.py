@@ -49,6 +49,23 @@ class Params(C.Structure):
                 ("occupancy", C.c_int), ("precision", C.c_int), ("f32_solve", C.c_int)]
 
 
+PF_DYNAMIC = {"random_walk": 0, "auto_regression1": 1}
+PF_UPDATE = {"additive": 0, "compositional": 1}
+PF_LIKELIHOOD = {"am": 0, "gaussian": 1, "reciprocal": 2}
+PF_RESAMPLING = {"none": 0, "binary_multinomial": 1, "linear_multinomial": 2, "residual": 3}
+PF_MEAN = {"none": 0, "ssm": 1, "corners": 2}
+
+
+class PFParams(C.Structure):
+    """mtfb_pf_params = the fields of PFParams (SM/include/mtf/SM/PFParams.h) this library implements"""
+    _fields_ = [("n_particles", C.c_int), ("max_iters", C.c_int), ("epsilon", C.c_double),
+                ("dynamic_model", C.c_int), ("update_type", C.c_int), ("likelihood_func", C.c_int),
+                ("resampling_type", C.c_int), ("mean_type", C.c_int), ("reset_to_mean", C.c_int),
+                ("adaptive_resampling_thresh", C.c_double), ("measurement_sigma", C.c_double), ("ar_coeff", C.c_double),
+                ("ssm_sigma", C.c_double * 8), ("ssm_mean", C.c_double * 8), ("corner_based_sampling", C.c_int),
+                ("seed", C.c_ulonglong), ("object_offset", C.c_int), ("record_randoms", C.c_int)]
+
+
 class IterLog(C.Structure):
     _fields_ = [("f", C.c_double), ("jacobian", C.c_double * 8), ("hessian", C.c_double * 64),
                 ("state_update", C.c_double * 8), ("corners", C.c_double * 8),
@@ -64,6 +81,7 @@ EXPORTS = [
     "mtfb_get_similarity", "mtfb_get_patch_status", "mtfb_get_init_warp", "mtfb_get_init_pts",
     "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_get_curr_stage_f32", "mtfb_device_results",
     "mtfb_state_size", "mtfb_debug_colpiv_qr_solve",
+    "mtfb_pf_default_params", "mtfb_pf_configure", "mtfb_pf_set_random_stream", "mtfb_pf_get_random_stream", "mtfb_pf_get_particles",
 ]
 
 _lib = None
@@ -109,9 +127,14 @@ def load_library(path=LIB_PATH):
     L.mtfb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mtfb_state_size.argtypes = [vp]
     L.mtfb_debug_colpiv_qr_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, ip]
+    L.mtfb_pf_default_params.argtypes = [C.POINTER(PFParams)]; L.mtfb_pf_default_params.restype = None
+    L.mtfb_pf_configure.argtypes = [vp, C.POINTER(PFParams)]
+    L.mtfb_pf_set_random_stream.argtypes = [vp, vp, vp]
+    L.mtfb_pf_get_random_stream.argtypes = [vp, vp, vp]
+    L.mtfb_pf_get_particles.argtypes = [vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params"):
+        if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_pf_default_params"):
             fn.restype = C.c_int
     _lib = L
     return L
@@ -372,3 +395,59 @@ class BatchTracker:
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._L.mtfb_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+def make_pf_params(n_particles=500, sigma=None, mean=None, **kw):
+    """mtfb_pf_params: the shipped configuration (Config/modules.cfg:152-177) with the sampler's sigma / mean set"""
+    p = PFParams()
+    load_library().mtfb_pf_default_params(C.byref(p))
+    p.n_particles = int(n_particles)
+    names = {"dynamic_model": PF_DYNAMIC, "update_type": PF_UPDATE, "likelihood_func": PF_LIKELIHOOD,
+             "resampling_type": PF_RESAMPLING, "mean_type": PF_MEAN}
+    if sigma is not None:
+        sg = np.broadcast_to(np.asarray(sigma, dtype=np.float64), (8,)) if np.ndim(sigma) == 0 else np.asarray(sigma, dtype=np.float64)
+        for i in range(min(8, len(sg))):
+            p.ssm_sigma[i] = float(sg[i])
+    if mean is not None:
+        mn = np.broadcast_to(np.asarray(mean, dtype=np.float64), (8,)) if np.ndim(mean) == 0 else np.asarray(mean, dtype=np.float64)
+        for i in range(min(8, len(mn))):
+            p.ssm_mean[i] = float(mn[i])
+    for k, v in kw.items():
+        if k in names and isinstance(v, str):
+            v = names[k][v]
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+class PFTracker(BatchTracker):
+    """P particle-filter trackers (nt::PF, SM/src/NT/PF.cc) sharing one image: initialize / update / setRegion / getRegion as
+    TrackerBase; every stage of PF::update runs on the device (mtf_b200/csrc/pf_tracker.cu)."""
+
+    def __init__(self, params, n_particles=500, sigma=None, mean=None, **pf_kw):
+        super().__init__(params)
+        self.pf_params = make_pf_params(n_particles, sigma, mean, **pf_kw)
+        self._check(self._L.mtfb_pf_configure(self._h, C.byref(self.pf_params)))
+        self.n_particles = self.pf_params.n_particles
+        self.n_normals = 10 if (self.pf_params.corner_based_sampling and self.S == 8) else self.S
+
+    def set_random_stream(self, normals=None, uniforms=None):
+        """host-supplied deviates for the next update(): normals (max_iters, P, n, R), uniforms (max_iters, P, n)"""
+        it = self.pf_params.max_iters
+        a = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64).reshape(it, self.P, self.n_particles, self.n_normals)
+        b = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64).reshape(it, self.P, self.n_particles)
+        self._check(self._L.mtfb_pf_set_random_stream(self._h, None if a is None else a.ctypes.data, None if b is None else b.ctypes.data))
+
+    def random_stream(self):
+        it = self.pf_params.max_iters
+        a = np.empty((it, self.P, self.n_particles, self.n_normals)); b = np.empty((it, self.P, self.n_particles))
+        self._check(self._L.mtfb_pf_get_random_stream(self._h, a.ctypes.data, b.ctypes.data))
+        return a, b
+
+    def particles(self):
+        """(states (P, n, S), weights (P, n), cum_weights (P, n), max_wt_id (P,)) after the last update"""
+        st = np.empty((self.P, self.n_particles, self.S)); w = np.empty((self.P, self.n_particles)); cw = np.empty_like(w)
+        mx = np.empty(self.P, dtype=np.int32)
+        self._check(self._L.mtfb_pf_get_particles(self._h, st.ctypes.data, w.ctypes.data, cw.ctypes.data, mx.ctypes.data))
+        return st, w, cw, mx

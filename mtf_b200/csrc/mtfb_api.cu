@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "lk_kernels.cuh"
+#include "pf_tracker.cuh"
 
 using namespace mtfb;
 
@@ -147,6 +148,12 @@ struct mtfb_ctx {
 	// F32 + FCLK: the moment kernel (lk_ssd_mom.cu) and its thread -> pixels table; the Affine SSM takes it only while
 	// every initial region is a parallelogram (the kernel's grid frame needs an affine DLT there)
 	int4 *d_mom_work; int mom_threads; bool all_parallelograms;
+	// sm = PF after mtfb_pf_configure (pf_tracker.cu)
+	bool pf_configured; mtfb_pf_params pfp; PFDev pf;
+	double *d_pf; int *d_pf_ints;               // particle arrays in one allocation each
+	double *d_pf_rand_in; size_t pf_rand_in_capacity; bool pf_normals_pending, pf_uniforms_pending;
+	double *d_pf_rand_out;
+	long pf_frame;
 };
 static const int4 *mom_work_for(const mtfb_ctx *c){
 	if(!c->d_mom_work) return nullptr;
@@ -183,6 +190,7 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaFree(c->d_img_own); cudaFree(c->d_grid); cudaFree(c->d_patch); cudaFree(c->d_ints);
 	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32); cudaFree(c->d_raw);
 	cudaFree(c->d_mom_work);
+	cudaFree(c->d_pf); cudaFree(c->d_pf_ints); cudaFree(c->d_pf_rand_in); cudaFree(c->d_pf_rand_out);
 	if(c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return MTFB_OK;
@@ -482,6 +490,12 @@ mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->d_mi_tab, c->stream));
 	++c->launches;
 	c->initialized = true;
+	if(c->pf_configured){
+		// PF::initialize (NT/PF.cc:136-183): initializeParticles, prev_corners = ssm->getCorners()
+		CUDA_TRY(launch_pf_init_particles(c->prm.ssm, c->pf, c->b, true, c->stream));
+		++c->launches;
+		c->pf_frame = 0;
+	}
 	return MTFB_OK;
 }
 
@@ -500,13 +514,165 @@ mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	if(ssm_only) CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
 	else CUDA_TRY(launch_reinit_ssd(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
+	if(c->pf_configured){
+		// PF::setRegion (NT/PF.cc:596-600): ssm->setCorners, initializeParticles
+		CUDA_TRY(launch_pf_init_particles(c->prm.ssm, c->pf, c->b, false, c->stream));
+		++c->launches;
+	}
+	return MTFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ particle filter tracker
+static mtfb_status pf_update(mtfb_ctx *c){
+	// PF::update (NT/PF.cc:207-446) for all objects
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const int ssm = c->prm.ssm;
+	const size_t n = (size_t)c->P*c->pfp.n_particles;
+	PFDev pf = c->pf;
+	++c->pf_frame;
+	CUDA_TRY(launch_pf_frame_begin(pf, c->b, c->stream)); ++c->launches;
+	for(int it = 0; it < c->pfp.max_iters; ++it){
+		const unsigned tag = (unsigned)(c->pf_frame*(long)c->pfp.max_iters + it);
+		pf.normals_in = c->pf_normals_pending ? c->d_pf_rand_in + (size_t)it*n*pf.n_normals : nullptr;
+		pf.uniforms_in = c->pf_uniforms_pending ? c->d_pf_rand_in + (size_t)c->pfp.max_iters*n*pf.n_normals + (size_t)it*n : nullptr;
+		pf.normals_out = c->d_pf_rand_out ? c->d_pf_rand_out + (size_t)it*n*pf.n_normals : nullptr;
+		pf.uniforms_out = c->d_pf_rand_out ? c->d_pf_rand_out + (size_t)c->pfp.max_iters*n*pf.n_normals + (size_t)it*n : nullptr;
+		CUDA_TRY(launch_pf_perturb(ssm, pf, c->b, tag, c->stream)); ++c->launches;
+		// ssm->setState -> am->updatePixVals -> am->updateSimilarity(false) -> am->getLikelihood() of every particle
+		mtfb_status st = mtfb_pf_evaluate_device(c, pf.states, c->pfp.n_particles, pf.weights, pf.similarity);
+		if(st != MTFB_OK) return st;
+		CUDA_TRY(launch_pf_weights(pf, c->b, c->stream)); ++c->launches;
+		if(c->pfp.resampling_type != MTFB_PF_RESAMPLE_NONE){
+			CUDA_TRY(launch_pf_resample(ssm, pf, c->b, tag, c->stream)); c->launches += 2;
+		}
+		CUDA_TRY(launch_pf_mean(ssm, pf, c->b, c->stream)); ++c->launches;
+	}
+	if(c->pfp.reset_to_mean){ CUDA_TRY(launch_pf_init_particles(ssm, pf, c->b, false, c->stream)); ++c->launches; }
+	c->pf_normals_pending = c->pf_uniforms_pending = false;
+	return MTFB_OK;
+}
+
+void mtfb_pf_default_params(mtfb_pf_params *p){
+	std::memset(p, 0, sizeof(*p));
+	p->n_particles = 500; p->max_iters = 1; p->epsilon = 0.01;
+	p->dynamic_model = MTFB_PF_AUTO_REGRESSION1; p->update_type = MTFB_PF_UPDATE_COMPOSITIONAL;
+	p->likelihood_func = MTFB_PF_LIKELIHOOD_AM; p->resampling_type = MTFB_PF_RESAMPLE_BINARY_MULTINOMIAL;
+	p->mean_type = MTFB_PF_MEAN_NONE; p->reset_to_mean = 0;
+	p->adaptive_resampling_thresh = 0.2; p->measurement_sigma = 0.1; p->ar_coeff = 0.5;
+	p->corner_based_sampling = 1; p->seed = 0x9E3779B97F4A7C15ull; p->object_offset = 0; p->record_randoms = 0;
+}
+
+mtfb_status mtfb_pf_configure(mtfb_ctx *c, const mtfb_pf_params *p){
+	if(!c || !p) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_configure: null argument");
+	if(c->prm.sm != MTFB_SM_PF) return fail(MTFB_ERR_LOGIC, "mtfb_pf_configure: the context was not created with sm = MTFB_SM_PF");
+	if(c->prm.ssm != MTFB_SSM_HOMOGRAPHY) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_configure: the Affine samplers (Affine.cc:464-560) "
+		"are not implemented; particle evaluation (mtfb_pf_evaluate) works for both");
+	if(p->n_particles < 1 || p->max_iters < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_configure: n_particles, max_iters >= 1 required");
+	if(p->dynamic_model < 0 || p->dynamic_model > 1 || p->update_type < 0 || p->update_type > 1 || p->likelihood_func < 0 ||
+		p->likelihood_func > 2 || p->mean_type < 0 || p->mean_type > 2 || p->resampling_type < 0 || p->resampling_type > 3)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_configure: enum parameter out of range");
+	if(p->resampling_type == MTFB_PF_RESAMPLE_RESIDUAL) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_pf_configure: Residual resampling "
+		"(NT/PF.cc:542-585, an unstable std::sort over all but the last particle) is not implemented");
+	if(p->likelihood_func != MTFB_PF_LIKELIHOOD_AM && c->prm.am == MTFB_AM_MI) return fail(MTFB_ERR_NOT_SUPPORTED,
+		"mtfb_pf_configure: MI particles support likelihood_func = AM only");
+	if(p->likelihood_func == MTFB_PF_LIKELIHOOD_GAUSSIAN && !(p->measurement_sigma > 0)) return fail(MTFB_ERR_INVALID_ARG,
+		"mtfb_pf_configure: measurement_sigma must be > 0");
+	for(int i = 0; i < 8; ++i) if(!(p->ssm_sigma[i] >= 0) || !std::isfinite(p->ssm_mean[i])) return fail(MTFB_ERR_INVALID_ARG,
+		"mtfb_pf_configure: ssm_sigma must be >= 0 and ssm_mean finite");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_pf); cudaFree(c->d_pf_ints); cudaFree(c->d_pf_rand_out); cudaFree(c->d_pf_rand_in);
+	c->d_pf = nullptr; c->d_pf_ints = nullptr; c->d_pf_rand_out = nullptr; c->d_pf_rand_in = nullptr; c->pf_rand_in_capacity = 0;
+	c->pf_configured = false;
+	const size_t P = c->P, n = p->n_particles, S = c->S, pn = P*n;
+	const size_t n_d = 4 * pn*S + 3 * pn + 8 * P;
+	CUDA_TRY(cudaMalloc(&c->d_pf, n_d*sizeof(double)));
+	CUDA_TRY(cudaMemset(c->d_pf, 0, n_d*sizeof(double)));
+	CUDA_TRY(cudaMalloc(&c->d_pf_ints, (pn + 3 * P)*sizeof(int)));
+	CUDA_TRY(cudaMemset(c->d_pf_ints, 0, (pn + 3 * P)*sizeof(int)));
+	PFDev &pf = c->pf;
+	std::memset(&pf, 0, sizeof(pf));
+	pf.n_particles = p->n_particles;
+	pf.corner_based = (p->corner_based_sampling != 0) ? 1 : 0;
+	pf.n_normals = pf.corner_based ? 10 : (int)S;
+	double *q = c->d_pf;
+	pf.states = q; q += pn*S; pf.ar = q; q += pn*S; pf.states_other = q; q += pn*S; pf.ar_other = q; q += pn*S;
+	pf.weights = q; q += pn; pf.cum_weights = q; q += pn; pf.similarity = q; q += pn; pf.prev_corners = q; q += 8 * P;
+	int *qi = c->d_pf_ints;
+	pf.src_id = qi; qi += pn; pf.max_wt_id = qi; qi += P; pf.resample_flag = qi; qi += P; pf.done = qi; qi += P;
+	for(int i = 0; i < 8; ++i){ pf.sigma[i] = p->ssm_sigma[i]; pf.mean[i] = p->ssm_mean[i]; }
+	pf.dynamic_model = p->dynamic_model; pf.update_type = p->update_type; pf.likelihood_func = p->likelihood_func;
+	pf.resampling_type = p->resampling_type; pf.mean_type = p->mean_type;
+	pf.adaptive = (p->adaptive_resampling_thresh > 0 && p->adaptive_resampling_thresh <= 1) ? 1 : 0;       // NT/PF.cc:113-117
+	pf.min_eff_particles = p->adaptive_resampling_thresh*p->n_particles;
+	pf.weights_in_smem = (n*sizeof(double) <= 160 * 1024) ? 1 : 0;
+	const double pi = 3.14159265358979323846;
+	pf.measurement_factor = 1.0 / std::sqrt(2 * pi*p->measurement_sigma);                                  // NT/PF.cc:81-82
+	pf.measurement_sigma = p->measurement_sigma;
+	// max_similarity = am->getSimilarity() after initializeSimilarity (NT/PF.cc:155-156): 0 for SSD, 1 for NCC
+	pf.max_similarity = c->prm.am == MTFB_AM_NCC ? 1.0 : 0.0;
+	pf.ar_coeff = p->ar_coeff; pf.epsilon = p->epsilon; pf.seed = p->seed; pf.object_offset = p->object_offset;
+	if(p->record_randoms){
+		const size_t n_r = (size_t)p->max_iters*pn*(pf.n_normals + 1);
+		CUDA_TRY(cudaMalloc(&c->d_pf_rand_out, n_r*sizeof(double)));
+		CUDA_TRY(cudaMemset(c->d_pf_rand_out, 0, n_r*sizeof(double)));
+	}
+	c->pfp = *p;
+	c->pf_configured = true;
+	c->pf_normals_pending = c->pf_uniforms_pending = false;
+	c->pf_frame = 0;
+	if(c->initialized){ CUDA_TRY(launch_pf_init_particles(c->prm.ssm, c->pf, c->b, true, c->stream)); ++c->launches; }
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_pf_set_random_stream(mtfb_ctx *c, const double *normals, const double *uniforms){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_set_random_stream: null context");
+	if(!c->pf_configured) return fail(MTFB_ERR_LOGIC, "mtfb_pf_set_random_stream: mtfb_pf_configure has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t pn = (size_t)c->P*c->pfp.n_particles, n_norm = (size_t)c->pfp.max_iters*pn*c->pf.n_normals, n_uni = (size_t)c->pfp.max_iters*pn;
+	if(!c->d_pf_rand_in){
+		CUDA_TRY(cudaMalloc(&c->d_pf_rand_in, (n_norm + n_uni)*sizeof(double)));
+		c->pf_rand_in_capacity = n_norm + n_uni;
+	}
+	if(normals) CUDA_TRY(cudaMemcpyAsync(c->d_pf_rand_in, normals, n_norm*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	if(uniforms) CUDA_TRY(cudaMemcpyAsync(c->d_pf_rand_in + n_norm, uniforms, n_uni*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->pf_normals_pending = normals != nullptr; c->pf_uniforms_pending = uniforms != nullptr;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_pf_get_random_stream(mtfb_ctx *c, double *normals, double *uniforms){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_get_random_stream: null context");
+	if(!c->pf_configured || !c->d_pf_rand_out) return fail(MTFB_ERR_LOGIC, "mtfb_pf_get_random_stream: configure with record_randoms = 1");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t pn = (size_t)c->P*c->pfp.n_particles, n_norm = (size_t)c->pfp.max_iters*pn*c->pf.n_normals, n_uni = (size_t)c->pfp.max_iters*pn;
+	if(normals) CUDA_TRY(cudaMemcpyAsync(normals, c->d_pf_rand_out, n_norm*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(uniforms) CUDA_TRY(cudaMemcpyAsync(uniforms, c->d_pf_rand_out + n_norm, n_uni*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_pf_get_particles(mtfb_ctx *c, double *states, double *weights, double *cum_weights, int *max_wt_id){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_pf_get_particles: null context");
+	if(!c->pf_configured || !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_pf_get_particles: configure and initialize first");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t pn = (size_t)c->P*c->pfp.n_particles;
+	if(states) CUDA_TRY(cudaMemcpyAsync(states, c->pf.states, pn*c->S*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(weights) CUDA_TRY(cudaMemcpyAsync(weights, c->pf.weights, pn*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(cum_weights) CUDA_TRY(cudaMemcpyAsync(cum_weights, c->pf.cum_weights, pn*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if(max_wt_id) CUDA_TRY(cudaMemcpyAsync(max_wt_id, c->pf.max_wt_id, (size_t)c->P*sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return MTFB_OK;
 }
 
 mtfb_status mtfb_update(mtfb_ctx *c){
 	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_update: null context");
 	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_update: initialize has not been called");
-	if(c->prm.sm == MTFB_SM_PF) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_update: a PF context evaluates particles with mtfb_pf_evaluate");
+	if(c->prm.sm == MTFB_SM_PF){
+		if(!c->pf_configured) return fail(MTFB_ERR_LOGIC, "mtfb_update: a PF context needs mtfb_pf_configure (before mtfb_initialize) to "
+			"track; without it it only evaluates particles (mtfb_pf_evaluate)");
+		return pf_update(c);
+	}
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
 	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads));

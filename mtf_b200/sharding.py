@@ -41,6 +41,15 @@ def all_gather_rows(local, n_total, group=None):
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
 
 
+def device_view(ptr, shape, device, typestr="<f8"):
+    """zero-copy torch view of a device array the library owns (mtfb_device_results): nothing is copied or moved"""
+    import torch
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_Raw(), device=device)
+
+
 class ShardedBatchTracker:
     """The batch of `corners.shape[0]` patches split over the ranks of a torch.distributed group.
 
@@ -55,6 +64,7 @@ class ShardedBatchTracker:
         self.n_total = n_total
         self.lo, self.hi = shard_range(n_total, self.world, self.rank)
         self.local = make_local(self.hi - self.lo)
+        self._d_corners = None
 
     def initialize(self, corners, img):
         c = np.asarray(corners, dtype=np.float64).reshape(self.n_total, 2, 4)
@@ -63,10 +73,24 @@ class ShardedBatchTracker:
     def update(self, img):
         self.local.update(img)
 
+    def local_corners_device(self, device):
+        """the local tracker's (n_local, 8) result array where the kernel wrote it: a torch view of the library's device
+        buffer (mtfb_device_results), no host hop"""
+        if self._d_corners is None:
+            ptr = self.local.device_results()[0]
+            self._d_corners = device_view(ptr, (self.hi - self.lo, 8), device)
+        return self._d_corners
+
     def getRegion(self, device=None):
-        """(n_total, 2, 4) corners of every patch, on every rank"""
+        """(n_total, 2, 4) corners of every patch, on every rank.  With a CUDA `device` and a local tracker that exposes its
+        device result array (BatchTracker.device_results) the all-gather reads the kernel's output buffer directly (NCCL on
+        the current stream, which must be the tracker's stream: bench.py sets both); otherwise (CPU tests over gloo) through
+        the host getter."""
         import torch
-        loc = torch.as_tensor(np.ascontiguousarray(self.local.getRegion()).reshape(-1, 8))
-        if device is not None:
-            loc = loc.to(device)
+        if device is not None and hasattr(self.local, "device_results"):
+            loc = self.local_corners_device(device)
+        else:
+            loc = torch.as_tensor(np.ascontiguousarray(self.local.getRegion()).reshape(-1, 8))
+            if device is not None:
+                loc = loc.to(device)
         return all_gather_rows(loc, self.n_total, self.group).reshape(self.n_total, 2, 4)

@@ -1662,4 +1662,259 @@ long orc_batch_track(const orc_params *p, const float *const *frames, int n_fram
 	return total;
 }
 
+// The same with GridTracker's per-frame reset (grid_reset_at_each_frame = 1, SM/src/GridTracker.cc:265-285, 345-392:
+// every cell is re-initialised on the current frame after its update; here at its initial corners, a static grid).
+long orc_batch_track_reset(const orc_params *p, const float *const *frames, int n_frames, int h, int w,
+	const double *corners, int n_patches, int n_threads, double *final_corners, int *iters_per_patch, double *seconds){
+	std::vector<orc_tracker*> tr(n_patches);
+#ifdef _OPENMP
+	if(n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+	#pragma omp parallel for schedule(dynamic)
+	for(int i = 0; i < n_patches; ++i){
+		tr[i] = new orc_tracker(*p);
+		tr[i]->am.setCurrImg(frames[0], h, w);
+		tr[i]->initialize(corners + 8 * (size_t)i);
+		if(iters_per_patch) iters_per_patch[i] = 0;
+	}
+	long total = 0;
+	double t0 = now_s();
+	for(int fr = 1; fr < n_frames; ++fr){
+		#pragma omp parallel for schedule(dynamic) reduction(+:total)
+		for(int i = 0; i < n_patches; ++i){
+			tr[i]->am.setCurrImg(frames[fr], h, w);
+			tr[i]->update();
+			total += tr[i]->n_iters;
+			if(iters_per_patch) iters_per_patch[i] += tr[i]->n_iters;
+			if(final_corners && fr == n_frames - 1) std::memcpy(final_corners + 8 * (size_t)i, tr[i]->ssm.curr_corners, 8 * sizeof(double));
+			tr[i]->initialize(corners + 8 * (size_t)i);
+		}
+	}
+	if(seconds) *seconds = now_s() - t0;
+	for(int i = 0; i < n_patches; ++i) delete tr[i];
+	return total;
+}
+
+// PF particle evaluation of n_objects templates x n_particles states (NT/PF.cc:303-320), OpenMP over (object, particle
+// chunk) pairs, every thread on its own copy of the object's tracker.  states: n_objects x n_particles x S.
+long orc_batch_pf_evaluate(const orc_params *p, const float *frame0, const float *frame1, int h, int w, const double *corners,
+	int n_objects, const double *states, int n_particles, int n_threads, double *likelihood, double *seconds){
+#ifdef _OPENMP
+	if(n_threads > 0) omp_set_num_threads(n_threads);
+	const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
+#else
+	const int nt = 1;
+#endif
+	int chunks = (nt + n_objects - 1) / n_objects;             // particle chunks per object: at least one task per thread
+	if(chunks < 1) chunks = 1;
+	const int n_tasks = n_objects*chunks;
+	std::vector<orc_tracker*> tr(n_tasks);
+	#pragma omp parallel for schedule(dynamic)
+	for(int k = 0; k < n_tasks; ++k){
+		const int o = k / chunks;
+		tr[k] = new orc_tracker(*p);
+		tr[k]->am.setCurrImg(frame0, h, w);
+		tr[k]->initialize(corners + 8 * (size_t)o);
+		tr[k]->am.setCurrImg(frame1, h, w);
+	}
+	const int S = tr[0]->S;
+	double t0 = now_s();
+	#pragma omp parallel for schedule(dynamic)
+	for(int k = 0; k < n_tasks; ++k){
+		const int o = k / chunks, c = k % chunks;
+		const int lo = (int)((long long)n_particles*c / chunks), hi = (int)((long long)n_particles*(c + 1) / chunks);
+		orc_pf_evaluate(tr[k], states + ((size_t)o*n_particles + lo)*S, hi - lo, likelihood + (size_t)o*n_particles + lo, nullptr);
+	}
+	if(seconds) *seconds = now_s() - t0;
+	for(int k = 0; k < n_tasks; ++k) delete tr[k];
+	return (long)n_objects*n_particles;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// nt::PF (SM/src/NT/PF.cc) with ONE sampler distribution, the random deviates supplied by the caller (the reference draws them
+// from Boost generators seeded by random_device: NT/PF.cc:100-110, ProjectiveBase.cc:192-197).
+// ---------------------------------------------------------------------------------------------
+struct orc_pf{
+	orc_tracker *t;
+	orc_pf_params p;
+	int S, n, n_normals;
+	std::vector<double> states[2], ar[2], wts, cum;
+	int cur, max_wt_id, n_iters, resampled;
+	double prev_corners[8], max_similarity, measurement_factor;
+	bool adaptive; double min_eff_particles;
+
+	// ProjectiveBase::generatePerturbation ProjectiveBase.cc:301-306 ; Homography::generatePerturbation Homography.cc:899-915
+	void generatePerturbation(double *z, const double *nrm){
+		if(t->ssm.type == ORC_SSM_HOMOGRAPHY && p.corner_based_sampling){
+			const double tx = p.ssm_mean[0] + p.ssm_sigma[0] * nrm[0], ty = p.ssm_mean[0] + p.ssm_sigma[0] * nrm[1];
+			double dc[8];
+			for(int c = 0; c < 4; ++c){
+				const double dx = p.ssm_mean[1] + p.ssm_sigma[1] * nrm[2 + 2 * c], dy = p.ssm_mean[1] + p.ssm_sigma[1] * nrm[3 + 2 * c];
+				dc[c] = (t->ssm.init_corners[c] + dx) + tx; dc[4 + c] = (t->ssm.init_corners[4 + c] + dy) + ty;
+			}
+			Mat3 W = computeHomographyDLT(t->ssm.init_corners, dc);        // estimateWarpFromCorners Homography.cc:877-883
+			const double d = W(2, 2);
+			for(int i = 0; i < 9; ++i) W.m[i] = W.m[i] / d;
+			t->ssm.getStateFromWarp(z, W);
+		} else{
+			for(int s = 0; s < S; ++s) z[s] = p.ssm_mean[s] + p.ssm_sigma[s] * nrm[s];
+		}
+	}
+	void normalize_hom(Mat3 &W) const{
+		if(t->ssm.type != ORC_SSM_HOMOGRAPHY) return;                   // ProjectiveBase's versions do not normalise
+		const double d = W(2, 2);
+		for(int i = 0; i < 9; ++i) W.m[i] = W.m[i] / d;
+	}
+	void perturb(double *st, double *a, const double *nrm){
+		double z[8], base[8], base_ar[8];
+		generatePerturbation(z, nrm);
+		for(int s = 0; s < S; ++s){ base[s] = st[s]; base_ar[s] = a[s]; }
+		if(p.update_type == 0){
+			if(p.dynamic_model == 0){ for(int s = 0; s < S; ++s) st[s] = base[s] + z[s]; }           // ProjectiveBase.cc:255-259
+			else{
+				for(int s = 0; s < S; ++s){ const double ns = base[s] + base_ar[s] + z[s]; st[s] = ns; a[s] = p.ar_coeff*(ns - base[s]); }
+			}
+			return;
+		}
+		Mat3 Wb, Wz, War;
+		t->ssm.getWarpFromState(Wb, base); t->ssm.getWarpFromState(Wz, z);
+		if(p.dynamic_model == 0){
+			Mat3 W = mul3(Wb, Wz);                                       // Homography.cc:917-926
+			normalize_hom(W);
+			t->ssm.getStateFromWarp(st, W);
+			return;
+		}
+		t->ssm.getWarpFromState(War, base_ar);
+		Mat3 W = mul3(mul3(Wb, War), Wz);                               // Homography.cc:928-942
+		normalize_hom(W);
+		Mat3 A = mul3(inverse3(Wb), W);
+		normalize_hom(A);
+		t->ssm.getStateFromWarp(st, W);
+		double na[8];
+		t->ssm.getStateFromWarp(na, A);
+		for(int s = 0; s < S; ++s) a[s] = na[s] * p.ar_coeff;
+	}
+	void initializeParticles(){                                          // NT/PF.cc:185-198
+		const double init_wt = 1.0 / n;
+		for(int i = 0; i < n; ++i){
+			for(int s = 0; s < S; ++s){ states[cur][(size_t)i*S + s] = t->ssm.curr_state[s]; ar[cur][(size_t)i*S + s] = 0; }
+			wts[i] = init_wt;
+			cum[i] = i > 0 ? wts[i] + cum[i - 1] : wts[i];
+		}
+	}
+	void multinomialResampling(const double *uni){                        // NT/PF.cc:448-540 (binary and linear pick the same particle)
+		const double total = cum[n - 1];
+		for(int i = 0; i < n; ++i) cum[i] = cum[i] / total;
+		double max_wt = std::numeric_limits<double>::lowest();
+		for(int i = 0; i < n; ++i){
+			const double u = uni[i];
+			int lower = 0, upper = n - 1, id = (lower + upper) / 2;
+			while(upper > lower){
+				if(cum[id] >= u) upper = id; else lower = id + 1;
+				id = (lower + upper) / 2;
+			}
+			std::memcpy(&states[1 - cur][(size_t)i*S], &states[cur][(size_t)id*S], S*sizeof(double));
+			std::memcpy(&ar[1 - cur][(size_t)i*S], &ar[cur][(size_t)id*S], S*sizeof(double));
+			if(wts[id] >= max_wt){ max_wt = wts[id]; max_wt_id = i; }
+		}
+		cur = 1 - cur;
+	}
+	int update(const double *normals, const double *uniforms){             // NT/PF.cc:207-446
+		n_iters = 0;
+		for(int it = 0; it < p.max_iters; ++it){
+			double max_wt = std::numeric_limits<double>::lowest();
+			for(int i = 0; i < n; ++i){
+				double *st = &states[cur][(size_t)i*S], *a = &ar[cur][(size_t)i*S];
+				perturb(st, a, normals + ((size_t)it*n + i)*n_normals);
+				t->ssm.setState(st);
+				t->am.updatePixVals(t->ssm.curr_pts.data());
+				t->am.updateSimilarity(false);
+				const double m = max_similarity - t->am.f;
+				double lik;
+				if(p.likelihood_func == 0) lik = t->am.getLikelihood();
+				else if(p.likelihood_func == 1) lik = measurement_factor * std::exp(-0.5*m / p.measurement_sigma);
+				else lik = 1.0 / (1.0 + m);
+				wts[i] = lik;
+				cum[i] = i == 0 ? wts[i] : wts[i] + cum[i - 1];
+				if(wts[i] >= max_wt){ max_wt = wts[i]; max_wt_id = i; }
+			}
+			bool perform_resampling = true;
+			if(adaptive){
+				double sum = 0; for(int i = 0; i < n; ++i) sum += wts[i];
+				double q = 0; for(int i = 0; i < n; ++i){ const double v = wts[i] / sum; q += v*v; }
+				const double n_eff = q == 0 ? 0 : 1.0 / q;
+				if(n_eff > min_eff_particles) perform_resampling = false;
+			}
+			resampled = 0;
+			if(perform_resampling && (p.resampling_type == 1 || p.resampling_type == 2)){
+				multinomialResampling(uniforms + (size_t)it*n); resampled = 1;
+			}
+			if(p.mean_type == 0){
+				t->ssm.setState(&states[cur][(size_t)max_wt_id*S]);
+			} else if(p.mean_type == 1){
+				double mean[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };                 // ProjectiveBase::estimateMeanOfSamples :308-314
+				for(int i = 0; i < n; ++i) for(int s = 0; s < S; ++s) mean[s] += (states[cur][(size_t)i*S + s] - mean[s]) / (i + 1);
+				t->ssm.setState(mean);
+			} else{
+				double mc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };                   // updateMeanCorners NT/PF.cc:587-594
+				for(int i = 0; i < n; ++i){
+					t->ssm.setState(&states[cur][(size_t)i*S]);
+					for(int k = 0; k < 8; ++k) mc[k] += (t->ssm.curr_corners[k] - mc[k]) / (i + 1);
+				}
+				t->ssm.setCorners(mc);
+			}
+			double upd = 0;
+			for(int k = 0; k < 8; ++k){ const double d = prev_corners[k] - t->ssm.curr_corners[k]; upd += d*d; }
+			std::memcpy(prev_corners, t->ssm.curr_corners, sizeof(prev_corners));
+			++n_iters;
+			if(upd < p.epsilon) break;
+		}
+		if(p.reset_to_mean) initializeParticles();
+		return 0;
+	}
+};
+
+extern "C" {
+
+orc_pf *orc_pf_create(const orc_params *tp, const orc_pf_params *pp){
+	orc_pf *f = new orc_pf();
+	orc_params q = *tp; q.sm = ORC_SM_FCLK;
+	f->t = new orc_tracker(q);
+	f->p = *pp; f->S = f->t->S; f->n = pp->n_particles;
+	f->n_normals = (f->t->ssm.type == ORC_SSM_HOMOGRAPHY && pp->corner_based_sampling) ? 10 : f->S;
+	for(int k = 0; k < 2; ++k){ f->states[k].assign((size_t)f->n*f->S, 0); f->ar[k].assign((size_t)f->n*f->S, 0); }
+	f->wts.assign(f->n, 0); f->cum.assign(f->n, 0);
+	f->cur = 0; f->max_wt_id = 0; f->n_iters = 0; f->resampled = 0;
+	const double pi = 3.14159265358979323846;
+	f->measurement_factor = 1.0 / std::sqrt(2 * pi*pp->measurement_sigma);
+	f->adaptive = pp->adaptive_resampling_thresh > 0 && pp->adaptive_resampling_thresh <= 1;
+	f->min_eff_particles = pp->adaptive_resampling_thresh*pp->n_particles;
+	f->max_similarity = 0;
+	return f;
+}
+void orc_pf_destroy(orc_pf *f){ if(f){ delete f->t; delete f; } }
+void orc_pf_set_image(orc_pf *f, const float *img, int h, int w){ f->t->am.setCurrImg(img, h, w); }
+int orc_pf_initialize(orc_pf *f, const double *corners){                  // NT/PF.cc:136-183
+	if(!f->t->ssm.setCorners(corners)) return 1;
+	f->t->am.initializePixVals(f->t->ssm.curr_pts.data());
+	f->t->am.initializeSimilarity();
+	f->max_similarity = f->t->am.f;
+	f->initializeParticles();
+	std::memcpy(f->prev_corners, f->t->ssm.curr_corners, sizeof(f->prev_corners));
+	return 0;
+}
+int orc_pf_update(orc_pf *f, const double *normals, const double *uniforms){ return f->update(normals, uniforms); }
+void orc_pf_get_corners(const orc_pf *f, double *out8){ std::memcpy(out8, f->t->ssm.curr_corners, 8 * sizeof(double)); }
+void orc_pf_get_state(const orc_pf *f, double *outS){ for(int s = 0; s < f->S; ++s) outS[s] = f->t->ssm.curr_state[s]; }
+int orc_pf_n_normals(const orc_pf *f){ return f->n_normals; }
+int orc_pf_get_particles(const orc_pf *f, double *states, double *wts, double *cum, int *resampled){
+	if(states) std::memcpy(states, f->states[f->cur].data(), (size_t)f->n*f->S*sizeof(double));
+	if(wts) std::memcpy(wts, f->wts.data(), f->n*sizeof(double));
+	if(cum) std::memcpy(cum, f->cum.data(), f->n*sizeof(double));
+	if(resampled) *resampled = f->resampled;
+	return f->max_wt_id;
+}
+
 } // extern "C"

@@ -131,6 +131,39 @@ long orc_batch_track(const orc_params *p, const float *const *frames, int n_fram
 	const double *corners /* P x 8 */, int n_patches, int n_threads,
 	double *final_corners /* P x 8 */, int *iters_per_patch, double *seconds);
 
+/* the same with GridTracker's per-frame reset of every cell at its initial corners (grid_reset_at_each_frame = 1);
+ * final_corners = the corners after the last frame's update, before its reset */
+long orc_batch_track_reset(const orc_params *p, const float *const *frames, int n_frames, int h, int w,
+	const double *corners /* P x 8 */, int n_patches, int n_threads,
+	double *final_corners /* P x 8 */, int *iters_per_patch, double *seconds);
+/* PF particle evaluation of n_objects templates (initialised on frame0) x n_particles states on frame1; returns the
+ * number of particle evaluations */
+long orc_batch_pf_evaluate(const orc_params *p, const float *frame0, const float *frame1, int h, int w,
+	const double *corners /* n_objects x 8 */, int n_objects, const double *states /* n_objects x n_particles x S */,
+	int n_particles, int n_threads, double *likelihood /* n_objects x n_particles */, double *seconds);
+
+/* nt::PF (SM/src/NT/PF.cc) with one sampler distribution; the caller supplies the random deviates:
+ * normals max_iters x n_particles x R (R = orc_pf_n_normals: S, or 10 with corner based sampling), uniforms max_iters x n_particles */
+typedef struct orc_pf_params {
+	int n_particles, max_iters;
+	double epsilon;
+	int dynamic_model, update_type, likelihood_func, resampling_type, mean_type, reset_to_mean;
+	double adaptive_resampling_thresh, measurement_sigma, ar_coeff;
+	double ssm_sigma[8], ssm_mean[8];
+	int corner_based_sampling;
+} orc_pf_params;
+typedef struct orc_pf orc_pf;
+orc_pf *orc_pf_create(const orc_params *tp, const orc_pf_params *pp);
+void orc_pf_destroy(orc_pf *f);
+void orc_pf_set_image(orc_pf *f, const float *img, int h, int w);
+int orc_pf_initialize(orc_pf *f, const double *corners);
+int orc_pf_update(orc_pf *f, const double *normals, const double *uniforms);
+void orc_pf_get_corners(const orc_pf *f, double *out8);
+void orc_pf_get_state(const orc_pf *f, double *outS);
+int orc_pf_n_normals(const orc_pf *f);
+/* particle_states[curr_set_id], particle_wts, particle_cum_wts (any may be NULL); returns max_wt_id */
+int orc_pf_get_particles(const orc_pf *f, double *states, double *wts, double *cum, int *resampled);
+
 #ifdef __cplusplus
 }
 #endif

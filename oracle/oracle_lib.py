@@ -25,6 +25,14 @@ class OrcParams(C.Structure):
                 ("likelihood_alpha", C.c_double), ("grad_mode", C.c_int), ("fast_sums", C.c_int)]
 
 
+class OrcPFParams(C.Structure):
+    _fields_ = [("n_particles", C.c_int), ("max_iters", C.c_int), ("epsilon", C.c_double),
+                ("dynamic_model", C.c_int), ("update_type", C.c_int), ("likelihood_func", C.c_int),
+                ("resampling_type", C.c_int), ("mean_type", C.c_int), ("reset_to_mean", C.c_int),
+                ("adaptive_resampling_thresh", C.c_double), ("measurement_sigma", C.c_double), ("ar_coeff", C.c_double),
+                ("ssm_sigma", C.c_double * 8), ("ssm_mean", C.c_double * 8), ("corner_based_sampling", C.c_int)]
+
+
 class OrcIterLog(C.Structure):
     _fields_ = [("f", C.c_double), ("jacobian", C.c_double * 8), ("hessian", C.c_double * 64),
                 ("state_update", C.c_double * 8), ("corners", C.c_double * 8),
@@ -82,6 +90,19 @@ def lib():
     L.orc_batch_track.argtypes = [C.POINTER(OrcParams), C.POINTER(fp), C.c_int, C.c_int, C.c_int, dp, C.c_int,
                                   C.c_int, dp, ip, dp]
     L.orc_batch_track.restype = C.c_long
+    L.orc_batch_track_reset.argtypes = L.orc_batch_track.argtypes
+    L.orc_batch_track_reset.restype = C.c_long
+    L.orc_batch_pf_evaluate.argtypes = [C.POINTER(OrcParams), fp, fp, C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, dp, dp]
+    L.orc_batch_pf_evaluate.restype = C.c_long
+    L.orc_pf_create.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcPFParams)]; L.orc_pf_create.restype = C.c_void_p
+    L.orc_pf_destroy.argtypes = [C.c_void_p]
+    L.orc_pf_set_image.argtypes = [C.c_void_p, fp, C.c_int, C.c_int]
+    L.orc_pf_initialize.argtypes = [C.c_void_p, dp]
+    L.orc_pf_update.argtypes = [C.c_void_p, dp, dp]
+    L.orc_pf_get_corners.argtypes = [C.c_void_p, dp]
+    L.orc_pf_get_state.argtypes = [C.c_void_p, dp]
+    L.orc_pf_n_normals.argtypes = [C.c_void_p]; L.orc_pf_n_normals.restype = C.c_int
+    L.orc_pf_get_particles.argtypes = [C.c_void_p, dp, dp, dp, ip]; L.orc_pf_get_particles.restype = C.c_int
     _lib = L
     return L
 
@@ -284,14 +305,81 @@ def norm_unit_square_pts(resx, resy, min_x=-0.5, min_y=-0.5, max_x=0.5, max_y=0.
     return pts.reshape(-1, 2), c.reshape(2, 4)
 
 
-def batch_track(params, frames, corners, n_threads=0):
-    """CPU baseline driver: P independent trackers, OpenMP over patches (GridTracker.cc:253-256)."""
+def batch_track(params, frames, corners, n_threads=0, reset_each_frame=False):
+    """CPU baseline driver: P independent trackers, OpenMP over patches (GridTracker.cc:253-256); reset_each_frame: every
+    tracker is re-initialised at its initial corners after each frame (GridTracker's grid_reset_at_each_frame)."""
     frames = [np.ascontiguousarray(f, dtype=np.float32) for f in frames]
     h, w = frames[0].shape
     arr = (C.POINTER(C.c_float) * len(frames))(*[_fp(f) for f in frames])
     corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 8)
     P = corners.shape[0]
     final = np.empty((P, 8)); iters = np.zeros(P, dtype=np.int32); secs = C.c_double(0)
-    total = lib().orc_batch_track(C.byref(params), arr, len(frames), h, w, _dp(corners), P, n_threads,
-                                  _dp(final), iters.ctypes.data_as(C.POINTER(C.c_int)), C.byref(secs))
+    fn = lib().orc_batch_track_reset if reset_each_frame else lib().orc_batch_track
+    total = fn(C.byref(params), arr, len(frames), h, w, _dp(corners), P, n_threads,
+               _dp(final), iters.ctypes.data_as(C.POINTER(C.c_int)), C.byref(secs))
     return total, secs.value, final.reshape(P, 2, 4), iters
+
+
+def batch_pf_evaluate(params, frame0, frame1, corners, states, n_threads=0):
+    """CPU baseline driver of the PF particle loop: (evaluations, seconds, likelihood (n_objects, n_particles))"""
+    f0 = np.ascontiguousarray(frame0, dtype=np.float32); f1 = np.ascontiguousarray(frame1, dtype=np.float32)
+    h, w = f0.shape
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 8)
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    n_obj, n_part = states.shape[0], states.shape[1]
+    lik = np.empty((n_obj, n_part)); secs = C.c_double(0)
+    n = lib().orc_batch_pf_evaluate(C.byref(params), _fp(f0), _fp(f1), h, w, _dp(corners), n_obj, _dp(states), n_part, n_threads,
+                                    _dp(lik), C.byref(secs))
+    return n, secs.value, lik
+
+
+class OraclePF:
+    """nt::PF restated (oracle/mtf_oracle.cpp orc_pf) for one object; the caller supplies the random deviates"""
+
+    def __init__(self, params, pf_params):
+        """pf_params: any structure with the OrcPFParams field names (e.g. mtf_b200.api.PFParams)"""
+        self._L = lib()
+        q = OrcPFParams()
+        for name, _ in OrcPFParams._fields_:
+            v = getattr(pf_params, name)
+            if name in ("ssm_sigma", "ssm_mean"):
+                for i in range(8):
+                    getattr(q, name)[i] = v[i]
+            else:
+                setattr(q, name, v)
+        self.pf_params = q
+        self._h = self._L.orc_pf_create(C.byref(params), C.byref(q))
+        self.S = 8 if params.ssm == 0 else 6
+        self.n = q.n_particles
+        self.n_normals = self._L.orc_pf_n_normals(self._h)
+        self._img = None
+
+    def __del__(self):
+        try:
+            self._L.orc_pf_destroy(self._h)
+        except Exception:
+            pass
+
+    def set_image(self, img):
+        self._img = np.ascontiguousarray(img, dtype=np.float32)
+        self._L.orc_pf_set_image(self._h, _fp(self._img), self._img.shape[0], self._img.shape[1])
+
+    def initialize(self, corners):
+        c = np.ascontiguousarray(corners, dtype=np.float64).reshape(8)
+        return self._L.orc_pf_initialize(self._h, _dp(c))
+
+    def update(self, normals, uniforms):
+        a = np.ascontiguousarray(normals, dtype=np.float64).reshape(self.pf_params.max_iters, self.n, self.n_normals)
+        b = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.pf_params.max_iters, self.n)
+        return self._L.orc_pf_update(self._h, _dp(a), _dp(b))
+
+    def corners(self):
+        out = np.empty(8); self._L.orc_pf_get_corners(self._h, _dp(out)); return out.reshape(2, 4)
+
+    def state(self):
+        out = np.empty(self.S); self._L.orc_pf_get_state(self._h, _dp(out)); return out
+
+    def particles(self):
+        st = np.empty((self.n, self.S)); w = np.empty(self.n); cw = np.empty(self.n); r = C.c_int(0)
+        mx = self._L.orc_pf_get_particles(self._h, _dp(st), _dp(w), _dp(cw), C.byref(r))
+        return st, w, cw, mx, bool(r.value)

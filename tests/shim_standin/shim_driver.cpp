@@ -34,6 +34,10 @@ int main(int argc, char **argv){
 			for(int k = 0; k < 8; ++k) c.at<double>(k / 4, k % 4) = corners[8 * (size_t)i + k];
 			single[i]->initialize(img, c);
 			members[i]->setImage(img); members[i]->initialize(c);
+			// GridTracker::resetTrackers reads the region right after initialising a member (GridTracker.cc:381-387): it must
+			// be the supplied one even though the batch is only (re)initialised when its last member has arrived
+			const cv::Mat &r = members[i]->getRegion();
+			for(int k = 0; k < 8; ++k) if(r.at<double>(k / 4, k % 4) != corners[8 * (size_t)i + k]){ printf("STALE %d\n", i); break; }
 		}
 		for(int t = 1; t < n; ++t){
 			load(t);
@@ -59,6 +63,22 @@ int main(int argc, char **argv){
 			for(int t = 1; t < n; ++t){ load8(t); raw.update(); }
 			const cv::Mat &a = raw.getRegion();
 			for(int k = 0; k < 8; ++k) printf("RAW %.17g\n", a.at<double>(k / 4, k % 4));
+		}
+		// (4) the particle filter as a TrackerBase (mtf::b200::PFTracker), device generator with a fixed seed
+		if(argc > 7 && !strcmp(argv[7], "raw") && !strcmp(argv[5], "8")){
+			mtfb_pf_params pf;
+			mtfb_pf_default_params(&pf);
+			pf.n_particles = 300; pf.ssm_sigma[0] = 0.5; pf.ssm_sigma[1] = 0.2; pf.seed = 77; pf.mean_type = MTFB_PF_MEAN_SSM;
+			mtf::b200::PFTracker pft(argv[4], argv[5], res, res, pf);
+			load(0);
+			cv::Mat c(2, 4, CV_64FC1);
+			for(int k = 0; k < 8; ++k) c.at<double>(k / 4, k % 4) = corners[k];
+			pft.initialize(img, c);
+			for(int t = 1; t < n; ++t){ load(t); pft.update(); }
+			const cv::Mat &a = pft.getRegion();
+			for(int k = 0; k < 8; ++k) printf("PF %.17g\n", a.at<double>(k / 4, k % 4));
+			try{ mtf::b200::Tracker bad("pf", argv[4], argv[5], res, res); printf("NOEXCPF\n"); }
+			catch(const mtf::utils::Exception &e){ printf("EXCPF %s\n", e.type()); }
 		}
 		// error contract: a bad corner matrix is an InvalidArgument exception, not a crash
 		try{ cv::Mat bad(3, 4, CV_64FC1); single[0]->initialize(bad); printf("NOEXC\n"); }

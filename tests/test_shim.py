@@ -44,6 +44,7 @@ def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
     vals = np.array([[float(x) for x in l.split()] for l in out if l and l[0] in "-0123456789"])
     single, member = vals[:, 0].reshape(len(cs), 2, 4), vals[:, 1].reshape(len(cs), 2, 4)
     assert "EXC InvalidArgument" in out
+    assert not [l for l in out if l.startswith("STALE")], out
     hess = {"fclk": 1, "esm": 2}[sm]
     tr = api.BatchTracker(api.make_params(am, {"8": "homography", "6": "affine"}[ssm], sm, n_patches=len(cs), resx=res, resy=res,
                                           hess_type=hess))
@@ -65,3 +66,13 @@ def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
     for t in (1, 2):
         t8.setRawImage(u8[t]); t8.update()
     assert np.abs(raw - t8.getRegion()[0]).max() <= 1e-9
+    if ssm == "8":
+        # mtf::b200::PFTracker == the Python binding's PFTracker with the same seed (device generator: deterministic)
+        pfc = np.array([float(l.split()[1]) for l in out if l.startswith("PF ")]).reshape(2, 4)
+        assert "EXCPF InvalidArgument" in out
+        pt = api.PFTracker(api.make_params(am, "homography", "pf", n_patches=1, resx=res, resy=res), n_particles=300,
+                           sigma=[0.5, 0.2, 0, 0, 0, 0, 0, 0], seed=77, mean_type="ssm")
+        pt.initialize(cs[:1], frames[0])
+        for t in (1, 2):
+            pt.update(frames[t])
+        assert np.abs(pfc - pt.getRegion()[0]).max() <= 1e-9
