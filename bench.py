@@ -244,54 +244,64 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
     last_frame = order[(args.warmup + args.steps - 1) % len(order)]
 
     # ------------------------------------------------------------------ end to end (host buffers)
-    tr.initialize(corners, frames[0])
+    # every step: one frame H2D from pinned host memory, the update, the P x 8 corners D2H, the caller waits for them.
+    # "serial": the frame of step i is uploaded in front of update(i) on the same stream (mtfb_set_image);
+    # "pipelined" (the e2e figure): frame i + 1 is handed over right after update(i) has been enqueued and uploads on the
+    # library's copy stream while update(i) runs (mtfb_set_image_async, double-buffered) -- what a video pipeline does
     host_out = torch.empty((P, 8), dtype=torch.float64).pin_memory()
-    for i in range(args.warmup):
-        tr.set_image_pinned(pinned[order[i % len(order)]].data_ptr(), IMG, IMG, IMG)
-        tr.update()
-        host_out.copy_(d_corners, non_blocking=True)
-    barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    win0 = time.time()
-    wall0 = time.perf_counter()
-    t0.record(stream)
-    for i in range(args.steps):
-        tr.set_image_pinned(pinned[order[(args.warmup + i) % len(order)]].data_ptr(), IMG, IMG, IMG)   # H2D, 4 MB
-        tr.update()
-        host_out.copy_(d_corners, non_blocking=True)                                                   # D2H, 64 KB
-        stream.synchronize()                                                                          # the caller reads the corners
-    t1.record(stream)
-    barrier()
-    e2e_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0))
-    windows.append((win0, time.time()))
 
-    # ------------------------------------------------------------------ end to end from RAW frames
-    # the host hands over the uint8 frame MTF's pre-processor would receive; gray conversion and the 5 x 5 Gaussian run on
-    # the device behind a 1 MB upload (instead of a host cv::GaussianBlur and a 4 MB upload)
-    tr.set_raw_image_pinned(raw_pinned[0].data_ptr(), IMG, IMG, IMG, 1)
-    tr.initialize(corners)
-    for i in range(args.warmup):
-        tr.set_raw_image_pinned(raw_pinned[order[i % len(order)]].data_ptr(), IMG, IMG, IMG, 1)
-        tr.update()
-        host_out.copy_(d_corners, non_blocking=True)
-    barrier()
-    wall0 = time.perf_counter()
-    t0.record(stream)
-    for i in range(args.steps):
-        tr.set_raw_image_pinned(raw_pinned[order[(args.warmup + i) % len(order)]].data_ptr(), IMG, IMG, IMG, 1)   # H2D, 1 MB
-        tr.update()
-        host_out.copy_(d_corners, non_blocking=True)
-        stream.synchronize()
-    t1.record(stream)
-    barrier()
-    raw_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0))
+    def frame_ptr(i, raw=False):
+        return (raw_pinned if raw else pinned)[order[i % len(order)]].data_ptr()
+
+    def e2e_loop(raw, pipelined):
+        def upload(i, prefetch):
+            if raw:
+                (tr.prefetch_raw_image_pinned if prefetch else tr.set_raw_image_pinned)(frame_ptr(i, True), IMG, IMG, IMG, 1)
+            else:
+                (tr.prefetch_image_pinned if prefetch else tr.set_image_pinned)(frame_ptr(i), IMG, IMG, IMG)
+
+        def run(n, first):
+            for i in range(first, first + n):
+                if pipelined:
+                    tr.update()                      # samples frame i (prefetched during step i - 1)
+                    upload(i + 1, True)              # H2D of the next frame overlaps this update
+                else:
+                    upload(i, False)
+                    tr.update()
+                host_out.copy_(d_corners, non_blocking=True)
+                stream.synchronize()                 # the caller reads the corners
+        if raw:
+            tr.set_raw_image_pinned(raw_pinned[0].data_ptr(), IMG, IMG, IMG, 1)
+            tr.initialize(corners)
+        else:
+            tr.initialize(corners, frames[0])
+        if pipelined:
+            upload(0, True)
+        run(args.warmup, 0)
+        barrier()
+        w0 = time.time()
+        wall0 = time.perf_counter()
+        t0.record(stream)
+        run(args.steps, args.warmup)
+        t1.record(stream)
+        barrier()
+        tr.update()                                  # consumes the last prefetched frame (pipelined) before the next arm
+        tr.synchronize()
+        return max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0)), (w0, time.time())
+
+    e2e_serial_ms, _ = e2e_loop(False, False)
+    e2e_ms, win = e2e_loop(False, True)
+    windows.append(win)
+    # end to end from RAW frames: the host hands over the uint8 frame MTF's pre-processor would receive; gray
+    # conversion and the 5 x 5 Gaussian run on the device behind a 1 MB upload (instead of a host cv::GaussianBlur + 4 MB)
+    raw_ms, _ = e2e_loop(True, True)
     if world > 1:
-        t = torch.tensor([ms, kms, e2e_ms, raw_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, kms, e2e_ms, raw_ms, e2e_serial_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, kms, e2e_ms, raw_ms = [float(x) for x in t.tolist()]
+        ms, kms, e2e_ms, raw_ms, e2e_serial_ms = [float(x) for x in t.tolist()]
     tr.close()
-    return dict(ms=ms, kms=kms, e2e_ms=e2e_ms, raw_ms=raw_ms, launches=int(launches), status=status, final=final, windows=windows,
+    return dict(ms=ms, kms=kms, e2e_ms=e2e_ms, raw_ms=raw_ms, e2e_serial_ms=e2e_serial_ms, launches=int(launches), status=status, final=final, windows=windows,
                 truth=truth_error(final, corners, last_frame))
 
 
@@ -365,7 +375,11 @@ def config2_line(args, env, sampler, strong):
                    "occupancy": args.occ if args.threads else "auto",
                    "collective": "all_gather of P x 8 corners per frame from the kernel's output buffer" if world > 1 else "none"},
         "e2e": {"value": total_iters / (main["e2e_ms"] * 1e-3), "unit": "iters/s",
-                "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8},
+                "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8,
+                "upload": "frame i + 1 uploads on the library's copy stream while update(i) runs (mtfb_set_image_async, two device "
+                          "buffers); every step still moves one frame H2D and the P x 8 corners D2H and waits for them",
+                # the same with the frame of step i uploaded in front of update(i) on one stream (mtfb_set_image)
+                "serial_upload_value": total_iters / (main["e2e_serial_ms"] * 1e-3)},
         # the same with RAW uint8 frames: upload 1 B / pixel, gray + 5 x 5 Gaussian on the device (mtfb_set_image_u8), update, D2H
         "e2e_raw_u8": {"value": total_iters / (main["raw_ms"] * 1e-3), "unit": "iters/s",
                        "h2d_bytes_per_step": IMG * IMG, "d2h_bytes_per_step": P * 8 * 8, "gpu_launches_per_step": 2},

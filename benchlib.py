@@ -110,9 +110,13 @@ def timed_steps(env, n_warm, n_steps, step, kernel=None):
     return ms, kms, (w0, time.time())
 
 
-def timed_e2e(env, n_warm, n_steps, step):
-    """the same step from host buffers, the caller reading the result every step (stream.synchronize inside step)"""
+def timed_e2e(env, n_warm, n_steps, step, prime=None, drain=None):
+    """the same step from host buffers, the caller reading the result every step (stream.synchronize inside step).
+    prime(): hands the first frame over before the loop (steps prefetch the NEXT frame: mtfb_set_image_async); drain():
+    consumes the frame the last step prefetched"""
     torch = env.torch
+    if prime is not None:
+        prime()
     for i in range(n_warm):
         step(i)
     env.barrier()
@@ -125,7 +129,11 @@ def timed_e2e(env, n_warm, n_steps, step):
         step(n_warm + i)
     t1.record(env.stream)
     env.barrier()
-    return max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0)), (w0, time.time())
+    out = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0)), (w0, time.time())
+    if drain is not None:
+        drain()
+        env.barrier()
+    return out
 
 
 def roofline(alg_bytes_per_unit, units_per_launch, kernel_ms_per_launch, root, kernel, note, traffic=None, traffic_source=None):
@@ -206,13 +214,14 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
     finite = bool(np.isfinite(tr.getRegion()).all())
 
     def e2e_step(i):
-        tr.set_image_pinned(pinned[order[i % len(order)]].data_ptr(), h, w, w)
-        tr.update()
+        tr.update()                                                                  # frame i, prefetched during step i - 1
         host_out.copy_(d_corners, non_blocking=True)
         tr.initialize(cells)
+        tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), h, w, w)     # overlaps the kernels above
         env.stream.synchronize()
     tr.initialize(cells, frames[0])
-    e2e_ms, win2 = timed_e2e(env, n_warm, n_steps, e2e_step)
+    e2e_ms, win2 = timed_e2e(env, n_warm, n_steps, e2e_step, prime=lambda: tr.prefetch_image_pinned(pinned[order[0]].data_ptr(), h, w, w),
+                             drain=tr.update)
     ms, kms, e2e_ms = env.max_over_ranks([ms, kms, e2e_ms])
     total_iters = n_job * iters * n_steps
     alg = 16 * N + 432
@@ -289,12 +298,13 @@ def run_config4(env, root, n_steps, n_warm, n_patches=8192, cpu=True):
     status = tr.patch_status()
 
     def e2e_step(i):
-        tr.set_image_pinned(pinned[order[i % len(order)]].data_ptr(), size, size, size)
         tr.update()
+        tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), size, size, size)
         host_out.copy_(d_corners, non_blocking=True)
         env.stream.synchronize()
     tr.initialize(corners_all[lo:hi], frames[0])
-    e2e_ms, _ = timed_e2e(env, n_warm, n_steps, e2e_step)
+    e2e_ms, _ = timed_e2e(env, n_warm, n_steps, e2e_step, prime=lambda: tr.prefetch_image_pinned(pinned[order[0]].data_ptr(), size, size, size),
+                          drain=tr.update)
     ms, kms, e2e_ms = env.max_over_ranks([ms, kms, e2e_ms])
     total_iters = n_patches * iters * n_steps
     alg = 16 * N + 152
@@ -363,12 +373,13 @@ def run_config5(env, root, n_steps, n_warm, n_objects=64, n_particles=10000, pre
     final = tr.getRegion()
 
     def e2e_step(i):
-        tr.set_image_pinned(pinned[order[i % len(order)]].data_ptr(), h, w, w)
         tr.update()
+        tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), h, w, w)
         host_out.copy_(d_corners, non_blocking=True)
         env.stream.synchronize()
     tr.initialize(objs_all[lo:hi], frames[0])
-    e2e_ms, _ = timed_e2e(env, n_warm, n_steps, e2e_step)
+    e2e_ms, _ = timed_e2e(env, n_warm, n_steps, e2e_step, prime=lambda: tr.prefetch_image_pinned(pinned[order[0]].data_ptr(), h, w, w),
+                          drain=tr.update)
     ms, kms, e2e_ms = env.max_over_ranks([ms, kms, e2e_ms])
     total = n_objects * n_particles * n_steps
     out = {

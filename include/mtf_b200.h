@@ -152,6 +152,17 @@ mtfb_status mtfb_set_image_device(mtfb_ctx *ctx, const float *dev_img, int h, in
  * mtfb_set_image with the smoothed float frame.  kernel_size must be 5; sigma > 0 (sigma_y = sigma_x as MTF passes it). */
 mtfb_status mtfb_set_image_u8(mtfb_ctx *ctx, const unsigned char *host_img, int h, int w, int row_stride, int channels,
 	int kernel_size, double sigma);
+/* PREFETCH variants: the upload (and, for raw frames, the pre-processing) runs on a private copy stream into one of two
+ * device buffers while the context stream is still tracking the previous frame; the next mtfb_initialize / mtfb_set_region /
+ * mtfb_update waits for it (event, no host synchronisation) and samples it.  One frame may be in flight.  The host buffer must
+ * be pinned for the copy to overlap and must stay untouched until that next call has been made and the context synchronised
+ * (mtfb_synchronize, or any getter).  The reference has no counterpart: it re-reads the caller's buffer in place on every
+ * update() (TrackerBase.h:21-26) -- an application that wants the overlap hands frame t+1 over right after update(t):
+ *     mtfb_set_image_async(ctx, frame[0]); mtfb_initialize(ctx, corners);
+ *     for t: mtfb_set_image_async(ctx, frame[t]); mtfb_update(ctx); (read the results of t - 1 meanwhile) */
+mtfb_status mtfb_set_image_async(mtfb_ctx *ctx, const float *host_img, int h, int w, int row_stride);
+mtfb_status mtfb_set_image_u8_async(mtfb_ctx *ctx, const unsigned char *host_img, int h, int w, int row_stride, int channels,
+	int kernel_size, double sigma);
 /* the frame the trackers currently sample (after mtfb_set_image / mtfb_set_image_u8), h x w floats, contiguous; host pointer */
 mtfb_status mtfb_get_image(mtfb_ctx *ctx, float *out);
 

@@ -75,6 +75,7 @@ class IterLog(C.Structure):
 EXPORTS = [
     "mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_create", "mtfb_destroy",
     "mtfb_set_stream", "mtfb_synchronize", "mtfb_set_image", "mtfb_set_image_device", "mtfb_set_image_u8",
+    "mtfb_set_image_async", "mtfb_set_image_u8_async",
     "mtfb_get_image", "mtfb_initialize",
     "mtfb_set_region", "mtfb_update", "mtfb_iterate_once", "mtfb_enable_iter_log", "mtfb_get_iter_log",
     "mtfb_pf_evaluate", "mtfb_pf_evaluate_device", "mtfb_get_corners", "mtfb_get_state", "mtfb_get_n_iters",
@@ -108,6 +109,8 @@ def load_library(path=LIB_PATH):
     L.mtfb_set_image.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.mtfb_set_image_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.mtfb_set_image_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.mtfb_set_image_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.mtfb_set_image_u8_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
     L.mtfb_get_image.argtypes = [vp, vp]
     L.mtfb_initialize.argtypes = [vp, dp]
     L.mtfb_set_region.argtypes = [vp, dp]
@@ -273,6 +276,13 @@ class BatchTracker:
         out = np.empty((h, w), dtype=np.float32)
         self._check(self._L.mtfb_get_image(self._h, C.c_void_p(out.ctypes.data)))
         return out
+
+    def prefetch_image_pinned(self, ptr, h, w, row_stride):
+        """mtfb_set_image_async: upload on the copy stream while the previous frame is tracked; the next update() samples it"""
+        self._check(self._L.mtfb_set_image_async(self._h, C.c_void_p(ptr), h, w, row_stride))
+
+    def prefetch_raw_image_pinned(self, ptr, h, w, row_stride, channels, kernel_size=5, sigma=3.0):
+        self._check(self._L.mtfb_set_image_u8_async(self._h, C.c_void_p(ptr), h, w, row_stride, channels, kernel_size, float(sigma)))
 
     def set_image_pinned(self, ptr, h, w, row_stride):
         """host pointer variant (pinned buffers owned by the caller)"""

@@ -154,6 +154,12 @@ struct mtfb_ctx {
 	double *d_pf_rand_in; size_t pf_rand_in_capacity; bool pf_normals_pending, pf_uniforms_pending;
 	double *d_pf_rand_out;
 	long pf_frame;
+	// mtfb_set_image_async: frames uploaded on a copy stream into one of two buffers while the previous frame is tracked
+	cudaStream_t copy_stream; cudaEvent_t ev_upload, ev_read[2];
+	float *d_pre_img[2]; size_t pre_img_capacity[2];
+	unsigned char *d_pre_raw[2]; size_t pre_raw_capacity[2];
+	Image pre_image[2];
+	int pre_next, pre_pending, pre_current;      // slot of the next upload; slot uploaded but not adopted yet (-1); slot b.img points to (-1)
 };
 static const int4 *mom_work_for(const mtfb_ctx *c){
 	if(!c->d_mom_work) return nullptr;
@@ -191,6 +197,11 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32); cudaFree(c->d_raw);
 	cudaFree(c->d_mom_work);
 	cudaFree(c->d_pf); cudaFree(c->d_pf_ints); cudaFree(c->d_pf_rand_in); cudaFree(c->d_pf_rand_out);
+	if(c->copy_stream){
+		cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream);
+		cudaEventDestroy(c->ev_upload); cudaEventDestroy(c->ev_read[0]); cudaEventDestroy(c->ev_read[1]);
+	}
+	for(int k = 0; k < 2; ++k){ cudaFree(c->d_pre_img[k]); cudaFree(c->d_pre_raw[k]); }
 	if(c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 	return MTFB_OK;
@@ -359,6 +370,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		}
 		b.grad_mult = b.pix_mult / (2 * p->grad_eps);
 		b.img = make_image(nullptr, 0, 0, 0);
+		c->pre_pending = -1; c->pre_current = -1; c->pre_next = 0;
 	} while(0);
 	if(st != MTFB_OK){
 		cudaError_t e = cudaGetLastError();
@@ -402,7 +414,7 @@ mtfb_status mtfb_set_image(mtfb_ctx *c, const float *host_img, int h, int w, int
 	CUDA_TRY(cudaMemcpy2DAsync(c->d_img_own, (size_t)pitch*sizeof(float), host_img, (size_t)row_stride*sizeof(float),
 		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->stream));
 	c->b.img = make_image(c->d_img_own, h, w, pitch);
-	c->have_image = true;
+	c->have_image = true; c->pre_current = -1;
 	return MTFB_OK;
 }
 
@@ -442,12 +454,105 @@ mtfb_status mtfb_set_image_u8(mtfb_ctx *c, const unsigned char *host_img, int h,
 	CUDA_TRY(launch_preproc_gauss5(c->d_raw, (int)raw_pitch, channels, c->d_img_own, pitch, h, w, k5, c->stream));
 	++c->launches;
 	c->b.img = make_image(c->d_img_own, h, w, pitch);
+	c->have_image = true; c->pre_current = -1;
+	return MTFB_OK;
+}
+
+// ---- prefetched frames (mtfb_set_image_async / mtfb_set_image_u8_async)
+static cudaError_t gauss_kernel5(double sigma, float *k5){
+	// cv::getGaussianKernel(5, sigma, CV_32F) as OpenCV 2.4 / 3.x computes it
+	const double scale2X = -0.5 / (sigma*sigma);
+	double sum = 0;
+	for(int i = 0; i < 5; ++i){ const double x = i - 2.0; k5[i] = (float)std::exp(scale2X*x*x); sum += k5[i]; }
+	sum = 1. / sum;
+	for(int i = 0; i < 5; ++i) k5[i] = (float)(k5[i] * sum);
+	return cudaSuccess;
+}
+// called by everything that samples the frame: the launch waits for the pending upload and reads that buffer from now on
+static mtfb_status adopt_prefetched(mtfb_ctx *c){
+	if(c->pre_pending < 0) return MTFB_OK;
+	CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_upload, 0));
+	c->b.img = c->pre_image[c->pre_pending];
+	c->pre_current = c->pre_pending; c->pre_pending = -1;
 	c->have_image = true;
 	return MTFB_OK;
+}
+// after a launch that sampled b.img: the copy stream must not overwrite that buffer before the launch has finished
+static mtfb_status mark_frame_read(mtfb_ctx *c){
+	if(c->pre_current >= 0) CUDA_TRY(cudaEventRecord(c->ev_read[c->pre_current], c->stream));
+	return MTFB_OK;
+}
+static mtfb_status prefetch_begin(mtfb_ctx *c, size_t need_img, size_t need_raw, int *slot_out){
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	if(!c->copy_stream){
+		CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&c->ev_read[0], cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&c->ev_read[1], cudaEventDisableTiming));
+	}
+	if(c->pre_pending >= 0) return fail(MTFB_ERR_LOGIC, "mtfb_set_image_async: the previous prefetched frame has not been consumed by "
+		"initialize() / update() yet (one frame may be in flight)");
+	const int slot = c->pre_next;
+	if(need_img > c->pre_img_capacity[slot] || need_raw > c->pre_raw_capacity[slot]){
+		CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+		if(need_img > c->pre_img_capacity[slot]){
+			cudaFree(c->d_pre_img[slot]); c->d_pre_img[slot] = nullptr; c->pre_img_capacity[slot] = 0;
+			CUDA_TRY(cudaMalloc(&c->d_pre_img[slot], need_img*sizeof(float)));
+			c->pre_img_capacity[slot] = need_img;
+		}
+		if(need_raw > c->pre_raw_capacity[slot]){
+			cudaFree(c->d_pre_raw[slot]); c->d_pre_raw[slot] = nullptr; c->pre_raw_capacity[slot] = 0;
+			CUDA_TRY(cudaMalloc(&c->d_pre_raw[slot], need_raw));
+			c->pre_raw_capacity[slot] = need_raw;
+		}
+	}
+	// the buffer of this slot was last sampled by the launch that recorded ev_read[slot] (two frames ago)
+	CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_read[slot], 0));
+	*slot_out = slot;
+	return MTFB_OK;
+}
+static mtfb_status prefetch_end(mtfb_ctx *c, int slot, int h, int w, int pitch){
+	CUDA_TRY(cudaEventRecord(c->ev_upload, c->copy_stream));
+	c->pre_image[slot] = make_image(c->d_pre_img[slot], h, w, pitch);
+	c->pre_pending = slot; c->pre_next = slot ^ 1;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_set_image_async(mtfb_ctx *c, const float *host_img, int h, int w, int row_stride){
+	if(!c || !host_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_async: null argument");
+	if(h < 2 || w < 2 || row_stride < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_async: bad geometry %d x %d stride %d", h, w, row_stride);
+	const int pitch = (w + 31) & ~31;
+	int slot;
+	mtfb_status st = prefetch_begin(c, (size_t)pitch*h, 0, &slot);
+	if(st != MTFB_OK) return st;
+	CUDA_TRY(cudaMemcpy2DAsync(c->d_pre_img[slot], (size_t)pitch*sizeof(float), host_img, (size_t)row_stride*sizeof(float),
+		(size_t)w*sizeof(float), h, cudaMemcpyHostToDevice, c->copy_stream));
+	return prefetch_end(c, slot, h, w, pitch);
+}
+
+mtfb_status mtfb_set_image_u8_async(mtfb_ctx *c, const unsigned char *host_img, int h, int w, int row_stride, int channels,
+	int kernel_size, double sigma){
+	if(!c || !host_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8_async: null argument");
+	if(channels != 1 && channels != 3) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8_async: channels must be 1 (gray) or 3 (BGR)");
+	if(h < 3 || w < 3 || row_stride < w*channels) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8_async: bad geometry %d x %d x %d stride %d", h, w, channels, row_stride);
+	if(kernel_size != 5) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_set_image_u8_async: gauss_kernel_size %d (only the default 5 is implemented)", kernel_size);
+	if(!(sigma > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_u8_async: sigma must be > 0");
+	const int pitch = (w + 31) & ~31;
+	const size_t raw_pitch = ((size_t)w*channels + 127) & ~(size_t)127;
+	int slot;
+	mtfb_status st = prefetch_begin(c, (size_t)pitch*h, raw_pitch*h, &slot);
+	if(st != MTFB_OK) return st;
+	CUDA_TRY(cudaMemcpy2DAsync(c->d_pre_raw[slot], raw_pitch, host_img, (size_t)row_stride, (size_t)w*channels, h, cudaMemcpyHostToDevice, c->copy_stream));
+	float k5[5];
+	gauss_kernel5(sigma, k5);
+	CUDA_TRY(launch_preproc_gauss5(c->d_pre_raw[slot], (int)raw_pitch, channels, c->d_pre_img[slot], pitch, h, w, k5, c->copy_stream));
+	++c->launches;
+	return prefetch_end(c, slot, h, w, pitch);
 }
 
 mtfb_status mtfb_get_image(mtfb_ctx *c, float *out){
 	if(!c || !out) return fail(MTFB_ERR_INVALID_ARG, "mtfb_get_image: null argument");
+	{ mtfb_status st = adopt_prefetched(c); if(st != MTFB_OK) return st; }
 	if(!c->have_image) return fail(MTFB_ERR_LOGIC, "mtfb_get_image: setImage has not been called");
 	CUDA_TRY(cudaSetDevice(c->prm.device));
 	CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)c->b.img.w*sizeof(float), c->b.img.data, (size_t)c->b.img.pitch*sizeof(float),
@@ -460,12 +565,13 @@ mtfb_status mtfb_set_image_device(mtfb_ctx *c, const float *dev_img, int h, int 
 	if(!c || !dev_img) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: null argument");
 	if(h < 2 || w < 2 || pitch < w) return fail(MTFB_ERR_INVALID_ARG, "mtfb_set_image_device: bad geometry %d x %d pitch %d", h, w, pitch);
 	c->b.img = make_image(dev_img, h, w, pitch);
-	c->have_image = true;
+	c->have_image = true; c->pre_current = -1;
 	return MTFB_OK;
 }
 
 static mtfb_status upload_corners(mtfb_ctx *c, const double *corners, const char *who){
 	if(!c || !corners) return fail(MTFB_ERR_INVALID_ARG, "%s: null argument", who);
+	{ mtfb_status st0 = adopt_prefetched(c); if(st0 != MTFB_OK) return st0; }
 	if(!c->have_image) return fail(MTFB_ERR_LOGIC, "%s: setImage has not been called", who);
 	for(size_t i = 0; i < 8 * (size_t)c->P; ++i)
 		if(!std::isfinite(corners[i])) return fail(MTFB_ERR_INVALID_ARG, "%s: non-finite corner coordinate in patch %zu", who, i / 8);
@@ -489,6 +595,7 @@ mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 	if(st != MTFB_OK) return st;
 	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->d_mi_tab, c->stream));
 	++c->launches;
+	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
 	c->initialized = true;
 	if(c->pf_configured){
 		// PF::initialize (NT/PF.cc:136-183): initializeParticles, prev_corners = ssm->getCorners()
@@ -514,6 +621,7 @@ mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	if(ssm_only) CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
 	else CUDA_TRY(launch_reinit_ssd(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
+	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
 	if(c->pf_configured){
 		// PF::setRegion (NT/PF.cc:596-600): ssm->setCorners, initializeParticles
 		CUDA_TRY(launch_pf_init_particles(c->prm.ssm, c->pf, c->b, false, c->stream));
@@ -668,16 +776,18 @@ mtfb_status mtfb_pf_get_particles(mtfb_ctx *c, double *states, double *weights, 
 mtfb_status mtfb_update(mtfb_ctx *c){
 	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_update: null context");
 	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_update: initialize has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	{ mtfb_status st0 = adopt_prefetched(c); if(st0 != MTFB_OK) return st0; }
 	if(c->prm.sm == MTFB_SM_PF){
 		if(!c->pf_configured) return fail(MTFB_ERR_LOGIC, "mtfb_update: a PF context needs mtfb_pf_configure (before mtfb_initialize) to "
 			"track; without it it only evaluates particles (mtfb_pf_evaluate)");
-		return pf_update(c);
+		mtfb_status st = pf_update(c);
+		return st != MTFB_OK ? st : mark_frame_read(c);
 	}
-	CUDA_TRY(cudaSetDevice(c->prm.device));
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
 	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads));
 	++c->launches;
-	return MTFB_OK;
+	return mark_frame_read(c);
 }
 
 static mtfb_status ensure_scratch(mtfb_ctx *c, size_t bytes){

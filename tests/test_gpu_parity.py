@@ -581,3 +581,45 @@ def test_set_region_rebuilds_template_jacobian(seq384, sm, hess, ssm, precision)
         else:
             assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= 1e-4
             assert np.abs(got[i] - o.corners()).max() <= 3e-2          # epsilon = 1e-4 stopping rule, fp32 arithmetic
+
+
+def test_prefetched_frames_equal_synchronous_uploads(seq384):
+    """mtfb_set_image_async (copy stream, two device buffers, event hand-over) tracks exactly what mtfb_set_image tracks; float
+    and raw uint8 frames; one frame may be in flight"""
+    import torch
+    from mtf_b200 import api
+    frames = seq384[0]
+    cs = common.patches(6, 49.0, 384, 384, seed=5)
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    raw = [torch.from_numpy(np.clip(np.rint(f), 0, 255).astype(np.uint8)).pin_memory() for f in frames]
+    for use_raw in (False, True):
+        a = api.BatchTracker(api.make_params("ssd", "homography", "fclk", n_patches=len(cs)))
+        b = api.BatchTracker(api.make_params("ssd", "homography", "fclk", n_patches=len(cs)))
+        if use_raw:
+            a.setRawImage(raw[0].numpy()); a.initialize(cs)
+            b.prefetch_raw_image_pinned(raw[0].data_ptr(), 384, 384, 384, 1); b.initialize(cs)
+        else:
+            a.initialize(cs, frames[0])
+            b.prefetch_image_pinned(pinned[0].data_ptr(), 384, 384, 384); b.initialize(cs)
+        assert np.array_equal(a.getRegion(), b.getRegion())
+        if use_raw:
+            b.prefetch_raw_image_pinned(raw[1].data_ptr(), 384, 384, 384, 1)
+        else:
+            b.prefetch_image_pinned(pinned[1].data_ptr(), 384, 384, 384)
+        for t in (1, 2, 3):
+            if use_raw:
+                a.setRawImage(raw[t].numpy())
+            else:
+                a.setImage(frames[t])
+            a.update()
+            b.update()                                   # samples frame t, handed over before
+            if t < 3:                                    # frame t + 1 uploads while update(t) runs
+                if use_raw:
+                    b.prefetch_raw_image_pinned(raw[t + 1].data_ptr(), 384, 384, 384, 1)
+                else:
+                    b.prefetch_image_pinned(pinned[t + 1].data_ptr(), 384, 384, 384)
+            assert np.array_equal(a.getRegion(), b.getRegion()), (use_raw, t)
+        b.prefetch_image_pinned(pinned[0].data_ptr(), 384, 384, 384)
+        with pytest.raises(api.MTFError) as e:
+            b.prefetch_image_pinned(pinned[1].data_ptr(), 384, 384, 384)
+        assert e.value.status == 3
