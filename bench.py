@@ -197,11 +197,13 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
     # zero-copy torch view of the library's P x 8 result array: what the all-gather reads (no host hop)
     d_corners = sharding.device_view(tr.device_results()[0], (P, 8), dev)
 
+    gathered = torch.empty((n_total, 8), dtype=torch.float64, device=dev) if world > 1 else None
+
     def gather():
         # north_star: one all-gather of the per-patch results over NVLink (per frame: LK iterations of different patches
         # never interact)
         if world > 1:
-            sharding.all_gather_rows(d_corners, n_total)
+            sharding.all_gather_rows(d_corners, n_total, out=gathered)
 
     tr.initialize(corners, d_frames[0])
     tr.synchronize()
@@ -269,6 +271,7 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
                 else:
                     upload(i, False)
                     tr.update()
+                gather()
                 host_out.copy_(d_corners, non_blocking=True)
                 stream.synchronize()                 # the caller reads the corners
         if raw:

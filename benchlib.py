@@ -215,6 +215,8 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
 
     def e2e_step(i):
         tr.update()                                                                  # frame i, prefetched during step i - 1
+        if env.world > 1:
+            sh.getRegion(device=env.dev)
         host_out.copy_(d_corners, non_blocking=True)
         tr.initialize(cells)
         tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), h, w, w)     # overlaps the kernels above
@@ -300,6 +302,8 @@ def run_config4(env, root, n_steps, n_warm, n_patches=8192, cpu=True):
     def e2e_step(i):
         tr.update()
         tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), size, size, size)
+        if env.world > 1:
+            sh.getRegion(device=env.dev)
         host_out.copy_(d_corners, non_blocking=True)
         env.stream.synchronize()
     tr.initialize(corners_all[lo:hi], frames[0])
@@ -367,7 +371,7 @@ def run_config5(env, root, n_steps, n_warm, n_objects=64, n_particles=10000, pre
 
     def post(i):
         if env.world > 1:
-            sharding.all_gather_rows(d_corners, n_objects)
+            sharding.all_gather_rows(d_corners, n_objects, out=gathered)
     ms, kms, win = timed_steps(env, n_warm, n_steps, (pre, post), kernel)
     launches = tr.launch_count - launches0
     final = tr.getRegion()
@@ -375,6 +379,8 @@ def run_config5(env, root, n_steps, n_warm, n_objects=64, n_particles=10000, pre
     def e2e_step(i):
         tr.update()
         tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), h, w, w)
+        if env.world > 1:
+            sharding.all_gather_rows(d_corners, n_objects, out=gathered)
         host_out.copy_(d_corners, non_blocking=True)
         env.stream.synchronize()
     tr.initialize(objs_all[lo:hi], frames[0])

@@ -63,35 +63,37 @@ template<int CNT, class V> __device__ __forceinline__ void warp_reduce_scatter(V
 	}
 }
 
-// 1 / sqrt(s) and 1 / d for the solve of the F32 precision (factor_fast<true>): fp32 MUFU seed on the exponent-reduced
-// argument, two Newton steps in fp64 (relative error ~2e-16, not correctly rounded).  The inputs of that solve carry fp32
-// rounding from the pixel sums, so the last bit is noise there; the F64 kernels keep sqrt() / __drcp_rn().
+// 1 / sqrt(s) and 1 / d for the solve of the F32 precision (factor_lean): the fp64 MUFU seeds (rsqrt.approx.f64 / rcp.approx.f64,
+// SASS MUFU.RSQ64H / MUFU.RCP64H: about 22 bits from the upper word, any exponent) and two Newton steps in fp64 (relative error
+// ~2e-16, not correctly rounded).  The inputs of that solve carry fp32 rounding from the pixel sums, so the last bit is noise
+// there; the F64 kernels keep sqrt() / __drcp_rn().
+__device__ __forceinline__ double rsqrt_seed(double s){
+	double r;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+	return r;
+}
+__device__ __forceinline__ double rcp_seed(double d){
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+	return r;
+}
 __device__ __forceinline__ double rsqrt_newton(double s){
 	const int hi = __double2hiint(s);
 	if(!((unsigned)(hi - 0x00100000) < 0x7fe00000u)) return 1.0 / sqrt(s);            // zero, subnormal, negative, inf, nan
-	const int e2 = ((hi >> 20) - 1023) & ~1;                                           // even exponent
-	const double m = __hiloint2double(hi - (e2 << 20), __double2loint(s));             // in [1, 4)
-	float r0;
-	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)m));
-	double r = (double)r0;
-	double mr = m * r;
-	r = fma(0.5 * r, fma(-mr, r, 1.0), r);
-	mr = m * r;
-	r = fma(0.5 * r, fma(-mr, r, 1.0), r);
-	return __hiloint2double(__double2hiint(r) - ((e2 >> 1) << 20), __double2loint(r));
+	double r = rsqrt_seed(s);
+	double sr = s * r;
+	r = fma(0.5 * r, fma(-sr, r, 1.0), r);
+	sr = s * r;
+	r = fma(0.5 * r, fma(-sr, r, 1.0), r);
+	return r;
 }
 __device__ __forceinline__ double rcp_newton_scaled(double d){
-	const int hi = __double2hiint(d);
-	const int ef = (hi >> 20) & 0x7ff;
+	const int ef = (__double2hiint(d) >> 20) & 0x7ff;
 	if(!(ef > 64 && ef < 1983)) return __drcp_rn(d);                                   // keeps the result's exponent normal too
-	const int ex = ef - 1023;
-	const double m = __hiloint2double(hi - (ex << 20), __double2loint(d));             // |m| in [1, 2), sign kept
-	float r0;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)m));
-	double r = (double)r0;
-	r = fma(fma(-m, r, 1.0), r, r);
-	r = fma(fma(-m, r, 1.0), r, r);
-	return __hiloint2double(__double2hiint(r) - (ex << 20), __double2loint(r));
+	double r = rcp_seed(d);
+	r = fma(fma(-d, r, 1.0), r, r);
+	r = fma(fma(-d, r, 1.0), r, r);
+	return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,12 +402,27 @@ template<int ROWS, int COLS> struct WarpColPivQR {
 			beta = c0; g = 0; wk = 0;                                                        // tau = 0: the identity
 		} else{
 			const double nrm2 = fma(c0, c0, tail_sq);
-			const double rs = rsqrt_newton(nrm2);
-			double nrm = nrm2 * rs;
-			nrm = fma(0.5 * rs, fma(-nrm, nrm, nrm2), nrm);
+			const int hi2 = __double2hiint(nrm2);
+			double rs, nrm;
+			if((unsigned)(hi2 - 0x08000000) < 0x70000000u){           // 2^-895 < |a_k|^2 < 2^897: the seeds and q below stay normal
+				// the reciprocal's seed is taken from the reciprocal square root's seed, so its MUFU overlaps the Newton steps
+				const double r0 = rsqrt_seed(nrm2);
+				double g0 = rcp_seed(fma(fabs(c0), nrm2 * r0, nrm2));
+				double sr = nrm2 * r0;
+				rs = fma(0.5 * r0, fma(-sr, r0, 1.0), r0);
+				sr = nrm2 * rs;
+				rs = fma(0.5 * rs, fma(-sr, rs, 1.0), rs);
+				nrm = nrm2 * rs;
+				const double q = fma(fabs(c0), nrm, nrm2);
+				g0 = fma(fma(-q, g0, 1.0), g0, g0);
+				g = fma(fma(-q, g0, 1.0), g0, g0);
+			} else{
+				rs = rsqrt_newton(nrm2);
+				nrm = nrm2 * rs;
+				g = rcp_newton_scaled(fma(fabs(c0), nrm, nrm2));
+			}
 			beta = c0 >= 0 ? -nrm : nrm;
 			wk = c0 - beta;
-			g = rcp_newton_scaled(fma(fabs(c0), nrm, nrm2));
 			if(lane == piv_lane) rdiag = c0 >= 0 ? -rs : rs;
 		}
 		if(lane == piv_lane){

@@ -19,18 +19,19 @@ def shard_sizes(n_items, world_size):
     return [shard_range(n_items, world_size, r)[1] - shard_range(n_items, world_size, r)[0] for r in range(world_size)]
 
 
-def all_gather_rows(local, n_total, group=None):
+def all_gather_rows(local, n_total, group=None, out=None):
     """all-gather a (n_local, ...) tensor whose row counts follow shard_range into a (n_total, ...) tensor.
 
-    Uses all_gather_into_tensor when the shards are equal (one NCCL call on the caller's stream), padded
-    all_gather otherwise."""
+    Uses all_gather_into_tensor when the shards are equal (one NCCL call on the caller's stream; `out`, if given, receives
+    the result: a per-frame caller keeps one buffer), padded all_gather otherwise."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     sizes = shard_sizes(n_total, world)
     tail = tuple(local.shape[1:])
     if len(set(sizes)) == 1:
-        out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
+        if out is None:
+            out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
         return out
     m = max(sizes)
@@ -65,6 +66,7 @@ class ShardedBatchTracker:
         self.lo, self.hi = shard_range(n_total, self.world, self.rank)
         self.local = make_local(self.hi - self.lo)
         self._d_corners = None
+        self._gathered = None
 
     def initialize(self, corners, img):
         c = np.asarray(corners, dtype=np.float64).reshape(self.n_total, 2, 4)
@@ -89,6 +91,9 @@ class ShardedBatchTracker:
         import torch
         if device is not None and hasattr(self.local, "device_results"):
             loc = self.local_corners_device(device)
+            if self._gathered is None:
+                self._gathered = torch.empty((self.n_total, 8), dtype=torch.float64, device=device)
+            return all_gather_rows(loc, self.n_total, self.group, out=self._gathered).reshape(self.n_total, 2, 4)
         else:
             loc = torch.as_tensor(np.ascontiguousarray(self.local.getRegion()).reshape(-1, 8))
             if device is not None:
