@@ -142,16 +142,41 @@ def truth_error(final, corners, frame_index):
     return {"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())}
 
 
-def oracle_params():
+def oracle_params(fast_sums=1):
     from oracle import oracle_lib as O
-    return O.make_params("ssd", "homography", "fclk", max_iters=ITERS, epsilon=0.0, grad_mode=0, fast_sums=1)
+    return O.make_params("ssd", "homography", "fclk", max_iters=ITERS, epsilon=0.0, grad_mode=0, fast_sums=fast_sums)
 
 
-def cpu_sample(frames, corners, n_patches, n_frames, threads):
-    """oracle batch driver (OpenMP over patches, GridTracker.cc:253-256) -> (iterations, seconds)"""
+def cpu_sample(frames, corners, n_patches, n_frames, threads, fast_sums=1):
+    """oracle batch driver (OpenMP over patches, GridTracker.cc:253-256) -> (iterations, seconds).
+    fast_sums 1: vectorised dot products for J^T J (all S^2 entries, as Eigen's general product computes them);
+    2: a cache-blocked SYRK on the upper triangle (less work than Eigen does: an upper bound on the reference's speed)"""
     from oracle import oracle_lib as O
-    total, secs, _, _ = O.batch_track(oracle_params(), frames[:n_frames + 1], corners[:n_patches], n_threads=threads)
+    total, secs, _, _ = O.batch_track(oracle_params(fast_sums), frames[:n_frames + 1], corners[:n_patches], n_threads=threads)
     return total, secs
+
+
+STAGES = ["updatePixVals", "updateSimilarity", "update*Grad", "updatePixGrad", "cmpt*PixJacobian", "cmpt*Jacobian", "cmpt*Hessian",
+          "solve", "compositionalUpdate"]          # record_event labels of NT/FCLK.cc:190-321 / NT/ESM.cc:190-290
+
+
+def cpu_config1(frames, corners):
+    """BASELINE.json configs[0]: ESM + SSD + Homography, ONE 50 x 50 patch, 30 iterations per frame at most (epsilon 1e-4),
+    one thread -- the reference's own CPU-runnable case -- with the per-stage wall clock of the oracle's update()"""
+    from oracle import oracle_lib as O
+    prm = O.make_params("ssd", "homography", "esm", max_iters=ITERS, epsilon=1e-4, grad_mode=0, fast_sums=1, hess_type=2, jac_type=1)
+    t = O.OracleTracker(prm)
+    t.set_image(frames[0]); t.initialize(corners[0])
+    iters, secs, stages = 0, 0.0, np.zeros(9)
+    for rep in range(3):
+        for f in frames[1:]:
+            t.set_image(f)
+            t0 = time.perf_counter(); t.update(); secs += time.perf_counter() - t0
+            iters += t.n_iters; stages += np.asarray(t.stage_times())
+        t.set_image(frames[0]); t.set_region(corners[0])
+    return {"workload": "ESM+SSD+Homography, 1 patch 50x50, <= 30 iters/frame (epsilon=1e-4), 1 thread", "value": iters / secs,
+            "unit": "iters/s", "iterations": int(iters), "us_per_iteration": 1e6 * secs / iters,
+            "stage_us_per_iteration": {k: 1e6 * float(v) / iters for k, v in zip(STAGES, stages)}}
 
 
 def run_reference(args):
@@ -162,23 +187,48 @@ def run_reference(args):
     frames, corners, _ = workload()
     # bounded sample: 2 patches per core x 1 frame x 30 iterations per step
     n_patches = min(P_PER_GPU, 2 * cores)
-    for _ in range(args.warmup):
-        cpu_sample(frames, corners, n_patches, 1, cores)
-    iters = secs = 0.0
-    for _ in range(args.steps):
-        a, b = cpu_sample(frames, corners, n_patches, 1, cores)
-        iters += a; secs += b
-    v = iters / secs
+    best = None
+    by_kernel = {}
+    for fs, name in ((1, "dot_products_full_SxS"), (2, "blocked_syrk_upper_triangle")):
+        for _ in range(args.warmup):
+            cpu_sample(frames, corners, n_patches, 1, cores, fs)
+        iters = secs = 0.0
+        for _ in range(args.steps):
+            a, b = cpu_sample(frames, corners, n_patches, 1, cores, fs)
+            iters += a; secs += b
+        by_kernel[name] = iters / secs
+        if best is None or iters / secs > best[0]:
+            best = (iters / secs, secs, name)
+    v, secs, kernel = best
     sample = "%d patches x 1 frame x %d iterations per step, %d steps" % (n_patches, ITERS, args.steps)
-    print(json.dumps({
+    if args.reference_brief:
+        print(json.dumps({"value": v, "by_hessian_kernel": by_kernel}))
+        return
+    out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "FCLK+SSD+Homography 50x50, %d iters/frame, CPU oracle (restatement of MTF, not MTF)" % ITERS,
                    "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
+        # value = the faster of the two J^T J kernels (Eigen's own GEMM lies between them: it is vectorised like the first and
+        # computes all S^2 entries like the first; the second skips the lower triangle)
+        "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample, "hessian_kernel": kernel,
+                         "by_hessian_kernel": by_kernel, "flags": "-O3 -march=native -ffp-contract=off -fopenmp"},
         "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}
+    try:
+        out["config1_single_thread"] = cpu_config1(frames, corners)
+    except Exception as e:
+        out["config1_single_thread"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        # the same sample with the oracle built like the reference's makefile builds MTF (plain -O3, no -march=native)
+        env = dict(os.environ, MTF_ORACLE_GENERIC="1")
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--reference-brief", "--steps", str(args.steps),
+                            "--warmup", str(args.warmup)], env=env, capture_output=True, text=True, timeout=600)
+        out["generic_build_O3"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        out["generic_build_O3"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    print(json.dumps(out))
 
 
 def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_frames, pinned, raw_pinned):
@@ -409,11 +459,16 @@ def config2_line(args, env, sampler, strong):
         cores = os.cpu_count() or 1
         n_patches = min(P, 4 * cores)
         it, secs = cpu_sample(frames, corners, n_patches, 1, cores)
+        reps = 1
         if secs < 5.0:                      # aim for ~10 s of wall clock
-            reps = int(min(8, max(1, 10.0 / max(secs, 1e-3))))
+            reps = int(min(8, max(1, 5.0 / max(secs, 1e-3))))
             it, secs = cpu_sample(frames, corners, n_patches, min(reps, N_FRAMES - 1), cores)
-        out["cpu_baseline"] = {"value": it / secs, "unit": "iters/s", "cores": cores, "kind": "port",
-                               "sample": "%d patches, %d LK iterations, OpenMP over patches" % (n_patches, it)}
+        it2, secs2 = cpu_sample(frames, corners, n_patches, min(reps, N_FRAMES - 1), cores, fast_sums=2)
+        by_kernel = {"dot_products_full_SxS": it / secs, "blocked_syrk_upper_triangle": it2 / secs2}
+        out["cpu_baseline"] = {"value": max(by_kernel.values()), "unit": "iters/s", "cores": cores, "kind": "port",
+                               "sample": "%d patches, %d LK iterations, OpenMP over patches" % (n_patches, it),
+                               # the oracle's J^T J two ways; Eigen's vectorised general product lies between them
+                               "by_hessian_kernel": by_kernel}
     return out
 
 
@@ -471,6 +526,7 @@ def main():
                     help="configs 2 / 3 at N > 1: patches per GPU fixed (weak) or 1024 patches in total split over the ranks "
                          "(strong); configs 4 and 5 are fixed-size batches, always strong")
     ap.add_argument("--res", type=int, default=0, help="config 3: cell resolution (25 = modules.cfg, 10 = parameters.h default)")
+    ap.add_argument("--reference-brief", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-others", action="store_true", help="config 2: do not append the other configurations' lines")
     ap.add_argument("--pitch-pad", type=int, default=0, help="experiment: extra floats per device frame row")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -627,7 +627,7 @@ static inline double bSpl3Hess(double x){
 
 struct AM{
 	int type, resx, resy, n_pix, patch_size;
-	double grad_eps, pix_norm_mult, pix_norm_add, likelihood_alpha; int grad_mode; bool fast_sums;
+	double grad_eps, pix_norm_mult, pix_norm_add, likelihood_alpha; int grad_mode; bool fast_sums; bool blocked_syrk;
 	const float *img; unsigned int img_height, img_width;
 	vec I0, It, dI0_dx, dIt_dx, df_dI0, df_dIt;
 	double f;
@@ -647,7 +647,7 @@ struct AM{
 
 	AM(const orc_params &p) : type(p.am), resx(p.resx), resy(p.resy), n_pix(p.resx*p.resy),
 		patch_size(p.resx*p.resy), grad_eps(p.grad_eps), pix_norm_mult(1), pix_norm_add(0),
-		likelihood_alpha(p.likelihood_alpha), grad_mode(p.grad_mode), fast_sums(p.fast_sums != 0), img(nullptr), img_height(0), img_width(0), f(0),
+		likelihood_alpha(p.likelihood_alpha), grad_mode(p.grad_mode), fast_sums(p.fast_sums != 0), blocked_syrk(p.fast_sums == 2), img(nullptr), img_height(0), img_width(0), f(0),
 		init_pix_vals(false), init_pix_grad(false), init_sim(false), init_grad(false), init_hess(false),
 		n_bins(p.mi_n_bins), pre_seed(p.mi_pre_seed), pou(p.mi_pou != 0){
 		if(type == ORC_AM_MI){                                                 // MI::MI AM/src/MI.cc:55-123
@@ -833,6 +833,30 @@ struct AM{
 	}
 	// ------------------------------------------------------------------ Hessians (column-major SxS out)
 	void neg_JtJ(double *H, const double *J, int N, int S) const{
+		if(blocked_syrk){
+			// fast_sums = 2 (timing only): a cache-blocked SYRK on the upper triangle -- 256-pixel blocks of the S columns stay in
+			// L1 while their S (S + 1) / 2 vectorised dot products are taken.  Does LESS work than Eigen's general product
+			// `dI_dp.transpose() * dI_dp` (SSDBase.cc:262-280 computes all S^2 entries): an upper bound on what the reference's
+			// Hessian stage can reach on this CPU
+			double acc[8][8];
+			for(int i = 0; i < S; ++i) for(int j = 0; j < S; ++j) acc[i][j] = 0;
+			const int B = 256;
+			for(int n0 = 0; n0 < N; n0 += B){
+				const int nb = N - n0 < B ? N - n0 : B;
+				for(int i = 0; i < S; ++i){
+					const double *a = J + (size_t)i*N + n0;
+					for(int j = i; j < S; ++j){
+						const double *b = J + (size_t)j*N + n0;
+						double sum = 0;
+						#pragma omp simd reduction(+:sum)
+						for(int n = 0; n < nb; ++n) sum += a[n] * b[n];
+						acc[i][j] += sum;
+					}
+				}
+			}
+			for(int i = 0; i < S; ++i) for(int j = i; j < S; ++j){ H[(size_t)j*S + i] = -acc[i][j]; H[(size_t)i*S + j] = -acc[i][j]; }
+			return;
+		}
 		for(int i = 0; i < S; ++i) for(int j = 0; j < S; ++j)
 			H[(size_t)j*S + i] = -dot(J + (size_t)i*N, J + (size_t)j*N, N, fast_sums);
 	}

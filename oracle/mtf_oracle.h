@@ -56,7 +56,9 @@ typedef struct orc_params {
 	int grad_mode;           /* 0: reference finite difference (imgUtils.cc:233-254); 1: its eps -> 0 limit,
 	                            evaluated analytically (not a reference mode; see mtf_oracle.cpp) */
 	int fast_sums;           /* 1: vectorised dot products in the Jacobian / Hessian products (CPU-baseline timing: Eigen's
-	                            product kernels are vectorised too); 0: sequential sums (parity tests) */
+	                            product kernels are vectorised too); 2: additionally the Hessian J^T J as a cache-blocked SYRK on
+	                            the upper triangle (less work than Eigen's full product: an upper bound on the reference's
+	                            speed); 0: sequential sums (parity tests) */
 } orc_params;
 
 typedef struct orc_tracker orc_tracker;

@@ -6,7 +6,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_DIR = _HERE
-_LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "libmtf_oracle.so")
+# MTF_ORACLE_GENERIC=1: the build without -march=native (CPU-baseline row of bench.py --impl reference)
+_LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "libmtf_oracle_generic.so" if os.environ.get("MTF_ORACLE_GENERIC") == "1"
+                         else "libmtf_oracle.so")
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
 SSM = {"homography": 0, "affine": 1}
