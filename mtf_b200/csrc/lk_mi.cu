@@ -14,6 +14,7 @@
 // Jacobian row, S or 2S sums).  Implemented Hessian: InitialSelf (the ICLK default, ICLKParams.cc:6).
 // The per-pass histograms are accumulated in per-lane private copies and folded in a fixed order: deterministic.
 // (Only initialize() uses shared-memory atomics, for the B^2 x S joint-histogram Jacobian of the self Hessian.)
+#include <cstdlib>
 #include "lk_solve.cuh"
 
 namespace mtfb {
@@ -60,7 +61,7 @@ __device__ __forceinline__ BinWeights bin_weights(double v, int B){
 	return o;
 }
 
-struct MiParams { int B; double pre_seed, hist_pre_seed, hist_norm_mult; };
+struct MiParams { int B; double pre_seed, hist_pre_seed, hist_norm_mult; int copies; };
 
 // per-template table kept in global memory (P x MI_TAB doubles): [0..B) init_hist, [16..16+B) init_hist_log
 constexpr int MI_TAB = 32;
@@ -212,9 +213,12 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 	const int HB = B + B*B;                                                 // curr_hist | joint_hist entries
 	double *s_It = s_dyn;                                                   // N current pixel values (bin units), if KEEP_IT
 	const int it_slots = KEEP_IT ? ((N + 1) & ~1) : 0;
-	// one PRIVATE copy of both histograms per lane, [entry][lane]: a lane only ever touches its own column, so the
-	// 20 updates per pixel are plain read-modify-writes (bank = lane: conflict-free, no atomics, fixed summation order)
-	double *s_priv = s_dyn + it_slots + (size_t)warp*HB * 32;
+	// PRIVATE copies of both histograms, [entry][copy]: C = mp.copies = 32 (one per lane) or 16 (lanes l and l + 16 share
+	// copy l and take turns).  A lane only ever touches its copy's column, so the 20 updates per pixel are plain
+	// read-modify-writes (conflict-free banks, no atomics, fixed summation order).  16 copies halve the 18 KB per warp that
+	// cap the residency at 8 warps per SM (profiles/r02_ncu_mi_summary.txt: 12 % warps active, long-scoreboard bound)
+	const int C = mp.copies, cl = lane & (C - 1), n_turns = 32 / C, my_turn = lane / C;
+	double *s_priv = s_dyn + it_slots + (size_t)warp*HB * C;
 	__shared__ double s_part[(T / 32) * NA];
 	__shared__ double s_sum[NA];
 	__shared__ double s_hist[MI_BMAX], s_hist_log[MI_BMAX], s_ihist_log[MI_BMAX], s_joint[MI_BMAX*MI_BMAX];
@@ -246,28 +250,45 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 #pragma unroll
 		for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
 		double abcd[4] = { (W.m[0] - 1) + 1, W.m[1], W.m[3], (W.m[4] - 1) + 1 };
-		for(int e = 0; e < HB; ++e) s_priv[e * 32 + lane] = 0;
+		if(lane < C) for(int e = 0; e < HB; ++e) s_priv[e * C + lane] = 0;
+		__syncwarp();
 		// ---- sweep 1: updatePixVals (MI.cc:166-192) + the histograms of updateSimilarity (MI.cc:346-370)
-		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
-			const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
-			if(KEEP_IT) s_It[it.pix] = It;
-			const BinWeights bc = bin_weights(It, B), bi = bin_weights(I0[it.pix], B);
+		// (the trip count is uniform over the warp so that the lanes sharing a copy can take turns; lanes past the end add nothing)
+		// (the template value of the NEXT trip is requested before this trip's arithmetic: the stream comes from DRAM, and with
+		// ~13 warps per SM nothing else hides its latency)
+		double i0_next = tid < N ? __ldcs(I0 + tid) : 0.0;
+		for(PixIter it(tid, T, b.resx); it.pix - lane < N; it.next(T)){
+			const bool live = it.pix < N;
+			const double i0 = i0_next;
+			if(it.pix + T < N) i0_next = __ldcs(I0 + it.pix + T);
+			BinWeights bc, bi;
+			bc.lo = 0; bc.hi = -1; bi.lo = 0; bi.hi = -1;
+			if(live){
+				PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+				const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
+				if(KEEP_IT) s_It[it.pix] = It;
+				bc = bin_weights(It, B); bi = bin_weights(i0, B);
+			}
+			for(int turn = 0; turn < n_turns; ++turn){
+				if(live && turn == my_turn){
 #pragma unroll
-			for(int k = 0; k < 4; ++k){
-				if(bc.lo + k > bc.hi) continue;
-				s_priv[(bc.lo + k) * 32 + lane] += bc.w[k];
+					for(int k = 0; k < 4; ++k){
+						if(bc.lo + k > bc.hi) continue;
+						s_priv[(bc.lo + k) * C + cl] += bc.w[k];
 #pragma unroll
-				for(int l = 0; l < 4; ++l){
-					if(bi.lo + l > bi.hi) continue;
-					s_priv[(B + (bi.lo + l)*B + (bc.lo + k)) * 32 + lane] += bc.w[k] * bi.w[l];    // JH(curr_id, init_id)
+						for(int l = 0; l < 4; ++l){
+							if(bi.lo + l > bi.hi) continue;
+							s_priv[(B + (bi.lo + l)*B + (bc.lo + k)) * C + cl] += bc.w[k] * bi.w[l];    // JH(curr_id, init_id)
+						}
+					}
 				}
+				if(n_turns > 1) __syncwarp();
 			}
 		}
 		__syncwarp();
-		// fold the 32 private columns (shuffle tree), then the warps, in a fixed order
+		// fold the private columns (shuffle tree), then the warps, in a fixed order
 		for(int e = 0; e < HB; ++e){
-			double v = s_priv[e * 32 + lane];
+			double v = lane < C ? s_priv[e * C + lane] : 0.0;
 #pragma unroll
 			for(int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL_MASK, v, off);
 			if(lane == 0) s_fold[warp*MI_HBMAX + e] = v;
@@ -303,10 +324,17 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		double acc[NA];
 #pragma unroll
 		for(int i = 0; i < NA; ++i) acc[i] = 0;
+		double p_i0 = tid < N ? __ldcs(I0 + tid) : 0.0, p_gx = 0, p_gy = 0;
+		if(INIT && tid < N){ p_gx = __ldcs(G0 + tid); p_gy = __ldcs(G0 + N + tid); }
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+			const double c_i0 = p_i0, c_gx = p_gx, c_gy = p_gy;
+			if(it.pix + T < N){
+				p_i0 = __ldcs(I0 + it.pix + T);
+				if(INIT){ p_gx = __ldcs(G0 + it.pix + T); p_gy = __ldcs(G0 + N + it.pix + T); }
+			}
 			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			const double It2 = KEEP_IT ? s_It[it.pix] : (b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add);
-			const BinWeights bc = bin_weights(It2, B), bi = bin_weights(I0[it.pix], B);
+			const BinWeights bc = bin_weights(It2, B), bi = bin_weights(c_i0, B);
 			double df_t = 0, df_0 = 0;
 			if(CURR){
 #pragma unroll
@@ -333,7 +361,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 				}
 			}
 			double D[S], D0[S];
-			if(INIT) init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D0);
+			if(INIT) init_pix_jacobian<SSM>(g.ix, g.iy, c_gx, c_gy, D0);
 			if(CURR){
 				Sample smp;
 				pixel_value_and_gradient<SSM, false>(b, W, g, smp);
@@ -495,6 +523,7 @@ static MiParams make_mi_params(const DevBatch &b, int n_bins, double pre_seed){
 	mp.B = n_bins; mp.pre_seed = pre_seed;
 	mp.hist_pre_seed = n_bins * pre_seed;                                          // MI.cc:101
 	mp.hist_norm_mult = 1.0 / (static_cast<double>(b.N) + mp.hist_pre_seed * n_bins);   // MI.cc:104
+	mp.copies = 32;
 	return mp;
 }
 
@@ -521,11 +550,18 @@ cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double
 #endif
 
 template<int SSM, int SM, int T, bool KEEP_IT, int HMODE> static cudaError_t launch_self(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
-	const size_t smem = ((KEEP_IT ? (size_t)((b.N + 1) & ~1) : 0) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * 32) * sizeof(double);
+	// private histogram copies per warp: 16 when the batch alone can fill the SMs' warp slots (then shared memory, not the
+	// batch size, caps the residency), else one per lane
+	MiParams mq = mp;
+	mq.copies = ((size_t)b.P * (T / 32) >= 148 * 12) ? 16 : 32;
+	if(const char *ev = std::getenv("MTFB_MI_COPIES")) mq.copies = (std::atoi(ev) == 16) ? 16 : 32;
+	const size_t smem = ((KEEP_IT ? (size_t)((b.N + 1) & ~1) : 0) + (size_t)(T / 32) * (mp.B + mp.B*mp.B) * mq.copies) * sizeof(double);
 	if(smem > 180 * 1024) return cudaErrorInvalidValue;
 	cudaError_t e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT, HMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
-	mi_update_kernel<SSM, SM, T, KEEP_IT, HMODE><<<b.P, T, smem, st>>>(b, mp, mi_tab);
+	e = cudaFuncSetAttribute(mi_update_kernel<SSM, SM, T, KEEP_IT, HMODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+	if(e != cudaSuccess) return e;
+	mi_update_kernel<SSM, SM, T, KEEP_IT, HMODE><<<b.P, T, smem, st>>>(b, mq, mi_tab);
 	return cudaGetLastError();
 }
 template<int SSM, int SM, int T, bool KEEP_IT> static cudaError_t launch_keep(const DevBatch &b, const MiParams &mp, const double *mi_tab, cudaStream_t st){
