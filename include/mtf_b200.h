@@ -45,12 +45,13 @@ typedef enum mtfb_status {
 /* AM/AM.cmake:5 names; SSM/SSM.cmake:1 names; SM/SM.cmake names */
 enum { MTFB_AM_SSD = 0, MTFB_AM_NCC = 1, MTFB_AM_MI = 2 };
 enum { MTFB_SSM_HOMOGRAPHY = 0, MTFB_SSM_AFFINE = 1 };
-enum { MTFB_SM_ESM = 0, MTFB_SM_FCLK = 1, MTFB_SM_ICLK = 2, MTFB_SM_PF = 3 };
+enum { MTFB_SM_ESM = 0, MTFB_SM_FCLK = 1, MTFB_SM_ICLK = 2, MTFB_SM_PF = 3,
+       MTFB_SM_FALK = 4, MTFB_SM_IALK = 5 };   /* the additive searches nt::FALK / nt::IALK (SM/src/NT/FALK.cc, IALK.cc): SSD, F64 */
 /* ESMParams::HessType / JacType (SM/include/mtf/SM/ESMParams.h:13-17) */
 enum { MTFB_ESM_HESS_INITIAL_SELF = 0, MTFB_ESM_HESS_CURRENT_SELF = 1, MTFB_ESM_HESS_SUM_OF_SELF = 2,
        MTFB_ESM_HESS_ORIGINAL = 3, MTFB_ESM_HESS_SUM_OF_STD = 4, MTFB_ESM_HESS_STD = 5 };
 enum { MTFB_ESM_JAC_ORIGINAL = 0, MTFB_ESM_JAC_DIFF_OF_JACS = 1 };
-/* FCLKParams::HessType / ICLKParams::HessType (FCLKParams.h:8, ICLKParams.h:9) */
+/* FCLKParams::HessType / ICLKParams::HessType / FALKParams / IALKParams::HessType (FCLKParams.h:8, ICLKParams.h:9) */
 enum { MTFB_LK_HESS_INITIAL_SELF = 0, MTFB_LK_HESS_CURRENT_SELF = 1, MTFB_LK_HESS_STD = 2 };
 /* arithmetic of the per-pixel part of the update kernel (mtfb_params::precision).
  *   F64: every operation in fp64, in the reference's order: warped points, sampling indices, pixel values bit-identical

@@ -52,6 +52,8 @@ inline mtfb_params makeParams(const char *sm, const char *am, const char *ssm, i
 	if(!strcmp(sm, "esm")){ p.sm = MTFB_SM_ESM; p.hess_type = MTFB_ESM_HESS_SUM_OF_SELF; }
 	else if(!strcmp(sm, "fclk") || !strcmp(sm, "fc")){ p.sm = MTFB_SM_FCLK; p.hess_type = MTFB_LK_HESS_CURRENT_SELF; }
 	else if(!strcmp(sm, "iclk") || !strcmp(sm, "ic")){ p.sm = MTFB_SM_ICLK; p.hess_type = MTFB_LK_HESS_INITIAL_SELF; }
+	else if(!strcmp(sm, "falk") || !strcmp(sm, "fa")){ p.sm = MTFB_SM_FALK; p.hess_type = MTFB_LK_HESS_INITIAL_SELF; }
+	else if(!strcmp(sm, "ialk") || !strcmp(sm, "ia")){ p.sm = MTFB_SM_IALK; p.hess_type = MTFB_LK_HESS_INITIAL_SELF; }
 	else if(!strcmp(sm, "pf")){ p.sm = MTFB_SM_PF; }
 	else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: unknown search method ") + sm); }
 	if(!strcmp(am, "ssd")){ p.am = MTFB_AM_SSD; }

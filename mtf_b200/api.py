@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MTFB_LIB") or os.path.join(_HERE, "libmtf_b200.so")  
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
 SSM = {"homography": 0, "affine": 1, "8": 0, "6": 1}
-SM = {"esm": 0, "fclk": 1, "iclk": 2, "pf": 3}
+SM = {"esm": 0, "fclk": 1, "iclk": 2, "pf": 3, "falk": 4, "ialk": 5}
 ESM_HESS = {"initial_self": 0, "current_self": 1, "sum_of_self": 2, "original": 3, "sum_of_std": 4, "std": 5}
 ESM_JAC = {"original": 0, "diff_of_jacs": 1}
 LK_HESS = {"initial_self": 0, "current_self": 1, "std": 2}
@@ -173,10 +173,11 @@ def set_params(p, **kw):
 
 def make_params(am="ssd", ssm="homography", sm="fclk", **kw):
     """Parameters of one (SM, AM, SSM) combination with the per-SM default Hessian of the reference
-    (ESMParams.cc:7 SumOfSelf, FCLKParams.cc:6 CurrentSelf, ICLKParams.cc:6 InitialSelf)."""
+    (ESMParams.cc:7 SumOfSelf, FCLKParams.cc:6 CurrentSelf, ICLKParams.cc:6 InitialSelf, FALKParams.cc:5 / IALKParams.cc:6
+    InitialSelf)."""
     p = default_params(am=am, ssm=ssm, sm=sm)
     if "hess_type" not in kw:
-        p.hess_type = {"esm": 2, "fclk": 1, "iclk": 0, "pf": 0}[sm if isinstance(sm, str) else
+        p.hess_type = {"esm": 2, "fclk": 1, "iclk": 0, "pf": 0, "falk": 0, "ialk": 0}[sm if isinstance(sm, str) else
                                                                   {v: k for k, v in SM.items()}[sm]]
     return set_params(p, **kw)
 

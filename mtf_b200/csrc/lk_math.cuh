@@ -24,7 +24,7 @@ namespace mtfb {
 
 enum { AM_SSD = 0, AM_NCC = 1, AM_MI = 2 };
 enum { SSM_HOM = 0, SSM_AFF = 1 };
-enum { SM_ESM = 0, SM_FCLK = 1, SM_ICLK = 2, SM_PF = 3 };
+enum { SM_ESM = 0, SM_FCLK = 1, SM_ICLK = 2, SM_PF = 3, SM_FALK = 4, SM_IALK = 5 };
 
 struct Image {
 	const float *data;   // pitched, row-major
@@ -372,6 +372,48 @@ template<int SSM> MTFB_HD void init_pix_jacobian(double x, double y, double Ix, 
 		J[7] = -x*Ixy - y*Iyy;
 	} else{
 		J[0] = Ix; J[1] = Iy; J[2] = Ixx; J[3] = Ixy; J[4] = Iyx; J[5] = Iyy;
+	}
+}
+
+// ssm.cmptPixJacobian (the forward ADDITIVE search, nt::FALK): Homography.cc:193-229; Affine.h:35-37 = cmptInitPixJacobian.
+// gx, gy = dI/dx at the warped point.
+template<int SSM> MTFB_HD void additive_pix_jacobian(const PixGeom &g, double gx, double gy, double *J){
+	const double x = g.ix, y = g.iy;
+	if(SSM == SSM_HOM){
+		const double inv_d = g.rD;                                  // 1.0 / curr_pts_hm(2, pt_id)
+		const double Ix = gx * inv_d, Iy = gy * inv_d;
+		const double Ixx = Ix*x, Iyy = Iy*y, Ixy = Ix*y, Iyx = Iy*x;
+		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
+		J[6] = (-g.wx*Ixx - g.wy*Iyx);
+		J[7] = (-g.wx*Ixy - g.wy*Iyy);
+	} else{
+		const double Ixx = gx*x, Ixy = gx*y, Iyy = gy*y, Iyx = gy*x;
+		J[0] = gx; J[1] = gy; J[2] = Ixx; J[3] = Ixy; J[4] = Iyx; J[5] = Iyy;
+	}
+}
+// ssm.cmptApproxPixJacobian (the inverse ADDITIVE search, nt::IALK): Homography.cc:296-358, Affine.cc:183-211.
+// g0x, g0y = the TEMPLATE's gradient (am.getInitPixGrad()); aff_abcd as for warped_pix_jacobian.
+template<int SSM, class MW> MTFB_HD void approx_pix_jacobian(const MW &W, const double *aff_abcd, const PixGeom &g,
+	double g0x, double g0y, double *J){
+	const double x = g.ix, y = g.iy;
+	if(SSM == SSM_HOM){
+		const double a = (W[0] - W[6] * g.wx), b = (W[1] - W[7] * g.wx);
+		const double c = (W[3] - W[6] * g.wy), d = (W[4] - W[7] * g.wy);
+		const double inv_factor = ieee_rcp(a*d - b*c);
+		const double Ix = (d*g0x - c*g0y)*inv_factor;
+		const double Iy = (a*g0y - b*g0x)*inv_factor;
+		const double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
+		J[6] = (-g.wx*Ixx - g.wy*Iyx);
+		J[7] = (-g.wx*Ixy - g.wy*Iyy);
+	} else{
+		const double a = aff_abcd[0], b = aff_abcd[1], c = aff_abcd[2], d = aff_abcd[3];
+		const double inv_det = ieee_rcp(a*d - b*c);
+		const double Ix = g0x, Iy = g0y;
+		const double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+		J[0] = (Ix*d - Iy*c) * inv_det; J[1] = (Iy*a - Ix*b) * inv_det;
+		J[2] = (Ixx*d - Iyx*c) * inv_det; J[3] = (Ixy*d - Iyy*c) * inv_det;
+		J[4] = (Iyx*a - Ixx*b) * inv_det; J[5] = (Iyy*a - Ixy*b) * inv_det;
 	}
 }
 

@@ -21,7 +21,7 @@ template<int SM> __device__ __forceinline__ int hessian_select(int hess_type){
 		return (hess_type == MTFB_ESM_HESS_INITIAL_SELF) ? 1 :
 			(hess_type == MTFB_ESM_HESS_SUM_OF_SELF || hess_type == MTFB_ESM_HESS_SUM_OF_STD) ? 2 : 0;
 	}
-	if(SM == SM_FCLK) return (hess_type == MTFB_LK_HESS_INITIAL_SELF) ? 1 : 0;
+	if(SM == SM_FCLK || SM == SM_FALK || SM == SM_IALK) return (hess_type == MTFB_LK_HESS_INITIAL_SELF) ? 1 : 0;
 	return (hess_type == MTFB_LK_HESS_CURRENT_SELF) ? 0 : 1;
 }
 
@@ -34,8 +34,11 @@ template<int SM> __device__ __forceinline__ int hessian_select(int hess_type){
 template<int SSM, int SM, bool PRESOLVED = false, int HSEL = -1>
 __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, int iter_id, int n_passes, double f,
 	const double *s_J, const double *s_Hc, double *s_W, double *s_corners, const double *s_init_corners,
-	LMState &lm, int &patch_status, const double *s_dp = nullptr){
+	LMState &lm, int &patch_status, const double *s_dp = nullptr, double *s_state = nullptr){
 	constexpr int S = StateSize<SSM>::value;
+	// the additive searches (nt::FALK / nt::IALK) keep the STATE and add to it (ssm->additiveUpdate, ProjectiveBase.cc:51-55:
+	// curr_state += update; setState(curr_state)); the compositional ones keep the warp
+	constexpr bool ADDITIVE = (SM == SM_FALK || SM == SM_IALK);
 #if MTFB_PROF
 	const long long pt0 = clock64();
 #endif
@@ -53,7 +56,16 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 				lm.lm_delta *= b.lm_delta_update;
 #pragma unroll
 				for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, lm.ssm_update, s);
-				if(SM == SM_ICLK){
+				if(ADDITIVE){
+					// ssm->additiveUpdate(-ssm_update) (NT/FALK.cc:150-152, NT/IALK.cc:110-112)
+					double ns[S];
+#pragma unroll
+					for(int s = 0; s < S; ++s) ns[s] = s_state[s] + (-dp[s]);
+					Wn = warp_from_state<SSM>(ns);
+					__syncwarp();
+#pragma unroll
+					for(int s = 0; s < S; ++s) if(lane == s) s_state[s] = ns[s];
+				} else if(SM == SM_ICLK){
 					// undo the inverse step by re-applying the forward update (NT/ICLK.cc:183)
 					Wn = compose_update<SSM>(W, dp);
 				} else{
@@ -121,7 +133,15 @@ __device__ __forceinline__ int serial_step(const DevBatch &b, int p, int lane, i
 		lm.ssm_update = x;
 #pragma unroll
 		for(int s = 0; s < S; ++s) dp[s] = __shfl_sync(FULL_MASK, x, s);
-		if(SM == SM_ICLK){
+		if(ADDITIVE){
+			double ns[S];
+#pragma unroll
+			for(int s = 0; s < S; ++s) ns[s] = s_state[s] + dp[s];
+			Wn = warp_from_state<SSM>(ns);
+			__syncwarp();
+#pragma unroll
+			for(int s = 0; s < S; ++s) if(lane == s) s_state[s] = ns[s];
+		} else if(SM == SM_ICLK){
 			double inv[S];
 			invert_state<SSM>(inv, dp);                          // NT/ICLK.cc:270-271
 			Wn = compose_update<SSM>(W, inv);
@@ -163,13 +183,17 @@ template<int SM> __device__ __forceinline__ bool counts_as_iteration(int ctrl, i
 
 // final state of the patch -> global memory (warp 0)
 template<int SSM> __device__ __forceinline__ void store_patch_state(const DevBatch &b, int p, int lane, const double *s_W,
-	const double *s_corners, double f, int n_passes, int patch_status){
+	const double *s_corners, double f, int n_passes, int patch_status, const double *s_state = nullptr){
 	constexpr int S = StateSize<SSM>::value;
 	Mat3 W;
 #pragma unroll
 	for(int i = 0; i < 9; ++i) W.m[i] = s_W[i];
 	double st[S];
 	state_from_warp<SSM>(st, W);
+	if(s_state){                                  // additive searches: the state itself is what was tracked
+#pragma unroll
+		for(int s = 0; s < S; ++s) st[s] = s_state[s];
+	}
 	if(lane < 9) b.warp[(size_t)p * 9 + lane] = W.m[lane];
 	if(lane < 8) b.corners[(size_t)p * 8 + lane] = s_corners[lane];
 #pragma unroll

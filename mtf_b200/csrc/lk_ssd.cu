@@ -155,8 +155,11 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 	__shared__ double s_J[S], s_Hc[S*S];
 	__shared__ int s_ctrl;
 	__shared__ double s_dlt[9];
+	constexpr bool ADDITIVE = (SM == SM_FALK || SM == SM_IALK);
+	__shared__ double s_state[ADDITIVE ? S : 1];
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
+	if(ADDITIVE && tid < S) s_state[tid] = b.state[(size_t)p*S + tid];
 	cta_sync<T>();
 	Mat3 dlt;
 #pragma unroll
@@ -164,7 +167,11 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 	const double *I0 = b.I0 + (size_t)p*b.N, *G0 = b.G0 + (size_t)p * 2 * b.N;
 	const bool esm_mean = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL || b.hess_type == MTFB_ESM_HESS_ORIGINAL);
 	const bool jac_half = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);     // NT/ESM.cc:308-309
+	// need_grad: the pass needs a pixel Jacobian of the CURRENT patch (the gradient of the current image, or for IALK the
+	// template's gradient pushed through cmptApproxPixJacobian); with_hess: it also rebuilds the Hessian from it
 	const bool need_grad = (SM != SM_ICLK) || (b.hess_type == MTFB_LK_HESS_CURRENT_SELF);
+	const bool with_hess = ADDITIVE ? (b.hess_type != MTFB_LK_HESS_INITIAL_SELF) : need_grad;
+	const bool sample_grad = need_grad && (SM != SM_IALK);
 	LMState lm = { 0.0, b.lm_delta_init, 0.0, false };          // uniform; only warp 0's copy is used
 	int iter_id = 0, n_passes = 0, patch_status = 0;
 	double f = 0;
@@ -174,6 +181,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 		if(SSM == SSM_AFF){
 			// Affine.cc:217-220 reads curr_state(2)+1, (3), (4), (5)+1 with curr_state = getStateFromWarp(curr_warp)
 			abcd[0] = (s_W[0] - 1) + 1; abcd[1] = s_W[1]; abcd[2] = s_W[3]; abcd[3] = (s_W[4] - 1) + 1;
+			if(ADDITIVE){ abcd[0] = s_state[2] + 1; abcd[1] = s_state[3]; abcd[2] = s_state[4]; abcd[3] = s_state[5] + 1; }
 		}
 		double acc[L::NA];
 #pragma unroll
@@ -186,11 +194,11 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 			const double i0 = __ldcg(I0 + it.pix);
 			const PixGeom g = pixel_geometry<SSM>(dlt, Wm, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 			Sample smp;
-			if(need_grad){ pixel_value_and_gradient<SSM, true>(b, Wm, g, smp); }
+			if(sample_grad){ pixel_value_and_gradient<SSM, true>(b, Wm, g, smp); }
 			else{ smp.val = sample_pixel(b.img, g.wx, g.wy); smp.gx = smp.gy = 0; smp.lit = 0; }
 			PixTerms<S> t;
 			pixel_terms<SSM, SM>(b, Wm, abcd, g, smp, i0, G0, it.pix, need_grad, esm_mean, t);
-			accumulate_terms<S>(acc, t, need_grad);
+			accumulate_terms<S>(acc, t, with_hess);
 		}
 		MTFB_PROF_T(1)
 		block_reduce<L::NA, T>(acc, s_part, s_sum);
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 		if(warp == 0){
 			f = -s_sum[0] / 2;
 			const int ctrl = serial_step<SSM, SM>(b, p, lane, iter_id, n_passes, f, s_J, s_Hc, s_W, s_corners, s_init_corners,
-				lm, patch_status);
+				lm, patch_status, nullptr, ADDITIVE ? s_state : nullptr);
 			if(lane == 0) s_ctrl = ctrl;
 		}
 		cta_sync<T>();
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 		if(ctrl == CTRL_BREAK) break;
 		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
 	}
-	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
+	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status, ADDITIVE ? s_state : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,10 +337,14 @@ cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBa
 	if(ssm == SSM_HOM){
 		if(sm == SM_ESM) return launch_update_t<SSM_HOM, SM_ESM>(threads, occ, b, st);
 		if(sm == SM_FCLK) return launch_update_t<SSM_HOM, SM_FCLK>(threads, occ, b, st);
+		if(sm == SM_FALK) return launch_update_o<SSM_HOM, SM_FALK, 0>(threads, b, st);
+		if(sm == SM_IALK) return launch_update_o<SSM_HOM, SM_IALK, 0>(threads, b, st);
 		return launch_update_t<SSM_HOM, SM_ICLK>(threads, occ, b, st);
 	}
 	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, occ, b, st);
 	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, occ, b, st);
+	if(sm == SM_FALK) return launch_update_o<SSM_AFF, SM_FALK, 0>(threads, b, st);
+	if(sm == SM_IALK) return launch_update_o<SSM_AFF, SM_IALK, 0>(threads, b, st);
 	return launch_update_t<SSM_AFF, SM_ICLK>(threads, occ, b, st);
 #endif
 }

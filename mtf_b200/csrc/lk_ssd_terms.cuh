@@ -13,6 +13,16 @@ template<int SSM, int SM, class MW> __device__ __forceinline__ void pixel_terms(
 	PixTerms<StateSize<SSM>::value> &t){
 	constexpr int S = StateSize<SSM>::value;
 	t.r = smp.val - i0;                                            // I_diff (SSDBase.cc:78)
+	if(SM == SM_FALK || SM == SM_IALK){
+		// the additive searches (NT/FALK.cc:170-181, NT/IALK.cc:131-138): am.cmptCurrJacobian(curr_pix_jacobian) with
+		// df_dIt = -I_diff; curr_pix_jacobian = ssm.cmptPixJacobian(curr grad) / ssm.cmptApproxPixJacobian(init grad, un-chained)
+		t.wj = -t.r;
+		if(SM == SM_FALK) additive_pix_jacobian<SSM>(g, smp.gx, smp.gy, t.Jt);
+		else approx_pix_jacobian<SSM>(W, abcd, g, __ldcg(b.G0raw + (size_t)(G0 - b.G0) + pix), __ldcg(b.G0raw + (size_t)(G0 - b.G0) + b.N + pix), t.Jt);
+#pragma unroll
+		for(int s = 0; s < S; ++s) t.Jj[s] = t.Jt[s];
+		return;
+	}
 	if(SM == SM_ICLK){
 		// df_dI0 = I_diff (SSDBase.cc:34: I_diff aliases df_dI0); Jacobian of the template
 		t.wj = t.r;

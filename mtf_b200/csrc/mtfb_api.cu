@@ -45,12 +45,19 @@ bool combo_supported(const mtfb_params *p, const char **why){
 	*why = "";
 	const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
 	if(!(p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE)){ *why = "ssm must be homography or affine"; return false; }
+	if(p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK){
+		// the additive searches: ssm.cmptPixJacobian / cmptApproxPixJacobian + ssm.additiveUpdate on the SSD skeleton
+		if(p->am != MTFB_AM_SSD){ *why = "FALK / IALK are implemented for SSD"; return false; }
+		if(p->precision != MTFB_PRECISION_F64){ *why = "FALK / IALK are implemented in the F64 precision"; return false; }
+		if(p->hess_type < MTFB_LK_HESS_INITIAL_SELF || p->hess_type > MTFB_LK_HESS_STD){ *why = "unknown Hessian type"; return false; }
+		return true;
+	}
 	if(p->sm == MTFB_SM_PF){
 		if(p->am == MTFB_AM_MI && (p->mi_n_bins < 4 || p->mi_n_bins > 16)){ *why = "MI: 4 <= mi_n_bins <= 16"; return false; }
 		if(p->am == MTFB_AM_MI && p->mi_pou && p->mi_n_bins < 6){ *why = "MI: partition of unity needs mi_n_bins >= 6"; return false; }
 		return p->am == MTFB_AM_SSD || p->am == MTFB_AM_NCC || p->am == MTFB_AM_MI;
 	}
-	if(!gn){ *why = "sm must be esm, fclk, iclk or pf"; return false; }
+	if(!gn){ *why = "sm must be esm, fclk, iclk, falk, ialk or pf"; return false; }
 	if(p->am == MTFB_AM_SSD) return true;
 	if(p->am == MTFB_AM_NCC){
 		// the self Hessians (NCC.cc:337-389) and the Std forms cmptCurrHessian / cmptInitHessian (NCC.cc:282-336) are
@@ -291,7 +298,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		if(cudaMemcpy(c->d_grid, grid.data(), grid.size()*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		// per-patch arrays
 		// SSD with ESM / FCLK keeps the un-chained template gradient for setRegion (NT/ESM.cc:150-168, NT/FCLK.cc:360-376)
-		const bool keep_raw_grad = p->am == MTFB_AM_SSD && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK);
+		// ... and IALK pushes it through cmptApproxPixJacobian on every pass (NT/IALK.cc:131)
+		const bool keep_raw_grad = p->am == MTFB_AM_SSD && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_IALK);
 		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + (keep_raw_grad ? 2 * (size_t)N : 0);
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
@@ -356,6 +364,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.leven_marq = p->leven_marq; b.nt_semantics = p->nt_semantics;
 		// the templated search methods have no chained_warp switch: always chained (ESM.cc:94-95, FCLK.cc:82-86, ICLK.cc:80-90)
 		b.chained = (p->chained_warp || !p->nt_semantics) ? 1 : 0;
+		// FALK / IALK have no such switch: am->updatePixGrad(ssm->getPts()) (NT/FALK.cc:166, NT/IALK.cc:64)
+		if(p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK) b.chained = 1;
 		b.norm_init = p->hom_normalized_init ? 1 : 0;
 		b.f32_local_solve = (p->f32_solve == MTFB_F32_SOLVE_LOCAL) ? 1 : 0;
 		b.epsilon = p->epsilon; b.lm_delta_init = p->lm_delta_init; b.lm_delta_update = p->lm_delta_update;
@@ -610,7 +620,7 @@ mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	if(c && !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_set_region: initialize has not been called");
 	bool ssm_only = true;
 	if(c){
-		ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) ||
+		ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) || (c->prm.sm == MTFB_SM_FALK) || (c->prm.sm == MTFB_SM_IALK) ||
 			(c->prm.sm == MTFB_SM_FCLK && c->prm.hess_type != MTFB_LK_HESS_INITIAL_SELF);
 		// ESM and FCLK-InitialSelf also rebuild the template Jacobian and init_self_hessian at the new points: SSD
 		if(!ssm_only && !c->b.G0raw) return fail(MTFB_ERR_NOT_SUPPORTED,

@@ -565,6 +565,61 @@ struct SSM{
 			}
 		}
 	}
+	// ProjectiveBase::additiveUpdate ProjectiveBase.cc:51-55 ; Affine::additiveUpdate (same: curr_state += update; setState)
+	void additiveUpdate(const double *state_update){
+		vec ns(state_size);
+		for(int i = 0; i < state_size; ++i) ns[i] = curr_state[i] + state_update[i];
+		setState(ns.data());
+	}
+	// Homography::cmptPixJacobian Homography.cc:193-229 ; Affine::cmptPixJacobian = cmptInitPixJacobian (Affine.h:35-37)
+	void cmptPixJacobian(double *dI_dp, const double *dI_dw) const{
+		if(type != ORC_SSM_HOMOGRAPHY){ cmptInitPixJacobian(dI_dp, dI_dw); return; }
+		const int N = n_pts;
+		for(int i = 0; i < N; ++i){
+			double x = init_pts[2 * i], y = init_pts[2 * i + 1];
+			double curr_x = curr_pts[2 * i], curr_y = curr_pts[2 * i + 1];
+			double inv_d = 1.0 / curr_pts_hm[3 * i + 2];
+			double Ix = dI_dw[i] * inv_d, Iy = dI_dw[N + i] * inv_d;
+			double Ixx = Ix*x, Iyy = Iy*y, Ixy = Ix*y, Iyx = Iy*x;
+			dI_dp[0 * N + i] = Ixx; dI_dp[1 * N + i] = Ixy; dI_dp[2 * N + i] = Ix;
+			dI_dp[3 * N + i] = Iyx; dI_dp[4 * N + i] = Iyy; dI_dp[5 * N + i] = Iy;
+			dI_dp[6 * N + i] = (-curr_x*Ixx - curr_y*Iyx);
+			dI_dp[7 * N + i] = (-curr_x*Ixy - curr_y*Iyy);
+		}
+	}
+	// Homography::cmptApproxPixJacobian Homography.cc:296-358 ; Affine::cmptApproxPixJacobian Affine.cc:183-211
+	void cmptApproxPixJacobian(double *dI_dp, const double *dI_dw) const{
+		const int N = n_pts;
+		if(type == ORC_SSM_HOMOGRAPHY){
+			Mat3 W = curr_warp;
+			double h00_plus_1 = W(0, 0), h01 = W(0, 1), h10 = W(1, 0), h11_plus_1 = W(1, 1), h20 = W(2, 0), h21 = W(2, 1);
+			for(int i = 0; i < N; ++i){
+				double curr_x = curr_pts[2 * i], curr_y = curr_pts[2 * i + 1];
+				double a = (h00_plus_1 - h20*curr_x), b = (h01 - h21*curr_x);
+				double c = (h10 - h20*curr_y), d = (h11_plus_1 - h21*curr_y);
+				double inv_factor = 1.0 / (a*d - b*c);
+				double x = init_pts[2 * i], y = init_pts[2 * i + 1];
+				double Ix = (d*dI_dw[i] - c*dI_dw[N + i])*inv_factor;
+				double Iy = (a*dI_dw[N + i] - b*dI_dw[i])*inv_factor;
+				double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+				dI_dp[0 * N + i] = Ixx; dI_dp[1 * N + i] = Ixy; dI_dp[2 * N + i] = Ix;
+				dI_dp[3 * N + i] = Iyx; dI_dp[4 * N + i] = Iyy; dI_dp[5 * N + i] = Iy;
+				dI_dp[6 * N + i] = (-curr_x*Ixx - curr_y*Iyx);
+				dI_dp[7 * N + i] = (-curr_x*Ixy - curr_y*Iyy);
+			}
+		} else{
+			double a = curr_state[2] + 1, b = curr_state[3], c = curr_state[4], d = curr_state[5] + 1;
+			double inv_det = 1.0 / (a*d - b*c);
+			for(int i = 0; i < N; ++i){
+				double x = init_pts[2 * i], y = init_pts[2 * i + 1];
+				double Ix = dI_dw[i], Iy = dI_dw[N + i];
+				double Ixx = Ix*x, Ixy = Ix*y, Iyy = Iy*y, Iyx = Iy*x;
+				dI_dp[0 * N + i] = (Ix*d - Iy*c) * inv_det; dI_dp[1 * N + i] = (Iy*a - Ix*b) * inv_det;
+				dI_dp[2 * N + i] = (Ixx*d - Iyx*c) * inv_det; dI_dp[3 * N + i] = (Ixy*d - Iyy*c) * inv_det;
+				dI_dp[4 * N + i] = (Iyx*a - Ixx*b) * inv_det; dI_dp[5 * N + i] = (Iyy*a - Ixy*b) * inv_det;
+			}
+		}
+	}
 	// Homography::cmptWarpedPixJacobian Homography.cc:231-294 ; Affine::cmptWarpedPixJacobian Affine.cc:213-242
 	void cmptWarpedPixJacobian(double *dI_dp, const double *dI_dw) const{
 		const int N = n_pts;
@@ -1282,6 +1337,16 @@ struct orc_tracker{
 				if(params.leven_marq){ init_self_hessian = hessian; }
 			}
 			break;
+		case ORC_SM_FALK:                                                      // NT/FALK.cc:93-130
+		case ORC_SM_IALK:                                                      // NT/IALK.cc:56-86
+			am.initializePixGrad(ssm.curr_pts.data());
+			am.initializeSimilarity(); am.initializeGrad(); am.initializeHess();
+			if(params.hess_type == ORC_LK_HESS_INITIAL_SELF){
+				ssm.cmptPixJacobian(init_pix_jacobian.data(), am.dI0_dx.data());
+				am.cmptSelfHessian(hessian.data(), init_pix_jacobian.data(), S);
+				if(params.leven_marq){ init_self_hessian = hessian; }
+			}
+			break;
 		default: return 1;
 		}
 		return 0;
@@ -1329,8 +1394,60 @@ struct orc_tracker{
 		case ORC_SM_FCLK: return update_fclk();
 		case ORC_SM_ESM: return update_esm();
 		case ORC_SM_ICLK: return update_iclk();
+		case ORC_SM_FALK: return update_additive(true);
+		case ORC_SM_IALK: return update_additive(false);
 		}
 		return 1;
+	}
+	// nt::FALK::update NT/FALK.cc:132-258 (forward = true) ; nt::IALK::update NT/IALK.cc:88-215 (forward = false): the additive
+	// searches -- same loop, the pixel Jacobian from the current image's gradient (cmptPixJacobian) or from the template's
+	// (cmptApproxPixJacobian), the state update added to the state (ssm->additiveUpdate)
+	int update_additive(bool forward){
+		double prev_similarity = 0, leven_marq_delta = params.lm_delta_init;
+		bool state_reset = false; n_iters = 0;
+		vec neg(S);
+		for(int iter_id = 0; iter_id < params.max_iters; ++iter_id){
+			++n_iters;
+			am.updatePixVals(ssm.curr_pts.data());
+			am.updateSimilarity(false);
+			if(params.leven_marq && !state_reset){
+				double curr_similarity = am.f;
+				if(iter_id > 0){
+					if(curr_similarity < prev_similarity){
+						leven_marq_delta *= params.lm_delta_update;
+						for(int i = 0; i < S; ++i) neg[i] = -ssm_update[i];
+						ssm.additiveUpdate(neg.data());
+						state_reset = true;
+						record(true, 0);
+						continue;
+					}
+					if(curr_similarity > prev_similarity){ leven_marq_delta /= params.lm_delta_update; }
+				}
+				prev_similarity = curr_similarity;
+			}
+			state_reset = false;
+			if(forward){
+				am.updatePixGrad(ssm.curr_pts.data());
+				ssm.cmptPixJacobian(curr_pix_jacobian.data(), am.dIt_dx.data());
+			} else{
+				ssm.cmptApproxPixJacobian(curr_pix_jacobian.data(), am.dI0_dx.data());
+			}
+			am.updateCurrGrad();
+			am.cmptCurrJacobian(jacobian.data(), curr_pix_jacobian.data(), S);
+			switch(params.hess_type){
+			case ORC_LK_HESS_INITIAL_SELF: if(params.leven_marq){ hessian = init_self_hessian; } break;
+			case ORC_LK_HESS_CURRENT_SELF: am.cmptSelfHessian(hessian.data(), curr_pix_jacobian.data(), S); break;
+			case ORC_LK_HESS_STD: am.cmptCurrHessian(hessian.data(), curr_pix_jacobian.data(), S); break;
+			}
+			if(params.leven_marq){ lm_damp(leven_marq_delta); }
+			solve();
+			std::memcpy(prev_corners, ssm.curr_corners, sizeof(prev_corners));
+			ssm.additiveUpdate(ssm_update.data());
+			double update_norm = cornerDiffSqNorm();
+			record(false, update_norm);
+			if(update_norm < params.epsilon){ break; }
+		}
+		return 0;
 	}
 	// nt::FCLK::update NT/FCLK.cc:171-358 ; FCLK<AM,SSM>::update FCLK.cc:106-224
 	int update_fclk(){

@@ -12,7 +12,7 @@ _LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "libmtf_oracle_generic.so" if os
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
 SSM = {"homography": 0, "affine": 1}
-SM = {"esm": 0, "fclk": 1, "iclk": 2}
+SM = {"esm": 0, "fclk": 1, "iclk": 2, "falk": 4, "ialk": 5}
 
 
 class OrcParams(C.Structure):
@@ -123,8 +123,8 @@ def make_params(am="ssd", ssm="homography", sm="fclk", **kw):
     p.am, p.ssm, p.sm = AM[am], SSM[ssm], SM[sm]
     if sm == "esm" and "hess_type" not in kw:
         p.hess_type = 2  # SumOfSelf (ESMParams.cc:7)
-    if sm == "iclk" and "hess_type" not in kw:
-        p.hess_type = 0  # InitialSelf (ICLKParams.cc:6)
+    if sm in ("iclk", "falk", "ialk") and "hess_type" not in kw:
+        p.hess_type = 0  # InitialSelf (ICLKParams.cc:6, FALKParams.cc:5, IALKParams.cc:6)
     for k, v in kw.items():
         if not hasattr(p, k):
             raise KeyError(k)
