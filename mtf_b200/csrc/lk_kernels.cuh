@@ -62,7 +62,9 @@ cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTap
 cudaError_t launch_update_ssd_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_stage_f32(int ssm, const DevBatch &b, const StageTapsF32 &t, cudaStream_t st);
 // lk_ssd_mom.cu: FCLK in the F32 precision with column-fixed threads (d_work: per thread {column, first row, rows, 0})
-cudaError_t launch_update_ssd_mom(int ssm, int threads, const DevBatch &b, const int4 *d_work, cudaStream_t st);
+// frame_tensor_map: a CUtensorMap of the frame (2-D, fp32, box MOM_WINP x F32_WIN = 64 x 56) for the TMA window copy, or null
+// (window filled by plain loads)
+cudaError_t launch_update_ssd_mom(int ssm, int threads, const DevBatch &b, const int4 *d_work, const void *frame_tensor_map, cudaStream_t st);
 cudaError_t launch_pf_evaluate_f32(int ssm, const DevBatch &b, const double *d_states, int n_particles, double *d_likelihood,
 	double *d_similarity, double alpha, cudaStream_t st);
 // lk_ncc.cu

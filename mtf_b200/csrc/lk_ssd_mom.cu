@@ -27,6 +27,7 @@
 // Homography.cc:68 keeps the DLT's un-normalised third row in init_pts_hm, so the reference's dI/dp is the true one divided
 // by hz = (D ~u)_2 (identically 1 unless the initial region is a general quadrilateral): the gradient is scaled by 1 / hz.
 #include <mutex>
+#include <cuda.h>
 #include "lk_f32.cuh"
 #include "lk_moment_tables.cuh"
 
@@ -39,6 +40,22 @@ namespace mom {
 // per-pass constants in shared memory (floats)
 enum { K_M = 0,            // 9: rows of [M0 - X0 M2; M1 - Y0 M2; M2], M = curr_warp . D
        K_DELTA = 9, K_LOX = 10, K_HIX = 11, K_LOY = 12, K_HIY = 13, K_COUNT = 14 };
+
+// The frame window of this kernel: MOM_WIN_ROWS rows of MOM_WINP floats, loaded by ONE 2-D TMA copy (cp.async.bulk.tensor.2d,
+// SASS UTMALDG) from the frame's tensor map with the box's first column rounded down to a multiple of 4 floats (the copy
+// faults unless the box starts on a 16-byte boundary: profiles/r02_tma2d_run.log), so the window's column 0 sits at offset
+// (ox & 3) of the box and F32_WIN usable columns always fit: 3 + 56 <= 64.  Columns of the box beyond the frame are zero filled
+// and never sampled.
+constexpr int MOM_WINP = 64, MOM_WIN_ROWS = F32_WIN;
+__device__ __forceinline__ bool elect_one(){
+	unsigned pred;
+	asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+	return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar){
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		:: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b){
 	unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
@@ -253,7 +270,7 @@ template<int SSM, bool WIN> __device__ __forceinline__ bool mom_pixel(const Pass
 	const float dx = wxl - fx, dy = wyl - fy;
 	bool fast = (dx >= k.delta) && (dx <= k.hi) && (dy >= k.delta) && (dy <= k.hi);          // written so that NaN fails
 	if(!WIN) fast = fast && (fx >= k.lox) && (fx <= k.hix) && (fy >= k.loy) && (fy <= k.hiy);
-	const int pitch = WIN ? F32_WINP : k.pitch;
+	const int pitch = WIN ? MOM_WINP : k.pitch;
 	const int off = fast ? (WIN ? iy*pitch + ix : (k.Yr + iy)*pitch + (k.Xr + ix)) : 0;
 	const float *r0 = base + off, *r1 = r0 + pitch;
 	const float p00 = r0[0], p01 = r0[1], p10 = r1[0], p11 = r1[1];
@@ -338,7 +355,7 @@ using namespace mom;
 // from resx, resy and T; a thread never leaves its column)
 template<int SSM, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const int4 *__restrict__ work, unsigned tmpl_bytes,
-	unsigned win_elems){
+	unsigned win_elems, unsigned win_off, const __grid_constant__ CUtensorMap frame_map, int use_tma){
 	constexpr int S = StateSize<SSM>::value;
 	constexpr int SM = SM_FCLK;
 	typedef AccLayout<S> L;
@@ -354,10 +371,12 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 	__shared__ float s_cf[K_COUNT];
 	__shared__ int s_ci[2], s_wi[6];
 	__shared__ int s_ctrl;
-	extern __shared__ __align__(16) float s_dyn[];
-	__shared__ __align__(8) unsigned long long s_bar;
+	extern __shared__ __align__(128) float s_dyn[];
+	__shared__ __align__(8) unsigned long long s_bar, s_bar_win;
 	const bool use_smem = tmpl_bytes != 0;
 	if(use_smem && tid == 0) mbar_init(&s_bar, 1);
+	if(tid == 0) mbar_init(&s_bar_win, 1);
+	unsigned win_phase = 0;
 	if(tid < 9){ s_W[tid] = b.warp[(size_t)p * 9 + tid]; s_dlt[tid] = b.dlt[(size_t)p * 9 + tid]; }
 	if(tid < 8){ s_corners[tid] = b.corners[(size_t)p * 8 + tid]; s_init_corners[tid] = b.init_corners[(size_t)p * 8 + tid]; }
 	cta_sync<T>();
@@ -367,7 +386,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 	}
 	// dynamic shared memory: template row | per-row powers of v | frame window
 	float4 *s_vtab = reinterpret_cast<float4*>(s_dyn + (use_smem ? b.I0f_stride : 0));
-	float *s_win = reinterpret_cast<float*>(s_vtab + b.resy);
+	float *s_win = s_dyn + win_off;                          // 128-byte aligned (TMA destination)
 	const double y_lo = __ldg(b.yv), y_hi = __ldg(b.yv + b.resy - 1), x_lo = __ldg(b.xv), x_hi = __ldg(b.xv + b.resx - 1);
 	for(int r = tid; r < b.resy; r += T){
 		const float v = (float)((__ldg(b.yv + r) - 0.5*(y_lo + y_hi)) / (0.5*(y_hi - y_lo)));
@@ -418,13 +437,24 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 		if(use_win){
 			const int ox = s_wi[0], oy = s_wi[1];
 			if(s_wi[3]){
-				for(int i = tid; i < F32_WIN*F32_WIN; i += T){
-					const int r = i / F32_WIN, c = i - r*F32_WIN;
-					s_win[r*F32_WINP + c] = __ldg(b.img.data + (size_t)(oy + r)*b.img.pitch + ox + c);
+				if(use_tma){
+					// one elected lane of warp 0 issues the tile copy; everybody waits on its mbarrier
+					cta_sync<T>();                                   // the previous pass's readers are done with the window
+					if(warp == 0 && elect_one()){
+						mbar_expect_tx(&s_bar_win, MOM_WINP*MOM_WIN_ROWS*(unsigned)sizeof(float));
+						tma_load_2d(s_win, &frame_map, ox & ~3, oy, &s_bar_win);
+					}
+					mbar_wait(&s_bar_win, win_phase);
+					win_phase ^= 1u;
+				} else{
+					for(int i = tid; i < F32_WIN*F32_WIN; i += T){
+						const int r = i / F32_WIN, c = i - r*F32_WIN;
+						s_win[r*MOM_WINP + (ox & 3) + c] = __ldg(b.img.data + (size_t)(oy + r)*b.img.pitch + ox + c);
+					}
+					cta_sync<T>();
 				}
-				cta_sync<T>();
 			}
-			k.Xr = k.X0 - ox; k.Yr = k.Y0 - oy; k.pitch = F32_WINP; k.base = s_win;
+			k.Xr = k.X0 - ox; k.Yr = k.Y0 - oy; k.pitch = MOM_WINP; k.base = s_win + (ox & 3);
 			k.lox = (float)(ox - k.X0); k.hix = (float)(ox + F32_WIN - 2 - k.X0);
 			k.loy = (float)(oy - k.Y0); k.hiy = (float)(oy + F32_WIN - 2 - k.Y0);
 		}
@@ -442,7 +472,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 				// (32-bit addresses, LDS): template row, powers of v, frame window at element (Y0, X0)
 				const float *tp = s_dyn + (row0 + c0)*resx + col;
 				const float4 *vp = reinterpret_cast<const float4*>(s_dyn + b.I0f_stride) + row0 + c0;
-				const float *wb = s_dyn + b.I0f_stride + 4 * b.resy + k.Yr*F32_WINP + k.Xr;
+				const float *wb = s_dyn + win_off + (s_wi[0] & 3) + k.Yr*MOM_WINP + k.Xr;
 				for(int i = 0; i < n; ++i, tp += resx){
 					const bool fast = mom_pixel<SSM, true>(k, wb, vp[i], proj, *tp, acc);
 					slow |= (fast ? 0u : 1u) << i;
@@ -617,16 +647,18 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 // ------------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------------
-template<int SSM, int T, int MINB> static cudaError_t launch_mom_one(const DevBatch &b, const int4 *d_work, cudaStream_t st){
+template<int SSM, int T, int MINB> static cudaError_t launch_mom_one(const DevBatch &b, const int4 *d_work, const CUtensorMap *frame_map,
+	cudaStream_t st){
 	size_t tmpl = (size_t)b.I0f_stride*sizeof(float);
 	if(tmpl*MINB > 96 * 1024) tmpl = 0;                   // large templates are read through L2
 	const size_t vtab = (size_t)b.resy*sizeof(float4);
-	size_t win = (size_t)F32_WIN*F32_WINP*sizeof(float);
+	const size_t win_off = (tmpl + vtab + 127) & ~(size_t)127;               // the TMA destination is 128-byte aligned
+	size_t win = (size_t)MOM_WIN_ROWS*MOM_WINP*sizeof(float);
 	cudaFuncAttributes fa;
 	cudaError_t e = cudaFuncGetAttributes(&fa, ssd_fclk_mom_kernel<SSM, T, MINB>);
 	if(e != cudaSuccess) return e;
-	if((fa.sharedSizeBytes + tmpl + vtab + win + 1024)*MINB > 227 * 1024) win = 0;
-	const size_t dyn = tmpl + vtab + win;
+	if((fa.sharedSizeBytes + win_off + win + 1024)*MINB > 227 * 1024) win = 0;
+	const size_t dyn = win_off + win;
 	// the shared-memory carve-out follows the largest footprint seen so far (attributes are per function and sticky)
 	static size_t configured_dev[64] = {};
 	static std::mutex mu;                                  // contexts of different host threads may share an instantiation
@@ -643,28 +675,31 @@ template<int SSM, int T, int MINB> static cudaError_t launch_mom_one(const DevBa
 		if(e != cudaSuccess) return e;
 		configured = dyn;
 	}
-	ssd_fclk_mom_kernel<SSM, T, MINB><<<b.P, T, dyn, st>>>(b, d_work, (unsigned)tmpl, (unsigned)(win / sizeof(float)));
+	static const CUtensorMap no_map = {};
+	ssd_fclk_mom_kernel<SSM, T, MINB><<<b.P, T, dyn, st>>>(b, d_work, (unsigned)tmpl, (unsigned)(win / sizeof(float)),
+		(unsigned)(win_off / sizeof(float)), frame_map ? *frame_map : no_map, frame_map ? 1 : 0);
 	return cudaGetLastError();
 }
 
 #ifndef MTFB_MOM_MINB128
 #define MTFB_MOM_MINB128 7
 #endif
-cudaError_t launch_update_ssd_mom(int ssm, int threads, const DevBatch &b, const int4 *d_work, cudaStream_t st){
+cudaError_t launch_update_ssd_mom(int ssm, int threads, const DevBatch &b, const int4 *d_work, const void *frame_tensor_map, cudaStream_t st){
+	const CUtensorMap *fm = static_cast<const CUtensorMap*>(frame_tensor_map);
 	if(ssm == SSM_HOM){
 		switch(threads){
-		case 32: return launch_mom_one<SSM_HOM, 32, 16>(b, d_work, st);
-		case 64: return launch_mom_one<SSM_HOM, 64, 8>(b, d_work, st);
-		case 128: return launch_mom_one<SSM_HOM, 128, MTFB_MOM_MINB128>(b, d_work, st);
-		case 256: return launch_mom_one<SSM_HOM, 256, 3>(b, d_work, st);
+		case 32: return launch_mom_one<SSM_HOM, 32, 16>(b, d_work, fm, st);
+		case 64: return launch_mom_one<SSM_HOM, 64, 8>(b, d_work, fm, st);
+		case 128: return launch_mom_one<SSM_HOM, 128, MTFB_MOM_MINB128>(b, d_work, fm, st);
+		case 256: return launch_mom_one<SSM_HOM, 256, 3>(b, d_work, fm, st);
 		default: return cudaErrorInvalidValue;
 		}
 	}
 	switch(threads){
-	case 32: return launch_mom_one<SSM_AFF, 32, 16>(b, d_work, st);
-	case 64: return launch_mom_one<SSM_AFF, 64, 8>(b, d_work, st);
-	case 128: return launch_mom_one<SSM_AFF, 128, MTFB_MOM_MINB128>(b, d_work, st);
-	case 256: return launch_mom_one<SSM_AFF, 256, 3>(b, d_work, st);
+	case 32: return launch_mom_one<SSM_AFF, 32, 16>(b, d_work, fm, st);
+	case 64: return launch_mom_one<SSM_AFF, 64, 8>(b, d_work, fm, st);
+	case 128: return launch_mom_one<SSM_AFF, 128, MTFB_MOM_MINB128>(b, d_work, fm, st);
+	case 256: return launch_mom_one<SSM_AFF, 256, 3>(b, d_work, fm, st);
 	default: return cudaErrorInvalidValue;
 	}
 }

@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <cuda.h>
 #include "lk_kernels.cuh"
 #include "pf_tracker.cuh"
 
@@ -124,8 +125,8 @@ cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, co
 	return launch_init_ssd(p.ssm, threads, b, d_corners, st);
 }
 cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st,
-	const int4 *mom_work = nullptr, int mom_threads = 0){
-	if(p.precision == MTFB_PRECISION_F32 && mom_work) return launch_update_ssd_mom(p.ssm, mom_threads, b, mom_work, st);
+	const int4 *mom_work = nullptr, int mom_threads = 0, const void *frame_map = nullptr){
+	if(p.precision == MTFB_PRECISION_F32 && mom_work) return launch_update_ssd_mom(p.ssm, mom_threads, b, mom_work, frame_map, st);
 	if(p.precision == MTFB_PRECISION_F32) return launch_update_ssd_f32(p.ssm, p.sm, threads, b, st);
 	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
@@ -167,7 +168,37 @@ struct mtfb_ctx {
 	unsigned char *d_pre_raw[2]; size_t pre_raw_capacity[2];
 	Image pre_image[2];
 	int pre_next, pre_pending, pre_current;      // slot of the next upload; slot uploaded but not adopted yet (-1); slot b.img points to (-1)
+	// tensor map of the current frame for the moment kernel's 2-D TMA window copy (re-encoded when the frame buffer changes)
+	alignas(64) CUtensorMap frame_map; const float *frame_map_ptr; int frame_map_h, frame_map_w, frame_map_pitch; bool frame_map_ok;
 };
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+static const void *frame_map_for(mtfb_ctx *c){
+	if(!c->d_mom_work) return nullptr;
+	const Image &im = c->b.img;
+	if(c->frame_map_ptr == im.data && c->frame_map_h == im.h && c->frame_map_w == im.w && c->frame_map_pitch == im.pitch)
+		return c->frame_map_ok ? &c->frame_map : nullptr;
+	c->frame_map_ptr = im.data; c->frame_map_h = im.h; c->frame_map_w = im.w; c->frame_map_pitch = im.pitch; c->frame_map_ok = false;
+	if(std::getenv("MTFB_NO_TMA2D")) return nullptr;
+	// the copy needs a 16-byte aligned base and row stride, and a frame at least as large as the box
+	if(((uintptr_t)im.data & 15) != 0 || (im.pitch & 3) != 0 || im.w < 64 || im.h < 56) return nullptr;
+	typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+		const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static encode_fn encode = nullptr;
+	static bool looked = false;
+	if(!looked){
+		void *ptr = nullptr; cudaDriverEntryPointQueryResult q;
+		if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			encode = reinterpret_cast<encode_fn>(ptr);
+		looked = true;
+	}
+	if(!encode) return nullptr;
+	const cuuint64_t dims[2] = { (cuuint64_t)im.w, (cuuint64_t)im.h }; const cuuint64_t strides[1] = { (cuuint64_t)im.pitch * sizeof(float) };
+	const cuuint32_t box[2] = { 64, 56 }; const cuuint32_t estr[2] = { 1, 1 };
+	const CUresult r = encode(&c->frame_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(im.data), dims, strides, box, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	c->frame_map_ok = (r == CUDA_SUCCESS);
+	return c->frame_map_ok ? &c->frame_map : nullptr;
+}
 static const int4 *mom_work_for(const mtfb_ctx *c){
 	if(!c->d_mom_work) return nullptr;
 	if(c->prm.ssm == MTFB_SSM_AFFINE && !c->all_parallelograms) return nullptr;
@@ -795,7 +826,7 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 		return st != MTFB_OK ? st : mark_frame_read(c);
 	}
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads, frame_map_for(c)));
 	++c->launches;
 	return mark_frame_read(c);
 }
@@ -847,7 +878,7 @@ mtfb_status mtfb_iterate_once(mtfb_ctx *c, double *jacobian, double *hessian, do
 	b.max_iters = 1; b.epsilon = -1;               // one pass, no early exit bookkeeping differences
 	b.log = reinterpret_cast<mtfb_iter_log*>(c->d_scratch); b.log_slots = 1;
 	CUDA_TRY(cudaMemsetAsync(b.log, 0, sizeof(mtfb_iter_log)*(size_t)P, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads));
+	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads, frame_map_for(c)));
 	++c->launches;
 	std::vector<mtfb_iter_log> host(P);
 	st = d2h(c, host.data(), b.log, sizeof(mtfb_iter_log)*(size_t)P);
