@@ -5,7 +5,7 @@
 //   pf_perturb_kernel    the dynamic model: ssm->{additive,compositional}{RandomWalk,AutoRegression1} (ProjectiveBase.cc:255-299,
 //                        Homography.cc:917-942) on a perturbation from ssm->generatePerturbation (ProjectiveBase.cc:301-306 one
 //                        normal deviate per state entry; Homography.cc:899-915 corner based: a common translation and four
-//                        corner offsets pushed through the 4-point DLT, one warp per particle)
+//                        corner offsets pushed through the 4-point homography, in closed form, one thread per particle)
 //   (evaluation)         ssm->setState -> am->updatePixVals -> am->updateSimilarity(false) -> likelihood (NT/PF.cc:303-320)
 //   pf_weights_kernel    measurement likelihood from the similarity (NT/PF.cc:329-339), particle_cum_wts in the reference's
 //                        sequential summation order (bit-identical prefix sums), max_wt_id, the adaptive-resampling test
@@ -142,12 +142,74 @@ template<int SSM> __global__ void __launch_bounds__(128) pf_perturb_kernel(PFDev
 	dynamic_model<SSM>(pf, z, pf.states + pi*S, pf.ar + pi*S);
 }
 
-// Homography with corner_based_sampling (Homography.cc:899-909): one warp per particle.  rand_dist[0] gives the common
-// translation (two deviates), rand_dist[1] the eight corner offsets; the perturbation is the state of the DLT warp from
-// the initial corners to the disturbed ones.
+// The homography that maps four points onto four points, in closed form (both quadruples in general position).  The reference
+// takes it from the null vector of the 8 x 9 DLT matrix (utils::computeHomographyDLT, warpUtils.cc:171-223, JacobiSVD); four
+// correspondences determine the homography exactly, so the two agree up to rounding.  Coordinates are centred and scaled with
+// the IN points' frame first (x' = s (x - cx)), which keeps the 3 x 3 determinants below well conditioned for pixel coordinates;
+// measured against the oracle's DLT on the perturbed corners of the tests: < 1e-12 relative on every entry (tests/test_pf.py).
+//   M(p) = [l1 p1 | l2 p2 | l3 p3],  (l1, l2, l3) = adj([p1 p2 p3]) p4   maps (e1, e2, e3, e1 + e2 + e3) to p1..p4 (up to scale)
+//   H' = M(out) adj(M(in)),   H = S^-1 H' S,   normalised by its last entry
+__device__ __forceinline__ void basis_to_points(const double *x, const double *y, double *M){
+	// adj([p1 p2 p3]) p4 with p_i = (x_i, y_i, 1)
+	const double c00 = y[1] - y[2], c01 = x[2] - x[1], c02 = x[1] * y[2] - x[2] * y[1];
+	const double c10 = y[2] - y[0], c11 = x[0] - x[2], c12 = x[2] * y[0] - x[0] * y[2];
+	const double c20 = y[0] - y[1], c21 = x[1] - x[0], c22 = x[0] * y[1] - x[1] * y[0];
+	const double l0 = c00 * x[3] + c01 * y[3] + c02, l1 = c10 * x[3] + c11 * y[3] + c12, l2 = c20 * x[3] + c21 * y[3] + c22;
+	M[0] = l0 * x[0]; M[1] = l1 * x[1]; M[2] = l2 * x[2];
+	M[3] = l0 * y[0]; M[4] = l1 * y[1]; M[5] = l2 * y[2];
+	M[6] = l0; M[7] = l1; M[8] = l2;
+}
+__device__ __forceinline__ Mat3 homography_4pt(const double *in_c, const double *out_c){
+	// the in points' frame
+	const double cx = 0.25 * (in_c[0] + in_c[1] + in_c[2] + in_c[3]), cy = 0.25 * (in_c[4] + in_c[5] + in_c[6] + in_c[7]);
+	double ext = 0;
+#pragma unroll
+	for(int i = 0; i < 4; ++i){ ext = fmax(ext, fabs(in_c[i] - cx)); ext = fmax(ext, fabs(in_c[4 + i] - cy)); }
+	const double s = ext > 0 ? 1.0 / ext : 1.0;
+	double xi[4], yi[4], xo[4], yo[4];
+#pragma unroll
+	for(int i = 0; i < 4; ++i){
+		xi[i] = s * (in_c[i] - cx); yi[i] = s * (in_c[4 + i] - cy);
+		xo[i] = s * (out_c[i] - cx); yo[i] = s * (out_c[4 + i] - cy);
+	}
+	double Mi[9], Mo[9];
+	basis_to_points(xi, yi, Mi);
+	basis_to_points(xo, yo, Mo);
+	Mat3 A, B, adj;
+#pragma unroll
+	for(int i = 0; i < 9; ++i){ A.m[i] = Mi[i]; B.m[i] = Mo[i]; }
+	// adjugate of Mi (transposed cofactors)
+	adj.m[0] = A.m[4] * A.m[8] - A.m[5] * A.m[7]; adj.m[1] = A.m[2] * A.m[7] - A.m[1] * A.m[8]; adj.m[2] = A.m[1] * A.m[5] - A.m[2] * A.m[4];
+	adj.m[3] = A.m[5] * A.m[6] - A.m[3] * A.m[8]; adj.m[4] = A.m[0] * A.m[8] - A.m[2] * A.m[6]; adj.m[5] = A.m[2] * A.m[3] - A.m[0] * A.m[5];
+	adj.m[6] = A.m[3] * A.m[7] - A.m[4] * A.m[6]; adj.m[7] = A.m[1] * A.m[6] - A.m[0] * A.m[7]; adj.m[8] = A.m[0] * A.m[4] - A.m[1] * A.m[3];
+	const Mat3 Hn = mat3_mul(B, adj);
+	// H = S^-1 Hn S with S = [s 0 -s cx; 0 s -s cy; 0 0 1], S^-1 = [1/s 0 cx; 0 1/s cy; 0 0 1]
+	Mat3 T;                                                               // Hn S
+#pragma unroll
+	for(int r = 0; r < 3; ++r){
+		T.m[3 * r] = Hn.m[3 * r] * s; T.m[3 * r + 1] = Hn.m[3 * r + 1] * s;
+		T.m[3 * r + 2] = Hn.m[3 * r + 2] - s * (Hn.m[3 * r] * cx + Hn.m[3 * r + 1] * cy);
+	}
+	Mat3 H;
+	const double rs = ext > 0 ? ext : 1.0;
+#pragma unroll
+	for(int c = 0; c < 3; ++c){
+		H.m[c] = rs * T.m[c] + cx * T.m[6 + c];
+		H.m[3 + c] = rs * T.m[3 + c] + cy * T.m[6 + c];
+		H.m[6 + c] = T.m[6 + c];
+	}
+	const double d = H.m[8];
+#pragma unroll
+	for(int k = 0; k < 9; ++k) H.m[k] = H.m[k] / d;
+	return H;
+}
+
+// Homography with corner_based_sampling (Homography.cc:899-909), one thread per particle: rand_dist[0] gives the common
+// translation (two deviates), rand_dist[1] the eight corner offsets; the perturbation is the state of the homography from the
+// initial corners to the disturbed ones (estimateWarpFromCorners, Homography.cc:877-883).
 __global__ void __launch_bounds__(128) pf_perturb_corner_kernel(PFDev pf, DevBatch b, unsigned iter_tag){
 	constexpr int S = 8;
-	const int obj = blockIdx.y, lane = threadIdx.x & 31, i = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int obj = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
 	if(i >= pf.n_particles || pf.done[obj]) return;
 	const size_t pi = (size_t)obj*pf.n_particles + i;
 	double n[10];
@@ -158,7 +220,7 @@ __global__ void __launch_bounds__(128) pf_perturb_corner_kernel(PFDev pf, DevBat
 #pragma unroll
 		for(int s = 0; s < 10; s += 2) normal2(pf.seed, (unsigned)i, (unsigned)(obj + pf.object_offset), iter_tag, STREAM_NORMALS + s / 2, n[s], n[s + 1]);
 	}
-	if(pf.normals_out && lane == 0){
+	if(pf.normals_out){
 #pragma unroll
 		for(int s = 0; s < 10; ++s) pf.normals_out[pi*pf.n_normals + s] = n[s];
 	}
@@ -171,15 +233,10 @@ __global__ void __launch_bounds__(128) pf_perturb_corner_kernel(PFDev pf, DevBat
 		in_c[c] = b.init_corners[(size_t)obj * 8 + c]; in_c[4 + c] = b.init_corners[(size_t)obj * 8 + 4 + c];
 		out_c[c] = (in_c[c] + dx) + tx; out_c[4 + c] = (in_c[4 + c] + dy) + ty;
 	}
-	Mat3 H = warp_homography_dlt(in_c, out_c, lane);                             // estimateWarpFromCorners, Homography.cc:877-883
-	{
-		const double d = H.m[8];
-#pragma unroll
-		for(int k = 0; k < 9; ++k) H.m[k] = H.m[k] / d;
-	}
+	const Mat3 H = homography_4pt(in_c, out_c);
 	double z[S];
 	state_from_warp<SSM_HOM>(z, H);
-	if(lane == 0) dynamic_model<SSM_HOM>(pf, z, pf.states + pi*S, pf.ar + pi*S);
+	dynamic_model<SSM_HOM>(pf, z, pf.states + pi*S, pf.ar + pi*S);
 }
 
 // one CTA per object.  Weights from the evaluation kernel's outputs, their running sum in the reference's order, max_wt_id,
@@ -457,7 +514,7 @@ cudaError_t launch_pf_frame_begin(const PFDev &pf, const DevBatch &b, cudaStream
 }
 cudaError_t launch_pf_perturb(int ssm, const PFDev &pf, const DevBatch &b, unsigned iter_tag, cudaStream_t st){
 	if(ssm == SSM_HOM && pf.corner_based){
-		const dim3 grid((pf.n_particles + 3) / 4, b.P);
+		const dim3 grid((pf.n_particles + 127) / 128, b.P);
 		pf_perturb_corner_kernel<<<grid, 128, 0, st>>>(pf, b, iter_tag);
 	} else{
 		const dim3 grid((pf.n_particles + 127) / 128, b.P);

