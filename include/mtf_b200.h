@@ -18,7 +18,7 @@
  * Layouts (all row-major C arrays, fp64 unless stated):
  *   corners   P x 2 x 4   x_UL,x_UR,x_LR,x_LL,y_UL,y_UR,y_LR,y_LL per patch -- the 2x4 CV_64FC1
  *                          cv::Mat of TrackerBase::initialize (SM/include/mtf/SM/SearchMethod.h:19)
- *   state     P x S        S = 8 (Homography.cc:94-107 order) or 6 (Affine.cc:117-131 order)
+ *   state     P x S        S = 8 (Homography.cc:94-107 order), 6 (Affine.cc:117-131 order) or 2 (Translation: tx, ty)
  *   pts       P x N x 2    x0,y0,x1,y1,... = Eigen column-major PtsT (2 x N)
  *   pix_vals  P x N
  *   pix_grad  P x 2 x N    all Ix then all Iy = column-major PixGradT (N x 2)
@@ -44,7 +44,8 @@ typedef enum mtfb_status {
 
 /* AM/AM.cmake:5 names; SSM/SSM.cmake:1 names; SM/SM.cmake names */
 enum { MTFB_AM_SSD = 0, MTFB_AM_NCC = 1, MTFB_AM_MI = 2 };
-enum { MTFB_SSM_HOMOGRAPHY = 0, MTFB_SSM_AFFINE = 1 };
+enum { MTFB_SSM_HOMOGRAPHY = 0, MTFB_SSM_AFFINE = 1,
+       MTFB_SSM_TRANSLATION = 2 };   /* SSM/src/Translation.cc (GridTracker's default cell model): SSD, F64, ESM / FCLK / ICLK / FALK / IALK */
 enum { MTFB_SM_ESM = 0, MTFB_SM_FCLK = 1, MTFB_SM_ICLK = 2, MTFB_SM_PF = 3,
        MTFB_SM_FALK = 4, MTFB_SM_IALK = 5 };   /* the additive searches nt::FALK / nt::IALK (SM/src/NT/FALK.cc, IALK.cc): SSD, F64 */
 /* ESMParams::HessType / JacType (SM/include/mtf/SM/ESMParams.h:13-17) */

@@ -62,6 +62,7 @@ inline mtfb_params makeParams(const char *sm, const char *am, const char *ssm, i
 	else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: unknown appearance model ") + am); }
 	if(!strcmp(ssm, "8") || !strcmp(ssm, "hom") || !strcmp(ssm, "homography")){ p.ssm = MTFB_SSM_HOMOGRAPHY; }
 	else if(!strcmp(ssm, "6") || !strcmp(ssm, "aff") || !strcmp(ssm, "affine")){ p.ssm = MTFB_SSM_AFFINE; }
+	else if(!strcmp(ssm, "2") || !strcmp(ssm, "trans") || !strcmp(ssm, "translation")){ p.ssm = MTFB_SSM_TRANSLATION; }
 	else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: unknown state space model ") + ssm); }
 	p.n_patches = n_patches; p.resx = resx; p.resy = resy;
 	return p;

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MTFB_LIB") or os.path.join(_HERE, "libmtf_b200.so")   # MTFB_LIB: experiment builds
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
-SSM = {"homography": 0, "affine": 1, "8": 0, "6": 1}
+SSM = {"homography": 0, "affine": 1, "translation": 2, "8": 0, "6": 1, "2": 2}
 SM = {"esm": 0, "fclk": 1, "iclk": 2, "pf": 3, "falk": 4, "ialk": 5}
 ESM_HESS = {"initial_self": 0, "current_self": 1, "sum_of_self": 2, "original": 3, "sum_of_std": 4, "std": 5}
 ESM_JAC = {"original": 0, "diff_of_jacs": 1}

@@ -23,7 +23,7 @@
 namespace mtfb {
 
 enum { AM_SSD = 0, AM_NCC = 1, AM_MI = 2 };
-enum { SSM_HOM = 0, SSM_AFF = 1 };
+enum { SSM_HOM = 0, SSM_AFF = 1, SSM_TRANS = 2 };   // Homography, Affine, Translation (SSM/src/Translation.cc: SSD, F64)
 enum { SM_ESM = 0, SM_FCLK = 1, SM_ICLK = 2, SM_PF = 3, SM_FALK = 4, SM_IALK = 5 };
 
 struct Image {
@@ -209,6 +209,11 @@ template<int SSM> MTFB_HD Mat3 warp_from_state(const double *s){
 		w.m[0] = 1 + s[0]; w.m[1] = s[1]; w.m[2] = s[2];
 		w.m[3] = s[3]; w.m[4] = 1 + s[4]; w.m[5] = s[5];
 		w.m[6] = s[6]; w.m[7] = s[7]; w.m[8] = 1;
+	} else if(SSM == SSM_TRANS){
+		// Translation::getWarpFromState Translation.cc:93-101
+		w.m[0] = 1; w.m[1] = 0; w.m[2] = s[0];
+		w.m[3] = 0; w.m[4] = 1; w.m[5] = s[1];
+		w.m[6] = 0; w.m[7] = 0; w.m[8] = 1;
 	} else{
 		w.m[0] = 1 + s[2]; w.m[1] = s[3]; w.m[2] = s[0];
 		w.m[3] = s[4]; w.m[4] = 1 + s[5]; w.m[5] = s[1];
@@ -222,6 +227,8 @@ template<int SSM> MTFB_HD void state_from_warp(double *s, const Mat3 &w){
 		s[0] = w.m[0] - 1; s[1] = w.m[1]; s[2] = w.m[2];
 		s[3] = w.m[3]; s[4] = w.m[4] - 1; s[5] = w.m[5];
 		s[6] = w.m[6]; s[7] = w.m[7];
+	} else if(SSM == SSM_TRANS){
+		s[0] = w.m[2]; s[1] = w.m[5];                              // Translation.cc:103-109
 	} else{
 		s[0] = w.m[2]; s[1] = w.m[5]; s[2] = w.m[0] - 1;
 		s[3] = w.m[1]; s[4] = w.m[3]; s[5] = w.m[4] - 1;
@@ -326,6 +333,8 @@ template<int SSM, class MW> MTFB_HD void warped_pix_jacobian(const MW &W, const 
 		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
 		J[6] = -x*Ixx - y*Iyx;
 		J[7] = -x*Ixy - y*Iyy;
+	} else if(SSM == SSM_TRANS){
+		J[0] = gx; J[1] = gy;                                      // Translation.h:51-54: the pixel Jacobian is the gradient
 	} else{
 		double a = aff_abcd[0], b = aff_abcd[1], c = aff_abcd[2], d = aff_abcd[3];
 		double Ix = gx, Iy = gy;
@@ -370,6 +379,8 @@ template<int SSM> MTFB_HD void init_pix_jacobian(double x, double y, double Ix, 
 		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
 		J[6] = -x*Ixx - y*Iyx;
 		J[7] = -x*Ixy - y*Iyy;
+	} else if(SSM == SSM_TRANS){
+		J[0] = Ix; J[1] = Iy;                                      // Translation.h:45-49
 	} else{
 		J[0] = Ix; J[1] = Iy; J[2] = Ixx; J[3] = Ixy; J[4] = Iyx; J[5] = Iyy;
 	}
@@ -386,6 +397,8 @@ template<int SSM> MTFB_HD void additive_pix_jacobian(const PixGeom &g, double gx
 		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
 		J[6] = (-g.wx*Ixx - g.wy*Iyx);
 		J[7] = (-g.wx*Ixy - g.wy*Iyy);
+	} else if(SSM == SSM_TRANS){
+		J[0] = gx; J[1] = gy;                                      // Translation.h:60-63
 	} else{
 		const double Ixx = gx*x, Ixy = gx*y, Iyy = gy*y, Iyx = gy*x;
 		J[0] = gx; J[1] = gy; J[2] = Ixx; J[3] = Ixy; J[4] = Iyx; J[5] = Iyy;
@@ -406,6 +419,8 @@ template<int SSM, class MW> MTFB_HD void approx_pix_jacobian(const MW &W, const 
 		J[0] = Ixx; J[1] = Ixy; J[2] = Ix; J[3] = Iyx; J[4] = Iyy; J[5] = Iy;
 		J[6] = (-g.wx*Ixx - g.wy*Iyx);
 		J[7] = (-g.wx*Ixy - g.wy*Iyy);
+	} else if(SSM == SSM_TRANS){
+		J[0] = g0x; J[1] = g0y;                                    // Translation.h:55-58
 	} else{
 		const double a = aff_abcd[0], b = aff_abcd[1], c = aff_abcd[2], d = aff_abcd[3];
 		const double inv_det = ieee_rcp(a*d - b*c);
@@ -417,6 +432,6 @@ template<int SSM, class MW> MTFB_HD void approx_pix_jacobian(const MW &W, const 
 	}
 }
 
-template<int SSM> struct StateSize { static const int value = (SSM == SSM_HOM) ? 8 : 6; };
+template<int SSM> struct StateSize { static const int value = (SSM == SSM_HOM) ? 8 : (SSM == SSM_AFF ? 6 : 2); };
 
 } // namespace mtfb

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 		// the template gradient as the Jacobian uses it: what cmptWarpedPixJacobian / cmptInitPixJacobian left in the
 		// Ix / Iy columns
 		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
-		G0[b.N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+		G0[b.N + it.pix] = (SSM == SSM_HOM) ? J[S > 5 ? 5 : 1] : J[1];
 		if(b.G0raw){ b.G0raw[(size_t)p * 2 * b.N + it.pix] = smp.gx; b.G0raw[(size_t)p * 2 * b.N + b.N + it.pix] = smp.gy; }
 		if(b.I0f){
 			// fp32 copies for the fp32-arithmetic update kernel (lk_ssd_f32.cu)
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, OCC)) ssd_update_kernel(DevBa
 __global__ void lk_set_region_kernel(DevBatch b, const double *__restrict__ corners_in, int S){
 	const int p = blockIdx.x, lane = threadIdx.x;
 	const double *c_in = corners_in + (size_t)p * 8;
-	if(S == 8) set_corners<SSM_HOM>(b, p, lane, c_in); else set_corners<SSM_AFF>(b, p, lane, c_in);
+	if(S == 8) set_corners<SSM_HOM>(b, p, lane, c_in); else if(S == 6) set_corners<SSM_AFF>(b, p, lane, c_in); else set_corners<SSM_TRANS>(b, p, lane, c_in);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -290,6 +290,7 @@ template<int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &
 }
 cudaError_t launch_init_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
 	if(ssm == SSM_HOM) return launch_init_t<SSM_HOM>(threads, b, d_corners, st);
+	if(ssm == SSM_TRANS) return launch_init_t<SSM_TRANS>(threads, b, d_corners, st);
 	return launch_init_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
@@ -306,11 +307,12 @@ template<int SSM> static cudaError_t launch_reinit_t(int threads, const DevBatch
 cudaError_t launch_reinit_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
 	if(!b.G0raw) return cudaErrorInvalidValue;
 	if(ssm == SSM_HOM) return launch_reinit_t<SSM_HOM>(threads, b, d_corners, st);
+	if(ssm == SSM_TRANS) return launch_reinit_t<SSM_TRANS>(threads, b, d_corners, st);
 	return launch_reinit_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st){
-	lk_set_region_kernel<<<b.P, 32, 0, st>>>(b, d_corners, ssm == SSM_HOM ? 8 : 6);
+	lk_set_region_kernel<<<b.P, 32, 0, st>>>(b, d_corners, ssm == SSM_HOM ? 8 : (ssm == SSM_AFF ? 6 : 2));
 	return cudaGetLastError();
 }
 
@@ -341,6 +343,15 @@ cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBa
 		if(sm == SM_IALK) return launch_update_o<SSM_HOM, SM_IALK, 0>(threads, b, st);
 		return launch_update_t<SSM_HOM, SM_ICLK>(threads, occ, b, st);
 	}
+	if(ssm == SSM_TRANS){
+		// the translation SSM (GridTracker's default cell model, parameters.h:502): two sums + three Hessian entries per pixel,
+		// one register budget
+		if(sm == SM_ESM) return launch_update_o<SSM_TRANS, SM_ESM, 2>(threads, b, st);
+		if(sm == SM_FCLK) return launch_update_o<SSM_TRANS, SM_FCLK, 2>(threads, b, st);
+		if(sm == SM_FALK) return launch_update_o<SSM_TRANS, SM_FALK, 2>(threads, b, st);
+		if(sm == SM_IALK) return launch_update_o<SSM_TRANS, SM_IALK, 2>(threads, b, st);
+		return launch_update_o<SSM_TRANS, SM_ICLK, 2>(threads, b, st);
+	}
 	if(sm == SM_ESM) return launch_update_t<SSM_AFF, SM_ESM>(threads, occ, b, st);
 	if(sm == SM_FCLK) return launch_update_t<SSM_AFF, SM_FCLK>(threads, occ, b, st);
 	if(sm == SM_FALK) return launch_update_o<SSM_AFF, SM_FALK, 0>(threads, b, st);
@@ -361,6 +372,7 @@ template<int SSM> static cudaError_t launch_stage_t(int threads, const DevBatch 
 }
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st){
 	if(ssm == SSM_HOM) return launch_stage_t<SSM_HOM>(threads, b, t, st);
+	if(ssm == SSM_TRANS) return launch_stage_t<SSM_TRANS>(threads, b, t, st);
 	return launch_stage_t<SSM_AFF>(threads, b, t, st);
 }
 

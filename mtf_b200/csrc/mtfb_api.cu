@@ -45,7 +45,12 @@ void lin_spaced(std::vector<double> &out, int size, double low, double high){
 bool combo_supported(const mtfb_params *p, const char **why){
 	*why = "";
 	const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
-	if(!(p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE)){ *why = "ssm must be homography or affine"; return false; }
+	if(!(p->ssm == MTFB_SSM_HOMOGRAPHY || p->ssm == MTFB_SSM_AFFINE || p->ssm == MTFB_SSM_TRANSLATION)){ *why = "ssm must be homography, affine or translation"; return false; }
+	if(p->ssm == MTFB_SSM_TRANSLATION){
+		// Translation (SSM/src/Translation.cc) runs on the SSD skeleton of the F64 precision
+		if(p->am != MTFB_AM_SSD || p->precision != MTFB_PRECISION_F64 || p->sm == MTFB_SM_PF){
+			*why = "the translation SSM is implemented for SSD in the F64 precision (ESM / FCLK / ICLK / FALK / IALK)"; return false; }
+	}
 	if(p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK){
 		// the additive searches: ssm.cmptPixJacobian / cmptApproxPixJacobian + ssm.additiveUpdate on the SSD skeleton
 		if(p->am != MTFB_AM_SSD){ *why = "FALK / IALK are implemented for SSD"; return false; }
@@ -308,7 +313,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(!c) return fail(MTFB_ERR_NO_MEMORY, "mtfb_create: out of host memory");
 	std::memset(static_cast<void*>(c), 0, sizeof(*c));
 	c->prm = *p; c->threads = threads; c->occ = occ;
-	c->S = p->ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6;
+	c->S = p->ssm == MTFB_SSM_HOMOGRAPHY ? 8 : (p->ssm == MTFB_SSM_AFFINE ? 6 : 2);
 	c->N = p->resx * p->resy; c->P = p->n_patches;
 	const int S = c->S, N = c->N, P = c->P;
 	mtfb_status st = MTFB_OK;

@@ -363,7 +363,7 @@ struct SSM{
 	// ProjectiveBase::ProjectiveBase SSM/src/ProjectiveBase.cc:9-18, Homography.cc:32-48, Affine.cc:37-62
 	SSM(int _type, int _resx, int _resy, bool _norm_init) : type(_type), resx(_resx), resy(_resy),
 		n_pts(_resx*_resy), normalized_init(_norm_init){
-		state_size = type == ORC_SSM_HOMOGRAPHY ? 8 : 6;
+		state_size = type == ORC_SSM_HOMOGRAPHY ? 8 : (type == ORC_SSM_AFFINE ? 6 : 2);
 		norm_pts.resize(2 * n_pts); norm_pts_hm.resize(3 * n_pts);
 		init_pts.resize(2 * n_pts); curr_pts.resize(2 * n_pts);
 		init_pts_hm.resize(3 * n_pts); curr_pts_hm.resize(3 * n_pts);
@@ -427,6 +427,14 @@ struct SSM{
 				curr_warp = identity3();
 				std::fill(curr_state.begin(), curr_state.end(), 0.0);
 			}
+		} else if(type == ORC_SSM_TRANSLATION){
+			// Translation::setCorners Translation.cc:56-66
+			std::memcpy(init_corners, curr_corners, sizeof(init_corners));
+			init_pts = curr_pts;
+			homogenize_corners(init_corners, init_corners_hm);
+			homogenize(init_pts.data(), init_pts_hm.data(), n_pts);
+			curr_warp = identity3();
+			std::fill(curr_state.begin(), curr_state.end(), 0.0);
 		} else{
 			if(normalized_init) return false;                          // computeAffineNDLT path not restated
 			std::memcpy(init_corners, curr_corners, sizeof(init_corners));
@@ -444,6 +452,8 @@ struct SSM{
 			w(0, 0) = 1 + s[0]; w(0, 1) = s[1]; w(0, 2) = s[2];
 			w(1, 0) = s[3]; w(1, 1) = 1 + s[4]; w(1, 2) = s[5];
 			w(2, 0) = s[6]; w(2, 1) = s[7]; w(2, 2) = 1;
+		} else if(type == ORC_SSM_TRANSLATION){                              // Translation.cc:93-101
+			w = identity3(); w(0, 2) = s[0]; w(1, 2) = s[1];
 		} else{
 			w(0, 0) = 1 + s[2]; w(0, 1) = s[3]; w(0, 2) = s[0];
 			w(1, 0) = s[4]; w(1, 1) = 1 + s[5]; w(1, 2) = s[1];
@@ -456,6 +466,8 @@ struct SSM{
 			s[0] = w(0, 0) - 1; s[1] = w(0, 1); s[2] = w(0, 2);
 			s[3] = w(1, 0); s[4] = w(1, 1) - 1; s[5] = w(1, 2);
 			s[6] = w(2, 0); s[7] = w(2, 1);
+		} else if(type == ORC_SSM_TRANSLATION){                              // Translation.cc:103-109
+			s[0] = w(0, 2); s[1] = w(1, 2);
 		} else{
 			s[0] = w(0, 2); s[1] = w(1, 2); s[2] = w(0, 0) - 1;
 			s[3] = w(0, 1); s[4] = w(1, 0); s[5] = w(1, 1) - 1;
@@ -490,6 +502,15 @@ struct SSM{
 	}
 	// Homography::compositionalUpdate Homography.cc:73-92 ; Affine::compositionalUpdate Affine.cc:90-107
 	void compositionalUpdate(const double *state_update){
+		if(type == ORC_SSM_TRANSLATION){
+			// Translation::compositionalUpdate Translation.cc:80-91: the points are moved by the UPDATE (they accumulate their
+			// own rounding, one addition per iteration), not recomputed from the state
+			curr_state[0] += state_update[0]; curr_state[1] += state_update[1];
+			curr_warp(0, 2) = curr_state[0]; curr_warp(1, 2) = curr_state[1];
+			for(int i = 0; i < n_pts; ++i){ curr_pts[2 * i] += state_update[0]; curr_pts[2 * i + 1] += state_update[1]; }
+			for(int i = 0; i < 4; ++i){ curr_corners[i] += state_update[0]; curr_corners[4 + i] += state_update[1]; }
+			return;
+		}
 		Mat3 warp_update_mat;
 		getWarpFromState(warp_update_mat, state_update);
 		curr_warp = mul3(curr_warp, warp_update_mat);
@@ -507,10 +528,16 @@ struct SSM{
 	void setState(const double *ssm_state){
 		for(int i = 0; i < state_size; ++i) curr_state[i] = ssm_state[i];
 		getWarpFromState(curr_warp, curr_state.data());
+		if(type == ORC_SSM_TRANSLATION){                                       // Translation::setState Translation.cc:68-78
+			for(int i = 0; i < n_pts; ++i){ curr_pts[2 * i] = init_pts[2 * i] + curr_state[0]; curr_pts[2 * i + 1] = init_pts[2 * i + 1] + curr_state[1]; }
+			for(int i = 0; i < 4; ++i){ curr_corners[i] = init_corners[i] + curr_state[0]; curr_corners[4 + i] = init_corners[4 + i] + curr_state[1]; }
+			return;
+		}
 		if(type == ORC_SSM_HOMOGRAPHY) projective_pts(); else affine_pts();
 	}
 	// Homography::invertState Homography.cc:109-114 ; Affine::invertState Affine.cc:145-150
 	void invertState(double *inv_state, const double *state) const{
+		if(type == ORC_SSM_TRANSLATION){ inv_state[0] = -state[0]; inv_state[1] = -state[1]; return; }   // Translation.cc:111-113
 		Mat3 warp_mat, inv_warp_mat;
 		getWarpFromState(warp_mat, state);
 		inv_warp_mat = inverse3(warp_mat);
@@ -521,6 +548,14 @@ struct SSM{
 	// Homography::updateGradPts Homography.cc:803-827 ; Affine::updateGradPts Affine.cc:293-312
 	void updateGradPts(double grad_eps){
 		grad_pts.resize(8 * (size_t)n_pts);
+		if(type == ORC_SSM_TRANSLATION){                                       // Translation.cc:115-130
+			for(int i = 0; i < n_pts; ++i){
+				double x = curr_pts[2 * i], y = curr_pts[2 * i + 1]; double *g = &grad_pts[8 * (size_t)i];
+				g[0] = x + grad_eps; g[1] = y; g[2] = x - grad_eps; g[3] = y;
+				g[4] = x; g[5] = y + grad_eps; g[6] = x; g[7] = y - grad_eps;
+			}
+			return;
+		}
 		if(type == ORC_SSM_HOMOGRAPHY){
 			double dx[3], dy[3];
 			for(int r = 0; r < 3; ++r){ dx[r] = curr_warp(r, 0)*grad_eps; dy[r] = curr_warp(r, 1)*grad_eps; }
@@ -549,6 +584,10 @@ struct SSM{
 	// Homography::cmptInitPixJacobian Homography.cc:157-191 ; Affine::cmptInitPixJacobian Affine.cc:160-181
 	void cmptInitPixJacobian(double *dI_dp, const double *dI_dw) const{
 		const int N = n_pts;
+		if(type == ORC_SSM_TRANSLATION){                                       // Translation.h:45-63: dI_dp = dI_dx
+			for(int i = 0; i < 2 * N; ++i) dI_dp[i] = dI_dw[i];
+			return;
+		}
 		for(int i = 0; i < N; ++i){
 			double x = init_pts[2 * i], y = init_pts[2 * i + 1];
 			double Ix = dI_dw[i], Iy = dI_dw[N + i];
@@ -590,6 +629,7 @@ struct SSM{
 	// Homography::cmptApproxPixJacobian Homography.cc:296-358 ; Affine::cmptApproxPixJacobian Affine.cc:183-211
 	void cmptApproxPixJacobian(double *dI_dp, const double *dI_dw) const{
 		const int N = n_pts;
+		if(type == ORC_SSM_TRANSLATION){ cmptInitPixJacobian(dI_dp, dI_dw); return; }
 		if(type == ORC_SSM_HOMOGRAPHY){
 			Mat3 W = curr_warp;
 			double h00_plus_1 = W(0, 0), h01 = W(0, 1), h10 = W(1, 0), h11_plus_1 = W(1, 1), h20 = W(2, 0), h21 = W(2, 1);
@@ -623,6 +663,7 @@ struct SSM{
 	// Homography::cmptWarpedPixJacobian Homography.cc:231-294 ; Affine::cmptWarpedPixJacobian Affine.cc:213-242
 	void cmptWarpedPixJacobian(double *dI_dp, const double *dI_dw) const{
 		const int N = n_pts;
+		if(type == ORC_SSM_TRANSLATION){ cmptInitPixJacobian(dI_dp, dI_dw); return; }
 		if(type == ORC_SSM_HOMOGRAPHY){
 			double a00 = curr_warp(0, 0), a01 = curr_warp(0, 1), a10 = curr_warp(1, 0);
 			double a11 = curr_warp(1, 1), a20 = curr_warp(2, 0), a21 = curr_warp(2, 1);

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 enum { ORC_AM_SSD = 0, ORC_AM_NCC = 1, ORC_AM_MI = 2 };
-enum { ORC_SSM_HOMOGRAPHY = 0, ORC_SSM_AFFINE = 1 };
+enum { ORC_SSM_HOMOGRAPHY = 0, ORC_SSM_AFFINE = 1, ORC_SSM_TRANSLATION = 2 };
 enum { ORC_SM_ESM = 0, ORC_SM_FCLK = 1, ORC_SM_ICLK = 2, ORC_SM_FALK = 4, ORC_SM_IALK = 5 };
 /* Hessian type codes: the reference has one enum per SM; values as in
  * SM/include/mtf/SM/{ESM,FCLK,ICLK}Params.h */

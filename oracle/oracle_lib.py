@@ -11,7 +11,7 @@ _LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "libmtf_oracle_generic.so" if os
                          else "libmtf_oracle.so")
 
 AM = {"ssd": 0, "ncc": 1, "mi": 2}
-SSM = {"homography": 0, "affine": 1}
+SSM = {"homography": 0, "affine": 1, "translation": 2}
 SM = {"esm": 0, "fclk": 1, "iclk": 2, "falk": 4, "ialk": 5}
 
 

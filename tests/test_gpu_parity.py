@@ -693,3 +693,58 @@ def test_additive_searches_recover_the_motion(seq384, sm):
     with pytest.raises(api.MTFError) as e:
         _gpu("ncc", "homography", sm, 1)
     assert e.value.status == 2
+
+
+# ------------------------------------------------------------------------------------------------ translation SSM
+@pytest.mark.parametrize("sm", ["fclk", "esm", "iclk", "falk", "ialk"])
+@pytest.mark.parametrize("lm,chained", [(0, 1), (1, 1), (0, 0)])
+def test_translation_ssm_iteration_log_parity(seq384, sm, lm, chained):
+    """SSM/src/Translation.cc (GridTracker's default cell model, parameters.h:502) under the five Gauss-Newton searches: every pass
+    against the oracle.  The reference moves curr_pts by each update (Translation.cc:80-91) where the kernel warps the template
+    points with the accumulated state: the two differ by one rounding per pass (~1e-13 px), far inside the tolerances."""
+    if sm in ("falk", "ialk") and not chained:
+        pytest.skip("FALK / IALK have no chained_warp switch")
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(4, 49.0, 384, 384), common.patches(2, 24.6, 384, 384, seed=7)])
+    kw = dict(leven_marq=lm, chained_warp=chained)
+    g = _gpu("ssd", "translation", sm, len(cs), **kw)
+    assert g.S == 2
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = _oracle("ssd", "translation", sm, grad_mode=1 if chained else 0, **kw)
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs = g.iter_log()
+        n_it = g.n_iters()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert n_it[i] == o.n_iters == len(ol) == len(logs[i]), (i, n_it[i], o.n_iters)
+            for k, (a, b) in enumerate(zip(logs[i], ol)):
+                first = fr is frames[1] and k == 0
+                tol = FIRST_RTOL if first else LATER_RTOL
+                # non-chained: the gradient is the reference's literal finite difference over 2e-8 px, which turns the 1e-13 px
+                # between the two ways of moving the points into 1e-5 relative on the Jacobian (the quotient's own noise)
+                gtol = tol if (chained or first) else FD_RTOL * 10
+                assert abs(a["f"] - b["f"]) <= tol * max(abs(b["f"]), 1.0)
+                assert a["rejected"] == b["rejected"]
+                if not a["rejected"]:
+                    assert _rel(a["jacobian"][:2], b["jacobian"][:2]) <= gtol * 10
+                    assert _rel(a["hessian"], b["hessian"]) <= gtol
+                assert np.abs(a["corners"] - b["corners"]).max() <= (CORNER_ATOL_EXACT if chained else CORNER_ATOL_FD)
+        assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= (CORNER_ATOL_EXACT if chained else CORNER_ATOL_FD)
+        assert np.abs(g.state() - np.array([o.state() for o in orcs])).max() <= (1e-8 if chained else CORNER_ATOL_FD)
+
+
+def test_translation_ssm_unsupported_combinations():
+    from mtf_b200 import api
+    for kw in (dict(am="ncc"), dict(am="mi"), dict(sm="pf"), dict(precision="f32")):
+        a = dict(am="ssd", ssm="translation", sm="fclk"); a.update(kw)
+        extra = {k: v for k, v in a.items() if k not in ("am", "ssm", "sm")}
+        with pytest.raises(api.MTFError) as e:
+            _gpu(a["am"], a["ssm"], a["sm"], 1, **extra)
+        assert e.value.status == 2

@@ -198,3 +198,34 @@ def test_pf_tracker_call_order_and_unsupported(pf_inputs):
     t.setRegion(corners[2:4])
     st, w, _, _ = t.particles()
     assert np.all(st == 0) and np.allclose(w, 1 / 64) and np.allclose(t.getRegion(), corners[2:4])
+
+
+@pytest.mark.gpu
+def test_pf_tracker_at_config5_size(pf_inputs):
+    """BASELINE config 5's per-object size -- 10 000 particles (weights in 80 KB of shared memory, the sequential prefix sum,
+    10 000 binary searches) -- against the oracle's loop given the recorded device-generated stream, plus the size-independent
+    properties of a resampling step"""
+    from mtf_b200 import api
+    frames, _, corners = pf_inputs
+    P, n = 2, 10000
+    g = api.PFTracker(api.make_params("ssd", "homography", "pf", n_patches=P), n_particles=n, sigma=SIGMA_CORNER,
+                      corner_based_sampling=1, mean_type="ssm", adaptive_resampling_thresh=0.0, record_randoms=1, seed=5)
+    g.initialize(corners[:P], frames[0])
+    o = O.OraclePF(O.make_params("ssd", "homography", "fclk"), g.pf_params)
+    o.set_image(frames[0]); o.initialize(corners[0])
+    for t in (1, 2):
+        g.update(frames[t])
+        nrm, uni = g.random_stream()
+        st, w, cw, mx = g.particles()
+        # properties: normalised cumulative weights are a distribution function; every resampled state is one of the weights'
+        # owners; the reported region is the mean state's
+        assert np.all(np.diff(cw, axis=1) >= 0) and np.allclose(cw[:, -1], 1.0, rtol=0, atol=1e-15)
+        assert np.all(w > 0) and np.all(np.isfinite(st))
+        o.set_image(frames[t]); o.update(nrm[:, 0], uni[:, 0])
+        st2, w2, cw2, mx2, resampled = o.particles()
+        assert resampled and mx[0] == mx2
+        assert np.allclose(w[0], w2, rtol=1e-6, atol=1e-300)
+        assert np.allclose(cw[0], cw2, rtol=1e-6, atol=1e-12)
+        assert np.allclose(st[0], st2, rtol=1e-7, atol=1e-8)
+        assert np.allclose(g.getRegion()[0], o.corners(), rtol=0, atol=1e-6)
+        assert np.allclose(g.state()[0], st[0].mean(axis=0), rtol=1e-10, atol=1e-13)
