@@ -44,7 +44,25 @@ __device__ __forceinline__ double bspl3_hess(double x){
 	return 0;
 }
 
-// the (up to) 4 histogram bins a pixel value touches and its B-spline weights / derivatives (MI.cc:231-243)
+// The four branches of bSpl3WithGrad (histUtils.h:206-224) one by one, in the reference's operation order; the division by 3
+// is the exact quotient from RN(1/3) and one correction (lk_math.cuh div_by) instead of an IEEE division sequence.
+__device__ __forceinline__ void bspl3_piece0(double &val, double &diff, double x){      // -2 < x <= -1
+	const double temp = 2 + x; diff = (temp * temp) * 0.5; val = div_by(diff * temp, 3.0, 0.33333333333333331);
+}
+__device__ __forceinline__ void bspl3_piece1(double &val, double &diff, double x){      // -1 < x <= 0
+	const double temp = x * 0.5; val = (2.0 / 3.0) - x*x*(1 + temp); diff = -x * (temp + x + 2);
+}
+__device__ __forceinline__ void bspl3_piece2(double &val, double &diff, double x){      //  0 < x <= 1
+	const double temp = x * 0.5; val = (2.0 / 3.0) - x*x*(1 - temp); diff = x * (temp + x - 2);
+}
+__device__ __forceinline__ void bspl3_piece3(double &val, double &diff, double x){      //  1 < x < 2 (x = 2: both zero)
+	const double temp = 2 - x; diff = -(temp * temp) * 0.5; val = -div_by(diff * temp, 3.0, 0.33333333333333331);
+}
+
+// the (up to) 4 histogram bins a pixel value touches and its B-spline weights / derivatives (MI.cc:231-243).
+// With bin = (int)v and lo = bin - 1 the k-th argument lo - v + k lies in the k-th branch's interval, so the four weights are
+// the four pieces in order (one when lo was clamped at 0: the pieces shift by one) -- no interval tests per weight.  Values
+// outside [0, B - 1) (not produced by pix_norm_mult on 8-bit frames) take the generic function.
 struct BinWeights { int lo, hi; double w[4], d[4]; };
 __device__ __forceinline__ BinWeights bin_weights(double v, int B){
 	BinWeights o;
@@ -52,6 +70,19 @@ __device__ __forceinline__ BinWeights bin_weights(double v, int B){
 	o.lo = bin - 1 > 0 ? bin - 1 : 0;
 	o.hi = bin + 2 < B - 1 ? bin + 2 : B - 1;
 	double x = o.lo - v;
+	if(v >= 0.0 && bin <= B - 1){
+		const double x1 = x + 1, x2 = x1 + 1, x3 = x2 + 1;              // curr_diff incremented bin by bin, as the reference does
+		if(o.lo == bin - 1){
+			bspl3_piece0(o.w[0], o.d[0], x); bspl3_piece1(o.w[1], o.d[1], x1);
+			bspl3_piece2(o.w[2], o.d[2], x2); bspl3_piece3(o.w[3], o.d[3], x3);
+		} else{                                                         // bin = 0: lo = 0 = bin
+			bspl3_piece1(o.w[0], o.d[0], x); bspl3_piece2(o.w[1], o.d[1], x1);
+			bspl3_piece3(o.w[2], o.d[2], x2); o.w[3] = 0; o.d[3] = 0;
+		}
+#pragma unroll
+		for(int k = 1; k < 4; ++k) if(o.lo + k > o.hi){ o.w[k] = 0; o.d[k] = 0; }
+		return o;
+	}
 #pragma unroll
 	for(int k = 0; k < 4; ++k){
 		bspl3_with_grad(o.w[k], o.d[k], x);
