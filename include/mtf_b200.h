@@ -243,6 +243,41 @@ mtfb_status mtfb_pf_get_random_stream(mtfb_ctx *ctx, double *normals, double *un
 mtfb_status mtfb_pf_get_particles(mtfb_ctx *ctx, double *states /* P x n x S */, double *weights /* P x n */,
 	double *cum_weights /* P x n */, int *max_wt_id /* P */);
 
+/* ---- robust warp estimation from point pairs: the step GridTracker::update runs after its cells
+ * Replaces SSM::estimateWarpFromPts of Homography (SSM/src/Homography.cc:885-897 -> estimateHomography,
+ * HomographyEstimator.cc:168-228) and Affine (Affine.cc:359-369 -> estimateAffine, AffineEstimator.cc:126-185) with the RANSAC /
+ * LMedS drivers and the Levenberg-Marquardt refinement of SSMEstimator.cc:73-518, as ONE kernel launch.  Fields and defaults
+ * = SSMEstimatorParams (SSMEstimatorParams.cc:5-13, .h:11-32) without use_boost_rng (the cvRNG stream only); `seed` replaces the
+ * reference's boost::random_device seed (SSMEstimator.cc:22-24) so that a run can be reproduced: the subsets drawn are those of
+ * cvRNG(seed) / cvRandInt.  Not implemented: Translation's estimator (Translation.cc:187-238), n_model_pts > 8. */
+enum { MTFB_EST_RANSAC = 0, MTFB_EST_LMEDS = 1, MTFB_EST_LEAST_SQUARES = 2 };   /* SSMEstimatorParams::EstType */
+typedef struct mtfb_est_params {
+	int method;
+	double ransac_reproj_thresh;   /* <= 0 -> 3 (SSMEstimatorParams.cc:55-57) */
+	int n_model_pts, refine, max_iters, max_subset_attempts;
+	double confidence;
+	int lm_max_iters;
+	unsigned long long seed;       /* 0 -> cvRNG's default state */
+} mtfb_est_params;
+void mtfb_est_default_params(mtfb_est_params *p);
+/* in_pts, out_pts: n x 2 floats (std::vector<cv::Point2f>), host pointers.  Outputs (host, any may be NULL): state_update (8
+ * doubles; 6 used for Affine), mask (n bytes: the inliers), warp (3 x 3 row-major; zeros when the estimation fails, as the
+ * reference returns), info = { result, hypotheses drawn, inliers, LM evaluations }.  ssm: MTFB_SSM_HOMOGRAPHY or _AFFINE
+ * (GridTracker's own SSM, independent of the cells' SSM). */
+mtfb_status mtfb_estimate_warp_from_pts(mtfb_ctx *ctx, int ssm, const float *in_pts, const float *out_pts, int n,
+	const mtfb_est_params *ep, double *state_update, unsigned char *mask, double *warp, int *info);
+/* the same on the context's own cells without a host copy of the points: in_pts = the centroids (utils::getCentroid,
+ * miscUtils.h:473-480) of the regions at the last mtfb_initialize / mtfb_set_region / mtfb_grid_commit (prev_pts,
+ * GridTracker.cc:389), out_pts = the centroids of the current regions (curr_pts, :257).  mtfb_grid_enable first (it allocates the
+ * point buffers; from then on initialize / set_region record prev_pts with one more small launch). */
+mtfb_status mtfb_grid_enable(mtfb_ctx *ctx);
+mtfb_status mtfb_grid_estimate(mtfb_ctx *ctx, int ssm, const mtfb_est_params *ep, double *state_update, unsigned char *mask,
+	double *warp, int *info);
+/* prev_pts = curr_pts: GridTracker::update with reset_at_each_frame = 0 (GridTracker.cc:276-279) */
+mtfb_status mtfb_grid_commit(mtfb_ctx *ctx);
+/* prev_pts / curr_pts as the last mtfb_grid_estimate saw them (P x 2 floats each, host; either may be NULL) */
+mtfb_status mtfb_grid_get_pts(mtfb_ctx *ctx, float *prev_pts, float *curr_pts);
+
 /* getters = the accessors of SURVEY.md 8(a18): ssm->getCorners/getState/getPts, am->getSimilarity,
  * am->getInitPixVals/getCurrPixVals/getCurrPixGrad ...; they synchronise the context stream.
  * Host pointers. */

@@ -66,6 +66,16 @@ class PFParams(C.Structure):
                 ("seed", C.c_ulonglong), ("object_offset", C.c_int), ("record_randoms", C.c_int)]
 
 
+class EstParams(C.Structure):
+    """mtfb_est_params = SSMEstimatorParams (SSM/src/SSMEstimatorParams.cc) + the cvRNG seed"""
+    _fields_ = [("method", C.c_int), ("ransac_reproj_thresh", C.c_double), ("n_model_pts", C.c_int), ("refine", C.c_int),
+                ("max_iters", C.c_int), ("max_subset_attempts", C.c_int), ("confidence", C.c_double),
+                ("lm_max_iters", C.c_int), ("seed", C.c_ulonglong)]
+
+
+EST_METHOD = {"ransac": 0, "lmeds": 1, "least_squares": 2}
+
+
 class IterLog(C.Structure):
     _fields_ = [("f", C.c_double), ("jacobian", C.c_double * 8), ("hessian", C.c_double * 64),
                 ("state_update", C.c_double * 8), ("corners", C.c_double * 8),
@@ -83,6 +93,8 @@ EXPORTS = [
     "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_get_curr_stage_f32", "mtfb_device_results",
     "mtfb_state_size", "mtfb_debug_colpiv_qr_solve",
     "mtfb_pf_default_params", "mtfb_pf_configure", "mtfb_pf_set_random_stream", "mtfb_pf_get_random_stream", "mtfb_pf_get_particles",
+    "mtfb_est_default_params", "mtfb_estimate_warp_from_pts", "mtfb_grid_enable", "mtfb_grid_estimate", "mtfb_grid_commit",
+    "mtfb_grid_get_pts",
 ]
 
 _lib = None
@@ -135,9 +147,16 @@ def load_library(path=LIB_PATH):
     L.mtfb_pf_set_random_stream.argtypes = [vp, vp, vp]
     L.mtfb_pf_get_random_stream.argtypes = [vp, vp, vp]
     L.mtfb_pf_get_particles.argtypes = [vp, vp, vp, vp, vp]
+    L.mtfb_est_default_params.argtypes = [C.POINTER(EstParams)]; L.mtfb_est_default_params.restype = None
+    L.mtfb_estimate_warp_from_pts.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
+    L.mtfb_grid_enable.argtypes = [vp]
+    L.mtfb_grid_estimate.argtypes = [vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
+    L.mtfb_grid_commit.argtypes = [vp]
+    L.mtfb_grid_get_pts.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_pf_default_params"):
+        if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_pf_default_params",
+                        "mtfb_est_default_params"):
             fn.restype = C.c_int
     _lib = L
     return L
@@ -401,11 +420,60 @@ class BatchTracker:
         self._check(self._L.mtfb_pf_evaluate(self._h, _dp(states), n, _dp(lik), _dp(sim)))
         return lik, sim
 
+    # ---- robust warp estimation from point pairs (SSM::estimateWarpFromPts; mtf_b200/csrc/grid_estimator.cu)
+    def _est_result(self, ssm, n, call):
+        S = 8 if ssm == 0 else 6
+        su = np.zeros(S); mask = np.zeros(n, dtype=np.uint8); warp = np.zeros(9); info = np.zeros(4, dtype=np.int32)
+        self._check(call(su.ctypes.data, mask.ctypes.data, warp.ctypes.data, info.ctypes.data))
+        return {"ok": bool(info[0]), "state_update": su, "mask": mask, "warp": warp.reshape(3, 3), "drawn": int(info[1]),
+                "n_inliers": int(info[2]), "lm_evals": int(info[3])}
+
+    def estimate_warp_from_pts(self, ssm, in_pts, out_pts, est_params):
+        """ssm.estimateWarpFromPts(state_update, mask, in_pts, out_pts, est_params) for Homography / Affine"""
+        ssm = SSM[ssm] if isinstance(ssm, str) else int(ssm)
+        a = np.ascontiguousarray(in_pts, dtype=np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(out_pts, dtype=np.float32).reshape(-1, 2)
+        if a.shape != b.shape:
+            raise ValueError("in_pts and out_pts differ in size")
+        n = a.shape[0]
+        return self._est_result(ssm, n, lambda su, mk, wp, inf: self._L.mtfb_estimate_warp_from_pts(
+            self._h, ssm, a.ctypes.data, b.ctypes.data, n, C.byref(est_params), su, mk, wp, inf))
+
+    def grid_enable(self):
+        self._check(self._L.mtfb_grid_enable(self._h))
+
+    def grid_estimate(self, ssm, est_params):
+        """the same between the centroids at the last initialize / setRegion / grid_commit and the current ones, on the device"""
+        ssm = SSM[ssm] if isinstance(ssm, str) else int(ssm)
+        return self._est_result(ssm, self.P, lambda su, mk, wp, inf: self._L.mtfb_grid_estimate(
+            self._h, ssm, C.byref(est_params), su, mk, wp, inf))
+
+    def grid_commit(self):
+        self._check(self._L.mtfb_grid_commit(self._h))
+
+    def grid_pts(self):
+        a = np.empty((self.P, 2), dtype=np.float32); b = np.empty((self.P, 2), dtype=np.float32)
+        self._check(self._L.mtfb_grid_get_pts(self._h, a.ctypes.data, b.ctypes.data))
+        return a, b
+
     def device_results(self):
         """raw device pointers (corners P x 8 f64, state P x S f64, n_iters P i32)"""
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._L.mtfb_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+def make_est_params(method="ransac", seed=0, **kw):
+    """mtfb_est_params: SSMEstimatorParams' defaults (SSMEstimatorParams.cc:5-13) with overrides"""
+    p = EstParams()
+    load_library().mtfb_est_default_params(C.byref(p))
+    p.method = EST_METHOD[method] if isinstance(method, str) else int(method)
+    p.seed = int(seed)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
 
 
 def make_pf_params(n_particles=500, sigma=None, mean=None, **kw):

@@ -1,0 +1,631 @@
+// grid_estimator.cu -- SSM::estimateWarpFromPts for Homography / Affine on the device: the RANSAC / LMedS / least-squares
+// estimation of one warp from the P cell centroids that GridTracker::update runs once per frame
+// (SM/src/GridTracker.cc:253-269 -> SSM/src/Homography.cc:885-897, Affine.cc:359-369 -> estimateHomography
+// HomographyEstimator.cc:168-228 / estimateAffine AffineEstimator.cc:126-185 -> SSMEstimator.cc runRANSAC :73-139, runLMeDS
+// :143-217, getSubset :220-259, LevMarq :298-518).
+//
+// One CTA of eight warps.  The reference's loop "draw a subset, fit, count" is sequential only through its generator and its
+// best-so-far bookkeeping: thread 0 draws a round of 32 subsets from the cvRNG stream (checkSubset included), the warps fit
+// and score them in parallel (one hypothesis per warp at a time: lane 0 fits, all lanes score the P points), thread 0 replays
+// the acceptance rule over the round in the reference's order, so the accepted model, the adaptive iteration count and the
+// mask are those of the sequential loop.  The final fit on the inliers and the Levenberg-Marquardt refinement are block-wide
+// reductions with thread 0 running the solver's state machine.
+//
+// Numerics: double precision throughout, the reprojection errors rounded to float as in the reference.  Where the reference
+// calls cvEigenVV for the eigenvector of the smallest eigenvalue of LtL this file runs inverse iteration on an LDLt
+// factorisation, and where it calls cvSVD + cvSVBkSb on the damped normal matrix a diagonally scaled elimination with partial
+// pivoting: the same vector / solution to rounding, not the same rounding.
+#include "grid_estimator.cuh"
+#include <cfloat>
+
+namespace mtfb {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int BATCH = 32;                 // hypotheses per round
+enum { M_RANSAC = 0, M_LMEDS = 1, M_LS = 2 };   // SSMEstimatorParams::EstType (SSMEstimatorParams.h:11)
+
+// cvRNG / cvRandInt (OpenCV core: multiply-with-carry)
+struct CvRng {
+	unsigned long long s;
+	__device__ unsigned next(){ s = (unsigned long long)(unsigned)s * 4164903690ULL + (s >> 32); return (unsigned)s; }
+};
+
+// cvRANSACUpdateNumIters as SSMEstimator.cc:49-71 has it
+__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters){
+	p = fmax(p, 0.); p = fmin(p, 1.);
+	ep = fmax(ep, 0.); ep = fmin(ep, 1.);
+	double num = fmax(1. - p, DBL_MIN);
+	double denom = 1. - pow(1. - ep, (double)model_points);
+	if(denom < DBL_MIN) return 0;
+	num = log(num); denom = log(denom);
+	return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
+}
+
+// SSMEstimator::checkSubset (:262-296) with checkPartialSubsets = false
+__device__ bool check_subset(const double *p, int count){
+	if(count <= 2) return true;
+	int i, j, k;
+	for(i = 0; i <= count - 1; ++i){
+		for(j = 0; j < i; ++j){
+			const double dx1 = p[2 * j] - p[2 * i], dy1 = p[2 * j + 1] - p[2 * i + 1];
+			for(k = 0; k < j; ++k){
+				const double dx2 = p[2 * k] - p[2 * i], dy2 = p[2 * k + 1] - p[2 * i + 1];
+				if(fabs(dx2 * dy1 - dy2 * dx1) <= FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) break;
+			}
+			if(k < j) break;
+		}
+		if(j < i) break;
+	}
+	return i > count - 1;
+}
+
+// SSMEstimator::getSubset (:220-259)
+__device__ bool get_subset(CvRng &rng, const float *m1, const float *m2, int count, int mp, int max_attempts, int *idx){
+	double ms1[2 * EST_MAX_MODEL_PTS], ms2[2 * EST_MAX_MODEL_PTS];
+	int i = 0, j, iters = 0;
+	for(; iters < max_attempts; ++iters){
+		for(i = 0; i < mp && iters < max_attempts;){
+			const int idx_i = idx[i] = (int)(rng.next() % (unsigned)count);
+			for(j = 0; j < i; ++j) if(idx_i == idx[j]) break;
+			if(j < i) continue;
+			ms1[2 * i] = m1[2 * idx_i]; ms1[2 * i + 1] = m1[2 * idx_i + 1];
+			ms2[2 * i] = m2[2 * idx_i]; ms2[2 * i + 1] = m2[2 * idx_i + 1];
+			++i;
+		}
+		if(i == mp && (!check_subset(ms1, i) || !check_subset(ms2, i))) continue;
+		break;
+	}
+	return i == mp && iters < max_attempts;
+}
+
+// eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix (A is overwritten by its LDLt
+// factors): inverse iteration with a zero shift; x is scaled to a largest component of +1
+__device__ void smallest_eigvec9(double *A, double *x, double *y){
+	double tr = 0;
+	for(int i = 0; i < 9; ++i) tr += A[i * 9 + i];
+	const double tiny = tr * 1e-30 + 1e-300;
+	for(int j = 0; j < 9; ++j){
+		double d = A[j * 9 + j];
+		for(int k = 0; k < j; ++k) d -= A[j * 9 + k] * A[j * 9 + k] * A[k * 9 + k];
+		if(fabs(d) < tiny) d = tiny;
+		A[j * 9 + j] = d;
+		for(int i = j + 1; i < 9; ++i){
+			double s = A[i * 9 + j];
+			for(int k = 0; k < j; ++k) s -= A[i * 9 + k] * A[j * 9 + k] * A[k * 9 + k];
+			A[i * 9 + j] = s / d;
+		}
+	}
+	for(int i = 0; i < 9; ++i) x[i] = 1.0;
+	for(int it = 0; it < 100; ++it){
+		for(int i = 0; i < 9; ++i){
+			double s = x[i];
+			for(int k = 0; k < i; ++k) s -= A[i * 9 + k] * y[k];
+			y[i] = s;
+		}
+		for(int i = 0; i < 9; ++i) y[i] /= A[i * 9 + i];
+		for(int i = 8; i >= 0; --i){
+			double s = y[i];
+			for(int k = i + 1; k < 9; ++k) s -= A[k * 9 + i] * y[k];
+			y[i] = s;
+		}
+		int im = 0;
+		for(int i = 1; i < 9; ++i) if(fabs(y[i]) > fabs(y[im])) im = i;
+		const double sc = 1.0 / y[im];
+		double diff = 0;
+		for(int i = 0; i < 9; ++i){ const double v = y[i] * sc; diff = fmax(diff, fabs(v - x[i])); x[i] = v; }
+		if(it > 0 && diff < 1e-15) break;
+	}
+}
+
+// the tail of HomographyEstimator::runKernel (:70-76): H = invHnorm * H0 * Hnorm2, scaled to H[8] = 1
+__device__ void denormalise(const double *H0, double cmx, double cmy, double smx, double smy, double cMx, double cMy, double sMx, double sMy, double *H){
+	const double invHnorm[9] = { 1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1 };
+	const double Hnorm2[9] = { sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1 };
+	double T[9], R[9];
+	for(int r = 0; r < 3; ++r) for(int c = 0; c < 3; ++c){ double s = 0; for(int k = 0; k < 3; ++k) s += invHnorm[r * 3 + k] * H0[k * 3 + c]; T[r * 3 + c] = s; }
+	for(int r = 0; r < 3; ++r) for(int c = 0; c < 3; ++c){ double s = 0; for(int k = 0; k < 3; ++k) s += T[r * 3 + k] * Hnorm2[k * 3 + c]; R[r * 3 + c] = s; }
+	const double sc = 1. / R[8];
+	for(int i = 0; i < 9; ++i) H[i] = R[i] * sc;
+}
+
+struct WarpWs { double A[81], x[9], y[9], M[2 * EST_MAX_MODEL_PTS], m[2 * EST_MAX_MODEL_PTS]; };
+
+// HomographyEstimator::runKernel (:16-78) for the few points of one hypothesis, by one thread, sums in the reference's order
+__device__ int hom_fit_subset(WarpWs &w, int count, double *H){
+	const double *M = w.M, *m = w.m;
+	double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
+	for(int i = 0; i < count; ++i){ cmx += m[2 * i]; cmy += m[2 * i + 1]; cMx += M[2 * i]; cMy += M[2 * i + 1]; }
+	cmx /= count; cmy /= count; cMx /= count; cMy /= count;
+	for(int i = 0; i < count; ++i){
+		smx += fabs(m[2 * i] - cmx); smy += fabs(m[2 * i + 1] - cmy);
+		sMx += fabs(M[2 * i] - cMx); sMy += fabs(M[2 * i + 1] - cMy);
+	}
+	if(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) return 0;
+	smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
+	for(int i = 0; i < 81; ++i) w.A[i] = 0;
+	for(int i = 0; i < count; ++i){
+		const double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
+		const double X = (M[2 * i] - cMx) * sMx, Y = (M[2 * i + 1] - cMy) * sMy;
+		const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
+		const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
+		for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k) w.A[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+	}
+	for(int j = 0; j < 9; ++j) for(int k = 0; k < j; ++k) w.A[j * 9 + k] = w.A[k * 9 + j];
+	smallest_eigvec9(w.A, w.x, w.y);
+	denormalise(w.x, cmx, cmy, smx, smy, cMx, cMy, sMx, sMy, H);
+	return 1;
+}
+
+// least squares of [X Y 1] a = x, [X Y 1] b = y from the centred second moments (utils::computeAffineDLT, warpUtils.cc:344-377,
+// takes the SVD of the block matrix; the solution is the same)
+__device__ int aff_from_moments(double n, double cX, double cY, double cx, double cy, double Sxx, double Sxy, double Syy,
+	double SXx, double SYx, double SXy, double SYy, double *H){
+	const double det = Sxx * Syy - Sxy * Sxy;
+	if(!(fabs(det) > 0)) return 0;
+	const double a0 = (SXx * Syy - SYx * Sxy) / det, a1 = (SYx * Sxx - SXx * Sxy) / det;
+	const double b0 = (SXy * Syy - SYy * Sxy) / det, b1 = (SYy * Sxx - SXy * Sxy) / det;
+	H[0] = a0; H[1] = a1; H[2] = cx - a0 * cX - a1 * cY;
+	H[3] = b0; H[4] = b1; H[5] = cy - b0 * cX - b1 * cY;
+	H[6] = 0; H[7] = 0; H[8] = 1;
+	return 1;
+}
+__device__ int aff_fit_subset(const WarpWs &w, int count, double *H){
+	const double *M = w.M, *m = w.m;
+	double cX = 0, cY = 0, cx = 0, cy = 0;
+	for(int i = 0; i < count; ++i){ cX += M[2 * i]; cY += M[2 * i + 1]; cx += m[2 * i]; cy += m[2 * i + 1]; }
+	cX /= count; cY /= count; cx /= count; cy /= count;
+	double Sxx = 0, Sxy = 0, Syy = 0, SXx = 0, SYx = 0, SXy = 0, SYy = 0;
+	for(int i = 0; i < count; ++i){
+		const double X = M[2 * i] - cX, Y = M[2 * i + 1] - cY, x = m[2 * i] - cx, y = m[2 * i + 1] - cy;
+		Sxx += X * X; Sxy += X * Y; Syy += Y * Y; SXx += X * x; SYx += Y * x; SXy += X * y; SYy += Y * y;
+	}
+	return aff_from_moments(count, cX, cY, cx, cy, Sxx, Sxy, Syy, SXx, SYx, SXy, SYy, H);
+}
+
+// HomographyEstimator / AffineEstimator::computeReprojError (:81-95 / :49-62) for one point
+template<bool HOM> __device__ __forceinline__ float reproj_err(const double *H, double Mx, double My, double mx, double my){
+	double dx, dy;
+	if(HOM){
+		const double ww = 1. / (H[6] * Mx + H[7] * My + 1.);
+		dx = (H[0] * Mx + H[1] * My + H[2]) * ww - mx;
+		dy = (H[3] * Mx + H[4] * My + H[5]) * ww - my;
+	} else {
+		dx = (H[0] * Mx + H[1] * My + H[2]) - mx;
+		dy = (H[3] * Mx + H[4] * My + H[5]) - my;
+	}
+	return (float)(dx * dx + dy * dy);
+}
+
+// k-th smallest (0-based) of n non-negative floats given as their bit patterns: radix select by one warp
+__device__ unsigned warp_select(const unsigned *v, int n, int k, unsigned *hist, int lane){
+	unsigned prefix = 0, mask_bits = 0;
+	int kk = k;
+	for(int shift = 24; shift >= 0; shift -= 8){
+		for(int i = lane; i < 256; i += 32) hist[i] = 0;
+		__syncwarp();
+		for(int i = lane; i < n; i += 32){ const unsigned x = v[i]; if((x & mask_bits) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u); }
+		__syncwarp();
+		unsigned c[8], tot = 0;
+#pragma unroll
+		for(int j = 0; j < 8; ++j){ c[j] = hist[8 * lane + j]; tot += c[j]; }
+		unsigned incl = tot;
+#pragma unroll
+		for(int off = 1; off < 32; off <<= 1){ const unsigned t = __shfl_up_sync(FULL, incl, off); if(lane >= off) incl += t; }
+		const unsigned excl = incl - tot;
+		const bool mine = (unsigned)kk >= excl && (unsigned)kk < incl;
+		const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+		int bin = 0, newk = 0;
+		if(mine){
+			unsigned run = excl;
+			bool found = false;
+#pragma unroll
+			for(int j = 0; j < 8; ++j){
+				if(!found && (unsigned)kk < run + c[j]){ bin = 8 * lane + j; newk = kk - (int)run; found = true; }
+				run += c[j];
+			}
+		}
+		bin = __shfl_sync(FULL, bin, src); newk = __shfl_sync(FULL, newk, src);
+		prefix |= (unsigned)bin << shift; mask_bits |= 255u << shift; kk = newk;
+		__syncwarp();
+	}
+	return prefix;
+}
+
+template<int K> __device__ void block_sum(double (&v)[K], double (*s_red)[48], double *s_sum){
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+	for(int k = 0; k < K; ++k){
+		double x = v[k];
+#pragma unroll
+		for(int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
+		if(lane == 0) s_red[warp][k] = x;
+	}
+	__syncthreads();
+	if(tid < K){ double s = 0; for(int w = 0; w < EST_WARPS; ++w) s += s_red[w][tid]; s_sum[tid] = s; }
+	__syncthreads();
+}
+
+// runKernel on the points mask selects, by the whole block; the model goes to s_model
+template<bool HOM> __device__ int fit_masked(const EstDev &e, WarpWs &ws, double (*s_red)[48], double *s_sum, double *s_model){
+	const int tid = threadIdx.x, n = e.n;
+	double a[5] = { 0, 0, 0, 0, 0 };
+	for(int i = tid; i < n; i += EST_THREADS) if(e.mask[i]){
+		a[0] += e.out_pts[2 * i]; a[1] += e.out_pts[2 * i + 1]; a[2] += e.in_pts[2 * i]; a[3] += e.in_pts[2 * i + 1]; a[4] += 1;
+	}
+	block_sum<5>(a, s_red, s_sum);
+	const double count = s_sum[4];
+	const double cmx = s_sum[0] / count, cmy = s_sum[1] / count, cMx = s_sum[2] / count, cMy = s_sum[3] / count;
+	if(HOM){
+		double d[4] = { 0, 0, 0, 0 };
+		for(int i = tid; i < n; i += EST_THREADS) if(e.mask[i]){
+			d[0] += fabs(e.out_pts[2 * i] - cmx); d[1] += fabs(e.out_pts[2 * i + 1] - cmy);
+			d[2] += fabs(e.in_pts[2 * i] - cMx); d[3] += fabs(e.in_pts[2 * i + 1] - cMy);
+		}
+		block_sum<4>(d, s_red, s_sum);
+		double smx = s_sum[0], smy = s_sum[1], sMx = s_sum[2], sMy = s_sum[3];
+		if(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) return 0;
+		smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
+		double L[45];
+#pragma unroll
+		for(int k = 0; k < 45; ++k) L[k] = 0;
+		for(int i = tid; i < n; i += EST_THREADS) if(e.mask[i]){
+			const double x = (e.out_pts[2 * i] - cmx) * smx, y = (e.out_pts[2 * i + 1] - cmy) * smy;
+			const double X = (e.in_pts[2 * i] - cMx) * sMx, Y = (e.in_pts[2 * i + 1] - cMy) * sMy;
+			const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
+			const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
+			int q = 0;
+#pragma unroll
+			for(int j = 0; j < 9; ++j)
+#pragma unroll
+				for(int k = j; k < 9; ++k) L[q++] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+		}
+		block_sum<45>(L, s_red, s_sum);
+		if(tid == 0){
+			int q = 0;
+			for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k){ ws.A[j * 9 + k] = s_sum[q]; ws.A[k * 9 + j] = s_sum[q]; ++q; }
+			smallest_eigvec9(ws.A, ws.x, ws.y);
+			denormalise(ws.x, cmx, cmy, smx, smy, cMx, cMy, sMx, sMy, s_model);
+		}
+		__syncthreads();
+		return 1;
+	} else {
+		double d[7] = { 0, 0, 0, 0, 0, 0, 0 };
+		for(int i = tid; i < n; i += EST_THREADS) if(e.mask[i]){
+			const double X = e.in_pts[2 * i] - cMx, Y = e.in_pts[2 * i + 1] - cMy, x = e.out_pts[2 * i] - cmx, y = e.out_pts[2 * i + 1] - cmy;
+			d[0] += X * X; d[1] += X * Y; d[2] += Y * Y; d[3] += X * x; d[4] += Y * x; d[5] += X * y; d[6] += Y * y;
+		}
+		block_sum<7>(d, s_red, s_sum);
+		__shared__ int s_ok;
+		if(tid == 0){
+			double H[9];
+			s_ok = aff_from_moments(count, cMx, cMy, cmx, cmy, s_sum[0], s_sum[1], s_sum[2], s_sum[3], s_sum[4], s_sum[5], s_sum[6], H);
+			if(s_ok) for(int i = 0; i < 9; ++i) s_model[i] = H[i];
+		}
+		__syncthreads();
+		return s_ok;
+	}
+}
+
+// mask[i] = err_i <= threshold^2 for every point, returns the count (SSMEstimator::findInliers :35-46) -- whole block
+template<bool HOM> __device__ int find_inliers_block(const EstDev &e, const double *H, double threshold, double (*s_red)[48], double *s_sum){
+	const double t2 = threshold * threshold;
+	double c[1] = { 0 };
+	for(int i = threadIdx.x; i < e.n; i += EST_THREADS){
+		const float er = reproj_err<HOM>(H, e.in_pts[2 * i], e.in_pts[2 * i + 1], e.out_pts[2 * i], e.out_pts[2 * i + 1]);
+		const bool in = (double)er <= t2;
+		e.mask[i] = in; c[0] += in;
+	}
+	block_sum<1>(c, s_red, s_sum);
+	return (int)s_sum[0];
+}
+
+// LevMarq::step (SSMEstimator.cc:489-516): param = prevParam - (JtJ with its diagonal scaled by 1 + lambda)^-1 JtErr
+template<int NP> __device__ void lm_step(const double *JtJ, const double *JtErr, const double *prev, double *param, int lambdaLg10){
+	const double lambda = exp(lambdaLg10 * log(10.));
+	double A[NP * NP], b[NP], sc[NP];
+	for(int i = 0; i < NP; ++i){
+		const double d = JtJ[i * NP + i] * (1. + lambda);
+		sc[i] = d > 0 ? rsqrt(d) : 1.0;
+	}
+	for(int i = 0; i < NP; ++i){
+		for(int j = 0; j < NP; ++j){
+			double v = i <= j ? JtJ[i * NP + j] : JtJ[j * NP + i];
+			if(i == j) v *= 1. + lambda;
+			A[i * NP + j] = v * sc[i] * sc[j];
+		}
+		b[i] = JtErr[i] * sc[i];
+	}
+	for(int k = 0; k < NP; ++k){
+		int pv = k;
+		for(int i = k + 1; i < NP; ++i) if(fabs(A[i * NP + k]) > fabs(A[pv * NP + k])) pv = i;
+		if(pv != k){
+			for(int j = 0; j < NP; ++j){ const double t = A[k * NP + j]; A[k * NP + j] = A[pv * NP + j]; A[pv * NP + j] = t; }
+			const double t = b[k]; b[k] = b[pv]; b[pv] = t;
+		}
+		double d = A[k * NP + k];
+		if(fabs(d) < 1e-300) d = 1e-300;
+		const double inv = 1.0 / d;
+		for(int i = k + 1; i < NP; ++i){
+			const double f = A[i * NP + k] * inv;
+			for(int j = k + 1; j < NP; ++j) A[i * NP + j] -= f * A[k * NP + j];
+			b[i] -= f * b[k];
+		}
+		A[k * NP + k] = d;
+	}
+	for(int k = NP - 1; k >= 0; --k){
+		double s = b[k];
+		for(int j = k + 1; j < NP; ++j) s -= A[k * NP + j] * b[j];
+		b[k] = s / A[k * NP + k];
+	}
+	for(int i = 0; i < NP; ++i) param[i] = prev[i] - b[i] * sc[i];
+}
+
+// HomographyEstimator::refine (:97-145) / AffineEstimator::refine (:64-106) around LevMarq::updateAlt (:436-487)
+template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48], double *s_sum, double *s_model){
+	constexpr int NP = HOM ? 8 : 6, NJ = NP * (NP + 1) / 2, K = NJ + NP + 1;
+	enum { DONE = 0, STARTED = 1, CALC_J = 2, CHECK_ERR = 3 };
+	__shared__ double s_JtJ[64], s_JtErr[8], s_param[8], s_prev[8];
+	__shared__ int s_flag[3];
+	const int tid = threadIdx.x;
+	int state = STARTED, iters = 0, lambdaLg10 = -3, evals = 0;
+	const int max_iter = min(max(e.lm_max_iters, 1), 1000);
+	double prevErrNorm = DBL_MAX, errNorm = 0;
+	if(tid < NP) s_param[tid] = s_model[tid];
+	__syncthreads();
+	for(;;){
+		if(tid == 0){
+			int cont = 1, want_J = 0, want_err = 0;
+			if(state == STARTED){ errNorm = 0; want_J = want_err = 1; state = CALC_J; }
+			else if(state == CALC_J){
+				for(int i = 0; i < NP; ++i) s_prev[i] = s_param[i];
+				lm_step<NP>(s_JtJ, s_JtErr, s_prev, s_param, lambdaLg10);
+				prevErrNorm = errNorm; errNorm = 0; want_err = 1; state = CHECK_ERR;
+			} else {
+				bool retried = false;
+				if(errNorm > prevErrNorm){
+					if(++lambdaLg10 <= 16){
+						lm_step<NP>(s_JtJ, s_JtErr, s_prev, s_param, lambdaLg10);
+						errNorm = 0; want_err = 1; state = CHECK_ERR; retried = true;
+					}
+				}
+				if(!retried){
+					lambdaLg10 = max(lambdaLg10 - 1, -16);
+					double dn = 0, pn = 0;
+					for(int i = 0; i < NP; ++i){ const double d = s_param[i] - s_prev[i]; dn += d * d; pn += s_prev[i] * s_prev[i]; }
+					const double change = sqrt(dn) / (sqrt(pn) + DBL_EPSILON);
+					if(++iters >= max_iter || change < DBL_EPSILON){ state = DONE; cont = 0; }
+					else { prevErrNorm = errNorm; want_J = 1; state = CALC_J; }
+				}
+			}
+			s_flag[0] = cont; s_flag[1] = want_J; s_flag[2] = want_err;
+		}
+		__syncthreads();
+		if(!s_flag[0]) break;
+		const bool want_J = s_flag[1] != 0, want_err = s_flag[2] != 0;
+		++evals;
+		double h[NP];
+#pragma unroll
+		for(int i = 0; i < NP; ++i) h[i] = s_param[i];
+		double acc[K];
+#pragma unroll
+		for(int k = 0; k < K; ++k) acc[k] = 0;
+		for(int i = tid; i < e.n; i += EST_THREADS) if(e.mask[i]){
+			const double Mx = e.in_pts[2 * i], My = e.in_pts[2 * i + 1];
+			double J0[NP], J1[NP], er0, er1;
+			if(HOM){
+				double ww = h[6] * Mx + h[7] * My + 1.;
+				ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+				const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww, yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+				er0 = xi - e.out_pts[2 * i]; er1 = yi - e.out_pts[2 * i + 1];
+				J0[0] = Mx * ww; J0[1] = My * ww; J0[2] = ww; J0[3] = 0; J0[4] = 0; J0[5] = 0; J0[6] = -Mx * ww * xi; J0[7] = -My * ww * xi;
+				J1[0] = 0; J1[1] = 0; J1[2] = 0; J1[3] = Mx * ww; J1[4] = My * ww; J1[5] = ww; J1[6] = -Mx * ww * yi; J1[7] = -My * ww * yi;
+			} else {
+				const double xi = h[0] * Mx + h[1] * My + h[2], yi = h[3] * Mx + h[4] * My + h[5];
+				er0 = xi - e.out_pts[2 * i]; er1 = yi - e.out_pts[2 * i + 1];
+				J0[0] = Mx; J0[1] = My; J0[2] = 1; J0[3] = 0; J0[4] = 0; J0[5] = 0;
+				J1[0] = 0; J1[1] = 0; J1[2] = 0; J1[3] = Mx; J1[4] = My; J1[5] = 1;
+			}
+			if(want_J){
+				int q = 0;
+#pragma unroll
+				for(int j = 0; j < NP; ++j){
+#pragma unroll
+					for(int k = j; k < NP; ++k) acc[q++] += J0[j] * J0[k] + J1[j] * J1[k];
+					acc[NJ + j] += J0[j] * er0 + J1[j] * er1;
+				}
+			}
+			acc[K - 1] += er0 * er0 + er1 * er1;
+		}
+		block_sum<K>(acc, s_red, s_sum);
+		if(tid == 0){
+			if(want_J){
+				int q = 0;
+				for(int j = 0; j < NP; ++j){ for(int k = j; k < NP; ++k) s_JtJ[j * NP + k] = s_sum[q++]; s_JtErr[j] = s_sum[NJ + j]; }
+			}
+			if(want_err) errNorm += s_sum[K - 1];
+		}
+	}
+	if(tid < NP) s_model[tid] = s_param[tid];
+	__syncthreads();
+	return evals;
+}
+
+template<bool HOM>
+__global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
+	__shared__ WarpWs s_ws[EST_WARPS];
+	__shared__ int s_idx[BATCH][EST_MAX_MODEL_PTS];
+	__shared__ int s_found[BATCH], s_valid[BATCH], s_good[BATCH];
+	__shared__ double s_hyp[BATCH][9], s_median[BATCH];
+	__shared__ double s_model[9];
+	__shared__ double s_red[EST_WARPS][48], s_sum[48];
+	__shared__ unsigned s_hist[EST_WARPS][256];
+	__shared__ int s_ctl[2];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int n = e.n, mp = e.model_points;
+	const int method = n == mp ? (int)M_LS : e.method;
+	constexpr int NM = HOM ? 9 : 6;
+
+	for(int i = tid; i < n; i += EST_THREADS) e.mask[i] = 1;
+	if(tid < 9) s_model[tid] = tid == 8 ? 1.0 : 0.0;
+	__syncthreads();
+
+	int result = 0, drawn = 0;
+	if(method == M_LS){
+		result = fit_masked<HOM>(e, s_ws[0], s_red, s_sum, s_model);
+	} else {
+		// thread 0's sequential state
+		CvRng rng; rng.s = e.seed ? e.seed : ~0ULL;
+		int iter = 0, niters = e.max_iters, max_good = 0;
+		double min_median = DBL_MAX;
+		bool first_failed = false;
+		if(method == M_LMEDS){
+			niters = __double2int_rn(log(1 - e.confidence) / log(1 - pow(1 - 0.45, (double)mp)));
+			niters = min(max(niters, 3), e.max_iters);
+		}
+		for(;;){
+			if(tid == 0){
+				int nb = min(BATCH, niters - iter);
+				for(int b = 0; b < nb; ++b){
+					s_found[b] = get_subset(rng, e.in_pts, e.out_pts, n, mp, e.max_attempts, s_idx[b]);
+					if(!s_found[b]){ nb = b + 1; break; }
+				}
+				s_ctl[0] = nb;
+			}
+			__syncthreads();
+			const int nb = s_ctl[0];
+			for(int b = warp; b < nb; b += EST_WARPS){
+				if(!s_found[b]) continue;
+				WarpWs &w = s_ws[warp];
+				if(lane < mp){
+					const int id = s_idx[b][lane];
+					w.M[2 * lane] = e.in_pts[2 * id]; w.M[2 * lane + 1] = e.in_pts[2 * id + 1];
+					w.m[2 * lane] = e.out_pts[2 * id]; w.m[2 * lane + 1] = e.out_pts[2 * id + 1];
+				}
+				__syncwarp();
+				if(lane == 0) s_valid[b] = HOM ? hom_fit_subset(w, mp, s_hyp[b]) : aff_fit_subset(w, mp, s_hyp[b]);
+				__syncwarp();
+				if(!s_valid[b]) continue;
+				double H[9];
+#pragma unroll
+				for(int i = 0; i < NM; ++i) H[i] = s_hyp[b][i];
+				if(method == M_RANSAC){
+					const double t2 = e.thresh * e.thresh;
+					int good = 0;
+					for(int i = lane; i < n; i += 32){
+						const float er = reproj_err<HOM>(H, e.in_pts[2 * i], e.in_pts[2 * i + 1], e.out_pts[2 * i], e.out_pts[2 * i + 1]);
+						good += (double)er <= t2;
+					}
+#pragma unroll
+					for(int off = 16; off >= 1; off >>= 1) good += __shfl_xor_sync(FULL, good, off);
+					if(lane == 0) s_good[b] = good;
+				} else {
+					float *er = e.err + (size_t)warp * n;
+					for(int i = lane; i < n; i += 32)
+						er[i] = reproj_err<HOM>(H, e.in_pts[2 * i], e.in_pts[2 * i + 1], e.out_pts[2 * i], e.out_pts[2 * i + 1]);
+					__syncwarp();
+					const unsigned *bits = reinterpret_cast<const unsigned *>(er);
+					const float hi = __uint_as_float(warp_select(bits, n, n / 2, s_hist[warp], lane));
+					double median = hi;
+					if(n % 2 == 0){
+						const float lo = __uint_as_float(warp_select(bits, n, n / 2 - 1, s_hist[warp], lane));
+						median = (double)(lo + hi) * 0.5;
+					}
+					if(lane == 0) s_median[b] = median;
+				}
+			}
+			__syncthreads();
+			if(tid == 0){
+				// the reference's loop body over this round's hypotheses, in order (SSMEstimator.cc:101-127 / :176-202)
+				int stop = 0;
+				for(int b = 0; b < nb && iter < niters; ++b, ++iter){
+					if(!s_found[b]){ if(iter == 0) first_failed = true; stop = 1; break; }
+					if(!s_valid[b]) continue;
+					if(method == M_RANSAC){
+						const int good = s_good[b];
+						if(good > max(max_good, mp - 1)){
+							for(int i = 0; i < NM; ++i) s_model[i] = s_hyp[b][i];
+							max_good = good;
+							niters = ransac_update_num_iters(e.confidence, (double)(n - good) / n, mp, niters);
+						}
+					} else if(s_median[b] < min_median){
+						min_median = s_median[b];
+						for(int i = 0; i < NM; ++i) s_model[i] = s_hyp[b][i];
+					}
+				}
+				if(iter >= niters) stop = 1;
+				s_ctl[1] = stop;
+			}
+			__syncthreads();
+			if(s_ctl[1]) break;
+		}
+		__shared__ int s_res[2];
+		__shared__ double s_sigma;
+		if(tid == 0){
+			int mode = 0;         // 0: failed, mask stays all ones; 1: RANSAC mask of the best model; 2: LMedS mask at sigma
+			if(!first_failed){
+				if(method == M_RANSAC) mode = max_good > 0 ? 1 : 0;
+				else if(min_median < DBL_MAX){
+					double sigma = 2.5 * 1.4826 * (1 + 5. / (n - mp)) * sqrt(min_median);
+					s_sigma = fmax(sigma, 0.001); mode = 2;
+				}
+			}
+			s_res[0] = mode; s_res[1] = iter;
+		}
+		__syncthreads();
+		drawn = s_res[1];
+		if(s_res[0] == 1){ find_inliers_block<HOM>(e, s_model, e.thresh, s_red, s_sum); result = 1; }
+		else if(s_res[0] == 2){ const int cnt = find_inliers_block<HOM>(e, s_model, s_sigma, s_red, s_sum); result = cnt >= mp; }
+	}
+	__syncthreads();
+	// estimateHomography :205-214: the points the mask keeps, the model re-fitted on them after RANSAC, the refinement
+	int n_in = n, evals = 0;
+	if(result && n > mp){
+		double c[1] = { 0 };
+		for(int i = tid; i < n; i += EST_THREADS) c[0] += e.mask[i] != 0;
+		block_sum<1>(c, s_red, s_sum);
+		n_in = (int)s_sum[0];
+		__syncthreads();
+		if(method == M_RANSAC) fit_masked<HOM>(e, s_ws[0], s_red, s_sum, s_model);
+		if(e.refine) evals = lm_refine<HOM>(e, s_red, s_sum, s_model);
+	}
+	if(tid == 0){
+		double H[9];
+		for(int i = 0; i < 9; ++i) H[i] = s_model[i];
+		if(!HOM){ H[6] = 0; H[7] = 0; H[8] = 1; }
+		if(!result) for(int i = 0; i < 9; ++i) H[i] = 0;
+		for(int i = 0; i < 9; ++i) e.out[i] = H[i];
+		double *su = e.out + 9;
+		if(HOM){
+			// Homography::estimateWarpFromPts (Homography.cc:885-897)
+			su[0] = H[0] - 1; su[1] = H[1]; su[2] = H[2]; su[3] = H[3]; su[4] = H[4] - 1; su[5] = H[5]; su[6] = H[6]; su[7] = H[7];
+		} else {
+			// Affine::estimateWarpFromPts (Affine.cc:359-369)
+			su[0] = H[2]; su[1] = H[5]; su[2] = H[0] - 1; su[3] = H[1]; su[4] = H[3]; su[5] = H[4] - 1; su[6] = 0; su[7] = 0;
+		}
+		e.info[0] = result; e.info[1] = drawn; e.info[2] = n_in; e.info[3] = evals;
+	}
+}
+
+__global__ void centroid_kernel(const double *corners, int P, float *pts){
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if(p >= P) return;
+	const double *c = corners + 8 * (size_t)p;
+	pts[2 * p] = (float)((c[0] + c[1] + c[2] + c[3]) / 4.0);
+	pts[2 * p + 1] = (float)((c[4] + c[5] + c[6] + c[7]) / 4.0);
+}
+
+} // namespace
+
+cudaError_t launch_centroids(const double *corners, int P, float *pts, cudaStream_t st){
+	centroid_kernel<<<(P + 255) / 256, 256, 0, st>>>(corners, P, pts);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_estimate(const EstDev &e, cudaStream_t st){
+	if(e.homography) estimate_kernel<true><<<1, EST_THREADS, 0, st>>>(e);
+	else estimate_kernel<false><<<1, EST_THREADS, 0, st>>>(e);
+	return cudaGetLastError();
+}
+
+} // namespace mtfb

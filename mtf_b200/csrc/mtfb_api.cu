@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include "lk_kernels.cuh"
 #include "pf_tracker.cuh"
+#include "grid_estimator.cuh"
 
 using namespace mtfb;
 
@@ -174,6 +175,10 @@ struct mtfb_ctx {
 	Image pre_image[2];
 	int pre_next, pre_pending, pre_current;      // slot of the next upload; slot uploaded but not adopted yet (-1); slot b.img points to (-1)
 	// tensor map of the current frame for the moment kernel's 2-D TMA window copy (re-encoded when the frame buffer changes)
+	// robust warp estimation from point pairs (grid_estimator.cu): staging for host points, outputs, LMedS scratch; the grid's
+	// own prev_pts / curr_pts after mtfb_grid_enable
+	float *d_est_pts; unsigned char *d_est_mask; float *d_est_err; double *d_est_out; int *d_est_info; size_t est_capacity;
+	float *d_grid_prev, *d_grid_curr; bool grid_enabled;
 	alignas(64) CUtensorMap frame_map; const float *frame_map_ptr; int frame_map_h, frame_map_w, frame_map_pitch; bool frame_map_ok;
 };
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -240,6 +245,8 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32); cudaFree(c->d_raw);
 	cudaFree(c->d_mom_work);
 	cudaFree(c->d_pf); cudaFree(c->d_pf_ints); cudaFree(c->d_pf_rand_in); cudaFree(c->d_pf_rand_out);
+	cudaFree(c->d_est_pts); cudaFree(c->d_est_mask); cudaFree(c->d_est_err); cudaFree(c->d_est_out); cudaFree(c->d_est_info);
+	cudaFree(c->d_grid_prev); cudaFree(c->d_grid_curr);
 	if(c->copy_stream){
 		cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream);
 		cudaEventDestroy(c->ev_upload); cudaEventDestroy(c->ev_read[0]); cudaEventDestroy(c->ev_read[1]);
@@ -643,6 +650,11 @@ mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 	++c->launches;
 	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
 	c->initialized = true;
+	if(c->grid_enabled){
+		// GridTracker::resetTrackers (GridTracker.cc:389): prev_pts = centroid of the cell's region
+		CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_prev, c->stream));
+		++c->launches;
+	}
 	if(c->pf_configured){
 		// PF::initialize (NT/PF.cc:136-183): initializeParticles, prev_corners = ssm->getCorners()
 		CUDA_TRY(launch_pf_init_particles(c->prm.ssm, c->pf, c->b, true, c->stream));
@@ -668,6 +680,10 @@ mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	else CUDA_TRY(launch_reinit_ssd(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
 	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
+	if(c->grid_enabled){
+		CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_prev, c->stream));
+		++c->launches;
+	}
 	if(c->pf_configured){
 		// PF::setRegion (NT/PF.cc:596-600): ssm->setCorners, initializeParticles
 		CUDA_TRY(launch_pf_init_particles(c->prm.ssm, c->pf, c->b, false, c->stream));
@@ -815,6 +831,116 @@ mtfb_status mtfb_pf_get_particles(mtfb_ctx *c, double *states, double *weights, 
 	if(weights) CUDA_TRY(cudaMemcpyAsync(weights, c->pf.weights, pn*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if(cum_weights) CUDA_TRY(cudaMemcpyAsync(cum_weights, c->pf.cum_weights, pn*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if(max_wt_id) CUDA_TRY(cudaMemcpyAsync(max_wt_id, c->pf.max_wt_id, (size_t)c->P*sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return MTFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ robust warp estimation
+void mtfb_est_default_params(mtfb_est_params *p){
+	if(!p) return;
+	// SSMEstimatorParams.cc:5-13
+	p->method = MTFB_EST_RANSAC; p->ransac_reproj_thresh = 10.0; p->n_model_pts = 4; p->refine = 1; p->max_iters = 2000;
+	p->max_subset_attempts = 300; p->confidence = 0.995; p->lm_max_iters = 10; p->seed = 0;
+}
+
+static mtfb_status est_reserve(mtfb_ctx *c, size_t n){
+	if(n <= c->est_capacity && c->d_est_out) return MTFB_OK;
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_est_pts); cudaFree(c->d_est_mask); cudaFree(c->d_est_err); c->d_est_pts = nullptr; c->d_est_mask = nullptr; c->d_est_err = nullptr;
+	c->est_capacity = 0;
+	CUDA_TRY(cudaMalloc(&c->d_est_pts, 4 * n*sizeof(float)));
+	CUDA_TRY(cudaMalloc(&c->d_est_mask, n));
+	CUDA_TRY(cudaMalloc(&c->d_est_err, (size_t)EST_WARPS*n*sizeof(float)));
+	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 17 * sizeof(double)));
+	if(!c->d_est_info) CUDA_TRY(cudaMalloc(&c->d_est_info, 4 * sizeof(int)));
+	c->est_capacity = n;
+	return MTFB_OK;
+}
+
+static mtfb_status est_run(mtfb_ctx *c, const char *who, int ssm, const float *d_in, const float *d_out, int n, const mtfb_est_params *ep,
+	double *state_update, unsigned char *mask, double *warp, int *info){
+	if(ssm != MTFB_SSM_HOMOGRAPHY && ssm != MTFB_SSM_AFFINE)
+		return fail(MTFB_ERR_NOT_SUPPORTED, "%s: the estimators of Homography and Affine are implemented (ssm = %d)", who, ssm);
+	if(ep->method != MTFB_EST_RANSAC && ep->method != MTFB_EST_LMEDS && ep->method != MTFB_EST_LEAST_SQUARES)
+		return fail(MTFB_ERR_INVALID_ARG, "%s: invalid estimation method %d", who, ep->method);
+	const int min_pts = ssm == MTFB_SSM_HOMOGRAPHY ? 4 : 3;           // the estimators' assert(_modelPoints >= 4 / 3)
+	if(ep->n_model_pts < min_pts) return fail(MTFB_ERR_INVALID_ARG, "%s: n_model_pts = %d, at least %d needed", who, ep->n_model_pts, min_pts);
+	if(ep->n_model_pts > EST_MAX_MODEL_PTS) return fail(MTFB_ERR_NOT_SUPPORTED, "%s: n_model_pts = %d, at most %d implemented", who, ep->n_model_pts, (int)EST_MAX_MODEL_PTS);
+	if(n < ep->n_model_pts) return fail(MTFB_ERR_INVALID_ARG, "%s: %d points, n_model_pts = %d (CV_Assert(n_pts >= params.n_model_pts))", who, n, ep->n_model_pts);
+	if(ep->max_iters < 1 || ep->max_subset_attempts < 1) return fail(MTFB_ERR_INVALID_ARG, "%s: max_iters and max_subset_attempts must be positive", who);
+	EstDev e;
+	e.in_pts = d_in; e.out_pts = d_out; e.n = n; e.homography = ssm == MTFB_SSM_HOMOGRAPHY;
+	e.method = ep->method; e.model_points = ep->n_model_pts; e.refine = ep->refine; e.max_iters = ep->max_iters;
+	e.max_attempts = ep->max_subset_attempts; e.lm_max_iters = ep->lm_max_iters;
+	e.thresh = ep->ransac_reproj_thresh > 0 ? ep->ransac_reproj_thresh : 3.0;
+	e.confidence = ep->confidence; e.seed = ep->seed;
+	e.out = c->d_est_out; e.info = c->d_est_info; e.mask = c->d_est_mask; e.err = c->d_est_err;
+	CUDA_TRY(launch_estimate(e, c->stream));
+	++c->launches;
+	double out[17]; int inf[4];
+	CUDA_TRY(cudaMemcpyAsync(out, c->d_est_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(inf, c->d_est_info, sizeof(inf), cudaMemcpyDeviceToHost, c->stream));
+	if(mask) CUDA_TRY(cudaMemcpyAsync(mask, c->d_est_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(warp) std::memcpy(warp, out, 9 * sizeof(double));
+	if(state_update) std::memcpy(state_update, out + 9, (ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6)*sizeof(double));
+	if(info) std::memcpy(info, inf, sizeof(inf));
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_estimate_warp_from_pts(mtfb_ctx *c, int ssm, const float *in_pts, const float *out_pts, int n, const mtfb_est_params *ep,
+	double *state_update, unsigned char *mask, double *warp, int *info){
+	if(!c || !in_pts || !out_pts || !ep) return fail(MTFB_ERR_INVALID_ARG, "mtfb_estimate_warp_from_pts: null argument");
+	if(n < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_estimate_warp_from_pts: no points");
+	for(size_t i = 0; i < 2 * (size_t)n; ++i)
+		if(!std::isfinite(in_pts[i]) || !std::isfinite(out_pts[i])) return fail(MTFB_ERR_INVALID_ARG, "mtfb_estimate_warp_from_pts: non-finite point %zu", i / 2);
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	{ mtfb_status st = est_reserve(c, (size_t)n); if(st != MTFB_OK) return st; }
+	CUDA_TRY(cudaMemcpyAsync(c->d_est_pts, in_pts, 2 * (size_t)n*sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->d_est_pts + 2 * (size_t)n, out_pts, 2 * (size_t)n*sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	return est_run(c, "mtfb_estimate_warp_from_pts", ssm, c->d_est_pts, c->d_est_pts + 2 * (size_t)n, n, ep, state_update, mask, warp, info);
+}
+
+mtfb_status mtfb_grid_enable(mtfb_ctx *c){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_enable: null context");
+	if(c->grid_enabled) return MTFB_OK;
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaMalloc(&c->d_grid_prev, 2 * (size_t)c->P*sizeof(float)));
+	CUDA_TRY(cudaMalloc(&c->d_grid_curr, 2 * (size_t)c->P*sizeof(float)));
+	c->grid_enabled = true;
+	if(c->initialized){
+		CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_prev, c->stream));
+		++c->launches;
+	}
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_grid_estimate(mtfb_ctx *c, int ssm, const mtfb_est_params *ep, double *state_update, unsigned char *mask, double *warp, int *info){
+	if(!c || !ep) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_estimate: null argument");
+	if(!c->grid_enabled) return fail(MTFB_ERR_LOGIC, "mtfb_grid_estimate: mtfb_grid_enable has not been called");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_grid_estimate: initialize has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	{ mtfb_status st = est_reserve(c, (size_t)c->P); if(st != MTFB_OK) return st; }
+	CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_curr, c->stream));
+	++c->launches;
+	return est_run(c, "mtfb_grid_estimate", ssm, c->d_grid_prev, c->d_grid_curr, c->P, ep, state_update, mask, warp, info);
+}
+
+mtfb_status mtfb_grid_commit(mtfb_ctx *c){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_commit: null context");
+	if(!c->grid_enabled || !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_grid_commit: mtfb_grid_enable and initialize first");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_prev, c->stream));
+	++c->launches;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_grid_get_pts(mtfb_ctx *c, float *prev_pts, float *curr_pts){
+	if(!c) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_get_pts: null context");
+	if(!c->grid_enabled || !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_grid_get_pts: mtfb_grid_enable and initialize first");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	if(prev_pts) CUDA_TRY(cudaMemcpyAsync(prev_pts, c->d_grid_prev, 2 * (size_t)c->P*sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	if(curr_pts) CUDA_TRY(cudaMemcpyAsync(curr_pts, c->d_grid_curr, 2 * (size_t)c->P*sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return MTFB_OK;
 }

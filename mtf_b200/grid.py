@@ -1,0 +1,168 @@
+"""GridTracker<SSM> (SM/src/GridTracker.cc) on the batch library: grid_size_x x grid_size_y patch trackers as ONE batch context,
+the warp of the whole region estimated from their centroids on the device (mtfb_grid_estimate: RANSAC / LMedS / least squares +
+LM refinement in one launch), the few host-side steps of GridTracker::update around it (the 4 corners of the region, the cell
+layout) in NumPy.  Host work per frame: 8 doubles down, the P x 8 cell corners up.
+
+Implemented: Homography / Affine as the grid's SSM with its default non-normalised initialisation, reset_at_each_frame 0 / 1,
+dyn_patch_size, patch_centroid_inside.  Not implemented (raise): forward-backward error estimation (fb_err_thresh > 0,
+GridTracker.cc:303-343), pyramidal cells, heterogeneous cells."""
+import numpy as np
+
+from . import api
+
+
+def norm_unit_square_pts(resx, resy):
+    """utils::getNormUnitSquarePts (warpUtils.cc:15-33): (2, resx*resy) points row by row, (2, 4) corners"""
+    xs = np.linspace(-0.5, 0.5, resx) if resx > 1 else np.array([-0.5])
+    ys = np.linspace(-0.5, 0.5, resy) if resy > 1 else np.array([-0.5])
+    pts = np.empty((2, resx * resy))
+    pts[0] = np.tile(xs, resy)
+    pts[1] = np.repeat(ys, resx)
+    corners = np.array([[-0.5, 0.5, 0.5, -0.5], [-0.5, -0.5, 0.5, 0.5]])
+    return pts, corners
+
+
+def homography_dlt(src, dst):
+    """utils::computeHomographyDLT (warpUtils.cc:183-220) for 4 point pairs: the homography with H[2, 2] = 1.  The reference takes
+    the null vector of the 8 x 9 system from its SVD and divides by its last entry; the 8 x 8 system solved here has the same
+    solution."""
+    src = np.asarray(src, dtype=np.float64).reshape(2, 4)
+    dst = np.asarray(dst, dtype=np.float64).reshape(2, 4)
+    A = np.zeros((8, 8)); b = np.zeros(8)
+    for i in range(4):
+        x, y, u, v = src[0, i], src[1, i], dst[0, i], dst[1, i]
+        A[2 * i] = [x, y, 1, 0, 0, 0, -u * x, -u * y]
+        A[2 * i + 1] = [0, 0, 0, x, y, 1, -v * x, -v * y]
+        b[2 * i], b[2 * i + 1] = u, v
+    h = np.linalg.solve(A, b)
+    return np.append(h, 1.0).reshape(3, 3)
+
+
+def pts_from_corners(corners, resx, resy):
+    """utils::getPtsFromCorners (warpUtils.cc:34-60): the regular grid of the unit square under the 4-corner homography"""
+    pts, nc = norm_unit_square_pts(resx, resy)
+    H = homography_dlt(nc, corners)
+    q = H @ np.vstack([pts, np.ones(pts.shape[1])])
+    return q[:2] / q[2]
+
+
+def apply_warp_to_corners(ssm, corners, state_update):
+    """ssm.applyWarpToCorners (Homography.cc / Affine.cc:371-380): the warp of a state applied to 4 corners"""
+    s = np.asarray(state_update, dtype=np.float64)
+    if ssm == "homography":
+        W = np.array([[1 + s[0], s[1], s[2]], [s[3], 1 + s[4], s[5]], [s[6], s[7], 1.0]])
+    else:
+        # Affine::getWarpFromState (Affine.cc:127-141): (tx, ty, a, b, c, d)
+        W = np.array([[1 + s[2], s[3], s[0]], [s[4], 1 + s[5], s[1]], [0, 0, 1.0]])
+    q = W @ np.vstack([np.asarray(corners, dtype=np.float64).reshape(2, 4), np.ones(4)])
+    return q[:2] / q[2]
+
+
+class GridTracker:
+    """mirror of GridTracker<SSM>: setImage / initialize / update / setRegion / getRegion"""
+
+    def __init__(self, cell_params, grid_size_x=10, grid_size_y=10, patch_size_x=10, patch_size_y=10, reset_at_each_frame=1,
+                 dyn_patch_size=0, patch_centroid_inside=True, fb_err_thresh=0, enable_pyr=0, ssm="homography", est_params=None,
+                 seed=1):
+        # defaults: GridTracker.h:8-23
+        if fb_err_thresh > 0:
+            raise api.MTFError(2, "GridTracker: forward-backward error estimation is not implemented")
+        if enable_pyr:
+            raise api.MTFError(2, "GridTracker: pyramidal patch trackers are not implemented")
+        if ssm not in ("homography", "affine"):
+            raise api.MTFError(2, "GridTracker: the grid's SSM must be homography or affine")
+        self.gx, self.gy = int(grid_size_x), int(grid_size_y)
+        n = self.gx * self.gy
+        if cell_params.n_patches != n:
+            # GridTracker.cc:126-131
+            raise api.MTFError(1, "GridTracker :: Mismatch between grid dimensions and no. of trackers")
+        self.patch_size_x, self.patch_size_y = float(patch_size_x), float(patch_size_y)
+        self.reset_at_each_frame = int(reset_at_each_frame)
+        self.reinit_at_each_frame = self.reset_at_each_frame == 1          # GridTracker.cc:138
+        self.dyn_patch_size, self.patch_centroid_inside = int(dyn_patch_size), bool(patch_centroid_inside)
+        # GridTrackerParams::updateRes (GridTracker.cc:85-93)
+        self.resx, self.resy = (self.gx + 1, self.gy + 1) if (self.dyn_patch_size or self.patch_centroid_inside) else (self.gx, self.gy)
+        self.ssm = ssm
+        self.est_params = est_params if est_params is not None else api.make_est_params()
+        self.seed = int(seed)
+        self.frame = 0
+        self.cells = api.BatchTracker(cell_params)
+        self.cells.grid_enable()
+        self.n_trackers = n
+        self.corners = None
+        self.pts = None
+        self.ssm_update = None
+        self.pix_mask = np.ones(n, dtype=np.uint8)
+        self.last_estimate = None
+
+    # the region's sample points after ssm.setCorners / ssm.initialize (ProjectiveBase.cc:27-39, Homography.cc:50-71)
+    def _set_corners(self, corners):
+        self.corners = np.array(corners, dtype=np.float64).reshape(2, 4)
+        self.pts = pts_from_corners(self.corners, self.resx, self.resy)
+
+    def cell_corners(self):
+        """GridTracker::resetTrackers (GridTracker.cc:345-392): the region of every patch tracker, (P, 2, 4)"""
+        out = np.empty((self.n_trackers, 2, 4))
+        for t in range(self.n_trackers):
+            r, c = divmod(t, self.gx)
+            if self.resx == self.gx + 1:
+                w = self.gx + 1
+                ids = [r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c]
+                pc = self.pts[:, ids]
+            else:
+                # with resx = grid_size_x the reference still indexes the (grid_size + 1)-wide table (GridTracker.cc:361-371):
+                # only the fixed-size branch below is meaningful there
+                pc = None
+            if not self.dyn_patch_size:
+                centroid = self.pts[:, t].copy()
+                if self.patch_centroid_inside:
+                    centroid = pc.sum(axis=1) / 4.0
+                x0, y0 = centroid[0] - self.patch_size_x / 2.0, centroid[1] - self.patch_size_y / 2.0
+                pc = np.array([[x0, x0 + self.patch_size_x, x0 + self.patch_size_x, x0],
+                               [y0, y0, y0 + self.patch_size_y, y0 + self.patch_size_y]])
+            out[t] = pc
+        return out
+
+    def _reset_trackers(self, reinit):
+        cells = self.cell_corners()
+        if reinit:
+            self.cells.initialize(cells)
+        else:
+            self.cells.setRegion(cells)
+
+    def setImage(self, img):
+        self.cells.setImage(img)
+
+    def initialize(self, corners, img=None):
+        if img is not None:
+            self.setImage(img)
+        self._set_corners(corners)
+        self._reset_trackers(True)
+
+    def setRegion(self, corners):
+        self._set_corners(corners)
+        self._reset_trackers(self.reinit_at_each_frame)
+
+    def update(self, img=None):
+        if img is not None:
+            self.setImage(img)
+        self.cells.update()
+        # every frame's estimator is a new object with a fresh seed in the reference (SSMEstimator.cc:22-24); here seed + frame
+        self.frame += 1
+        ep = api.EstParams.from_buffer_copy(self.est_params)
+        ep.seed = self.seed + self.frame
+        est = self.cells.grid_estimate(self.ssm, ep)
+        self.last_estimate = est
+        self.ssm_update, self.pix_mask = est["state_update"], est["mask"]
+        self._set_corners(apply_warp_to_corners(self.ssm, self.corners, self.ssm_update))
+        if self.reset_at_each_frame:
+            self._reset_trackers(self.reinit_at_each_frame)
+        else:
+            self.cells.grid_commit()
+        return self.getRegion()
+
+    def getRegion(self):
+        return self.corners.copy()
+
+    def close(self):
+        self.cells.close()

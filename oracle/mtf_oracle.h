@@ -166,6 +166,26 @@ int orc_pf_n_normals(const orc_pf *f);
 /* particle_states[curr_set_id], particle_wts, particle_cum_wts (any may be NULL); returns max_wt_id */
 int orc_pf_get_particles(const orc_pf *f, double *states, double *wts, double *cum, int *resampled);
 
+/* robust warp estimation from point pairs (mtf_oracle_est.cpp): SSM::estimateWarpFromPts of Homography / Affine, i.e.
+ * estimateHomography / estimateAffine (SSM/src/{SSMEstimator,HomographyEstimator,AffineEstimator}.cc).  method follows
+ * SSMEstimatorParams::EstType (SSMEstimatorParams.h:11); seed feeds cvRNG (the reference seeds from random_device). */
+enum { ORC_EST_RANSAC = 0, ORC_EST_LMEDS = 1, ORC_EST_LEAST_SQUARES = 2 };
+typedef struct orc_est_params {
+	int method;
+	double ransac_reproj_thresh;
+	int n_model_pts, refine, max_iters, max_subset_attempts;
+	double confidence;
+	int lm_max_iters;
+	unsigned long long seed;
+} orc_est_params;
+void orc_est_default_params(orc_est_params *p);
+int orc_estimate_warp(int ssm, const float *in_pts, const float *out_pts, int n, const orc_est_params *ep,
+	double *warp9, unsigned char *mask, double *state_update, int *info4);
+int orc_est_subsets(const float *in_pts, const float *out_pts, int n, int model_points, int max_attempts, unsigned long long seed,
+	int n_subsets, int *idx);
+unsigned orc_cv_rand_int(unsigned long long *state);
+void orc_sym_eigen(const double *A, int n, double *V_rows, double *w_desc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,16 @@ class OrcPFParams(C.Structure):
                 ("ssm_sigma", C.c_double * 8), ("ssm_mean", C.c_double * 8), ("corner_based_sampling", C.c_int)]
 
 
+class OrcEstParams(C.Structure):
+    """orc_est_params: SSMEstimatorParams (SSM/src/SSMEstimatorParams.cc) + the cvRNG seed"""
+    _fields_ = [("method", C.c_int), ("ransac_reproj_thresh", C.c_double), ("n_model_pts", C.c_int), ("refine", C.c_int),
+                ("max_iters", C.c_int), ("max_subset_attempts", C.c_int), ("confidence", C.c_double),
+                ("lm_max_iters", C.c_int), ("seed", C.c_ulonglong)]
+
+
+EST_METHOD = {"ransac": 0, "lmeds": 1, "least_squares": 2}
+
+
 class OrcIterLog(C.Structure):
     _fields_ = [("f", C.c_double), ("jacobian", C.c_double * 8), ("hessian", C.c_double * 64),
                 ("state_update", C.c_double * 8), ("corners", C.c_double * 8),
@@ -43,7 +53,7 @@ class OrcIterLog(C.Structure):
 
 def build():
     """(Re)build the oracle shared library if its sources are newer than the binary."""
-    src = [os.path.join(_ORACLE_DIR, f) for f in ("mtf_oracle.cpp", "mtf_oracle.h", "Makefile")]
+    src = [os.path.join(_ORACLE_DIR, f) for f in ("mtf_oracle.cpp", "mtf_oracle_est.cpp", "mtf_oracle.h", "Makefile")]
     if os.path.exists(_LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(_LIB_PATH) for s in src):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _ORACLE_DIR], stdout=subprocess.DEVNULL)
@@ -105,6 +115,12 @@ def lib():
     L.orc_pf_get_state.argtypes = [C.c_void_p, dp]
     L.orc_pf_n_normals.argtypes = [C.c_void_p]; L.orc_pf_n_normals.restype = C.c_int
     L.orc_pf_get_particles.argtypes = [C.c_void_p, dp, dp, dp, ip]; L.orc_pf_get_particles.restype = C.c_int
+    L.orc_est_default_params.argtypes = [C.POINTER(OrcEstParams)]
+    L.orc_estimate_warp.argtypes = [C.c_int, fp, fp, C.c_int, C.POINTER(OrcEstParams), dp, C.POINTER(C.c_ubyte), dp, ip]
+    L.orc_estimate_warp.restype = C.c_int
+    L.orc_est_subsets.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_int, ip]; L.orc_est_subsets.restype = C.c_int
+    L.orc_cv_rand_int.argtypes = [C.POINTER(C.c_ulonglong)]; L.orc_cv_rand_int.restype = C.c_uint
+    L.orc_sym_eigen.argtypes = [dp, C.c_int, dp, dp]
     _lib = L
     return L
 
@@ -385,3 +401,144 @@ class OraclePF:
         st = np.empty((self.n, self.S)); w = np.empty(self.n); cw = np.empty(self.n); r = C.c_int(0)
         mx = self._L.orc_pf_get_particles(self._h, _dp(st), _dp(w), _dp(cw), C.byref(r))
         return st, w, cw, mx, bool(r.value)
+
+
+def make_est_params(method="ransac", seed=0, **kw):
+    """SSMEstimatorParams defaults (SSMEstimatorParams.cc:5-13) with overrides"""
+    q = OrcEstParams()
+    lib().orc_est_default_params(C.byref(q))
+    q.method = EST_METHOD[method] if isinstance(method, str) else int(method)
+    q.seed = seed
+    for k, v in kw.items():
+        if not hasattr(q, k):
+            raise KeyError(k)
+        setattr(q, k, v)
+    return q
+
+
+def estimate_warp(ssm, in_pts, out_pts, est_params):
+    """SSM::estimateWarpFromPts for Homography / Affine.  in_pts, out_pts: n x 2 (cv::Point2f).  est_params: any structure
+    with the OrcEstParams field names.  Returns dict(ok, warp 3x3, mask, state_update, drawn, n_inliers, lm_evals)."""
+    L = lib()
+    q = OrcEstParams()
+    for name, _ in OrcEstParams._fields_:
+        setattr(q, name, getattr(est_params, name))
+    a = np.ascontiguousarray(in_pts, dtype=np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(out_pts, dtype=np.float32).reshape(-1, 2)
+    n = a.shape[0]
+    S = 8 if SSM.get(ssm, ssm) == 0 else 6
+    warp = np.zeros(9); mask = np.zeros(n, dtype=np.uint8); su = np.zeros(S); info = np.zeros(4, dtype=np.int32)
+    rc = L.orc_estimate_warp(SSM.get(ssm, ssm), _fp(a), _fp(b), n, C.byref(q), _dp(warp),
+                             mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(su), info.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc < 0:
+        raise ValueError("orc_estimate_warp: invalid arguments")
+    return {"ok": bool(rc), "warp": warp.reshape(3, 3), "mask": mask, "state_update": su, "drawn": int(info[1]),
+            "n_inliers": int(info[2]), "lm_evals": int(info[3])}
+
+
+def est_subsets(in_pts, out_pts, model_points, max_attempts, seed, n_subsets):
+    a = np.ascontiguousarray(in_pts, dtype=np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(out_pts, dtype=np.float32).reshape(-1, 2)
+    idx = np.zeros((n_subsets, model_points), dtype=np.int32)
+    k = lib().orc_est_subsets(_fp(a), _fp(b), a.shape[0], model_points, max_attempts, seed, n_subsets,
+                              idx.ctypes.data_as(C.POINTER(C.c_int)))
+    return k, idx
+
+
+def cv_rand_ints(seed, n):
+    st = C.c_ulonglong(seed if seed else 0xFFFFFFFFFFFFFFFF)
+    return np.array([lib().orc_cv_rand_int(C.byref(st)) for _ in range(n)], dtype=np.uint32)
+
+
+def sym_eigen(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    V = np.zeros((n, n)); w = np.zeros(n)
+    lib().orc_sym_eigen(_dp(A), n, _dp(V), _dp(w))
+    return w, V
+
+
+class OracleGrid:
+    """GridTracker<SSM> (SM/src/GridTracker.cc:232-285, 345-392) restated on the oracle's own pieces: one OracleTracker per
+    cell, orc_estimate_warp for ssm.estimateWarpFromPts, orc_homography_dlt / orc_norm_unit_square_pts for ssm.setCorners.
+    fb_err_thresh = 0, no pyramids.  est_params: any structure with the OrcEstParams fields; frame t uses seed + t."""
+
+    def __init__(self, cell_params, grid_size_x, grid_size_y, patch_size_x, patch_size_y, reset_at_each_frame=1, dyn_patch_size=0,
+                 patch_centroid_inside=True, ssm="homography", est_params=None, seed=1):
+        self.gx, self.gy = grid_size_x, grid_size_y
+        self.n = grid_size_x * grid_size_y
+        self.psx, self.psy = float(patch_size_x), float(patch_size_y)
+        self.reset, self.reinit = int(reset_at_each_frame), int(reset_at_each_frame) == 1
+        self.dyn, self.inside = int(dyn_patch_size), bool(patch_centroid_inside)
+        self.resx, self.resy = (self.gx + 1, self.gy + 1) if (self.dyn or self.inside) else (self.gx, self.gy)
+        self.ssm = ssm
+        self.est_params = est_params if est_params is not None else make_est_params()
+        self.seed, self.frame = seed, 0
+        self.trackers = [OracleTracker(cell_params) for _ in range(self.n)]
+        self.prev_pts = np.zeros((self.n, 2), dtype=np.float32)
+        self.curr_pts = np.zeros((self.n, 2), dtype=np.float32)
+        self.last = None
+
+    @staticmethod
+    def _centroid(c):
+        c = np.asarray(c, dtype=np.float64).reshape(2, 4)
+        return np.array([np.float32((c[0, 0] + c[0, 1] + c[0, 2] + c[0, 3]) / 4.0), np.float32((c[1, 0] + c[1, 1] + c[1, 2] + c[1, 3]) / 4.0)],
+                        dtype=np.float32)
+
+    def _set_corners(self, corners):
+        self.corners = np.array(corners, dtype=np.float64).reshape(2, 4)
+        bp, bc = norm_unit_square_pts(self.resx, self.resy)
+        H = homography_dlt(bc, self.corners)
+        q = H @ np.vstack([bp.T, np.ones(bp.shape[0])])
+        self.pts = q[:2] / q[2]
+
+    def _reset(self, reinit):
+        for t in range(self.n):
+            r, c = divmod(t, self.gx)
+            pc = None
+            if self.resx == self.gx + 1:
+                w = self.gx + 1
+                pc = self.pts[:, [r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c]]
+            if not self.dyn:
+                cen = self.pts[:, t].copy()
+                if self.inside:
+                    cen = np.array([(pc[0, 0] + pc[0, 1] + pc[0, 2] + pc[0, 3]) / 4.0, (pc[1, 0] + pc[1, 1] + pc[1, 2] + pc[1, 3]) / 4.0])
+                x0, y0 = cen[0] - self.psx / 2.0, cen[1] - self.psy / 2.0
+                pc = np.array([[x0, x0 + self.psx, x0 + self.psx, x0], [y0, y0, y0 + self.psy, y0 + self.psy]])
+            if reinit:
+                self.trackers[t].initialize(pc)
+            else:
+                self.trackers[t].set_region(pc)
+            self.prev_pts[t] = self._centroid(self.trackers[t].corners())
+
+    def set_image(self, img):
+        for t in self.trackers:
+            t.set_image(img)
+
+    def initialize(self, corners):
+        self._set_corners(corners)
+        self._reset(True)
+
+    def update(self):
+        for t in range(self.n):
+            self.trackers[t].update()
+            self.curr_pts[t] = self._centroid(self.trackers[t].corners())
+        self.frame += 1
+        q = OrcEstParams()
+        for name, _ in OrcEstParams._fields_:
+            setattr(q, name, getattr(self.est_params, name))
+        q.seed = self.seed + self.frame
+        est = estimate_warp(self.ssm, self.prev_pts, self.curr_pts, q)
+        self.last = est
+        s = est["state_update"]
+        if self.ssm == "homography":
+            W = np.array([[1 + s[0], s[1], s[2]], [s[3], 1 + s[4], s[5]], [s[6], s[7], 1.0]])
+        else:
+            W = np.array([[1 + s[2], s[3], s[0]], [s[4], 1 + s[5], s[1]], [0, 0, 1.0]])
+        qh = W @ np.vstack([self.corners, np.ones(4)])
+        self._set_corners(qh[:2] / qh[2])
+        if self.reset:
+            self._reset(self.reinit)
+        else:
+            self.prev_pts[:] = self.curr_pts
+        return self.corners.copy()

@@ -31,16 +31,17 @@ def test_header_is_plain_c_and_structs_match(tmp_path):
     from mtf_b200 import api
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mtf_b200.h"\n'
-                    'int main(void){ printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(mtfb_params), sizeof(mtfb_iter_log), '
+                    'int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mtfb_params), sizeof(mtfb_iter_log), '
                     'offsetof(mtfb_params, epsilon), offsetof(mtfb_iter_log, rejected), sizeof(mtfb_pf_params), '
-                    'offsetof(mtfb_pf_params, seed)); return 0; }\n')
+                    'offsetof(mtfb_pf_params, seed), sizeof(mtfb_est_params), offsetof(mtfb_est_params, seed)); return 0; }\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(prog), "-o", str(exe)])
-    a, b, c, d, e, f = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c, d, e, f, g, h = map(int, subprocess.check_output([str(exe)]).split())
     assert a == C.sizeof(api.Params) and b == C.sizeof(api.IterLog)
     assert c == api.Params.epsilon.offset and d == api.IterLog.rejected.offset
     assert e == C.sizeof(api.PFParams) and f == api.PFParams.seed.offset
+    assert g == C.sizeof(api.EstParams) and h == api.EstParams.seed.offset
 
 
 def test_default_params_and_loud_failure_without_gpu():

@@ -1,0 +1,392 @@
+"""Robust warp estimation from point pairs: ssm.estimateWarpFromPts of Homography / Affine, the
+step GridTracker::update runs after its cells (SM/src/GridTracker.cc:253-269).
+
+CPU: the oracle's restatement (oracle/mtf_oracle_est.cpp) against OpenCV 4's generator / findHomography / estimateAffine2D, NumPy
+and its own invariants; the host-side pieces of mtf_b200/grid.py against the oracle's.
+GPU: mtfb_estimate_warp_from_pts / mtfb_grid_estimate / mtf_b200.grid.GridTracker through the C ABI against the oracle on the same
+points and seeds.  Bar: the hypotheses drawn, the inlier mask and the inlier count identical; the estimated warp to 1e-6 px on the
+points it maps (the device runs inverse iteration where the oracle runs a Jacobi eigen-solver, and an elimination where it runs
+an SVD: same solutions, different rounding)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_lib as O
+
+try:
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+H_TRUE = np.array([[1.02, 0.03, 5.0], [-0.02, 0.98, -3.0], [1e-5, -2e-5, 1.0]])
+A_TRUE = np.array([[1.03, -0.04, 6.5], [0.05, 0.97, -2.25], [0, 0, 1.0]])
+
+
+def make_points(n=1024, warp=H_TRUE, noise=0.3, n_outliers=150, seed=0, lo=50.0, hi=950.0):
+    rng = np.random.default_rng(seed)
+    P = rng.uniform(lo, hi, (n, 2)).astype(np.float32)
+    Q = np.c_[P, np.ones(n)] @ warp.T
+    Q = (Q[:, :2] / Q[:, 2:]).astype(np.float32)
+    Q = Q + rng.normal(0, noise, (n, 2)).astype(np.float32)
+    out = rng.choice(n, n_outliers, replace=False) if n_outliers else np.zeros(0, dtype=int)
+    if n_outliers:
+        d = rng.uniform(40, 120, (n_outliers, 2)) * rng.choice([-1, 1], (n_outliers, 2))
+        Q[out] += d.astype(np.float32)
+    return P, Q.astype(np.float32), np.sort(out)
+
+
+def apply(W, pts):
+    q = np.c_[pts, np.ones(len(pts))] @ np.asarray(W).reshape(3, 3).T
+    return q[:, :2] / q[:, 2:]
+
+
+PROBE = np.array([[50.0, 50], [950, 50], [950, 950], [50, 950], [500, 500], [250, 700]])
+
+
+# ------------------------------------------------------------------------------------------------------------------- CPU
+@pytest.mark.skipif(cv2 is None, reason="OpenCV not importable")
+def test_cv_rng_stream_is_opencvs():
+    """cvRandInt restated (multiply-with-carry) against OpenCV's own generator: randu on uint8 with range 256 hands out the
+    bytes of consecutive RNG::next() words"""
+    for seed in (12345, 1, 0xDEADBEEF12345):
+        cv2.setRNGSeed(seed & 0x7FFFFFFF)
+        a = np.zeros((1, 64), np.uint8)
+        cv2.randu(a, 0, 256)
+        mine = O.cv_rand_ints(seed & 0x7FFFFFFF, 16)
+        assert np.array_equal(a.ravel(), mine.view(np.uint8))
+
+
+def test_symmetric_eigen_against_numpy():
+    rng = np.random.default_rng(1)
+    for n in (6, 8, 9):
+        A = rng.standard_normal((n, n)); A = A @ A.T
+        w, V = O.sym_eigen(A)
+        w2, V2 = np.linalg.eigh(A)
+        assert np.allclose(w, w2[::-1], rtol=1e-12, atol=1e-12)
+        for i in range(n):
+            assert np.allclose(np.abs(V[i]), np.abs(V2[:, n - 1 - i]), atol=1e-9)
+
+
+@pytest.mark.skipif(cv2 is None, reason="OpenCV not importable")
+def test_least_squares_homography_and_lm_against_opencv():
+    """method 0: normalised DLT on all points + LM refinement; OpenCV 4's findHomography(method=0) minimises the same
+    reprojection error from the same start"""
+    P, Q, _ = make_points(400, noise=0.5, n_outliers=0, seed=3)
+    r = O.estimate_warp("homography", P, Q, O.make_est_params("least_squares"))
+    Hc, _ = cv2.findHomography(P, Q, 0)
+    assert r["ok"] and r["lm_evals"] > 2
+    assert np.abs(apply(r["warp"], PROBE) - apply(Hc, PROBE)).max() < 1e-4
+    assert np.abs(apply(r["warp"], PROBE) - apply(H_TRUE, PROBE)).max() < 0.2
+    # without the refinement: the plain normalised DLT, against NumPy's SVD of the same system
+    r0 = O.estimate_warp("homography", P, Q, O.make_est_params("least_squares", refine=0))
+    M, m = P.astype(np.float64), Q.astype(np.float64)
+    cM, cm = M.mean(0), m.mean(0)
+    sM, sm = len(M) / np.abs(M - cM).sum(0), len(m) / np.abs(m - cm).sum(0)
+    X, x = (M - cM) * sM, (m - cm) * sm
+    L = np.zeros((2 * len(M), 9))
+    L[0::2] = np.c_[X, np.ones(len(M)), np.zeros((len(M), 3)), -x[:, :1] * X, -x[:, :1]]
+    L[1::2] = np.c_[np.zeros((len(M), 3)), X, np.ones(len(M)), -x[:, 1:] * X, -x[:, 1:]]
+    h = np.linalg.svd(L)[2][-1].reshape(3, 3)
+    Hn = np.array([[1 / sm[0], 0, cm[0]], [0, 1 / sm[1], cm[1]], [0, 0, 1]]) @ h @ np.array([[sM[0], 0, -cM[0] * sM[0]], [0, sM[1], -cM[1] * sM[1]], [0, 0, 1]])
+    Hn /= Hn[2, 2]
+    assert np.abs(apply(r0["warp"], PROBE) - apply(Hn, PROBE)).max() < 1e-8
+
+
+def test_least_squares_affine_against_numpy():
+    P, Q, _ = make_points(300, warp=A_TRUE, noise=0.4, n_outliers=0, seed=4)
+    r = O.estimate_warp("affine", P, Q, O.make_est_params("least_squares", refine=0))
+    B = np.c_[P.astype(np.float64), np.ones(len(P))]
+    sol = np.linalg.lstsq(B, Q.astype(np.float64), rcond=None)[0].T
+    assert np.allclose(r["warp"][:2], sol, rtol=1e-10, atol=1e-9)
+    assert np.array_equal(r["warp"][2], [0, 0, 1])
+    # the refinement of a linear model starts at its optimum: LM must not move it
+    r1 = O.estimate_warp("affine", P, Q, O.make_est_params("least_squares"))
+    assert np.abs(apply(r1["warp"], PROBE) - apply(r["warp"], PROBE)).max() < 1e-7
+    # Affine::estimateWarpFromPts (Affine.cc:359-369)
+    W = r["warp"]
+    assert np.allclose(r["state_update"], [W[0, 2], W[1, 2], W[0, 0] - 1, W[0, 1], W[1, 0], W[1, 1] - 1])
+
+
+@pytest.mark.parametrize("method", ["ransac", "lmeds"])
+@pytest.mark.parametrize("ssm", ["homography", "affine"])
+def test_robust_methods_find_the_inliers(method, ssm):
+    warp = H_TRUE if ssm == "homography" else A_TRUE
+    P, Q, out = make_points(1024, warp=warp, noise=0.3, n_outliers=150, seed=5)
+    r = O.estimate_warp(ssm, P, Q, O.make_est_params(method, seed=2024))
+    truth = np.ones(1024, np.uint8); truth[out] = 0
+
+    def found(res):
+        if method == "ransac":
+            return np.array_equal(res["mask"], truth) and res["n_inliers"] == 1024 - 150
+        # LMedS keeps what lies within 2.5 * 1.4826 * (1 + 5 / (n - 4)) * sqrt(median) (SSMEstimator.cc:208-212): no planted
+        # outlier, and all but the tail of the noise
+        return not np.any(res["mask"][out]) and res["n_inliers"] >= 0.97 * (1024 - 150) and res["n_inliers"] == res["mask"].sum()
+
+    assert r["ok"] and found(r)
+    assert np.abs(apply(r["warp"], PROBE) - apply(warp, PROBE)).max() < 0.2
+    if method == "ransac":
+        assert 1 <= r["drawn"] < 60          # the adaptive count: 85 % inliers need ~8 hypotheses at 99.5 % confidence
+    else:
+        assert r["drawn"] == 55              # cvRound(log(1 - 0.995) / log(1 - 0.55^4))
+    # Homography::estimateWarpFromPts (Homography.cc:885-897)
+    if ssm == "homography":
+        W = r["warp"]
+        assert np.allclose(r["state_update"], [W[0, 0] - 1, W[0, 1], W[0, 2], W[1, 0], W[1, 1] - 1, W[1, 2], W[2, 0], W[2, 1]])
+    # a different stream draws different subsets and lands on the same answer
+    r2 = O.estimate_warp(ssm, P, Q, O.make_est_params(method, seed=77))
+    assert found(r2)
+    assert np.abs(apply(r2["warp"], PROBE) - apply(r["warp"], PROBE)).max() < (1e-6 if method == "ransac" else 0.05)
+
+
+@pytest.mark.skipif(cv2 is None, reason="OpenCV not importable")
+def test_ransac_mask_against_opencv():
+    P, Q, out = make_points(600, noise=0.2, n_outliers=90, seed=6)
+    r = O.estimate_warp("homography", P, Q, O.make_est_params("ransac", seed=9, ransac_reproj_thresh=5.0))
+    Hc, mc = cv2.findHomography(P, Q, cv2.RANSAC, 5.0)
+    assert np.array_equal(mc.ravel(), r["mask"])
+    assert np.abs(apply(r["warp"], PROBE) - apply(Hc, PROBE)).max() < 1e-3
+    Ac, ma = cv2.estimateAffine2D(P, Q, method=cv2.RANSAC, ransacReprojThreshold=5.0)
+    Pa, Qa, outa = make_points(600, warp=A_TRUE, noise=0.2, n_outliers=90, seed=6)
+    ra = O.estimate_warp("affine", Pa, Qa, O.make_est_params("ransac", seed=9, ransac_reproj_thresh=5.0))
+    Ac, ma = cv2.estimateAffine2D(Pa, Qa, method=cv2.RANSAC, ransacReprojThreshold=5.0)
+    assert np.array_equal(ma.ravel(), ra["mask"])
+    assert np.abs(apply(ra["warp"], PROBE) - apply(np.vstack([Ac, [0, 0, 1]]), PROBE)).max() < 1e-3
+
+
+def test_subsets_are_distinct_non_degenerate_and_reproducible():
+    P, Q, _ = make_points(64, n_outliers=8, seed=7)
+    k, idx = O.est_subsets(P, Q, 4, 300, 4242, 200)
+    assert k == 200
+    assert all(len(set(row)) == 4 for row in idx)
+    k2, idx2 = O.est_subsets(P, Q, 4, 300, 4242, 200)
+    assert np.array_equal(idx, idx2)
+    # the indices are cvRandInt % count, duplicates redrawn (SSMEstimator.cc:236-241)
+    stream = O.cv_rand_ints(4242, 16) % 64
+    first, used = [], 0
+    while len(first) < 4:
+        v = int(stream[used]); used += 1
+        if v not in first:
+            first.append(v)
+    assert list(idx[0]) == first
+    # collinear points: every subset fails checkSubset, getSubset gives up after max_attempts
+    line = np.c_[np.arange(32, dtype=np.float32) * 3 + 1, np.arange(32, dtype=np.float32) * 2 + 5]
+    k3, _ = O.est_subsets(line, line, 4, 50, 1, 3)
+    assert k3 == 0
+    r = O.estimate_warp("homography", line, line, O.make_est_params("ransac", seed=1, max_subset_attempts=50))
+    assert not r["ok"] and np.all(r["warp"] == 0) and np.all(r["mask"] == 1)     # H = cv::Scalar(0), the mask untouched
+
+
+def test_exactly_model_points_and_argument_checks():
+    P, Q, _ = make_points(4, noise=0.0, n_outliers=0, seed=8)
+    r = O.estimate_warp("homography", P, Q, O.make_est_params("ransac", seed=3))
+    assert r["ok"] and r["drawn"] == 0 and r["lm_evals"] == 0        # method forced to 0, no refinement (:193, :205)
+    assert np.abs(apply(r["warp"], P.astype(np.float64)) - Q).max() < 1e-3
+    with pytest.raises(ValueError):
+        O.estimate_warp("homography", P[:3], Q[:3], O.make_est_params("ransac"))
+    with pytest.raises(ValueError):
+        O.estimate_warp("translation", P, Q, O.make_est_params("ransac"))
+
+
+def test_grid_host_pieces_against_the_oracles():
+    from mtf_b200 import grid
+    for resx, resy in ((5, 5), (9, 4), (33, 33)):
+        pts, nc = grid.norm_unit_square_pts(resx, resy)
+        op, oc = O.norm_unit_square_pts(resx, resy)
+        assert np.allclose(pts.T, op, atol=1e-15) and np.array_equal(nc, oc)
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        src = np.array([[100.0, 400, 420, 90], [80, 95, 380, 400]]) + rng.uniform(-20, 20, (2, 4))
+        dst = src + rng.uniform(-15, 15, (2, 4))
+        H, Ho = grid.homography_dlt(src, dst), O.homography_dlt(src, dst)
+        probe = np.c_[rng.uniform(90, 420, 20), rng.uniform(80, 400, 20)]
+        assert np.abs(apply(H, probe) - apply(Ho, probe)).max() < 1e-9
+        p = grid.pts_from_corners(dst, 7, 6)
+        assert np.allclose(p[:, [0, 6, 41, 35]], dst, atol=1e-9)             # the grid's own corners
+    s = rng.uniform(-0.01, 0.01, 8)
+    c = grid.apply_warp_to_corners("homography", src, s)
+    W = np.array([[1 + s[0], s[1], s[2]], [s[3], 1 + s[4], s[5]], [s[6], s[7], 1]])
+    assert np.allclose(c.T, apply(W, src.T))
+    c = grid.apply_warp_to_corners("affine", src, s[:6])
+    W = np.array([[1 + s[2], s[3], s[0]], [s[4], 1 + s[5], s[1]], [0, 0, 1]])
+    assert np.allclose(c.T, apply(W, src.T))
+
+
+# ------------------------------------------------------------------------------------------------------------------- GPU
+def _ctx():
+    from mtf_b200 import api
+    return api.BatchTracker(api.make_params("ssd", "homography", "fclk", n_patches=1, resx=10, resy=10))
+
+
+def _same(dev, orc, tol=1e-6):
+    assert dev["ok"] == orc["ok"]
+    assert dev["drawn"] == orc["drawn"]
+    assert np.array_equal(dev["mask"], orc["mask"])
+    assert dev["n_inliers"] == orc["n_inliers"]
+    if orc["ok"]:
+        assert np.abs(apply(dev["warp"], PROBE) - apply(orc["warp"], PROBE)).max() < tol
+        assert np.allclose(dev["state_update"], orc["state_update"], rtol=1e-5, atol=1e-7)
+    else:
+        assert np.all(dev["warp"] == 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["ransac", "lmeds", "least_squares"])
+@pytest.mark.parametrize("ssm", ["homography", "affine"])
+def test_device_estimator_matches_oracle(method, ssm):
+    from mtf_b200 import api
+    t = _ctx()
+    warp = H_TRUE if ssm == "homography" else A_TRUE
+    for seed, n, n_out, noise in ((11, 1024, 150, 0.3), (12, 1024, 400, 0.5), (13, 257, 30, 0.1), (14, 1000, 0, 1.0), (15, 2500, 700, 0.4)):
+        P, Q, _ = make_points(n, warp=warp, noise=noise, n_outliers=n_out, seed=seed)
+        dev = t.estimate_warp_from_pts(ssm, P, Q, api.make_est_params(method, seed=1000 + seed))
+        orc = O.estimate_warp(ssm, P, Q, O.make_est_params(method, seed=1000 + seed))
+        _same(dev, orc)
+        # the refinement starts at the least-squares optimum: its accept / reject decisions compare error norms that differ in
+        # the last bits, so the number of evaluations is not comparable, only that it ran and stopped
+        assert (dev["lm_evals"] > 0) == (orc["lm_evals"] > 0) and dev["lm_evals"] <= 10 * 19 + 2
+    t.close()
+
+
+@pytest.mark.gpu
+def test_device_estimator_options_and_edges():
+    from mtf_b200 import api
+    t = _ctx()
+    P, Q, _ = make_points(800, noise=0.3, n_outliers=200, seed=21)
+    for kw in (dict(refine=0), dict(n_model_pts=5), dict(n_model_pts=8), dict(ransac_reproj_thresh=2.0), dict(ransac_reproj_thresh=-1.0),
+               dict(confidence=0.9), dict(max_iters=3), dict(lm_max_iters=1), dict(lm_max_iters=30)):
+        for method in ("ransac", "lmeds"):
+            dev = t.estimate_warp_from_pts("homography", P, Q, api.make_est_params(method, seed=5, **kw))
+            orc = O.estimate_warp("homography", P, Q, O.make_est_params(method, seed=5, **kw))
+            _same(dev, orc)
+    # the default generator state (seed 0), affine with three-point models
+    Pa, Qa, _ = make_points(500, warp=A_TRUE, noise=0.3, n_outliers=100, seed=22)
+    _same(t.estimate_warp_from_pts("affine", Pa, Qa, api.make_est_params("ransac", seed=0, n_model_pts=3)),
+          O.estimate_warp("affine", Pa, Qa, O.make_est_params("ransac", seed=0, n_model_pts=3)))
+    # exactly n_model_pts points: plain fit, no refinement
+    P4, Q4, _ = make_points(4, noise=0.0, n_outliers=0, seed=8)
+    _same(t.estimate_warp_from_pts("homography", P4, Q4, api.make_est_params("ransac", seed=3)),
+          O.estimate_warp("homography", P4, Q4, O.make_est_params("ransac", seed=3)), tol=1e-5)
+    # collinear points: no subset passes checkSubset -> failure, zero matrix, mask of ones
+    line = np.c_[np.arange(32, dtype=np.float32) * 3 + 1, np.arange(32, dtype=np.float32) * 2 + 5]
+    dev = t.estimate_warp_from_pts("homography", line, line, api.make_est_params("ransac", seed=1, max_subset_attempts=50))
+    assert not dev["ok"] and np.all(dev["warp"] == 0) and np.all(dev["mask"] == 1)
+    # more outliers than any model explains at this threshold: a model through a handful of points.  The hypotheses, the mask
+    # and the count are still the oracle's; the refinement of 8 parameters on ~5 points is ill-posed away from those points, so
+    # the two refined models are compared where they are determined -- by the error they leave on their inliers
+    Pn, Qn, _ = make_points(300, noise=0.3, n_outliers=280, seed=23)
+    dev = t.estimate_warp_from_pts("homography", Pn, Qn, api.make_est_params("ransac", seed=6, ransac_reproj_thresh=1.0, max_iters=200))
+    orc = O.estimate_warp("homography", Pn, Qn, O.make_est_params("ransac", seed=6, ransac_reproj_thresh=1.0, max_iters=200))
+    assert dev["ok"] and orc["ok"] and dev["drawn"] == orc["drawn"] == 200 and np.array_equal(dev["mask"], orc["mask"])
+    sel = orc["mask"] != 0
+    e_dev = np.sum((apply(dev["warp"], Pn[sel]) - Qn[sel]) ** 2); e_orc = np.sum((apply(orc["warp"], Pn[sel]) - Qn[sel]) ** 2)
+    assert e_dev <= e_orc * 1.05 + 1e-6
+    # ... and without the refinement the two fits agree everywhere
+    kw = dict(seed=6, ransac_reproj_thresh=1.0, max_iters=200, refine=0)
+    _same(t.estimate_warp_from_pts("homography", Pn, Qn, api.make_est_params("ransac", **kw)),
+          O.estimate_warp("homography", Pn, Qn, O.make_est_params("ransac", **kw)), tol=1e-5)
+    t.close()
+
+
+@pytest.mark.gpu
+def test_device_estimator_errors():
+    from mtf_b200 import api
+    t = _ctx()
+    P, Q, _ = make_points(16, n_outliers=2, seed=1)
+    for args, status in ((("translation", P, Q, api.make_est_params()), 2),
+                         (("homography", P[:3], Q[:3], api.make_est_params()), 1),
+                         (("homography", P, Q, api.make_est_params(n_model_pts=9)), 2),
+                         (("homography", P, Q, api.make_est_params(n_model_pts=3)), 1),
+                         (("homography", P, Q, api.make_est_params(method=7)), 1)):
+        with pytest.raises(api.MTFError) as e:
+            t.estimate_warp_from_pts(*args)
+        assert e.value.status == status
+    bad = Q.copy(); bad[3, 1] = np.nan
+    with pytest.raises(api.MTFError):
+        t.estimate_warp_from_pts("homography", P, bad, api.make_est_params())
+    with pytest.raises(api.MTFError) as e:
+        t.grid_estimate("homography", api.make_est_params())       # mtfb_grid_enable first
+    assert e.value.status == 3
+    t.close()
+
+
+def _grid_setup(ssm_cells="translation", grid=6, res=20):
+    from mtf_b200 import synth
+    frames, _ = synth.make_sequence(4, 384, 384)
+    kw = dict(resx=res, resy=res, max_iters=10)
+    return frames, kw
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(ssm="homography", reset=1), dict(ssm="affine", reset=1), dict(ssm="homography", reset=0),
+                                 dict(ssm="homography", reset=2), dict(ssm="homography", reset=1, inside=False),
+                                 dict(ssm="homography", reset=1, dyn=1), dict(ssm="homography", reset=1, method="lmeds")])
+def test_grid_tracker_against_oracle_grid(cfg):
+    """GridTracker::initialize / update over three frames: cells (SSD + Translation + ICLK, the reference's grid default is a
+    2-dof cell model) -> centroids -> RANSAC -> the region's corners -> the cells' next regions"""
+    from mtf_b200 import api, grid, synth
+    frames, _ = synth.make_sequence(4, 384, 384)
+    g = 6
+    region = np.array([[90.0, 300, 305, 85], [80, 84, 290, 296]])
+    method = cfg.get("method", "ransac")
+    common = dict(grid_size_x=g, grid_size_y=g, patch_size_x=24, patch_size_y=24, reset_at_each_frame=cfg["reset"],
+                  dyn_patch_size=cfg.get("dyn", 0), patch_centroid_inside=cfg.get("inside", True), ssm=cfg["ssm"], seed=31)
+    cell_kw = dict(resx=16, resy=16, max_iters=10)
+    gt = grid.GridTracker(api.make_params("ssd", "translation", "iclk", n_patches=g * g, **cell_kw),
+                          est_params=api.make_est_params(method, ransac_reproj_thresh=2.0), **common)
+    og = O.OracleGrid(O.make_params("ssd", "translation", "iclk", **cell_kw), est_params=O.make_est_params(method, ransac_reproj_thresh=2.0),
+                      **common)
+    gt.setImage(frames[0]); og.set_image(frames[0])
+    gt.initialize(region); og.initialize(region)
+    assert np.allclose(gt.cell_corners().reshape(-1, 8), np.array([t.corners().reshape(8) for t in og.trackers]), atol=1e-9)
+    for f in frames[1:]:
+        gt.setImage(f); og.set_image(f)
+        c = gt.update(); oc = og.update()
+        prev, curr = gt.cells.grid_pts()
+        assert np.array_equal(curr, og.curr_pts) or np.abs(curr - og.curr_pts).max() < 1e-4     # float centroids of 1e-9-equal corners
+        assert gt.last_estimate["ok"] and og.last["ok"]
+        assert gt.last_estimate["drawn"] == og.last["drawn"]
+        assert np.array_equal(gt.pix_mask, og.last["mask"])
+        assert np.abs(c - oc).max() < 1e-4
+    # the region follows the sequence's motion: the estimate is not the identity
+    assert np.abs(c - region).max() > 0.05
+    gt.close()
+
+
+@pytest.mark.gpu
+def test_grid_centroids_and_commit():
+    from mtf_b200 import api, synth
+    frames, _ = synth.make_sequence(2, 384, 384)
+    cs = synth.make_patches(64, 30.0, 384, 384)
+    t = api.BatchTracker(api.make_params("ssd", "homography", "fclk", n_patches=64, resx=20, resy=20))
+    t.grid_enable()
+    t.setImage(frames[0]); t.initialize(cs)
+    t.setImage(frames[1]); t.update()
+    est = t.grid_estimate("homography", api.make_est_params(seed=4))
+    prev, curr = t.grid_pts()
+    c0 = np.asarray(cs).reshape(-1, 2, 4); c1 = t.getRegion().reshape(-1, 2, 4)
+    cen = lambda c: np.stack([((c[:, 0, 0] + c[:, 0, 1] + c[:, 0, 2] + c[:, 0, 3]) / 4.0), ((c[:, 1, 0] + c[:, 1, 1] + c[:, 1, 2] + c[:, 1, 3]) / 4.0)], 1).astype(np.float32)
+    assert np.array_equal(prev, cen(c0)) and np.array_equal(curr, cen(c1))
+    orc = O.estimate_warp("homography", prev, curr, O.make_est_params(seed=4))
+    _same(est, orc)
+    t.grid_commit()
+    prev2, _ = t.grid_pts()
+    assert np.array_equal(prev2, curr)
+    t.close()
+
+
+@pytest.mark.gpu
+def test_estimator_at_full_size():
+    """8192 points (config 4's batch): the properties that do not need the oracle -- the inliers are the planted ones, the model
+    maps them within the noise, and a second run with the same seed is bit-identical"""
+    from mtf_b200 import api
+    t = _ctx()
+    P, Q, out = make_points(8192, noise=0.3, n_outliers=2000, seed=41, lo=20, hi=2000)
+    truth = np.ones(8192, np.uint8); truth[out] = 0
+    for method in ("ransac", "lmeds"):
+        a = t.estimate_warp_from_pts("homography", P, Q, api.make_est_params(method, seed=17))
+        b = t.estimate_warp_from_pts("homography", P, Q, api.make_est_params(method, seed=17))
+        assert a["ok"] and not np.any(a["mask"][out]) and (np.array_equal(a["mask"], truth) if method == "ransac" else a["n_inliers"] > 0.97 * truth.sum())
+        assert np.array_equal(a["warp"], b["warp"]) and a["drawn"] == b["drawn"]
+        assert np.abs(apply(a["warp"], PROBE) - apply(H_TRUE, PROBE)).max() < 0.1
+    _same(a, O.estimate_warp("homography", P, Q, O.make_est_params("lmeds", seed=17)))
+    t.close()
