@@ -163,17 +163,23 @@ def _gather(env, sharded, strong):
 
 # ------------------------------------------------------------------------------------------------ config 3
 def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
-    from mtf_b200 import api, sharding, workloads as W
+    """GridTracker<Homography>::update (SM/src/GridTracker.cc:247-285) with 32 x 32 ESM + NCC + Affine cells: the cells' update,
+    the warp of the region from their centroids (RANSAC + LM refinement on the device), the cells re-initialised on the frame
+    at the regions the new corners give them.  weak scaling: one such grid per GPU (the regions all-gathered per frame);
+    strong: the cells of one grid split over the GPUs (their corners all-gathered, every rank estimates)."""
+    from mtf_b200 import api, grid, sharding, workloads as W
     torch = env.torch
     frames, _ = W.sequence()
     order = W.frame_order()
-    cells_all = W.grid_cells(32, float(res))
-    n_cells = cells_all.shape[0]
+    G = W.CONFIG3["grid"]
+    n_cells = G * G
     N = res * res
     iters = 30
+    split = strong and env.world > 1
     lo, hi, n_job = _shard(env, n_cells, strong)
-    cells = cells_all[lo:hi]
     P = hi - lo
+    size = frames[0].shape[0]
+    region = np.array([[24.0, size - 25.0, size - 25.0, 24.0], [24.0, 24.0, size - 25.0, size - 25.0]])
 
     def make_local(n):
         tr = api.BatchTracker(api.make_params("ncc", "affine", "esm", n_patches=n, resx=res, resy=res, max_iters=iters, epsilon=0.0,
@@ -181,47 +187,49 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
         tr.set_stream(env.stream.cuda_stream)
         return tr
 
-    class _Dist:           # ShardedBatchTracker wants a process group; N = 1 runs without one
-        pass
-    if env.world > 1:
-        sh = sharding.ShardedBatchTracker(n_cells if strong else n_cells * env.world, make_local)
-        if not strong:
-            sh.lo, sh.hi = env.rank * n_cells, (env.rank + 1) * n_cells
+    common = dict(grid_size_x=G, grid_size_y=G, patch_size_x=res, patch_size_y=res, reset_at_each_frame=1, ssm="homography",
+                  est_params=api.make_est_params("ransac"), seed=7)
+    if split:
+        sh = sharding.ShardedBatchTracker(n_cells, make_local)
         tr = sh.local
+        gt = grid.GridTracker(None, cells=tr, shard=(sh.lo, sh.hi), gather=lambda: sh.getRegion(device=env.dev),
+                              upload=lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(env.dev), **common)
     else:
-        sh, tr = None, make_local(P)
+        tr = make_local(n_cells)
+        gt = grid.GridTracker(None, cells=tr, **common)
     d_frames = [torch.from_numpy(f).to(env.dev) for f in frames]
     pinned = [torch.from_numpy(f).pin_memory() for f in frames]
     h, w = frames[0].shape
-    d_corners = sharding.device_view(tr.device_results()[0], (P, 8), env.dev)
-    host_out = torch.empty((P, 8), dtype=torch.float64).pin_memory()
-    tr.initialize(cells, d_frames[0]); tr.synchronize()
+    regions = torch.empty((env.world, 8), dtype=torch.float64, device=env.dev) if (env.world > 1 and not split) else None
+    gt.setImage(d_frames[0]); gt.initialize(region); tr.synchronize()
     launches0 = tr.launch_count
 
+    def finish():
+        gt.finish_update()
+        if regions is not None:          # every rank learns every grid's region
+            sharding.all_gather_rows(torch.from_numpy(gt.corners.reshape(1, 8)).to(env.dev), env.world, None, out=regions)
+
     def pre(i):
-        tr.setImage(d_frames[order[i % len(order)]])
+        gt.setImage(d_frames[order[i % len(order)]])
 
     def kernel(i):
         tr.update()
 
     def post(i):
-        if env.world > 1:
-            sh.getRegion(device=env.dev)
-        tr.initialize(cells)                         # GridTracker::resetTrackers on the current frame
+        finish()
     ms, kms, win = timed_steps(env, n_warm, n_steps, (pre, post), kernel)
     launches = tr.launch_count - launches0
-    n_it = tr.n_iters()
-    finite = bool(np.isfinite(tr.getRegion()).all())
+    pre(0); kernel(0); n_it = tr.n_iters(); post(0)          # (the reset zeroes the cells' iteration counts: read them in between)
+    est = gt.last_estimate
+    finite = bool(np.isfinite(gt.corners).all())
+    drift = float(np.abs(gt.corners - region).max())
 
     def e2e_step(i):
         tr.update()                                                                  # frame i, prefetched during step i - 1
-        if env.world > 1:
-            sh.getRegion(device=env.dev)
-        host_out.copy_(d_corners, non_blocking=True)
-        tr.initialize(cells)
-        tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), h, w, w)     # overlaps the kernels above
+        finish()                                                                     # reads the estimate back: the step's result
+        tr.prefetch_image_pinned(pinned[order[(i + 1) % len(order)]].data_ptr(), h, w, w)
         env.stream.synchronize()
-    tr.initialize(cells, frames[0])
+    gt.setImage(frames[0]); gt.initialize(region)
     e2e_ms, win2 = timed_e2e(env, n_warm, n_steps, e2e_step, prime=lambda: tr.prefetch_image_pinned(pinned[order[0]].data_ptr(), h, w, w),
                              drain=tr.update)
     ms, kms, e2e_ms = env.max_over_ranks([ms, kms, e2e_ms])
@@ -231,25 +239,41 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
         "metric": "LK iters/sec (%dx%d NCC+Affine ESM, GridTracker 32x32 cells)" % (res, res), "value": total_iters / (ms * 1e-3),
         "unit": "iters/s", "n_gpus": env.world, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms / n_steps,
         "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ESM+NCC+Affine, GridTracker 32x32 = %d cells%s of %dx%d px, %d iters/frame (epsilon=0), every cell "
-                               "re-initialised on every frame, 1024x1024 f32 frames" % (n_cells, "" if strong else " per GPU", res, res, iters),
+        "config": {"workload": "GridTracker<Homography>::update: ESM+NCC+Affine cells, 32x32 = %d cells%s of %dx%d px, %d iters/frame "
+                               "(epsilon=0), region warp by RANSAC + LM from the cell centroids on the device, every cell "
+                               "re-initialised on every frame where the new region puts it, 1024x1024 f32 frames"
+                               % (n_cells, "" if strong else " per GPU", res, res, iters),
                    "l2": "flushed between timed steps (256 MB write)",
-                   "collective": "all_gather of P x 8 corners per frame from the kernel's output buffer" if env.world > 1 else "none"},
-        "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": h * w * 4, "d2h_bytes_per_step": P * 64},
+                   "collective": ("none" if env.world == 1 else "all_gather of the cells' P x 8 corners per frame from the kernel's output "
+                                  "buffer, every rank estimates" if split else "all_gather of the grids' regions per frame")},
+        "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": h * w * 4 + P * 64,
+                "d2h_bytes_per_step": 21 * 8 + n_cells},
         "gpu_launches": int(launches),
         "roofline": roofline(alg, P * iters, kms / n_steps, root, "ncc_update_kernel<Affine,ESM>",
                              "fp64-issue bound (three sweeps per pass over It kept in shared memory), not HBM bound"),
-        "valid": {"finite": finite, "n_iters_per_cell": int(n_it[0])},
+        "stages_ms_per_step": {"cells_update_kernel": kms / n_steps, "estimate_and_reset": (ms - kms) / n_steps},
+        "valid": {"finite": finite, "n_iters_per_cell": int(n_it[0]), "estimate_ok": bool(est["ok"]), "inliers": int(est["n_inliers"]),
+                  "hypotheses": int(est["drawn"]), "region_drift_px": drift},
     }
     if cpu and env.rank == 0 and env.world == 1:
         from oracle import oracle_lib as O
         cores = os.cpu_count() or 1
         n = min(n_cells, 8 * cores)
+        cells_all = gt.cell_corners()
         prm = O.make_params("ncc", "affine", "esm", resx=res, resy=res, max_iters=iters, epsilon=0.0, grad_mode=0, fast_sums=1,
                             hess_type=W.CONFIG3["hess_type"], jac_type=W.CONFIG3["jac_type"])
         it, secs, _, _ = O.batch_track(prm, frames[:3], cells_all[:n], n_threads=cores, reset_each_frame=True)
-        out["cpu_baseline"] = {"value": it / secs, "unit": "iters/s", "cores": cores, "kind": "port",
-                               "sample": "%d cells x 2 frames, %d LK iterations, re-initialised every frame, OpenMP over cells" % (n, it)}
+        # + the estimation on all the centroids, once per frame (single thread, as the reference runs it)
+        prev, curr = tr.grid_pts()
+        t0 = time.perf_counter()
+        for k in range(10):
+            O.estimate_warp("homography", prev, curr, O.make_est_params("ransac", seed=7 + k))
+        t_est = (time.perf_counter() - t0) / 10
+        per_frame = secs / 2 * (n_cells / n) + t_est
+        out["cpu_baseline"] = {"value": n_cells * iters / per_frame, "unit": "iters/s", "cores": cores, "kind": "port",
+                               "estimate_ms_per_frame": t_est * 1e3,
+                               "sample": "%d of the %d cells x 2 frames (%d LK iterations, re-initialised every frame, OpenMP over cells) scaled "
+                                         "to the grid, + estimateWarpFromPts (RANSAC + LM, one thread) on the %d centroids" % (n, n_cells, it, n_cells)}
     tr.close()
     return out
 

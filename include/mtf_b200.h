@@ -266,6 +266,10 @@ void mtfb_est_default_params(mtfb_est_params *p);
  * (GridTracker's own SSM, independent of the cells' SSM). */
 mtfb_status mtfb_estimate_warp_from_pts(mtfb_ctx *ctx, int ssm, const float *in_pts, const float *out_pts, int n,
 	const mtfb_est_params *ep, double *state_update, unsigned char *mask, double *warp, int *info);
+/* the same from two DEVICE arrays of n quadrilaterals (n x 8 doubles, x0..x3 y0..y3): the points are their centroids
+ * (utils::getCentroid, miscUtils.h:473-480).  What a multi-GPU host runs on the all-gathered corners of every rank's cells. */
+mtfb_status mtfb_estimate_warp_from_corners_device(mtfb_ctx *ctx, int ssm, const double *d_in_corners, const double *d_out_corners,
+	int n, const mtfb_est_params *ep, double *state_update, unsigned char *mask, double *warp, int *info);
 /* the same on the context's own cells without a host copy of the points: in_pts = the centroids (utils::getCentroid,
  * miscUtils.h:473-480) of the regions at the last mtfb_initialize / mtfb_set_region / mtfb_grid_commit (prev_pts,
  * GridTracker.cc:389), out_pts = the centroids of the current regions (curr_pts, :257).  mtfb_grid_enable first (it allocates the

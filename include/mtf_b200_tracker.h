@@ -116,6 +116,36 @@ public:
 		}
 		upload(); check(mtfb_update(ctx)); fetch(); updated_frame = frame_id;
 	}
+	// ---- GridTracker::update's step after its cells (SM/src/GridTracker.cc:265-280) on the device.
+	//! `ssm.estimateWarpFromPts(ssm_update, pix_mask, prev_pts, curr_pts, est_params)` (GridTracker.cc:269) for the grid's own
+	//! Homography / Affine: in_pts / out_pts = reinterpret_cast<const float*>(prev_pts.data()) of the std::vector<cv::Point2f>,
+	//! state_update = ssm_update.data(), mask = pix_mask.data().  Returns the estimator's result (false: zero update).
+	bool estimateWarpFromPts(int ssm, double *state_update, unsigned char *mask, const float *in_pts, const float *out_pts, int n,
+		const mtfb_est_params &ep){
+		int info[4];
+		check(mtfb_estimate_warp_from_pts(ctx, ssm, in_pts, out_pts, n, &ep, state_update, mask, nullptr, info));
+		return info[0] != 0;
+	}
+	//! the same without the points leaving the device: prev_pts / curr_pts are the centroids of this batch's regions at the last
+	//! initialize / setRegion / gridCommit and now (GridTracker.cc:257, :389); call gridEnable() once after construction
+	void gridEnable(){ check(mtfb_grid_enable(ctx)); }
+	bool gridEstimate(int ssm, double *state_update, unsigned char *mask, const mtfb_est_params &ep){
+		int info[4];
+		check(mtfb_grid_estimate(ctx, ssm, &ep, state_update, mask, nullptr, info));
+		return info[0] != 0;
+	}
+	//! prev_pts = curr_pts (reset_at_each_frame = 0, GridTracker.cc:276-279)
+	void gridCommit(){ check(mtfb_grid_commit(ctx)); }
+	//! mtf::SSMEstimatorParams -> mtfb_est_params (method: SSMEstimatorParams::EstType as an int); seed replaces random_device
+	static mtfb_est_params estParams(int method, double ransac_reproj_thresh, int n_model_pts, bool refine, int max_iters,
+		int max_subset_attempts, double confidence, int lm_max_iters, unsigned long long seed){
+		mtfb_est_params ep;
+		mtfb_est_default_params(&ep);
+		ep.method = method; ep.ransac_reproj_thresh = ransac_reproj_thresh; ep.n_model_pts = n_model_pts; ep.refine = refine ? 1 : 0;
+		ep.max_iters = max_iters; ep.max_subset_attempts = max_subset_attempts; ep.confidence = confidence;
+		ep.lm_max_iters = lm_max_iters; ep.seed = seed;
+		return ep;
+	}
 	//! bumped whenever the regions are refreshed from the device (initialize / setRegion / update)
 	long generation() const{ return gen; }
 	const double* region(int i) const{ return &corners[8 * (size_t)i]; }

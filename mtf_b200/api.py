@@ -93,7 +93,7 @@ EXPORTS = [
     "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_get_curr_stage_f32", "mtfb_device_results",
     "mtfb_state_size", "mtfb_debug_colpiv_qr_solve",
     "mtfb_pf_default_params", "mtfb_pf_configure", "mtfb_pf_set_random_stream", "mtfb_pf_get_random_stream", "mtfb_pf_get_particles",
-    "mtfb_est_default_params", "mtfb_estimate_warp_from_pts", "mtfb_grid_enable", "mtfb_grid_estimate", "mtfb_grid_commit",
+    "mtfb_est_default_params", "mtfb_estimate_warp_from_pts", "mtfb_estimate_warp_from_corners_device", "mtfb_grid_enable", "mtfb_grid_estimate", "mtfb_grid_commit",
     "mtfb_grid_get_pts",
 ]
 
@@ -149,6 +149,7 @@ def load_library(path=LIB_PATH):
     L.mtfb_pf_get_particles.argtypes = [vp, vp, vp, vp, vp]
     L.mtfb_est_default_params.argtypes = [C.POINTER(EstParams)]; L.mtfb_est_default_params.restype = None
     L.mtfb_estimate_warp_from_pts.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
+    L.mtfb_estimate_warp_from_corners_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
     L.mtfb_grid_enable.argtypes = [vp]
     L.mtfb_grid_estimate.argtypes = [vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
     L.mtfb_grid_commit.argtypes = [vp]
@@ -438,6 +439,12 @@ class BatchTracker:
         n = a.shape[0]
         return self._est_result(ssm, n, lambda su, mk, wp, inf: self._L.mtfb_estimate_warp_from_pts(
             self._h, ssm, a.ctypes.data, b.ctypes.data, n, C.byref(est_params), su, mk, wp, inf))
+
+    def estimate_warp_from_corners_device(self, ssm, d_in_corners, d_out_corners, n, est_params):
+        """the same from two device arrays (raw pointers) of n x 8 corners: the points are their centroids"""
+        ssm = SSM[ssm] if isinstance(ssm, str) else int(ssm)
+        return self._est_result(ssm, n, lambda su, mk, wp, inf: self._L.mtfb_estimate_warp_from_corners_device(
+            self._h, ssm, d_in_corners, d_out_corners, n, C.byref(est_params), su, mk, wp, inf))
 
     def grid_enable(self):
         self._check(self._L.mtfb_grid_enable(self._h))

@@ -79,43 +79,76 @@ __device__ bool get_subset(CvRng &rng, const float *m1, const float *m2, int cou
 	return i == mp && iters < max_attempts;
 }
 
-// eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix (A is overwritten by its LDLt
-// factors): inverse iteration with a zero shift; x is scaled to a largest component of +1
-__device__ void smallest_eigvec9(double *A, double *x, double *y){
+// eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix A (shared memory, overwritten):
+// inverse iteration with a zero shift on an LDLt factorisation, by one warp -- lane i holds row i of L, then also column i, so
+// that both triangular solves are "broadcast the newest unknown, every lane updates its own partial sum".  x (shared, 9) is
+// scaled to a largest component of +1.
+__device__ void smallest_eigvec9_warp(double *A, double *x, int lane){
+	const int row = lane < 9 ? lane : 8;
+	double a[9], d[9];
+#pragma unroll
+	for(int k = 0; k < 9; ++k) a[k] = A[row * 9 + k];
 	double tr = 0;
+#pragma unroll
 	for(int i = 0; i < 9; ++i) tr += A[i * 9 + i];
 	const double tiny = tr * 1e-30 + 1e-300;
+	__syncwarp();
+#pragma unroll
 	for(int j = 0; j < 9; ++j){
-		double d = A[j * 9 + j];
-		for(int k = 0; k < j; ++k) d -= A[j * 9 + k] * A[j * 9 + k] * A[k * 9 + k];
-		if(fabs(d) < tiny) d = tiny;
-		A[j * 9 + j] = d;
-		for(int i = j + 1; i < 9; ++i){
-			double s = A[i * 9 + j];
-			for(int k = 0; k < j; ++k) s -= A[i * 9 + k] * A[j * 9 + k] * A[k * 9 + k];
-			A[i * 9 + j] = s / d;
-		}
+		double Lj[9];
+#pragma unroll
+		for(int k = 0; k < j; ++k) Lj[k] = __shfl_sync(FULL, a[k], j);
+		double dj = __shfl_sync(FULL, a[j], j);
+#pragma unroll
+		for(int k = 0; k < j; ++k) dj -= Lj[k] * Lj[k] * d[k];
+		if(fabs(dj) < tiny) dj = tiny;
+		d[j] = dj;
+		double sacc = a[j];
+#pragma unroll
+		for(int k = 0; k < j; ++k) sacc -= a[k] * Lj[k] * d[k];
+		if(row > j) a[j] = sacc / dj;
 	}
-	for(int i = 0; i < 9; ++i) x[i] = 1.0;
+	// column `row` of L: lt[k] = L[k][row], k > row
+#pragma unroll
+	for(int k = 0; k < 9; ++k) if(lane < 9 && k < row) A[row * 9 + k] = a[k];
+	__syncwarp();
+	double lt[9];
+#pragma unroll
+	for(int k = 0; k < 9; ++k) lt[k] = k > row ? A[k * 9 + row] : 0.0;
+	double xv[9], yv[9];
+#pragma unroll
+	for(int i = 0; i < 9; ++i) xv[i] = 1.0;
+	double prev_diff = 1e300;
 	for(int it = 0; it < 100; ++it){
+		double acc = 1.0;
+#pragma unroll
+		for(int i = 0; i < 9; ++i) if(row == i) acc = xv[i];
+#pragma unroll
 		for(int i = 0; i < 9; ++i){
-			double s = x[i];
-			for(int k = 0; k < i; ++k) s -= A[i * 9 + k] * y[k];
-			y[i] = s;
+			yv[i] = __shfl_sync(FULL, acc, i);
+			if(row > i) acc -= a[i] * yv[i];
 		}
-		for(int i = 0; i < 9; ++i) y[i] /= A[i * 9 + i];
+#pragma unroll
+		for(int i = 0; i < 9; ++i){ yv[i] /= d[i]; if(row == i) acc = yv[i]; }
+#pragma unroll
 		for(int i = 8; i >= 0; --i){
-			double s = y[i];
-			for(int k = i + 1; k < 9; ++k) s -= A[k * 9 + i] * y[k];
-			y[i] = s;
+			yv[i] = __shfl_sync(FULL, acc, i);
+			if(row < i) acc -= lt[i] * yv[i];
 		}
-		int im = 0;
-		for(int i = 1; i < 9; ++i) if(fabs(y[i]) > fabs(y[im])) im = i;
-		const double sc = 1.0 / y[im];
+		double big = yv[0];
+#pragma unroll
+		for(int i = 1; i < 9; ++i) if(fabs(yv[i]) > fabs(big)) big = yv[i];
+		const double sc = 1.0 / big;
 		double diff = 0;
-		for(int i = 0; i < 9; ++i){ const double v = y[i] * sc; diff = fmax(diff, fabs(v - x[i])); x[i] = v; }
-		if(it > 0 && diff < 1e-15) break;
+#pragma unroll
+		for(int i = 0; i < 9; ++i){ const double v = yv[i] * sc; diff = fmax(diff, fabs(v - xv[i])); xv[i] = v; }
+		// converged, or at the rounding floor of this matrix (the iterates stop contracting)
+		if(diff < 1e-15 || (it >= 2 && diff < 1e-10 && diff > 0.25 * prev_diff)) break;
+		prev_diff = diff;
 	}
+#pragma unroll
+	for(int i = 0; i < 9; ++i) if(lane == i) x[i] = xv[i];
+	__syncwarp();
 }
 
 // the tail of HomographyEstimator::runKernel (:70-76): H = invHnorm * H0 * Hnorm2, scaled to H[8] = 1
@@ -131,29 +164,39 @@ __device__ void denormalise(const double *H0, double cmx, double cmy, double smx
 
 struct WarpWs { double A[81], x[9], y[9], M[2 * EST_MAX_MODEL_PTS], m[2 * EST_MAX_MODEL_PTS]; };
 
-// HomographyEstimator::runKernel (:16-78) for the few points of one hypothesis, by one thread, sums in the reference's order
-__device__ int hom_fit_subset(WarpWs &w, int count, double *H){
-	const double *M = w.M, *m = w.m;
-	double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
-	for(int i = 0; i < count; ++i){ cmx += m[2 * i]; cmy += m[2 * i + 1]; cMx += M[2 * i]; cMy += M[2 * i + 1]; }
-	cmx /= count; cmy /= count; cMx /= count; cMy /= count;
-	for(int i = 0; i < count; ++i){
-		smx += fabs(m[2 * i] - cmx); smy += fabs(m[2 * i + 1] - cmy);
-		sMx += fabs(M[2 * i] - cMx); sMy += fabs(M[2 * i + 1] - cMy);
+// HomographyEstimator::runKernel (:16-78) for the few points of one hypothesis: lane 0 accumulates the normalisation and LtL with
+// the sums in the reference's order, the warp finds the eigenvector, lane 0 undoes the normalisation
+__device__ int hom_fit_subset(WarpWs &w, int count, double *H, int lane){
+	if(lane == 0){
+		const double *M = w.M, *m = w.m;
+		double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
+		for(int i = 0; i < count; ++i){ cmx += m[2 * i]; cmy += m[2 * i + 1]; cMx += M[2 * i]; cMy += M[2 * i + 1]; }
+		cmx /= count; cmy /= count; cMx /= count; cMy /= count;
+		for(int i = 0; i < count; ++i){
+			smx += fabs(m[2 * i] - cmx); smy += fabs(m[2 * i + 1] - cmy);
+			sMx += fabs(M[2 * i] - cMx); sMy += fabs(M[2 * i + 1] - cMy);
+		}
+		int ok = 1;
+		if(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) ok = 0;
+		if(ok){
+			smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
+			for(int i = 0; i < 81; ++i) w.A[i] = 0;
+			for(int i = 0; i < count; ++i){
+				const double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
+				const double X = (M[2 * i] - cMx) * sMx, Y = (M[2 * i + 1] - cMy) * sMy;
+				const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
+				const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
+				for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k) w.A[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+			}
+			for(int j = 0; j < 9; ++j) for(int k = 0; k < j; ++k) w.A[j * 9 + k] = w.A[k * 9 + j];
+		}
+		w.y[0] = cmx; w.y[1] = cmy; w.y[2] = smx; w.y[3] = smy; w.y[4] = cMx; w.y[5] = cMy; w.y[6] = sMx; w.y[7] = sMy; w.y[8] = ok;
 	}
-	if(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) return 0;
-	smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
-	for(int i = 0; i < 81; ++i) w.A[i] = 0;
-	for(int i = 0; i < count; ++i){
-		const double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
-		const double X = (M[2 * i] - cMx) * sMx, Y = (M[2 * i + 1] - cMy) * sMy;
-		const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
-		const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
-		for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k) w.A[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
-	}
-	for(int j = 0; j < 9; ++j) for(int k = 0; k < j; ++k) w.A[j * 9 + k] = w.A[k * 9 + j];
-	smallest_eigvec9(w.A, w.x, w.y);
-	denormalise(w.x, cmx, cmy, smx, smy, cMx, cMy, sMx, sMy, H);
+	__syncwarp();
+	if(w.y[8] == 0) return 0;
+	smallest_eigvec9_warp(w.A, w.x, lane);
+	if(lane == 0) denormalise(w.x, w.y[0], w.y[1], w.y[2], w.y[3], w.y[4], w.y[5], w.y[6], w.y[7], H);
+	__syncwarp();
 	return 1;
 }
 
@@ -281,11 +324,14 @@ template<bool HOM> __device__ int fit_masked(const EstDev &e, WarpWs &ws, double
 				for(int k = j; k < 9; ++k) L[q++] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
 		}
 		block_sum<45>(L, s_red, s_sum);
-		if(tid == 0){
-			int q = 0;
-			for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k){ ws.A[j * 9 + k] = s_sum[q]; ws.A[k * 9 + j] = s_sum[q]; ++q; }
-			smallest_eigvec9(ws.A, ws.x, ws.y);
-			denormalise(ws.x, cmx, cmy, smx, smy, cMx, cMy, sMx, sMy, s_model);
+		if(tid < 32){
+			if(tid == 0){
+				int q = 0;
+				for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k){ ws.A[j * 9 + k] = s_sum[q]; ws.A[k * 9 + j] = s_sum[q]; ++q; }
+			}
+			__syncwarp();
+			smallest_eigvec9_warp(ws.A, ws.x, tid);
+			if(tid == 0) denormalise(ws.x, cmx, cmy, smx, smy, cMx, cMy, sMx, sMy, s_model);
 		}
 		__syncthreads();
 		return 1;
@@ -320,45 +366,65 @@ template<bool HOM> __device__ int find_inliers_block(const EstDev &e, const doub
 	return (int)s_sum[0];
 }
 
-// LevMarq::step (SSMEstimator.cc:489-516): param = prevParam - (JtJ with its diagonal scaled by 1 + lambda)^-1 JtErr
-template<int NP> __device__ void lm_step(const double *JtJ, const double *JtErr, const double *prev, double *param, int lambdaLg10){
+// LevMarq::step (SSMEstimator.cc:489-516): param = prevParam - (JtJ with its diagonal scaled by 1 + lambda)^-1 JtErr, by one
+// warp: lane i holds row i of the diagonally scaled system, elimination with partial pivoting without moving rows (the pivot
+// row is broadcast, a row that has been a pivot drops out), back-substitution by broadcasting each unknown
+template<int NP> __device__ void lm_step_warp(const double *JtJ, const double *JtErr, const double *prev, double *param, int lambdaLg10, int lane){
 	const double lambda = exp(lambdaLg10 * log(10.));
-	double A[NP * NP], b[NP], sc[NP];
-	for(int i = 0; i < NP; ++i){
-		const double d = JtJ[i * NP + i] * (1. + lambda);
-		sc[i] = d > 0 ? rsqrt(d) : 1.0;
+	const int row = lane < NP ? lane : NP - 1;
+	double sc[NP], a[NP];
+#pragma unroll
+	for(int j = 0; j < NP; ++j){ const double dd = JtJ[j * NP + j] * (1. + lambda); sc[j] = dd > 0 ? rsqrt(dd) : 1.0; }
+	double scr = 1.0;
+#pragma unroll
+	for(int j = 0; j < NP; ++j) if(row == j) scr = sc[j];
+#pragma unroll
+	for(int j = 0; j < NP; ++j){
+		double v = row <= j ? JtJ[row * NP + j] : JtJ[j * NP + row];
+		if(row == j) v *= 1. + lambda;
+		a[j] = v * scr * sc[j];
 	}
-	for(int i = 0; i < NP; ++i){
-		for(int j = 0; j < NP; ++j){
-			double v = i <= j ? JtJ[i * NP + j] : JtJ[j * NP + i];
-			if(i == j) v *= 1. + lambda;
-			A[i * NP + j] = v * sc[i] * sc[j];
-		}
-		b[i] = JtErr[i] * sc[i];
-	}
+	double b = JtErr[row] * scr;
+	bool used = lane >= NP;
+	int piv[NP];
+#pragma unroll
 	for(int k = 0; k < NP; ++k){
-		int pv = k;
-		for(int i = k + 1; i < NP; ++i) if(fabs(A[i * NP + k]) > fabs(A[pv * NP + k])) pv = i;
-		if(pv != k){
-			for(int j = 0; j < NP; ++j){ const double t = A[k * NP + j]; A[k * NP + j] = A[pv * NP + j]; A[pv * NP + j] = t; }
-			const double t = b[k]; b[k] = b[pv]; b[pv] = t;
+		double mag = used ? -1.0 : fabs(a[k]);
+		int who = lane;
+#pragma unroll
+		for(int off = 16; off >= 1; off >>= 1){
+			const double m2 = __shfl_xor_sync(FULL, mag, off);
+			const int w2 = __shfl_xor_sync(FULL, who, off);
+			if(m2 > mag || (m2 == mag && w2 < who)){ mag = m2; who = w2; }
 		}
-		double d = A[k * NP + k];
-		if(fabs(d) < 1e-300) d = 1e-300;
-		const double inv = 1.0 / d;
-		for(int i = k + 1; i < NP; ++i){
-			const double f = A[i * NP + k] * inv;
-			for(int j = k + 1; j < NP; ++j) A[i * NP + j] -= f * A[k * NP + j];
-			b[i] -= f * b[k];
+		piv[k] = who;
+		double pk[NP];
+#pragma unroll
+		for(int j = k; j < NP; ++j) pk[j] = __shfl_sync(FULL, a[j], who);
+		const double pb = __shfl_sync(FULL, b, who);
+		double dpv = pk[k];
+		if(fabs(dpv) < 1e-300) dpv = 1e-300;
+		if(lane == who) used = true;
+		if(!used){
+			const double f = a[k] / dpv;
+#pragma unroll
+			for(int j = k + 1; j < NP; ++j) a[j] -= f * pk[j];
+			b -= f * pb;
 		}
-		A[k * NP + k] = d;
 	}
+	double x[NP];
+#pragma unroll
 	for(int k = NP - 1; k >= 0; --k){
-		double s = b[k];
-		for(int j = k + 1; j < NP; ++j) s -= A[k * NP + j] * b[j];
-		b[k] = s / A[k * NP + k];
+		double t = b;
+#pragma unroll
+		for(int j = k + 1; j < NP; ++j) t -= a[j] * x[j];
+		double dpv = a[k];
+		if(fabs(dpv) < 1e-300) dpv = 1e-300;
+		x[k] = __shfl_sync(FULL, t / dpv, piv[k]);
 	}
-	for(int i = 0; i < NP; ++i) param[i] = prev[i] - b[i] * sc[i];
+#pragma unroll
+	for(int k = 0; k < NP; ++k) if(lane == k) param[k] = prev[k] - x[k] * sc[k];
+	__syncwarp();
 }
 
 // HomographyEstimator::refine (:97-145) / AffineEstimator::refine (:64-106) around LevMarq::updateAlt (:436-487)
@@ -366,7 +432,7 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 	constexpr int NP = HOM ? 8 : 6, NJ = NP * (NP + 1) / 2, K = NJ + NP + 1;
 	enum { DONE = 0, STARTED = 1, CALC_J = 2, CHECK_ERR = 3 };
 	__shared__ double s_JtJ[64], s_JtErr[8], s_param[8], s_prev[8];
-	__shared__ int s_flag[3];
+	__shared__ int s_flag[5];
 	const int tid = threadIdx.x;
 	int state = STARTED, iters = 0, lambdaLg10 = -3, evals = 0;
 	const int max_iter = min(max(e.lm_max_iters, 1), 1000);
@@ -374,31 +440,32 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 	if(tid < NP) s_param[tid] = s_model[tid];
 	__syncthreads();
 	for(;;){
-		if(tid == 0){
-			int cont = 1, want_J = 0, want_err = 0;
-			if(state == STARTED){ errNorm = 0; want_J = want_err = 1; state = CALC_J; }
-			else if(state == CALC_J){
-				for(int i = 0; i < NP; ++i) s_prev[i] = s_param[i];
-				lm_step<NP>(s_JtJ, s_JtErr, s_prev, s_param, lambdaLg10);
-				prevErrNorm = errNorm; errNorm = 0; want_err = 1; state = CHECK_ERR;
-			} else {
-				bool retried = false;
-				if(errNorm > prevErrNorm){
-					if(++lambdaLg10 <= 16){
-						lm_step<NP>(s_JtJ, s_JtErr, s_prev, s_param, lambdaLg10);
-						errNorm = 0; want_err = 1; state = CHECK_ERR; retried = true;
+		if(tid < 32){
+			if(tid == 0){
+				int cont = 1, want_J = 0, want_err = 0, step = 0;
+				if(state == STARTED){ errNorm = 0; want_J = want_err = 1; state = CALC_J; }
+				else if(state == CALC_J){
+					for(int i = 0; i < NP; ++i) s_prev[i] = s_param[i];
+					step = 1;
+					prevErrNorm = errNorm; errNorm = 0; want_err = 1; state = CHECK_ERR;
+				} else {
+					bool retried = false;
+					if(errNorm > prevErrNorm){
+						if(++lambdaLg10 <= 16){ step = 1; errNorm = 0; want_err = 1; state = CHECK_ERR; retried = true; }
+					}
+					if(!retried){
+						lambdaLg10 = max(lambdaLg10 - 1, -16);
+						double dn = 0, pn = 0;
+						for(int i = 0; i < NP; ++i){ const double d = s_param[i] - s_prev[i]; dn += d * d; pn += s_prev[i] * s_prev[i]; }
+						const double change = sqrt(dn) / (sqrt(pn) + DBL_EPSILON);
+						if(++iters >= max_iter || change < DBL_EPSILON){ state = DONE; cont = 0; }
+						else { prevErrNorm = errNorm; want_J = 1; state = CALC_J; }
 					}
 				}
-				if(!retried){
-					lambdaLg10 = max(lambdaLg10 - 1, -16);
-					double dn = 0, pn = 0;
-					for(int i = 0; i < NP; ++i){ const double d = s_param[i] - s_prev[i]; dn += d * d; pn += s_prev[i] * s_prev[i]; }
-					const double change = sqrt(dn) / (sqrt(pn) + DBL_EPSILON);
-					if(++iters >= max_iter || change < DBL_EPSILON){ state = DONE; cont = 0; }
-					else { prevErrNorm = errNorm; want_J = 1; state = CALC_J; }
-				}
+				s_flag[0] = cont; s_flag[1] = want_J; s_flag[2] = want_err; s_flag[3] = step; s_flag[4] = lambdaLg10;
 			}
-			s_flag[0] = cont; s_flag[1] = want_J; s_flag[2] = want_err;
+			__syncwarp();
+			if(s_flag[3]) lm_step_warp<NP>(s_JtJ, s_JtErr, s_prev, s_param, s_flag[4], tid);
 		}
 		__syncthreads();
 		if(!s_flag[0]) break;
@@ -427,12 +494,21 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 				J1[0] = 0; J1[1] = 0; J1[2] = 0; J1[3] = Mx; J1[4] = My; J1[5] = 1;
 			}
 			if(want_J){
+				// the rows of J are zero in columns 3-5 / 0-2: only the products that are not identically zero (the reference adds the zeros)
 				int q = 0;
 #pragma unroll
 				for(int j = 0; j < NP; ++j){
 #pragma unroll
-					for(int k = j; k < NP; ++k) acc[q++] += J0[j] * J0[k] + J1[j] * J1[k];
-					acc[NJ + j] += J0[j] * er0 + J1[j] * er1;
+					for(int k = j; k < NP; ++k){
+						const bool a0 = (j < 3 || j > 5) && (k < 3 || k > 5), a1 = j >= 3 && k >= 3;
+						if(a0 && a1) acc[q] += J0[j] * J0[k] + J1[j] * J1[k];
+						else if(a0) acc[q] += J0[j] * J0[k];
+						else if(a1) acc[q] += J1[j] * J1[k];
+						++q;
+					}
+					if(j < 3) acc[NJ + j] += J0[j] * er0;
+					else if(j < 6) acc[NJ + j] += J1[j] * er1;
+					else acc[NJ + j] += J0[j] * er0 + J1[j] * er1;
 				}
 			}
 			acc[K - 1] += er0 * er0 + er1 * er1;
@@ -485,7 +561,8 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 		}
 		for(;;){
 			if(tid == 0){
-				int nb = min(BATCH, niters - iter);
+				// the first round is one hypothesis per warp: with mostly inliers RANSAC's adaptive count ends there
+				int nb = min(iter == 0 ? (int)EST_WARPS : BATCH, niters - iter);
 				for(int b = 0; b < nb; ++b){
 					s_found[b] = get_subset(rng, e.in_pts, e.out_pts, n, mp, e.max_attempts, s_idx[b]);
 					if(!s_found[b]){ nb = b + 1; break; }
@@ -503,7 +580,8 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 					w.m[2 * lane] = e.out_pts[2 * id]; w.m[2 * lane + 1] = e.out_pts[2 * id + 1];
 				}
 				__syncwarp();
-				if(lane == 0) s_valid[b] = HOM ? hom_fit_subset(w, mp, s_hyp[b]) : aff_fit_subset(w, mp, s_hyp[b]);
+				if(HOM){ const int ok = hom_fit_subset(w, mp, s_hyp[b], lane); if(lane == 0) s_valid[b] = ok; }
+				else if(lane == 0) s_valid[b] = aff_fit_subset(w, mp, s_hyp[b]);
 				__syncwarp();
 				if(!s_valid[b]) continue;
 				double H[9];
@@ -603,7 +681,8 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 			// Affine::estimateWarpFromPts (Affine.cc:359-369)
 			su[0] = H[2]; su[1] = H[5]; su[2] = H[0] - 1; su[3] = H[1]; su[4] = H[3]; su[5] = H[4] - 1; su[6] = 0; su[7] = 0;
 		}
-		e.info[0] = result; e.info[1] = drawn; e.info[2] = n_in; e.info[3] = evals;
+		// result | hypotheses drawn | inliers | LM evaluations, in the same buffer: one copy back
+		e.out[17] = result; e.out[18] = drawn; e.out[19] = n_in; e.out[20] = evals;
 	}
 }
 

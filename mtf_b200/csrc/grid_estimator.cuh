@@ -14,8 +14,7 @@ struct EstDev {
 	int method, model_points, refine, max_iters, max_attempts, lm_max_iters;
 	double thresh, confidence;
 	unsigned long long seed;
-	double *out;                       // 9 warp matrix | 8 state update
-	int *info;                         // result | hypotheses drawn | inliers | LM evaluations
+	double *out;                       // 9 warp matrix | 8 state update | result, hypotheses drawn, inliers, LM evaluations
 	unsigned char *mask;               // n
 	float *err;                        // EST_WARPS x n floats (LMedS: the reprojection errors of a warp's hypothesis)
 };

@@ -177,7 +177,7 @@ struct mtfb_ctx {
 	// tensor map of the current frame for the moment kernel's 2-D TMA window copy (re-encoded when the frame buffer changes)
 	// robust warp estimation from point pairs (grid_estimator.cu): staging for host points, outputs, LMedS scratch; the grid's
 	// own prev_pts / curr_pts after mtfb_grid_enable
-	float *d_est_pts; unsigned char *d_est_mask; float *d_est_err; double *d_est_out; int *d_est_info; size_t est_capacity;
+	float *d_est_pts; unsigned char *d_est_mask; float *d_est_err; double *d_est_out; size_t est_capacity;
 	float *d_grid_prev, *d_grid_curr; bool grid_enabled;
 	alignas(64) CUtensorMap frame_map; const float *frame_map_ptr; int frame_map_h, frame_map_w, frame_map_pitch; bool frame_map_ok;
 };
@@ -245,7 +245,7 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaFree(c->d_corners_in); cudaFree(c->d_log); cudaFree(c->d_scratch); cudaFree(c->d_f32); cudaFree(c->d_raw);
 	cudaFree(c->d_mom_work);
 	cudaFree(c->d_pf); cudaFree(c->d_pf_ints); cudaFree(c->d_pf_rand_in); cudaFree(c->d_pf_rand_out);
-	cudaFree(c->d_est_pts); cudaFree(c->d_est_mask); cudaFree(c->d_est_err); cudaFree(c->d_est_out); cudaFree(c->d_est_info);
+	cudaFree(c->d_est_pts); cudaFree(c->d_est_mask); cudaFree(c->d_est_err); cudaFree(c->d_est_out);
 	cudaFree(c->d_grid_prev); cudaFree(c->d_grid_curr);
 	if(c->copy_stream){
 		cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream);
@@ -851,8 +851,7 @@ static mtfb_status est_reserve(mtfb_ctx *c, size_t n){
 	CUDA_TRY(cudaMalloc(&c->d_est_pts, 4 * n*sizeof(float)));
 	CUDA_TRY(cudaMalloc(&c->d_est_mask, n));
 	CUDA_TRY(cudaMalloc(&c->d_est_err, (size_t)EST_WARPS*n*sizeof(float)));
-	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 17 * sizeof(double)));
-	if(!c->d_est_info) CUDA_TRY(cudaMalloc(&c->d_est_info, 4 * sizeof(int)));
+	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 21 * sizeof(double)));
 	c->est_capacity = n;
 	return MTFB_OK;
 }
@@ -874,17 +873,16 @@ static mtfb_status est_run(mtfb_ctx *c, const char *who, int ssm, const float *d
 	e.max_attempts = ep->max_subset_attempts; e.lm_max_iters = ep->lm_max_iters;
 	e.thresh = ep->ransac_reproj_thresh > 0 ? ep->ransac_reproj_thresh : 3.0;
 	e.confidence = ep->confidence; e.seed = ep->seed;
-	e.out = c->d_est_out; e.info = c->d_est_info; e.mask = c->d_est_mask; e.err = c->d_est_err;
+	e.out = c->d_est_out; e.mask = c->d_est_mask; e.err = c->d_est_err;
 	CUDA_TRY(launch_estimate(e, c->stream));
 	++c->launches;
-	double out[17]; int inf[4];
+	double out[21];
 	CUDA_TRY(cudaMemcpyAsync(out, c->d_est_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
-	CUDA_TRY(cudaMemcpyAsync(inf, c->d_est_info, sizeof(inf), cudaMemcpyDeviceToHost, c->stream));
 	if(mask) CUDA_TRY(cudaMemcpyAsync(mask, c->d_est_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if(warp) std::memcpy(warp, out, 9 * sizeof(double));
 	if(state_update) std::memcpy(state_update, out + 9, (ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6)*sizeof(double));
-	if(info) std::memcpy(info, inf, sizeof(inf));
+	if(info) for(int i = 0; i < 4; ++i) info[i] = (int)out[17 + i];
 	return MTFB_OK;
 }
 
@@ -899,6 +897,18 @@ mtfb_status mtfb_estimate_warp_from_pts(mtfb_ctx *c, int ssm, const float *in_pt
 	CUDA_TRY(cudaMemcpyAsync(c->d_est_pts, in_pts, 2 * (size_t)n*sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(c->d_est_pts + 2 * (size_t)n, out_pts, 2 * (size_t)n*sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	return est_run(c, "mtfb_estimate_warp_from_pts", ssm, c->d_est_pts, c->d_est_pts + 2 * (size_t)n, n, ep, state_update, mask, warp, info);
+}
+
+mtfb_status mtfb_estimate_warp_from_corners_device(mtfb_ctx *c, int ssm, const double *d_in_corners, const double *d_out_corners, int n,
+	const mtfb_est_params *ep, double *state_update, unsigned char *mask, double *warp, int *info){
+	if(!c || !d_in_corners || !d_out_corners || !ep) return fail(MTFB_ERR_INVALID_ARG, "mtfb_estimate_warp_from_corners_device: null argument");
+	if(n < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_estimate_warp_from_corners_device: no points");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	{ mtfb_status st = est_reserve(c, (size_t)n); if(st != MTFB_OK) return st; }
+	CUDA_TRY(launch_centroids(d_in_corners, n, c->d_est_pts, c->stream));
+	CUDA_TRY(launch_centroids(d_out_corners, n, c->d_est_pts + 2 * (size_t)n, c->stream));
+	c->launches += 2;
+	return est_run(c, "mtfb_estimate_warp_from_corners_device", ssm, c->d_est_pts, c->d_est_pts + 2 * (size_t)n, n, ep, state_update, mask, warp, info);
 }
 
 mtfb_status mtfb_grid_enable(mtfb_ctx *c){

@@ -63,7 +63,11 @@ class GridTracker:
 
     def __init__(self, cell_params, grid_size_x=10, grid_size_y=10, patch_size_x=10, patch_size_y=10, reset_at_each_frame=1,
                  dyn_patch_size=0, patch_centroid_inside=True, fb_err_thresh=0, enable_pyr=0, ssm="homography", est_params=None,
-                 seed=1):
+                 seed=1, cells=None, shard=None, gather=None, upload=None):
+        """cells / shard / gather / upload: the cells split over several processes (one GPU each).  cells = this process's
+        BatchTracker of the cells [shard[0], shard[1]); gather() -> a device array (.data_ptr()) of the current corners of ALL
+        cells (n x 8) on this device; upload(ndarray) -> the same kind of object for the regions the cells were reset to.  Every
+        process then runs the estimation on all the centroids (same seed, same result) and resets its own cells."""
         # defaults: GridTracker.h:8-23
         if fb_err_thresh > 0:
             raise api.MTFError(2, "GridTracker: forward-backward error estimation is not implemented")
@@ -73,9 +77,11 @@ class GridTracker:
             raise api.MTFError(2, "GridTracker: the grid's SSM must be homography or affine")
         self.gx, self.gy = int(grid_size_x), int(grid_size_y)
         n = self.gx * self.gy
-        if cell_params.n_patches != n:
+        self.shard = (0, n) if shard is None else (int(shard[0]), int(shard[1]))
+        if (cells.P if cells is not None else cell_params.n_patches) != self.shard[1] - self.shard[0]:
             # GridTracker.cc:126-131
             raise api.MTFError(1, "GridTracker :: Mismatch between grid dimensions and no. of trackers")
+        self.gather, self.upload, self._d_prev = gather, upload, None
         self.patch_size_x, self.patch_size_y = float(patch_size_x), float(patch_size_y)
         self.reset_at_each_frame = int(reset_at_each_frame)
         self.reinit_at_each_frame = self.reset_at_each_frame == 1          # GridTracker.cc:138
@@ -86,8 +92,9 @@ class GridTracker:
         self.est_params = est_params if est_params is not None else api.make_est_params()
         self.seed = int(seed)
         self.frame = 0
-        self.cells = api.BatchTracker(cell_params)
-        self.cells.grid_enable()
+        self.cells = cells if cells is not None else api.BatchTracker(cell_params)
+        if self.gather is None:
+            self.cells.grid_enable()
         self.n_trackers = n
         self.corners = None
         self.pts = None
@@ -102,33 +109,34 @@ class GridTracker:
 
     def cell_corners(self):
         """GridTracker::resetTrackers (GridTracker.cc:345-392): the region of every patch tracker, (P, 2, 4)"""
-        out = np.empty((self.n_trackers, 2, 4))
-        for t in range(self.n_trackers):
-            r, c = divmod(t, self.gx)
-            if self.resx == self.gx + 1:
-                w = self.gx + 1
-                ids = [r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c]
-                pc = self.pts[:, ids]
+        t = np.arange(self.n_trackers)
+        r, c = t // self.gx, t % self.gx
+        pc = None
+        if self.resx == self.gx + 1:
+            w = self.gx + 1
+            ids = np.stack([r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c], axis=1)      # (P, 4)
+            pc = self.pts[:, ids].transpose(1, 0, 2)                                                       # (P, 2, 4)
+        # (with resx = grid_size_x the reference still indexes the (grid_size + 1)-wide table, GridTracker.cc:361-371, and then
+        # overwrites the result: only the fixed-size branch is meaningful there)
+        if not self.dyn_patch_size:
+            if self.patch_centroid_inside:
+                cen = (pc[:, :, 0] + pc[:, :, 1] + pc[:, :, 2] + pc[:, :, 3]) / 4.0
             else:
-                # with resx = grid_size_x the reference still indexes the (grid_size + 1)-wide table (GridTracker.cc:361-371):
-                # only the fixed-size branch below is meaningful there
-                pc = None
-            if not self.dyn_patch_size:
-                centroid = self.pts[:, t].copy()
-                if self.patch_centroid_inside:
-                    centroid = pc.sum(axis=1) / 4.0
-                x0, y0 = centroid[0] - self.patch_size_x / 2.0, centroid[1] - self.patch_size_y / 2.0
-                pc = np.array([[x0, x0 + self.patch_size_x, x0 + self.patch_size_x, x0],
-                               [y0, y0, y0 + self.patch_size_y, y0 + self.patch_size_y]])
-            out[t] = pc
-        return out
+                cen = self.pts[:, t].T
+            x0, y0 = cen[:, 0] - self.patch_size_x / 2.0, cen[:, 1] - self.patch_size_y / 2.0
+            x1, y1 = x0 + self.patch_size_x, y0 + self.patch_size_y
+            pc = np.stack([np.stack([x0, x1, x1, x0], axis=1), np.stack([y0, y0, y1, y1], axis=1)], axis=1)
+        return np.ascontiguousarray(pc)
 
     def _reset_trackers(self, reinit):
         cells = self.cell_corners()
+        if self.gather is not None:
+            self._d_prev = self.upload(cells.reshape(-1, 8))
+        mine = cells[self.shard[0]:self.shard[1]]
         if reinit:
-            self.cells.initialize(cells)
+            self.cells.initialize(mine)
         else:
-            self.cells.setRegion(cells)
+            self.cells.setRegion(mine)
 
     def setImage(self, img):
         self.cells.setImage(img)
@@ -147,18 +155,28 @@ class GridTracker:
         if img is not None:
             self.setImage(img)
         self.cells.update()
+        return self.finish_update()
+
+    def finish_update(self):
+        """GridTracker::update after the cells' own update (GridTracker.cc:265-285)"""
         # every frame's estimator is a new object with a fresh seed in the reference (SSMEstimator.cc:22-24); here seed + frame
         self.frame += 1
         ep = api.EstParams.from_buffer_copy(self.est_params)
         ep.seed = self.seed + self.frame
-        est = self.cells.grid_estimate(self.ssm, ep)
+        if self.gather is None:
+            est = self.cells.grid_estimate(self.ssm, ep)
+        else:
+            curr = self.gather()
+            est = self.cells.estimate_warp_from_corners_device(self.ssm, self._d_prev.data_ptr(), curr.data_ptr(), self.n_trackers, ep)
         self.last_estimate = est
         self.ssm_update, self.pix_mask = est["state_update"], est["mask"]
         self._set_corners(apply_warp_to_corners(self.ssm, self.corners, self.ssm_update))
         if self.reset_at_each_frame:
             self._reset_trackers(self.reinit_at_each_frame)
-        else:
+        elif self.gather is None:
             self.cells.grid_commit()
+        else:
+            self._d_prev = curr.clone()
         return self.getRegion()
 
     def getRegion(self):

@@ -80,6 +80,27 @@ int main(int argc, char **argv){
 			try{ mtf::b200::Tracker bad("pf", argv[4], argv[5], res, res); printf("NOEXCPF\n"); }
 			catch(const mtf::utils::Exception &e){ printf("EXCPF %s\n", e.type()); }
 		}
+		// (5) the step after the cells in GridTracker::update: the warp of the region from the members' centroids, on the device
+		// through the batch the members share (Batch::gridEstimate) and from host points (Batch::estimateWarpFromPts)
+		{
+			std::shared_ptr<mtf::b200::Batch> gb(new mtf::b200::Batch(mtf::b200::makeParams(argv[3], argv[4], argv[5], P, res, res)));
+			gb->gridEnable();
+			load(0); gb->setImage(img); gb->initialize(corners.data());
+			std::vector<float> prev(2 * (size_t)P), curr(2 * (size_t)P);
+			for(int i = 0; i < P; ++i){ const double *r = gb->region(i);
+				prev[2 * i] = (float)((r[0] + r[1] + r[2] + r[3]) / 4.0); prev[2 * i + 1] = (float)((r[4] + r[5] + r[6] + r[7]) / 4.0); }
+			load(1); gb->setImage(img); gb->update();
+			for(int i = 0; i < P; ++i){ const double *r = gb->region(i);
+				curr[2 * i] = (float)((r[0] + r[1] + r[2] + r[3]) / 4.0); curr[2 * i + 1] = (float)((r[4] + r[5] + r[6] + r[7]) / 4.0); }
+			const mtfb_est_params ep = mtf::b200::Batch::estParams(MTFB_EST_RANSAC, 10.0, 4, true, 2000, 300, 0.995, 10, 99);
+			double su_dev[8], su_host[8]; std::vector<unsigned char> m_dev(P), m_host(P);
+			const bool ok_dev = gb->gridEstimate(MTFB_SSM_HOMOGRAPHY, su_dev, m_dev.data(), ep);
+			const bool ok_host = gb->estimateWarpFromPts(MTFB_SSM_HOMOGRAPHY, su_host, m_host.data(), prev.data(), curr.data(), P, ep);
+			printf("EST %d %d\n", (int)ok_dev, (int)ok_host);
+			for(int k = 0; k < 8; ++k) printf("ESTSU %.17g %.17g\n", su_dev[k], su_host[k]);
+			for(int i = 0; i < P; ++i) if(m_dev[i] != m_host[i]){ printf("ESTMASK %d\n", i); }
+			for(int i = 0; i < P; ++i) printf("ESTPT %.9g %.9g %.9g %.9g\n", prev[2 * i], prev[2 * i + 1], curr[2 * i], curr[2 * i + 1]);
+		}
 		// error contract: a bad corner matrix is an InvalidArgument exception, not a crash
 		try{ cv::Mat bad(3, 4, CV_64FC1); single[0]->initialize(bad); printf("NOEXC\n"); }
 		catch(const mtf::utils::Exception &e){ printf("EXC %s\n", e.type()); }

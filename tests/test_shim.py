@@ -66,6 +66,15 @@ def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
     for t in (1, 2):
         t8.setRawImage(u8[t]); t8.update()
     assert np.abs(raw - t8.getRegion()[0]).max() <= 1e-9
+    # Batch::gridEstimate (points stay on the device) == Batch::estimateWarpFromPts on the same centroids from the host == the
+    # oracle's estimateHomography on them
+    from oracle import oracle_lib as O
+    assert "EST 1 1" in out and not [l for l in out if l.startswith("ESTMASK")]
+    su = np.array([[float(x) for x in l.split()[1:]] for l in out if l.startswith("ESTSU ")])
+    assert np.array_equal(su[:, 0], su[:, 1])
+    pts = np.array([[float(x) for x in l.split()[1:]] for l in out if l.startswith("ESTPT ")], dtype=np.float32)
+    orc = O.estimate_warp("homography", pts[:, :2], pts[:, 2:], O.make_est_params("ransac", seed=99))
+    assert orc["ok"] and np.allclose(su[:, 0], orc["state_update"], rtol=1e-5, atol=1e-6)
     if ssm == "8":
         # mtf::b200::PFTracker == the Python binding's PFTracker with the same seed (device generator: deterministic)
         pfc = np.array([float(l.split()[1]) for l in out if l.startswith("PF ")]).reshape(2, 4)
