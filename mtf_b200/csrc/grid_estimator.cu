@@ -22,7 +22,17 @@ namespace mtfb {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+// -DEST_PROF: thread 0 accumulates clock64 deltas of the kernel's phases into out[21..31] (profiles/experiments)
+#ifdef EST_PROF
+#define PROF_T0() const long long prof_t0 = clock64()
+#define PROF_ADD(slot) do{ if(threadIdx.x == 0) g_prof[slot] += (double)(clock64() - prof_t0); }while(0)
+__device__ double g_prof[11];
+#else
+#define PROF_T0() do{}while(0)
+#define PROF_ADD(slot) do{}while(0)
+#endif
 constexpr int BATCH = 32;                 // hypotheses per round
+constexpr int EST_STAGED = 1024;          // points kept in shared memory
 enum { M_RANSAC = 0, M_LMEDS = 1, M_LS = 2 };   // SSMEstimatorParams::EstType (SSMEstimatorParams.h:11)
 
 // cvRNG / cvRandInt (OpenCV core: multiply-with-carry)
@@ -162,6 +172,15 @@ __device__ void denormalise(const double *H0, double cmx, double cmy, double smx
 	for(int i = 0; i < 9; ++i) H[i] = R[i] * sc;
 }
 
+// entry c of the row Lx (r = 0) / Ly (r = 1) of the DLT system for one normalised point pair (HomographyEstimator.cc:61-62)
+__device__ __forceinline__ double l_entry(int r, int c, double x, double y, double X, double Y){
+	const double t = r ? y : x;
+	if(c >= 6) return c == 6 ? -t * X : (c == 7 ? -t * Y : -t);
+	const int base = r ? 3 : 0;
+	if(c < base || c >= base + 3) return 0.0;
+	return c == base ? X : (c == base + 1 ? Y : 1.0);
+}
+
 struct WarpWs { double A[81], x[9], y[9], M[2 * EST_MAX_MODEL_PTS], m[2 * EST_MAX_MODEL_PTS]; };
 
 // HomographyEstimator::runKernel (:16-78) for the few points of one hypothesis: lane 0 accumulates the normalisation and LtL with
@@ -178,22 +197,26 @@ __device__ int hom_fit_subset(WarpWs &w, int count, double *H, int lane){
 		}
 		int ok = 1;
 		if(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) ok = 0;
-		if(ok){
-			smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy;
-			for(int i = 0; i < 81; ++i) w.A[i] = 0;
-			for(int i = 0; i < count; ++i){
-				const double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
-				const double X = (M[2 * i] - cMx) * sMx, Y = (M[2 * i + 1] - cMy) * sMy;
-				const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
-				const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
-				for(int j = 0; j < 9; ++j) for(int k = j; k < 9; ++k) w.A[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
-			}
-			for(int j = 0; j < 9; ++j) for(int k = 0; k < j; ++k) w.A[j * 9 + k] = w.A[k * 9 + j];
-		}
+		if(ok){ smx = count / smx; smy = count / smy; sMx = count / sMx; sMy = count / sMy; }
 		w.y[0] = cmx; w.y[1] = cmy; w.y[2] = smx; w.y[3] = smy; w.y[4] = cMx; w.y[5] = cMy; w.y[6] = sMx; w.y[7] = sMy; w.y[8] = ok;
 	}
 	__syncwarp();
 	if(w.y[8] == 0) return 0;
+	{
+		// LtL (HomographyEstimator.cc:59-68): entry (j, k) by one lane, the points in the reference's order
+		const double cmx = w.y[0], cmy = w.y[1], smx = w.y[2], smy = w.y[3], cMx = w.y[4], cMy = w.y[5], sMx = w.y[6], sMy = w.y[7];
+		for(int q = lane; q < 81; q += 32){
+			const int j = q / 9, k = q % 9;
+			double acc = 0;
+			for(int i = 0; i < count; ++i){
+				const double x = (w.m[2 * i] - cmx) * smx, y = (w.m[2 * i + 1] - cmy) * smy;
+				const double X = (w.M[2 * i] - cMx) * sMx, Y = (w.M[2 * i + 1] - cMy) * sMy;
+				acc += l_entry(0, j, x, y, X, Y) * l_entry(0, k, x, y, X, Y) + l_entry(1, j, x, y, X, Y) * l_entry(1, k, x, y, X, Y);
+			}
+			w.A[q] = acc;
+		}
+		__syncwarp();
+	}
 	smallest_eigvec9_warp(w.A, w.x, lane);
 	if(lane == 0) denormalise(w.x, w.y[0], w.y[1], w.y[2], w.y[3], w.y[4], w.y[5], w.y[6], w.y[7], H);
 	__syncwarp();
@@ -275,14 +298,47 @@ __device__ unsigned warp_select(const unsigned *v, int n, int k, unsigned *hist,
 	return prefix;
 }
 
+// sum of each of P2 (a power of two <= 32) values over the lanes of a warp in P2 - 1 + (5 - log2 P2) exchanges instead of 5 P2:
+// at every stage a lane keeps one half of its values and trades the other half with its partner.  v[0] ends up holding the
+// total of element (lane >> (5 - log2 P2)).
+template<int P2> __device__ __forceinline__ void warp_transpose_sum(double *v, int lane){
+	int off = 16;
+#pragma unroll
+	for(int h = P2 / 2; h >= 1; h >>= 1){
+		const bool up = (lane & off) != 0;
+#pragma unroll
+		for(int j = 0; j < h; ++j){
+			const double send = up ? v[j] : v[j + h];
+			const double keep = up ? v[j + h] : v[j];
+			v[j] = keep + __shfl_xor_sync(FULL, send, off);
+		}
+		off >>= 1;
+	}
+#pragma unroll
+	for(; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(FULL, v[0], off);
+}
+
 template<int K> __device__ void block_sum(double (&v)[K], double (*s_red)[48], double *s_sum){
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	if constexpr(K >= 24){
+		static_assert(K <= 48, "block_sum: at most 48 values");
+		double a[32], b[16];
 #pragma unroll
-	for(int k = 0; k < K; ++k){
-		double x = v[k];
+		for(int k = 0; k < 32; ++k) a[k] = v[k];
 #pragma unroll
-		for(int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
-		if(lane == 0) s_red[warp][k] = x;
+		for(int k = 0; k < 16; ++k) b[k] = 32 + k < K ? v[32 + k < K ? 32 + k : 0] : 0.0;
+		warp_transpose_sum<32>(a, lane);
+		warp_transpose_sum<16>(b, lane);
+		s_red[warp][lane] = a[0];
+		if(!(lane & 1) && 32 + (lane >> 1) < K) s_red[warp][32 + (lane >> 1)] = b[0];
+	} else {
+#pragma unroll
+		for(int k = 0; k < K; ++k){
+			double x = v[k];
+#pragma unroll
+			for(int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
+			if(lane == 0) s_red[warp][k] = x;
+		}
 	}
 	__syncthreads();
 	if(tid < K){ double s = 0; for(int w = 0; w < EST_WARPS; ++w) s += s_red[w][tid]; s_sum[tid] = s; }
@@ -387,6 +443,7 @@ template<int NP> __device__ void lm_step_warp(const double *JtJ, const double *J
 	double b = JtErr[row] * scr;
 	bool used = lane >= NP;
 	int piv[NP];
+	double pinv[NP];
 #pragma unroll
 	for(int k = 0; k < NP; ++k){
 		double mag = used ? -1.0 : fabs(a[k]);
@@ -404,9 +461,10 @@ template<int NP> __device__ void lm_step_warp(const double *JtJ, const double *J
 		const double pb = __shfl_sync(FULL, b, who);
 		double dpv = pk[k];
 		if(fabs(dpv) < 1e-300) dpv = 1e-300;
+		pinv[k] = 1.0 / dpv;                       // one reciprocal per pivot, shared by the elimination and the back-substitution
 		if(lane == who) used = true;
 		if(!used){
-			const double f = a[k] / dpv;
+			const double f = a[k] * pinv[k];
 #pragma unroll
 			for(int j = k + 1; j < NP; ++j) a[j] -= f * pk[j];
 			b -= f * pb;
@@ -418,9 +476,7 @@ template<int NP> __device__ void lm_step_warp(const double *JtJ, const double *J
 		double t = b;
 #pragma unroll
 		for(int j = k + 1; j < NP; ++j) t -= a[j] * x[j];
-		double dpv = a[k];
-		if(fabs(dpv) < 1e-300) dpv = 1e-300;
-		x[k] = __shfl_sync(FULL, t / dpv, piv[k]);
+		x[k] = __shfl_sync(FULL, t * pinv[k], piv[k]);
 	}
 #pragma unroll
 	for(int k = 0; k < NP; ++k) if(lane == k) param[k] = prev[k] - x[k] * sc[k];
@@ -440,6 +496,7 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 	if(tid < NP) s_param[tid] = s_model[tid];
 	__syncthreads();
 	for(;;){
+		{ PROF_T0();
 		if(tid < 32){
 			if(tid == 0){
 				int cont = 1, want_J = 0, want_err = 0, step = 0;
@@ -468,7 +525,9 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 			if(s_flag[3]) lm_step_warp<NP>(s_JtJ, s_JtErr, s_prev, s_param, s_flag[4], tid);
 		}
 		__syncthreads();
+		PROF_ADD(4); }
 		if(!s_flag[0]) break;
+		PROF_T0();
 		const bool want_J = s_flag[1] != 0, want_err = s_flag[2] != 0;
 		++evals;
 		double h[NP];
@@ -513,7 +572,9 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 			}
 			acc[K - 1] += er0 * er0 + er1 * er1;
 		}
+		PROF_ADD(5);
 		block_sum<K>(acc, s_red, s_sum);
+		PROF_ADD(6);
 		if(tid == 0){
 			if(want_J){
 				int q = 0;
@@ -528,7 +589,18 @@ template<bool HOM> __device__ int lm_refine(const EstDev &e, double (*s_red)[48]
 }
 
 template<bool HOM>
-__global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
+__global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e_in){
+	const long long prof_k0 = clock64(); (void)prof_k0;
+	// up to EST_STAGED points live in shared memory for the whole kernel (every phase walks them; the subset draw by one thread
+	// is pure load latency otherwise); the mask goes back at the end
+	__shared__ float s_in[2 * EST_STAGED], s_out[2 * EST_STAGED];
+	__shared__ unsigned char s_mask[EST_STAGED];
+	EstDev e = e_in;
+	const bool staged = e_in.n <= EST_STAGED;
+	if(staged){
+		for(int i = threadIdx.x; i < 2 * e_in.n; i += EST_THREADS){ s_in[i] = e_in.in_pts[i]; s_out[i] = e_in.out_pts[i]; }
+		e.in_pts = s_in; e.out_pts = s_out; e.mask = s_mask;
+	}
 	__shared__ WarpWs s_ws[EST_WARPS];
 	__shared__ int s_idx[BATCH][EST_MAX_MODEL_PTS];
 	__shared__ int s_found[BATCH], s_valid[BATCH], s_good[BATCH];
@@ -560,6 +632,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 			niters = min(max(niters, 3), e.max_iters);
 		}
 		for(;;){
+			PROF_T0();
 			if(tid == 0){
 				// the first round is one hypothesis per warp: with mostly inliers RANSAC's adaptive count ends there
 				int nb = min(iter == 0 ? (int)EST_WARPS : BATCH, niters - iter);
@@ -570,6 +643,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 				s_ctl[0] = nb;
 			}
 			__syncthreads();
+			PROF_ADD(0);
 			const int nb = s_ctl[0];
 			for(int b = warp; b < nb; b += EST_WARPS){
 				if(!s_found[b]) continue;
@@ -613,6 +687,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 				}
 			}
 			__syncthreads();
+			PROF_ADD(1);
 			if(tid == 0){
 				// the reference's loop body over this round's hypotheses, in order (SSMEstimator.cc:101-127 / :176-202)
 				int stop = 0;
@@ -664,8 +739,15 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 		block_sum<1>(c, s_red, s_sum);
 		n_in = (int)s_sum[0];
 		__syncthreads();
+		PROF_T0();
 		if(method == M_RANSAC) fit_masked<HOM>(e, s_ws[0], s_red, s_sum, s_model);
+		PROF_ADD(2);
 		if(e.refine) evals = lm_refine<HOM>(e, s_red, s_sum, s_model);
+		PROF_ADD(3);
+	}
+	if(staged){
+		__syncthreads();
+		for(int i = tid; i < n; i += EST_THREADS) e_in.mask[i] = s_mask[i];
 	}
 	if(tid == 0){
 		double H[9];
@@ -683,6 +765,10 @@ __global__ void __launch_bounds__(EST_THREADS, 1) estimate_kernel(EstDev e){
 		}
 		// result | hypotheses drawn | inliers | LM evaluations, in the same buffer: one copy back
 		e.out[17] = result; e.out[18] = drawn; e.out[19] = n_in; e.out[20] = evals;
+#ifdef EST_PROF
+		g_prof[10] = (double)(clock64() - prof_k0);
+		for(int i = 0; i < 11; ++i){ e.out[21 + i] = g_prof[i]; g_prof[i] = 0; }
+#endif
 	}
 }
 

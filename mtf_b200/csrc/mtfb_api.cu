@@ -851,7 +851,7 @@ static mtfb_status est_reserve(mtfb_ctx *c, size_t n){
 	CUDA_TRY(cudaMalloc(&c->d_est_pts, 4 * n*sizeof(float)));
 	CUDA_TRY(cudaMalloc(&c->d_est_mask, n));
 	CUDA_TRY(cudaMalloc(&c->d_est_err, (size_t)EST_WARPS*n*sizeof(float)));
-	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 21 * sizeof(double)));
+	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 32 * sizeof(double)));
 	c->est_capacity = n;
 	return MTFB_OK;
 }
@@ -876,13 +876,19 @@ static mtfb_status est_run(mtfb_ctx *c, const char *who, int ssm, const float *d
 	e.out = c->d_est_out; e.mask = c->d_est_mask; e.err = c->d_est_err;
 	CUDA_TRY(launch_estimate(e, c->stream));
 	++c->launches;
-	double out[21];
+	double out[32];
 	CUDA_TRY(cudaMemcpyAsync(out, c->d_est_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
 	if(mask) CUDA_TRY(cudaMemcpyAsync(mask, c->d_est_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if(warp) std::memcpy(warp, out, 9 * sizeof(double));
 	if(state_update) std::memcpy(state_update, out + 9, (ssm == MTFB_SSM_HOMOGRAPHY ? 8 : 6)*sizeof(double));
 	if(info) for(int i = 0; i < 4; ++i) info[i] = (int)out[17 + i];
+#ifdef EST_PROF
+	if(std::getenv("MTFB_EST_PROF")){
+		std::fprintf(stderr, "est_prof cycles: draw %.0f  round %.0f  fit_inliers %.0f  lm %.0f (ctl+step %.0f  points %.0f  points+sum %.0f)  kernel %.0f\n",
+			out[21], out[22], out[23], out[24] - out[23], out[25], out[26], out[27], out[31]);
+	}
+#endif
 	return MTFB_OK;
 }
 

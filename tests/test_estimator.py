@@ -257,7 +257,9 @@ def test_device_estimator_options_and_edges():
         for method in ("ransac", "lmeds"):
             dev = t.estimate_warp_from_pts("homography", P, Q, api.make_est_params(method, seed=5, **kw))
             orc = O.estimate_warp("homography", P, Q, O.make_est_params(method, seed=5, **kw))
-            _same(dev, orc)
+            # max_iters = 3 leaves a model through a few points of a 25 %-outlier set: the probe corners are an extrapolation
+            # of it, where the two solvers' rounding shows at the 1e-5 px level
+            _same(dev, orc, tol=1e-6 if kw.get("max_iters", 2000) > 3 else 1e-4)
     # the default generator state (seed 0), affine with three-point models
     Pa, Qa, _ = make_points(500, warp=A_TRUE, noise=0.3, n_outliers=100, seed=22)
     _same(t.estimate_warp_from_pts("affine", Pa, Qa, api.make_est_params("ransac", seed=0, n_model_pts=3)),
