@@ -144,7 +144,9 @@ mtfb_status mtfb_synchronize(mtfb_ctx *ctx);
  * must be called before every initialize()/update(): it uploads the h x w float frame (row_stride in
  * elements) to the device asynchronously on the context stream. */
 mtfb_status mtfb_set_image(mtfb_ctx *ctx, const float *host_img, int h, int w, int row_stride);
-/* same, frame already resident on the device (pitch in elements); the pointer is used, not copied */
+/* same, frame already resident on the device (pitch in elements); the pointer is used, not copied: it must belong to the
+ * context's device, and the buffer must stay valid and unmodified until the work queued on it has finished (mtfb_synchronize,
+ * or any getter); writes to it must be ordered after that on the context stream (mtfb_set_stream) */
 mtfb_status mtfb_set_image_device(mtfb_ctx *ctx, const float *dev_img, int h, int w, int pitch);
 
 /* replaces the pre-processing in front of setImage: utils::GaussianSmoothing (PreProcBase::processFrame for CV_32FC1,

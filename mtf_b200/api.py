@@ -267,8 +267,10 @@ class BatchTracker:
         """img: float32 h x w NumPy array (CV_32FC1, inputType() of the reference trackers), or a CUDA
         float32 torch tensor (kept by reference, like the cv::Mat header ImageBase::setCurrImg keeps)."""
         if hasattr(img, "data_ptr"):      # torch tensor
-            if not img.is_cuda or img.dtype.itemsize != 4 or img.dim() != 2 or img.stride(1) != 1:
+            if not img.is_cuda or str(img.dtype) != "torch.float32" or img.dim() != 2 or img.stride(1) != 1:
                 raise MTFError(1, "setImage: CUDA float32 2-D tensor with unit column stride required")
+            if img.device.index is not None and img.device.index != self.params.device:
+                raise MTFError(1, "setImage: the tensor lives on cuda:%d, the context on cuda:%d" % (img.device.index, self.params.device))
             self._img = img
             self._check(self._L.mtfb_set_image_device(self._h, C.c_void_p(img.data_ptr()), img.shape[0],
                                                       img.shape[1], img.stride(0)))

@@ -27,6 +27,7 @@
 //
 // This file is compiled with -fmad=false like the rest (the fp64 slow path must not contract); fp32 fused
 // multiply-adds are spelled fmaf().
+#include <mutex>
 #include "lk_f32.cuh"
 
 namespace mtfb {
@@ -463,23 +464,26 @@ template<int SSM, int SM, int T, int MINB, int U> static cudaError_t launch_one(
 #ifdef MTFB_F32_NO_WINDOW    // experiment: gather from the frame in global memory
 	win_bytes = 0;
 #endif
-	static bool configured_dev[64] = {};             // per instantiation and device; attributes are per function and sticky
+	// per instantiation and device; attributes are per function and sticky: the carve-out follows the largest footprint seen
+	static size_t configured_dev[64] = {};
+	static std::mutex mu;                            // contexts of different host threads may share an instantiation
+	std::lock_guard<std::mutex> lock(mu);
 	int dev = 0;
 	cudaGetDevice(&dev);
-	bool &configured = configured_dev[dev & 63];
-	if(!configured){
-		cudaError_t e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 / MINB + 32 * 1024);
+	size_t &configured = configured_dev[dev & 63];
+	cudaFuncAttributes fa;
+	cudaError_t e = cudaFuncGetAttributes(&fa, ssd_update_f32_kernel<SSM, SM, T, MINB, U>);
+	if(e != cudaSuccess) return e;
+	// shared memory carve-out: what MINB resident CTAs need (static + dynamic + 1 KB the system reserves per CTA);
+	// the rest of the SM's 228 KB stays L1 for the image gathers.  Too small a carve-out would cost resident CTAs.
+	const size_t per_cta = fa.sharedSizeBytes + (size_t)b.I0f_stride*sizeof(float) + slow_bytes + (size_t)F32_WIN*F32_WINP*sizeof(float) + 1024;
+	if(per_cta > configured){
+		e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 / MINB + 32 * 1024);
 		if(e != cudaSuccess) return e;
-		// shared memory carve-out: what MINB resident CTAs need (static + dynamic + 1 KB the system reserves per CTA);
-		// the rest of the SM's 228 KB stays L1 for the image gathers.  Too small a carve-out would cost resident CTAs.
-		cudaFuncAttributes fa;
-		e = cudaFuncGetAttributes(&fa, ssd_update_f32_kernel<SSM, SM, T, MINB, U>);
-		if(e != cudaSuccess) return e;
-		const size_t per_cta = fa.sharedSizeBytes + (size_t)b.I0f_stride*sizeof(float) + slow_bytes + (size_t)F32_WIN*F32_WINP*sizeof(float) + 1024;
 		const int carve = (int)((per_cta*MINB * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
 		e = cudaFuncSetAttribute(ssd_update_f32_kernel<SSM, SM, T, MINB, U>, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
 		if(e != cudaSuccess) return e;
-		configured = true;
+		configured = per_cta;
 	}
 	if(slow_bytes > 16 * 1024) return cudaErrorInvalidValue;      // > 4 M pixels per patch
 	ssd_update_f32_kernel<SSM, SM, T, MINB, U><<<b.P, T, smem + slow_bytes + win_bytes, st>>>(b, (unsigned)smem, (unsigned)(win_bytes / sizeof(float)));

@@ -28,21 +28,27 @@ def homography_dlt(src, dst):
     solution."""
     src = np.asarray(src, dtype=np.float64).reshape(2, 4)
     dst = np.asarray(dst, dtype=np.float64).reshape(2, 4)
-    A = np.zeros((8, 8)); b = np.zeros(8)
-    for i in range(4):
-        x, y, u, v = src[0, i], src[1, i], dst[0, i], dst[1, i]
-        A[2 * i] = [x, y, 1, 0, 0, 0, -u * x, -u * y]
-        A[2 * i + 1] = [0, 0, 0, x, y, 1, -v * x, -v * y]
-        b[2 * i], b[2 * i + 1] = u, v
+    x, y, u, v = src[0], src[1], dst[0], dst[1]
+    A = np.zeros((8, 8))
+    A[0::2, 0], A[0::2, 1], A[0::2, 2], A[0::2, 6], A[0::2, 7] = x, y, 1.0, -u * x, -u * y
+    A[1::2, 3], A[1::2, 4], A[1::2, 5], A[1::2, 6], A[1::2, 7] = x, y, 1.0, -v * x, -v * y
+    b = np.empty(8)
+    b[0::2], b[1::2] = u, v
     h = np.linalg.solve(A, b)
     return np.append(h, 1.0).reshape(3, 3)
 
 
+_NORM_CACHE = {}
+
+
 def pts_from_corners(corners, resx, resy):
     """utils::getPtsFromCorners (warpUtils.cc:34-60): the regular grid of the unit square under the 4-corner homography"""
-    pts, nc = norm_unit_square_pts(resx, resy)
-    H = homography_dlt(nc, corners)
-    q = H @ np.vstack([pts, np.ones(pts.shape[1])])
+    key = (resx, resy)
+    if key not in _NORM_CACHE:
+        pts, nc = norm_unit_square_pts(resx, resy)
+        _NORM_CACHE[key] = (np.vstack([pts, np.ones(pts.shape[1])]), nc)
+    pts_hm, nc = _NORM_CACHE[key]
+    q = homography_dlt(nc, corners) @ pts_hm
     return q[:2] / q[2]
 
 
@@ -101,6 +107,7 @@ class GridTracker:
         self.ssm_update = None
         self.pix_mask = np.ones(n, dtype=np.uint8)
         self.last_estimate = None
+        self._ids = None
 
     # the region's sample points after ssm.setCorners / ssm.initialize (ProjectiveBase.cc:27-39, Homography.cc:50-71)
     def _set_corners(self, corners):
@@ -109,24 +116,30 @@ class GridTracker:
 
     def cell_corners(self):
         """GridTracker::resetTrackers (GridTracker.cc:345-392): the region of every patch tracker, (P, 2, 4)"""
-        t = np.arange(self.n_trackers)
-        r, c = t // self.gx, t % self.gx
+        if self._ids is None:
+            t = np.arange(self.n_trackers)
+            r, c = t // self.gx, t % self.gx
+            w = self.gx + 1
+            self._ids = np.stack([r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c], axis=0)      # (4, P)
         pc = None
         if self.resx == self.gx + 1:
-            w = self.gx + 1
-            ids = np.stack([r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c], axis=1)      # (P, 4)
-            pc = self.pts[:, ids].transpose(1, 0, 2)                                                       # (P, 2, 4)
+            pc = self.pts.take(self._ids, axis=1)                                                            # (2, 4, P)
         # (with resx = grid_size_x the reference still indexes the (grid_size + 1)-wide table, GridTracker.cc:361-371, and then
         # overwrites the result: only the fixed-size branch is meaningful there)
+        out = np.empty((2, 4, self.n_trackers))
         if not self.dyn_patch_size:
             if self.patch_centroid_inside:
-                cen = (pc[:, :, 0] + pc[:, :, 1] + pc[:, :, 2] + pc[:, :, 3]) / 4.0
+                cen = (pc[:, 0] + pc[:, 1] + pc[:, 2] + pc[:, 3]) / 4.0                                      # (2, P)
             else:
-                cen = self.pts[:, t].T
-            x0, y0 = cen[:, 0] - self.patch_size_x / 2.0, cen[:, 1] - self.patch_size_y / 2.0
+                cen = self.pts[:, :self.n_trackers]
+            x0, y0 = cen[0] - self.patch_size_x / 2.0, cen[1] - self.patch_size_y / 2.0
             x1, y1 = x0 + self.patch_size_x, y0 + self.patch_size_y
-            pc = np.stack([np.stack([x0, x1, x1, x0], axis=1), np.stack([y0, y0, y1, y1], axis=1)], axis=1)
-        return np.ascontiguousarray(pc)
+            out[0, 0] = x0; out[0, 3] = x0; out[0, 1] = x1; out[0, 2] = x1
+            out[1, 0] = y0; out[1, 1] = y0; out[1, 2] = y1; out[1, 3] = y1
+        else:
+            out[:] = pc
+        out = np.ascontiguousarray(out.transpose(2, 0, 1))
+        return out
 
     def _reset_trackers(self, reinit):
         cells = self.cell_corners()
