@@ -228,14 +228,14 @@ struct PassRegs {
 	int X0, Y0;
 };
 
-// chain rule and sums of one pixel once its sample is known (shared by the three evaluation tiers): gradient with respect to
-// (u, v), scaled as the reference's dI/dp is (Homography.cc:250-262 in the grid frame); valid = false adds nothing
-template<int SSM> __device__ __forceinline__ void mom_pixel_back(const PassRegs &k, const float4 &vt, bool proj, float wxl, float wyl,
-	float invD, float gx, float gy, float val, float i0, bool valid, MomAcc<SSM> &acc){
+// chain rule of one pixel once its sample is known (shared by the three evaluation tiers): gradient with respect to
+// (u, v), scaled as the reference's dI/dp is (Homography.cc:250-262 in the grid frame), and the residual; valid = false gives
+// zeros.  cZ: the column's part of hz (general quadrilaterals only)
+template<int SSM> __device__ __forceinline__ void mom_pixel_grad(const PassRegs &k, float cZ, float v, bool proj, float wxl, float wyl,
+	float invD, float gx, float gy, float val, float i0, bool valid, float &Gu, float &Gv, float &r){
 	float gs = valid ? invD : 0.0f;
-	if(SSM == SSM_HOM && proj) gs *= rcp_approx(fmaf(k.d7, vt.x, k.cZ));
+	if(SSM == SSM_HOM && proj) gs *= rcp_approx(fmaf(k.d7, v, cZ));
 	const float gxd = gx * gs, gyd = gy * gs;
-	float Gu, Gv;
 	if(SSM == SSM_HOM){
 		Gu = fmaf(fmaf(-k.m6, wxl, k.m0), gxd, fmaf(-k.m6, wyl, k.m3) * gyd);
 		Gv = fmaf(fmaf(-k.m7, wxl, k.m1), gxd, fmaf(-k.m7, wyl, k.m4) * gyd);
@@ -243,7 +243,13 @@ template<int SSM> __device__ __forceinline__ void mom_pixel_back(const PassRegs 
 		Gu = fmaf(k.m0, gxd, k.m3 * gyd);
 		Gv = fmaf(k.m1, gxd, k.m4 * gyd);
 	}
-	const float r = valid ? val - i0 : 0.0f;                                      // I_diff (SSDBase.cc:78)
+	r = valid ? val - i0 : 0.0f;                                                  // I_diff (SSDBase.cc:78)
+}
+// ... and its sums
+template<int SSM> __device__ __forceinline__ void mom_pixel_back(const PassRegs &k, const float4 &vt, bool proj, float wxl, float wyl,
+	float invD, float gx, float gy, float val, float i0, bool valid, MomAcc<SSM> &acc){
+	float Gu, Gv, r;
+	mom_pixel_grad<SSM>(k, k.cZ, vt.x, proj, wxl, wyl, invD, gx, gy, val, i0, valid, Gu, Gv, r);
 	acc.add(Gu, Gv, -r, r, vt);                                                   // df_dIt = -I_diff (SSDBase.cc:115-121)
 }
 
@@ -291,8 +297,8 @@ template<int SSM, bool WIN> __device__ __forceinline__ bool mom_pixel(const Pass
 // patch like tier 1, from the frame in global memory.  Returns false for the rest (on or next to the pixel lattice, outside
 // the frame): tier 3.
 struct MidArgs { Image img; const double *xv, *yv, *M; double uc, uh, vc, vh, d2; int X0, Y0; };
-template<int SSM> __device__ __forceinline__ bool mom_pixel_mid(const PassRegs &k, const MidArgs &a, const float4 &vt, bool proj,
-	int row, int col, float i0, MomAcc<SSM> &acc){
+template<int SSM> __device__ __forceinline__ bool mom_pixel_mid(const PassRegs &k, const MidArgs &a, float cZ, float v32, bool proj,
+	int row, int col, float i0, float &Gu, float &Gv, float &r){
 	const double u = (__ldg(a.xv + col) - a.uc) / a.uh, v = (__ldg(a.yv + row) - a.vc) / a.vh;
 	const double nx = fma(a.M[0], u, fma(a.M[1], v, a.M[2])), ny = fma(a.M[3], u, fma(a.M[4], v, a.M[5]));
 	double rd = 1.0, x = nx, y = ny;
@@ -312,18 +318,18 @@ template<int SSM> __device__ __forceinline__ bool mom_pixel_mid(const PassRegs &
 	const float gy = bot - top;
 	const float val = fmaf(dyf, gy, top);
 	const float gx = fmaf(dyf, t1 - t0, t0);
-	mom_pixel_back<SSM>(k, vt, proj, (float)(x - a.X0), (float)(y - a.Y0), (float)rd, gx, gy, val, i0, true, acc);
+	mom_pixel_grad<SSM>(k, cZ, v32, proj, (float)(x - a.X0), (float)(y - a.Y0), (float)rd, gx, gy, val, i0, true, Gu, Gv, r);
 	return true;
 }
 
 // TIER 3.  The same pixel through the reference-exact fp64 functions (lk_f32.cuh exact_pixel), then the fp32 chain rule and sums.
-template<int SSM> __device__ __forceinline__ void mom_pixel_exact(const DevBatch &b, const PassRegs &k, const float4 &vt, bool proj,
-	const double *s_dlt, const double *s_W, int row, int col, float i0, MomAcc<SSM> &acc){
+template<int SSM> __device__ __forceinline__ void mom_pixel_exact(const DevBatch &b, const PassRegs &k, float cZ, float v32, bool proj,
+	const double *s_dlt, const double *s_W, int row, int col, float i0, float &Gu, float &Gv, float &r){
 	ExactArgs a;
 	a.img = b.img; a.xv = b.xv; a.yv = b.yv; a.s_dlt = s_dlt; a.s_W = s_W; a.grad_eps = b.grad_eps; a.grad_mult = b.grad_mult;
 	a.norm_init = b.norm_init; a.X0 = k.X0; a.Y0 = k.Y0;
 	const ExactOut e = exact_pixel<SSM>(a, row, col);
-	mom_pixel_back<SSM>(k, vt, proj, e.wxl, e.wyl, e.invD, e.gx, e.gy, e.val, i0, true, acc);
+	mom_pixel_grad<SSM>(k, cZ, v32, proj, e.wxl, e.wyl, e.invD, e.gx, e.gy, e.val, i0, true, Gu, Gv, r);
 }
 
 } // namespace mom
@@ -363,7 +369,8 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 	constexpr int NM = MT::NM, NR = NM + 1;                // moments + sum r^2
 	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	MOM_PROF_KERNEL_T(0)
-	__shared__ double s_part[(T / 32) * NR];
+	constexpr int PART = NR > 48 ? NR : 48;                 // per warp: NR partial sums, or 32 x 3 floats of pooled deferred pixels
+	__shared__ double s_part[(T / 32) * PART];
 	__shared__ double s_sum[L::NA];
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8], s_dlt[9], s_Dt[9];
 	__shared__ double s_J[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_Tinv[S*S], s_x[S], s_dp[S];
@@ -487,14 +494,61 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 #if MTFB_PROF == 2
 			prof_slow += __popc(slow);
 #endif
-			while(slow){
-				const int i = c0 + __ffs((int)slow) - 1;
-				slow &= slow - 1;
+			// THE DEFERRED PIXELS, SHARED OUT OVER THE WARP.  A sampling-grid row or column that lands within the guard band of
+			// the pixel lattice defers all its pixels at once; a column's fall on the two or three threads that own it (up to 25
+			// evaluations of ~1 K cycles one after the other: such a patch used to set the duration of the whole launch,
+			// profiles/r02_patch_spread.txt).  Any lane can evaluate any pixel of the patch -- only the sums are tied to the
+			// column -- so the warp pools its deferred pixels, lane j evaluates the j-th of them, and the owners add the results
+			// to their sums in the order they would have used alone.
+			if(__any_sync(FULL_MASK, slow != 0u)){
+				float *res = reinterpret_cast<float*>(s_part + warp*PART);       // 32 x (Gu, Gv, r): free until the reduction
+				const unsigned cnt = (unsigned)__popc(slow);
+				unsigned incl = cnt;
+#pragma unroll
+				for(int off = 1; off < 32; off <<= 1){
+					const unsigned t = __shfl_up_sync(FULL_MASK, incl, off);
+					if(lane >= off) incl += t;
+				}
+				const unsigned total = __shfl_sync(FULL_MASK, incl, 31), first = incl - cnt;
 				MidArgs ma;
 				ma.img = b.img; ma.xv = b.xv; ma.yv = b.yv; ma.M = s_M64; ma.uc = s_gc[0]; ma.uh = s_gc[1]; ma.vc = s_gc[2]; ma.vh = s_gc[3];
 				ma.d2 = 2.0*b.grad_eps + 1e-9; ma.X0 = k.X0; ma.Y0 = k.Y0;
-				if(!mom_pixel_mid<SSM>(k, ma, s_vtab[row0 + i], proj, row0 + i, col, tmpl[i*resx], acc))
-					mom_pixel_exact<SSM>(b, k, s_vtab[row0 + i], proj, s_dlt, s_W, row0 + i, col, tmpl[i*resx], acc);
+				for(unsigned start = 0; start < total; start += 32){
+					// whose pixel is number start + lane?  the last lane whose run begins at or before it
+					const unsigned want = start + lane;
+					int owner = 0;
+					for(int l = 0; l < 32; ++l){
+						const unsigned fl = __shfl_sync(FULL_MASK, first, l), cl = __shfl_sync(FULL_MASK, cnt, l);
+						if(cl != 0u && fl <= want) owner = l;
+					}
+					const unsigned o_slow = __shfl_sync(FULL_MASK, slow, owner), o_first = __shfl_sync(FULL_MASK, first, owner);
+					const int o_row0 = __shfl_sync(FULL_MASK, row0, owner), o_col = __shfl_sync(FULL_MASK, col, owner);
+					const float o_cZ = __shfl_sync(FULL_MASK, k.cZ, owner);
+					if(want < total){
+						const int bit = (int)__fns(o_slow, 0u, (int)(want - o_first) + 1);
+						const int row = o_row0 + c0 + bit;
+						const float i0 = (use_smem ? (const float*)s_dyn : I0)[row*resx + o_col];
+						const float v32 = s_vtab[row].x;
+						float Gu, Gv, r;
+						if(!mom_pixel_mid<SSM>(k, ma, o_cZ, v32, proj, row, o_col, i0, Gu, Gv, r))
+							mom_pixel_exact<SSM>(b, k, o_cZ, v32, proj, s_dlt, s_W, row, o_col, i0, Gu, Gv, r);
+						res[3 * lane] = Gu; res[3 * lane + 1] = Gv; res[3 * lane + 2] = r;
+					}
+					__syncwarp();
+					{
+						unsigned m = slow, j = first;
+						while(m){
+							const int i = c0 + __ffs((int)m) - 1;
+							m &= m - 1;
+							if(j >= start && j < start + 32u){
+								const float *q = res + 3 * (j - start);
+								acc.add(q[0], q[1], -q[2], q[2], s_vtab[row0 + i]);
+							}
+							++j;
+						}
+					}
+					__syncwarp();
+				}
 			}
 		}
 		// moments: u^a S_b
@@ -511,7 +565,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 		{
 			int idx[3];
 			warp_reduce_scatter<NR>(mv, lane, idx);
-			double *dst = s_part + warp*NR;
+			double *dst = s_part + warp*PART;
 			if(idx[0] >= 0) dst[idx[0]] = (double)mv[0];
 			if(idx[1] >= 0) dst[idx[1]] = (double)mv[1];
 			if(NR > 64 && idx[2] >= 0) dst[idx[2]] = (double)mv[2];
@@ -520,7 +574,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 				double a = 0;
 				if(e == 0){
 #pragma unroll
-					for(int w = 0; w < T / 32; ++w) a += s_part[w*NR + NM];
+					for(int w = 0; w < T / 32; ++w) a += s_part[w*PART + NM];
 				} else if(e < 1 + S){
 					const signed char (*g)[2][2] = MT::grad_dev();
 #pragma unroll
@@ -529,7 +583,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 						if(mi >= 0){
 							double s = 0;
 #pragma unroll
-							for(int w = 0; w < T / 32; ++w) s += s_part[w*NR + mi];
+							for(int w = 0; w < T / 32; ++w) s += s_part[w*PART + mi];
 							a = fma((double)g[e - 1][t][1], s, a);
 						}
 					}
@@ -541,7 +595,7 @@ __global__ void __launch_bounds__(T, MINB) ssd_fclk_mom_kernel(DevBatch b, const
 						if(mi >= 0){
 							double s = 0;
 #pragma unroll
-							for(int w = 0; w < T / 32; ++w) s += s_part[w*NR + mi];
+							for(int w = 0; w < T / 32; ++w) s += s_part[w*PART + mi];
 							a = fma((double)h[e - 1 - S][t][1], s, a);
 						}
 					}
