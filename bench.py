@@ -248,11 +248,19 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
     d_corners = sharding.device_view(tr.device_results()[0], (P, 8), dev)
 
     gathered = torch.empty((n_total, 8), dtype=torch.float64, device=dev) if world > 1 else None
+    peer = world > 1 and args.collective == "peer"
+    if peer:
+        # the library's own exchange over NVLink peer memory: the update kernel stores each patch's corners into the gathered
+        # arrays of all ranks (CUDA IPC mappings), mtfb_peer_gather signals / waits -- no collective library on the path
+        handles = sharding.exchange_peer_handles(tr.peer_export(n_total))
+        tr.peer_attach(env.rank, world, sharding.shard_range(n_total, world, env.rank)[0], handles)
 
     def gather():
         # north_star: one all-gather of the per-patch results over NVLink (per frame: LK iterations of different patches
         # never interact)
-        if world > 1:
+        if peer:
+            tr.peer_gather()
+        elif world > 1:
             sharding.all_gather_rows(d_corners, n_total, out=gathered)
 
     tr.initialize(corners, d_frames[0])
@@ -272,6 +280,13 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
     for i in range(args.warmup):
         step_device(i)
     barrier()
+    if peer:
+        # the peer exchange against NCCL's all-gather of the same frame: identical bytes on every rank
+        ptr, n = tr.peer_gathered_ptr()
+        sharding.all_gather_rows(d_corners, n_total, out=gathered)
+        same = bool(torch.equal(sharding.device_view(ptr, (n, 8), dev), gathered))
+        if not same:
+            raise RuntimeError("rank %d: the peer-memory exchange differs from NCCL's all-gather" % env.rank)
     launches0 = tr.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -340,6 +355,7 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
         t1.record(stream)
         barrier()
         tr.update()                                  # consumes the last prefetched frame (pipelined) before the next arm
+        gather()
         tr.synchronize()
         return max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0)), (w0, time.time())
 
@@ -426,7 +442,9 @@ def config2_line(args, env, sampler, strong):
                    "frames": "ping-pong over frames 1..%d of the synthetic sequence; frame 0 initialises" % (N_FRAMES - 1),
                    "l2": "flushed between timed steps (256 MB write)", "threads_per_patch": args.threads or "auto",
                    "occupancy": args.occ if args.threads else "auto",
-                   "collective": "all_gather of P x 8 corners per frame from the kernel's output buffer" if world > 1 else "none"},
+                   "collective": ("none" if world == 1 else "per frame, fused: the update kernel stores the P x 8 corners into every rank's gathered "
+                                  "array over NVLink peer memory (CUDA IPC), one signal / wait kernel; checked against NCCL's all-gather"
+                                  if args.collective == "peer" else "NCCL all_gather of the P x 8 corners per frame from the kernel's output buffer")},
         "e2e": {"value": total_iters / (main["e2e_ms"] * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8,
                 "upload": "frame i + 1 uploads on the library's copy stream while update(i) runs (mtfb_set_image_async, two device "
@@ -530,6 +548,9 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="config 2: do not append the other configurations' lines")
     ap.add_argument("--pitch-pad", type=int, default=0, help="experiment: extra floats per device frame row")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, config 2: the per-frame exchange of the corners -- the library's own stores into peer memory over "
+                         "NVLink (mtfb_peer_*) or NCCL's all-gather of the result buffer")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

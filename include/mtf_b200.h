@@ -309,6 +309,28 @@ mtfb_status mtfb_get_curr_stage_f32(mtfb_ctx *ctx, int *idx /* P x N x 2 */, flo
 mtfb_status mtfb_device_results(mtfb_ctx *ctx, double **d_corners, double **d_state, int **d_n_iters);
 int mtfb_state_size(const mtfb_ctx *ctx);
 
+/* ---- Multi-GPU: the per-frame exchange of the batch's corners over NVLink peer memory (one process per GPU).
+ * The reference's fan-out is a shared-memory loop over trackers[i]->update() whose results every later stage reads
+ * (SM/src/GridTracker.cc:247-274: the cells' regions feed ssm.estimateWarpFromPts); split over GPUs, each rank tracks a
+ * contiguous range of the job's n_total patches and needs all n_total x 8 corners after every frame.  No collective library:
+ * every rank exports an array (CUDA IPC), maps the others', and the update kernels store each patch's final corners
+ * straight into the arrays of all ranks; mtfb_peer_gather then publishes / awaits one sequence flag per rank.
+ *   mtfb_peer_export   allocate this rank's gathered array (n_total x 8 fp64, double-buffered) and return its IPC handle;
+ *                      the host exchanges the handles (any transport: torch.distributed, MPI, a file)
+ *   mtfb_peer_attach   rank / world (<= 8) / this rank's first row / the handles of all ranks (its own entry is ignored)
+ *   mtfb_peer_gather   after mtfb_update (or initialize / set_region: their corners are pushed by one small kernel):
+ *                      stream-ordered; when it has run, the local gathered array is complete.  Every rank calls it once per
+ *                      frame; mtfb_update refuses to start the next frame before.
+ *   mtfb_peer_gathered device pointer of the current gathered array (valid until the next but one frame)
+ *   mtfb_get_gathered_region  the same, copied to the host (synchronises; reports a rank that never signalled) */
+#define MTFB_PEER_HANDLE_BYTES 64
+typedef struct mtfb_peer_handle { unsigned char bytes[MTFB_PEER_HANDLE_BYTES]; } mtfb_peer_handle;
+mtfb_status mtfb_peer_export(mtfb_ctx *ctx, int n_total, mtfb_peer_handle *out);
+mtfb_status mtfb_peer_attach(mtfb_ctx *ctx, int rank, int world, int row0, const mtfb_peer_handle *handles /* world */);
+mtfb_status mtfb_peer_gather(mtfb_ctx *ctx);
+mtfb_status mtfb_peer_gathered(mtfb_ctx *ctx, const double **d_corners /* n_total x 8 */, int *n_total);
+mtfb_status mtfb_get_gathered_region(mtfb_ctx *ctx, double *out /* n_total x 8 */);
+
 /* test entry point (no reference counterpart as a function: the solve inside nt::FCLK / ESM / ICLK::update,
  * `H.colPivHouseholderQr().solve(J^T)`, SM/src/NT/FCLK.cc:298, NT/ESM.cc:266, NT/ICLK.cc:228): runs the device's warp-level
  * column-pivoted Householder QR on n_sys caller-supplied n x n systems (n = 6 or 8; A column-major, host pointers).

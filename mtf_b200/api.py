@@ -95,8 +95,10 @@ EXPORTS = [
     "mtfb_pf_default_params", "mtfb_pf_configure", "mtfb_pf_set_random_stream", "mtfb_pf_get_random_stream", "mtfb_pf_get_particles",
     "mtfb_est_default_params", "mtfb_estimate_warp_from_pts", "mtfb_estimate_warp_from_corners_device", "mtfb_grid_enable", "mtfb_grid_estimate", "mtfb_grid_commit",
     "mtfb_grid_get_pts",
+    "mtfb_peer_export", "mtfb_peer_attach", "mtfb_peer_gather", "mtfb_peer_gathered", "mtfb_get_gathered_region",
 ]
 
+PEER_HANDLE_BYTES = 64
 _lib = None
 
 
@@ -154,6 +156,11 @@ def load_library(path=LIB_PATH):
     L.mtfb_grid_estimate.argtypes = [vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
     L.mtfb_grid_commit.argtypes = [vp]
     L.mtfb_grid_get_pts.argtypes = [vp, vp, vp]
+    L.mtfb_peer_export.argtypes = [vp, C.c_int, vp]
+    L.mtfb_peer_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.mtfb_peer_gather.argtypes = [vp]
+    L.mtfb_peer_gathered.argtypes = [vp, C.POINTER(vp), ip]
+    L.mtfb_get_gathered_region.argtypes = [vp, dp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("mtfb_last_error", "mtfb_version", "mtfb_launch_count", "mtfb_default_params", "mtfb_pf_default_params",
@@ -464,6 +471,33 @@ class BatchTracker:
         a = np.empty((self.P, 2), dtype=np.float32); b = np.empty((self.P, 2), dtype=np.float32)
         self._check(self._L.mtfb_grid_get_pts(self._h, a.ctypes.data, b.ctypes.data))
         return a, b
+
+    # ---------------------------------------------------------------- multi-GPU exchange over NVLink peer memory
+    def peer_export(self, n_total):
+        """allocate this rank's gathered array for a job of n_total patches; returns its 64-byte CUDA IPC handle"""
+        h = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)
+        self._check(self._L.mtfb_peer_export(self._h, int(n_total), h.ctypes.data))
+        self._peer_n_total = int(n_total)
+        return h
+
+    def peer_attach(self, rank, world, row0, handles):
+        """handles: (world, 64) uint8, the ranks' peer_export() results in rank order"""
+        h = np.ascontiguousarray(np.asarray(handles, dtype=np.uint8).reshape(world, PEER_HANDLE_BYTES))
+        self._check(self._L.mtfb_peer_attach(self._h, int(rank), int(world), int(row0), h.ctypes.data))
+
+    def peer_gather(self):
+        """after update(): signal the peers and wait for theirs (stream-ordered)"""
+        self._check(self._L.mtfb_peer_gather(self._h))
+
+    def peer_gathered_ptr(self):
+        a, n = C.c_void_p(), C.c_int()
+        self._check(self._L.mtfb_peer_gathered(self._h, C.byref(a), C.byref(n)))
+        return a.value, n.value
+
+    def getGatheredRegion(self):
+        out = np.empty((self._peer_n_total, 2, 4))
+        self._check(self._L.mtfb_get_gathered_region(self._h, _dp(out)))
+        return out
 
     def device_results(self):
         """raw device pointers (corners P x 8 f64, state P x S f64, n_iters P i32)"""

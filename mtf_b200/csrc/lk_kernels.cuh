@@ -8,6 +8,12 @@ namespace mtfb {
 
 // Everything one launch needs, passed by value.  All pointers are device pointers; per-patch arrays are
 // indexed [patch][...] (SoA per patch so that consecutive threads touch consecutive addresses).
+// Multi-GPU exchange over NVLink peer memory (peer_gather.cu): where the ranks of the job keep their (n_total x 8) arrays of
+// gathered corners -- this rank's own and, mapped through CUDA IPC, the others' -- and this rank's first row in them.
+// The update kernels store a patch's final corners straight into all of them (n = 0: single GPU, nothing extra).
+enum { MTFB_MAX_PEERS = 8 };
+struct PeerOut { double *dst[MTFB_MAX_PEERS]; int n, row0; };
+
 struct DevBatch {
 	int P, N, resx, resy;
 	Image img;
@@ -43,6 +49,7 @@ struct DevBatch {
 	double epsilon, lm_delta_init, lm_delta_update, grad_eps;
 	double pix_mult, pix_add;    // am pix_norm_mult / pix_norm_add (1, 0 except MI)
 	double grad_mult;            // pix_mult / (2 grad_eps)  (imgUtils.cc:238)
+	PeerOut peers;               // gathered-corner arrays of all ranks (fused all-gather), n = 0 unless mtfb_peer_attach
 };
 
 struct StageTaps { double *pts, *pix_vals, *pix_grad, *pix_jac; };
@@ -58,6 +65,11 @@ cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corner
 // setRegion of the search methods that keep template Jacobians (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): SSD
 cudaError_t launch_reinit_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
+// peer_gather.cu: corners -> every rank's gathered array (producers other than the update kernels); flags to the peers +
+// wait for theirs (one warp; *d_err set on time-out)
+cudaError_t launch_peer_push(const double *corners, int P, const PeerOut &peers, cudaStream_t st);
+cudaError_t launch_peer_signal_wait(unsigned *const *peer_flags, unsigned *my_flags, int rank, int world, unsigned seq, int *d_err,
+	cudaStream_t st);
 // lk_ssd_f32.cu
 cudaError_t launch_update_ssd_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_stage_f32(int ssm, const DevBatch &b, const StageTapsF32 &t, cudaStream_t st);

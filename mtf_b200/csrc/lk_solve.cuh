@@ -195,7 +195,12 @@ template<int SSM> __device__ __forceinline__ void store_patch_state(const DevBat
 		for(int s = 0; s < S; ++s) st[s] = s_state[s];
 	}
 	if(lane < 9) b.warp[(size_t)p * 9 + lane] = W.m[lane];
-	if(lane < 8) b.corners[(size_t)p * 8 + lane] = s_corners[lane];
+	if(lane < 8){
+		const double c = s_corners[lane];
+		b.corners[(size_t)p * 8 + lane] = c;
+		// the all-gather, fused: the same 64 bytes into the gathered array of every rank of the job (peer memory, NVLink)
+		for(int r = 0; r < b.peers.n; ++r) b.peers.dst[r][(size_t)(b.peers.row0 + p) * 8 + lane] = c;
+	}
 #pragma unroll
 	for(int s = 0; s < S; ++s) if(lane == s) b.state[(size_t)p*S + s] = st[s];
 	if(lane == 0){ b.f[p] = f; b.n_iters[p] = n_passes; b.status[p] = patch_status; }

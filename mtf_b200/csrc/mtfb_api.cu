@@ -179,6 +179,11 @@ struct mtfb_ctx {
 	// own prev_pts / curr_pts after mtfb_grid_enable
 	float *d_est_pts; unsigned char *d_est_mask; float *d_est_err; double *d_est_out; size_t est_capacity;
 	float *d_grid_prev, *d_grid_curr; bool grid_enabled;
+	// the all-gather over NVLink peer memory (peer_gather.cu): this rank's two gathered arrays + flag row + error word in one
+	// allocation, the other ranks' mapped through CUDA IPC
+	double *d_peer_buf; int peer_n_total, peer_rank, peer_world, peer_row0; bool peer_attached, peer_pending;
+	unsigned peer_seq;
+	double *peer_base[MTFB_MAX_PEERS]; unsigned *peer_flags[MTFB_MAX_PEERS]; void *peer_mapped[MTFB_MAX_PEERS];
 	alignas(64) CUtensorMap frame_map; const float *frame_map_ptr; int frame_map_h, frame_map_w, frame_map_pitch; bool frame_map_ok;
 };
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -208,6 +213,11 @@ static const void *frame_map_for(mtfb_ctx *c){
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	c->frame_map_ok = (r == CUDA_SUCCESS);
 	return c->frame_map_ok ? &c->frame_map : nullptr;
+}
+static void peer_out_for(const mtfb_ctx *c, unsigned seq, PeerOut &po){
+	po.n = c->peer_world; po.row0 = c->peer_row0;
+	for(int r = 0; r < MTFB_MAX_PEERS; ++r)
+		po.dst[r] = r < c->peer_world ? c->peer_base[r] + (size_t)(seq & 1u)*c->peer_n_total * 8 : nullptr;
 }
 static const int4 *mom_work_for(const mtfb_ctx *c){
 	if(!c->d_mom_work) return nullptr;
@@ -247,6 +257,8 @@ mtfb_status mtfb_destroy(mtfb_ctx *c){
 	cudaFree(c->d_pf); cudaFree(c->d_pf_ints); cudaFree(c->d_pf_rand_in); cudaFree(c->d_pf_rand_out);
 	cudaFree(c->d_est_pts); cudaFree(c->d_est_mask); cudaFree(c->d_est_err); cudaFree(c->d_est_out);
 	cudaFree(c->d_grid_prev); cudaFree(c->d_grid_curr);
+	for(int r = 0; r < MTFB_MAX_PEERS; ++r) if(c->peer_mapped[r]) cudaIpcCloseMemHandle(c->peer_mapped[r]);
+	cudaFree(c->d_peer_buf);
 	if(c->copy_stream){
 		cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream);
 		cudaEventDestroy(c->ev_upload); cudaEventDestroy(c->ev_read[0]); cudaEventDestroy(c->ev_read[1]);
@@ -973,7 +985,17 @@ mtfb_status mtfb_update(mtfb_ctx *c){
 		return st != MTFB_OK ? st : mark_frame_read(c);
 	}
 	if(c->b.log) CUDA_TRY(cudaMemsetAsync(c->b.log, 0, sizeof(mtfb_iter_log)*(size_t)c->P*c->b.log_slots, c->stream));
-	CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads, frame_map_for(c)));
+	if(c->peer_attached){
+		// the frame's all-gather rides on the update kernel: every patch's final corners go straight into the gathered
+		// array (of this frame's parity) of every rank; mtfb_peer_gather then only signals and waits
+		if(c->peer_pending) return fail(MTFB_ERR_LOGIC, "mtfb_update: the previous frame's corners have not been gathered "
+			"(mtfb_peer_gather): the ranks of a job exchange every frame");
+		DevBatch b = c->b;
+		peer_out_for(c, c->peer_seq + 1, b.peers);
+		CUDA_TRY(launch_update(c->prm, c->threads, c->occ, b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads, frame_map_for(c)));
+		++c->peer_seq; c->peer_pending = true;
+	} else
+		CUDA_TRY(launch_update(c->prm, c->threads, c->occ, c->b, c->d_mi_tab, c->stream, mom_work_for(c), c->mom_threads, frame_map_for(c)));
 	++c->launches;
 	return mark_frame_read(c);
 }
@@ -1187,6 +1209,89 @@ mtfb_status mtfb_debug_colpiv_qr_solve(int device, int n, int fast, int n_sys, c
 	if(e == cudaSuccess && perm) e = cudaMemcpy(perm, di + n_sys, nv*sizeof(int), cudaMemcpyDeviceToHost);
 	cudaFree(d); cudaFree(di);
 	if(e != cudaSuccess) return fail(MTFB_ERR_CUDA, "mtfb_debug_colpiv_qr_solve: %s", cudaGetErrorString(e));
+	return MTFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU exchange
+static size_t peer_flags_offset(int n_total){ return ((size_t)2 * n_total * 8 * sizeof(double) + 255) & ~(size_t)255; }
+
+mtfb_status mtfb_peer_export(mtfb_ctx *c, int n_total, mtfb_peer_handle *out){
+	if(!c || !out || n_total < 1) return fail(MTFB_ERR_INVALID_ARG, "mtfb_peer_export: bad argument");
+	if(c->d_peer_buf) return fail(MTFB_ERR_LOGIC, "mtfb_peer_export: already exported");
+	static_assert(sizeof(cudaIpcMemHandle_t) <= MTFB_PEER_HANDLE_BYTES, "handle size");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	const size_t bytes = peer_flags_offset(n_total) + 256 + 64;              // arrays | 64 flags | error word
+	CUDA_TRY(cudaMalloc(&c->d_peer_buf, bytes));
+	CUDA_TRY(cudaMemset(c->d_peer_buf, 0, bytes));
+	CUDA_TRY(cudaDeviceSynchronize());
+	cudaIpcMemHandle_t h;
+	CUDA_TRY(cudaIpcGetMemHandle(&h, c->d_peer_buf));
+	std::memset(out->bytes, 0, sizeof(out->bytes));
+	std::memcpy(out->bytes, &h, sizeof(h));
+	c->peer_n_total = n_total;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_peer_attach(mtfb_ctx *c, int rank, int world, int row0, const mtfb_peer_handle *handles){
+	if(!c || !handles || world < 1 || world > MTFB_MAX_PEERS || rank < 0 || rank >= world)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_peer_attach: 1 <= world <= %d, 0 <= rank < world required", (int)MTFB_MAX_PEERS);
+	if(!c->d_peer_buf) return fail(MTFB_ERR_LOGIC, "mtfb_peer_attach: mtfb_peer_export has not been called");
+	if(c->peer_attached) return fail(MTFB_ERR_LOGIC, "mtfb_peer_attach: already attached");
+	if(row0 < 0 || row0 + c->P > c->peer_n_total) return fail(MTFB_ERR_INVALID_ARG, "mtfb_peer_attach: rows %d .. %d do not fit %d",
+		row0, row0 + c->P, c->peer_n_total);
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	for(int r = 0; r < world; ++r){
+		void *base = c->d_peer_buf;
+		if(r != rank){
+			cudaIpcMemHandle_t h;
+			std::memcpy(&h, handles[r].bytes, sizeof(h));
+			CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+			c->peer_mapped[r] = base;
+		}
+		c->peer_base[r] = static_cast<double*>(base);
+		c->peer_flags[r] = reinterpret_cast<unsigned*>(static_cast<char*>(base) + peer_flags_offset(c->peer_n_total));
+	}
+	c->peer_rank = rank; c->peer_world = world; c->peer_row0 = row0; c->peer_seq = 0; c->peer_pending = false;
+	c->peer_attached = true;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_peer_gather(mtfb_ctx *c){
+	if(!c || !c->peer_attached) return fail(MTFB_ERR_LOGIC, "mtfb_peer_gather: mtfb_peer_attach has not been called");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	if(!c->peer_pending){
+		// the corners come from something else than an update kernel (initialize, setRegion, the particle filter): push them
+		++c->peer_seq;
+		PeerOut po;
+		peer_out_for(c, c->peer_seq, po);
+		CUDA_TRY(launch_peer_push(c->b.corners, c->P, po, c->stream));
+		++c->launches;
+	}
+	int *d_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->peer_flags[c->peer_rank]) + 256);
+	CUDA_TRY(launch_peer_signal_wait(c->peer_flags, c->peer_flags[c->peer_rank], c->peer_rank, c->peer_world, c->peer_seq, d_err, c->stream));
+	++c->launches;
+	c->peer_pending = false;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_peer_gathered(mtfb_ctx *c, const double **d_corners, int *n_total){
+	if(!c || !c->peer_attached) return fail(MTFB_ERR_LOGIC, "mtfb_peer_gathered: mtfb_peer_attach has not been called");
+	if(d_corners) *d_corners = c->peer_base[c->peer_rank] + (size_t)(c->peer_seq & 1u)*c->peer_n_total * 8;
+	if(n_total) *n_total = c->peer_n_total;
+	return MTFB_OK;
+}
+
+mtfb_status mtfb_get_gathered_region(mtfb_ctx *c, double *out){
+	if(!c || !out || !c->peer_attached) return fail(MTFB_ERR_LOGIC, "mtfb_get_gathered_region: mtfb_peer_attach has not been called");
+	if(c->peer_pending) return fail(MTFB_ERR_LOGIC, "mtfb_get_gathered_region: mtfb_peer_gather has not been called for this frame");
+	const double *src = c->peer_base[c->peer_rank] + (size_t)(c->peer_seq & 1u)*c->peer_n_total * 8;
+	int err = 0;
+	const int *d_err = reinterpret_cast<const int*>(reinterpret_cast<const char*>(c->peer_flags[c->peer_rank]) + 256);
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)c->peer_n_total * 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(err) return fail(MTFB_ERR_CUDA, "mtfb_get_gathered_region: rank %d never signalled its frame (5 s)", err - 1);
 	return MTFB_OK;
 }
 

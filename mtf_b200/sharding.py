@@ -51,6 +51,20 @@ def device_view(ptr, shape, device, typestr="<f8"):
     return torch.as_tensor(_Raw(), device=device)
 
 
+def exchange_peer_handles(handle, group=None):
+    """all-gather the ranks' 64-byte IPC handles (host side, through whatever backend the group has)"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(np.ascontiguousarray(handle, dtype=np.uint8))
+    if backend == "nccl":
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    return np.stack([p.cpu().numpy() for p in parts])
+
+
 class ShardedBatchTracker:
     """The batch of `corners.shape[0]` patches split over the ranks of a torch.distributed group.
 
@@ -67,6 +81,21 @@ class ShardedBatchTracker:
         self.local = make_local(self.hi - self.lo)
         self._d_corners = None
         self._gathered = None
+        self._peer = False
+
+    def attach_peers(self):
+        """set up the exchange over NVLink peer memory (mtfb_peer_*): from now on update() writes every patch's corners into
+        the gathered arrays of all ranks and getRegion(device=...) needs no collective call"""
+        h = self.local.peer_export(self.n_total)
+        handles = exchange_peer_handles(h, self.group)
+        self.local.peer_attach(self.rank, self.world, self.lo, handles)
+        self._peer = True
+
+    def gathered_device(self, device):
+        """(n_total, 8) torch view of the current gathered array after the frame's signal / wait"""
+        self.local.peer_gather()
+        ptr, n = self.local.peer_gathered_ptr()
+        return device_view(ptr, (n, 8), device)
 
     def initialize(self, corners, img):
         c = np.asarray(corners, dtype=np.float64).reshape(self.n_total, 2, 4)
@@ -89,6 +118,11 @@ class ShardedBatchTracker:
         the current stream, which must be the tracker's stream: bench.py sets both); otherwise (CPU tests over gloo) through
         the host getter."""
         import torch
+        if self._peer:
+            if device is not None:
+                return self.gathered_device(device).reshape(self.n_total, 2, 4)
+            self.local.peer_gather()
+            return self.local.getGatheredRegion()
         if device is not None and hasattr(self.local, "device_results"):
             loc = self.local_corners_device(device)
             if self._gathered is None:

@@ -7,6 +7,6 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=fa
 nvcc $FLAGS -Xptxas -v -c lk_ssd_mom.cu -o $V/$1_mom.o 2> $V/$1.lk_ssd_mom.ptxas.log &
 nvcc $FLAGS -c mtfb_api.cu -o $V/$1_api.o 2> $V/$1.api.log &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $V/lib$1.so $V/$1_mom.o $V/$1_api.o _obj/lk_ssd.o _obj/lk_ssd_f32.o _obj/lk_ncc.o _obj/lk_mi.o _obj/lk_mi_aff.o _obj/pf_kernels.o _obj/pf_tracker.o _obj/preproc.o _obj/debug_kernels.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $V/lib$1.so $V/$1_mom.o $V/$1_api.o $(ls _obj/*.o | grep -v -e lk_ssd_mom.o -e mtfb_api.o)
 rm -f $V/$1_mom.o $V/$1_api.o
 grep -A2 "ssd_fclk_mom_kernelILi0ELi128E" $V/$1.lk_ssd_mom.ptxas.log | grep -E "Used|spill" | sed 's/ptxas info    : //'
