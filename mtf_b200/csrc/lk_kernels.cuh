@@ -33,6 +33,8 @@ struct DevBatch {
 	float *I0f, *G0f;            // fp32 copies of I0 / G0 (precision = MTFB_PRECISION_F32), else null
 	int I0f_stride;              // elements per patch in I0f (N rounded up to 4: 16-byte aligned rows for the bulk copy)
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
+	double *It_scratch;          // P x N   MI with templates too large for shared memory: the current pixel values of a
+	                             //         pass, written by the histogram sweep and read back by the gradient sweep, else null
 	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
 	double *ncc_tab;             // P x 64  NCC: template sums behind cmptInitHessian (sum D0 | sum D0 D0^T | sum I0cc D0)
 	double *f;                   // P       similarity

@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
 	const double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
+	double *It_g = (!KEEP_IT && b.It_scratch) ? b.It_scratch + (size_t)p*N : nullptr;
 	const bool jac_orig = (SM == SM_ESM) && (b.jac_type == MTFB_ESM_JAC_ORIGINAL);
 	const bool hess_orig = (SM == SM_ESM) && (b.hess_type == MTFB_ESM_HESS_ORIGINAL);        // cmptCurrHessian(mean_pix_jacobian)
 	const bool jac_half = (SM == SM_ESM) && !jac_orig;
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 				PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 				const double It = b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add;
 				if(KEEP_IT) s_It[it.pix] = It;
+				else if(It_g) __stcs(It_g + it.pix, It);                           // read back by this thread in sweep 2
 				bc = bin_weights(It, B); bi = bin_weights(i0, B);
 			}
 			for(int turn = 0; turn < n_turns; ++turn){
@@ -355,16 +357,20 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		double acc[NA];
 #pragma unroll
 		for(int i = 0; i < NA; ++i) acc[i] = 0;
-		double p_i0 = tid < N ? __ldcs(I0 + tid) : 0.0, p_gx = 0, p_gy = 0;
+		double p_i0 = tid < N ? __ldcs(I0 + tid) : 0.0, p_gx = 0, p_gy = 0, p_it = 0;
 		if(INIT && tid < N){ p_gx = __ldcs(G0 + tid); p_gy = __ldcs(G0 + N + tid); }
+		if(!KEEP_IT && It_g && tid < N) p_it = __ldcs(It_g + tid);
 		for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-			const double c_i0 = p_i0, c_gx = p_gx, c_gy = p_gy;
+			const double c_i0 = p_i0, c_gx = p_gx, c_gy = p_gy, c_it = p_it;
 			if(it.pix + T < N){
 				p_i0 = __ldcs(I0 + it.pix + T);
 				if(INIT){ p_gx = __ldcs(G0 + it.pix + T); p_gy = __ldcs(G0 + N + it.pix + T); }
+				if(!KEEP_IT && It_g) p_it = __ldcs(It_g + it.pix + T);
 			}
 			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
-			const double It2 = KEEP_IT ? s_It[it.pix] : (b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add);
+			// the pixel's value of sweep 1: from shared memory (small templates), from the pass's scratch row in global memory
+			// (this thread wrote it), or -- neither available -- sampled again
+			const double It2 = KEEP_IT ? s_It[it.pix] : (It_g ? c_it : (b.pix_mult*sample_pixel(b.img, g.wx, g.wy) + b.pix_add));
 			const BinWeights bc = bin_weights(It2, B), bi = bin_weights(c_i0, B);
 			double df_t = 0, df_0 = 0;
 			if(CURR){

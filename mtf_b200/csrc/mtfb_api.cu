@@ -355,7 +355,10 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		// SSD with ESM / FCLK keeps the un-chained template gradient for setRegion (NT/ESM.cc:150-168, NT/FCLK.cc:360-376)
 		// ... and IALK pushes it through cmptApproxPixJacobian on every pass (NT/IALK.cc:131)
 		const bool keep_raw_grad = p->am == MTFB_AM_SSD && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_IALK);
-		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + (keep_raw_grad ? 2 * (size_t)N : 0);
+		// MI, templates beyond the 24 KB the update kernel keeps in shared memory (lk_mi.cu launch_one): a pass's pixel values
+		const bool mi_it_scratch = p->am == MTFB_AM_MI && (size_t)N*sizeof(double) > 24 * 1024 && !std::getenv("MTFB_MI_RESAMPLE");
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + (keep_raw_grad ? 2 * (size_t)N : 0) +
+			(mi_it_scratch ? (size_t)N : 0);
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -378,6 +381,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.I0 = q; q += (size_t)N*P;
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.G0raw = nullptr;
+		b.It_scratch = nullptr;
+		if(mi_it_scratch){ b.It_scratch = q; q += (size_t)N*P; }
 		if(keep_raw_grad){ b.G0raw = q; q += 2 * (size_t)N*P; }
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
 		b.I0f = b.G0f = nullptr; b.I0f_stride = 0;
