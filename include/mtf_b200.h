@@ -96,8 +96,9 @@ typedef struct mtfb_params {
 	double grad_eps;             /* ImageBase.h:7-9; used for the out-of-image edge emulation only:
 	                                the product computes the eps -> 0 limit of the reference's finite
 	                                difference analytically (DESIGN.md "gradient semantics")      */
-	int hom_normalized_init;     /* 0: factory default (parameters.h:261); 1: Config/modules.cfg.
-	                                Homography only                                                */
+	int hom_normalized_init;     /* the SSM's normalized_init: hom_normalized_init (0: factory default, parameters.h:261;
+	                                1: Config/modules.cfg) for the Homography; aff_normalized_init for the Affine SSM
+	                                (Affine.cc:65-74: start from utils::computeAffineNDLT; F64 precision)              */
 	int mi_n_bins;               /* MIParams n_bins (parameters.h:344)                            */
 	double mi_pre_seed;
 	int mi_pou;

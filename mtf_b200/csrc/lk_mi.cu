@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
 	if(b.norm_init) W = dlt;                                 // Homography.cc:57-62: curr_warp starts as the DLT warp
-	const double abcd[4] = { 1, 0, 0, 1 };
+	// (the affine chain rule's a, b, c, d = curr_state + identity, Affine.cc:220-223: the identity unless the start is the NDLT warp)
+	const double abcd[4] = { (W.m[0] - 1) + 1, W.m[1], W.m[3], (W.m[4] - 1) + 1 };
 	double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
 	// phase 1: template values (scaled to bin units, MI.cc:91-94), chained gradient, init_hist and the self joint histogram
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){

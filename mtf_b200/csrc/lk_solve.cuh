@@ -206,9 +206,97 @@ template<int SSM> __device__ __forceinline__ void store_patch_state(const DevBat
 	if(lane == 0){ b.f[p] = f; b.n_iters[p] = n_passes; b.status[p] = patch_status; }
 }
 
+// utils::computeAffineNDLT(in_corners, out_corners), warpUtils.cc:378-386: normalizePts(out) (warpUtils.cc:802-832), the
+// least-squares affine map of computeAffineDLT (warpUtils.cc:276-343: JacobiSVD pseudo-inverse of the 8 x 6 system, which
+// is block diagonal with the 4 x 3 block P = [x y 1] for both rows, full column rank), inv_norm_mat * warp.  Householder QR
+// least squares instead of Eigen's Jacobi SVD: the two agree to rounding (1e-15 relative; tolerance stated in the tests).
+// Evaluated by every lane alike (uniform result).
+__device__ __forceinline__ Mat3 affine_ndlt(const double *in_c, const double *out_c){
+	double cx = 0, cy = 0;
+#pragma unroll
+	for(int i = 0; i < 4; ++i){ cx += out_c[i]; cy += out_c[4 + i]; }
+	cx /= 4; cy /= 4;
+	double A[4][3], c0[4], c1[4], mean_dist = 0;
+#pragma unroll
+	for(int i = 0; i < 4; ++i){
+		c0[i] = out_c[i] - cx; c1[i] = out_c[4 + i] - cy;
+		mean_dist += sqrt(c0[i] * c0[i] + c1[i] * c1[i]);
+		A[i][0] = in_c[i]; A[i][1] = in_c[4 + i]; A[i][2] = 1;
+	}
+	mean_dist /= 4;
+	const double norm_scale = sqrt(2.0) / mean_dist;
+#pragma unroll
+	for(int i = 0; i < 4; ++i){ c0[i] *= norm_scale; c1[i] *= norm_scale; }
+#pragma unroll
+	for(int k = 0; k < 3; ++k){
+		double nrm = 0;
+#pragma unroll
+		for(int i = k; i < 4; ++i) nrm += A[i][k] * A[i][k];
+		nrm = sqrt(nrm);
+		const double alpha = A[k][k] >= 0 ? -nrm : nrm;
+		double v[4] = { 0, 0, 0, 0 };
+#pragma unroll
+		for(int i = k; i < 4; ++i) v[i] = A[i][k];
+		v[k] -= alpha;
+		double vv = 0;
+#pragma unroll
+		for(int i = k; i < 4; ++i) vv += v[i] * v[i];
+		if(nrm == 0 || vv == 0) continue;
+#pragma unroll
+		for(int j = k; j < 3; ++j){
+			double d = 0;
+#pragma unroll
+			for(int i = k; i < 4; ++i) d += v[i] * A[i][j];
+			d = 2 * d / vv;
+#pragma unroll
+			for(int i = k; i < 4; ++i) A[i][j] -= d * v[i];
+		}
+		double d0 = 0, d1 = 0;
+#pragma unroll
+		for(int i = k; i < 4; ++i){ d0 += v[i] * c0[i]; d1 += v[i] * c1[i]; }
+		d0 = 2 * d0 / vv; d1 = 2 * d1 / vv;
+#pragma unroll
+		for(int i = k; i < 4; ++i){ c0[i] -= d0 * v[i]; c1[i] -= d1 * v[i]; }
+	}
+	double a0[3], a1[3];
+#pragma unroll
+	for(int k = 2; k >= 0; --k){
+		double s0 = c0[k], s1 = c1[k];
+#pragma unroll
+		for(int j = k + 1; j < 3; ++j){ s0 -= A[k][j] * a0[j]; s1 -= A[k][j] * a1[j]; }
+		a0[k] = s0 / A[k][k]; a1[k] = s1 / A[k][k];
+	}
+	// inv_norm_mat * affine_mat, entry by entry in Eigen's order (k ascending)
+	const double is = 1.0 / norm_scale;
+	Mat3 W;
+	W.m[0] = is*a0[0] + 0.0*a1[0] + cx*0.0; W.m[1] = is*a0[1] + 0.0*a1[1] + cx*0.0; W.m[2] = is*a0[2] + 0.0*a1[2] + cx*1.0;
+	W.m[3] = 0.0*a0[0] + is*a1[0] + cy*0.0; W.m[4] = 0.0*a0[1] + is*a1[1] + cy*0.0; W.m[5] = 0.0*a0[2] + is*a1[2] + cy*1.0;
+	W.m[6] = 0; W.m[7] = 0; W.m[8] = 1;
+	return W;
+}
+
 // ssm.setCorners for one patch (warp 0): 4-point DLT, identity warp, zero state
 template<int SSM> __device__ __forceinline__ Mat3 set_corners(const DevBatch &b, int p, int lane, const double *c_in){
 	constexpr int S = StateSize<SSM>::value;
+	if(SSM == SSM_AFF && b.norm_init){
+		// Affine::setCorners with normalized_init (Affine.cc:65-74): the template stays the pixel-scaled square, curr_warp =
+		// computeAffineNDLT(init_corners, corners), curr_corners = curr_warp . init_corners_hm (NOT the supplied corners: a
+		// general quadrilateral is only fitted in the least-squares sense)
+		const Mat3 aw = affine_ndlt(b.norm_corners, c_in);
+		double st[S];
+		state_from_warp<SSM>(st, aw);
+		if(lane < 9){ b.warp[(size_t)p * 9 + lane] = aw.m[lane]; b.dlt[(size_t)p * 9 + lane] = aw.m[lane]; }
+#pragma unroll
+		for(int s = 0; s < S; ++s) if(lane == s) b.state[(size_t)p*S + s] = st[s];
+		if(lane < 8){
+			const int i = lane & 3, r = lane >> 2;
+			const double px = b.norm_corners[i], py = b.norm_corners[4 + i];
+			double v = aw.m[3 * r] * px; v = v + aw.m[3 * r + 1] * py; v = v + aw.m[3 * r + 2] * 1.0;
+			b.corners[(size_t)p * 8 + lane] = v;
+			b.init_corners[(size_t)p * 8 + lane] = b.norm_corners[lane];
+		}
+		return aw;
+	}
 	Mat3 dlt = warp_homography_dlt(b.norm_corners, c_in, lane);
 	Mat3 I = mat3_identity();
 	if(b.norm_init){

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 #pragma unroll
 	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
 	if(b.norm_init) W = dlt;                                 // Homography.cc:57-62: curr_warp starts as the DLT warp
-	const double abcd[4] = { 1, 0, 0, 1 };
+	// (the affine chain rule's a, b, c, d = curr_state + identity, Affine.cc:220-223: the identity unless the start is the NDLT warp)
+	const double abcd[4] = { (W.m[0] - 1) + 1, W.m[1], W.m[3], (W.m[4] - 1) + 1 };
 	double acc[L::NA];
 #pragma unroll
 	for(int i = 0; i < L::NA; ++i) acc[i] = 0;

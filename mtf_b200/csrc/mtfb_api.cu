@@ -278,9 +278,14 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(!combo_supported(p, &why))
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: (am %d, ssm %d, sm %d, hess %d, jac %d) is not implemented: %s",
 			p->am, p->ssm, p->sm, p->hess_type, p->jac_type, why);
-	if(p->hom_normalized_init && p->ssm != MTFB_SSM_HOMOGRAPHY)
-		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: normalized_init is implemented for the homography only (the affine "
-			"variant goes through computeAffineNDLT, warpUtils.cc:345-390)");
+	if(p->hom_normalized_init && p->ssm == MTFB_SSM_TRANSLATION)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: the Translation SSM has no normalized_init (TranslationParams.h)");
+	if(p->hom_normalized_init && (p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK))
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: the additive searches (FALK / IALK) are implemented for normalized_init = 0 "
+			"(their template Jacobian, ssm.cmptPixJacobian at the start state, assumes the identity start)");
+	if(p->hom_normalized_init && p->ssm == MTFB_SSM_AFFINE && p->precision != MTFB_PRECISION_F64)
+		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: the affine normalized_init (computeAffineNDLT, warpUtils.cc:378-386) is "
+			"implemented in the F64 precision");
 	if(!(p->grad_eps > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: grad_eps must be > 0");
 	if(p->precision != MTFB_PRECISION_F64 && p->precision != MTFB_PRECISION_F32)
 		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: precision must be MTFB_PRECISION_F64 or MTFB_PRECISION_F32");

@@ -348,6 +348,70 @@ static void getNormUnitSquarePts(double *basis_pts, double *basis_corners, int r
 	basis_corners[4] = min_y; basis_corners[5] = min_y; basis_corners[6] = max_y; basis_corners[7] = max_y;
 }
 
+// utils::computeAffineNDLT(in_corners, out_corners)                           warpUtils.cc:378-386
+//   = normalizePts(out_corners) (warpUtils.cc:802-832: centroid, mean distance, scale sqrt(2) / mean_dist)
+//   + computeAffineDLT(in_corners, norm_corners) (warpUtils.cc:276-343: the least-squares solution of the 8 x 6 system
+//     [x y 1 0 0 0; 0 0 0 x y 1] a = (ox, oy) through JacobiSVD's pseudo-inverse)
+//   + inv_norm_mat * warp.
+// The system is block diagonal with the same 4 x 3 block P = [x y 1] for both rows of the affine warp and has full column rank,
+// so its pseudo-inverse solution is the pair of least-squares solutions of P a = ox, P a = oy; they are computed here by
+// Householder QR (no SVD: Eigen's Jacobi sweeps are not restated -- the two agree to rounding, ~1e-15 relative, and
+// tests/test_oracle.py pins this function against numpy.linalg.lstsq, which is SVD based like the reference).
+static void lstsq_4x3(const double P[4][3], const double *b0, const double *b1, double *a0, double *a1){
+	double A[4][3], c0[4], c1[4];
+	for(int i = 0; i < 4; ++i){ for(int j = 0; j < 3; ++j) A[i][j] = P[i][j]; c0[i] = b0[i]; c1[i] = b1[i]; }
+	for(int k = 0; k < 3; ++k){
+		double nrm = 0;
+		for(int i = k; i < 4; ++i) nrm += A[i][k] * A[i][k];
+		nrm = std::sqrt(nrm);
+		if(nrm == 0) continue;
+		const double alpha = A[k][k] >= 0 ? -nrm : nrm;
+		double v[4] = { 0, 0, 0, 0 };
+		for(int i = k; i < 4; ++i) v[i] = A[i][k];
+		v[k] -= alpha;
+		double vv = 0;
+		for(int i = k; i < 4; ++i) vv += v[i] * v[i];
+		if(vv == 0) continue;
+		for(int j = k; j < 3; ++j){
+			double d = 0;
+			for(int i = k; i < 4; ++i) d += v[i] * A[i][j];
+			d = 2 * d / vv;
+			for(int i = k; i < 4; ++i) A[i][j] -= d * v[i];
+		}
+		double d0 = 0, d1 = 0;
+		for(int i = k; i < 4; ++i){ d0 += v[i] * c0[i]; d1 += v[i] * c1[i]; }
+		d0 = 2 * d0 / vv; d1 = 2 * d1 / vv;
+		for(int i = k; i < 4; ++i){ c0[i] -= d0 * v[i]; c1[i] -= d1 * v[i]; }
+	}
+	for(int k = 2; k >= 0; --k){
+		double s0 = c0[k], s1 = c1[k];
+		for(int j = k + 1; j < 3; ++j){ s0 -= A[k][j] * a0[j]; s1 -= A[k][j] * a1[j]; }
+		a0[k] = s0 / A[k][k]; a1[k] = s1 / A[k][k];
+	}
+}
+static Mat3 computeAffineNDLT(const double *in_c, const double *out_c){
+	// normalizePts
+	double cx = 0, cy = 0;
+	for(int i = 0; i < 4; ++i){ cx += out_c[i]; cy += out_c[4 + i]; }
+	cx /= 4; cy /= 4;
+	double tx[4], ty[4], mean_dist = 0;
+	for(int i = 0; i < 4; ++i){ tx[i] = out_c[i] - cx; ty[i] = out_c[4 + i] - cy; mean_dist += std::sqrt(tx[i] * tx[i] + ty[i] * ty[i]); }
+	mean_dist /= 4;
+	const double norm_scale = std::sqrt(2.0) / mean_dist;
+	double nx[4], ny[4];
+	for(int i = 0; i < 4; ++i){ nx[i] = tx[i] * norm_scale; ny[i] = ty[i] * norm_scale; }
+	// computeAffineDLT
+	double P[4][3], a0[3], a1[3];
+	for(int i = 0; i < 4; ++i){ P[i][0] = in_c[i]; P[i][1] = in_c[4 + i]; P[i][2] = 1; }
+	lstsq_4x3(P, nx, ny, a0, a1);
+	Mat3 aff, inv_norm = identity3();
+	aff(0, 0) = a0[0]; aff(0, 1) = a0[1]; aff(0, 2) = a0[2];
+	aff(1, 0) = a1[0]; aff(1, 1) = a1[1]; aff(1, 2) = a1[2];
+	aff(2, 0) = 0; aff(2, 1) = 0; aff(2, 2) = 1;
+	inv_norm(0, 0) = 1.0 / norm_scale; inv_norm(1, 1) = 1.0 / norm_scale; inv_norm(0, 2) = cx; inv_norm(1, 2) = cy;
+	return mul3(inv_norm, aff);
+}
+
 // ---------------------------------------------------------------------------------------------
 // SSM: ProjectiveBase + Homography + Affine
 // ---------------------------------------------------------------------------------------------
@@ -410,6 +474,20 @@ struct SSM{
 	}
 	// Homography::setCorners Homography.cc:50-71 ; Affine::setCorners Affine.cc:64-88 (normalized_init=0)
 	bool setCorners(const double *corners){
+		if(type == ORC_SSM_AFFINE && normalized_init){
+			// Affine::setCorners with normalized_init (Affine.cc:65-74): the template stays the pixel-scaled square, the least-squares
+			// affine warp onto the corners becomes curr_warp, and the corners are what that warp makes of the square's
+			curr_warp = computeAffineNDLT(norm_corners, corners);
+			dlt_warp = curr_warp;
+			std::memcpy(init_corners, norm_corners, sizeof(init_corners));
+			std::memcpy(init_corners_hm, norm_corners_hm, sizeof(init_corners_hm));
+			init_pts = norm_pts; init_pts_hm = norm_pts_hm;
+			getStateFromWarp(curr_state.data(), curr_warp);
+			affine_pts();
+			homogenize(curr_pts.data(), curr_pts_hm.data(), n_pts);
+			homogenize_corners(curr_corners, curr_corners_hm);
+			return true;
+		}
 		std::memcpy(curr_corners, corners, sizeof(curr_corners));
 		homogenize_corners(curr_corners, curr_corners_hm);
 		getPtsFromCorners(curr_warp, curr_pts.data(), curr_pts_hm.data(), curr_corners);
@@ -436,7 +514,6 @@ struct SSM{
 			curr_warp = identity3();
 			std::fill(curr_state.begin(), curr_state.end(), 0.0);
 		} else{
-			if(normalized_init) return false;                          // computeAffineNDLT path not restated
 			std::memcpy(init_corners, curr_corners, sizeof(init_corners));
 			init_pts = curr_pts;
 			homogenize_corners(init_corners, init_corners_hm);         // Affine.cc:81-82: re-homogenised
@@ -1730,6 +1807,9 @@ void orc_get_img_grad_analytic(const float *img, int h, int w, const double *pts
 }
 void orc_homography_dlt(const double *in_c, const double *out_c, double *H9){
 	Mat3 H = computeHomographyDLT(in_c, out_c); std::memcpy(H9, H.m, sizeof(H.m));
+}
+void orc_affine_ndlt(const double *in_c, const double *out_c, double *H9){
+	Mat3 H = computeAffineNDLT(in_c, out_c); std::memcpy(H9, H.m, sizeof(H.m));
 }
 void orc_colpiv_qr_solve(const double *A, const double *b, int n, double *x){
 	ColPivQR qr; qr.compute(A, n, n); qr.solve(b, x);

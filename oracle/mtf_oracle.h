@@ -117,6 +117,8 @@ void orc_get_img_grad(const float *img, int h, int w, const double *pts, int n,
 void orc_get_img_grad_analytic(const float *img, int h, int w, const double *pts, int n,
 	double grad_eps, double pix_mult, double *outN2);
 void orc_homography_dlt(const double *in_corners, const double *out_corners, double *H9);
+/* utils::computeAffineNDLT (warpUtils.cc:378-386), row-major 3 x 3 */
+void orc_affine_ndlt(const double *in_corners, const double *out_corners, double *H9);
 void orc_colpiv_qr_solve(const double *A, const double *b, int n, double *x);
 int orc_colpiv_qr(const double *A, int rows, int cols, double *qr_out, int *perm_out, double *hcoeffs_out);
 void orc_norm_unit_square_pts(int resx, int resy, double min_x, double min_y,

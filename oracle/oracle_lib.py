@@ -96,6 +96,7 @@ def lib():
     L.orc_get_img_grad.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_get_img_grad_analytic.argtypes = [fp, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp]
     L.orc_homography_dlt.argtypes = [dp, dp, dp]
+    L.orc_affine_ndlt.argtypes = [dp, dp, dp]
     L.orc_colpiv_qr_solve.argtypes = [dp, dp, C.c_int, dp]
     L.orc_colpiv_qr.argtypes = [dp, C.c_int, C.c_int, dp, ip, dp]; L.orc_colpiv_qr.restype = C.c_int
     L.orc_norm_unit_square_pts.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
@@ -296,6 +297,15 @@ def homography_dlt(in_corners, out_corners):
     b = np.ascontiguousarray(out_corners, dtype=np.float64).reshape(8)
     H = np.empty(9)
     lib().orc_homography_dlt(_dp(a), _dp(b), _dp(H))
+    return H.reshape(3, 3)
+
+
+def affine_ndlt(in_corners, out_corners):
+    """utils::computeAffineNDLT (warpUtils.cc:378-386)"""
+    a = np.ascontiguousarray(in_corners, dtype=np.float64).reshape(8)
+    b = np.ascontiguousarray(out_corners, dtype=np.float64).reshape(8)
+    H = np.empty(9)
+    lib().orc_affine_ndlt(_dp(a), _dp(b), _dp(H))
     return H.reshape(3, 3)
 
 

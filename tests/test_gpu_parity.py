@@ -225,8 +225,12 @@ def test_error_contract(seq384):
         g.initialize(common.patches(2, 49.0, 384, 384))
     assert e.value.type == "LogicError"                       # no image yet
     with pytest.raises(api.MTFError) as e:
-        _gpu("ssd", "affine", "fclk", 2, hom_normalized_init=1)
+        _gpu("ssd", "affine", "fclk", 2, hom_normalized_init=1, precision="f32")       # the affine NDLT start: F64 only
     assert e.value.type == "FunctonNotImplemented"
+    for ssm in ("homography", "affine"):
+        with pytest.raises(api.MTFError) as e:
+            _gpu("ssd", ssm, "falk", 2, hom_normalized_init=1)                         # additive searches: identity start only
+        assert e.value.type == "FunctonNotImplemented"
     bad = common.patches(2, 49.0, 384, 384); bad[0, 0, 0] = np.nan
     g.setImage(frames[0])
     with pytest.raises(api.MTFError) as e:
@@ -548,6 +552,53 @@ def test_hom_normalized_init(seq384, am, sm):
                 assert _rel(a["hessian"], b["hessian"]) <= tol
                 assert np.abs(a["corners"] - b["corners"]).max() <= (1e-4 if am == "mi" else 1e-6)
     assert (g.patch_status() & 2 == 0).all() or am == "mi"
+
+
+@pytest.mark.parametrize("am,sm", [("ssd", "fclk"), ("ssd", "esm"), ("ssd", "iclk"), ("ncc", "esm"), ("mi", "iclk"), ("ncc", "fclk")])
+def test_affine_normalized_init(seq384, am, sm):
+    """aff_normalized_init = 1 (Affine.cc:65-74): the template stays the pixel-scaled square [1 - res/2, res/2]^2, curr_warp
+    starts as utils::computeAffineNDLT(init_corners, corners) (warpUtils.cc:378-386: normalizePts + least squares + inverse
+    normalisation), and the region is what that warp makes of the square -- for a general quadrilateral NOT the corners
+    supplied.  The device solves the least-squares problem by Householder QR where Eigen runs a Jacobi SVD: the start
+    warp agrees with the oracle (pinned against numpy's SVD-based lstsq in tests/test_oracle.py) to 1e-13 relative, and
+    everything downstream within the tolerances of a state that differs by that much."""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(3, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=23)])
+    kw = {"hess_type": 0} if am == "mi" else {}
+    g = _gpu(am, "affine", sm, len(cs), hom_normalized_init=1, **kw)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    ipts, I0, st0, c0 = g.init_pts(), g.init_pix_vals(), g.state(), g.getRegion()
+    orcs = []
+    for i, c in enumerate(cs):
+        o = _oracle(am, "affine", sm, grad_mode=1, hom_normalized_init=1, **kw)
+        o.set_image(frames[0]); o.initialize(c)
+        assert np.array_equal(ipts[i], o.init_pts())                               # the square's grid itself
+        assert np.abs(st0[i] - o.state()).max() <= 1e-13 * max(1.0, np.abs(o.state()).max())
+        assert np.abs(c0[i] - o.corners()).max() <= 1e-11
+        assert np.abs(I0[i] - o.init_pix_vals()).max() <= 1e-9
+        orcs.append(o)
+    # rectangles are reproduced, quadrilaterals fitted
+    assert np.abs(c0[:3] - cs[:3]).max() <= 1e-10 and np.abs(c0[3:] - cs[3:]).max() > 0.1
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs = g.iter_log()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert len(ol) == len(logs[i])
+            for k, (a, b) in enumerate(zip(logs[i], ol)):
+                tol = 1e-6
+                assert abs(a["f"] - b["f"]) <= tol * max(abs(b["f"]), 1.0)
+                assert _rel(a["hessian"], b["hessian"]) <= tol
+                assert np.abs(a["corners"] - b["corners"]).max() <= (1e-4 if am == "mi" else 1e-6)
+    # setRegion goes through the same start
+    moved = g.getRegion() + np.array([[0.7], [-0.4]])
+    if sm in ("iclk", "fclk"):
+        g.setRegion(moved)
+        for i, o in enumerate(orcs):
+            o.set_region(moved[i])
+        assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= 1e-10
 
 
 @pytest.mark.parametrize("sm,hess", [("esm", "sum_of_self"), ("esm", "initial_self"), ("esm", "current_self"), ("fclk", "initial_self")])

@@ -178,3 +178,25 @@ def test_dlt_matches_opencv():
         m = H2 @ np.vstack([unit, np.ones(4)])
         assert np.allclose(m[:2] / m[2], c, atol=2e-4)
         assert np.allclose(H / H[2, 2], H2 / H2[2, 2], rtol=2e-5, atol=2e-5 * np.abs(H).max())
+
+
+def test_affine_ndlt_against_svd_least_squares():
+    """utils::computeAffineNDLT (warpUtils.cc:378-386) as the oracle restates it (Householder QR) against the reference's own
+    formulation -- normalizePts, the 8 x 6 system solved through an SVD pseudo-inverse (numpy.linalg.lstsq), inv_norm_mat * warp"""
+    from oracle import oracle_lib as O
+    rng = np.random.default_rng(3)
+    for res in (10, 25, 50):
+        inc = np.array([[1 - res / 2, res / 2, res / 2, 1 - res / 2], [1 - res / 2, 1 - res / 2, res / 2, res / 2]])
+        for _ in range(50):
+            out = np.array([[100, 150, 150, 100], [200, 200, 250, 250.0]]) + rng.uniform(-8, 8, (2, 4)) + rng.uniform(0, 500)
+            H = O.affine_ndlt(inc, out)
+            c = out.mean(axis=1, keepdims=True); t = out - c
+            s = np.sqrt(2) / np.sqrt((t ** 2).sum(axis=0)).mean(); n = t * s
+            A = np.zeros((8, 6)); b = np.zeros(8)
+            for i in range(4):
+                A[2 * i, :3] = [inc[0, i], inc[1, i], 1]; A[2 * i + 1, 3:] = [inc[0, i], inc[1, i], 1]
+                b[2 * i] = n[0, i]; b[2 * i + 1] = n[1, i]
+            x = np.linalg.lstsq(A, b, rcond=None)[0]
+            R = np.array([[1 / s, 0, c[0, 0]], [0, 1 / s, c[1, 0]], [0, 0, 1]]) @ np.array([[x[0], x[1], x[2]], [x[3], x[4], x[5]], [0, 0, 1]])
+            assert np.abs(H - R).max() <= 1e-14 * np.abs(R).max()
+            assert H[2, 0] == 0 and H[2, 1] == 0 and H[2, 2] == 1
