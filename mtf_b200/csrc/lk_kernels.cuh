@@ -34,7 +34,8 @@ struct DevBatch {
 	int I0f_stride;              // elements per patch in I0f (N rounded up to 4: 16-byte aligned rows for the bulk copy)
 	double *Hinit;               // P x 64  init_self_hessian, column-major S x S
 	double *It_scratch;          // P x N   MI with templates too large for shared memory: the current pixel values of a
-	                             //         pass, written by the histogram sweep and read back by the gradient sweep, else null
+	                             //         pass, written by the histogram sweep and read back by the gradient sweep; NCC with
+	                             //         ESM / FCLK: the pixel values of the last pass (what setRegion's Hessian reads); else null
 	double *am_scal;             // P x 8   per-template scalars of the AM (NCC: I0_mean, c)
 	double *ncc_tab;             // P x 64  NCC: template sums behind cmptInitHessian (sum D0 | sum D0 D0^T | sum I0cc D0)
 	double *f;                   // P       similarity
@@ -66,6 +67,8 @@ cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBa
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
 // setRegion of the search methods that keep template Jacobians (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): SSD
 cudaError_t launch_reinit_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
+// ... NCC (lk_ncc.cu)
+cudaError_t launch_reinit_ncc(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);
 // peer_gather.cu: corners -> every rank's gathered array (producers other than the update kernels); flags to the peers +
 // wait for theirs (one warp; *d_err set on time-out)

@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 		double J[S];
 		pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, J);
 		I0[it.pix] = val;
+		if(b.It_scratch) b.It_scratch[(size_t)p*N + it.pix] = val;          // am.initializePixVals sets It = I0 (ImageBase.cc:62-99)
+		if(b.G0raw){ b.G0raw[(size_t)p * 2 * N + it.pix] = smp.gx; b.G0raw[(size_t)p * 2 * N + N + it.pix] = smp.gy; }
 		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
 		G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
 		s1[0] += val;
@@ -267,6 +269,94 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) ncc_update_kernel(DevBatc
 		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
 	}
 	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
+	// the AM's pixel values stay those of the last pass: what setRegion's cmptSelfHessian will see (ncc_reinit_kernel)
+	if(b.It_scratch) for(int pix = tid; pix < N; pix += T) b.It_scratch[(size_t)p*N + pix] = s_It[pix];
+}
+
+// ------------------------------------------------------------------------------------------------
+// setRegion() of the search methods that keep template Jacobians -- nt::ESM::setRegion (NT/ESM.cc:150-168) and nt::FCLK::setRegion
+// with the InitialSelf Hessian (NT/FCLK.cc:360-376) -- for NCC: ssm.setCorners, init_pix_jacobian =
+// ssm.cmptInitPixJacobian(am.getInitPixGrad()) at the NEW template points, init_self_hessian = am.cmptSelfHessian(init_pix_jacobian).
+// NCC::cmptSelfHessian (NCC.cc:337-389) reads the appearance model's CURRENT state -- b = |It - mean| and It_cntr_b of the
+// last pass of the last update (or of initialize) -- which the update kernel leaves in It_scratch.  The template values and
+// their statistics are kept; the template gradient becomes the un-chained one (G0raw: it differs from the chained one of
+// initialize() by the 1 / hz of Homography.cc:68 for general quadrilaterals); the template sums behind cmptInitHessian
+// (ncc_tab) follow the new Jacobian.
+// ------------------------------------------------------------------------------------------------
+template<int SSM, int T>
+__global__ void __launch_bounds__(T) ncc_reinit_kernel(DevBatch b, const double *__restrict__ corners_in){
+	constexpr int S = StateSize<SSM>::value;
+	typedef NccLayout<S, SM_FCLK> L;                        // sum D0 | sum D0 D0^T | sum I0cc D0 (slot oW) | sum i D0
+	const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	__shared__ double s_dlt[9];
+	__shared__ double s_part[(T / 32) * L::NA];
+	__shared__ double s_sum[L::NA];
+	__shared__ double s_tmp[(T / 32) * 2];
+	if(warp == 0){
+		Mat3 dlt = set_corners<SSM>(b, p, lane, corners_in + (size_t)p * 8);
+		if(lane < 9) s_dlt[lane] = dlt.m[lane];
+	}
+	cta_sync<T>();
+	Mat3 dlt, W = mat3_identity();
+#pragma unroll
+	for(int i = 0; i < 9; ++i) dlt.m[i] = s_dlt[i];
+	const int N = b.N;
+	const double *I0 = b.I0 + (size_t)p*N, *Gr = b.G0raw + (size_t)p * 2 * N, *It = b.It_scratch + (size_t)p*N;
+	double *G0 = b.G0 + (size_t)p * 2 * N;
+	const double I0_mean = b.am_scal[(size_t)p * 8], c = b.am_scal[(size_t)p * 8 + 1], rc = ieee_rcp(c);
+	double s1[1] = { 0 };
+	for(int pix = tid; pix < N; pix += T) s1[0] += It[pix];
+	block_allreduce<1, T>(s1, s_tmp);
+	const double It_mean = s1[0] / N;
+	double s2[2] = { 0, 0 };
+	for(int pix = tid; pix < N; pix += T){
+		const double Itc = It[pix] - It_mean;
+		s2[0] = fma(Itc, Itc, s2[0]); s2[1] += Itc;
+	}
+	block_allreduce<2, T>(s2, s_tmp);
+	const double bn = sqrt(s2[0]), rb = ieee_rcp(bn);
+	double acc[L::NA];
+#pragma unroll
+	for(int i = 0; i < L::NA; ++i) acc[i] = 0;
+	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
+		const PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], false);
+		double D[S];
+		const double gx = Gr[it.pix], gy = Gr[N + it.pix];
+		init_pix_jacobian<SSM>(g.ix, g.iy, gx, gy, D);
+		G0[it.pix] = gx; G0[N + it.pix] = gy;                               // the Ix / Iy columns of cmptInitPixJacobian
+		const double Itcb = div_by(It[it.pix] - It_mean, bn, rb);
+		const double I0cc = div_by(I0[it.pix] - I0_mean, c, rc);
+#pragma unroll
+		for(int i = 0; i < S; ++i){
+			acc[L::oD + i] += D[i];
+			acc[L::oB + i] = fma(Itcb, D[i], acc[L::oB + i]);
+			acc[L::oW + i] = fma(I0cc, D[i], acc[L::oW + i]);
+#pragma unroll
+			for(int j = i; j < S; ++j) acc[L::oDD + L::tri(i, j)] = fma(D[i], D[j], acc[L::oDD + L::tri(i, j)]);
+		}
+	}
+	block_reduce<L::NA, T>(acc, s_part, s_sum);
+	for(int e = tid; e < S*S; e += T){
+		const int i = e % S, j = e / S;
+		b.Hinit[(size_t)p * 64 + j*S + i] = ncc_self_hessian<S>(i, j, s_sum + L::oD, s_sum + L::oDD, s_sum + L::oB, s2[1] / bn, bn, N);
+	}
+	for(int e = tid; e < S; e += T){ b.ncc_tab[(size_t)p * 64 + e] = s_sum[L::oD + e]; b.ncc_tab[(size_t)p * 64 + S + L::NH + e] = s_sum[L::oW + e]; }
+	for(int e = tid; e < L::NH; e += T) b.ncc_tab[(size_t)p * 64 + S + e] = s_sum[L::oDD + e];
+}
+
+template<int SSM> static cudaError_t launch_reinit_t(int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	switch(threads){
+	case 32: ncc_reinit_kernel<SSM, 32><<<b.P, 32, 0, st>>>(b, d_corners); break;
+	case 64: ncc_reinit_kernel<SSM, 64><<<b.P, 64, 0, st>>>(b, d_corners); break;
+	case 128: ncc_reinit_kernel<SSM, 128><<<b.P, 128, 0, st>>>(b, d_corners); break;
+	case 256: ncc_reinit_kernel<SSM, 256><<<b.P, 256, 0, st>>>(b, d_corners); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_reinit_ncc(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st){
+	if(ssm == SSM_HOM) return launch_reinit_t<SSM_HOM>(threads, b, d_corners, st);
+	return launch_reinit_t<SSM_AFF>(threads, b, d_corners, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -362,8 +362,11 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		const bool keep_raw_grad = p->am == MTFB_AM_SSD && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_IALK);
 		// MI, templates beyond the 24 KB the update kernel keeps in shared memory (lk_mi.cu launch_one): a pass's pixel values
 		const bool mi_it_scratch = p->am == MTFB_AM_MI && (size_t)N*sizeof(double) > 24 * 1024 && !std::getenv("MTFB_MI_RESAMPLE");
-		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + (keep_raw_grad ? 2 * (size_t)N : 0) +
-			(mi_it_scratch ? (size_t)N : 0);
+		// NCC with ESM / FCLK: the pixel values of the last pass and the un-chained template gradient, for setRegion (lk_ncc.cu
+		// ncc_reinit_kernel)
+		const bool ncc_it_last = p->am == MTFB_AM_NCC && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK);
+		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + ((keep_raw_grad || ncc_it_last) ? 2 * (size_t)N : 0) +
+			((mi_it_scratch || ncc_it_last) ? (size_t)N : 0);
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
 		if(cudaMemset(c->d_patch, 0, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_CUDA; break; }
 		if(cudaMalloc(&c->d_ints, 2 * (size_t)P*sizeof(int)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -387,8 +390,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.G0 = q; q += 2 * (size_t)N*P;
 		b.G0raw = nullptr;
 		b.It_scratch = nullptr;
-		if(mi_it_scratch){ b.It_scratch = q; q += (size_t)N*P; }
-		if(keep_raw_grad){ b.G0raw = q; q += 2 * (size_t)N*P; }
+		if(mi_it_scratch || ncc_it_last){ b.It_scratch = q; q += (size_t)N*P; }
+		if(keep_raw_grad || ncc_it_last){ b.G0raw = q; q += 2 * (size_t)N*P; }
 		b.n_iters = c->d_ints; b.status = c->d_ints + P;
 		b.I0f = b.G0f = nullptr; b.I0f_stride = 0;
 		b.gx_lo = b.gx_step = b.gy_lo = b.gy_step = 0;
@@ -688,17 +691,21 @@ mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 
 mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	if(c && !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_set_region: initialize has not been called");
-	bool ssm_only = true;
+	bool ssm_only = true, ncc_reinit = false;
 	if(c){
 		ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) || (c->prm.sm == MTFB_SM_FALK) || (c->prm.sm == MTFB_SM_IALK) ||
 			(c->prm.sm == MTFB_SM_FCLK && c->prm.hess_type != MTFB_LK_HESS_INITIAL_SELF);
-		// ESM and FCLK-InitialSelf also rebuild the template Jacobian and init_self_hessian at the new points: SSD
-		if(!ssm_only && !c->b.G0raw) return fail(MTFB_ERR_NOT_SUPPORTED,
-			"mtfb_set_region: for ESM and for FCLK with the InitialSelf Hessian only the SSD appearance model is implemented");
+		// ESM and FCLK-InitialSelf also rebuild the template Jacobian and init_self_hessian at the new points: SSD, and NCC
+		// from an identity start (its kept template gradient is then the un-chained one)
+		ncc_reinit = !ssm_only && c->prm.am == MTFB_AM_NCC && !c->prm.hom_normalized_init && c->b.It_scratch;
+		if(!ssm_only && !(c->prm.am == MTFB_AM_SSD && c->b.G0raw) && !ncc_reinit) return fail(MTFB_ERR_NOT_SUPPORTED,
+			"mtfb_set_region: for ESM and for FCLK with the InitialSelf Hessian the SSD and NCC (normalized_init = 0) appearance "
+			"models are implemented; MI's cmptSelfHessian at the new points is not");
 	}
 	mtfb_status st = upload_corners(c, corners, "mtfb_set_region");
 	if(st != MTFB_OK) return st;
 	if(ssm_only) CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
+	else if(ncc_reinit) CUDA_TRY(launch_reinit_ncc(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	else CUDA_TRY(launch_reinit_ssd(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
 	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
