@@ -4,8 +4,8 @@ LM refinement in one launch), the few host-side steps of GridTracker::update aro
 layout) in NumPy.  Host work per frame: 8 doubles down, the P x 8 cell corners up.
 
 Implemented: Homography / Affine as the grid's SSM with its default non-normalised initialisation, reset_at_each_frame 0 / 1,
-dyn_patch_size, patch_centroid_inside.  Not implemented (raise): forward-backward error estimation (fb_err_thresh > 0,
-GridTracker.cc:303-343), pyramidal cells, heterogeneous cells."""
+dyn_patch_size, patch_centroid_inside, forward-backward error estimation (fb_err_thresh > 0, fb_reinit: GridTracker.cc:292-343;
+cells in one process).  Not implemented (raise): pyramidal cells, heterogeneous cells."""
 import numpy as np
 
 from . import api
@@ -68,15 +68,15 @@ class GridTracker:
     """mirror of GridTracker<SSM>: setImage / initialize / update / setRegion / getRegion"""
 
     def __init__(self, cell_params, grid_size_x=10, grid_size_y=10, patch_size_x=10, patch_size_y=10, reset_at_each_frame=1,
-                 dyn_patch_size=0, patch_centroid_inside=True, fb_err_thresh=0, enable_pyr=0, ssm="homography", est_params=None,
-                 seed=1, cells=None, shard=None, gather=None, upload=None):
+                 dyn_patch_size=0, patch_centroid_inside=True, fb_err_thresh=0, fb_reinit=0, enable_pyr=0, ssm="homography",
+                 est_params=None, seed=1, cells=None, shard=None, gather=None, upload=None):
         """cells / shard / gather / upload: the cells split over several processes (one GPU each).  cells = this process's
         BatchTracker of the cells [shard[0], shard[1]); gather() -> a device array (.data_ptr()) of the current corners of ALL
         cells (n x 8) on this device; upload(ndarray) -> the same kind of object for the regions the cells were reset to.  Every
         process then runs the estimation on all the centroids (same seed, same result) and resets its own cells."""
         # defaults: GridTracker.h:8-23
-        if fb_err_thresh > 0:
-            raise api.MTFError(2, "GridTracker: forward-backward error estimation is not implemented")
+        if fb_err_thresh > 0 and gather is not None:
+            raise api.MTFError(2, "GridTracker: forward-backward error estimation is not implemented for cells split over processes")
         if enable_pyr:
             raise api.MTFError(2, "GridTracker: pyramidal patch trackers are not implemented")
         if ssm not in ("homography", "affine"):
@@ -92,6 +92,11 @@ class GridTracker:
         self.reset_at_each_frame = int(reset_at_each_frame)
         self.reinit_at_each_frame = self.reset_at_each_frame == 1          # GridTracker.cc:138
         self.dyn_patch_size, self.patch_centroid_inside = int(dyn_patch_size), bool(patch_centroid_inside)
+        # forward-backward error estimation (GridTracker.cc:186-189, 292-343)
+        self.fb_err_thresh, self.fb_reinit = float(fb_err_thresh), bool(fb_reinit)
+        self.enable_fb_err_est = self.fb_err_thresh > 0
+        self._curr_img = self._prev_img = None
+        self.fb_err_mask = None
         # GridTrackerParams::updateRes (GridTracker.cc:85-93)
         self.resx, self.resy = (self.gx + 1, self.gy + 1) if (self.dyn_patch_size or self.patch_centroid_inside) else (self.gx, self.gy)
         self.ssm = ssm
@@ -152,13 +157,61 @@ class GridTracker:
             self.cells.setRegion(mine)
 
     def setImage(self, img):
+        self._curr_img = img
         self.cells.setImage(img)
+
+    @staticmethod
+    def _clone(img):
+        return img.clone() if hasattr(img, "clone") else np.array(img, copy=True)
 
     def initialize(self, corners, img=None):
         if img is not None:
             self.setImage(img)
         self._set_corners(corners)
         self._reset_trackers(True)
+        if self.enable_fb_err_est:
+            self._prev_img = self._clone(self._curr_img)                       # GridTracker.cc:241-243
+
+    @staticmethod
+    def _centroids(regions):
+        """utils::getCentroid of every region as cv::Point2f: the mean of the four corners in double, rounded to float"""
+        c = np.asarray(regions, dtype=np.float64).reshape(-1, 2, 4)
+        return np.stack([(c[:, 0, 0] + c[:, 0, 1] + c[:, 0, 2] + c[:, 0, 3]) / 4.0,
+                         (c[:, 1, 0] + c[:, 1, 1] + c[:, 1, 2] + c[:, 1, 3]) / 4.0], axis=1).astype(np.float32)
+
+    def _backward_estimation(self, ep):
+        """GridTracker::backwardEstimation (GridTracker.cc:292-343): every cell tracks back into the previous frame from where
+        it is now; cells that do not return to where they started (squared distance > fb_err_thresh) are left out of the
+        estimation.  Batched: one backward update of all the cells instead of a loop over trackers."""
+        prev_pts, _ = self.cells.grid_pts()                                    # prev_pts of the last reset / frame
+        loc = self.cells.getRegion()
+        curr_pts = self._centroids(loc)
+        if self.fb_reinit:
+            self.cells.initialize(loc)
+        self.cells.setImage(self._prev_img)
+        self.cells.update()
+        fb_prev_pts = self._centroids(self.cells.getRegion())
+        self.cells.setImage(self._curr_img)
+        self.cells.setRegion(loc)
+        # cv::Point2f coordinates: the difference is a float operation, its square a double one (GridTracker.cc:310-313)
+        d = (fb_prev_pts - prev_pts).astype(np.float64)
+        first = ~((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) > self.fb_err_thresh)
+        mask = first.copy()
+        late = []
+        if int(mask.sum()) < ep.n_model_pts:
+            for t in range(self.n_trackers):
+                if mask[t]:
+                    continue
+                mask[t] = True; late.append(t)
+                if int(mask.sum()) == ep.n_model_pts:
+                    break
+        order = np.array(list(np.flatnonzero(first)) + late, dtype=np.int64)
+        est = dict(self.cells.estimate_warp_from_pts(self.ssm, prev_pts[order], curr_pts[order], ep))
+        pix_mask = np.zeros(self.n_trackers, dtype=np.uint8)
+        pix_mask[np.flatnonzero(mask)] = np.asarray(est["mask"])[:int(mask.sum())]    # walked in tracker order (GridTracker.cc:336-342)
+        self.fb_err_mask = mask
+        est["mask_est"], est["mask"], est["order"] = est["mask"], pix_mask, order
+        return est
 
     def setRegion(self, corners):
         self._set_corners(corners)
@@ -176,7 +229,10 @@ class GridTracker:
         self.frame += 1
         ep = api.EstParams.from_buffer_copy(self.est_params)
         ep.seed = self.seed + self.frame
-        if self.gather is None:
+        if self.enable_fb_err_est:
+            est = self._backward_estimation(ep)
+            self._prev_img = self._clone(self._curr_img)
+        elif self.gather is None:
             est = self.cells.grid_estimate(self.ssm, ep)
         else:
             curr = self.gather()
@@ -186,6 +242,8 @@ class GridTracker:
         self._set_corners(apply_warp_to_corners(self.ssm, self.corners, self.ssm_update))
         if self.reset_at_each_frame:
             self._reset_trackers(self.reinit_at_each_frame)
+        elif self.enable_fb_err_est:
+            pass                                 # the backward pass's setRegion left prev_pts = the cells' current centroids
         elif self.gather is None:
             self.cells.grid_commit()
         else:

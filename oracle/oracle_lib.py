@@ -471,10 +471,15 @@ def sym_eigen(A):
 class OracleGrid:
     """GridTracker<SSM> (SM/src/GridTracker.cc:232-285, 345-392) restated on the oracle's own pieces: one OracleTracker per
     cell, orc_estimate_warp for ssm.estimateWarpFromPts, orc_homography_dlt / orc_norm_unit_square_pts for ssm.setCorners.
-    fb_err_thresh = 0, no pyramids.  est_params: any structure with the OrcEstParams fields; frame t uses seed + t."""
+    Forward-backward error estimation (fb_err_thresh > 0: GridTracker.cc:292-343) included; no pyramids.  est_params: any
+    structure with the OrcEstParams fields; frame t uses seed + t."""
 
     def __init__(self, cell_params, grid_size_x, grid_size_y, patch_size_x, patch_size_y, reset_at_each_frame=1, dyn_patch_size=0,
-                 patch_centroid_inside=True, ssm="homography", est_params=None, seed=1):
+                 patch_centroid_inside=True, ssm="homography", est_params=None, seed=1, fb_err_thresh=0, fb_reinit=0):
+        self.fb_err_thresh, self.fb_reinit = float(fb_err_thresh), bool(fb_reinit)
+        self.enable_fb = self.fb_err_thresh > 0                                # GridTracker.cc:186-189
+        self.curr_img = self.prev_img = None
+        self.fb_err_mask = None
         self.gx, self.gy = grid_size_x, grid_size_y
         self.n = grid_size_x * grid_size_y
         self.psx, self.psy = float(patch_size_x), float(patch_size_y)
@@ -522,12 +527,52 @@ class OracleGrid:
             self.prev_pts[t] = self._centroid(self.trackers[t].corners())
 
     def set_image(self, img):
+        self.curr_img = img
         for t in self.trackers:
             t.set_image(img)
 
     def initialize(self, corners):
         self._set_corners(corners)
         self._reset(True)
+        if self.enable_fb:
+            self.prev_img = np.array(self.curr_img, copy=True)                 # GridTracker.cc:241-243
+
+    def _backward_estimation(self, q):
+        """GridTracker::backwardEstimation (GridTracker.cc:292-343)"""
+        fb_prev = np.zeros((self.n, 2), dtype=np.float32)
+        for t in range(self.n):
+            tr = self.trackers[t]
+            loc = tr.corners().copy()
+            if self.fb_reinit:
+                tr.initialize(loc)
+            tr.set_image(self.prev_img)
+            tr.update()
+            fb_prev[t] = self._centroid(tr.corners())
+            tr.set_image(self.curr_img)
+            tr.set_region(loc)
+        # cv::Point2f coordinates: the difference is a float operation, its square a double one (GridTracker.cc:310-313)
+        d = (fb_prev - self.prev_pts).astype(np.float64)
+        mask = ~((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) > self.fb_err_thresh)
+        if int(mask.sum()) < q.n_model_pts:
+            for t in range(self.n):
+                if mask[t]:
+                    continue
+                mask[t] = True
+                if int(mask.sum()) == q.n_model_pts:
+                    break
+        # (the reference appends the late additions at the END of the masked lists: same order here)
+        first = ~((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) > self.fb_err_thresh)
+        order = list(np.flatnonzero(first)) + [t for t in range(self.n) if mask[t] and not first[t]]
+        est = estimate_warp(self.ssm, self.prev_pts[order], self.curr_pts[order], q)
+        pix_mask = np.zeros(self.n, dtype=np.uint8)
+        # pix_mask[tracker] = fb_err_mask ? pix_mask_est[est_pt_id++] : 0, walking the trackers in order (GridTracker.cc:336-342)
+        k = 0
+        for t in range(self.n):
+            if mask[t]:
+                pix_mask[t] = est["mask"][k]; k += 1
+        self.fb_err_mask = mask
+        est = dict(est); est["mask_est"] = est["mask"]; est["mask"] = pix_mask; est["order"] = np.array(order)
+        return est
 
     def update(self):
         for t in range(self.n):
@@ -538,7 +583,11 @@ class OracleGrid:
         for name, _ in OrcEstParams._fields_:
             setattr(q, name, getattr(self.est_params, name))
         q.seed = self.seed + self.frame
-        est = estimate_warp(self.ssm, self.prev_pts, self.curr_pts, q)
+        if self.enable_fb:
+            est = self._backward_estimation(q)
+            self.prev_img = np.array(self.curr_img, copy=True)
+        else:
+            est = estimate_warp(self.ssm, self.prev_pts, self.curr_pts, q)
         self.last = est
         s = est["state_update"]
         if self.ssm == "homography":

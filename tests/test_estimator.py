@@ -355,6 +355,41 @@ def test_grid_tracker_against_oracle_grid(cfg):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(reset=0, fb_reinit=0, thresh=0.05), dict(reset=1, fb_reinit=0, thresh=0.05),
+                                 dict(reset=0, fb_reinit=1, thresh=0.02), dict(reset=0, fb_reinit=0, thresh=1e-7)])
+def test_grid_tracker_forward_backward(cfg):
+    """GridTracker with fb_err_thresh > 0 (GridTracker.cc:265-267, 292-343): after the cells' update every cell tracks back
+    into the previous frame; those that do not return to their starting point are left out of the estimation (and, when
+    fewer than n_model_pts survive, re-admitted in tracker order).  Cells: SSD + Homography + FCLK (setRegion is SSM-only)"""
+    from mtf_b200 import api, grid, synth
+    frames, _ = synth.make_sequence(4, 384, 384)
+    g = 5
+    region = np.array([[90.0, 300, 305, 85], [80, 84, 290, 296]])
+    common = dict(grid_size_x=g, grid_size_y=g, patch_size_x=24, patch_size_y=24, reset_at_each_frame=cfg["reset"], ssm="homography",
+                  seed=31, fb_err_thresh=cfg["thresh"], fb_reinit=cfg["fb_reinit"])
+    cell_kw = dict(resx=16, resy=16, max_iters=10)
+    gt = grid.GridTracker(api.make_params("ssd", "homography", "fclk", n_patches=g * g, **cell_kw),
+                          est_params=api.make_est_params("ransac", ransac_reproj_thresh=2.0), **common)
+    og = O.OracleGrid(O.make_params("ssd", "homography", "fclk", grad_mode=1, **cell_kw),
+                      est_params=O.make_est_params("ransac", ransac_reproj_thresh=2.0), **common)
+    gt.setImage(frames[0]); og.set_image(frames[0])
+    gt.initialize(region); og.initialize(region)
+    dropped = 0
+    for f in frames[1:]:
+        gt.setImage(f); og.set_image(f)
+        c = gt.update(); oc = og.update()
+        assert np.array_equal(gt.fb_err_mask, og.fb_err_mask)
+        assert np.array_equal(gt.last_estimate["order"], og.last["order"])
+        assert gt.last_estimate["drawn"] == og.last["drawn"]
+        assert np.array_equal(gt.pix_mask, og.last["mask"])
+        assert np.abs(c - oc).max() < 1e-4
+        dropped += int((~gt.fb_err_mask).sum())
+    if cfg["thresh"] < 1e-6:
+        assert dropped > 0                                   # nearly every cell fails the test: the re-admission path ran
+    gt.close()
+
+
+@pytest.mark.gpu
 def test_grid_centroids_and_commit():
     from mtf_b200 import api, synth
     frames, _ = synth.make_sequence(2, 384, 384)
