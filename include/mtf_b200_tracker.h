@@ -146,6 +146,23 @@ public:
 		ep.lm_max_iters = lm_max_iters; ep.seed = seed;
 		return ep;
 	}
+	// ---- the batch split over several GPUs (one process each): the per-frame exchange of the regions over NVLink peer memory.
+	//! peerExport: this rank's gathered array for a job of n_total patches -> its 64-byte handle, to be exchanged by the host
+	//! (MPI_Allgather, a pipe, a file); peerAttach: rank / world / this rank's first patch / all the handles; from then on
+	//! update() stores every region into the arrays of all ranks and peerGather() (once per frame, on every rank) completes
+	//! the exchange: gathered[i] = the region of patch i of the whole job
+	mtfb_peer_handle peerExport(int n_total){
+		mtfb_peer_handle h;
+		check(mtfb_peer_export(ctx, n_total, &h));
+		gathered.assign(8 * (size_t)n_total, 0.0);
+		return h;
+	}
+	void peerAttach(int rank, int world, int row0, const mtfb_peer_handle *handles){ check(mtfb_peer_attach(ctx, rank, world, row0, handles)); }
+	const double* peerGather(){
+		check(mtfb_peer_gather(ctx));
+		check(mtfb_get_gathered_region(ctx, gathered.data()));
+		return gathered.data();
+	}
 	//! bumped whenever the regions are refreshed from the device (initialize / setRegion / update)
 	long generation() const{ return gen; }
 	const double* region(int i) const{ return &corners[8 * (size_t)i]; }
@@ -168,7 +185,7 @@ private:
 	mtfb_ctx *ctx;
 	mtfb_params prm;
 	cv::Mat curr_img;
-	std::vector<double> corners, pending;
+	std::vector<double> corners, pending, gathered;
 	int n_supplied, frame_id, updated_frame;
 	long gen;
 	int raw_channels, gauss_kernel_size;
