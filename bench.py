@@ -53,8 +53,8 @@ N_FRAMES = 8
 ALG_BYTES_PER_ITER = 8 * N_PIX + 432          # I_t footprint + I_0 (fp32 each) + W in + J,H,f out
 METRIC = "LK iters/sec (50x50 SSD+Homography)"
 # ncu --set full, this workload: the frame and the template once, everything else stays on chip
-NCU_DRAM_BYTES_PER_LAUNCH = {"f64": 24466688, "f32": 14248192}
-NCU_TRAFFIC_SOURCE = {"f64": "profiles/r01_ncu_f64_summary.txt", "f32": "profiles/r01_ncu_f32_summary.txt"}
+NCU_DRAM_BYTES_PER_LAUNCH = {"f64": 24466688, "f32": 15141888}
+NCU_TRAFFIC_SOURCE = {"f64": "profiles/r01_ncu_f64_summary.txt", "f32": "profiles/r02_ncu_mom_final_summary.txt"}
 
 
 def peaks():

@@ -347,7 +347,11 @@ def run_config4(env, root, n_steps, n_warm, n_patches=8192, cpu=True):
         "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": size * size * 4, "d2h_bytes_per_step": P * 64},
         "gpu_launches": int(launches),
         "roofline": roofline(alg, P * iters, kms / n_steps, root, "mi_update_kernel<Homography,ICLK>",
-                             "fp64 issue + shared-memory histogram updates, not HBM bound"),
+                             "fp64 issue + shared-memory histogram updates, not HBM bound",
+                             # one launch of the whole 8192-patch batch (fp64 template, its gradient and the pass's pixel values
+                             # stream from DRAM on every pass): scaled to this rank's share
+                             traffic=int((95087834000 + 19510694000) * P / 8192),
+                             traffic_source="profiles/r02_ncu_mi_final_summary.txt (dram__bytes_read + write, one launch of 8192 patches)"),
         "valid": {"finite": bool(np.isfinite(final).all()), "patches_nan": int((status & 1 != 0).sum())},
     }
     if cpu and env.rank == 0 and env.world == 1:
