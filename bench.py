@@ -504,6 +504,7 @@ def run_ours(args):
             others = {}
             for name, fn in (("config3_res25", lambda: benchlib.run_config3(env, ROOT, 25, few, 3, strong, cpu)),
                              ("config3_res10", lambda: benchlib.run_config3(env, ROOT, 10, few, 3, strong, cpu)),
+                             ("config3_res25_f64", lambda: benchlib.run_config3(env, ROOT, 25, few, 3, strong, False, precision="f64")),
                              ("config4", lambda: benchlib.run_config4(env, ROOT, few, 3, cpu=cpu)),
                              ("config5", lambda: benchlib.run_config5(env, ROOT, few, 3, cpu=cpu))):
                 try:
@@ -512,7 +513,7 @@ def run_ours(args):
                     others[name] = {"error": "%s: %s" % (type(e).__name__, e)}
             out["other_configs"] = others
     elif args.config == 3:
-        out = benchlib.run_config3(env, ROOT, args.res or 25, args.steps, args.warmup, strong, cpu)
+        out = benchlib.run_config3(env, ROOT, args.res or 25, args.steps, args.warmup, strong, cpu, precision=args.precision)
     elif args.config == 4:
         out = benchlib.run_config4(env, ROOT, args.steps, args.warmup, cpu=cpu)
     else:

@@ -162,7 +162,7 @@ def _gather(env, sharded, strong):
 
 
 # ------------------------------------------------------------------------------------------------ config 3
-def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
+def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True, precision="f32"):
     """GridTracker<Homography>::update (SM/src/GridTracker.cc:247-285) with 32 x 32 ESM + NCC + Affine cells: the cells' update,
     the warp of the region from their centroids (RANSAC + LM refinement on the device), the cells re-initialised on the frame
     at the regions the new corners give them.  weak scaling: one such grid per GPU (the regions all-gathered per frame);
@@ -183,7 +183,8 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
 
     def make_local(n):
         tr = api.BatchTracker(api.make_params("ncc", "affine", "esm", n_patches=n, resx=res, resy=res, max_iters=iters, epsilon=0.0,
-                                              device=env.local_rank, hess_type=W.CONFIG3["hess_type"], jac_type=W.CONFIG3["jac_type"]))
+                                              device=env.local_rank, hess_type=W.CONFIG3["hess_type"], jac_type=W.CONFIG3["jac_type"],
+                                              precision=precision))
         tr.set_stream(env.stream.cuda_stream)
         return tr
 
@@ -238,19 +239,22 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True):
     out = {
         "metric": "LK iters/sec (%dx%d NCC+Affine ESM, GridTracker 32x32 cells)" % (res, res), "value": total_iters / (ms * 1e-3),
         "unit": "iters/s", "n_gpus": env.world, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms / n_steps,
-        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f64" if precision == "f64" else "f32 per pixel (bit-exact sampling indices), f64 reduction + solve", "data": "synthetic",
         "config": {"workload": "GridTracker<Homography>::update: ESM+NCC+Affine cells, 32x32 = %d cells%s of %dx%d px, %d iters/frame "
                                "(epsilon=0), region warp by RANSAC + LM from the cell centroids on the device, every cell "
                                "re-initialised on every frame where the new region puts it, 1024x1024 f32 frames"
                                % (n_cells, "" if strong else " per GPU", res, res, iters),
-                   "l2": "flushed between timed steps (256 MB write)",
+                   "precision": precision, "l2": "flushed between timed steps (256 MB write)",
                    "collective": ("none" if env.world == 1 else "all_gather of the cells' P x 8 corners per frame from the kernel's output "
                                   "buffer, every rank estimates" if split else "all_gather of the grids' regions per frame")},
         "e2e": {"value": total_iters / (e2e_ms * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": h * w * 4 + P * 64,
                 "d2h_bytes_per_step": 21 * 8 + n_cells},
         "gpu_launches": int(launches),
-        "roofline": roofline(alg, P * iters, kms / n_steps, root, "ncc_update_kernel<Affine,ESM>",
-                             "fp64-issue bound (three sweeps per pass over It kept in shared memory), not HBM bound"),
+        "roofline": roofline(alg, P * iters, kms / n_steps, root,
+                             "ncc_update_kernel<Affine,ESM>" if precision == "f64" else "ncc_update_f32_kernel<Affine,ESM>",
+                             "fp64-issue bound (three sweeps per pass over It kept in shared memory), not HBM bound" if precision == "f64"
+                             else "one fp32 sweep per pass; bound by the per-pass serial tail (6 x 6 QR, update), not HBM"),
         "stages_ms_per_step": {"cells_update_kernel": kms / n_steps, "estimate_and_reset": (ms - kms) / n_steps},
         "valid": {"finite": finite, "n_iters_per_cell": int(n_it[0]), "estimate_ok": bool(est["ok"]), "inliers": int(est["n_inliers"]),
                   "hypotheses": int(est["drawn"]), "region_drift_px": drift},

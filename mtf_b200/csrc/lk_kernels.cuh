@@ -78,6 +78,8 @@ cudaError_t launch_peer_signal_wait(unsigned *const *peer_flags, unsigned *my_fl
 // lk_ssd_f32.cu
 cudaError_t launch_update_ssd_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
 cudaError_t launch_stage_f32(int ssm, const DevBatch &b, const StageTapsF32 &t, cudaStream_t st);
+// lk_ncc_f32.cu: NCC under ESM / FCLK in the F32 precision (one fp32 sweep per pass)
+cudaError_t launch_update_ncc_f32(int ssm, int sm, int threads, const DevBatch &b, cudaStream_t st);
 // lk_ssd_mom.cu: FCLK in the F32 precision with column-fixed threads (d_work: per thread {column, first row, rows, 0})
 // frame_tensor_map: a CUtensorMap of the frame (2-D, fp32, box MOM_WINP x F32_WIN = 64 x 56) for the TMA window copy, or null
 // (window filled by plain loads)

@@ -89,6 +89,12 @@ __global__ void __launch_bounds__(T) ncc_init_kernel(DevBatch b, const double *_
 		if(b.G0raw){ b.G0raw[(size_t)p * 2 * N + it.pix] = smp.gx; b.G0raw[(size_t)p * 2 * N + N + it.pix] = smp.gy; }
 		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
 		G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+		if(b.I0f){
+			// fp32 copies for the F32 precision (lk_ncc_f32.cu)
+			b.I0f[(size_t)p*b.I0f_stride + it.pix] = (float)val;
+			b.G0f[(size_t)p * 2 * N + it.pix] = (float)G0[it.pix];
+			b.G0f[(size_t)p * 2 * N + N + it.pix] = (float)G0[N + it.pix];
+		}
 		s1[0] += val;
 	}
 	block_allreduce<1, T>(s1, s_tmp);
@@ -324,6 +330,7 @@ __global__ void __launch_bounds__(T) ncc_reinit_kernel(DevBatch b, const double 
 		const double gx = Gr[it.pix], gy = Gr[N + it.pix];
 		init_pix_jacobian<SSM>(g.ix, g.iy, gx, gy, D);
 		G0[it.pix] = gx; G0[N + it.pix] = gy;                               // the Ix / Iy columns of cmptInitPixJacobian
+		if(b.G0f){ b.G0f[(size_t)p * 2 * N + it.pix] = (float)gx; b.G0f[(size_t)p * 2 * N + N + it.pix] = (float)gy; }
 		const double Itcb = div_by(It[it.pix] - It_mean, bn, rb);
 		const double I0cc = div_by(I0[it.pix] - I0_mean, c, rc);
 #pragma unroll

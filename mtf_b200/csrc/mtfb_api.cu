@@ -133,6 +133,7 @@ cudaError_t launch_init(const mtfb_params &p, int threads, const DevBatch &b, co
 cudaError_t launch_update(const mtfb_params &p, int threads, int occ, const DevBatch &b, const double *mi_tab, cudaStream_t st,
 	const int4 *mom_work = nullptr, int mom_threads = 0, const void *frame_map = nullptr){
 	if(p.precision == MTFB_PRECISION_F32 && mom_work) return launch_update_ssd_mom(p.ssm, mom_threads, b, mom_work, frame_map, st);
+	if(p.precision == MTFB_PRECISION_F32 && p.am == MTFB_AM_NCC) return launch_update_ncc_f32(p.ssm, p.sm, threads, b, st);
 	if(p.precision == MTFB_PRECISION_F32) return launch_update_ssd_f32(p.ssm, p.sm, threads, b, st);
 	if(p.am == MTFB_AM_MI) return launch_update_mi(p.ssm, p.sm, threads, b, p.mi_n_bins, p.mi_pre_seed, mi_tab, st);
 	if(p.am == MTFB_AM_NCC) return launch_update_ncc(p.ssm, p.sm, threads, b, st);
@@ -294,9 +295,14 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 	if(p->precision == MTFB_PRECISION_F32){
 		const bool gn = p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK || p->sm == MTFB_SM_ICLK;
 		const bool pf = p->sm == MTFB_SM_PF;
-		if(p->am != MTFB_AM_SSD || !(gn || pf) || (gn && !(p->chained_warp || !p->nt_semantics)))
+		// NCC: ESM / FCLK with the self Hessians (and ESM's DiffOfJacs Jacobian): the one-sweep kernel of lk_ncc_f32.cu
+		const bool ncc_f32 = p->am == MTFB_AM_NCC && p->ssm != MTFB_SSM_TRANSLATION && (p->chained_warp || !p->nt_semantics) &&
+			((p->sm == MTFB_SM_ESM && p->jac_type == MTFB_ESM_JAC_DIFF_OF_JACS && (p->hess_type == MTFB_ESM_HESS_INITIAL_SELF ||
+				p->hess_type == MTFB_ESM_HESS_CURRENT_SELF || p->hess_type == MTFB_ESM_HESS_SUM_OF_SELF)) ||
+			 (p->sm == MTFB_SM_FCLK && (p->hess_type == MTFB_LK_HESS_INITIAL_SELF || p->hess_type == MTFB_LK_HESS_CURRENT_SELF)));
+		if(!ncc_f32 && (p->am != MTFB_AM_SSD || !(gn || pf) || (gn && !(p->chained_warp || !p->nt_semantics))))
 			return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 is implemented for SSD with ESM / FCLK / ICLK (chained "
-				"warp) and PF; use MTFB_PRECISION_F64");
+				"warp) and PF, and for NCC with ESM (DiffOfJacs) / FCLK and the self Hessians (chained warp); use MTFB_PRECISION_F64");
 		if(!(p->grad_eps < 1e-6)) return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: MTFB_PRECISION_F32 needs grad_eps < 1e-6 (the fp32 "
 			"path returns the cell slope, the eps -> 0 limit of the reference's finite difference)");
 	}
@@ -314,6 +320,8 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		// CTAs per SM (148 x 4 = 592 patches: 0.355 ms against 0.412 ms at two warps), two warps per patch above that
 		// (888 patches: 0.512 against 0.600 ms), eight warps per patch for small batches
 		threads = p->n_patches > 592 ? 64 : p->n_patches >= 150 ? 128 : 256;
+		// NCC's one-sweep kernel on small cells (lk_ncc_f32.cu): 10 x 10 cells 0.33 ms at one warp against 0.35 at two
+		if(p->am == MTFB_AM_NCC && p->n_patches > 592 && p->resx*p->resy < 256) threads = 32;
 	}
 	if(!threads){
 		if(p->n_patches >= 900){ threads = 32; occ = 0; }

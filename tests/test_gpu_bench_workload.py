@@ -245,15 +245,17 @@ def test_device_qr_rank_threshold_is_eigens():
 
 
 # ------------------------------------------------------------------------------------------------ configs 3, 4, 5
+@pytest.mark.parametrize("precision", ["f64", "f32"])
 @pytest.mark.parametrize("res,cell", [(10, 10.0), (25, 25.0)])
-def test_config3_grid_cells_vs_oracle(bench_inputs, res, cell):
+def test_config3_grid_cells_vs_oracle(bench_inputs, res, cell, precision):
     """ESM + NCC + Affine on all 1024 GridTracker cells of the bench frames, re-initialised on every frame
-    (grid_reset_at_each_frame = 1, SM/src/GridTracker.cc:265-277)"""
+    (grid_reset_at_each_frame = 1, SM/src/GridTracker.cc:265-277), in both precisions (F32: the one-sweep kernel of
+    lk_ncc_f32.cu; stated tolerance: median 1e-4 px, 99th percentile 2e-2 px -- the cells are tiny and some never lock)"""
     from mtf_b200 import api, workloads
     frames, _, _ = bench_inputs
     cells = workloads.grid_cells(32, cell)
     kw = dict(resx=res, resy=res, max_iters=30, epsilon=0.0)
-    g = api.BatchTracker(api.make_params("ncc", "affine", "esm", n_patches=len(cells), **kw))
+    g = api.BatchTracker(api.make_params("ncc", "affine", "esm", n_patches=len(cells), precision=precision, **kw))
     worst = []
     for t in (0, 1):
         g.initialize(cells, frames[t])
@@ -266,9 +268,12 @@ def test_config3_grid_cells_vs_oracle(bench_inputs, res, cell):
             o.set_image(frames[t]); o.initialize(c); o.set_image(frames[t + 1]); o.update()
             d[i] = np.abs(got[i] - o.corners()).max()
         worst.append({"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())})
-    _record("config3_res%d" % res, worst)
+    _record("config3_res%d%s" % (res, "" if precision == "f64" else "_f32"), worst)
     for w in worst:
-        assert w["median"] <= 1e-6 and w["p99"] <= 1e-3, w
+        if precision == "f64":
+            assert w["median"] <= 1e-6 and w["p99"] <= 1e-3, w
+        else:
+            assert w["median"] <= 1e-4 and w["p99"] <= 2e-2, w
 
 
 def test_config4_mi_iclk_100x100_vs_oracle():

@@ -38,6 +38,11 @@ def _oracle(ssm, sm, **kw):
     return O.OracleTracker(O.make_params("ssd", ssm, sm, **kw))
 
 
+def _gpu_am(am, ssm, sm, P, **kw):
+    from mtf_b200 import api
+    return api.BatchTracker(api.make_params(am, ssm, sm, n_patches=P, precision="f32", **kw))
+
+
 def _ref_indices(pts, h, w):
     """(lx, ly) of getPixVal (imgUtils.h:91-113): (int)x, (int)y for points inside [0, w) x [0, h); -1 outside"""
     inb = (pts[:, 0] >= 0) & (pts[:, 0] < w) & (pts[:, 1] >= 0) & (pts[:, 1] < h)
@@ -234,7 +239,9 @@ def test_f32_matches_f64_kernel_large_batch(seq384):
 
 def test_f32_unsupported_combinations():
     from mtf_b200 import api
-    for kw in (dict(am="ncc"), dict(am="mi", sm="iclk"), dict(chained_warp=0), dict(am="ncc", sm="pf")):
+    # (NCC: ESM / FCLK with the self Hessians run in F32 since the end of round 2; its ICLK, Std Hessians and PF do not)
+    for kw in (dict(am="ncc", sm="iclk"), dict(am="ncc", hess_type=3), dict(am="ncc", sm="esm", jac_type=0), dict(am="mi", sm="iclk"),
+               dict(chained_warp=0), dict(am="ncc", sm="pf")):
         am = kw.pop("am", "ssd"); sm = kw.pop("sm", "fclk")
         with pytest.raises(api.MTFError) as e:
             api.BatchTracker(api.make_params(am, "homography", sm, n_patches=2, precision="f32", **kw))
@@ -406,3 +413,66 @@ def test_f32_pf_evaluate(seq384, ssm):
         ol, os_ = o.pf_evaluate(states[i])
         assert np.allclose(sim[i], os_, rtol=F32_RTOL, atol=0)
         assert np.allclose(lik[i], ol, rtol=1e-3, atol=1e-300)
+
+
+# ------------------------------------------------------------------------------------------------ NCC in the F32 precision
+@pytest.mark.parametrize("ssm", ["affine", "homography"])
+@pytest.mark.parametrize("sm,hess", [("esm", 2), ("esm", 0), ("esm", 1), ("fclk", 1), ("fclk", 0)])
+def test_ncc_f32_one_sweep_kernel(seq384, ssm, sm, hess):
+    """NCC under ESM (DiffOfJacs; InitialSelf / CurrentSelf / SumOfSelf) and FCLK in the F32 precision (lk_ncc_f32.cu: every sum
+    of a pass from ONE fp32 sweep, the pass's scalars applied afterwards) against the oracle.  Stated tolerances: first pass f 1e-6,
+    Jacobian 5e-5, Hessian 1e-5 relative to the largest entry; corners after 30 passes 2e-3 px; the same number of passes."""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(4, 49.0, 384, 384), common.patches(4, 52.3, 384, 384, seed=5)])
+    kw = dict(hess_type=hess, epsilon=0.0, max_iters=30)
+    if ssm == "homography":
+        kw["hom_normalized_init"] = 1
+    g = _gpu_am("ncc", ssm, sm, len(cs), **kw)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = O.OracleTracker(O.make_params("ncc", ssm, sm, grad_mode=1, **kw))
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    for fr in frames[1:3]:
+        g.update(fr)
+        logs, got = g.iter_log(), g.getRegion()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            ol = o.log()
+            assert len(ol) == len(logs[i])
+            if fr is frames[1]:
+                a, b = logs[i][0], ol[0]
+                assert abs(a["f"] - b["f"]) <= 1e-6 * max(abs(b["f"]), 1.0)
+                assert np.abs(a["jacobian"] - b["jacobian"]).max() <= 5e-5 * np.abs(b["jacobian"]).max()
+                assert np.abs(a["hessian"] - b["hessian"]).max() <= 1e-5 * np.abs(b["hessian"]).max()
+            assert np.abs(got[i] - o.corners()).max() <= 2e-3
+
+
+def test_ncc_f32_shipped_stopping_rule_and_set_region(seq384):
+    """epsilon = 1e-4 (Config/mtf.cfg:24) against the reference's finite-difference mode, and setRegion in between (the
+    template Jacobian in both copies, fp64 and fp32, follows the new points)"""
+    frames, _ = seq384
+    cs = common.patches(6, 52.3, 384, 384, seed=5)
+    g = _gpu_am("ncc", "affine", "esm", len(cs), hess_type=2)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = O.OracleTracker(O.make_params("ncc", "affine", "esm", grad_mode=0, hess_type=2))
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    g.update(frames[1])
+    for o in orcs:
+        o.set_image(frames[1]); o.update()
+    assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= 3e-2
+    moved = g.getRegion() + np.array([[0.6], [-0.5]])
+    g.setRegion(moved)
+    for i, o in enumerate(orcs):
+        o.set_region(moved[i])
+    g.update(frames[2])
+    n_it = g.n_iters()
+    for i, o in enumerate(orcs):
+        o.set_image(frames[2]); o.update()
+        assert abs(int(n_it[i]) - o.n_iters) <= 2
+    assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= 3e-2
