@@ -41,6 +41,47 @@ template<int S> __device__ __forceinline__ double ncc_f32_self_hessian(int i, in
 	return -jcjc + vi*vj;
 }
 
+// The solve of a pass by ONE warp, for the tails without Levenberg-Marquardt and without an iteration log (the counterpart of
+// solve_reference_warp, lk_f32.cuh): lane j < S builds column j of T^T H_loc T in registers, combines it with the stored
+// init_self_hessian as the search method's Hessian type says (hsel 0: this pass's, 1: the stored one, 2: their mean --
+// serial_step's rule), lane S carries J_ref = T^T J_loc; the reference's column-pivoted QR (factor_lean) and back-substitution.
+template<int S> __device__ __forceinline__ void solve_stored_warp(int lane, const double *s_Hl, const double *s_Jl, const double *s_T,
+	const double *Hinit, int hsel, double *s_dp, int &patch_status){
+	const int j = lane < S ? lane : 0;
+	double tj[S], A[S];
+#pragma unroll
+	for(int n = 0; n < S; ++n) tj[n] = s_T[n*S + j];
+#pragma unroll
+	for(int m = 0; m < S; ++m){
+		double a0 = 0, a1 = 0;
+#pragma unroll
+		for(int n = 0; n < S; n += 2){ a0 = fma(s_Hl[m*S + n], tj[n], a0); a1 = fma(s_Hl[m*S + n + 1], tj[n + 1], a1); }
+		A[m] = a0 + a1;                                                   // (H_loc T)[m][j]
+	}
+	if(lane == S){
+#pragma unroll
+		for(int m = 0; m < S; ++m) A[m] = s_Jl[m];
+	}
+	WarpColPivQR<S, S> qr;
+#pragma unroll
+	for(int i = 0; i < S; ++i){
+		double a0 = 0, a1 = 0;
+#pragma unroll
+		for(int m = 0; m < S; m += 2){ a0 = fma(s_T[m*S + i], A[m], a0); a1 = fma(s_T[(m + 1)*S + i], A[m + 1], a1); }
+		double v = a0 + a1;
+		if(lane < S && hsel != 0){
+			const double hi0 = Hinit[j*S + i];
+			v = hsel == 1 ? hi0 : (v + hi0) * 0.5;
+		}
+		qr.a[i] = v;
+	}
+	qr.factor_lean(lane, true);
+	const double x = -qr.solve_fast_cols(lane);                          // state_update = -H^-1 J^T (NT/ESM.cc:266, NT/FCLK.cc:298)
+	if(qr.nonzero_pivots < S) patch_status |= MTFB_PATCH_SINGULAR;
+	if(lane < S) s_dp[lane] = x;
+	__syncwarp();
+}
+
 template<int SSM, bool ESM> struct NccF32Acc {
 	static constexpr int S = StateSize<SSM>::value;
 	typedef NccF32Layout<S, ESM> L;
@@ -79,6 +120,7 @@ __global__ void __launch_bounds__(T, MINB) ncc_update_f32_kernel(DevBatch b, uns
 	__shared__ double s_W[9], s_corners[8], s_init_corners[8], s_dlt[9];
 	__shared__ double s_J[S], s_Jl[S], s_Hc[S*S], s_Hl[S*S], s_A[S*S], s_T[S*S], s_Tinv[S*S], s_loc[3], s_B[S];
 	__shared__ double s_scal[4];                       // f, bn, mean_t', (spare)
+	__shared__ double s_dp[S];
 	__shared__ float s_cf[C_COUNT], s_dl[9];
 	__shared__ int s_ci[2], s_wi[6];
 	__shared__ int s_ctrl;
@@ -206,6 +248,49 @@ __global__ void __launch_bounds__(T, MINB) ncc_update_f32_kernel(DevBatch b, uns
 		block_reduce_f32<L::NA, T>(acc.a, s_part, s_sum);
 		++n_passes;
 		// ---- the pass's scalars and vectors (fp64, local basis)
+		const bool lean_tail = !b.leven_marq && !b.log;
+		if(lean_tail){
+			// everything by warp 0, no block barrier until the pass ends
+			if(warp == 0){
+				const double S_it = s_sum[0], S_it2 = s_sum[1], S_i0it = s_sum[2], S_i0 = s_sum[3];
+				const double mt = S_it / N;                               // mean of It' = It - m0f
+				const double bn = sqrt(S_it2 - S_it*mt);                  // |It - mean|          (NCC.cc:145-147)
+				const double fv = (S_i0it - mt*S_i0) / (bn*c);            // f = <I0c, Itc> / bc  (NCC.cc:141, 151-152)
+				f = fv;
+				const double rb = 1.0 / bn;
+				if(lane < S){
+					const double sD = s_sum[L::oD + lane];
+					const double sB = (s_sum[L::oItD + lane] - mt*sD) * rb;
+					const double sC = (s_sum[L::oI0D + lane] - delta0*sD) / c;
+					double jv = (sC - fv*sB) * rb;
+					if(ESM){
+						const double sD0 = s_t0[lane];
+						jv -= ((s_sum[L::oItD0 + lane] - mt*sD0) * rb - fv*(s_t0[S + lane] - delta0*sD0) / c) / c;
+					}
+					s_B[lane] = sB;
+					s_Jl[lane] = jac_half ? jv * 0.5 : jv;
+				}
+				__syncwarp();
+				if(lane < S){
+					const double rN = 1.0 / N, rb2 = rb*rb, mj = s_sum[L::oD + lane] * rN, vj = s_B[lane];
+#pragma unroll
+					for(int i = 0; i < S; ++i){
+						const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
+						const double mi = s_sum[L::oD + i] * rN;
+						s_Hl[i*S + lane] = (vj*s_B[i] - (s_sum[L::oDD + L::tri(lo, hi)] - N*mi*mj)) * rb2;     // NCC.cc:337-389
+					}
+				}
+				__syncwarp();
+				solve_stored_warp<S>(lane, s_Hl, s_Jl, s_T, b.Hinit + (size_t)p * 64, hessian_select<SM>(b.hess_type), s_dp, patch_status);
+				const int ctrl = apply_update_lean<SSM>(b, lane, f, s_dp, s_W, s_corners, s_init_corners, patch_status);
+				if(lane == 0) s_ctrl = ctrl;
+				__syncwarp();
+				if(ctrl != CTRL_BREAK){
+					pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
+					if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
+				}
+			}
+		} else{
 		if(tid == 0){
 			const double S_it = s_sum[0], S_it2 = s_sum[1], S_i0it = s_sum[2], S_i0 = s_sum[3];
 			const double mt = S_it / N;                                   // mean of It' = It - m0f
@@ -267,6 +352,7 @@ __global__ void __launch_bounds__(T, MINB) ncc_update_f32_kernel(DevBatch b, uns
 				pass_constants<SSM>(b, lane, s_W, s_dlt, s_loc[0], s_loc[1], s_loc[2], s_cf, s_ci);
 				if(lane == 0) window_decide(b, s_corners, win_elems != 0, s_wi);
 			}
+		}
 		}
 		cta_sync<T>();
 		const int ctrl = s_ctrl;
