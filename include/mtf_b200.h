@@ -59,8 +59,10 @@ enum { MTFB_LK_HESS_INITIAL_SELF = 0, MTFB_LK_HESS_CURRENT_SELF = 1, MTFB_LK_HES
  *        to the reference's Eigen path; Jacobian / Hessian to summation order.
  *   F32: fp32 per-pixel arithmetic in patch-local coordinates with BIT-EXACT SAMPLING INDICES (pixels whose fp32
  *        coordinate is within the fp32 error bound of a cell boundary are re-evaluated in fp64), fp64 reduction and
- *        solve; Jacobian / Hessian / corners agree with F64 to fp32 tolerance.  SSD only: ESM / FCLK /
- *        ICLK with the chained warp, and PF particle evaluation. */
+ *        solve; Jacobian / Hessian / corners agree with F64 to fp32 tolerance.  SSD: ESM / FCLK /
+ *        ICLK with the chained warp, and PF particle evaluation.  NCC: ESM (DiffOfJacs Jacobian) / FCLK with the Initial /
+ *        Current / SumOf Self Hessians, chained warp -- one fp32 sweep per pass instead of the reference's three
+ *        (AM/src/NCC.cc:124-280, 337-389; DESIGN.md section 4 "NCC"). */
 enum { MTFB_PRECISION_F64 = 0, MTFB_PRECISION_F32 = 1 };
 /* how the F32 precision solves H dp = -J^T when the Hessian is the pass's own (FCLK / ESM CurrentSelf, no LM)
  * (mtfb_params::f32_solve; F64 contexts always run the reference's solve):

@@ -7,5 +7,5 @@ timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_fi
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-others > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:ssd_fclk_mom -s 3 -c 1 -f -o gpurun_out/prof_mom python bench.py --one-arm --no-others --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mi_update -s 1 -c 1 -f -o gpurun_out/prof_mi python bench.py --config 4 --steps 1 --warmup 1 --no-cpu > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ncc_update_f32 -s 3 -c 1 -f -o gpurun_out/prof_ncc_f32 python bench.py --config 3 --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1
 ls -la gpurun_out | tail -n 12
