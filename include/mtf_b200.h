@@ -284,6 +284,15 @@ mtfb_status mtfb_grid_estimate(mtfb_ctx *ctx, int ssm, const mtfb_est_params *ep
 	double *warp, int *info);
 /* prev_pts = curr_pts: GridTracker::update with reset_at_each_frame = 0 (GridTracker.cc:276-279) */
 mtfb_status mtfb_grid_commit(mtfb_ctx *ctx);
+/* GridTracker::update after its cells, WITHOUT a host hop (SM/src/GridTracker.cc:265-280 + resetTrackers :345-392 for
+ * reset_at_each_frame = 1, patch_centroid_inside = 1, dyn_patch_size = 0 -- the shipped grid): mtfb_grid_estimate, then on the
+ * device region <- ssm.applyWarpToCorners(region, state_update), the (grid_size + 1)^2 grid of the region
+ * (utils::getPtsFromCorners), every cell's patch_size box around the centroid of its four grid points, every cell
+ * re-initialised there on the current frame, prev_pts <- the new centroids.  region: 2 x 4 corners of the grid's own SSM,
+ * in / out (host).  One stream synchronisation, at the end. */
+mtfb_status mtfb_grid_advance(mtfb_ctx *ctx, int ssm, const mtfb_est_params *ep, int grid_size_x, int grid_size_y,
+	double patch_size_x, double patch_size_y, double *region /* 8, in / out */, double *state_update, unsigned char *mask /* P */,
+	double *warp /* 9 */, int *info /* 4 */);
 /* prev_pts / curr_pts as the last mtfb_grid_estimate saw them (P x 2 floats each, host; either may be NULL) */
 mtfb_status mtfb_grid_get_pts(mtfb_ctx *ctx, float *prev_pts, float *curr_pts);
 

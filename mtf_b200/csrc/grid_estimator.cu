@@ -17,6 +17,7 @@
 // pivoting: the same vector / solution to rounding, not the same rounding.
 #include "grid_estimator.cuh"
 #include <cfloat>
+#include "lk_warp.cuh"
 
 namespace mtfb {
 namespace {
@@ -780,7 +781,59 @@ __global__ void centroid_kernel(const double *corners, int P, float *pts){
 	pts[2 * p + 1] = (float)((c[4] + c[5] + c[6] + c[7]) / 4.0);
 }
 
+// One CTA.  Warp 0: the new region and its DLT (warp_homography_dlt: the reference's computeHomographyDLT, lk_warp.cuh); then
+// one thread per cell.
+__global__ void grid_layout_kernel(int homography, const double *__restrict__ su, double *region, int gx, int gy, double psx, double psy,
+	double *__restrict__ cells){
+	__shared__ double s_c[8], s_H[9];
+	const int tid = threadIdx.x, lane = tid & 31;
+	if(tid < 32){
+		// ssm.applyWarpToCorners: q = W [c; 1], c' = q / q_z with W = getWarpFromState(state_update) (Homography.cc:94-107, Affine.cc:117-131)
+		double W[9];
+		if(homography){ W[0] = 1 + su[0]; W[1] = su[1]; W[2] = su[2]; W[3] = su[3]; W[4] = 1 + su[4]; W[5] = su[5]; W[6] = su[6]; W[7] = su[7]; W[8] = 1; }
+		else{ W[0] = 1 + su[2]; W[1] = su[3]; W[2] = su[0]; W[3] = su[4]; W[4] = 1 + su[5]; W[5] = su[1]; W[6] = 0; W[7] = 0; W[8] = 1; }
+		if(lane < 4){
+			const double x = region[lane], y = region[4 + lane];
+			const double qx = W[0]*x + W[1]*y + W[2], qy = W[3]*x + W[4]*y + W[5], qz = W[6]*x + W[7]*y + W[8];
+			s_c[lane] = qx / qz; s_c[4 + lane] = qy / qz;
+		}
+		__syncwarp();
+		const double nc[8] = { -0.5, 0.5, 0.5, -0.5, -0.5, -0.5, 0.5, 0.5 };
+		double c[8];
+#pragma unroll
+		for(int i = 0; i < 8; ++i) c[i] = s_c[i];
+		const Mat3 H = warp_homography_dlt(nc, c, lane);
+		if(lane < 9) s_H[lane] = H.m[lane];
+		if(lane < 8) region[lane] = c[lane];
+	}
+	__syncthreads();
+	const int w = gx + 1, h = gy + 1;
+	const double sx = 1.0 / (w - 1), sy = 1.0 / (h - 1);
+	for(int t = tid; t < gx*gy; t += blockDim.x){
+		const int r = t / gx, cc = t - r*gx;
+		double cx = 0, cy = 0;
+		// the four grid points of the cell: (r, c), (r, c + 1), (r + 1, c + 1), (r + 1, c) -- GridTracker.cc:361-371; LinSpaced values
+#pragma unroll
+		for(int k = 0; k < 4; ++k){
+			const int j = cc + ((k == 1 || k == 2) ? 1 : 0), i = r + ((k >= 2) ? 1 : 0);
+			const double x = (j == w - 1) ? 0.5 : -0.5 + j*sx, y = (i == h - 1) ? 0.5 : -0.5 + i*sy;
+			const double qx = s_H[0]*x + s_H[1]*y + s_H[2], qy = s_H[3]*x + s_H[4]*y + s_H[5], qz = s_H[6]*x + s_H[7]*y + s_H[8];
+			cx += qx / qz; cy += qy / qz;
+		}
+		cx /= 4.0; cy /= 4.0;
+		const double x0 = cx - psx / 2.0, y0 = cy - psy / 2.0, x1 = x0 + psx, y1 = y0 + psy;
+		double *o = cells + 8 * (size_t)t;
+		o[0] = x0; o[1] = x1; o[2] = x1; o[3] = x0; o[4] = y0; o[5] = y0; o[6] = y1; o[7] = y1;
+	}
+}
+
 } // namespace
+
+cudaError_t launch_grid_layout(int homography, const double *d_state_update, double *d_region, int gx, int gy, double psx, double psy,
+	double *d_cells, cudaStream_t st){
+	grid_layout_kernel<<<1, 256, 0, st>>>(homography, d_state_update, d_region, gx, gy, psx, psy, d_cells);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_centroids(const double *corners, int P, float *pts, cudaStream_t st){
 	centroid_kernel<<<(P + 255) / 256, 256, 0, st>>>(corners, P, pts);

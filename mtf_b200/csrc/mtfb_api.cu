@@ -888,13 +888,14 @@ static mtfb_status est_reserve(mtfb_ctx *c, size_t n){
 	CUDA_TRY(cudaMalloc(&c->d_est_pts, 4 * n*sizeof(float)));
 	CUDA_TRY(cudaMalloc(&c->d_est_mask, n));
 	CUDA_TRY(cudaMalloc(&c->d_est_err, (size_t)EST_WARPS*n*sizeof(float)));
-	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 32 * sizeof(double)));
+	if(!c->d_est_out) CUDA_TRY(cudaMalloc(&c->d_est_out, 48 * sizeof(double)));   // 32 outputs | the grid's region (mtfb_grid_advance)
 	c->est_capacity = n;
 	return MTFB_OK;
 }
 
+static mtfb_status est_fetch(mtfb_ctx *c, int ssm, int n, double *state_update, unsigned char *mask, double *warp, int *info);
 static mtfb_status est_run(mtfb_ctx *c, const char *who, int ssm, const float *d_in, const float *d_out, int n, const mtfb_est_params *ep,
-	double *state_update, unsigned char *mask, double *warp, int *info){
+	double *state_update, unsigned char *mask, double *warp, int *info, bool launch_only = false){
 	if(ssm != MTFB_SSM_HOMOGRAPHY && ssm != MTFB_SSM_AFFINE)
 		return fail(MTFB_ERR_NOT_SUPPORTED, "%s: the estimators of Homography and Affine are implemented (ssm = %d)", who, ssm);
 	if(ep->method != MTFB_EST_RANSAC && ep->method != MTFB_EST_LMEDS && ep->method != MTFB_EST_LEAST_SQUARES)
@@ -913,6 +914,10 @@ static mtfb_status est_run(mtfb_ctx *c, const char *who, int ssm, const float *d
 	e.out = c->d_est_out; e.mask = c->d_est_mask; e.err = c->d_est_err;
 	CUDA_TRY(launch_estimate(e, c->stream));
 	++c->launches;
+	if(launch_only) return MTFB_OK;
+	return est_fetch(c, ssm, n, state_update, mask, warp, info);
+}
+static mtfb_status est_fetch(mtfb_ctx *c, int ssm, int n, double *state_update, unsigned char *mask, double *warp, int *info){
 	double out[32];
 	CUDA_TRY(cudaMemcpyAsync(out, c->d_est_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
 	if(mask) CUDA_TRY(cudaMemcpyAsync(mask, c->d_est_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
@@ -977,6 +982,37 @@ mtfb_status mtfb_grid_estimate(mtfb_ctx *c, int ssm, const mtfb_est_params *ep, 
 	CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_curr, c->stream));
 	++c->launches;
 	return est_run(c, "mtfb_grid_estimate", ssm, c->d_grid_prev, c->d_grid_curr, c->P, ep, state_update, mask, warp, info);
+}
+
+mtfb_status mtfb_grid_advance(mtfb_ctx *c, int ssm, const mtfb_est_params *ep, int grid_size_x, int grid_size_y, double patch_size_x,
+	double patch_size_y, double *region, double *state_update, unsigned char *mask, double *warp, int *info){
+	if(!c || !ep || !region) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_advance: null argument");
+	if(!c->grid_enabled) return fail(MTFB_ERR_LOGIC, "mtfb_grid_advance: mtfb_grid_enable has not been called");
+	if(!c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_grid_advance: initialize has not been called");
+	if(grid_size_x < 1 || grid_size_y < 1 || grid_size_x*grid_size_y != c->P)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_advance: %d x %d cells, the batch has %d patches", grid_size_x, grid_size_y, c->P);
+	if(!(patch_size_x > 0) || !(patch_size_y > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_advance: patch sizes must be positive");
+	for(int i = 0; i < 8; ++i) if(!std::isfinite(region[i])) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_advance: non-finite region corner");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	{ mtfb_status st = est_reserve(c, (size_t)c->P); if(st != MTFB_OK) return st; }
+	// the region rides behind the estimator's 32 output doubles
+	double *d_region = c->d_est_out + 32;
+	CUDA_TRY(cudaMemcpyAsync(d_region, region, 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_curr, c->stream));
+	++c->launches;
+	{ mtfb_status st = est_run(c, "mtfb_grid_advance", ssm, c->d_grid_prev, c->d_grid_curr, c->P, ep, nullptr, nullptr, nullptr, nullptr, true);
+	  if(st != MTFB_OK) return st; }
+	CUDA_TRY(launch_grid_layout(ssm == MTFB_SSM_HOMOGRAPHY, c->d_est_out + 9, d_region, grid_size_x, grid_size_y, patch_size_x, patch_size_y,
+		c->d_corners_in, c->stream));
+	++c->launches;
+	// GridTracker::resetTrackers(reinit = true): every cell re-initialised on the current frame at its new region
+	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->d_mi_tab, c->stream));
+	++c->launches;
+	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
+	CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_prev, c->stream));
+	++c->launches;
+	CUDA_TRY(cudaMemcpyAsync(region, d_region, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	return est_fetch(c, ssm, c->P, state_update, mask, warp, info);
 }
 
 mtfb_status mtfb_grid_commit(mtfb_ctx *c){

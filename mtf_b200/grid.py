@@ -69,7 +69,7 @@ class GridTracker:
 
     def __init__(self, cell_params, grid_size_x=10, grid_size_y=10, patch_size_x=10, patch_size_y=10, reset_at_each_frame=1,
                  dyn_patch_size=0, patch_centroid_inside=True, fb_err_thresh=0, fb_reinit=0, enable_pyr=0, ssm="homography",
-                 est_params=None, seed=1, cells=None, shard=None, gather=None, upload=None):
+                 est_params=None, seed=1, cells=None, shard=None, gather=None, upload=None, device_layout=True):
         """cells / shard / gather / upload: the cells split over several processes (one GPU each).  cells = this process's
         BatchTracker of the cells [shard[0], shard[1]); gather() -> a device array (.data_ptr()) of the current corners of ALL
         cells (n x 8) on this device; upload(ndarray) -> the same kind of object for the regions the cells were reset to.  Every
@@ -93,6 +93,7 @@ class GridTracker:
         self.reinit_at_each_frame = self.reset_at_each_frame == 1          # GridTracker.cc:138
         self.dyn_patch_size, self.patch_centroid_inside = int(dyn_patch_size), bool(patch_centroid_inside)
         # forward-backward error estimation (GridTracker.cc:186-189, 292-343)
+        self.device_layout = bool(device_layout)       # False: the host-side layout (NumPy), the reference for the device one
         self.fb_err_thresh, self.fb_reinit = float(fb_err_thresh), bool(fb_reinit)
         self.enable_fb_err_est = self.fb_err_thresh > 0
         self._curr_img = self._prev_img = None
@@ -127,6 +128,8 @@ class GridTracker:
             w = self.gx + 1
             self._ids = np.stack([r * w + c, r * w + c + 1, (r + 1) * w + c + 1, (r + 1) * w + c], axis=0)      # (4, P)
         pc = None
+        if self.pts is None:                       # (the device-side layout keeps only the region's corners on the host)
+            self.pts = pts_from_corners(self.corners, self.resx, self.resy)
         if self.resx == self.gx + 1:
             pc = self.pts.take(self._ids, axis=1)                                                            # (2, 4, P)
         # (with resx = grid_size_x the reference still indexes the (grid_size + 1)-wide table, GridTracker.cc:361-371, and then
@@ -229,6 +232,15 @@ class GridTracker:
         self.frame += 1
         ep = api.EstParams.from_buffer_copy(self.est_params)
         ep.seed = self.seed + self.frame
+        if (self.gather is None and not self.enable_fb_err_est and self.reinit_at_each_frame and not self.dyn_patch_size
+                and self.patch_centroid_inside and self.device_layout):
+            # the shipped grid (reset_at_each_frame = 1, fixed patch size, centroids inside): estimate, region, cell layout and
+            # re-initialisation without a host hop (mtfb_grid_advance); the host keeps its copy of the region
+            est, region = self.cells.grid_advance(self.ssm, ep, self.gx, self.gy, self.patch_size_x, self.patch_size_y, self.corners)
+            self.last_estimate = est
+            self.ssm_update, self.pix_mask = est["state_update"], est["mask"]
+            self.corners, self.pts = region, None
+            return self.getRegion()
         if self.enable_fb_err_est:
             est = self._backward_estimation(ep)
             self._prev_img = self._clone(self._curr_img)

@@ -355,6 +355,32 @@ def test_grid_tracker_against_oracle_grid(cfg):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ssm", ["homography", "affine"])
+def test_grid_advance_on_the_device_equals_the_host_layout(ssm):
+    """mtfb_grid_advance (estimate -> region -> cell layout -> re-initialisation without a host hop) against the same steps
+    with the layout in NumPy: same hypotheses and mask, region and cell regions to 1e-9 px, frame after frame"""
+    from mtf_b200 import api, grid, synth
+    frames, _ = synth.make_sequence(4, 384, 384)
+    g = 6
+    region = np.array([[90.0, 300, 305, 85], [80, 84, 290, 296]])
+    mk = lambda dev: grid.GridTracker(api.make_params("ncc", "affine", "esm", n_patches=g * g, resx=12, resy=12, max_iters=10),
+                                      grid_size_x=g, grid_size_y=g, patch_size_x=20, patch_size_y=22, reset_at_each_frame=1, ssm=ssm,
+                                      est_params=api.make_est_params("ransac", ransac_reproj_thresh=2.0), seed=5, device_layout=dev)
+    a, b = mk(True), mk(False)
+    a.setImage(frames[0]); b.setImage(frames[0])
+    a.initialize(region); b.initialize(region)
+    for f in frames[1:]:
+        a.setImage(f); b.setImage(f)
+        ca, cb = a.update(), b.update()
+        assert a.last_estimate["drawn"] == b.last_estimate["drawn"] and np.array_equal(a.pix_mask, b.pix_mask)
+        assert np.abs(ca - cb).max() <= 1e-9
+        assert np.abs(a.cells.getRegion() - b.cells.getRegion()).max() <= 1e-9
+        assert np.abs(a.cell_corners() - b.cell_corners()).max() <= 1e-9
+    assert np.abs(ca - region).max() > 0.05
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("cfg", [dict(reset=0, fb_reinit=0, thresh=0.05), dict(reset=1, fb_reinit=0, thresh=0.05),
                                  dict(reset=0, fb_reinit=1, thresh=0.02), dict(reset=0, fb_reinit=0, thresh=1e-7)])
 def test_grid_tracker_forward_backward(cfg):
