@@ -136,6 +136,18 @@ public:
 	}
 	//! prev_pts = curr_pts (reset_at_each_frame = 0, GridTracker.cc:276-279)
 	void gridCommit(){ check(mtfb_grid_commit(ctx)); }
+	//! everything GridTracker::update does after its cells, queued on the device without a host hop (GridTracker.cc:265-280 +
+	//! resetTrackers(true), :345-392, for the shipped grid: reset_at_each_frame = 1, patch_centroid_inside = 1, fixed patch size):
+	//! the estimate, `ssm.applyWarpToCorners` + `ssm.setCorners` on `region` (2 x 4 doubles of the grid's own SSM, updated in
+	//! place), every cell re-initialised at the patch_size box around the centroid of its four grid points.  A GridBase subclass
+	//! that owns this Batch calls it from update() and copies `region` into cv_corners_mat.
+	bool gridAdvance(int ssm, int grid_size_x, int grid_size_y, double patch_size_x, double patch_size_y, double *region,
+		double *state_update, unsigned char *mask, const mtfb_est_params &ep){
+		int info[4];
+		check(mtfb_grid_advance(ctx, ssm, &ep, grid_size_x, grid_size_y, patch_size_x, patch_size_y, region, state_update, mask, nullptr, info));
+		fetch();
+		return info[0] != 0;
+	}
 	//! mtf::SSMEstimatorParams -> mtfb_est_params (method: SSMEstimatorParams::EstType as an int); seed replaces random_device
 	static mtfb_est_params estParams(int method, double ransac_reproj_thresh, int n_model_pts, bool refine, int max_iters,
 		int max_subset_attempts, double confidence, int lm_max_iters, unsigned long long seed){
