@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(T, MINB) ncc_update_f32_kernel(DevBatch b, uns
 	const float m0f = (float)m0;
 	const double delta0 = m0 - (double)m0f;            // I0 - mean_0 = (I0 - m0f) - delta0
 	const bool jac_half = ESM && (b.jac_type == MTFB_ESM_JAC_DIFF_OF_JACS);
+	const double rN = 1.0 / N, rc = 1.0 / c;
 	// template-local coordinates of a grid position, as front_fast computes them
 	auto local_xy = [&](float rowf, float colf, float &xl, float &yl){
 		const float u = fmaf(colf, b.gx_step, b.gx_lo), v = fmaf(rowf, b.gy_step, b.gy_lo);
@@ -252,27 +253,30 @@ __global__ void __launch_bounds__(T, MINB) ncc_update_f32_kernel(DevBatch b, uns
 		if(lean_tail){
 			// everything by warp 0, no block barrier until the pass ends
 			if(warp == 0){
+				// (reciprocals instead of the ten IEEE divisions of the straightforward form: each costs ~20 dependent fp64
+				// instructions on this warp's critical path, and the sums carry fp32 rounding anyway)
 				const double S_it = s_sum[0], S_it2 = s_sum[1], S_i0it = s_sum[2], S_i0 = s_sum[3];
-				const double mt = S_it / N;                               // mean of It' = It - m0f
-				const double bn = sqrt(S_it2 - S_it*mt);                  // |It - mean|          (NCC.cc:145-147)
-				const double fv = (S_i0it - mt*S_i0) / (bn*c);            // f = <I0c, Itc> / bc  (NCC.cc:141, 151-152)
+				const double mt = S_it * rN;                              // mean of It' = It - m0f
+				const double bn2 = S_it2 - S_it*mt;
+				const double rb = rsqrt_newton(bn2), bn = bn2 * rb;      // |It - mean|          (NCC.cc:145-147)
+				const double fv = (S_i0it - mt*S_i0) * rb * rc;           // f = <I0c, Itc> / bc  (NCC.cc:141, 151-152)
 				f = fv;
-				const double rb = 1.0 / bn;
 				if(lane < S){
 					const double sD = s_sum[L::oD + lane];
 					const double sB = (s_sum[L::oItD + lane] - mt*sD) * rb;
-					const double sC = (s_sum[L::oI0D + lane] - delta0*sD) / c;
+					const double sC = (s_sum[L::oI0D + lane] - delta0*sD) * rc;
 					double jv = (sC - fv*sB) * rb;
 					if(ESM){
 						const double sD0 = s_t0[lane];
-						jv -= ((s_sum[L::oItD0 + lane] - mt*sD0) * rb - fv*(s_t0[S + lane] - delta0*sD0) / c) / c;
+						jv -= ((s_sum[L::oItD0 + lane] - mt*sD0) * rb - fv*(s_t0[S + lane] - delta0*sD0) * rc) * rc;
 					}
 					s_B[lane] = sB;
 					s_Jl[lane] = jac_half ? jv * 0.5 : jv;
 				}
+				(void)bn;
 				__syncwarp();
 				if(lane < S){
-					const double rN = 1.0 / N, rb2 = rb*rb, mj = s_sum[L::oD + lane] * rN, vj = s_B[lane];
+					const double rb2 = rb*rb, mj = s_sum[L::oD + lane] * rN, vj = s_B[lane];
 #pragma unroll
 					for(int i = 0; i < S; ++i){
 						const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
