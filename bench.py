@@ -249,11 +249,34 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
 
     gathered = torch.empty((n_total, 8), dtype=torch.float64, device=dev) if world > 1 else None
     peer = world > 1 and args.collective == "peer"
+    peer_note = None
     if peer:
         # the library's own exchange over NVLink peer memory: the update kernel stores each patch's corners into the gathered
-        # arrays of all ranks (CUDA IPC mappings), mtfb_peer_gather signals / waits -- no collective library on the path
-        handles = sharding.exchange_peer_handles(tr.peer_export(n_total))
-        tr.peer_attach(env.rank, world, sharding.shard_range(n_total, world, env.rank)[0], handles)
+        # arrays of all ranks (CUDA IPC mappings), mtfb_peer_gather signals / waits -- no collective library on the path.
+        # Should the mapping fail on ANY rank (no peer access between two of the GPUs, IPC disabled in the container), every
+        # rank falls back to NCCL's all-gather together, and the line says so
+        ok, why = 1, ""
+        try:
+            handle = tr.peer_export(n_total)
+        except Exception as e:
+            ok, why, handle = 0, "export: %s" % e, np.zeros(api.PEER_HANDLE_BYTES, dtype=np.uint8)
+        handles = sharding.exchange_peer_handles(handle)
+        if ok:
+            try:
+                if os.environ.get("MTFB_BENCH_PEER_FAIL") == str(env.rank):       # (test hook: exercise the fallback)
+                    raise RuntimeError("forced by MTFB_BENCH_PEER_FAIL")
+                tr.peer_attach(env.rank, world, sharding.shard_range(n_total, world, env.rank)[0], handles)
+            except Exception as e:
+                ok, why = 0, "attach: %s" % e
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = False
+            peer_note = "peer-memory exchange unavailable (%s): NCCL all-gather instead" % (why or "another rank")
+            tr.close()
+            tr = api.BatchTracker(prm)
+            tr.set_stream(stream.cuda_stream)
+            d_corners = sharding.device_view(tr.device_results()[0], (P, 8), dev)
 
     def gather():
         # north_star: one all-gather of the per-patch results over NVLink (per frame: LK iterations of different patches
@@ -371,6 +394,7 @@ def measure(args, precision, f32_solve, env, n_total, frames, corners, order, d_
         ms, kms, e2e_ms, raw_ms, e2e_serial_ms = [float(x) for x in t.tolist()]
     tr.close()
     return dict(ms=ms, kms=kms, e2e_ms=e2e_ms, raw_ms=raw_ms, e2e_serial_ms=e2e_serial_ms, launches=int(launches), status=status, final=final, windows=windows,
+                peer=peer, peer_note=peer_note,
                 truth=truth_error(final, corners, last_frame))
 
 
@@ -444,7 +468,7 @@ def config2_line(args, env, sampler, strong):
                    "occupancy": args.occ if args.threads else "auto",
                    "collective": ("none" if world == 1 else "per frame, fused: the update kernel stores the P x 8 corners into every rank's gathered "
                                   "array over NVLink peer memory (CUDA IPC), one signal / wait kernel; checked against NCCL's all-gather"
-                                  if args.collective == "peer" else "NCCL all_gather of the P x 8 corners per frame from the kernel's output buffer")},
+                                  if main.get("peer") else (main.get("peer_note") or "NCCL all_gather of the P x 8 corners per frame from the kernel's output buffer"))},
         "e2e": {"value": total_iters / (main["e2e_ms"] * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": IMG * IMG * 4, "d2h_bytes_per_step": P * 8 * 8,
                 "upload": "frame i + 1 uploads on the library's copy stream while update(i) runs (mtfb_set_image_async, two device "
