@@ -67,6 +67,9 @@ cudaError_t launch_update_ssd(int ssm, int sm, int threads, int occ, const DevBa
 cudaError_t launch_set_region(int ssm, const DevBatch &b, const double *d_corners, cudaStream_t st);
 // setRegion of the search methods that keep template Jacobians (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): SSD
 cudaError_t launch_reinit_ssd(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
+// ... MI (lk_mi.cu)
+cudaError_t launch_reinit_mi(int ssm, int threads, const DevBatch &b, const double *d_corners, int n_bins, double pre_seed,
+	double *mi_tab, cudaStream_t st);
 // ... NCC (lk_ncc.cu)
 cudaError_t launch_reinit_ncc(int ssm, int threads, const DevBatch &b, const double *d_corners, cudaStream_t st);
 cudaError_t launch_stage(int ssm, int threads, const DevBatch &b, const StageTaps &t, cudaStream_t st);

@@ -97,7 +97,13 @@ struct MiParams { int B; double pre_seed, hist_pre_seed, hist_norm_mult; int cop
 // per-template table kept in global memory (P x MI_TAB doubles): [0..B) init_hist, [16..16+B) init_hist_log
 constexpr int MI_TAB = 32;
 
-template<int SSM, int T>
+// REINIT: setRegion() of the search methods that keep template Jacobians -- nt::ESM::setRegion (NT/ESM.cc:150-168), nt::FCLK::setRegion
+// with InitialSelf (NT/FCLK.cc:360-376): ssm.setCorners, init_pix_jacobian = cmptInitPixJacobian(am.getInitPixGrad()) at the NEW
+// template points, init_self_hessian = MI::cmptSelfHessian(init_pix_jacobian) (MI.cc:515-594), which reads the appearance model's
+// CURRENT state: curr_hist and the self joint histogram of the pixel values of the LAST pass of the last update (the update kernel
+// leaves them in It_scratch; after initialize() they are the template's).  The template values, init_hist and f are kept; the
+// template gradient becomes the un-chained one (G0raw).
+template<int SSM, int T, bool REINIT = false>
 __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__restrict__ corners_in, MiParams mp, double *mi_tab){
 	constexpr int S = StateSize<SSM>::value;
 	constexpr int NH = S*(S + 1) / 2;
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 	if(warp == 0){
 		Mat3 dlt = set_corners<SSM>(b, p, lane, c_in);
 		if(lane < 9) s_dlt[lane] = dlt.m[lane];
-		if(lane == 0){ b.n_iters[p] = 0; b.status[p] = 0; }
+		if(!REINIT && lane == 0){ b.n_iters[p] = 0; b.status[p] = 0; }
 	}
 	for(int i = tid; i < B; i += T) s_hist[i] = mp.hist_pre_seed;
 	for(int i = tid; i < B*B; i += T) s_joint[i] = mp.pre_seed;
@@ -125,17 +131,27 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 	// (the affine chain rule's a, b, c, d = curr_state + identity, Affine.cc:220-223: the identity unless the start is the NDLT warp)
 	const double abcd[4] = { (W.m[0] - 1) + 1, W.m[1], W.m[3], (W.m[4] - 1) + 1 };
 	double *I0 = b.I0 + (size_t)p*N, *G0 = b.G0 + (size_t)p * 2 * N;
+	// the pixel values the self Hessian is built on: the template's own at initialize(), the last pass's at setRegion()
+	const double *Vh = REINIT ? b.It_scratch + (size_t)p*N : I0;
 	// phase 1: template values (scaled to bin units, MI.cc:91-94), chained gradient, init_hist and the self joint histogram
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
-		Sample smp;
-		pixel_value_and_gradient<SSM, false>(b, W, g, smp);
-		const double val = b.pix_mult*smp.val + b.pix_add;
-		double J[S];
-		pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, J);
-		I0[it.pix] = val;
-		G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
-		G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+		double val;
+		if(REINIT){
+			val = Vh[it.pix];
+			G0[it.pix] = b.G0raw[(size_t)p * 2 * N + it.pix]; G0[N + it.pix] = b.G0raw[(size_t)p * 2 * N + N + it.pix];
+		} else{
+			PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
+			Sample smp;
+			pixel_value_and_gradient<SSM, false>(b, W, g, smp);
+			val = b.pix_mult*smp.val + b.pix_add;
+			double J[S];
+			pixel_jacobian_row<SSM>(b, W, abcd, g, smp.gx, smp.gy, J);
+			I0[it.pix] = val;
+			G0[it.pix] = (SSM == SSM_HOM) ? J[2] : J[0];
+			G0[N + it.pix] = (SSM == SSM_HOM) ? J[5] : J[1];
+			if(b.G0raw){ b.G0raw[(size_t)p * 2 * N + it.pix] = smp.gx; b.G0raw[(size_t)p * 2 * N + N + it.pix] = smp.gy; }
+			if(b.It_scratch) b.It_scratch[(size_t)p*N + it.pix] = val;          // am.initializePixVals: It = I0
+		}
 		const BinWeights bw = bin_weights(val, B);
 #pragma unroll
 		for(int k = 0; k < 4; ++k){
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 	for(int i = tid; i < B; i += T){
 		const double h = s_hist[i] * mp.hist_norm_mult;
 		s_hist[i] = h; s_hist_log[i] = log(h);
-		mi_tab[(size_t)p*MI_TAB + i] = h; mi_tab[(size_t)p*MI_TAB + 16 + i] = s_hist_log[i];
+		if(!REINIT){ mi_tab[(size_t)p*MI_TAB + i] = h; mi_tab[(size_t)p*MI_TAB + 16 + i] = s_hist_log[i]; }
 	}
 	cta_sync<T>();
 	for(int i = tid; i < B*B; i += T){
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 		s_factor[i] = 1 + log(jh) - s_hist_log[r];                        // self_grad_factor(curr = r, init = c) (MI.cc:655)
 	}
 	cta_sync<T>();
-	if(tid == 0){
+	if(!REINIT && tid == 0){
 		// f = max_similarity = MI of the template with itself (MI.cc:270-283)
 		double f = 0;
 		for(int c = 0; c < B; ++c) for(int r = 0; r < B; ++r){
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(T) mi_init_kernel(DevBatch b, const double *__
 		PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);
 		double D[S];
 		init_pix_jacobian<SSM>(g.ix, g.iy, G0[it.pix], G0[N + it.pix], D);
-		const double v = I0[it.pix];
+		const double v = Vh[it.pix];
 		const BinWeights bw = bin_weights(v, B);
 		double x = bw.lo - v, hist_hess_term = 0;
 #pragma unroll
@@ -553,6 +569,9 @@ __global__ void __launch_bounds__(T, min_blocks(T, 1)) mi_update_kernel(DevBatch
 		if(counts_as_iteration<SM>(ctrl, b.nt_semantics)) ++iter_id;
 	}
 	if(warp == 0) store_patch_state<SSM>(b, p, lane, s_W, s_corners, f, n_passes, patch_status);
+	// the AM's pixel values stay those of the last pass: what setRegion's cmptSelfHessian will see (mi_init_kernel<REINIT>);
+	// large templates already keep them in the scratch row
+	if(KEEP_IT && b.It_scratch) for(int pix = tid; pix < N; pix += T) b.It_scratch[(size_t)p*N + pix] = s_It[pix];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,6 +595,24 @@ template<int SSM> static cudaError_t launch_init_t(int threads, const DevBatch &
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
+}
+template<int SSM> static cudaError_t launch_reinit_t(int threads, const DevBatch &b, const double *d_corners, const MiParams &mp,
+	double *mi_tab, cudaStream_t st){
+	switch(threads){
+	case 32: mi_init_kernel<SSM, 32, true><<<b.P, 32, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	case 64: mi_init_kernel<SSM, 64, true><<<b.P, 64, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	case 128: mi_init_kernel<SSM, 128, true><<<b.P, 128, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	case 256: mi_init_kernel<SSM, 256, true><<<b.P, 256, 0, st>>>(b, d_corners, mp, mi_tab); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_reinit_mi(int ssm, int threads, const DevBatch &b, const double *d_corners, int n_bins, double pre_seed,
+	double *mi_tab, cudaStream_t st){
+	if(n_bins < 4 || n_bins > MI_BMAX || !b.It_scratch || !b.G0raw) return cudaErrorInvalidValue;
+	const MiParams mp = make_mi_params(b, n_bins, pre_seed);
+	if(ssm == SSM_HOM) return launch_reinit_t<SSM_HOM>(threads, b, d_corners, mp, mi_tab, st);
+	return launch_reinit_t<SSM_AFF>(threads, b, d_corners, mp, mi_tab, st);
 }
 cudaError_t launch_init_mi(int ssm, int threads, const DevBatch &b, const double *d_corners, int n_bins, double pre_seed,
 	double *mi_tab, cudaStream_t st){

@@ -372,7 +372,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		const bool mi_it_scratch = p->am == MTFB_AM_MI && (size_t)N*sizeof(double) > 24 * 1024 && !std::getenv("MTFB_MI_RESAMPLE");
 		// NCC with ESM / FCLK: the pixel values of the last pass and the un-chained template gradient, for setRegion (lk_ncc.cu
 		// ncc_reinit_kernel)
-		const bool ncc_it_last = p->am == MTFB_AM_NCC && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK);
+		const bool ncc_it_last = (p->am == MTFB_AM_NCC || p->am == MTFB_AM_MI) && (p->sm == MTFB_SM_ESM || p->sm == MTFB_SM_FCLK);   // (and MI: mi_init_kernel<REINIT>)
 		size_t per_patch = 9 + 9 + S + 8 + 8 + (size_t)N + 2 * (size_t)N + 64 + 1 + 8 + 32 + 64 + ((keep_raw_grad || ncc_it_last) ? 2 * (size_t)N : 0) +
 			((mi_it_scratch || ncc_it_last) ? (size_t)N : 0);
 		if(cudaMalloc(&c->d_patch, per_patch*P*sizeof(double)) != cudaSuccess){ st = MTFB_ERR_NO_MEMORY; break; }
@@ -699,21 +699,22 @@ mtfb_status mtfb_initialize(mtfb_ctx *c, const double *corners){
 
 mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 	if(c && !c->initialized) return fail(MTFB_ERR_LOGIC, "mtfb_set_region: initialize has not been called");
-	bool ssm_only = true, ncc_reinit = false;
+	bool ssm_only = true, ncc_reinit = false, mi_reinit = false;
 	if(c){
 		ssm_only = (c->prm.sm == MTFB_SM_ICLK) || (c->prm.sm == MTFB_SM_PF) || (c->prm.sm == MTFB_SM_FALK) || (c->prm.sm == MTFB_SM_IALK) ||
 			(c->prm.sm == MTFB_SM_FCLK && c->prm.hess_type != MTFB_LK_HESS_INITIAL_SELF);
 		// ESM and FCLK-InitialSelf also rebuild the template Jacobian and init_self_hessian at the new points: SSD, and NCC
 		// from an identity start (its kept template gradient is then the un-chained one)
 		ncc_reinit = !ssm_only && c->prm.am == MTFB_AM_NCC && !c->prm.hom_normalized_init && c->b.It_scratch;
-		if(!ssm_only && !(c->prm.am == MTFB_AM_SSD && c->b.G0raw) && !ncc_reinit) return fail(MTFB_ERR_NOT_SUPPORTED,
-			"mtfb_set_region: for ESM and for FCLK with the InitialSelf Hessian the SSD and NCC (normalized_init = 0) appearance "
-			"models are implemented; MI's cmptSelfHessian at the new points is not");
+		mi_reinit = !ssm_only && c->prm.am == MTFB_AM_MI && !c->prm.hom_normalized_init && c->b.It_scratch && c->b.G0raw;
+		if(!ssm_only && !(c->prm.am == MTFB_AM_SSD && c->b.G0raw) && !ncc_reinit && !mi_reinit) return fail(MTFB_ERR_NOT_SUPPORTED,
+			"mtfb_set_region: for ESM and for FCLK with the InitialSelf Hessian, NCC and MI are implemented for normalized_init = 0");
 	}
 	mtfb_status st = upload_corners(c, corners, "mtfb_set_region");
 	if(st != MTFB_OK) return st;
 	if(ssm_only) CUDA_TRY(launch_set_region(c->prm.ssm, c->b, c->d_corners_in, c->stream));
 	else if(ncc_reinit) CUDA_TRY(launch_reinit_ncc(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
+	else if(mi_reinit) CUDA_TRY(launch_reinit_mi(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->prm.mi_n_bins, c->prm.mi_pre_seed, c->d_mi_tab, c->stream));
 	else CUDA_TRY(launch_reinit_ssd(c->prm.ssm, c->threads, c->b, c->d_corners_in, c->stream));
 	++c->launches;
 	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }

@@ -603,17 +603,19 @@ def test_affine_normalized_init(seq384, am, sm):
 
 @pytest.mark.parametrize("sm,hess", [("esm", "sum_of_self"), ("esm", "initial_self"), ("esm", "sum_of_std"), ("fclk", "initial_self")])
 @pytest.mark.parametrize("ssm", SSMS)
-def test_set_region_ncc(seq384, sm, hess, ssm):
-    """nt::ESM::setRegion / nt::FCLK::setRegion (InitialSelf) with NCC (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): the new
-    init_self_hessian is NCC::cmptSelfHessian (NCC.cc:337-389) of the template Jacobian at the NEW points, evaluated on the
-    appearance model's state of the LAST pass of the last update -- and of initialize() when setRegion comes first"""
+@pytest.mark.parametrize("am", ["ncc", "mi"])
+def test_set_region_ncc(seq384, sm, hess, ssm, am):
+    """nt::ESM::setRegion / nt::FCLK::setRegion (InitialSelf) with NCC and MI (NT/ESM.cc:150-168, NT/FCLK.cc:360-376): the new
+    init_self_hessian is NCC::cmptSelfHessian (NCC.cc:337-389) / MI::cmptSelfHessian (MI.cc:515-594) of the template Jacobian at
+    the NEW points, evaluated on the appearance model's state of the LAST pass of the last update -- and of initialize() when
+    setRegion comes first"""
     from mtf_b200 import api
     frames, _ = seq384
     cs = np.concatenate([common.patches(3, 52.3, 384, 384, seed=23), common.quad_patches(3, 384, 384, seed=24)])
     h = (api.ESM_HESS if sm == "esm" else api.LK_HESS)[hess]
     shift = np.array([[0.8], [-0.6]])
     for first_update in (True, False):
-        g = _gpu("ncc", ssm, sm, len(cs), hess_type=h)
+        g = _gpu(am, ssm, sm, len(cs), hess_type=h)
         g.enable_iter_log(30)
         g.initialize(cs, frames[0])
         if first_update:
@@ -624,7 +626,7 @@ def test_set_region_ncc(seq384, sm, hess, ssm):
         g.update(frames[2])
         got, logs = g.getRegion(), g.iter_log()
         for i, c in enumerate(cs):
-            o = _oracle("ncc", ssm, sm, grad_mode=1, hess_type=h)
+            o = _oracle(am, ssm, sm, grad_mode=1, hess_type=h)
             o.set_image(frames[0]); o.initialize(c)
             if first_update:
                 o.set_image(frames[1]); o.update()
@@ -633,13 +635,36 @@ def test_set_region_ncc(seq384, sm, hess, ssm):
             assert len(o.log()) == len(logs[i])
             assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= 1e-7
             assert _rel(logs[i][0]["jacobian"], o.log()[0]["jacobian"]) <= 1e-6
-            assert np.abs(got[i] - o.corners()).max() <= 1e-5
-    # MI keeps failing loudly
-    gm = _gpu("mi", ssm, "esm", 2)
+            assert np.abs(got[i] - o.corners()).max() <= (1e-4 if am == "mi" else 1e-5)
+    # with a normalised start the kept template gradient is not the one setRegion needs: loud
+    gm = _gpu(am, "homography", "esm", 2, hom_normalized_init=1)
     gm.initialize(cs[:2], frames[0])
     with pytest.raises(api.MTFError) as e:
         gm.setRegion(cs[:2])
     assert e.value.type == "FunctonNotImplemented"
+
+
+def test_set_region_mi_large_template(seq384):
+    """the same for an MI template too large for the update kernel's shared memory (60 x 60: the pass's pixel values then live in
+    the global scratch row that setRegion reads)"""
+    from mtf_b200 import api
+    frames, _ = seq384
+    cs = common.patches(3, 61.3, 384, 384, seed=23)
+    shift = np.array([[0.8], [-0.6]])
+    kw = dict(resx=60, resy=60, hess_type=api.ESM_HESS["sum_of_self"])
+    g = _gpu("mi", "homography", "esm", len(cs), **kw)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0]); g.update(frames[1])
+    g.setRegion(g.getRegion() + shift)
+    g.update(frames[2])
+    got, logs = g.getRegion(), g.iter_log()
+    for i, c in enumerate(cs):
+        o = _oracle("mi", "homography", "esm", grad_mode=1, **kw)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        o.set_region(o.corners() + shift)
+        o.set_image(frames[2]); o.update()
+        assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= 1e-7
+        assert np.abs(got[i] - o.corners()).max() <= 1e-4
 
 
 @pytest.mark.parametrize("sm,hess", [("esm", "sum_of_self"), ("esm", "initial_self"), ("esm", "current_self"), ("fclk", "initial_self")])
