@@ -479,3 +479,32 @@ def test_ncc_f32_shipped_stopping_rule_and_set_region(seq384):
         o.set_image(frames[2]); o.update()
         assert abs(int(n_it[i]) - o.n_iters) <= 2
     assert np.abs(g.getRegion() - np.array([o.corners() for o in orcs])).max() <= 3e-2
+
+
+@pytest.mark.parametrize("ssm,sm,hess,extra", [("affine", "esm", 2, dict(leven_marq=1)),
+                                                ("homography", "fclk", 1, dict(leven_marq=1, hom_normalized_init=1)),
+                                                ("affine", "esm", 2, dict(nt_semantics=0)), ("homography", "esm", 2, dict())])
+def test_ncc_f32_variants(seq384, ssm, sm, hess, extra):
+    """NCC in F32 with Levenberg-Marquardt, the templated iteration counting and the Homography on general quadrilaterals without
+    normalised initialisation.  Without LM: corners 2e-3 px and the same pass counts.  With LM the accept / reject decisions compare
+    similarities that differ at fp32 rounding level once converged, so the number of (rejected) passes may differ; the corners stay
+    within 5e-3 px (measured 1.7e-3)"""
+    frames, _ = seq384
+    cs = np.concatenate([common.patches(4, 49.0, 384, 384), common.quad_patches(3, 384, 384, seed=11)])
+    kw = dict(hess_type=hess, epsilon=0.0, max_iters=30, **extra)
+    g = _gpu_am("ncc", ssm, sm, len(cs), **kw)
+    g.initialize(cs, frames[0])
+    orcs = []
+    for c in cs:
+        o = O.OracleTracker(O.make_params("ncc", ssm, sm, grad_mode=1, **kw))
+        o.set_image(frames[0]); o.initialize(c)
+        orcs.append(o)
+    lm = bool(extra.get("leven_marq"))
+    for fr in frames[1:3]:
+        g.update(fr)
+        got, n_it = g.getRegion(), g.n_iters()
+        for i, o in enumerate(orcs):
+            o.set_image(fr); o.update()
+            assert np.abs(got[i] - o.corners()).max() <= (5e-3 if lm else 2e-3)
+            if not lm:
+                assert int(n_it[i]) == o.n_iters
