@@ -254,7 +254,10 @@ def run_config3(env, root, res, n_steps, n_warm, strong=False, cpu=True, precisi
         "roofline": roofline(alg, P * iters, kms / n_steps, root,
                              "ncc_update_kernel<Affine,ESM>" if precision == "f64" else "ncc_update_f32_kernel<Affine,ESM>",
                              "fp64-issue bound (three sweeps per pass over It kept in shared memory), not HBM bound" if precision == "f64"
-                             else "one fp32 sweep per pass; bound by the per-pass serial tail (6 x 6 QR, update), not HBM"),
+                             else "one fp32 sweep per pass; bound by the per-pass serial tail (6 x 6 QR, update), not HBM",
+                             traffic=(12614656 if (precision != "f64" and res == 25 and P == 1024) else None),
+                             traffic_source=("profiles/r02_ncu_ncc_f32_summary.txt (dram__bytes_read + write, one launch)"
+                                             if (precision != "f64" and res == 25 and P == 1024) else None)),
         "stages_ms_per_step": {"cells_update_kernel": kms / n_steps, "estimate_and_reset": (ms - kms) / n_steps},
         "valid": {"finite": finite, "n_iters_per_cell": int(n_it[0]), "estimate_ok": bool(est["ok"]), "inliers": int(est["n_inliers"]),
                   "hypotheses": int(est["drawn"]), "region_drift_px": drift},
