@@ -46,6 +46,7 @@ struct DevBatch {
 	int log_slots;
 	// parameters
 	int max_iters, hess_type, jac_type, leven_marq, nt_semantics;
+	int additive_sm;             // the search method is nt::FALK / nt::IALK: their template Jacobian is ssm.cmptPixJacobian at the start state
 	int chained;                 // {esm,fc,ic}_chained_warp
 	int norm_init;               // hom_normalized_init
 	int f32_local_solve;         // mtfb_params::f32_solve == MTFB_F32_SOLVE_LOCAL

@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(T) ssd_init_kernel(DevBatch b, const double *_
 			b.G0f[(size_t)p * 2 * b.N + it.pix] = (float)G0[it.pix];
 			b.G0f[(size_t)p * 2 * b.N + b.N + it.pix] = (float)G0[b.N + it.pix];
 		}
+		// nt::FALK / nt::IALK::initialize (NT/FALK.cc:108-118, NT/IALK.cc:70-80): init_pix_jacobian = ssm.cmptPixJacobian(am.getInitPixGrad())
+		// at the START state -- the same row as above from an identity start, not from a normalised one
+		if(b.additive_sm) additive_pix_jacobian<SSM>(g, smp.gx, smp.gy, J);
 #pragma unroll
 		for(int i = 0; i < S; ++i){
 #pragma unroll

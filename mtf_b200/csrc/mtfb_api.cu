@@ -281,9 +281,6 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 			p->am, p->ssm, p->sm, p->hess_type, p->jac_type, why);
 	if(p->hom_normalized_init && p->ssm == MTFB_SSM_TRANSLATION)
 		return fail(MTFB_ERR_INVALID_ARG, "mtfb_create: the Translation SSM has no normalized_init (TranslationParams.h)");
-	if(p->hom_normalized_init && (p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK))
-		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: the additive searches (FALK / IALK) are implemented for normalized_init = 0 "
-			"(their template Jacobian, ssm.cmptPixJacobian at the start state, assumes the identity start)");
 	if(p->hom_normalized_init && p->ssm == MTFB_SSM_AFFINE && p->precision != MTFB_PRECISION_F64)
 		return fail(MTFB_ERR_NOT_SUPPORTED, "mtfb_create: the affine normalized_init (computeAffineNDLT, warpUtils.cc:378-386) is "
 			"implemented in the F64 precision");
@@ -440,6 +437,7 @@ mtfb_status mtfb_create(const mtfb_params *p, mtfb_ctx **out){
 		b.leven_marq = p->leven_marq; b.nt_semantics = p->nt_semantics;
 		// the templated search methods have no chained_warp switch: always chained (ESM.cc:94-95, FCLK.cc:82-86, ICLK.cc:80-90)
 		b.chained = (p->chained_warp || !p->nt_semantics) ? 1 : 0;
+		b.additive_sm = (p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK) ? 1 : 0;
 		// FALK / IALK have no such switch: am->updatePixGrad(ssm->getPts()) (NT/FALK.cc:166, NT/IALK.cc:64)
 		if(p->sm == MTFB_SM_FALK || p->sm == MTFB_SM_IALK) b.chained = 1;
 		b.norm_init = p->hom_normalized_init ? 1 : 0;

@@ -227,10 +227,6 @@ def test_error_contract(seq384):
     with pytest.raises(api.MTFError) as e:
         _gpu("ssd", "affine", "fclk", 2, hom_normalized_init=1, precision="f32")       # the affine NDLT start: F64 only
     assert e.value.type == "FunctonNotImplemented"
-    for ssm in ("homography", "affine"):
-        with pytest.raises(api.MTFError) as e:
-            _gpu("ssd", ssm, "falk", 2, hom_normalized_init=1)                         # additive searches: identity start only
-        assert e.value.type == "FunctonNotImplemented"
     bad = common.patches(2, 49.0, 384, 384); bad[0, 0, 0] = np.nan
     g.setImage(frames[0])
     with pytest.raises(api.MTFError) as e:
@@ -521,7 +517,7 @@ def test_non_chained_warp_path(seq384, am, sm, ssm):
 
 
 # ------------------------------------------------------------------------------------------------ hom_normalized_init
-@pytest.mark.parametrize("am,sm", [("ssd", "fclk"), ("ssd", "esm"), ("ssd", "iclk"), ("ncc", "esm"), ("mi", "iclk")])
+@pytest.mark.parametrize("am,sm", [("ssd", "fclk"), ("ssd", "esm"), ("ssd", "iclk"), ("ncc", "esm"), ("mi", "iclk"), ("ssd", "falk"), ("ssd", "ialk")])
 def test_hom_normalized_init(seq384, am, sm):
     """hom_normalized_init = 1 (shipped in Config/modules.cfg): the template points are the unit-square grid and the DLT
     warp lives in curr_warp; the Hessian is then well conditioned and never rank-truncated"""
@@ -554,7 +550,7 @@ def test_hom_normalized_init(seq384, am, sm):
     assert (g.patch_status() & 2 == 0).all() or am == "mi"
 
 
-@pytest.mark.parametrize("am,sm", [("ssd", "fclk"), ("ssd", "esm"), ("ssd", "iclk"), ("ncc", "esm"), ("mi", "iclk"), ("ncc", "fclk")])
+@pytest.mark.parametrize("am,sm", [("ssd", "fclk"), ("ssd", "esm"), ("ssd", "iclk"), ("ncc", "esm"), ("mi", "iclk"), ("ncc", "fclk"), ("ssd", "falk"), ("ssd", "ialk")])
 def test_affine_normalized_init(seq384, am, sm):
     """aff_normalized_init = 1 (Affine.cc:65-74): the template stays the pixel-scaled square [1 - res/2, res/2]^2, curr_warp
     starts as utils::computeAffineNDLT(init_corners, corners) (warpUtils.cc:378-386: normalizePts + least squares + inverse
