@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(T) ncc_reinit_kernel(DevBatch b, const double 
 #pragma unroll
 	for(int i = 0; i < L::NA; ++i) acc[i] = 0;
 	for(PixIter it(tid, T, b.resx); it.pix < N; it.next(T)){
-		const PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], false);
+		const PixGeom g = pixel_geometry<SSM>(dlt, W, b.xv[it.col], b.yv[it.row], b.norm_init != 0);   // (only the template point is used)
 		double D[S];
 		const double gx = Gr[it.pix], gy = Gr[N + it.pix];
 		init_pix_jacobian<SSM>(g.ix, g.iy, gx, gy, D);

@@ -703,10 +703,10 @@ mtfb_status mtfb_set_region(mtfb_ctx *c, const double *corners){
 			(c->prm.sm == MTFB_SM_FCLK && c->prm.hess_type != MTFB_LK_HESS_INITIAL_SELF);
 		// ESM and FCLK-InitialSelf also rebuild the template Jacobian and init_self_hessian at the new points: SSD, and NCC
 		// from an identity start (its kept template gradient is then the un-chained one)
-		ncc_reinit = !ssm_only && c->prm.am == MTFB_AM_NCC && !c->prm.hom_normalized_init && c->b.It_scratch;
-		mi_reinit = !ssm_only && c->prm.am == MTFB_AM_MI && !c->prm.hom_normalized_init && c->b.It_scratch && c->b.G0raw;
+		ncc_reinit = !ssm_only && c->prm.am == MTFB_AM_NCC && c->b.It_scratch && c->b.G0raw;
+		mi_reinit = !ssm_only && c->prm.am == MTFB_AM_MI && c->b.It_scratch && c->b.G0raw;
 		if(!ssm_only && !(c->prm.am == MTFB_AM_SSD && c->b.G0raw) && !ncc_reinit && !mi_reinit) return fail(MTFB_ERR_NOT_SUPPORTED,
-			"mtfb_set_region: for ESM and for FCLK with the InitialSelf Hessian, NCC and MI are implemented for normalized_init = 0");
+			"mtfb_set_region: this context keeps neither the un-chained template gradient nor the last pass's pixel values");
 	}
 	mtfb_status st = upload_corners(c, corners, "mtfb_set_region");
 	if(st != MTFB_OK) return st;

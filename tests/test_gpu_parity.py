@@ -632,12 +632,25 @@ def test_set_region_ncc(seq384, sm, hess, ssm, am):
             assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= 1e-7
             assert _rel(logs[i][0]["jacobian"], o.log()[0]["jacobian"]) <= 1e-6
             assert np.abs(got[i] - o.corners()).max() <= (1e-4 if am == "mi" else 1e-5)
-    # with a normalised start the kept template gradient is not the one setRegion needs: loud
-    gm = _gpu(am, "homography", "esm", 2, hom_normalized_init=1)
-    gm.initialize(cs[:2], frames[0])
-    with pytest.raises(api.MTFError) as e:
-        gm.setRegion(cs[:2])
-    assert e.value.type == "FunctonNotImplemented"
+    # ... and from a normalised start (the shipped hom_normalized_init = 1; the Affine NDLT start)
+    g = _gpu(am, ssm, sm, len(cs), hess_type=h, hom_normalized_init=1)
+    g.enable_iter_log(30)
+    g.initialize(cs, frames[0]); g.update(frames[1])
+    g.setRegion(g.getRegion() + shift)
+    g.update(frames[2])
+    got, logs = g.getRegion(), g.iter_log()
+    for i, c in enumerate(cs):
+        o = _oracle(am, ssm, sm, grad_mode=1, hess_type=h, hom_normalized_init=1)
+        o.set_image(frames[0]); o.initialize(c); o.set_image(frames[1]); o.update()
+        o.set_region(o.corners() + shift)
+        o.set_image(frames[2]); o.update()
+        # the first pass after setRegion is what this test is about; the rest of the frame only where the reference itself
+        # converges (on the stored Hessian alone, rebuilt on the last pass's state, the reference's iteration diverges or
+        # collapses the region for some of these patches: nothing to compare a trajectory with)
+        assert _rel(logs[i][0]["hessian"], o.log()[0]["hessian"]) <= 1e-6
+        assert _rel(logs[i][0]["jacobian"], o.log()[0]["jacobian"]) <= 1e-5
+        if hess.startswith("sum") and np.isfinite(o.corners()).all() and o.n_iters < 30:
+            assert np.abs(got[i] - o.corners()).max() <= 1e-4
 
 
 def test_set_region_mi_large_template(seq384):
