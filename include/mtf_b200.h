@@ -290,6 +290,11 @@ mtfb_status mtfb_grid_commit(mtfb_ctx *ctx);
  * (utils::getPtsFromCorners), every cell's patch_size box around the centroid of its four grid points, every cell
  * re-initialised there on the current frame, prev_pts <- the new centroids.  region: 2 x 4 corners of the grid's own SSM,
  * in / out (host).  One stream synchronisation, at the end. */
+/* GridTracker::initialize / setRegion with reset_at_each_frame = 1 (GridTracker.cc:232-245, 282-287): the same layout for a given
+ * region, every cell initialised there on the current frame (the region is not changed: with an identity update the layout
+ * kernel's applyWarpToCorners is the identity up to the division by one) */
+mtfb_status mtfb_grid_initialize(mtfb_ctx *ctx, int grid_size_x, int grid_size_y, double patch_size_x, double patch_size_y,
+	const double *region /* 8 */);
 mtfb_status mtfb_grid_advance(mtfb_ctx *ctx, int ssm, const mtfb_est_params *ep, int grid_size_x, int grid_size_y,
 	double patch_size_x, double patch_size_y, double *region /* 8, in / out */, double *state_update, unsigned char *mask /* P */,
 	double *warp /* 9 */, int *info /* 4 */);

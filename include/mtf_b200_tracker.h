@@ -141,6 +141,12 @@ public:
 	//! the estimate, `ssm.applyWarpToCorners` + `ssm.setCorners` on `region` (2 x 4 doubles of the grid's own SSM, updated in
 	//! place), every cell re-initialised at the patch_size box around the centroid of its four grid points.  A GridBase subclass
 	//! that owns this Batch calls it from update() and copies `region` into cv_corners_mat.
+	//! GridTracker::initialize / setRegion of the shipped grid: the cells' regions for `region`, every cell initialised there
+	void gridInitialize(int grid_size_x, int grid_size_y, double patch_size_x, double patch_size_y, const double *region){
+		upload();
+		check(mtfb_grid_initialize(ctx, grid_size_x, grid_size_y, patch_size_x, patch_size_y, region));
+		fetch();
+	}
 	bool gridAdvance(int ssm, int grid_size_x, int grid_size_y, double patch_size_x, double patch_size_y, double *region,
 		double *state_update, unsigned char *mask, const mtfb_est_params &ep){
 		int info[4];
@@ -281,6 +287,64 @@ private:
 	}
 	Batch batch;
 	double c8[8];
+};
+
+//! mtf::GridTracker<SSM> (SM/include/mtf/SM/GridTracker.h, SM/src/GridTracker.cc) for the shipped grid -- grid_size_x x grid_size_y
+//! patch trackers of ONE search method / appearance model / cell SSM, reset_at_each_frame = 1, patch_centroid_inside = 1, fixed
+//! patch size, no forward-backward estimation -- as ONE batch on the device: the cells' update is one launch, and everything
+//! after it (the robust estimate of the grid's own Homography / Affine from the cells' centroids, the region's new corners, the
+//! cells' next regions, their re-initialisation) is queued behind it without a host hop (Batch::gridAdvance).  The reference's
+//! GridTracker is composed in mtf.h:748-802 from a vector<TrackerBase*>; this class takes its place there when every cell runs
+//! the same tracker.  est: Batch::estParams(...); its seed advances by one per frame (the reference seeds every frame's
+//! estimator from random_device, SSMEstimator.cc:22-24).
+class GridTracker : public mtf::TrackerBase{
+public:
+	GridTracker(const char *sm, const char *am, const char *cell_ssm, int grid_size_x, int grid_size_y, int patch_size_x, int patch_size_y,
+		int cell_resx, int cell_resy, const char *grid_ssm, const mtfb_est_params &est) :
+		batch(makeParams(sm, am, cell_ssm, grid_size_x*grid_size_y, cell_resx, cell_resy)), gx(grid_size_x), gy(grid_size_y),
+		psx(patch_size_x), psy(patch_size_y), ep(est), seed0(est.seed), frame(0), mask((size_t)grid_size_x*grid_size_y, 1){
+		if(!strcmp(grid_ssm, "8") || !strcmp(grid_ssm, "hom") || !strcmp(grid_ssm, "homography")){ ssm = MTFB_SSM_HOMOGRAPHY; }
+		else if(!strcmp(grid_ssm, "6") || !strcmp(grid_ssm, "aff") || !strcmp(grid_ssm, "affine")){ ssm = MTFB_SSM_AFFINE; }
+		else{ throw mtf::utils::InvalidArgument(std::string("mtf_b200 :: GridTracker: the grid's SSM must be homography or affine, not ") + grid_ssm); }
+		name = "b200_grid";
+		cv_corners_mat.create(2, 4, CV_64FC1);
+		batch.gridEnable();
+	}
+	using TrackerBase::initialize;
+	using TrackerBase::update;
+	using TrackerBase::setRegion;
+	void setImage(const cv::Mat &img) override{ batch.setImage(img); }
+	//! GridTracker::initialize (GridTracker.cc:232-245): ssm.initialize(corners); resetTrackers(true)
+	void initialize(const cv::Mat &corners) override{ toRegion(corners); batch.gridInitialize(gx, gy, psx, psy, region); publish(); }
+	//! GridTracker::update (GridTracker.cc:247-285)
+	void update() override{
+		batch.update();
+		ep.seed = seed0 + (unsigned long long)(++frame);
+		batch.gridAdvance(ssm, gx, gy, psx, psy, region, ssm_update, mask.data(), ep);
+		publish();
+	}
+	//! GridTracker::setRegion (GridTracker.cc:287-291): ssm.setCorners(corners); resetTrackers(reinit_at_each_frame = true)
+	void setRegion(const cv::Mat &corners) override{ toRegion(corners); batch.gridInitialize(gx, gy, psx, psy, region); publish(); }
+	int inputType() const override{ return batch.inputType(); }
+	//! the estimator's inlier mask of the last update (pix_mask, GridTracker.h) and the cells' regions
+	const std::vector<unsigned char>& getPixMask() const{ return mask; }
+	Batch& getBatch(){ return batch; }
+private:
+	void toRegion(const cv::Mat &corners){
+		if(corners.rows != 2 || corners.cols != 4 || corners.type() != CV_64FC1){
+			throw mtf::utils::InvalidArgument("mtf_b200 :: corners must be a 2 x 4 CV_64FC1 matrix");
+		}
+		for(int k = 0; k < 8; ++k){ region[k] = corners.at<double>(k / 4, k % 4); }
+	}
+	void publish(){ for(int k = 0; k < 8; ++k){ cv_corners_mat.at<double>(k / 4, k % 4) = region[k]; } }
+	Batch batch;
+	int gx, gy, ssm;
+	double psx, psy;
+	mtfb_est_params ep;
+	unsigned long long seed0;
+	long frame;
+	double region[8], ssm_update[8];
+	std::vector<unsigned char> mask;
 };
 
 //! Patch i of a shared Batch.  A composite that loops `trackers[i]->update()` (GridTracker.cc:256-259, serial

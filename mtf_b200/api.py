@@ -93,7 +93,7 @@ EXPORTS = [
     "mtfb_get_init_pix_vals", "mtfb_get_curr_stage", "mtfb_get_curr_stage_f32", "mtfb_device_results",
     "mtfb_state_size", "mtfb_debug_colpiv_qr_solve",
     "mtfb_pf_default_params", "mtfb_pf_configure", "mtfb_pf_set_random_stream", "mtfb_pf_get_random_stream", "mtfb_pf_get_particles",
-    "mtfb_est_default_params", "mtfb_estimate_warp_from_pts", "mtfb_estimate_warp_from_corners_device", "mtfb_grid_enable", "mtfb_grid_estimate", "mtfb_grid_commit", "mtfb_grid_advance",
+    "mtfb_est_default_params", "mtfb_estimate_warp_from_pts", "mtfb_estimate_warp_from_corners_device", "mtfb_grid_enable", "mtfb_grid_estimate", "mtfb_grid_commit", "mtfb_grid_advance", "mtfb_grid_initialize",
     "mtfb_grid_get_pts",
     "mtfb_peer_export", "mtfb_peer_attach", "mtfb_peer_gather", "mtfb_peer_gathered", "mtfb_get_gathered_region",
 ]
@@ -155,6 +155,7 @@ def load_library(path=LIB_PATH):
     L.mtfb_grid_enable.argtypes = [vp]
     L.mtfb_grid_estimate.argtypes = [vp, C.c_int, C.POINTER(EstParams), vp, vp, vp, vp]
     L.mtfb_grid_commit.argtypes = [vp]
+    L.mtfb_grid_initialize.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, vp]
     L.mtfb_grid_advance.argtypes = [vp, C.c_int, C.POINTER(EstParams), C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     L.mtfb_grid_get_pts.argtypes = [vp, vp, vp]
     L.mtfb_peer_export.argtypes = [vp, C.c_int, vp]
@@ -464,6 +465,12 @@ class BatchTracker:
         ssm = SSM[ssm] if isinstance(ssm, str) else int(ssm)
         return self._est_result(ssm, self.P, lambda su, mk, wp, inf: self._L.mtfb_grid_estimate(
             self._h, ssm, C.byref(est_params), su, mk, wp, inf))
+
+    def grid_initialize(self, grid_size_x, grid_size_y, patch_size_x, patch_size_y, region):
+        """GridTracker::initialize for the shipped grid on the device: cell layout for `region` + every cell initialised there"""
+        reg = np.ascontiguousarray(region, dtype=np.float64).reshape(8)
+        self._check(self._L.mtfb_grid_initialize(self._h, int(grid_size_x), int(grid_size_y), float(patch_size_x), float(patch_size_y),
+                                                 reg.ctypes.data))
 
     def grid_advance(self, ssm, est_params, grid_size_x, grid_size_y, patch_size_x, patch_size_y, region):
         """grid_estimate + the region's update + the cell layout + the cells' re-initialisation, all on the device

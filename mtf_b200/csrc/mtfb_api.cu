@@ -983,6 +983,34 @@ mtfb_status mtfb_grid_estimate(mtfb_ctx *c, int ssm, const mtfb_est_params *ep, 
 	return est_run(c, "mtfb_grid_estimate", ssm, c->d_grid_prev, c->d_grid_curr, c->P, ep, state_update, mask, warp, info);
 }
 
+mtfb_status mtfb_grid_initialize(mtfb_ctx *c, int grid_size_x, int grid_size_y, double patch_size_x, double patch_size_y, const double *region){
+	if(!c || !region) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_initialize: null argument");
+	if(!c->grid_enabled) return fail(MTFB_ERR_LOGIC, "mtfb_grid_initialize: mtfb_grid_enable has not been called");
+	{ mtfb_status st0 = adopt_prefetched(c); if(st0 != MTFB_OK) return st0; }
+	if(!c->have_image) return fail(MTFB_ERR_LOGIC, "mtfb_grid_initialize: setImage has not been called");
+	if(grid_size_x < 1 || grid_size_y < 1 || grid_size_x*grid_size_y != c->P)
+		return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_initialize: %d x %d cells, the batch has %d patches", grid_size_x, grid_size_y, c->P);
+	if(!(patch_size_x > 0) || !(patch_size_y > 0)) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_initialize: patch sizes must be positive");
+	for(int i = 0; i < 8; ++i) if(!std::isfinite(region[i])) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_initialize: non-finite region corner");
+	CUDA_TRY(cudaSetDevice(c->prm.device));
+	{ mtfb_status st = est_reserve(c, (size_t)c->P); if(st != MTFB_OK) return st; }
+	c->all_parallelograms = true;                        // the cells are axis-aligned boxes
+	// GridTracker::initialize (GridTracker.cc:232-245): ssm.initialize(corners); resetTrackers(true) -- the layout kernel with a
+	// zero state update (the identity warp) leaves the region as it is
+	double *d_region = c->d_est_out + 32, *d_zero = c->d_est_out + 40;
+	CUDA_TRY(cudaMemcpyAsync(d_region, region, 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemsetAsync(d_zero, 0, 8 * sizeof(double), c->stream));
+	CUDA_TRY(launch_grid_layout(1, d_zero, d_region, grid_size_x, grid_size_y, patch_size_x, patch_size_y, c->d_corners_in, c->stream));
+	++c->launches;
+	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->d_mi_tab, c->stream));
+	++c->launches;
+	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }
+	c->initialized = true;
+	CUDA_TRY(launch_centroids(c->b.corners, c->P, c->d_grid_prev, c->stream));
+	++c->launches;
+	return MTFB_OK;
+}
+
 mtfb_status mtfb_grid_advance(mtfb_ctx *c, int ssm, const mtfb_est_params *ep, int grid_size_x, int grid_size_y, double patch_size_x,
 	double patch_size_y, double *region, double *state_update, unsigned char *mask, double *warp, int *info){
 	if(!c || !ep || !region) return fail(MTFB_ERR_INVALID_ARG, "mtfb_grid_advance: null argument");
@@ -1005,6 +1033,7 @@ mtfb_status mtfb_grid_advance(mtfb_ctx *c, int ssm, const mtfb_est_params *ep, i
 		c->d_corners_in, c->stream));
 	++c->launches;
 	// GridTracker::resetTrackers(reinit = true): every cell re-initialised on the current frame at its new region
+	c->all_parallelograms = true;                        // the cells are axis-aligned boxes
 	CUDA_TRY(launch_init(c->prm, c->threads, c->b, c->d_corners_in, c->d_mi_tab, c->stream));
 	++c->launches;
 	{ mtfb_status st1 = mark_frame_read(c); if(st1 != MTFB_OK) return st1; }

@@ -101,6 +101,20 @@ int main(int argc, char **argv){
 			for(int i = 0; i < P; ++i) if(m_dev[i] != m_host[i]){ printf("ESTMASK %d\n", i); }
 			for(int i = 0; i < P; ++i) printf("ESTPT %.9g %.9g %.9g %.9g\n", prev[2 * i], prev[2 * i + 1], curr[2 * i], curr[2 * i + 1]);
 		}
+		// (5) mtf::b200::GridTracker: a 4 x 4 grid of 12 x 12 ESM + NCC + Affine cells under a Homography, driven like any TrackerBase
+		if(argc > 7 && !strcmp(argv[7], "raw")){
+			const mtfb_est_params ep = mtf::b200::Batch::estParams(MTFB_EST_RANSAC, 2.0, 4, true, 2000, 300, 0.995, 10, 5);
+			mtf::b200::GridTracker grid("esm", "ncc", "6", 4, 4, 20, 22, 12, 12, "8", ep);
+			cv::Mat c(2, 4, CV_64FC1);
+			const double reg[8] = { 90.0, 300, 305, 85, 80, 84, 290, 296 };
+			for(int k = 0; k < 8; ++k) c.at<double>(k / 4, k % 4) = reg[k];
+			load(0); grid.initialize(img, c);
+			for(int t = 1; t < n; ++t){
+				load(t); grid.update(img);
+				const cv::Mat &r = grid.getRegion();
+				for(int k = 0; k < 8; ++k) printf("GRID %d %.17g\n", t, r.at<double>(k / 4, k % 4));
+			}
+		}
 		// error contract: a bad corner matrix is an InvalidArgument exception, not a crash
 		try{ cv::Mat bad(3, 4, CV_64FC1); single[0]->initialize(bad); printf("NOEXC\n"); }
 		catch(const mtf::utils::Exception &e){ printf("EXC %s\n", e.type()); }

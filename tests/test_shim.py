@@ -75,6 +75,20 @@ def test_shim_drives_the_tracker(tmp_path, seq384, sm, am, ssm, res):
     pts = np.array([[float(x) for x in l.split()[1:]] for l in out if l.startswith("ESTPT ")], dtype=np.float32)
     orc = O.estimate_warp("homography", pts[:, :2], pts[:, 2:], O.make_est_params("ransac", seed=99))
     assert orc["ok"] and np.allclose(su[:, 0], orc["state_update"], rtol=1e-5, atol=1e-6)
+    # mtf::b200::GridTracker (cells + estimate + region + layout + re-initialisation behind the TrackerBase interface) == the Python
+    # GridTracker on the same inputs (its first cell layout is NumPy's, the shim's the device's: 1e-9 px)
+    from mtf_b200 import grid
+    gl = np.array([[int(l.split()[1]), float(l.split()[2])] for l in out if l.startswith("GRID ")])
+    gt = grid.GridTracker(api.make_params("ncc", "affine", "esm", n_patches=16, resx=12, resy=12, hess_type=2), grid_size_x=4, grid_size_y=4,
+                          patch_size_x=20, patch_size_y=22, reset_at_each_frame=1, ssm="homography",
+                          est_params=api.make_est_params("ransac", ransac_reproj_thresh=2.0), seed=5)
+    gt.setImage(frames[0]); gt.initialize(np.array([[90.0, 300, 305, 85], [80, 84, 290, 296]]))
+    for t in (1, 2):
+        gt.setImage(frames[t])
+        want = gt.update()
+        got_t = gl[gl[:, 0] == t][:, 1].reshape(2, 4)
+        assert np.abs(got_t - want).max() <= 1e-7
+    gt.close()
     if ssm == "8":
         # mtf::b200::PFTracker == the Python binding's PFTracker with the same seed (device generator: deterministic)
         pfc = np.array([float(l.split()[1]) for l in out if l.startswith("PF ")]).reshape(2, 4)
