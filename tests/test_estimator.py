@@ -211,6 +211,27 @@ def test_grid_host_pieces_against_the_oracles():
     assert np.allclose(c.T, apply(W, src.T))
 
 
+def test_oracle_grid_forward_backward():
+    """the oracle's GridTracker with fb_err_thresh > 0 (GridTracker.cc:292-343), CPU only: a generous threshold keeps every cell and
+    gives the region of the plain grid; a tiny one rejects nearly all of them and re-admits the first n_model_pts in tracker order"""
+    from mtf_b200 import synth
+    frames, _ = synth.make_sequence(3, 384, 384)
+    region = np.array([[90.0, 300, 305, 85], [80, 84, 290, 296]])
+    cell = O.make_params("ssd", "homography", "fclk", grad_mode=1, resx=12, resy=12, max_iters=8)
+    common_kw = dict(reset_at_each_frame=0, ssm="homography", est_params=O.make_est_params("ransac", ransac_reproj_thresh=2.0), seed=31)
+    outs = {}
+    for name, kw in (("plain", {}), ("loose", dict(fb_err_thresh=100.0)), ("tight", dict(fb_err_thresh=1e-9))):
+        og = O.OracleGrid(cell, 4, 4, 24, 24, **common_kw, **kw)
+        og.set_image(frames[0]); og.initialize(region)
+        og.set_image(frames[1]); c = og.update()
+        outs[name] = (c, og)
+    assert np.abs(outs["loose"][0] - outs["plain"][0]).max() < 1e-9 and outs["loose"][1].fb_err_mask.all()
+    tight = outs["tight"][1]
+    n_model = tight.est_params.n_model_pts
+    assert int(tight.fb_err_mask.sum()) >= n_model and list(tight.last["order"][:n_model]) == sorted(tight.last["order"][:n_model])
+    assert np.isfinite(outs["tight"][0]).all()
+
+
 # ------------------------------------------------------------------------------------------------------------------- GPU
 def _ctx():
     from mtf_b200 import api

@@ -68,3 +68,36 @@ def test_sharded_tracker_gloo(world, n_total):
     assert all(ok for _, ok, _, _ in res)
     spans = sorted((lo, hi) for _, _, lo, hi in res)
     assert spans[0][0] == 0 and spans[-1][1] == n_total
+
+
+def _handle_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h = np.full(64, rank + 1, dtype=np.uint8); h[0] = 200 + rank
+        out = sharding.exchange_peer_handles(h)
+        q.put((rank, out.shape, out[:, 0].tolist(), out[:, 1].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_handles_travel_in_rank_order():
+    """the 64-byte IPC handles of mtfb_peer_export are all-gathered by whatever backend the group has (here gloo, two and three
+    ranks): row r of the result is rank r's handle on every rank -- what mtfb_peer_attach expects"""
+    import torch.multiprocessing as mp
+    for world in (2, 3):
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_handle_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        for rank, shape, first, second in res:
+            assert shape == (world, 64)
+            assert first == [200 + r for r in range(world)] and second == [r + 1 for r in range(world)]
